@@ -1,0 +1,60 @@
+"""Batched steer -- mirror of motion_planning/baseline/batch_tsa.py:191-231.
+
+``steer`` keeps the reference's host loop (per-step batched CUDA ops replace its per-row pybullet loops,
+arm_dynamics.py:274,497 and batch_tsa.py:225); ``steer_fused`` runs all rows and all steps in one launch.
+"""
+import time
+
+import numpy as np
+import torch
+
+from .tsa import _rollout
+
+
+@torch.no_grad()
+def steer(u, dynamics_model, sample_states, nearests, RRT_step=10, device="cpu"):
+    """batch_tsa.py:191-231 -> (x_last (B,n), no_collisions [bool]*B, time_dict, xs_list)."""
+    time_dict = {"complete_sample": 0., "cl_dynamics": 0.}
+    t0 = time.time()
+    B = len(sample_states)
+    no_collisions = [True for _ in range(B)]
+    xs_list = [[] for _ in range(B)]
+    controller_update_freq = dynamics_model.controller_dt // dynamics_model.dt
+    dynamics_model.set_intermediate_goals(np.asarray(sample_states))
+    x_current = dynamics_model.complete_sample_with_observations(
+        torch.tensor(np.asarray(nearests), device=device, dtype=torch.float32), len(nearests))
+    time_dict["complete_sample"] += (time.time() - t0) / B
+    for tstep in range(RRT_step):
+        if tstep % controller_update_freq == 0:
+            u_current = u(x_current)
+            if isinstance(u_current, tuple):
+                u_current, u_time_dict = u_current
+            else:
+                u_time_dict = {}
+            for key in u_time_dict.keys():
+                time_dict[key] = time_dict.get(key, 0.) + u_time_dict[key] / B
+        t1 = time.time()
+        x_current = dynamics_model.closed_loop_dynamics(
+            x_current, u_current, update_observation=((tstep + 1) % controller_update_freq == 0))
+        time_dict["cl_dynamics"] += (time.time() - t1) / B
+        unsafe = dynamics_model.unsafe_mask(x_current).cpu().numpy()  # one launch instead of B (batch_tsa.py:225)
+        x_np = x_current.cpu().numpy()
+        for i in range(B):
+            stuck = len(xs_list[i]) > 10 and np.linalg.norm(xs_list[i][-1] - xs_list[i][-10]) < 3e-2
+            no_collisions[i] = no_collisions[i] and not stuck and not bool(unsafe[i])
+            if no_collisions[i]:
+                xs_list[i].append(x_np[i])
+        if True not in no_collisions:
+            break
+    return x_current.cpu().numpy()[:, :dynamics_model.q_dims], no_collisions, time_dict, xs_list
+
+
+@torch.no_grad()
+def steer_fused(controller, dynamics_model, sample_states, nearests, RRT_step=10, want_traj=False):
+    """All rows x all steps in one launch (no stuck test, like the timed closed-loop rollouts of BASELINE
+    config 4) -> (q_final (B,n) tensor, alive bool (B,), steps_done (B,), traj or None)."""
+    dm = dynamics_model
+    dm.set_intermediate_goals(np.asarray(sample_states))
+    q0 = torch.as_tensor(np.asarray(nearests), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
+    qf, alive, done, traj = _rollout(controller, dm, q0, RRT_step, want_traj=want_traj)
+    return qf, alive.bool(), done, (traj if want_traj else None)

@@ -1,0 +1,106 @@
+"""steer / edge_checking -- mirror of motion_planning/baseline/tsa.py:217-286.
+
+Two flavours of each:
+  * ``steer`` / ``edge_checking``: the reference's host loops verbatim (same signature, same return values),
+    running on this package's dynamics_model / controller, i.e. every call inside the loop is a CUDA op;
+  * ``steer_fused`` / ``edge_checking_batch``: the whole loop in ONE launch (cbfrrt::rollout /
+    cbfrrt::edge_validity) with identical semantics -- what the planners should call.
+Tree growth, nearest-neighbour search and BIT* queues stay host Python.
+"""
+import time
+
+import numpy as np
+import torch
+
+from ... import ops
+
+
+@torch.no_grad()
+def steer(u, dynamics_model, new_state, nearest, RRT_step=10, device="cpu"):
+    """tsa.py:217-269, unchanged control flow -> (x_last, no_collision, time_dict, x_list)."""
+    time_dict = {"complete_sample": 0, "cl_dynamics": 0, "misc": 0, "collision_checking": 0}
+    t0 = time.time()
+    no_collision = True
+    x_list = [nearest]
+    controller_update_freq = dynamics_model.controller_dt // dynamics_model.dt
+    dynamics_model.set_intermediate_goals(new_state)
+    x_current = dynamics_model.complete_sample_with_observations(
+        torch.tensor(nearest, device=device, dtype=torch.float32).unsqueeze(0), 1)
+    time_dict["complete_sample"] += (time.time() - t0)
+    for tstep in range(RRT_step):
+        if tstep % controller_update_freq == 0:
+            tt0 = time.time()
+            u_current = u(x_current)
+            if isinstance(u_current, tuple):
+                u_current, u_time_dict = u_current
+            else:
+                u_time_dict = {"u": time.time() - tt0}
+            for key in u_time_dict.keys():
+                time_dict[key] = time_dict.get(key, 0) + u_time_dict[key]
+        x_current, tt_list = dynamics_model.closed_loop_dynamics(
+            x_current, u_current, update_observation=((tstep + 1) % controller_update_freq == 0), return_time=True)
+        time_dict["cl_dynamics"] += tt_list[0]
+        time_dict["complete_sample"] += tt_list[1]
+        tt1 = time.time()
+        if dynamics_model.unsafe_mask(x_current):
+            no_collision = False
+            break
+        tt2 = time.time()
+        x_list.append(x_current.cpu().squeeze().numpy()[:dynamics_model.q_dims])
+        if tstep > 10 and np.linalg.norm(x_list[-1] - x_list[-10]) < 1e-1:  # stuck
+            break
+        time_dict["collision_checking"] += (tt2 - tt1)
+        time_dict["misc"] += (time.time() - tt2)
+    return x_list[-1], no_collision, time_dict, x_list
+
+
+@torch.no_grad()
+def steer_fused(controller, dynamics_model, new_state, nearest, RRT_step=10, device="cpu"):
+    """Same contract as ``steer(controller.u, ...)`` in one kernel launch (cbfrrt::rollout)."""
+    t0 = time.time()
+    dm = dynamics_model
+    dm.set_intermediate_goals(np.asarray(new_state))
+    q0 = torch.as_tensor(np.asarray(nearest), dtype=torch.float32).reshape(1, -1).to(dm.device)
+    qf, alive, done, traj = _rollout(controller, dm, q0, RRT_step, stuck=(9, 10, 0.1), want_traj=True)
+    k = int(done.item())
+    x_list = [nearest] + [row for row in traj[0, :k].cpu().numpy()]
+    time_dict = {"complete_sample": 0, "cl_dynamics": 0, "misc": 0, "collision_checking": 0,
+                 "fused_rollout": time.time() - t0}
+    return x_list[-1], bool(alive.item()), time_dict, x_list
+
+
+def _rollout(controller, dm, q0, steps, stuck=(0, 10, 0.1), want_traj=False):
+    b, s, fl = dm.env.scene
+    lo, hi = controller._limits()
+    ctrl_every = int(dm.controller_dt // dm.dt)
+    return ops.rollout(q0, dm.goal_tensor(dm.device), int(steps), ctrl_every, float(dm.dt), int(stuck[0]),
+                       int(stuck[1]), float(stuck[2]), bool(want_traj), b, s, fl, controller._weights(),
+                       dm.K.to(dm.device, torch.float32), lo, hi, float(controller.clf_lambda),
+                       float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard),
+                       dm.robot.robot_id, controller.h_hidden_size, controller.h_hidden_layers)
+
+
+def edge_checking(state, new_state, dynamics_model, eps):
+    """tsa.py:272-286, unchanged: K+1 single-state safe_mask calls with early exit."""
+    assert state.size == new_state.size
+    if not dynamics_model.safe_mask(torch.Tensor(new_state).unsqueeze(0)):
+        return False
+    disp = new_state - state
+    d = np.linalg.norm(state - new_state)
+    K = int(d / eps)
+    for k in range(0, K):
+        c = state + k * 1. / K * disp
+        if not dynamics_model.safe_mask(torch.Tensor(c).unsqueeze(0)):
+            return False
+    return True
+
+
+def edge_checking_batch(states, new_states, dynamics_model, n_interp):
+    """E edges x (n_interp + 1) points in one launch (cbfrrt::edge_validity) -> (valid bool[E], first_bad i32[E])."""
+    dm = dynamics_model
+    b, s, fl = dm.env.scene
+    qf = torch.as_tensor(np.asarray(states), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
+    qt = torch.as_tensor(np.asarray(new_states), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
+    valid, first_bad = ops.edge_validity(qf, qt, int(n_interp), b, s, fl, float(dm.dis_threshold), float(dm.thr_hard),
+                                         dm.robot.robot_id)
+    return valid.bool(), first_bad

@@ -1,0 +1,8 @@
+"""Mirror of neural_cbf/controllers/__init__.py (inference classes on the hot path)."""
+from .controller import Controller
+from .clf_controller import CLFController
+from .cbf_controller import CBFController
+from .neural_obs_cbf_controller import NeuralObsCBFController
+from .neural_mindis_cbf_controller import NeuralMindisCBFController
+
+__all__ = ["Controller", "CLFController", "CBFController", "NeuralObsCBFController", "NeuralMindisCBFController"]

@@ -1,0 +1,108 @@
+"""CLFController -- mirror of neural_cbf/controllers/clf_controller.py:29-535 (inference path).
+
+The reference builds a CvxpyLayer (:82-139) and solves one SCS conic program per row (:354-404).  Here the same
+QP     min ||u - u_ref||^2 + p * sum r_i   s.t.  Lf_i + Lg_i u + lambda V - r_i <= 0,  r_i >= 0,  lo <= u <= hi
+is solved exactly (KKT closed form) for the whole batch by cbfrrt::qp.  Only n_scenarios == 1 is on the hot
+path of every shipped entry point; more scenarios raise NotImplementedError.
+"""
+import time
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from ... import ops
+from .controller import Controller
+
+
+class CLFController(Controller):
+    def __init__(self, dynamics_model, scenarios, experiment_suite=None, clf_lambda: float = 1.0,
+                 clf_relaxation_penalty: float = 50.0, controller_period: float = 0.01, **kwargs):
+        super(CLFController, self).__init__(dynamics_model=dynamics_model, experiment_suite=experiment_suite,
+                                            controller_period=controller_period)
+        self.scenarios = scenarios
+        self.n_scenarios = len(scenarios)
+        self.experiment_suite = experiment_suite
+        self.clf_lambda = clf_lambda
+        if "safe_level" in kwargs:
+            self.safe_level = kwargs["safe_level"]
+            self.unsafe_level = kwargs["unsafe_level"]
+        self.clf_relaxation_penalty = clf_relaxation_penalty
+
+    @property
+    def device(self):
+        return self.dynamics_model.device
+
+    def V(self, x: torch.Tensor) -> torch.Tensor:
+        V, _ = self.V_with_jacobian(x)
+        return V
+
+    def V_with_jacobian(self, x: torch.Tensor, data_jacobian: tuple = ()):
+        """clf_controller.py:146-167: V = 0.5 x^T P x, JV = P x.  (3-tuple like the neural subclasses so that
+        V_with_lie_derivatives can call either.)"""
+        n = self.dynamics_model.n_dims
+        P = self.dynamics_model.P.type_as(x).reshape(1, n, n)
+        V = 0.5 * F.bilinear(x, x, P).squeeze().reshape(x.shape[0])
+        JV = F.linear(x, P.reshape(n, n)).reshape(x.shape[0], 1, n)
+        return V, JV, {}
+
+    def V_with_lie_derivatives(self, x: torch.Tensor, data_jacobian: tuple = (), scenarios=None):
+        """clf_controller.py:169-218 -> (V, Lf_V (bs,S,1), Lg_V (bs,S,n), t_dict)"""
+        t_dict = {}
+        t0 = time.time()
+        if scenarios is None:
+            scenarios = self.scenarios
+        n_scenarios = len(scenarios)
+        V, gradV, jacob_tdict = self.V_with_jacobian(x, data_jacobian=data_jacobian)
+        t_dict.update(jacob_tdict)
+        t_dict["V_w_Jacobian"] = time.time() - t0
+        t1 = time.time()
+        bs = x.shape[0]
+        Lf_V = torch.zeros(bs, n_scenarios, 1).type_as(gradV)
+        Lg_V = torch.zeros(bs, n_scenarios, self.dynamics_model.n_controls).type_as(gradV)
+        for i in range(n_scenarios):
+            f, g = self.dynamics_model.control_affine_dynamics(x[:, :self.dynamics_model.n_dims], params=scenarios[i])
+            Lf_V[:, i, :] = torch.bmm(gradV, f.type_as(gradV).to(gradV.device)).squeeze(1)
+            Lg_V[:, i, :] = torch.bmm(gradV, g.type_as(gradV).to(gradV.device)).squeeze(1)
+        t_dict["lie_derivative"] = time.time() - t1
+        return V, Lf_V, Lg_V, t_dict
+
+    def u_reference(self, x: torch.Tensor) -> torch.Tensor:
+        return self.dynamics_model.u_nominal(x)
+
+    def _solve_CLF_QP_exact(self, x, u_ref, V, Lf_V, Lg_V, relaxation_penalty: float):
+        """Batched exact solve on the GPU (replaces _solve_CLF_QP_cvxpylayers, clf_controller.py:354-404)."""
+        if self.n_scenarios != 1:
+            raise NotImplementedError("multi-scenario CLF-QP (n_scenarios > 1) is a 'next' row (SURVEY.md 8f)")
+        dev = self.device
+        upper, lower = self.dynamics_model.control_limits
+        a = Lg_V[:, 0, :].to(dev, torch.float32)
+        c = (Lf_V[:, 0, 0] + self.clf_lambda * V.reshape(-1)).to(dev, torch.float32)
+        u, r = ops.qp(a, c, u_ref.to(dev, torch.float32), lower.to(dev, torch.float32), upper.to(dev, torch.float32),
+                      float(relaxation_penalty))
+        return u.to(x.device).type_as(x), r.reshape(-1, 1).to(x.device).type_as(x)
+
+    def solve_CLF_QP(self, x, relaxation_penalty: Optional[float] = None, u_ref: Optional[torch.Tensor] = None,
+                     requires_grad: bool = False, strict_solution: bool = False) -> Tuple[tuple, dict]:
+        """clf_controller.py:461-528 -> ((u, r), t_dict)"""
+        t_dict = {}
+        a = time.time()
+        V, Lf_V, Lg_V, lie_t_dict = self.V_with_lie_derivatives(x)
+        t_dict.update(lie_t_dict)
+        t_dict["nn_forward"] = time.time() - a
+        b = time.time()
+        if u_ref is not None:
+            assert u_ref.shape[0] == x.shape[0], f"u_ref must have {x.shape[0]} rows, but got {u_ref.shape[0]}"
+            assert u_ref.shape[1] == self.dynamics_model.n_controls
+        else:
+            u_ref = self.u_reference(x)
+        if relaxation_penalty is None:
+            relaxation_penalty = self.clf_relaxation_penalty
+        sol = self._solve_CLF_QP_exact(x, u_ref, V, Lf_V, Lg_V, relaxation_penalty)
+        t_dict["QP"] = time.time() - b
+        return sol, t_dict
+
+    def u(self, x):
+        """clf_controller.py:530-535 -> (u, t_dict)"""
+        u, t_dict = self.solve_CLF_QP(x)
+        return u[0], t_dict

@@ -1,0 +1,344 @@
+"""PyTorch custom ops (namespace ``cbfrrt::``) over the C-ABI of libcbfrrt.so.
+
+CUDA-only registration: there is no CPU kernel, no Triton path and no dispatch table -- calling an op with CPU
+tensors raises NotImplementedError from the dispatcher.  PyTorch is plumbing here (device memory, current
+stream); every op is one call into include/cbfrrt.h with raw device pointers.
+
+Reference call sites each op replaces are listed in include/cbfrrt.h.
+"""
+import ctypes as C
+from typing import Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import lib, check, Scene, CbfNet, FilterParams, RolloutParams
+
+ROBOT_ID = _lib.ROBOT_ID
+ROBOT_N = {0: 7, 1: 4}
+ROBOT_LINKS = {0: 12, 1: 4}
+
+
+# ----------------------------------------------------------------------------- helpers
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
+
+
+def _rows(q: Tensor, n: int):
+    """float32 rows with unit inner stride; returns (tensor, row_stride) without copying views like x[:, :n]."""
+    if q.dtype != torch.float32:
+        q = q.float()
+    if q.dim() != 2 or q.shape[1] < n:
+        raise ValueError(f"expected a (B, >={n}) tensor, got {tuple(q.shape)}")
+    if q.stride(1) != 1 or (q.shape[0] > 1 and q.stride(0) < n):
+        q = q.contiguous()
+    return q, (q.stride(0) if q.shape[0] > 1 else max(q.shape[1], n))
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t.to(dtype=torch.float32).contiguous()
+
+
+def _scene(boxes8: Tensor, spheres: Tensor, floor: int) -> Scene:
+    if boxes8.numel() and (boxes8.dim() != 2 or boxes8.shape[1] != 8):
+        raise ValueError("boxes must be packed as (Ob, 8): cx cy cz hx hy hz 0 0 (use pack_scene)")
+    if spheres.numel() and (spheres.dim() != 2 or spheres.shape[1] != 4):
+        raise ValueError("spheres must be (Os, 4): cx cy cz r")
+    return Scene(int(boxes8.shape[0]) if boxes8.numel() else 0, int(spheres.shape[0]) if spheres.numel() else 0,
+                 int(bool(floor)), 0, _ptr(boxes8).value, _ptr(spheres).value)
+
+
+def pack_scene(positions, sizes, spheres=None, device="cuda"):
+    """(positions (O,3), half-extents (O,3)) as held by ArmEnv.obs_positions / obs_sizes (arm_env.py:154-182)
+    -> device tensors in the library's layout: boxes (O,8), spheres (P,4)."""
+    positions = np.asarray(positions, dtype=np.float32).reshape(-1, 3)
+    sizes = np.asarray(sizes, dtype=np.float32).reshape(-1, 3)
+    b8 = np.zeros((positions.shape[0], 8), np.float32)
+    b8[:, :3] = positions
+    b8[:, 3:6] = sizes
+    sp = np.zeros((0, 4), np.float32) if spheres is None else np.asarray(spheres, np.float32).reshape(-1, 4)
+    return torch.from_numpy(b8).to(device), torch.from_numpy(np.ascontiguousarray(sp)).to(device)
+
+
+def packed_weight_count(n: int, hidden: int, layers: int) -> int:
+    in_pad = (n + 1 + 3) & ~3
+    return hidden * in_pad + hidden + layers * (hidden * hidden + hidden) + hidden + 4
+
+
+def pack_weights(state_dict, n: int, hidden: int, layers: int, device="cuda") -> Tensor:
+    """h_nn state_dict (keys input_linear / layer_{i}_linear / output_linear, with or without the ``h_nn.``
+    prefix; neural_mindis_cbf_controller.py:44-53) -> packed float32 buffer described in include/cbfrrt.h."""
+    def get(name):
+        for k in (name, "h_nn." + name):
+            if k in state_dict:
+                v = state_dict[k]
+                return v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        raise KeyError(name)
+
+    in_pad = (n + 1 + 3) & ~3
+    out = np.zeros(packed_weight_count(n, hidden, layers), np.float32)
+    w_in = np.zeros((hidden, in_pad), np.float32)
+    w_in[:, :n + 1] = get("input_linear.weight")
+    o = 0
+    out[o:o + hidden * in_pad] = w_in.ravel(); o += hidden * in_pad
+    out[o:o + hidden] = get("input_linear.bias"); o += hidden
+    for i in range(layers):
+        out[o:o + hidden * hidden] = get(f"layer_{i}_linear.weight").ravel(); o += hidden * hidden
+        out[o:o + hidden] = get(f"layer_{i}_linear.bias"); o += hidden
+    out[o:o + hidden] = get("output_linear.weight").ravel(); o += hidden
+    out[o] = float(np.asarray(get("output_linear.bias")).ravel()[0])
+    return torch.from_numpy(out).to(device)
+
+
+def _net_params(n, W, K, lo, hi, goal, B, lam, penalty, hidden, layers, u_ref=None):
+    W, K, lo, hi, goal = _f32c(W), _f32c(K), _f32c(lo), _f32c(hi), _f32c(goal).reshape(-1, n)
+    if u_ref is not None and u_ref.numel() > 0:
+        u_ref = _f32c(u_ref)
+        if tuple(u_ref.shape) != (B, n):
+            raise ValueError(f"u_ref must be ({B}, {n})")
+    else:
+        u_ref = None
+    if W.numel() != packed_weight_count(n, hidden, layers):
+        raise ValueError(f"packed weights have {W.numel()} floats, expected {packed_weight_count(n, hidden, layers)}")
+    if K.numel() != n * n or lo.numel() != n or hi.numel() != n:
+        raise ValueError("K must be (n,n); control limits (n,)")
+    if goal.shape[0] not in (1, B):
+        raise ValueError(f"goal must have 1 or {B} rows, got {goal.shape[0]}")
+    net = CbfNet(n + 1, hidden, layers, 0, _ptr(W).value)
+    fp = FilterParams(_ptr(goal).value, goal.shape[0], _ptr(K).value, _ptr(lo).value, _ptr(hi).value, float(lam),
+                      float(penalty), _ptr(u_ref).value if u_ref is not None else None)
+    return net, fp, (W, K, lo, hi, goal, u_ref)  # keep tensors alive until the call returns
+
+
+# ----------------------------------------------------------------------------- ops
+@torch.library.custom_op("cbfrrt::fk", mutates_args=(), device_types="cuda")
+def fk(q: Tensor, robot_id: int) -> Tuple[Tensor, Tensor]:
+    n, L = ROBOT_N[robot_id], ROBOT_LINKS[robot_id]
+    q, qs = _rows(q, n)
+    B = q.shape[0]
+    pos = torch.empty((B, L, 3), dtype=torch.float32, device=q.device)
+    rot = torch.empty((B, L, 3, 3), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(lib.cbfrrt_fk(robot_id, _ptr(q), qs, B, _ptr(pos), _ptr(rot), _stream()), "cbfrrt_fk")
+    return pos, rot
+
+
+@torch.library.custom_op("cbfrrt::collide", mutates_args=(), device_types="cuda")
+def collide(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: float, thr_hard: float,
+            robot_id: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> safe u8[B], unsafe u8[B], datax f32[B,2n+1], arg_link i32[B], arg_obs i32[B], mins f32[B,3]"""
+    n = ROBOT_N[robot_id]
+    q, qs = _rows(q, n)
+    B, dev = q.shape[0], q.device
+    safe = torch.empty(B, dtype=torch.uint8, device=dev)
+    unsafe = torch.empty(B, dtype=torch.uint8, device=dev)
+    datax = torch.empty((B, 2 * n + 1), dtype=torch.float32, device=dev)
+    arg_link = torch.empty(B, dtype=torch.int32, device=dev)
+    arg_obs = torch.empty(B, dtype=torch.int32, device=dev)
+    mins = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    sc = _scene(boxes, spheres, floor)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_collide(robot_id, C.byref(sc), _ptr(q), qs, B, thr_soft, thr_hard, _ptr(safe), _ptr(unsafe),
+                                 _ptr(datax), _ptr(arg_link), _ptr(arg_obs), _ptr(mins), _stream()), "cbfrrt_collide")
+    return safe, unsafe, datax, arg_link, arg_obs, mins
+
+
+@torch.library.custom_op("cbfrrt::observe", mutates_args=(), device_types="cuda")
+def observe(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: float, thr_hard: float,
+            robot_id: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> safe u8[B], unsafe u8[B], datax f32[B,2n+1]   (complete_sample_with_observations + masks)"""
+    n = ROBOT_N[robot_id]
+    q, qs = _rows(q, n)
+    B, dev = q.shape[0], q.device
+    safe = torch.empty(B, dtype=torch.uint8, device=dev)
+    unsafe = torch.empty(B, dtype=torch.uint8, device=dev)
+    datax = torch.empty((B, 2 * n + 1), dtype=torch.float32, device=dev)
+    sc = _scene(boxes, spheres, floor)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_collide(robot_id, C.byref(sc), _ptr(q), qs, B, thr_soft, thr_hard, _ptr(safe), _ptr(unsafe),
+                                 _ptr(datax), None, None, None, _stream()), "cbfrrt_collide")
+    return safe, unsafe, datax
+
+
+@torch.library.custom_op("cbfrrt::masks", mutates_args=(), device_types="cuda")
+def masks(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: float, thr_hard: float,
+          robot_id: int) -> Tuple[Tensor, Tensor]:
+    """-> safe u8[B], unsafe u8[B]   (safe_mask / unsafe_mask only: no arg-min, no gradient)"""
+    n = ROBOT_N[robot_id]
+    q, qs = _rows(q, n)
+    B, dev = q.shape[0], q.device
+    safe = torch.empty(B, dtype=torch.uint8, device=dev)
+    unsafe = torch.empty(B, dtype=torch.uint8, device=dev)
+    sc = _scene(boxes, spheres, floor)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_collide(robot_id, C.byref(sc), _ptr(q), qs, B, thr_soft, thr_hard, _ptr(safe), _ptr(unsafe),
+                                 None, None, None, None, _stream()), "cbfrrt_collide")
+    return safe, unsafe
+
+
+@torch.library.custom_op("cbfrrt::cbf_filter", mutates_args=(), device_types="cuda")
+def cbf_filter(datax: Tensor, goal: Tensor, weights: Tensor, K: Tensor, u_lo: Tensor, u_hi: Tensor, lam: float,
+               penalty: float, hidden: int, layers: int, u_ref: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """datax f32[B,2n+1] -> h f32[B], J f32[B,n], u f32[B,n], r f32[B].  u_ref: (B,n) caller-supplied reference
+    control, or an empty tensor to use the nominal controller -K(q-goal)."""
+    datax = _f32c(datax)
+    if datax.dim() != 2 or datax.shape[1] % 2 != 1:
+        raise ValueError("datax must be (B, 2n+1)")
+    B, n, dev = datax.shape[0], (datax.shape[1] - 1) // 2, datax.device
+    net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers, u_ref)
+    h = torch.empty(B, dtype=torch.float32, device=dev)
+    J = torch.empty((B, n), dtype=torch.float32, device=dev)
+    u = torch.empty((B, n), dtype=torch.float32, device=dev)
+    r = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_cbf_filter(n, C.byref(net), _ptr(datax), B, C.byref(fp), _ptr(h), _ptr(J), _ptr(u), _ptr(r),
+                                    _stream()), "cbfrrt_cbf_filter")
+    del keep
+    return h, J, u, r
+
+
+@torch.library.custom_op("cbfrrt::qp", mutates_args=(), device_types="cuda")
+def qp(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty: float) -> Tuple[Tensor, Tensor]:
+    """a = Lg_V f32[B,n], c = Lf_V + lam*V f32[B], u_ref f32[B,n] -> u f32[B,n], r f32[B]"""
+    a, c, u_ref, u_lo, u_hi = _f32c(a), _f32c(c).reshape(-1), _f32c(u_ref), _f32c(u_lo), _f32c(u_hi)
+    B, n = a.shape
+    if u_ref.shape != a.shape or c.numel() != B or u_lo.numel() != n or u_hi.numel() != n:
+        raise ValueError("qp: inconsistent shapes")
+    u = torch.empty((B, n), dtype=torch.float32, device=a.device)
+    r = torch.empty(B, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.cbfrrt_qp(n, _ptr(a), _ptr(c), _ptr(u_ref), B, _ptr(u_lo), _ptr(u_hi), penalty, _ptr(u), _ptr(r),
+                            _stream()), "cbfrrt_qp")
+    return u, r
+
+
+@torch.library.custom_op("cbfrrt::safety_filter", mutates_args=(), device_types="cuda")
+def safety_filter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, weights: Tensor, K: Tensor,
+                  u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float,
+                  robot_id: int, hidden: int, layers: int
+                  ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """fused q -> safe, unsafe, datax, h, J, u, r"""
+    n = ROBOT_N[robot_id]
+    q, qs = _rows(q, n)
+    B, dev = q.shape[0], q.device
+    net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers)
+    sc = _scene(boxes, spheres, floor)
+    safe = torch.empty(B, dtype=torch.uint8, device=dev)
+    unsafe = torch.empty(B, dtype=torch.uint8, device=dev)
+    datax = torch.empty((B, 2 * n + 1), dtype=torch.float32, device=dev)
+    h = torch.empty(B, dtype=torch.float32, device=dev)
+    J = torch.empty((B, n), dtype=torch.float32, device=dev)
+    u = torch.empty((B, n), dtype=torch.float32, device=dev)
+    r = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_safety_filter(robot_id, C.byref(sc), C.byref(net), _ptr(q), qs, B, C.byref(fp), thr_soft,
+                                       thr_hard, _ptr(safe), _ptr(unsafe), _ptr(datax), _ptr(h), _ptr(J), _ptr(u),
+                                       _ptr(r), _stream()), "cbfrrt_safety_filter")
+    del keep
+    return safe, unsafe, datax, h, J, u, r
+
+
+@torch.library.custom_op("cbfrrt::valid_control", mutates_args=(), device_types="cuda")
+def valid_control(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, weights: Tensor, K: Tensor,
+                  u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float,
+                  robot_id: int, hidden: int, layers: int) -> Tuple[Tensor, Tensor]:
+    """fused q -> (valid u8[B], u f32[B,n]): the sweep outputs that are all-gathered across GPUs"""
+    n = ROBOT_N[robot_id]
+    q, qs = _rows(q, n)
+    B, dev = q.shape[0], q.device
+    net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers)
+    sc = _scene(boxes, spheres, floor)
+    safe = torch.empty(B, dtype=torch.uint8, device=dev)
+    u = torch.empty((B, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_safety_filter(robot_id, C.byref(sc), C.byref(net), _ptr(q), qs, B, C.byref(fp), thr_soft,
+                                       thr_hard, _ptr(safe), None, None, None, None, _ptr(u), None, _stream()),
+              "cbfrrt_safety_filter")
+    del keep
+    return safe, u
+
+
+@torch.library.custom_op("cbfrrt::edge_validity", mutates_args=(), device_types="cuda")
+def edge_validity(q_from: Tensor, q_to: Tensor, n_interp: int, boxes: Tensor, spheres: Tensor, floor: int,
+                  thr_soft: float, thr_hard: float, robot_id: int) -> Tuple[Tensor, Tensor]:
+    """-> valid u8[E], first_bad i32[E]"""
+    n = ROBOT_N[robot_id]
+    q_from, q_to = _f32c(q_from), _f32c(q_to)
+    if q_from.shape != q_to.shape or q_from.dim() != 2 or q_from.shape[1] != n:
+        raise ValueError(f"q_from / q_to must both be (E, {n})")
+    E, dev = q_from.shape[0], q_from.device
+    valid = torch.empty(E, dtype=torch.uint8, device=dev)
+    first_bad = torch.empty(E, dtype=torch.int32, device=dev)
+    sc = _scene(boxes, spheres, floor)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_edge_validity(robot_id, C.byref(sc), _ptr(q_from), _ptr(q_to), E, n_interp, thr_soft, thr_hard,
+                                       _ptr(valid), _ptr(first_bad), _stream()), "cbfrrt_edge_validity")
+    return valid, first_bad
+
+
+@torch.library.custom_op("cbfrrt::rollout", mutates_args=(), device_types="cuda")
+def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, stuck_lag: int, stuck_after: int,
+            stuck_eps: float, want_traj: bool, boxes: Tensor, spheres: Tensor, floor: int, weights: Tensor, K: Tensor,
+            u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float, robot_id: int,
+            hidden: int, layers: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """the steer loop in one launch -> q_final f32[T,n], alive u8[T], steps_done i32[T], traj f32[T,steps,n]
+    (traj is (0,) unless want_traj or the stuck test is on)"""
+    n = ROBOT_N[robot_id]
+    q0 = _f32c(q0)
+    if q0.dim() != 2 or q0.shape[1] != n:
+        raise ValueError(f"q0 must be (T, {n})")
+    T, dev = q0.shape[0], q0.device
+    net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, T, lam, penalty, hidden, layers)
+    sc = _scene(boxes, spheres, floor)
+    rp = RolloutParams(steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps)
+    qf = torch.empty((T, n), dtype=torch.float32, device=dev)
+    alive = torch.empty(T, dtype=torch.uint8, device=dev)
+    done = torch.empty(T, dtype=torch.int32, device=dev)
+    traj = (torch.zeros((T, steps, n), dtype=torch.float32, device=dev) if (want_traj or stuck_lag > 0)
+            else torch.empty(0, dtype=torch.float32, device=dev))
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_rollout(robot_id, C.byref(sc), C.byref(net), _ptr(q0), T, C.byref(fp), C.byref(rp), thr_soft,
+                                 thr_hard, _ptr(qf), _ptr(alive), _ptr(done), _ptr(traj) if traj.numel() else None,
+                                 _stream()), "cbfrrt_rollout")
+    del keep
+    return qf, alive, done, traj
+
+
+def sample_states(B: int, seed: int, start_row: int, robot_id: int, device="cuda") -> Tensor:
+    """counter-based uniform sampler over the joint limits; row g depends only on (seed, g)"""
+    n = ROBOT_N[robot_id]
+    q = torch.empty((B, n), dtype=torch.float32, device=device)
+    with torch.cuda.device(q.device):
+        check(lib.cbfrrt_sample_states(robot_id, seed & 0xFFFFFFFF, start_row, B, _ptr(q), _stream()),
+              "cbfrrt_sample_states")
+    return q
+
+
+def safety_filter_host(robot: str, q: np.ndarray, boxes6: np.ndarray, spheres: np.ndarray, floor: bool,
+                       weights: np.ndarray, hidden: int, layers: int, goal: np.ndarray, K: np.ndarray, u_lo, u_hi,
+                       lam: float, penalty: float, thr_soft: float, thr_hard: float, out: dict, device: int = 0):
+    """Host-buffer entry point (numpy in / numpy out; include/cbfrrt.h cbfrrt_safety_filter_host).
+    ``out`` maps any of safe, unsafe, datax, h, J, u, r to preallocated (ideally pinned) numpy arrays."""
+    n = ROBOT_N[ROBOT_ID[robot]]
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    q, goal, K, u_lo, u_hi, weights = f(q), f(goal).reshape(-1, n), f(K), f(u_lo), f(u_hi), f(weights)
+    boxes6 = f(boxes6).reshape(-1, 6)
+    spheres = f(spheres).reshape(-1, 4) if spheres is not None else np.zeros((0, 4), np.float32)
+    hs = _lib.HostScene(boxes6.shape[0], spheres.shape[0], int(bool(floor)), 0, boxes6.ctypes.data, spheres.ctypes.data)
+    p = lambda k: C.c_void_p(out[k].ctypes.data) if out.get(k) is not None else None
+    check(lib.cbfrrt_safety_filter_host(device, ROBOT_ID[robot], C.byref(hs), hidden, layers, weights.ctypes.data,
+                                        weights.size, q.ctypes.data, q.shape[0], goal.ctypes.data, goal.shape[0],
+                                        K.ctypes.data, u_lo.ctypes.data, u_hi.ctypes.data, lam, penalty, thr_soft,
+                                        thr_hard, p("safe"), p("unsafe"), p("datax"), p("h"), p("J"), p("u"), p("r")),
+          "cbfrrt_safety_filter_host")
+    return out
+
+
+def launch_count() -> int:
+    return int(lib.cbfrrt_launch_count())

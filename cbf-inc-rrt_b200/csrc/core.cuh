@@ -1,0 +1,445 @@
+// core.cuh -- per-state device code of the CBF-INC-RRT hot path (sm_100a).
+//
+// One thread owns one manipulator state.  The chain is walked once with everything in registers:
+//   FK frame of link l  ->  world centres of that link's spheres  ->  distance sweep over the scene that the CTA
+//   staged in shared memory (TMA bulk copy, see kernels.cu)  ->  running minima  ->  self-collision predicate
+//   ->  arg-min recovery + geometric-Jacobian gradient.
+//
+// DETERMINISTIC-MATH CONTRACT: every value that feeds a boolean or an index is produced by the
+// same sequence of single IEEE binary32 operations as oracle/cbfrrt_oracle.c -- written here with explicit
+// __fadd_rn/__fsub_rn/__fmul_rn/fmaf so that neither -fmad nor instruction selection can re-associate or
+// contract anything.  Two algebraic restructurings are used, both EXACT (bit-identical results):
+//   (1) box sweep without sqrt: for one sphere, sd_j = fl(fl(fl(sqrt(dsq_j)) + mi_j) - r) where at most one of
+//       the two inner terms is non-zero, and correctly rounded sqrt / subtraction are monotone, hence
+//       min_j sd_j = fl(fl(sqrt(min_j dsq_j)) + min(min_j max3(a_j), 0)) - r);
+//   (2) self-collision by squared-distance thresholds: the oracle predicate fl(fl(sqrt(dsq)-ri)-rj) > 0.01f is
+//       monotone in dsq, so it equals dsq > X_ij with X_ij tabulated per sphere pair (robot_tables.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "robot_tables.cuh"
+
+namespace cbfrrt {
+
+// ------------------------------------------------------------------ robot traits over the generated tables
+struct Panda {
+    static constexpr int ID = 0;
+    static constexpr int N = PANDA_N, NLINKS = PANDA_NLINKS, NSPH = PANDA_NSPHERES, NSELFSPH = PANDA_NSELFSPH;
+    static constexpr float LINK0_FLOOR = PANDA_LINK0_FLOOR_DIST;
+    __device__ static constexpr int parent(int l) { return PANDA_PARENT[l]; }
+    __device__ static constexpr int qidx(int l) { return PANDA_QIDX[l]; }
+    __device__ static constexpr float t(int l, int k) { return PANDA_T[l][k]; }
+    __device__ static constexpr float rfix(int l, int k) { return PANDA_R[l][k]; }
+    __device__ static constexpr int sph_begin(int l) { return PANDA_SPH_BEGIN[l + 1]; }
+    __device__ static constexpr int sph_end(int l) { return PANDA_SPH_BEGIN[l + 2]; }
+    __device__ static constexpr float sph(int i, int k) { return PANDA_SPH[i][k]; }
+    __device__ static constexpr int sph_link(int i) { return PANDA_SPH_LINK[i]; }
+    __device__ static constexpr int anc_mask(int l) { return PANDA_ANC_MASK[l]; }
+    __device__ static constexpr int self_i(int p) { return PANDA_SELFSPH_I[p]; }
+    __device__ static constexpr int self_j(int p) { return PANDA_SELFSPH_J[p]; }
+    __device__ static constexpr float self_x(int p) { return PANDA_SELFSPH_X[p]; }
+    __device__ static constexpr float qlo(int j) { return PANDA_QLO[j]; }
+    __device__ static constexpr float qhi(int j) { return PANDA_QHI[j]; }
+};
+struct Magician {
+    static constexpr int ID = 1;
+    static constexpr int N = MAGICIAN_N, NLINKS = MAGICIAN_NLINKS, NSPH = MAGICIAN_NSPHERES,
+                         NSELFSPH = MAGICIAN_NSELFSPH;
+    static constexpr float LINK0_FLOOR = MAGICIAN_LINK0_FLOOR_DIST;
+    __device__ static constexpr int parent(int l) { return MAGICIAN_PARENT[l]; }
+    __device__ static constexpr int qidx(int l) { return MAGICIAN_QIDX[l]; }
+    __device__ static constexpr float t(int l, int k) { return MAGICIAN_T[l][k]; }
+    __device__ static constexpr float rfix(int l, int k) { return MAGICIAN_R[l][k]; }
+    __device__ static constexpr int sph_begin(int l) { return MAGICIAN_SPH_BEGIN[l + 1]; }
+    __device__ static constexpr int sph_end(int l) { return MAGICIAN_SPH_BEGIN[l + 2]; }
+    __device__ static constexpr float sph(int i, int k) { return MAGICIAN_SPH[i][k]; }
+    __device__ static constexpr int sph_link(int i) { return MAGICIAN_SPH_LINK[i]; }
+    __device__ static constexpr int anc_mask(int l) { return MAGICIAN_ANC_MASK[l]; }
+    __device__ static constexpr int self_i(int p) { return MAGICIAN_SELFSPH_I[p]; }
+    __device__ static constexpr int self_j(int p) { return MAGICIAN_SELFSPH_J[p]; }
+    __device__ static constexpr float self_x(int p) { return MAGICIAN_SELFSPH_X[p]; }
+    __device__ static constexpr float qlo(int j) { return MAGICIAN_QLO[j]; }
+    __device__ static constexpr float qhi(int j) { return MAGICIAN_QHI[j]; }
+};
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
+template <int I>
+struct IC {
+    static constexpr int value = I;
+};
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(IC<B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+#define CBF_INF __int_as_float(0x7f800000)
+
+// ------------------------------------------------------------------ contract sincos (oracle: det_sincosf)
+__device__ __forceinline__ void det_sincosf(float x, float& so, float& co) {
+    const float k = rintf(__fmul_rn(x, 0.636619772f));
+    float r = fmaf(-k, 1.57079637050628662109375f, x);
+    r = fmaf(-k, -4.37113900018624283e-8f, r);
+    const float z = __fmul_rn(r, r);
+    float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(z, sp, -1.6666654611e-1f);
+    sp = __fmul_rn(sp, z);
+    const float s = fmaf(sp, r, r);
+    float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(z, cp, 4.166664568298827e-2f);
+    cp = fmaf(z, cp, -0.5f);
+    const float c = fmaf(z, cp, 1.0f);
+    const int n = ((int)k) & 3;
+    const float a = (n & 1) ? c : s;  // sin-slot magnitude
+    const float b = (n & 1) ? s : c;  // cos-slot magnitude
+    so = (n & 2) ? -a : a;            // n: 0 -> s, 1 -> c, 2 -> -s, 3 -> -c
+    co = ((n + 1) & 2) ? -b : b;      // n: 0 -> c, 1 -> -s, 2 -> -c, 3 -> s
+}
+
+// ------------------------------------------------------------------ frames
+struct Frame {
+    float p[3];
+    float R[9];  // row-major
+};
+
+// x*F + acc with F a compile-time table constant: multiplications by 0 / +-1 are dropped.  Dropping them is
+// exact: fmaf(x, 0, acc) == acc, x*(+-1) == +-x and fmaf(x, +-1, 0-product) == +-x for finite x; only the sign
+// of an exact zero can differ from the oracle's general formula, which no comparison can observe.
+template <class RB, int L>
+__device__ __forceinline__ void child_frame(const Frame& par, bool par_is_base, float sq, float cq, Frame& out) {
+    // position: p = fma(Rp[r][2], t2, fma(Rp[r][1], t1, fma(Rp[r][0], t0, pp[r])))
+    constexpr float t0 = RB::t(L, 0), t1 = RB::t(L, 1), t2 = RB::t(L, 2);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float acc = par.p[r];
+        if constexpr (t0 != 0.f) acc = fmaf(par.R[3 * r + 0], t0, acc);
+        if constexpr (t1 != 0.f) acc = fmaf(par.R[3 * r + 1], t1, acc);
+        if constexpr (t2 != 0.f) acc = fmaf(par.R[3 * r + 2], t2, acc);
+        out.p[r] = acc;
+    }
+    // A = Rp * F : A[r][c] = fma(Rp[r][2], F[2][c], fma(Rp[r][1], F[1][c], Rp[r][0]*F[0][c]))
+    float A[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        static_for<0, 3>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr float f0 = RB::rfix(L, c), f1 = RB::rfix(L, 3 + c), f2 = RB::rfix(L, 6 + c);
+            float acc = 0.f;
+            if constexpr (f0 == 1.f) acc = par.R[3 * r + 0];
+            else if constexpr (f0 == -1.f) acc = -par.R[3 * r + 0];
+            else if constexpr (f0 != 0.f) acc = __fmul_rn(par.R[3 * r + 0], f0);
+            if constexpr (f1 != 0.f) {
+                if constexpr (f0 == 0.f && f1 == 1.f) acc = par.R[3 * r + 1];
+                else if constexpr (f0 == 0.f && f1 == -1.f) acc = -par.R[3 * r + 1];
+                else acc = fmaf(par.R[3 * r + 1], f1, acc);
+            }
+            if constexpr (f2 != 0.f) {
+                if constexpr (f0 == 0.f && f1 == 0.f && f2 == 1.f) acc = par.R[3 * r + 2];
+                else if constexpr (f0 == 0.f && f1 == 0.f && f2 == -1.f) acc = -par.R[3 * r + 2];
+                else acc = fmaf(par.R[3 * r + 2], f2, acc);
+            }
+            A[3 * r + c] = acc;
+        });
+    }
+    if constexpr (RB::qidx(L) >= 0) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float a0 = A[3 * r + 0], a1 = A[3 * r + 1];
+            out.R[3 * r + 0] = fmaf(a1, sq, __fmul_rn(a0, cq));
+            out.R[3 * r + 1] = fmaf(a1, cq, -__fmul_rn(a0, sq));
+            out.R[3 * r + 2] = A[3 * r + 2];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out.R[k] = A[k];
+    }
+}
+
+__device__ __forceinline__ Frame identity_frame() {
+    Frame f;
+    f.p[0] = f.p[1] = f.p[2] = 0.f;
+    f.R[0] = 1.f; f.R[1] = 0.f; f.R[2] = 0.f;
+    f.R[3] = 0.f; f.R[4] = 1.f; f.R[5] = 0.f;
+    f.R[6] = 0.f; f.R[7] = 0.f; f.R[8] = 1.f;
+    return f;
+}
+
+// ------------------------------------------------------------------ scene view in shared memory
+struct SceneS {
+    const float4* boxes;    // 2 x float4 per box: (cx cy cz hx) (hy hz 0 0)
+    const float4* spheres;  // (cx cy cz r)
+    int n_boxes, n_spheres, floor;
+};
+
+// exact per-pair formulas (oracle: sd_box / sd_sphere / normal_box / normal_sphere)
+__device__ __forceinline__ float sd_box_exact(float cx, float cy, float cz, float4 b0, float4 b1, float r) {
+    const float dx = __fsub_rn(cx, b0.x), dy = __fsub_rn(cy, b0.y), dz = __fsub_rn(cz, b0.z);
+    const float ax = __fsub_rn(fabsf(dx), b0.w), ay = __fsub_rn(fabsf(dy), b1.x), az = __fsub_rn(fabsf(dz), b1.y);
+    const float qx = fmaxf(ax, 0.f), qy = fmaxf(ay, 0.f), qz = fmaxf(az, 0.f);
+    const float dsq = fmaf(qz, qz, fmaf(qy, qy, __fmul_rn(qx, qx)));
+    const float mi = fminf(fmaxf(ax, fmaxf(ay, az)), 0.f);
+    return __fsub_rn(__fadd_rn(__fsqrt_rn(dsq), mi), r);
+}
+__device__ __forceinline__ float sd_sphere_exact(float cx, float cy, float cz, float4 s, float r) {
+    const float dx = __fsub_rn(cx, s.x), dy = __fsub_rn(cy, s.y), dz = __fsub_rn(cz, s.z);
+    const float dsq = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+    return __fsub_rn(__fsub_rn(__fsqrt_rn(dsq), s.w), r);
+}
+__device__ __forceinline__ void normal_box(float cx, float cy, float cz, float4 b0, float4 b1, float* n) {
+    const float dx = __fsub_rn(cx, b0.x), dy = __fsub_rn(cy, b0.y), dz = __fsub_rn(cz, b0.z);
+    const float ax = __fsub_rn(fabsf(dx), b0.w), ay = __fsub_rn(fabsf(dy), b1.x), az = __fsub_rn(fabsf(dz), b1.y);
+    const float qx = fmaxf(ax, 0.f), qy = fmaxf(ay, 0.f), qz = fmaxf(az, 0.f);
+    const float dsq = fmaf(qz, qz, fmaf(qy, qy, __fmul_rn(qx, qx)));
+    if (dsq > 0.f) {
+        const float d = __fsqrt_rn(dsq);
+        n[0] = __fdiv_rn(copysignf(qx, dx), d);
+        n[1] = __fdiv_rn(copysignf(qy, dy), d);
+        n[2] = __fdiv_rn(copysignf(qz, dz), d);
+    } else {
+        n[0] = n[1] = n[2] = 0.f;
+        if (ax >= ay && ax >= az) n[0] = copysignf(1.f, dx);
+        else if (ay >= az) n[1] = copysignf(1.f, dy);
+        else n[2] = copysignf(1.f, dz);
+    }
+}
+__device__ __forceinline__ void normal_sphere(float cx, float cy, float cz, float4 s, float* n) {
+    const float dx = __fsub_rn(cx, s.x), dy = __fsub_rn(cy, s.y), dz = __fsub_rn(cz, s.z);
+    const float dsq = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+    if (dsq > 0.f) {
+        const float d = __fsqrt_rn(dsq);
+        n[0] = __fdiv_rn(dx, d); n[1] = __fdiv_rn(dy, d); n[2] = __fdiv_rn(dz, d);
+    } else {
+        n[0] = 0.f; n[1] = 0.f; n[2] = 1.f;
+    }
+}
+
+// min over the scene's boxes and spheres of the signed distance of K spheres (centres C[k], radii r[k]) that
+// belong to one link -- restructuring (1) above.  out[k] = min_j sd(k, j)  (floor not included).
+template <int K>
+__device__ __forceinline__ void sweep_scene(const SceneS& sc, const float (&C)[K][3], const float (&rad)[K],
+                                            float (&out)[K]) {
+    float D[K], M[K], E[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { D[k] = CBF_INF; M[k] = CBF_INF; E[k] = CBF_INF; }
+    for (int j = 0; j < sc.n_boxes; ++j) {
+        const float4 b0 = sc.boxes[2 * j], b1 = sc.boxes[2 * j + 1];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float ax = __fsub_rn(fabsf(__fsub_rn(C[k][0], b0.x)), b0.w);
+            const float ay = __fsub_rn(fabsf(__fsub_rn(C[k][1], b0.y)), b1.x);
+            const float az = __fsub_rn(fabsf(__fsub_rn(C[k][2], b0.z)), b1.y);
+            const float qx = fmaxf(ax, 0.f), qy = fmaxf(ay, 0.f), qz = fmaxf(az, 0.f);
+            const float dsq = fmaf(qz, qz, fmaf(qy, qy, __fmul_rn(qx, qx)));
+            D[k] = fminf(D[k], dsq);
+            M[k] = fminf(M[k], fmaxf(ax, fmaxf(ay, az)));
+        }
+    }
+    for (int j = 0; j < sc.n_spheres; ++j) {
+        const float4 s = sc.spheres[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float dx = __fsub_rn(C[k][0], s.x), dy = __fsub_rn(C[k][1], s.y), dz = __fsub_rn(C[k][2], s.z);
+            const float dsq = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+            E[k] = fminf(E[k], __fsub_rn(__fsqrt_rn(dsq), s.w));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        // boxes: e = sqrt(min dsq) + min(min max3, 0); with no boxes D = M = +inf -> e = +inf
+        const float e_box = __fadd_rn(__fsqrt_rn(D[k]), fminf(M[k], 0.f));
+        out[k] = __fsub_rn(fminf(e_box, E[k]), rad[k]);
+    }
+}
+
+// ------------------------------------------------------------------ per-state result
+template <class RB>
+struct CollideResult {
+    float o;         // min signed distance over non-base links x (floor, boxes, spheres)  (arm_mindis.py:71-90)
+    float soft_min;  // as checked by check_collision_free_soft  (arm_dynamics.py:169-182), before self test
+    float hard_min;  // as checked by check_collision_free_hard  (arm_dynamics.py:184-187, arm_env.py:82-84)
+    bool self_ok;    // no non-adjacent link pair within 0.01 m    (basic_robot.py:89-98)
+    float self_min;  // only when WANT_SELFMIN
+    int arg_sphere, arg_obs;
+    float dodq[RB::N];
+};
+
+// base link (-1) is static: its distance to every obstacle is a per-scene constant that the CTA computes once
+// (kernels.cu: base_min_cta) and passes in.  The floor is exempt for the base in both checks.
+template <class RB, bool WANT_GRAD, bool WANT_SELFMIN>
+__device__ __forceinline__ void collide_state(const float (&q)[RB::N], const SceneS& sc, float base_min,
+                                              CollideResult<RB>& res) {
+    constexpr int N = RB::N;
+    float o = CBF_INF, soft = base_min, hard = base_min;
+    int arg_s = -1;
+    float argC[3] = {0.f, 0.f, 0.f};
+    // joint frames needed by the gradient: z axis + origin of every revolute joint frame
+    float jz[WANT_GRAD ? N : 1][3], jp[WANT_GRAD ? N : 1][3];
+    // sphere centres kept for the self-collision predicate (only spheres that appear in a self pair)
+    float SC[RB::NSPH][3];
+
+    Frame fr[RB::NLINKS];  // fully unrolled: only live frames stay in registers
+    static_for<0, RB::NLINKS>([&](auto lc) {
+        constexpr int L = decltype(lc)::value;
+        constexpr int P = RB::parent(L);
+        float sq = 0.f, cq = 1.f;
+        if constexpr (RB::qidx(L) >= 0) det_sincosf(q[RB::qidx(L)], sq, cq);
+        if constexpr (P < 0) {
+            const Frame base = identity_frame();
+            child_frame<RB, L>(base, true, sq, cq, fr[L]);
+        } else {
+            child_frame<RB, L>(fr[P], false, sq, cq, fr[L]);
+        }
+        if constexpr (WANT_GRAD && RB::qidx(L) >= 0) {
+            constexpr int J = RB::qidx(L);
+            jz[J][0] = fr[L].R[2]; jz[J][1] = fr[L].R[5]; jz[J][2] = fr[L].R[8];
+            jp[J][0] = fr[L].p[0]; jp[J][1] = fr[L].p[1]; jp[J][2] = fr[L].p[2];
+        }
+        constexpr int S0 = RB::sph_begin(L), S1 = RB::sph_end(L), K = S1 - S0;
+        if constexpr (K > 0) {
+            float C[K][3], rad[K], m[K];
+            static_for<0, K>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                constexpr int i = S0 + k;
+                constexpr float c0 = RB::sph(i, 0), c1 = RB::sph(i, 1), c2 = RB::sph(i, 2);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    C[k][r] = fmaf(fr[L].R[3 * r + 2], c2, fmaf(fr[L].R[3 * r + 1], c1, fmaf(fr[L].R[3 * r + 0], c0, fr[L].p[r])));
+                rad[k] = RB::sph(i, 3);
+                SC[i][0] = C[k][0]; SC[i][1] = C[k][1]; SC[i][2] = C[k][2];
+            });
+            sweep_scene<K>(sc, C, rad, m);
+            // merge in sphere order, floor candidate first (oracle iteration order; strict '<')
+            static_for<0, K>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                constexpr int i = S0 + k;
+                if (sc.floor) {
+                    if constexpr (L == 0) {
+                        if constexpr (k == 0) {  // kinematic constant attached to the link's first sphere
+                            const float d = RB::LINK0_FLOOR;
+                            if (d < o) { o = d; arg_s = i; argC[0] = C[k][0]; argC[1] = C[k][1]; argC[2] = C[k][2]; }
+                            hard = fminf(hard, d);  // soft: link 0 is floor-exempt (arm_dynamics.py:180)
+                        }
+                    } else {
+                        const float d = __fsub_rn(C[k][2], rad[k]);
+                        if (d < o) { o = d; arg_s = i; argC[0] = C[k][0]; argC[1] = C[k][1]; argC[2] = C[k][2]; }
+                        soft = fminf(soft, d);
+                        if constexpr (L != 1) hard = fminf(hard, d);  // link 1 is filtered vs plane (arm_env.py:84)
+                    }
+                }
+                if (m[k] < o) { o = m[k]; arg_s = i; argC[0] = C[k][0]; argC[1] = C[k][1]; argC[2] = C[k][2]; }
+                soft = fminf(soft, m[k]);
+                hard = fminf(hard, m[k]);
+            });
+        }
+    });
+
+    // self collision, restructuring (2)
+    bool self_ok = true;
+    float self_min = CBF_INF;
+    static_for<0, RB::NSELFSPH>([&](auto pc) {
+        constexpr int p = decltype(pc)::value;
+        constexpr int i = RB::self_i(p), j = RB::self_j(p);
+        const float dx = __fsub_rn(SC[i][0], SC[j][0]), dy = __fsub_rn(SC[i][1], SC[j][1]), dz = __fsub_rn(SC[i][2], SC[j][2]);
+        const float dsq = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+        self_ok = self_ok && (dsq > RB::self_x(p));
+        if constexpr (WANT_SELFMIN)
+            self_min = fminf(self_min, __fsub_rn(__fsub_rn(__fsqrt_rn(dsq), RB::sph(i, 3)), RB::sph(j, 3)));
+    });
+
+    res.o = o; res.soft_min = soft; res.hard_min = hard; res.self_ok = self_ok; res.self_min = self_min;
+    res.arg_sphere = arg_s; res.arg_obs = -1;
+#pragma unroll
+    for (int k = 0; k < N; ++k) res.dodq[k] = 0.f;
+    if constexpr (WANT_GRAD) {
+        if (arg_s < 0) return;
+        // recover the obstacle: first j (floor, boxes, spheres) whose exact pair distance equals o
+        const int link = RB::sph_link(arg_s);
+        const float r = RB::sph(arg_s, 3);
+        const int off = sc.floor ? 1 : 0;
+        float nrm[3] = {0.f, 0.f, 1.f};
+        int arg_o = -1;
+        if (sc.floor) {
+            const float d = (link == 0) ? RB::LINK0_FLOOR : __fsub_rn(argC[2], r);
+            if (d == o) arg_o = 0;
+        }
+        if (arg_o < 0) {
+            for (int j = 0; j < sc.n_boxes; ++j) {
+                const float4 b0 = sc.boxes[2 * j], b1 = sc.boxes[2 * j + 1];
+                if (sd_box_exact(argC[0], argC[1], argC[2], b0, b1, r) == o) {
+                    arg_o = off + j;
+                    normal_box(argC[0], argC[1], argC[2], b0, b1, nrm);
+                    break;
+                }
+            }
+        }
+        if (arg_o < 0) {
+            for (int j = 0; j < sc.n_spheres; ++j) {
+                const float4 s = sc.spheres[j];
+                if (sd_sphere_exact(argC[0], argC[1], argC[2], s, r) == o) {
+                    arg_o = off + sc.n_boxes + j;
+                    normal_sphere(argC[0], argC[1], argC[2], s, nrm);
+                    break;
+                }
+            }
+        }
+        res.arg_obs = arg_o;
+        // n^T (z_j x (C - p_j)) for the joints that move the arg-min link (arm_mindis.py:56-69)
+        const int mask = RB::anc_mask(link);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float rx = __fsub_rn(argC[0], jp[j][0]), ry = __fsub_rn(argC[1], jp[j][1]), rz = __fsub_rn(argC[2], jp[j][2]);
+            const float cx = fmaf(jz[j][1], rz, -__fmul_rn(jz[j][2], ry));
+            const float cy = fmaf(jz[j][2], rx, -__fmul_rn(jz[j][0], rz));
+            const float cz = fmaf(jz[j][0], ry, -__fmul_rn(jz[j][1], rx));
+            const float g = fmaf(nrm[2], cz, fmaf(nrm[1], cy, __fmul_rn(nrm[0], cx)));
+            res.dodq[j] = ((mask >> j) & 1) ? g : 0.f;
+        }
+    }
+}
+
+// FK only: all link frames (basic_robot.py:55-62)
+template <class RB, class Sink>
+__device__ __forceinline__ void fk_all(const float (&q)[RB::N], Sink&& sink) {
+    Frame fr[RB::NLINKS];
+    static_for<0, RB::NLINKS>([&](auto lc) {
+        constexpr int L = decltype(lc)::value;
+        constexpr int P = RB::parent(L);
+        float sq = 0.f, cq = 1.f;
+        if constexpr (RB::qidx(L) >= 0) det_sincosf(q[RB::qidx(L)], sq, cq);
+        if constexpr (P < 0) {
+            const Frame base = identity_frame();
+            child_frame<RB, L>(base, true, sq, cq, fr[L]);
+        } else {
+            child_frame<RB, L>(fr[P], false, sq, cq, fr[L]);
+        }
+        sink(L, fr[L]);
+    });
+}
+
+// distance of the static base link to the scene: every thread of the CTA takes a slice of the obstacles,
+// then a block-wide min.  Order-independent (min of identical values), so bit-exact with the oracle.
+template <class RB>
+__device__ __forceinline__ float base_min_partial(const SceneS& sc, int tid, int nthreads) {
+    float m = CBF_INF;
+    constexpr int S0 = RB::sph_begin(-1), S1 = RB::sph_end(-1);
+    for (int j = tid; j < sc.n_boxes; j += nthreads) {
+        const float4 b0 = sc.boxes[2 * j], b1 = sc.boxes[2 * j + 1];
+        static_for<S0, S1>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            m = fminf(m, sd_box_exact(RB::sph(i, 0), RB::sph(i, 1), RB::sph(i, 2), b0, b1, RB::sph(i, 3)));
+        });
+    }
+    for (int j = tid; j < sc.n_spheres; j += nthreads) {
+        const float4 s = sc.spheres[j];
+        static_for<S0, S1>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            m = fminf(m, sd_sphere_exact(RB::sph(i, 0), RB::sph(i, 1), RB::sph(i, 2), s, RB::sph(i, 3)));
+        });
+    }
+    return m;
+}
+
+}  // namespace cbfrrt

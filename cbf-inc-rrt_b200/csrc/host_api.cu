@@ -1,0 +1,141 @@
+// host_api.cu -- host-buffer front end of libcbfrrt (include/cbfrrt.h: cbfrrt_safety_filter_host).
+//
+// What a numpy/ctypes caller of the reference would use: every pointer is a HOST pointer.  Rows are cut into
+// chunks that flow through NSTREAM private streams (H2D copy -> fused kernel -> D2H copy), so the PCIe
+// transfers of one chunk overlap the kernel of another.  Copies run straight from/to the caller's buffers:
+// truly asynchronous when those are pinned (bench.py pins them), staged by the driver otherwise.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/cbfrrt.h"
+
+namespace {
+
+constexpr int NSTREAM = 3;
+
+struct Lane {
+    cudaStream_t st = nullptr;
+    float *q = nullptr, *goal = nullptr, *datax = nullptr, *h = nullptr, *J = nullptr, *u = nullptr, *r = nullptr;
+    uint8_t *safe = nullptr, *unsafe = nullptr;
+};
+
+struct Ctx {
+    int device = -1;
+    int64_t cap_rows = 0;
+    Lane lane[NSTREAM];
+    float *boxes = nullptr, *spheres = nullptr, *weights = nullptr, *small = nullptr;  // small: goal(1 row) K lo hi
+    int64_t cap_boxes = 0, cap_spheres = 0, cap_weights = 0;
+    std::mutex mu;
+};
+
+Ctx g_ctx[16];
+
+#define CK(x)                                    \
+    do {                                         \
+        if ((x) != cudaSuccess) return CBFRRT_ERR_CUDA; \
+    } while (0)
+
+int ensure(Ctx& c, int device, int64_t rows, int n, int64_t n_boxes, int64_t n_spheres, int64_t n_weights) {
+    if (c.device != device) {
+        c.device = device;
+        for (auto& l : c.lane) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+        CK(cudaMalloc(&c.small, 4 * (8 + 64 + 8 + 8)));
+    }
+    if (rows > c.cap_rows) {
+        for (auto& l : c.lane) {
+            cudaFree(l.q); cudaFree(l.goal); cudaFree(l.datax); cudaFree(l.h); cudaFree(l.J); cudaFree(l.u);
+            cudaFree(l.r); cudaFree(l.safe); cudaFree(l.unsafe);
+            CK(cudaMalloc(&l.q, rows * 8 * 4));
+            CK(cudaMalloc(&l.goal, rows * 8 * 4));
+            CK(cudaMalloc(&l.datax, rows * 17 * 4));
+            CK(cudaMalloc(&l.h, rows * 4));
+            CK(cudaMalloc(&l.J, rows * 8 * 4));
+            CK(cudaMalloc(&l.u, rows * 8 * 4));
+            CK(cudaMalloc(&l.r, rows * 4));
+            CK(cudaMalloc(&l.safe, rows));
+            CK(cudaMalloc(&l.unsafe, rows));
+        }
+        c.cap_rows = rows;
+    }
+    if (n_boxes > c.cap_boxes) { cudaFree(c.boxes); CK(cudaMalloc(&c.boxes, n_boxes * 32)); c.cap_boxes = n_boxes; }
+    if (n_spheres > c.cap_spheres) { cudaFree(c.spheres); CK(cudaMalloc(&c.spheres, n_spheres * 16)); c.cap_spheres = n_spheres; }
+    if (n_weights > c.cap_weights) { cudaFree(c.weights); CK(cudaMalloc(&c.weights, n_weights * 4)); c.cap_weights = n_weights; }
+    return CBFRRT_OK;
+}
+
+}  // namespace
+
+extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_host_scene* scene, int32_t hidden,
+                                         int32_t layers, const float* weights, int64_t n_weights, const float* q,
+                                         int64_t B, const float* goal, int64_t goal_rows, const float* K,
+                                         const float* u_lo, const float* u_hi, float cbf_lambda,
+                                         float relaxation_penalty, float thr_soft, float thr_hard, uint8_t* safe,
+                                         uint8_t* unsafe, float* datax, float* h, float* J, float* u, float* r) {
+    int32_t n = 0, nl = 0, ns = 0;
+    int rc = cbfrrt_robot_info(robot, &n, &nl, &ns);
+    if (rc) return rc;
+    if (device < 0 || device >= 16 || B < 0 || !scene || !weights || !q || !goal || !K || !u_lo || !u_hi)
+        return CBFRRT_ERR_BAD_SHAPE;
+    if (goal_rows != 1 && goal_rows != B) return CBFRRT_ERR_BAD_SHAPE;
+    if (B == 0) return CBFRRT_OK;
+    CK(cudaSetDevice(device));
+    Ctx& c = g_ctx[device];
+    std::lock_guard<std::mutex> lock(c.mu);
+
+    // chunking: enough chunks to overlap copies with compute, big enough to fill the GPU (148 SMs x 512 rows)
+    int64_t chunk = (B + 2 * NSTREAM - 1) / (2 * NSTREAM);
+    const int64_t min_chunk = 148 * 512, max_chunk = 1 << 20;
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > max_chunk) chunk = max_chunk;
+    if (chunk > B) chunk = B;
+    rc = ensure(c, device, chunk, n, scene->n_boxes, scene->n_spheres, n_weights);
+    if (rc) return rc;
+
+    // scene / weights / small parameters: tiny, uploaded on lane 0, the other lanes wait on an event
+    cudaStream_t s0 = c.lane[0].st;
+    std::vector<float> b8((size_t)scene->n_boxes * 8, 0.f);
+    for (int i = 0; i < scene->n_boxes; ++i) memcpy(&b8[8 * i], scene->boxes + 6 * i, 24);
+    if (scene->n_boxes) CK(cudaMemcpyAsync(c.boxes, b8.data(), b8.size() * 4, cudaMemcpyHostToDevice, s0));
+    if (scene->n_spheres) CK(cudaMemcpyAsync(c.spheres, scene->spheres, (size_t)scene->n_spheres * 16, cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(c.weights, weights, n_weights * 4, cudaMemcpyHostToDevice, s0));
+    float small[8 + 64 + 8 + 8] = {0};
+    if (goal_rows == 1) memcpy(small, goal, 4 * n);
+    memcpy(small + 8, K, 4 * n * n);
+    memcpy(small + 72, u_lo, 4 * n);
+    memcpy(small + 80, u_hi, 4 * n);
+    CK(cudaMemcpyAsync(c.small, small, sizeof small, cudaMemcpyHostToDevice, s0));
+    CK(cudaStreamSynchronize(s0));  // b8/small live on this stack frame
+
+    cbfrrt_scene dsc{scene->n_boxes, scene->n_spheres, scene->floor, 0, c.boxes, c.spheres};
+    cbfrrt_cbf_net net{n + 1, hidden, layers, 0, c.weights};
+
+    int lane_i = 0;
+    for (int64_t off = 0; off < B; off += chunk, lane_i = (lane_i + 1) % NSTREAM) {
+        Lane& l = c.lane[lane_i];
+        const int64_t rows = (B - off < chunk) ? (B - off) : chunk;
+        CK(cudaMemcpyAsync(l.q, q + off * n, rows * n * 4, cudaMemcpyHostToDevice, l.st));
+        cbfrrt_filter_params fp{c.small, 1, c.small + 8, c.small + 72, c.small + 80, cbf_lambda, relaxation_penalty, nullptr};
+        if (goal_rows != 1) {
+            CK(cudaMemcpyAsync(l.goal, goal + off * n, rows * n * 4, cudaMemcpyHostToDevice, l.st));
+            fp.goal = l.goal;
+            fp.goal_rows = rows;
+        }
+        rc = cbfrrt_safety_filter(robot, &dsc, &net, l.q, n, rows, &fp, thr_soft, thr_hard, safe ? l.safe : nullptr,
+                                  unsafe ? l.unsafe : nullptr, datax ? l.datax : nullptr, h ? l.h : nullptr,
+                                  J ? l.J : nullptr, u ? l.u : nullptr, r ? l.r : nullptr, l.st);
+        if (rc) return rc;
+        if (safe) CK(cudaMemcpyAsync(safe + off, l.safe, rows, cudaMemcpyDeviceToHost, l.st));
+        if (unsafe) CK(cudaMemcpyAsync(unsafe + off, l.unsafe, rows, cudaMemcpyDeviceToHost, l.st));
+        if (datax) CK(cudaMemcpyAsync(datax + off * (2 * n + 1), l.datax, rows * (2 * n + 1) * 4, cudaMemcpyDeviceToHost, l.st));
+        if (h) CK(cudaMemcpyAsync(h + off, l.h, rows * 4, cudaMemcpyDeviceToHost, l.st));
+        if (J) CK(cudaMemcpyAsync(J + off * n, l.J, rows * n * 4, cudaMemcpyDeviceToHost, l.st));
+        if (u) CK(cudaMemcpyAsync(u + off * n, l.u, rows * n * 4, cudaMemcpyDeviceToHost, l.st));
+        if (r) CK(cudaMemcpyAsync(r + off, l.r, rows * 4, cudaMemcpyDeviceToHost, l.st));
+    }
+    for (auto& l : c.lane) CK(cudaStreamSynchronize(l.st));
+    return CBFRRT_OK;
+}

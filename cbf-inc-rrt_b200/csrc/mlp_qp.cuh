@@ -1,0 +1,239 @@
+// mlp_qp.cuh -- barrier MLP (value + exact reverse-mode Jacobian), nominal control and the closed-form
+// single-constraint CBF-QP, one state per thread (sm_100a).
+//
+// Reference semantics:
+//   h = W3 relu(W2 relu(W1 relu(W0 [q,o] + b0) + b1) + b2) + b3      neural_mindis_cbf_controller.py:41-53,71-81
+//   Jh = dh/d[q,o] (autograd == analytic backward with the ReLU masks) :83-98
+//   J  = Jh_q + Jh_o * do/dq                                           :99-101
+//   Lf_V = J f = 0, Lg_V = J g = J  (f = 0, g = I)                     clf_controller.py:169-218, arm_dynamics.py:327-363
+//   u_ref = clamp(-K (q - goal), lo, hi)                               arm_dynamics.py:124-161
+//   QP: min ||u-u_ref||^2 + p r  s.t. Lf + Lg.u + lam h - r <= 0, r >= 0, lo <= u <= hi   clf_controller.py:82-139
+//
+// Layout: the packed weights live in shared memory (staged once per CTA by a TMA bulk copy); every lane of a
+// warp reads the same weight at the same time, so each LDS.128 is a single broadcast wavefront feeding 4 FFMAs.
+// The activation vector of the thread lives in registers for the dot products of a layer and is parked in a
+// per-thread shared-memory column (scratch[k * NT + tid], conflict-free) between layers, which keeps the layer
+// loops rolled (small code, ~80 registers) instead of a 200 KB fully unrolled body.
+// These values are tolerance-checked (1e-5), not bit-exact, so plain fmaf ordering is free here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cbfrrt {
+
+template <int N_IN, int H, int L>
+struct NetLayout {
+    static constexpr int IN_PAD = (N_IN + 3) & ~3;
+    static constexpr int W_IN = 0;
+    static constexpr int B_IN = H * IN_PAD;
+    static constexpr int HID0 = B_IN + H;              // first hidden block: [W HxH][b H]
+    static constexpr int HID_STRIDE = H * H + H;
+    static constexpr int W_OUT = HID0 + L * HID_STRIDE;
+    static constexpr int B_OUT = W_OUT + H;
+    static constexpr int TOTAL = B_OUT + 4;            // b_out padded to 4 floats
+};
+
+// dot(W_row[0..H), a[0..H)) + bias with 4 partial sums (breaks the 48-long dependent FFMA chain)
+template <int H>
+__device__ __forceinline__ float dot_row(const float* __restrict__ wrow, const float (&a)[H], float bias) {
+    float s0 = bias, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+    for (int k = 0; k < H / 4; ++k) {
+        const float4 w = w4[k];
+        s0 = fmaf(w.x, a[4 * k + 0], s0);
+        s1 = fmaf(w.y, a[4 * k + 1], s1);
+        s2 = fmaf(w.z, a[4 * k + 2], s2);
+        s3 = fmaf(w.w, a[4 * k + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// value h and Jacobian jac = dh/dx for x = [q, o]  (N_IN = n + 1).
+//   w: packed weights in shared memory;  scr: this thread's scratch column (stride NT floats between entries)
+template <int N_IN, int H, int L, int NT>
+__device__ __forceinline__ void mlp_h_jac(const float* __restrict__ w, float* __restrict__ scr, const float (&x)[N_IN],
+                                          float& h_out, float (&jac)[N_IN]) {
+    using LY = NetLayout<N_IN, H, L>;
+    static_assert(H % 4 == 0 && H <= 64, "hidden size must be a multiple of 4, at most 64 (ReLU masks are 64-bit)");
+    float a[H];
+    uint64_t mask[L + 1];
+    // ---- input layer
+    {
+        uint64_t m = 0;
+#pragma unroll 4
+        for (int j = 0; j < H; ++j) {
+            const float4* w4 = reinterpret_cast<const float4*>(w + LY::W_IN + j * LY::IN_PAD);
+            float s = w[LY::B_IN + j];
+#pragma unroll
+            for (int k4 = 0; k4 < LY::IN_PAD / 4; ++k4) {
+                const float4 ww = w4[k4];
+                if (4 * k4 + 0 < N_IN) s = fmaf(ww.x, x[4 * k4 + 0 < N_IN ? 4 * k4 + 0 : 0], s);
+                if (4 * k4 + 1 < N_IN) s = fmaf(ww.y, x[4 * k4 + 1 < N_IN ? 4 * k4 + 1 : 0], s);
+                if (4 * k4 + 2 < N_IN) s = fmaf(ww.z, x[4 * k4 + 2 < N_IN ? 4 * k4 + 2 : 0], s);
+                if (4 * k4 + 3 < N_IN) s = fmaf(ww.w, x[4 * k4 + 3 < N_IN ? 4 * k4 + 3 : 0], s);
+            }
+            const bool on = s > 0.f;
+            m |= (uint64_t)on << j;
+            scr[j * NT] = on ? s : 0.f;
+        }
+        mask[0] = m;
+    }
+    // ---- hidden layers
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int k = 0; k < H; ++k) a[k] = scr[k * NT];
+        const float* W = w + LY::HID0 + l * LY::HID_STRIDE;
+        const float* bia = W + H * H;
+        uint64_t m = 0;
+#pragma unroll 2
+        for (int j = 0; j < H; ++j) {
+            const float s = dot_row<H>(W + j * H, a, bia[j]);
+            const bool on = s > 0.f;
+            m |= (uint64_t)on << j;
+            scr[j * NT] = on ? s : 0.f;
+        }
+        mask[l + 1] = m;
+    }
+    // ---- output layer + seed of the backward pass
+#pragma unroll
+    for (int k = 0; k < H; ++k) a[k] = scr[k * NT];
+    h_out = dot_row<H>(w + LY::W_OUT, a, w[LY::B_OUT]);
+    {
+        const float4* w4 = reinterpret_cast<const float4*>(w + LY::W_OUT);
+        const uint64_t m = mask[L];
+#pragma unroll
+        for (int k = 0; k < H / 4; ++k) {
+            const float4 ww = w4[k];
+            scr[(4 * k + 0) * NT] = ((m >> (4 * k + 0)) & 1) ? ww.x : 0.f;
+            scr[(4 * k + 1) * NT] = ((m >> (4 * k + 1)) & 1) ? ww.y : 0.f;
+            scr[(4 * k + 2) * NT] = ((m >> (4 * k + 2)) & 1) ? ww.z : 0.f;
+            scr[(4 * k + 3) * NT] = ((m >> (4 * k + 3)) & 1) ? ww.w : 0.f;
+        }
+    }
+    // ---- backward through the hidden layers: g_prev[k] = relu'_prev[k] * sum_j W[j][k] g[j]
+#pragma unroll
+    for (int l = L - 1; l >= 0; --l) {
+        const float* W = w + LY::HID0 + l * LY::HID_STRIDE;
+#pragma unroll
+        for (int k = 0; k < H; ++k) a[k] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < H; ++j) {
+            const float g = scr[j * NT];
+            const float4* w4 = reinterpret_cast<const float4*>(W + j * H);
+#pragma unroll
+            for (int k = 0; k < H / 4; ++k) {
+                const float4 ww = w4[k];
+                a[4 * k + 0] = fmaf(ww.x, g, a[4 * k + 0]);
+                a[4 * k + 1] = fmaf(ww.y, g, a[4 * k + 1]);
+                a[4 * k + 2] = fmaf(ww.z, g, a[4 * k + 2]);
+                a[4 * k + 3] = fmaf(ww.w, g, a[4 * k + 3]);
+            }
+        }
+        const uint64_t m = mask[l];
+#pragma unroll
+        for (int k = 0; k < H; ++k) scr[k * NT] = ((m >> k) & 1) ? a[k] : 0.f;
+    }
+    // ---- input layer backward: jac[k] = sum_j W_in[j][k] g[j]
+#pragma unroll
+    for (int k = 0; k < N_IN; ++k) jac[k] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < H; ++j) {
+        const float g = scr[j * NT];
+        const float4* w4 = reinterpret_cast<const float4*>(w + LY::W_IN + j * LY::IN_PAD);
+#pragma unroll
+        for (int k4 = 0; k4 < LY::IN_PAD / 4; ++k4) {
+            const float4 ww = w4[k4];
+            if (4 * k4 + 0 < N_IN) jac[4 * k4 + 0 < N_IN ? 4 * k4 + 0 : 0] = fmaf(ww.x, g, jac[4 * k4 + 0 < N_IN ? 4 * k4 + 0 : 0]);
+            if (4 * k4 + 1 < N_IN) jac[4 * k4 + 1 < N_IN ? 4 * k4 + 1 : 0] = fmaf(ww.y, g, jac[4 * k4 + 1 < N_IN ? 4 * k4 + 1 : 0]);
+            if (4 * k4 + 2 < N_IN) jac[4 * k4 + 2 < N_IN ? 4 * k4 + 2 : 0] = fmaf(ww.z, g, jac[4 * k4 + 2 < N_IN ? 4 * k4 + 2 : 0]);
+            if (4 * k4 + 3 < N_IN) jac[4 * k4 + 3 < N_IN ? 4 * k4 + 3 : 0] = fmaf(ww.w, g, jac[4 * k4 + 3 < N_IN ? 4 * k4 + 3 : 0]);
+        }
+    }
+}
+
+// filter parameters staged in shared memory next to the weights: [K n*n][u_lo n][u_hi n]
+template <int N>
+struct ParamLayout {
+    static constexpr int K = 0, LO = N * N, HI = N * N + N, TOTAL = ((N * N + 2 * N) + 3) & ~3;
+};
+
+template <int N>
+__device__ __forceinline__ float qp_g(const float (&a)[N], const float (&uref)[N], const float* __restrict__ lo,
+                                      const float* __restrict__ hi, float c, float mu) {
+    float g = c;
+    const float hm = 0.5f * mu;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const float v = fminf(fmaxf(fmaf(-hm, a[i], uref[i]), lo[i]), hi[i]);
+        g = fmaf(a[i], v, g);
+    }
+    return g;
+}
+
+// Exact KKT solution of the single-constraint CBF-QP.  u(mu) = clip(u_ref - mu a/2, lo, hi), 0 <= mu <= p;
+// g(mu) = c + a.u(mu) is non-increasing and piecewise linear with at most N breakpoints.  mu* = 0 if g(0) <= 0,
+// else the root of g in (0, p], found by evaluating g at every breakpoint (no sort: N^2 is 49) and
+// interpolating inside the bracketing segment (exact: g is linear there); if g(p) > 0 the constraint is relaxed
+// with mu = p and r = g(p).
+template <int N>
+__device__ __forceinline__ void qp_solve(const float (&a)[N], const float (&uref)[N], const float* __restrict__ lo,
+                                         const float* __restrict__ hi, float c, float p, float (&u)[N], float& r) {
+    r = 0.f;
+    const float g0 = qp_g<N>(a, uref, lo, hi, c, 0.f);
+    float mu = 0.f;
+    if (g0 > 0.f) {
+        float mu_lo = 0.f, g_lo = g0;
+        float mu_hi = p, g_hi = qp_g<N>(a, uref, lo, hi, c, p);
+        if (g_hi > 0.f) {
+            mu = p;
+            r = g_hi;
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                float m = -1.f;
+                if (a[i] > 0.f) m = 2.f * (uref[i] - lo[i]) / a[i];
+                else if (a[i] < 0.f) m = 2.f * (uref[i] - hi[i]) / a[i];
+                if (m > 0.f && m < p) {
+                    const float gm = qp_g<N>(a, uref, lo, hi, c, m);
+                    if (gm > 0.f) { if (m > mu_lo) { mu_lo = m; g_lo = gm; } }
+                    else          { if (m < mu_hi) { mu_hi = m; g_hi = gm; } }
+                }
+            }
+            mu = (g_lo > g_hi) ? fmaf(mu_hi - mu_lo, g_lo / (g_lo - g_hi), mu_lo) : mu_hi;
+        }
+    }
+    const float hm = 0.5f * mu;
+#pragma unroll
+    for (int i = 0; i < N; ++i) u[i] = fminf(fmaxf(fmaf(-hm, a[i], uref[i]), lo[i]), hi[i]);
+}
+
+// datax = [q | o | do/dq]  ->  h, J, u, r   (one controller.u call of the reference)
+template <int N, int H, int L, int NT>
+__device__ __forceinline__ void cbf_filter_state(const float* __restrict__ w, const float* __restrict__ prm,
+                                                 float* __restrict__ scr, const float (&q)[N], float o,
+                                                 const float (&dodq)[N], const float (&goal)[N], bool goal_is_uref,
+                                                 float lam, float penalty, float& h, float (&J)[N], float (&u)[N],
+                                                 float& r) {
+    float x[N + 1], jac[N + 1];
+#pragma unroll
+    for (int k = 0; k < N; ++k) x[k] = q[k];
+    x[N] = o;
+    mlp_h_jac<N + 1, H, L, NT>(w, scr, x, h, jac);
+#pragma unroll
+    for (int k = 0; k < N; ++k) J[k] = fmaf(jac[N], dodq[k], jac[k]);
+    using PL = ParamLayout<N>;
+    float uref[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) acc = fmaf(prm[PL::K + i * N + k], q[k] - goal[k], acc);
+        uref[i] = fminf(fmaxf(-acc, prm[PL::LO + i]), prm[PL::HI + i]);
+        if (goal_is_uref) uref[i] = goal[i];  // caller-supplied u_ref is used verbatim (clf_controller.py:497-504)
+    }
+    qp_solve<N>(J, uref, prm + PL::LO, prm + PL::HI, lam * h, fminf(penalty, 1e6f), u, r);
+}
+
+}  // namespace cbfrrt

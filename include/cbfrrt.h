@@ -1,0 +1,191 @@
+/*
+ * cbfrrt.h -- C-ABI of libcbfrrt (B200 / sm_100a): batched safety evaluation and control of manipulator states.
+ *
+ * This is the drop-in boundary for the CBF-INC-RRT hot path.  Every entry point replaces one per-state Python
+ * loop of the reference (file:line under the reference repository root) and is what a maintainer of the
+ * reference would bind with ctypes.  Conventions:
+ *
+ *   - plain C: pointers + sizes + scalars; no torch / C++ types cross this boundary;
+ *   - "device" entry points take DEVICE pointers and a cudaStream_t passed as void* (NULL = legacy default
+ *     stream); they never allocate, never synchronise and never throw; they return CBFRRT_OK (0) or a negative
+ *     cbfrrt_status and leave the outputs untouched on error;
+ *   - "_host" entry points take HOST pointers, stage through an internal pinned/device arena on private
+ *     streams, and return after the results are in the caller's buffers (they synchronise their own streams);
+ *   - all floating-point data is IEEE binary32, row-major, contiguous unless a stride argument says otherwise;
+ *     masks are uint8 (0/1); indices are int32;
+ *   - optional outputs may be NULL.
+ *
+ * Robots (compile-time tables generated from the reference's URDFs + collision meshes, spec/robot_models.json):
+ *   CBFRRT_ROBOT_PANDA    n=7, 12 pybullet links, 32 link spheres    environment/franka_panda.py:17-28
+ *   CBFRRT_ROBOT_MAGICIAN n=4,  4 pybullet links, 24 link spheres    environment/magician.py:18-22
+ *
+ * Scene (environment/arm_env.py:63-99,154-182): optional floor plane z=0 + axis-aligned boxes; sphere obstacles
+ * are an extension required by BASELINE.json config 3.  Device layout:
+ *   boxes   [n_boxes, 8]   cx cy cz hx | hy hz 0 0        (two 16-byte words per box)
+ *   spheres [n_spheres, 4] cx cy cz r
+ * Obstacle indices reported by the library follow the reference's env.obstacle_ids order: floor first (if
+ * present), then boxes, then spheres.
+ *
+ * CBF weight packing (neural_cbf/controllers/neural_mindis_cbf_controller.py:41-53; state_dict keys
+ * h_nn.input_linear / layer_{i}_linear / output_linear), IN_PAD = round_up(n+1, 4), H = hidden size,
+ * L = number of hidden->hidden layers:
+ *   [W_in  H x IN_PAD (zero padded)] [b_in H] { [W_l H x H] [b_l H] } x L  [w_out H] [b_out 1, padded to 4]
+ */
+#ifndef CBFRRT_H
+#define CBFRRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBFRRT_ABI_VERSION 1
+
+typedef enum {
+    CBFRRT_OK = 0,
+    CBFRRT_ERR_BAD_ROBOT = -1,
+    CBFRRT_ERR_BAD_SHAPE = -2,    /* negative size, missing required pointer, goal_rows not in {1,B}, ... */
+    CBFRRT_ERR_UNSUPPORTED = -3,  /* network shape / scene size outside what the kernels are built for */
+    CBFRRT_ERR_CUDA = -4,         /* launch or runtime failure; cbfrrt_last_cuda_error() has the code */
+    CBFRRT_ERR_ALIGNMENT = -5     /* scene / weight buffers must be 16-byte aligned */
+} cbfrrt_status;
+
+typedef enum { CBFRRT_ROBOT_PANDA = 0, CBFRRT_ROBOT_MAGICIAN = 1 } cbfrrt_robot;
+
+#define CBFRRT_MAX_OBSTACLES 1024 /* boxes + spheres staged in shared memory per CTA */
+
+typedef struct {
+    int32_t n_boxes;
+    int32_t n_spheres;
+    int32_t floor;        /* 1: plane z=0 present (ArmEnv(include_floor=True), arm_env.py:68-70) */
+    int32_t _pad;
+    const float *boxes;   /* device, [n_boxes, 8], 16-byte aligned */
+    const float *spheres; /* device, [n_spheres, 4], 16-byte aligned */
+} cbfrrt_scene;
+
+typedef struct {
+    int32_t n_in;          /* n + 1 */
+    int32_t hidden;        /* cbf_hidden_size  (48 in every shipped entry point) */
+    int32_t layers;        /* cbf_hidden_layers (2) */
+    int32_t _pad;
+    const float *weights;  /* device, packed as described above, 16-byte aligned */
+} cbfrrt_cbf_net;
+
+/* Parameters of the CBF-QP safety filter (neural_cbf/controllers/clf_controller.py:82-139,354-404) and of the
+ * nominal controller (neural_cbf/systems/arm_dynamics.py:124-161). */
+typedef struct {
+    const float *goal;   /* device [goal_rows, n]: dynamics_model.intermediate_goals (arm_dynamics.py:71-74) */
+    int64_t goal_rows;   /* 1 (shared goal) or B (one goal per row, batch_tsa.py:199) */
+    const float *K;      /* device [n, n] LQR gain (control_affine_system.py:125-157) */
+    const float *u_lo;   /* device [n]  control_limits lower (arm_dynamics.py:111-119) */
+    const float *u_hi;   /* device [n]  control_limits upper */
+    float cbf_lambda;    /* cbf_alpha */
+    float relaxation_penalty; /* clamped to 1e6 inside, clf_controller.py:380 */
+    const float *u_ref;  /* optional device [B, n]: caller-supplied reference control, bypasses the nominal
+                            controller exactly like solve_CLF_QP(u_ref=...) (clf_controller.py:497-504); when set,
+                            goal and K may be NULL */
+} cbfrrt_filter_params;
+
+/* steer-loop parameters (motion_planning/baseline/tsa.py:217-269) */
+typedef struct {
+    int32_t steps;        /* RRT_step */
+    int32_t ctrl_every;   /* controller_dt // dt (4 in every shipped entry point) */
+    float dt;             /* simulation step */
+    int32_t stuck_lag;    /* 0 disables the stuck test; tsa.py:263 uses 9 (x_list[-1] vs x_list[-10]) */
+    int32_t stuck_after;  /* test only when tstep > stuck_after (10) */
+    float stuck_eps;      /* 0.1 */
+} cbfrrt_rollout_params;
+
+/* ---- library info ------------------------------------------------------------------------------------- */
+int cbfrrt_abi_version(void);
+const char *cbfrrt_status_string(int status);
+int cbfrrt_last_cuda_error(void);
+/* n (dof), number of pybullet links (FK rows), number of link spheres */
+int cbfrrt_robot_info(int robot, int32_t *n, int32_t *n_links, int32_t *n_spheres);
+
+/* ---- K1  forward kinematics ----------------------------------------------------------------------------
+ * Replaces BasicRobot.forward_kinematics + set_joint_position (environment/basic_robot.py:55-68): world pose
+ * of every pybullet link frame (getLinkState[4], [5]).   q [B, n] (row stride q_stride floats)
+ *   -> pos [B, n_links, 3], rot [B, n_links, 9] (row-major 3x3).  */
+int cbfrrt_fk(int robot, const float *q, int64_t q_stride, int64_t B, float *pos, float *rot, void *stream);
+
+/* ---- K1+K2+K3  collision masks + min-distance observation ---------------------------------------------
+ * Replaces ArmDynamics.safe_mask / unsafe_mask (neural_cbf/systems/arm_dynamics.py:169-232, incl.
+ * BasicRobot.check_self_collision_free basic_robot.py:89-98) and ArmMindis._get_observation_with_state +
+ * complete_sample_with_observations (arm_mindis.py:56-90, arm_dynamics.py:267-279).
+ *   safe/unsafe [B] uint8;  datax [B, 2n+1] = [q | o | do/dq];  arg_link/arg_obs [B] = arg-min pair of o;
+ *   mins [B,3] = (self_min, soft_min, hard_min) diagnostics.  All outputs optional. */
+int cbfrrt_collide(int robot, const cbfrrt_scene *scene, const float *q, int64_t q_stride, int64_t B,
+                   float thr_soft, float thr_hard, uint8_t *safe, uint8_t *unsafe, float *datax,
+                   int32_t *arg_link, int32_t *arg_obs, float *mins, void *stream);
+
+/* ---- K4+K5+K6+K7+K8  barrier value, Jacobian, Lie derivatives, nominal control, CBF-QP -----------------
+ * Replaces NeuralMindisCBFController.h / h_with_jacobian (neural_mindis_cbf_controller.py:71-102),
+ * CLFController.V_with_lie_derivatives / solve_CLF_QP / u (clf_controller.py:169-218,461-535) and
+ * ArmDynamics.u_nominal (arm_dynamics.py:124-161) for n_scenarios == 1.
+ *   datax [B, 2n+1] -> h [B], J [B, n] (= Lg_V; Lf_V = 0), u [B, n], r [B].  Outputs optional. */
+int cbfrrt_cbf_filter(int n, const cbfrrt_cbf_net *net, const float *datax, int64_t B,
+                      const cbfrrt_filter_params *fp, float *h, float *J, float *u, float *r, void *stream);
+
+/* ---- K8 alone: batched single-constraint CLF/CBF-QP -------------------------------------------------------
+ * Replaces CLFController._solve_CLF_QP_cvxpylayers (clf_controller.py:354-404) for n_scenarios == 1 when the
+ * caller already has the Lie derivatives:  min ||u-u_ref||^2 + p r  s.t. c + a.u - r <= 0, r >= 0, lo<=u<=hi
+ * with a = Lg_V [B, n], c = Lf_V + lambda V [B].  1 <= n <= 8.  p is clamped to 1e6 (:380). */
+int cbfrrt_qp(int n, const float *a, const float *c, const float *u_ref, int64_t B, const float *u_lo,
+              const float *u_hi, float relaxation_penalty, float *u, float *r, void *stream);
+
+/* ---- fused q -> (masks, datax, h, J, u, r): one launch for sampled states ------------------------------ */
+int cbfrrt_safety_filter(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_net *net, const float *q,
+                         int64_t q_stride, int64_t B, const cbfrrt_filter_params *fp, float thr_soft,
+                         float thr_hard, uint8_t *safe, uint8_t *unsafe, float *datax, float *h, float *J,
+                         float *u, float *r, void *stream);
+
+/* ---- K10 edge validity -----------------------------------------------------------------------------------
+ * Replaces edge_checking (motion_planning/baseline/tsa.py:272-286) for E edges with a fixed number n_interp
+ * of interpolation points: valid <=> safe(q_to) and safe(q_from + k/n_interp (q_to - q_from)), k=0..n_interp-1.
+ * first_bad = smallest failing along-edge index (k, or n_interp for the end point), -1 if the edge is valid. */
+int cbfrrt_edge_validity(int robot, const cbfrrt_scene *scene, const float *q_from, const float *q_to, int64_t E,
+                         int32_t n_interp, float thr_soft, float thr_hard, uint8_t *valid, int32_t *first_bad,
+                         void *stream);
+
+/* ---- K9 closed-loop rollouts ------------------------------------------------------------------------------
+ * Replaces the steer loop (motion_planning/baseline/tsa.py:217-269, batch_tsa.py:191-231) built on
+ * ArmDynamics.closed_loop_dynamics (arm_dynamics.py:474-523): control every ctrl_every steps, Euler every
+ * step, observation refresh when (t+1) % ctrl_every == 0, unsafe check after every step.  A trajectory stops
+ * when the new state is unsafe (that state is NOT appended: alive = 0) or when the stuck test fires
+ * (alive stays 1).   q0 [T, n], goal [goal_rows, n] ->
+ *   q_final [T, n]  = last appended state (x_list[-1]),  alive [T] = no_collision,
+ *   steps_done [T]  = number of appended states,  traj [T, steps, n] optional = x_list[1:] (rows beyond
+ *   steps_done are left untouched); required when the stuck test is enabled. */
+int cbfrrt_rollout(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_net *net, const float *q0, int64_t T,
+                   const cbfrrt_filter_params *fp, const cbfrrt_rollout_params *rp, float thr_soft, float thr_hard,
+                   float *q_final, uint8_t *alive, int32_t *steps_done, float *traj, void *stream);
+
+/* ---- counter-based uniform state sampler (ControlAffineSystem.sample_state_space,
+ * control_affine_system.py:291-300, made shard-invariant): row g = start_row + b, q[b,j] = lo_j + U(g,j)(hi_j-lo_j) */
+int cbfrrt_sample_states(int robot, uint32_t seed, uint64_t start_row, int64_t B, float *q, void *stream);
+
+/* ---- host-buffer front end (what a ctypes / numpy caller of the reference would use) ----------------------
+ * Same semantics as cbfrrt_safety_filter but every pointer (including scene, weights and parameters) is a
+ * HOST pointer.  Rows are processed in chunks on private streams: H2D copy, kernel and D2H copy of
+ * consecutive chunks overlap.  device: CUDA device ordinal. */
+typedef struct {
+    int32_t n_boxes, n_spheres, floor, _pad;
+    const float *boxes;   /* host [n_boxes, 6]  cx cy cz hx hy hz   (ArmEnv.obs_positions / obs_sizes) */
+    const float *spheres; /* host [n_spheres, 4] */
+} cbfrrt_host_scene;
+
+int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_host_scene *scene, int32_t hidden, int32_t layers,
+                              const float *weights, int64_t n_weights, const float *q, int64_t B, const float *goal,
+                              int64_t goal_rows, const float *K, const float *u_lo, const float *u_hi,
+                              float cbf_lambda, float relaxation_penalty, float thr_soft, float thr_hard,
+                              uint8_t *safe, uint8_t *unsafe, float *datax, float *h, float *J, float *u, float *r);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches evidence) */
+int64_t cbfrrt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBFRRT_H */

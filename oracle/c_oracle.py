@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE -- ctypes/numpy front-end of oracle/cbfrrt_oracle.c (see that file's header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_DIR, "_build", "libcbfrrt_oracle.so")
+ROBOT_ID = {"panda": 0, "magician": 1}
+
+
+def build(force=False):
+    src = os.path.join(_DIR, "cbfrrt_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(_DIR, "robot_tables.h"))):
+        subprocess.check_call(["make", "-C", _DIR, "-B"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def set_threads(t):
+    lib().oracle_set_threads(int(t))
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def pack_scene(boxes, spheres=None):
+    """boxes (Ob,6) [c, h] -> (Ob,8) device layout; spheres (Os,4)."""
+    boxes = np.zeros((0, 6), np.float32) if boxes is None else _f(boxes).reshape(-1, 6)
+    b8 = np.zeros((boxes.shape[0], 8), np.float32)
+    b8[:, :6] = boxes
+    sp = np.zeros((0, 4), np.float32) if spheres is None else _f(spheres).reshape(-1, 4)
+    return b8, sp
+
+
+def robot_info(robot):
+    n, l, s = C.c_int(), C.c_int(), C.c_int()
+    lib().oracle_robot_info(ROBOT_ID[robot], C.byref(n), C.byref(l), C.byref(s))
+    return n.value, l.value, s.value
+
+
+def sincos(x):
+    x = _f(x)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().oracle_sincos(_p(x), C.c_long(x.size), _p(s), _p(c))
+    return s, c
+
+
+def fk(robot, q):
+    q = _f(q)
+    n, L, _ = robot_info(robot)
+    B = q.shape[0]
+    pos = np.empty((B, L, 3), np.float32)
+    rot = np.empty((B, L, 3, 3), np.float32)
+    lib().oracle_fk(ROBOT_ID[robot], _p(q), C.c_long(q.shape[1]), C.c_long(B), _p(pos), _p(rot))
+    return pos, rot
+
+
+def collide(robot, q, boxes, spheres=None, floor=True, thr_soft=0.02, thr_hard=0.0):
+    q = _f(q)
+    n, L, _ = robot_info(robot)
+    B = q.shape[0]
+    b8, sp = pack_scene(boxes, spheres)
+    out = dict(safe=np.empty(B, np.uint8), unsafe=np.empty(B, np.uint8), datax=np.empty((B, 2 * n + 1), np.float32),
+               arg_link=np.empty(B, np.int32), arg_obs=np.empty(B, np.int32), mins=np.empty((B, 3), np.float32))
+    lib().oracle_collide(ROBOT_ID[robot], b8.shape[0], _p(b8), sp.shape[0], _p(sp), int(bool(floor)), _p(q),
+                         C.c_long(q.shape[1]), C.c_long(B), C.c_float(thr_soft), C.c_float(thr_hard), _p(out["safe"]),
+                         _p(out["unsafe"]), _p(out["datax"]), _p(out["arg_link"]), _p(out["arg_obs"]), _p(out["mins"]))
+    return out
+
+
+def cbf_filter(n, weights, hidden, layers, datax, goal, K, u_lo, u_hi, lam, penalty, u_ref=None):
+    datax = _f(datax)
+    B = datax.shape[0]
+    goal = _f(goal).reshape(-1, n)
+    u_ref = _f(u_ref) if u_ref is not None else None
+    w, K, u_lo, u_hi = _f(weights), _f(K), _f(u_lo), _f(u_hi)
+    out = dict(h=np.empty(B, np.float32), J=np.empty((B, n), np.float32), u=np.empty((B, n), np.float32),
+               r=np.empty(B, np.float32))
+    rc = lib().oracle_cbf_filter(n, hidden, layers, _p(w), _p(datax), C.c_long(B), _p(goal), C.c_long(goal.shape[0]),
+                                 _p(u_ref), _p(K), _p(u_lo), _p(u_hi), C.c_float(lam), C.c_float(penalty), _p(out["h"]),
+                                 _p(out["J"]), _p(out["u"]), _p(out["r"]))
+    assert rc == 0
+    return out
+
+
+def safety_filter(robot, q, boxes, spheres, floor, weights, hidden, layers, goal, K, u_lo, u_hi, thr_soft, thr_hard,
+                  lam, penalty):
+    q = _f(q)
+    n, L, _ = robot_info(robot)
+    B = q.shape[0]
+    b8, sp = pack_scene(boxes, spheres)
+    goal = _f(goal).reshape(-1, n)
+    w, K, u_lo, u_hi = _f(weights), _f(K), _f(u_lo), _f(u_hi)
+    out = dict(safe=np.empty(B, np.uint8), unsafe=np.empty(B, np.uint8), datax=np.empty((B, 2 * n + 1), np.float32),
+               h=np.empty(B, np.float32), J=np.empty((B, n), np.float32), u=np.empty((B, n), np.float32),
+               r=np.empty(B, np.float32))
+    rc = lib().oracle_safety_filter(ROBOT_ID[robot], b8.shape[0], _p(b8), sp.shape[0], _p(sp), int(bool(floor)), hidden,
+                                    layers, _p(w), _p(q), C.c_long(q.shape[1]), C.c_long(B), _p(goal),
+                                    C.c_long(goal.shape[0]), _p(K), _p(u_lo), _p(u_hi), C.c_float(thr_soft),
+                                    C.c_float(thr_hard), C.c_float(lam), C.c_float(penalty), _p(out["safe"]),
+                                    _p(out["unsafe"]), _p(out["datax"]), _p(out["h"]), _p(out["J"]), _p(out["u"]),
+                                    _p(out["r"]))
+    assert rc == 0
+    return out
+
+
+def edge_validity(robot, q_from, q_to, n_interp, boxes, spheres=None, floor=True, thr_soft=0.02, thr_hard=0.0):
+    q_from, q_to = _f(q_from), _f(q_to)
+    E = q_from.shape[0]
+    b8, sp = pack_scene(boxes, spheres)
+    valid = np.empty(E, np.uint8)
+    first_bad = np.empty(E, np.int32)
+    lib().oracle_edge_validity(ROBOT_ID[robot], b8.shape[0], _p(b8), sp.shape[0], _p(sp), int(bool(floor)), _p(q_from),
+                               _p(q_to), C.c_long(E), int(n_interp), C.c_float(thr_soft), C.c_float(thr_hard),
+                               _p(valid), _p(first_bad))
+    return valid, first_bad
+
+
+def rollout(robot, q0, goal, steps, ctrl_every, dt, boxes, spheres, floor, weights, hidden, layers, K, u_lo, u_hi,
+            thr_soft, thr_hard, lam, penalty, stuck_lag=0, stuck_after=10, stuck_eps=0.1, want_traj=False):
+    q0 = _f(q0)
+    n, L, _ = robot_info(robot)
+    T = q0.shape[0]
+    goal = _f(goal).reshape(-1, n)
+    b8, sp = pack_scene(boxes, spheres)
+    w, K, u_lo, u_hi = _f(weights), _f(K), _f(u_lo), _f(u_hi)
+    qf = np.empty((T, n), np.float32)
+    alive = np.empty(T, np.uint8)
+    done = np.empty(T, np.int32)
+    traj = np.zeros((T, steps, n), np.float32) if (want_traj or stuck_lag > 0) else None
+    rc = lib().oracle_rollout(ROBOT_ID[robot], b8.shape[0], _p(b8), sp.shape[0], _p(sp), int(bool(floor)), hidden,
+                              layers, _p(w), _p(q0), _p(goal), C.c_long(goal.shape[0]), C.c_long(T), int(steps),
+                              int(ctrl_every), C.c_float(dt), int(stuck_lag), int(stuck_after), C.c_float(stuck_eps),
+                              _p(K), _p(u_lo), _p(u_hi), C.c_float(thr_soft),
+                              C.c_float(thr_hard), C.c_float(lam), C.c_float(penalty), _p(qf), _p(alive), _p(done),
+                              _p(traj))
+    assert rc == 0
+    return qf, alive, done, traj
+
+
+def sample_states(robot, seed, start_row, B):
+    n, _, _ = robot_info(robot)
+    q = np.empty((B, n), np.float32)
+    lib().oracle_sample_states(ROBOT_ID[robot], C.c_uint32(seed), C.c_uint64(start_row), C.c_long(B), _p(q))
+    return q

@@ -1,0 +1,714 @@
+/*
+ * TEST INFRASTRUCTURE -- scalar C restatement ("oracle") of the CBF-INC-RRT hot path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library.  The product (cbf-inc-rrt_b200/) never links, imports or executes it.
+ *
+ * PARITY STATUS: "parity unpinned" at the pybullet / SCS boundaries: the reference's FK,
+ * closest-point and contact arithmetic lives in pybullet 3.2.5 and its QP in cvxpylayers 0.1.5 -> diffcp
+ * 1.0.19 -> SCS 3.2.0; none is installed here and the reference ships no golden vectors.  Pinned pieces:
+ * URDF constants, FK at q=0/q0 (hand-computed), LQR gain K (scipy DARE), and the MLP + Jacobian +
+ * Lie-derivative + nominal-control code, which IS checked against the reference's own Python executed in
+ * the dev container (tests/golden/make_golden.py).
+ *
+ * Reference code followed (file:line under /root/reference):
+ *   FK of the URDF chain                 environment/basic_robot.py:55-68, utils/robot/{franka_panda/panda,magician/urdf/demo}.urdf
+ *   safe / unsafe masks                  neural_cbf/systems/arm_dynamics.py:169-232, environment/basic_robot.py:89-98,
+ *                                        environment/arm_env.py:82-84
+ *   observation o = min distance, do/dq  neural_cbf/systems/arm_mindis.py:56-90
+ *   barrier MLP h and its Jacobian       neural_cbf/controllers/neural_mindis_cbf_controller.py:41-53,71-102
+ *   Lie derivatives (f=0, g=I)           neural_cbf/controllers/clf_controller.py:169-218, arm_dynamics.py:327-363
+ *   nominal control                      neural_cbf/systems/arm_dynamics.py:124-161
+ *   CBF-QP                               neural_cbf/controllers/clf_controller.py:82-139,354-404
+ *   Euler step / steer loop              neural_cbf/systems/arm_dynamics.py:474-523, motion_planning/baseline/tsa.py:217-269
+ *   edge check                           motion_planning/baseline/tsa.py:272-286
+ *
+ * DETERMINISTIC FLOAT32 CONTRACT (DESIGN.md "Deterministic-math contract"): every geometric quantity that
+ * feeds a boolean or an index is computed with exactly the operation sequence written below -- single
+ * IEEE-754 binary32 operations (add, sub, mul, fmaf, sqrtf, div, rintf), no contraction (compile with
+ * -ffp-contract=off), own sincos.  The CUDA kernels follow the same sequence with __fmul_rn/__fadd_rn/fmaf,
+ * so masks and arg-min indices are bit-exact between the two.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "robot_tables.h"
+
+#define MAXN 8
+#define MAXLINKS 16
+#define MAXSPH 64
+
+typedef struct {
+    int n, n_links, n_spheres, n_self;
+    const int *parent, *qidx;
+    const float (*T)[3];
+    const float (*R)[9];
+    const int *sph_link;
+    const float (*sph)[4];
+    const int (*self_pairs)[2];
+    float link0_floor;
+} Robot;
+
+static const Robot ROBOTS[2] = {
+    {PANDA_N, PANDA_NLINKS, PANDA_NSPHERES, PANDA_NSELFPAIRS, PANDA_PARENT, PANDA_QIDX, PANDA_T, PANDA_R,
+     PANDA_SPH_LINK, PANDA_SPH, PANDA_SELF_PAIRS, PANDA_LINK0_FLOOR_DIST},
+    {MAGICIAN_N, MAGICIAN_NLINKS, MAGICIAN_NSPHERES, MAGICIAN_NSELFPAIRS, MAGICIAN_PARENT, MAGICIAN_QIDX, MAGICIAN_T,
+     MAGICIAN_R, MAGICIAN_SPH_LINK, MAGICIAN_SPH, MAGICIAN_SELF_PAIRS, MAGICIAN_LINK0_FLOOR_DIST},
+};
+
+/* exemptions (same for both robots): arm_dynamics.py:180 (soft: links -1,0 vs floor) and
+ * arm_env.py:83-84 (hard: collision filter for links -1 and 1 vs plane) */
+static inline int soft_floor_exempt(int link) { return link == -1 || link == 0; }
+static inline int hard_floor_exempt(int link) { return link == -1 || link == 1; }
+
+/* ------------------------------------------------------------------ contract sincos */
+static inline void det_sincosf(float x, float *s_out, float *c_out) {
+    const float TWO_OVER_PI = 0.636619772f;
+    const float PIO2_HI = 1.57079637050628662109375f;
+    const float PIO2_LO = -4.37113900018624283e-8f;
+    float k = rintf(x * TWO_OVER_PI);
+    float r = fmaf(-k, PIO2_HI, x);
+    r = fmaf(-k, PIO2_LO, r);
+    float z = r * r;
+    /* sin(r) = r + r*z*(S1 + z*(S2 + z*S3)),  cos(r) = 1 + z*(-1/2 + z*(C1 + z*(C2 + z*C3))) on |r|<=pi/4 */
+    float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(z, sp, -1.6666654611e-1f);
+    sp = sp * z;
+    float s = fmaf(sp, r, r);
+    float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(z, cp, 4.166664568298827e-2f);
+    cp = fmaf(z, cp, -0.5f);
+    float c = fmaf(z, cp, 1.0f);
+    int n = ((int)k) & 3;
+    float so, co;
+    switch (n) {
+        case 0: so = s; co = c; break;
+        case 1: so = c; co = -s; break;
+        case 2: so = -s; co = -c; break;
+        default: so = -c; co = s; break;
+    }
+    *s_out = so;
+    *c_out = co;
+}
+
+/* ------------------------------------------------------------------ FK (contract order) */
+typedef struct {
+    float p[3];
+    float R[9]; /* row-major */
+} Frame;
+
+static void fk_chain(const Robot *rb, const float *q, Frame *fr /* [n_links] */) {
+    for (int i = 0; i < rb->n_links; ++i) {
+        float pp[3] = {0.f, 0.f, 0.f};
+        float Rp[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+        if (rb->parent[i] >= 0) {
+            memcpy(pp, fr[rb->parent[i]].p, sizeof pp);
+            memcpy(Rp, fr[rb->parent[i]].R, sizeof Rp);
+        }
+        const float *t = rb->T[i];
+        const float *F = rb->R[i];
+        Frame *o = &fr[i];
+        for (int r = 0; r < 3; ++r)
+            o->p[r] = fmaf(Rp[3 * r + 2], t[2], fmaf(Rp[3 * r + 1], t[1], fmaf(Rp[3 * r + 0], t[0], pp[r])));
+        float A[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                A[3 * r + c] = fmaf(Rp[3 * r + 2], F[6 + c], fmaf(Rp[3 * r + 1], F[3 + c], Rp[3 * r + 0] * F[c]));
+        if (rb->qidx[i] >= 0) {
+            float s, c;
+            det_sincosf(q[rb->qidx[i]], &s, &c);
+            for (int r = 0; r < 3; ++r) {
+                float a0 = A[3 * r + 0], a1 = A[3 * r + 1];
+                o->R[3 * r + 0] = fmaf(a1, s, a0 * c);
+                o->R[3 * r + 1] = fmaf(a1, c, -(a0 * s));
+                o->R[3 * r + 2] = A[3 * r + 2];
+            }
+        } else {
+            memcpy(o->R, A, sizeof A);
+        }
+    }
+}
+
+static inline void sphere_centre(const Robot *rb, const Frame *fr, int i, float *C) {
+    int link = rb->sph_link[i];
+    const float *c = rb->sph[i];
+    if (link < 0) { /* base frame = identity at the origin: centre is the table value */
+        C[0] = c[0]; C[1] = c[1]; C[2] = c[2];
+        return;
+    }
+    const Frame *f = &fr[link];
+    for (int r = 0; r < 3; ++r)
+        C[r] = fmaf(f->R[3 * r + 2], c[2], fmaf(f->R[3 * r + 1], c[1], fmaf(f->R[3 * r + 0], c[0], f->p[r])));
+}
+
+/* ------------------------------------------------------------------ pair distances (contract order) */
+static inline float sd_box(const float *C, const float *b /* cx cy cz hx hy hz */, float r) {
+    float dx = C[0] - b[0], dy = C[1] - b[1], dz = C[2] - b[2];
+    float ax = fabsf(dx) - b[3], ay = fabsf(dy) - b[4], az = fabsf(dz) - b[5];
+    float qx = fmaxf(ax, 0.f), qy = fmaxf(ay, 0.f), qz = fmaxf(az, 0.f);
+    float dsq = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
+    float mi = fminf(fmaxf(ax, fmaxf(ay, az)), 0.f);
+    return (sqrtf(dsq) + mi) - r;
+}
+
+static inline void normal_box(const float *C, const float *b, float *n) {
+    float dx = C[0] - b[0], dy = C[1] - b[1], dz = C[2] - b[2];
+    float ax = fabsf(dx) - b[3], ay = fabsf(dy) - b[4], az = fabsf(dz) - b[5];
+    float qx = fmaxf(ax, 0.f), qy = fmaxf(ay, 0.f), qz = fmaxf(az, 0.f);
+    float dsq = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
+    if (dsq > 0.f) {
+        float d = sqrtf(dsq);
+        n[0] = copysignf(qx, dx) / d;
+        n[1] = copysignf(qy, dy) / d;
+        n[2] = copysignf(qz, dz) / d;
+    } else {
+        n[0] = n[1] = n[2] = 0.f;
+        if (ax >= ay && ax >= az) n[0] = copysignf(1.f, dx);
+        else if (ay >= az) n[1] = copysignf(1.f, dy);
+        else n[2] = copysignf(1.f, dz);
+    }
+}
+
+static inline float sd_sphere(const float *C, const float *s /* cx cy cz r */, float r) {
+    float dx = C[0] - s[0], dy = C[1] - s[1], dz = C[2] - s[2];
+    float dsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return (sqrtf(dsq) - s[3]) - r;
+}
+
+static inline void normal_sphere(const float *C, const float *s, float *n) {
+    float dx = C[0] - s[0], dy = C[1] - s[1], dz = C[2] - s[2];
+    float dsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (dsq > 0.f) {
+        float d = sqrtf(dsq);
+        n[0] = dx / d; n[1] = dy / d; n[2] = dz / d;
+    } else {
+        n[0] = 0.f; n[1] = 0.f; n[2] = 1.f;
+    }
+}
+
+typedef struct {
+    int n_boxes, n_spheres, floor;
+    const float *boxes;   /* [n_boxes, 8]: cx cy cz hx hy hz 0 0  (device layout, see include/cbfrrt.h) */
+    const float *spheres; /* [n_spheres, 4]: cx cy cz r */
+} Scene;
+
+typedef struct {
+    uint8_t safe, unsafe;
+    float o, self_min, soft_min, hard_min;
+    int arg_link, arg_obs, arg_sphere;
+    float dodq[MAXN];
+} CollideOut;
+
+/* One state: masks + observation + gradient.  Iteration order (sphere-major; floor, boxes, spheres) with
+ * strict '<' defines the arg-min tie-break: lowest (sphere, obstacle) index wins. */
+static void collide_state(const Robot *rb, const Scene *sc, const float *q, float thr_soft, float thr_hard,
+                          CollideOut *out) {
+    Frame fr[MAXLINKS];
+    float C[MAXSPH][3];
+    fk_chain(rb, q, fr);
+    for (int i = 0; i < rb->n_spheres; ++i) sphere_centre(rb, fr, i, C[i]);
+
+    const int off = sc->floor ? 1 : 0;
+    float o = INFINITY, soft = INFINITY, hard = INFINITY;
+    int arg_s = -1, arg_o = -1;
+    int prev_link = -2;
+    for (int i = 0; i < rb->n_spheres; ++i) {
+        int link = rb->sph_link[i];
+        float r = rb->sph[i][3];
+        int first_of_link = (link != prev_link);
+        prev_link = link;
+        if (sc->floor) {
+            int have = 1;
+            float d;
+            if (link == 0) { /* kinematic constant, attached to the link's first sphere (spec floor_const) */
+                have = first_of_link;
+                d = rb->link0_floor;
+            } else {
+                d = C[i][2] - r;
+            }
+            if (have) {
+                if (link >= 0 && d < o) { o = d; arg_s = i; arg_o = 0; }
+                if (!soft_floor_exempt(link) && d < soft) soft = d;
+                if (!hard_floor_exempt(link) && d < hard) hard = d;
+            }
+        }
+        for (int j = 0; j < sc->n_boxes; ++j) {
+            float d = sd_box(C[i], sc->boxes + 8 * j, r);
+            if (link >= 0 && d < o) { o = d; arg_s = i; arg_o = off + j; }
+            if (d < soft) soft = d;
+            if (d < hard) hard = d;
+        }
+        for (int j = 0; j < sc->n_spheres; ++j) {
+            float d = sd_sphere(C[i], sc->spheres + 4 * j, r);
+            if (link >= 0 && d < o) { o = d; arg_s = i; arg_o = off + sc->n_boxes + j; }
+            if (d < soft) soft = d;
+            if (d < hard) hard = d;
+        }
+    }
+    /* self collision, basic_robot.py:89-98 (threshold 0.01) */
+    float self_min = INFINITY;
+    for (int p = 0; p < rb->n_self; ++p) {
+        int a = rb->self_pairs[p][0], b = rb->self_pairs[p][1];
+        for (int i = 0; i < rb->n_spheres; ++i) {
+            if (rb->sph_link[i] != a) continue;
+            for (int j = 0; j < rb->n_spheres; ++j) {
+                if (rb->sph_link[j] != b) continue;
+                float dx = C[i][0] - C[j][0], dy = C[i][1] - C[j][1], dz = C[i][2] - C[j][2];
+                float dsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                float d = (sqrtf(dsq) - rb->sph[i][3]) - rb->sph[j][3];
+                if (d < self_min) self_min = d;
+            }
+        }
+    }
+    out->unsafe = (uint8_t)(hard <= thr_hard);
+    out->safe = (uint8_t)((self_min > 0.01f) && (soft > thr_soft) && !(hard <= thr_hard));
+    out->o = o;
+    out->self_min = self_min;
+    out->soft_min = soft;
+    out->hard_min = hard;
+    out->arg_sphere = arg_s;
+    out->arg_obs = arg_o;
+    out->arg_link = arg_s >= 0 ? rb->sph_link[arg_s] : -2;
+    for (int k = 0; k < rb->n; ++k) out->dodq[k] = 0.f;
+    if (arg_s < 0) return;
+    /* gradient: n^T J_lin(link, closest point)[:, body_joints] (arm_mindis.py:56-69); for a sphere the r*n
+     * offset of the surface point is orthogonal to z x n, so the centre gives the same value. */
+    float nrm[3];
+    if (sc->floor && arg_o == 0) { nrm[0] = 0.f; nrm[1] = 0.f; nrm[2] = 1.f; }
+    else if (arg_o - off < sc->n_boxes) normal_box(C[arg_s], sc->boxes + 8 * (arg_o - off), nrm);
+    else normal_sphere(C[arg_s], sc->spheres + 4 * (arg_o - off - sc->n_boxes), nrm);
+    for (int l = out->arg_link; l >= 0; l = rb->parent[l]) {
+        int qi = rb->qidx[l];
+        if (qi < 0) continue;
+        const Frame *f = &fr[l];
+        float zx = f->R[2], zy = f->R[5], zz = f->R[8];
+        float rx = C[arg_s][0] - f->p[0], ry = C[arg_s][1] - f->p[1], rz = C[arg_s][2] - f->p[2];
+        float cx = fmaf(zy, rz, -(zz * ry));
+        float cy = fmaf(zz, rx, -(zx * rz));
+        float cz = fmaf(zx, ry, -(zy * rx));
+        out->dodq[qi] = fmaf(nrm[2], cz, fmaf(nrm[1], cy, nrm[0] * cx));
+    }
+}
+
+/* ------------------------------------------------------------------ barrier MLP + Jacobian (fp32, tolerance-checked)
+ * Packed weights (include/cbfrrt.h "CBF weight packing"): IN_PAD = round_up(n+1,4), H hidden, L hidden->hidden
+ * layers: [W_in H x IN_PAD][b_in H] { [W_l H x H][b_l H] } x L [w_out H][b_out 1 (+3 pad)] */
+typedef struct {
+    int n_in, hidden, layers;
+    const float *w;
+} Net;
+
+#define MAXH 128
+#define MAXL 4
+
+static void mlp_h_jac(const Net *net, const float *x /* n_in */, float *h_out, float *jac /* n_in */) {
+    const int H = net->hidden, L = net->layers, IN = net->n_in, INP = (IN + 3) & ~3;
+    float act[MAXL + 1][MAXH];
+    const float *w = net->w;
+    const float *W = w, *b = w + H * INP;
+    for (int j = 0; j < H; ++j) {
+        float a = b[j];
+        for (int k = 0; k < IN; ++k) a = fmaf(W[j * INP + k], x[k], a);
+        act[0][j] = a > 0.f ? a : 0.f;
+    }
+    const float *wl = w + H * INP + H;
+    for (int l = 0; l < L; ++l) {
+        const float *Wl = wl + (size_t)l * (H * H + H), *bl = Wl + H * H;
+        for (int j = 0; j < H; ++j) {
+            float a = bl[j];
+            for (int k = 0; k < H; ++k) a = fmaf(Wl[j * H + k], act[l][k], a);
+            act[l + 1][j] = a > 0.f ? a : 0.f;
+        }
+    }
+    const float *wo = wl + (size_t)L * (H * H + H), *bo = wo + H;
+    float h = bo[0];
+    for (int k = 0; k < H; ++k) h = fmaf(wo[k], act[L][k], h);
+    *h_out = h;
+    /* reverse mode with the ReLU masks (== autograd, neural_mindis_cbf_controller.py:93-96) */
+    float g[MAXH], gp[MAXH];
+    for (int k = 0; k < H; ++k) g[k] = act[L][k] > 0.f ? wo[k] : 0.f;
+    for (int l = L - 1; l >= 0; --l) {
+        const float *Wl = wl + (size_t)l * (H * H + H);
+        for (int k = 0; k < H; ++k) gp[k] = 0.f;
+        for (int j = 0; j < H; ++j)
+            for (int k = 0; k < H; ++k) gp[k] = fmaf(Wl[j * H + k], g[j], gp[k]);
+        for (int k = 0; k < H; ++k) g[k] = act[l][k] > 0.f ? gp[k] : 0.f;
+    }
+    for (int k = 0; k < IN; ++k) {
+        float a = 0.f;
+        for (int j = 0; j < H; ++j) a = fmaf(W[j * INP + k], g[j], a);
+        jac[k] = a;
+    }
+}
+
+/* ------------------------------------------------------------------ exact single-constraint CBF-QP (double)
+ *   min ||u-u_ref||^2 + p r   s.t.  c + a.u - r <= 0, r >= 0, lo <= u <= hi      (clf_controller.py:82-139)
+ * KKT: u(mu) = clip(u_ref - mu a / 2, lo, hi), 0 <= mu <= p; g(mu) = c + a.u(mu) is non-increasing and
+ * piecewise linear.  mu = 0 if g(0) <= 0; else the root of g on (0,p]; if g(p) > 0: mu = p, r = g(p). */
+static double qp_g(int n, const double *a, const double *uref, const double *lo, const double *hi, double c,
+                   double mu, double *u) {
+    double g = c;
+    for (int i = 0; i < n; ++i) {
+        double v = uref[i] - 0.5 * mu * a[i];
+        v = v < lo[i] ? lo[i] : (v > hi[i] ? hi[i] : v);
+        if (u) u[i] = v;
+        g += a[i] * v;
+    }
+    return g;
+}
+
+static void qp_exact(int n, const double *a, const double *uref_in, const double *lo, const double *hi, double c,
+                     double p, double *u, double *r_out) {
+    double uref[MAXN];
+    for (int i = 0; i < n; ++i) uref[i] = uref_in[i];
+    double g0 = qp_g(n, a, uref, lo, hi, c, 0.0, u);
+    *r_out = 0.0;
+    if (g0 <= 0.0) return;
+    /* breakpoints of u(mu) */
+    double bp[MAXN + 2];
+    int nb = 0;
+    bp[nb++] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double m = -1.0;
+        if (a[i] > 0.0) m = 2.0 * (uref[i] - lo[i]) / a[i];
+        else if (a[i] < 0.0) m = 2.0 * (uref[i] - hi[i]) / a[i];
+        if (m > 0.0 && m < p) bp[nb++] = m;
+    }
+    bp[nb++] = p;
+    for (int i = 1; i < nb; ++i) { /* insertion sort */
+        double v = bp[i];
+        int j = i - 1;
+        while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; --j; }
+        bp[j + 1] = v;
+    }
+    double mu_lo = 0.0, g_lo = g0;
+    for (int k = 1; k < nb; ++k) {
+        double g_hi = qp_g(n, a, uref, lo, hi, c, bp[k], 0);
+        if (g_hi <= 0.0) {
+            double mu = bp[k];
+            if (g_lo > g_hi) mu = mu_lo + (bp[k] - mu_lo) * (g_lo / (g_lo - g_hi));
+            qp_g(n, a, uref, lo, hi, c, mu, u);
+            return;
+        }
+        mu_lo = bp[k];
+        g_lo = g_hi;
+    }
+    *r_out = qp_g(n, a, uref, lo, hi, c, p, u); /* constraint relaxed: mu = p */
+}
+
+/* ------------------------------------------------------------------ exported batch API (ctypes) */
+/* ------------------------------------------------------------------ tiny pthread parallel-for (no libgomp here) */
+#include <pthread.h>
+static int g_threads = 1;
+typedef void (*range_fn)(long lo, long hi, void *ctx);
+typedef struct { range_fn fn; void *ctx; long lo, hi; } Job;
+static void *job_main(void *p) { Job *j = (Job *)p; j->fn(j->lo, j->hi, j->ctx); return 0; }
+static void par_for(long B, range_fn fn, void *ctx) {
+    int T = g_threads;
+    if (T > B) T = (int)(B > 0 ? B : 1);
+    if (T <= 1) { fn(0, B, ctx); return; }
+    pthread_t th[256]; Job jobs[256];
+    if (T > 256) T = 256;
+    long chunk = (B + T - 1) / T;
+    for (int t = 0; t < T; ++t) {
+        long lo = t * chunk, hi = lo + chunk < B ? lo + chunk : B;
+        if (lo > hi) lo = hi;
+        jobs[t] = (Job){fn, ctx, lo, hi};
+        pthread_create(&th[t], 0, job_main, &jobs[t]);
+    }
+    for (int t = 0; t < T; ++t) pthread_join(th[t], 0);
+}
+/* the range workers are cloned for FMA-capable CPUs (fmaf -> vfmadd; same correctly-rounded result) */
+#define CLONES __attribute__((target_clones("default", "fma"), flatten))
+#define API __attribute__((visibility("default")))
+API void oracle_set_threads(int t) { g_threads = t < 1 ? 1 : t; }
+
+API int oracle_robot_info(int robot, int *n, int *n_links, int *n_spheres) {
+    if (robot < 0 || robot > 1) return -1;
+    *n = ROBOTS[robot].n; *n_links = ROBOTS[robot].n_links; *n_spheres = ROBOTS[robot].n_spheres;
+    return 0;
+}
+
+API void oracle_sincos(const float *x, long B, float *s, float *c) {
+    for (long i = 0; i < B; ++i) det_sincosf(x[i], &s[i], &c[i]);
+}
+
+/* one context struct for every batch entry point (unused fields stay 0) */
+typedef struct {
+    const Robot *rb; Scene sc; Net net; int n;
+    const float *q, *q2, *goal, *K, *u_lo, *u_hi, *datax_in, *u_ref;
+    long q_stride, goal_rows;
+    float thr_soft, thr_hard, lam, penalty, dt;
+    int Kint, steps, ctrl_every, stuck_lag, stuck_after;
+    float stuck_eps, *traj;
+    uint8_t *safe, *unsafe, *alive;
+    float *datax, *h, *J, *u, *r, *mins, *pos, *rot, *q_final;
+    int *arg_link, *arg_obs, *first_bad, *steps_done;
+} Ctx;
+
+/* FK: pos [B, L, 3], rot [B, L, 9] for L = n_links pybullet links (basic_robot.py:55-62) */
+CLONES static void fk_range(long lo, long hi, void *p) {
+    Ctx *c = (Ctx *)p; const Robot *rb = c->rb;
+    for (long b = lo; b < hi; ++b) {
+        Frame fr[MAXLINKS];
+        fk_chain(rb, c->q + b * c->q_stride, fr);
+        for (int l = 0; l < rb->n_links; ++l) {
+            memcpy(c->pos + (b * rb->n_links + l) * 3, fr[l].p, 12);
+            memcpy(c->rot + (b * rb->n_links + l) * 9, fr[l].R, 36);
+        }
+    }
+}
+API int oracle_fk(int robot, const float *q, long q_stride, long B, float *pos, float *rot) {
+    Ctx c; memset(&c, 0, sizeof c);
+    c.rb = &ROBOTS[robot]; c.q = q; c.q_stride = q_stride; c.pos = pos; c.rot = rot;
+    par_for(B, fk_range, &c);
+    return 0;
+}
+
+/* collide: masks (arm_dynamics.py:189-232), observation + gradient packed as datax = [q | o | do/dq]
+ * (arm_dynamics.py:267-279), plus the arg-min pair and the three minima for diagnostics. */
+CLONES static void collide_range(long lo, long hi, void *p) {
+    Ctx *c = (Ctx *)p; const int n = c->n;
+    for (long b = lo; b < hi; ++b) {
+        CollideOut co;
+        const float *q = c->q + b * c->q_stride;
+        collide_state(c->rb, &c->sc, q, c->thr_soft, c->thr_hard, &co);
+        if (c->safe) c->safe[b] = co.safe;
+        if (c->unsafe) c->unsafe[b] = co.unsafe;
+        if (c->datax) {
+            float *d = c->datax + b * (2 * n + 1);
+            for (int k = 0; k < n; ++k) d[k] = q[k];
+            d[n] = co.o;
+            for (int k = 0; k < n; ++k) d[n + 1 + k] = co.dodq[k];
+        }
+        if (c->arg_link) c->arg_link[b] = co.arg_link;
+        if (c->arg_obs) c->arg_obs[b] = co.arg_obs;
+        if (c->mins) { c->mins[3 * b] = co.self_min; c->mins[3 * b + 1] = co.soft_min; c->mins[3 * b + 2] = co.hard_min; }
+    }
+}
+API int oracle_collide(int robot, int n_boxes, const float *boxes, int n_sph, const float *spheres, int floor,
+                       const float *q, long q_stride, long B, float thr_soft, float thr_hard, uint8_t *safe,
+                       uint8_t *unsafe, float *datax, int *arg_link, int *arg_obs, float *mins /* [B,3] or NULL */) {
+    Ctx c; memset(&c, 0, sizeof c);
+    c.rb = &ROBOTS[robot]; c.n = c.rb->n; c.sc = (Scene){n_boxes, n_sph, floor, boxes, spheres};
+    c.q = q; c.q_stride = q_stride; c.thr_soft = thr_soft; c.thr_hard = thr_hard;
+    c.safe = safe; c.unsafe = unsafe; c.datax = datax; c.arg_link = arg_link; c.arg_obs = arg_obs; c.mins = mins;
+    par_for(B, collide_range, &c);
+    return 0;
+}
+
+/* cbf_filter: datax [B, 2n+1] -> h, J (bs x n), u, r    (controller.u)
+ *   goal [goal_rows, n] with goal_rows in {1, B}; K [n, n]; u_lo/u_hi [n] */
+static void filter_state(int n, const Net *net, const float *d, const float *goal, const float *uref_in, const float *K,
+                         const float *u_lo, const float *u_hi, float lam, float penalty, float *h_out, float *J,
+                         float *u, float *r) {
+    float x[MAXN + 1], jac[MAXN + 1], h;
+    for (int k = 0; k <= n; ++k) x[k] = d[k];
+    mlp_h_jac(net, x, &h, jac);
+    /* J = Jh_q + Jh_o * do/dq   (neural_mindis_cbf_controller.py:99-101) */
+    double a[MAXN], uref[MAXN], lo[MAXN], hi[MAXN], ud[MAXN], rd;
+    for (int k = 0; k < n; ++k) {
+        float j = fmaf(jac[n], d[n + 1 + k], jac[k]);
+        J[k] = j;
+        a[k] = (double)j; /* Lg_V = J g = J  (g = I), Lf_V = 0 */
+    }
+    /* u_ref = clamp(-K (q - goal), lo, hi)   (arm_dynamics.py:124-161) */
+    for (int i = 0; i < n; ++i) {
+        float v;
+        if (uref_in) { /* solve_CLF_QP(u_ref=...) bypasses the nominal controller, clf_controller.py:497-504 */
+            v = uref_in[i];
+        } else {
+            float acc = 0.f;
+            for (int k = 0; k < n; ++k) acc = fmaf(K[i * n + k], d[k] - goal[k], acc);
+            v = -acc;
+            v = v < u_lo[i] ? u_lo[i] : (v > u_hi[i] ? u_hi[i] : v);
+        }
+        uref[i] = (double)v; lo[i] = (double)u_lo[i]; hi[i] = (double)u_hi[i];
+    }
+    double p = penalty < 1e6f ? (double)penalty : 1e6; /* clf_controller.py:380 */
+    qp_exact(n, a, uref, lo, hi, (double)lam * (double)h, p, ud, &rd);
+    *h_out = h;
+    for (int k = 0; k < n; ++k) u[k] = (float)ud[k];
+    *r = (float)rd;
+}
+
+CLONES static void filter_range(long lo, long hi, void *p) {
+    Ctx *c = (Ctx *)p; const int n = c->n;
+    for (long b = lo; b < hi; ++b) {
+        const float *g = c->goal ? c->goal + (c->goal_rows == 1 ? 0 : b * n) : 0;
+        filter_state(n, &c->net, c->datax_in + b * (2 * n + 1), g, c->u_ref ? c->u_ref + b * n : 0, c->K, c->u_lo,
+                     c->u_hi, c->lam, c->penalty, c->h + b, c->J + b * n, c->u + b * n, c->r + b);
+    }
+}
+API int oracle_cbf_filter(int n, int hidden, int layers, const float *weights, const float *datax, long B,
+                          const float *goal, long goal_rows, const float *u_ref, const float *K, const float *u_lo,
+                          const float *u_hi, float lam, float penalty, float *h, float *J, float *u, float *r) {
+    if (hidden > MAXH || layers > MAXL || n > MAXN) return -1;
+    Ctx c; memset(&c, 0, sizeof c);
+    c.n = n; c.net = (Net){n + 1, hidden, layers, weights}; c.datax_in = datax; c.goal = goal; c.goal_rows = goal_rows;
+    c.u_ref = u_ref; c.K = K; c.u_lo = u_lo; c.u_hi = u_hi; c.lam = lam; c.penalty = penalty; c.h = h; c.J = J; c.u = u; c.r = r;
+    par_for(B, filter_range, &c);
+    return 0;
+}
+
+/* fused q -> everything (the "safety filter" of BASELINE configs 1, 2, 5) */
+CLONES static void safety_range(long lo, long hi, void *p) {
+    Ctx *c = (Ctx *)p; const int n = c->n;
+    for (long b = lo; b < hi; ++b) {
+        CollideOut co;
+        const float *q = c->q + b * c->q_stride;
+        collide_state(c->rb, &c->sc, q, c->thr_soft, c->thr_hard, &co);
+        float d[2 * MAXN + 1];
+        for (int k = 0; k < n; ++k) d[k] = q[k];
+        d[n] = co.o;
+        for (int k = 0; k < n; ++k) d[n + 1 + k] = co.dodq[k];
+        if (c->safe) c->safe[b] = co.safe;
+        if (c->unsafe) c->unsafe[b] = co.unsafe;
+        if (c->datax) memcpy(c->datax + b * (2 * n + 1), d, sizeof(float) * (2 * n + 1));
+        float hh, JJ[MAXN], uu[MAXN], rr;
+        const float *g = c->goal + (c->goal_rows == 1 ? 0 : b * n);
+        filter_state(n, &c->net, d, g, 0, c->K, c->u_lo, c->u_hi, c->lam, c->penalty, &hh, JJ, uu, &rr);
+        if (c->h) c->h[b] = hh;
+        if (c->J) memcpy(c->J + b * n, JJ, sizeof(float) * n);
+        if (c->u) memcpy(c->u + b * n, uu, sizeof(float) * n);
+        if (c->r) c->r[b] = rr;
+    }
+}
+API int oracle_safety_filter(int robot, int n_boxes, const float *boxes, int n_sph, const float *spheres, int floor,
+                             int hidden, int layers, const float *weights, const float *q, long q_stride, long B,
+                             const float *goal, long goal_rows, const float *K, const float *u_lo, const float *u_hi,
+                             float thr_soft, float thr_hard, float lam, float penalty, uint8_t *safe, uint8_t *unsafe,
+                             float *datax, float *h, float *J, float *u, float *r) {
+    if (hidden > MAXH || layers > MAXL) return -1;
+    Ctx c; memset(&c, 0, sizeof c);
+    c.rb = &ROBOTS[robot]; c.n = c.rb->n; c.sc = (Scene){n_boxes, n_sph, floor, boxes, spheres};
+    c.net = (Net){c.n + 1, hidden, layers, weights};
+    c.q = q; c.q_stride = q_stride; c.goal = goal; c.goal_rows = goal_rows; c.K = K; c.u_lo = u_lo; c.u_hi = u_hi;
+    c.thr_soft = thr_soft; c.thr_hard = thr_hard; c.lam = lam; c.penalty = penalty;
+    c.safe = safe; c.unsafe = unsafe; c.datax = datax; c.h = h; c.J = J; c.u = u; c.r = r;
+    par_for(B, safety_range, &c);
+    return 0;
+}
+
+/* edge validity, tsa.py:272-286 with a fixed number K of interpolation points:
+ *   valid <=> safe(q_to) and safe(q_from + (k/K)(q_to - q_from)) for k = 0..K-1
+ * first_bad = smallest along-edge index that fails (k for interpolation points, K for the end point), -1 if valid.
+ * Interpolation contract: t = (float)k / (float)K (one division), c_i = fmaf(t, q_to_i - q_from_i, q_from_i). */
+CLONES static void edge_range(long lo, long hi, void *p) {
+    Ctx *c = (Ctx *)p; const int n = c->n, K = c->Kint;
+    for (long e = lo; e < hi; ++e) {
+        int bad = -1;
+        for (int k = 0; k <= K && bad < 0; ++k) {
+            float x[MAXN];
+            if (k == K) {
+                for (int i = 0; i < n; ++i) x[i] = c->q2[e * n + i];
+            } else {
+                float t = (float)k / (float)K;
+                for (int i = 0; i < n; ++i) x[i] = fmaf(t, c->q2[e * n + i] - c->q[e * n + i], c->q[e * n + i]);
+            }
+            CollideOut co;
+            collide_state(c->rb, &c->sc, x, c->thr_soft, c->thr_hard, &co);
+            if (!co.safe) bad = k;
+        }
+        c->safe[e] = (uint8_t)(bad < 0);
+        c->first_bad[e] = bad;
+    }
+}
+API int oracle_edge_validity(int robot, int n_boxes, const float *boxes, int n_sph, const float *spheres, int floor,
+                             const float *q_from, const float *q_to, long E, int K, float thr_soft, float thr_hard,
+                             uint8_t *valid, int *first_bad) {
+    Ctx c; memset(&c, 0, sizeof c);
+    c.rb = &ROBOTS[robot]; c.n = c.rb->n; c.sc = (Scene){n_boxes, n_sph, floor, boxes, spheres};
+    c.q = q_from; c.q2 = q_to; c.Kint = K; c.thr_soft = thr_soft; c.thr_hard = thr_hard; c.safe = valid;
+    c.first_bad = first_bad;
+    par_for(E, edge_range, &c);
+    return 0;
+}
+
+/* closed-loop rollout = the steer loop (tsa.py:217-269; eval_obs_only_env.py:121-148):
+ *   every ctrl_every-th step: u = CBF-QP(x);  every step: q' = q + u*dt (arm_dynamics.py:497-510), then the
+ *   unsafe check on q' (tsa.py:251: a colliding state is NOT appended, no_collision = False, loop ends);
+ *   the observation (o, do/dq) is refreshed when (t+1) % ctrl_every == 0 (tsa.py:242-245);
+ *   stuck test (tsa.py:263): stop when t > stuck_after and ||x_t - x_{t-stuck_lag}|| < stuck_eps.
+ * q_final = x_list[-1], alive = no_collision, steps_done = number of appended states, traj = x_list[1:]. */
+CLONES static void rollout_range(long lo, long hi, void *p) {
+    Ctx *c = (Ctx *)p; const int n = c->n;
+    for (long b = lo; b < hi; ++b) {
+        float d[2 * MAXN + 1], qn[MAXN], u[MAXN] = {0};
+        CollideOut co;
+        for (int k = 0; k < n; ++k) d[k] = c->q[b * n + k];
+        collide_state(c->rb, &c->sc, d, c->thr_soft, c->thr_hard, &co);
+        d[n] = co.o;
+        for (int k = 0; k < n; ++k) d[n + 1 + k] = co.dodq[k];
+        int ok = 1, done = 0;
+        float *tr = c->traj ? c->traj + b * (long)c->steps * n : 0;
+        for (int t = 0; t < c->steps; ++t) {
+            if (t % c->ctrl_every == 0) {
+                float hh, JJ[MAXN], rr;
+                const float *g = c->goal + (c->goal_rows == 1 ? 0 : b * n);
+                filter_state(n, &c->net, d, g, 0, c->K, c->u_lo, c->u_hi, c->lam, c->penalty, &hh, JJ, u, &rr);
+            }
+            for (int k = 0; k < n; ++k) qn[k] = fmaf(u[k], c->dt, d[k]);
+            collide_state(c->rb, &c->sc, qn, c->thr_soft, c->thr_hard, &co);
+            if ((t + 1) % c->ctrl_every == 0) {
+                d[n] = co.o;
+                for (int k = 0; k < n; ++k) d[n + 1 + k] = co.dodq[k];
+            }
+            if (co.unsafe) { ok = 0; break; }
+            for (int k = 0; k < n; ++k) d[k] = qn[k];
+            if (tr) for (int k = 0; k < n; ++k) tr[t * n + k] = d[k];
+            done = t + 1;
+            if (c->stuck_lag > 0 && t > c->stuck_after) {
+                const float *old = tr + (t - c->stuck_lag) * n;
+                float dsq = 0.f;
+                for (int k = 0; k < n; ++k) { float e = d[k] - old[k]; dsq = fmaf(e, e, dsq); }
+                if (sqrtf(dsq) < c->stuck_eps) break;
+            }
+        }
+        for (int k = 0; k < n; ++k) c->q_final[b * n + k] = d[k];
+        c->alive[b] = (uint8_t)ok;
+        c->steps_done[b] = done;
+    }
+}
+API int oracle_rollout(int robot, int n_boxes, const float *boxes, int n_sph, const float *spheres, int floor,
+                       int hidden, int layers, const float *weights, const float *q0, const float *goal, long goal_rows,
+                       long T, int steps, int ctrl_every, float dt, int stuck_lag, int stuck_after, float stuck_eps,
+                       const float *K, const float *u_lo, const float *u_hi, float thr_soft, float thr_hard, float lam,
+                       float penalty, float *q_final, uint8_t *alive, int *steps_done, float *traj) {
+    if (hidden > MAXH || layers > MAXL) return -1;
+    if (stuck_lag > 0 && !traj) return -1;
+    Ctx c; memset(&c, 0, sizeof c);
+    c.rb = &ROBOTS[robot]; c.n = c.rb->n; c.sc = (Scene){n_boxes, n_sph, floor, boxes, spheres};
+    c.net = (Net){c.n + 1, hidden, layers, weights};
+    c.q = q0; c.goal = goal; c.goal_rows = goal_rows; c.steps = steps; c.ctrl_every = ctrl_every; c.dt = dt;
+    c.stuck_lag = stuck_lag; c.stuck_after = stuck_after; c.stuck_eps = stuck_eps; c.traj = traj;
+    c.K = K; c.u_lo = u_lo; c.u_hi = u_hi; c.thr_soft = thr_soft; c.thr_hard = thr_hard; c.lam = lam; c.penalty = penalty;
+    c.q_final = q_final; c.alive = alive; c.steps_done = steps_done;
+    par_for(T, rollout_range, &c);
+    return 0;
+}
+
+/* counter-based state sampler (BASELINE config 5: results must not depend on the shard count):
+ *   x = hash(seed, global_row * n + j)  ->  u = (x >> 8) * 2^-24 in [0,1)  ->  q = fmaf(u, hi-lo, lo)
+ * hash = two rounds of the 32-bit "lowbias32" mix over (index ^ seed*0x9E3779B9). */
+static inline uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+API int oracle_sample_states(int robot, uint32_t seed, uint64_t start_row, long B, float *q) {
+    const Robot *rb = &ROBOTS[robot];
+    const float *lo = robot == 0 ? PANDA_QLO : MAGICIAN_QLO;
+    const float *hi = robot == 0 ? PANDA_QHI : MAGICIAN_QHI;
+    const int n = rb->n;
+    for (long b = 0; b < B; ++b)
+        for (int j = 0; j < n; ++j) {
+            uint64_t idx = (start_row + (uint64_t)b) * (uint64_t)n + (uint64_t)j;
+            uint32_t x = mix32((uint32_t)idx ^ (seed * 0x9E3779B9U));
+            x = mix32(x + (uint32_t)(idx >> 32) + 0x85ebca6bU);
+            float u = (float)(x >> 8) * 5.9604644775390625e-8f;
+            q[b * n + j] = fmaf(u, hi[j] - lo[j], lo[j]);
+        }
+    return 0;
+}

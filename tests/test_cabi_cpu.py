@@ -1,0 +1,79 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/cbfrrt.h declares, and validates arguments
+before touching CUDA (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "cbfrrt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cbfrrt_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cbfrrt import _lib
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in include/cbfrrt.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in cbfrrt/_lib.py"
+    assert _lib.lib.cbfrrt_abi_version() == 1
+
+
+def test_robot_info_and_status_strings():
+    from cbfrrt import _lib
+    assert _lib.robot_info("panda") == (7, 12, 32)
+    assert _lib.robot_info("magician") == (4, 4, 24)
+    n = C.c_int32()
+    assert _lib.lib.cbfrrt_robot_info(9, C.byref(n), C.byref(n), C.byref(n)) == -1
+    assert _lib.lib.cbfrrt_status_string(-3) == b"unsupported network shape or scene size"
+
+
+def test_argument_validation_happens_before_cuda():
+    from cbfrrt import _lib
+    lib = _lib.lib
+    sc = _lib.Scene(0, 0, 1, 0, None, None)
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    assert lib.cbfrrt_fk(5, p, 7, 1, p, p, None) == -1                                   # bad robot
+    assert lib.cbfrrt_fk(0, p, 7, -1, p, p, None) == -2                                  # negative batch
+    assert lib.cbfrrt_fk(0, p, 3, 1, p, p, None) == -2                                   # stride < n
+    assert lib.cbfrrt_collide(0, C.byref(sc), None, 7, 1, 0.02, 0.0, *([None] * 6), None) == -2
+    big = _lib.Scene(2000, 0, 1, 0, p, None)
+    assert lib.cbfrrt_collide(0, C.byref(big), p, 7, 1, 0.02, 0.0, *([None] * 6), None) == -3  # > MAX_OBSTACLES
+    mis = _lib.Scene(1, 0, 1, 0, C.c_void_p(p.value + 4), None)
+    assert lib.cbfrrt_collide(0, C.byref(mis), p, 7, 1, 0.02, 0.0, *([None] * 6), None) == -5  # alignment
+    net = _lib.CbfNet(8, 64, 2, 0, p)
+    fp = _lib.FilterParams(p, 1, p, p, p, 0.1, 5000.0, None)
+    assert lib.cbfrrt_cbf_filter(7, C.byref(net), p, 1, C.byref(fp), p, p, p, p, None) == -3   # hidden != 48
+    net = _lib.CbfNet(8, 48, 2, 0, p)
+    fp = _lib.FilterParams(p, 3, p, p, p, 0.1, 5000.0, None)
+    assert lib.cbfrrt_cbf_filter(7, C.byref(net), p, 5, C.byref(fp), p, p, p, p, None) == -2   # goal_rows not in {1,B}
+    assert lib.cbfrrt_qp(9, p, p, p, 1, p, p, 1.0, p, p, None) == -3
+    # B == 0 is a valid no-op everywhere
+    assert lib.cbfrrt_fk(0, p, 7, 0, p, p, None) == 0
+    assert lib.cbfrrt_collide(0, C.byref(sc), p, 7, 0, 0.02, 0.0, *([None] * 6), None) == 0
+
+
+def test_ops_refuse_cpu_tensors():
+    """CUDA-only registration: no CPU kernel exists, so the dispatcher must raise (no silent fallback)."""
+    import torch
+    from cbfrrt import ops
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.fk(torch.zeros(2, 7), 0)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.masks(torch.zeros(2, 7), torch.zeros(0, 8), torch.zeros(0, 4), 1, 0.02, 0.0, 0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cbf-inc-rrt_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "c_oracle" not in txt, os.path.join(dp, f)

@@ -1,0 +1,372 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C-ABI (torch custom ops are thin ctypes wrappers over
+include/cbfrrt.h), against the C oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): collision booleans and indices bit-exact; FK poses, barrier values, gradients
+and QP controls within 1e-5 relative (conftest.rel_err: |a-b| / max(|b|, natural scale))."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_state_dict, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda"
+
+
+def _t(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=DEV)
+
+
+def _scene(boxes6, spheres):
+    from cbfrrt import ops
+    boxes6 = np.zeros((0, 6), np.float32) if boxes6 is None else np.asarray(boxes6, np.float32).reshape(-1, 6)
+    return ops.pack_scene(boxes6[:, :3], boxes6[:, 3:], spheres, device=DEV)
+
+
+def _net(w):
+    from cbfrrt import ops
+    sd = w["state_dict"]
+    return ops.pack_weights(sd, w["n"], w["hidden"], w["layers"], device=DEV)
+
+
+SCENES = {
+    "default3": (np.array([[0.3, 0.17, 0.3, 0.05, 0.05, 0.1], [-0.4, 0.23, 0.4, 0.05, 0.05, 0.1],
+                           [0.0, -0.23, 0.6, 0.05, 0.05, 0.1]], np.float32), None, True),
+    "mixed": (None, None, True),  # filled in below from workloads
+    "empty_floor": (None, None, True),
+    "empty_nofloor": (None, None, False),
+    "spheres_only_nofloor": (None, np.array([[0.3, -0.3, 0.5, 0.1], [0.0, 0.4, 0.7, 0.15]], np.float32), False),
+}
+
+
+def _get_scene(name):
+    from cbfrrt import workloads as W
+    if name == "mixed":
+        return W.random_boxes(21, 2, 0.02, 0.1), W.random_spheres(13, 5, 0.02, 0.1), True
+    return SCENES[name]
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_fk_matches_oracle(coracle, robot):
+    from cbfrrt import ops, workloads as W
+    q = W.sample_states(robot, 5000, 3)
+    pos, rot = ops.fk(_t(q), ops.ROBOT_ID[robot])
+    pos_o, rot_o = coracle.fk(robot, q)
+    assert rel_err(pos.cpu().numpy(), pos_o) < TOL and rel_err(rot.cpu().numpy(), rot_o) < TOL
+    # the deterministic-math contract makes FK bit-identical, not merely close
+    assert np.array_equal(pos.cpu().numpy(), pos_o) and np.array_equal(rot.cpu().numpy(), rot_o)
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+@pytest.mark.parametrize("scene", list(SCENES))
+@pytest.mark.parametrize("B", [1, 127, 4096])
+def test_collide_bit_exact(coracle, robot, scene, B):
+    from cbfrrt import ops, workloads as W
+    boxes, sph, floor = _get_scene(scene)
+    q = W.sample_states(robot, B, 17 + B)
+    b8, s4 = _scene(boxes, sph)
+    safe, unsafe, datax, arg_link, arg_obs, mins = ops.collide(_t(q), b8, s4, int(floor), 0.02, 0.0, ops.ROBOT_ID[robot])
+    o = coracle.collide(robot, q, boxes, sph, floor, 0.02, 0.0)
+    n = q.shape[1]
+    assert np.array_equal(safe.cpu().numpy(), o["safe"]) and np.array_equal(unsafe.cpu().numpy(), o["unsafe"])
+    assert np.array_equal(arg_link.cpu().numpy(), o["arg_link"]) and np.array_equal(arg_obs.cpu().numpy(), o["arg_obs"])
+    d = datax.cpu().numpy()
+    assert np.array_equal(d[:, :n + 1], o["datax"][:, :n + 1])          # q and the observation o: bit-exact
+    assert rel_err(d[:, n + 1:], o["datax"][:, n + 1:]) < TOL          # do/dq
+    assert np.array_equal(mins.cpu().numpy(), o["mins"])
+    # the mask-only and observation-only instantiations agree with the full one
+    s2, u2 = ops.masks(_t(q), b8, s4, int(floor), 0.02, 0.0, ops.ROBOT_ID[robot])
+    s3, u3, d3 = ops.observe(_t(q), b8, s4, int(floor), 0.02, 0.0, ops.ROBOT_ID[robot])
+    assert torch.equal(s2, safe) and torch.equal(u2, unsafe) and torch.equal(s3, safe) and torch.equal(d3, datax)
+
+
+def test_collide_thresholds_and_strided_rows(coracle):
+    from cbfrrt import ops, workloads as W
+    boxes, sph, floor = _get_scene("mixed")
+    q = W.sample_states("panda", 3000, 1)
+    b8, s4 = _scene(boxes, sph)
+    wide = torch.zeros(3000, 15, device=DEV)
+    wide[:, :7] = _t(q)
+    for ts, th in ((0.05, 0.0), (0.02, 0.02), (0.0, -0.01)):
+        s, u = ops.masks(wide[:, :7], b8, s4, 1, ts, th, 0)   # x[:, :q_dims] view: row stride 15, no copy
+        o = coracle.collide("panda", q, boxes, sph, True, ts, th)
+        assert np.array_equal(s.cpu().numpy(), o["safe"]) and np.array_equal(u.cpu().numpy(), o["unsafe"])
+
+
+def test_collide_many_obstacles_and_limit(coracle):
+    from cbfrrt import ops, workloads as W
+    from cbfrrt._lib import CbfrrtError
+    q = W.sample_states("panda", 2048, 9)
+    boxes, sph = W.random_boxes(700, 2, 0.01, 0.04), W.random_spheres(324, 5, 0.01, 0.04)   # 1024 = the maximum
+    b8, s4 = _scene(boxes, sph)
+    safe, unsafe, datax, al, ao, mins = ops.collide(_t(q), b8, s4, 1, 0.02, 0.0, 0)
+    o = coracle.collide("panda", q, boxes, sph, True, 0.02, 0.0)
+    assert np.array_equal(safe.cpu().numpy(), o["safe"]) and np.array_equal(ao.cpu().numpy(), o["arg_obs"])
+    assert np.array_equal(datax.cpu().numpy()[:, 7], o["datax"][:, 7])
+    b8big, _ = _scene(W.random_boxes(1025, 2, 0.01, 0.02), None)
+    with pytest.raises(CbfrrtError):
+        ops.masks(_t(q), b8big, s4[:0], 1, 0.02, 0.0, 0)
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_cbf_filter_matches_reference_python_golden(golden, robot):
+    """CUDA h / J / u / r against the vectors produced by the reference's own Python."""
+    from cbfrrt import ops
+    g = golden[robot]
+    n = g["datax"].shape[1] // 2
+    W = ops.pack_weights(golden_state_dict(g), n, 48, 2, device=DEV)
+    for tag in ("shared", "rows"):
+        h, J, u, r = ops.cbf_filter(_t(g["datax"]), _t(g[f"{tag}_goal"]), W, _t(g["K"]), _t(g["u_lower"]),
+                                    _t(g["u_upper"]), float(g["lam"]), float(g["penalty"]), 48, 2,
+                                    torch.empty(0, device=DEV))
+        assert rel_err(h.cpu().numpy(), g[f"{tag}_h"][:, 0], floor=0.1) < TOL
+        assert rel_err(J.cpu().numpy(), g[f"{tag}_J"][:, 0], floor=0.1) < TOL
+        assert rel_err(u.cpu().numpy(), g[f"{tag}_u"]) < TOL
+        assert np.abs(r.cpu().numpy() - g[f"{tag}_r"][:, 0]).max() < TOL
+    h, J, u, r = ops.cbf_filter(_t(g["datax"]), _t(g["shared_goal"]), W, _t(g["K"]), _t(g["u_lower"]), _t(g["u_upper"]),
+                                float(g["lam"]), 0.05, 48, 2, torch.empty(0, device=DEV))
+    assert rel_err(u.cpu().numpy(), g["shared_u_pen0.05"]) < TOL
+    assert rel_err(r.cpu().numpy(), g["shared_r_pen0.05"][:, 0], floor=0.1) < TOL
+
+
+@pytest.mark.parametrize("robot,B", [("panda", 4096), ("magician", 10007)])
+def test_cbf_filter_matches_oracle(coracle, robot, B):
+    from cbfrrt import ops, workloads as W
+    w = W.config(0 if robot == "panda" else 1, scale=0.001)
+    n = w["n"]
+    rng = np.random.default_rng(4)
+    datax = np.concatenate([W.sample_states(robot, B, 2), rng.uniform(-0.1, 0.3, (B, 1)).astype(np.float32),
+                            (3 * rng.normal(size=(B, n))).astype(np.float32)], 1)
+    goal = W.sample_states(robot, B, 8)
+    for goal_np, pen, lam in ((goal, 5000.0, 1.0), (goal[:1], 0.5, 1.0), (goal, 50.0, 0.1)):
+        h, J, u, r = ops.cbf_filter(_t(datax), _t(goal_np), _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), lam, pen,
+                                    48, 2, torch.empty(0, device=DEV))
+        o = coracle.cbf_filter(n, w["weights"], 48, 2, datax, goal_np, w["K"], w["u_lo"], w["u_hi"], lam, pen)
+        assert rel_err(h.cpu().numpy(), o["h"], floor=0.1) < TOL and rel_err(J.cpu().numpy(), o["J"], floor=0.1) < TOL
+        assert rel_err(u.cpu().numpy(), o["u"]) < TOL and rel_err(r.cpu().numpy(), o["r"], floor=0.1) < TOL
+        assert (np.abs(o["u"] - np.clip(-(datax[:, :n] - goal_np) @ w["K"].T, w["u_lo"], w["u_hi"])).max(1) > 1e-4).sum() > B // 20
+    # caller-supplied u_ref (solve_CLF_QP(u_ref=...))
+    uref = rng.uniform(-1, 1, (B, n)).astype(np.float32)
+    h, J, u, r = ops.cbf_filter(_t(datax), _t(goal[:1]), _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), 1.0, 5000.0,
+                                48, 2, _t(uref))
+    o = coracle.cbf_filter(n, w["weights"], 48, 2, datax, goal[:1], w["K"], w["u_lo"], w["u_hi"], 1.0, 5000.0, u_ref=uref)
+    assert rel_err(u.cpu().numpy(), o["u"]) < TOL
+
+
+def test_qp_op_matches_oracle_semantics(coracle):
+    """cbfrrt::qp (generic CLFController path) on the QP data of the fused filter gives the same controls."""
+    from cbfrrt import ops, workloads as W
+    w = W.config(0, scale=0.001)
+    B, n = 5000, 7
+    rng = np.random.default_rng(6)
+    datax = np.concatenate([W.sample_states("panda", B, 2), rng.uniform(-0.1, 0.3, (B, 1)).astype(np.float32),
+                            (3 * rng.normal(size=(B, n))).astype(np.float32)], 1)
+    o = coracle.cbf_filter(n, w["weights"], 48, 2, datax, w["goal"], w["K"], w["u_lo"], w["u_hi"], 1.0, 50.0)
+    uref = np.clip(-(datax[:, :n] - w["goal"]) @ w["K"].T, w["u_lo"], w["u_hi"]).astype(np.float32)
+    u, r = ops.qp(_t(o["J"]), _t(1.0 * o["h"]), _t(uref), _t(w["u_lo"]), _t(w["u_hi"]), 50.0)
+    assert rel_err(u.cpu().numpy(), o["u"]) < 2e-5 and rel_err(r.cpu().numpy(), o["r"], floor=0.1) < 2e-5
+
+
+@pytest.mark.parametrize("cfg,scale", [(0, 1.0), (1, 1 / 64)])
+def test_safety_filter_fused_configs(coracle, cfg, scale):
+    """BASELINE configs[0] in full (4096 Panda states, the reference's CPU-runnable case) and configs[1] at 1/64."""
+    from cbfrrt import ops, workloads as W
+    w = W.config(cfg, scale=scale)
+    b8, s4 = _scene(w["boxes"], w["spheres"])
+    rid = ops.ROBOT_ID[w["robot"]]
+    args = (_t(w["q"]), _t(w["goal"]), b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"],
+            w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
+    safe, unsafe, datax, h, J, u, r = ops.safety_filter(*args)
+    o = coracle.safety_filter(w["robot"], w["q"], w["boxes"], w["spheres"], True, w["weights"], 48, 2, w["goal"],
+                              w["K"], w["u_lo"], w["u_hi"], w["thr_soft"], w["thr_hard"], w["lam"], w["penalty"])
+    n = w["n"]
+    assert np.array_equal(safe.cpu().numpy(), o["safe"]) and np.array_equal(unsafe.cpu().numpy(), o["unsafe"])
+    assert np.array_equal(datax.cpu().numpy()[:, :n + 1], o["datax"][:, :n + 1])
+    assert rel_err(datax.cpu().numpy()[:, n + 1:], o["datax"][:, n + 1:]) < TOL
+    assert rel_err(h.cpu().numpy(), o["h"], floor=0.1) < TOL and rel_err(J.cpu().numpy(), o["J"], floor=0.1) < TOL
+    assert rel_err(u.cpu().numpy(), o["u"]) < TOL and rel_err(r.cpu().numpy(), o["r"], floor=0.1) < TOL
+    v2, u2 = ops.valid_control(*args)
+    assert torch.equal(v2, safe) and torch.equal(u2, u)
+    assert 0 < o["safe"].mean() < 1
+
+
+@pytest.mark.parametrize("robot,K", [("panda", 32), ("panda", 5), ("magician", 32), ("panda", 200)])
+def test_edge_validity_bit_exact(coracle, robot, K):
+    from cbfrrt import ops, workloads as W
+    w = W.config(2, scale=1 / 4096)
+    E = 700 if K < 128 else 150
+    qf = W.sample_states(robot, E, 0)
+    m_lo, m_hi = np.array(W.ROBOT_MODELS[robot]["q_lower"], np.float32), np.array(W.ROBOT_MODELS[robot]["q_upper"], np.float32)
+    qt = np.clip(qf + np.random.default_rng(1).uniform(-0.35, 0.35, qf.shape).astype(np.float32), m_lo, m_hi)
+    b8, s4 = _scene(w["boxes"], w["spheres"])
+    valid, first_bad = ops.edge_validity(_t(qf), _t(qt), K, b8, s4, 1, 0.02, 0.0, ops.ROBOT_ID[robot])
+    vo, fo = coracle.edge_validity(robot, qf, qt, K, w["boxes"], w["spheres"], True, 0.02, 0.0)
+    assert np.array_equal(valid.cpu().numpy(), vo) and np.array_equal(first_bad.cpu().numpy(), fo)
+    assert 0 < vo.mean() < 1
+
+
+def test_edge_validity_equals_pointwise_safe_mask():
+    """size-independent property: an edge is valid iff every interpolated configuration is safe (tsa.py:272-286)."""
+    from cbfrrt import ops, workloads as W
+    w = W.config(2, scale=1 / 1024)
+    qf, qt, K = _t(w["q"]), _t(w["q_to"]), 32
+    b8, s4 = _scene(w["boxes"], w["spheres"])
+    valid, first_bad = ops.edge_validity(qf, qt, K, b8, s4, 1, 0.02, 0.0, 0)
+    bad = torch.full((qf.shape[0],), 1 << 30, device=DEV, dtype=torch.int64)
+    for k in range(K + 1):
+        # the interpolation contract is c = fmaf(k/K, q_to - q_from, q_from); float64 holds the product exactly
+        t = np.float64(np.float32(k) / np.float32(K))
+        d = (w["q_to"] - w["q"]).astype(np.float64)
+        c = qt if k == K else _t((t * d + w["q"].astype(np.float64)).astype(np.float32))
+        s, _ = ops.masks(c, b8, s4, 1, 0.02, 0.0, 0)
+        bad = torch.where((s == 0) & (bad > k), torch.full_like(bad, k), bad)
+    exp_valid = (bad == (1 << 30))
+    assert torch.equal(valid.bool(), exp_valid)
+    assert torch.equal(first_bad.long()[~exp_valid], bad[~exp_valid])
+
+
+def test_sampler_bit_exact_and_shard_invariant(coracle):
+    from cbfrrt import ops
+    for robot in ("panda", "magician"):
+        rid = ops.ROBOT_ID[robot]
+        a = ops.sample_states(100000, 7, 12345, rid).cpu().numpy()
+        assert np.array_equal(a, coracle.sample_states(robot, 7, 12345, 100000))
+        b = torch.cat([ops.sample_states(33333, 7, 12345, rid), ops.sample_states(66667, 7, 12345 + 33333, rid)])
+        assert np.array_equal(a, b.cpu().numpy())
+    big = ops.sample_states(10, 7, (1 << 33) + 5, 0).cpu().numpy()   # rows beyond 2^32
+    assert np.array_equal(big, coracle.sample_states("panda", 7, (1 << 33) + 5, 10))
+
+
+def test_rollout_against_oracle(coracle):
+    """Closed loop (steer semantics).  The QP runs in fp32 on the GPU and fp64 in the oracle, so trajectories
+    agree to tolerance, not bitwise; a discrete event (collision / stuck) may only differ where the oracle's own
+    margin to that event is within tolerance."""
+    from cbfrrt import ops, workloads as W
+    w = W.config(3, scale=1 / 256)
+    b8, s4 = _scene(w["boxes"], w["spheres"])
+    T = w["q"].shape[0]
+    safe0 = coracle.collide("panda", w["q"], w["boxes"], None, True)["safe"].astype(bool)
+    q0, goal = w["q"][safe0][:600], w["goal"][safe0][:600]
+    for steps, stuck in ((30, (9, 10, 0.1)), (60, (0, 10, 0.1))):
+        qf, alive, done, traj = ops.rollout(_t(q0), _t(goal), steps, w["ctrl_every"], w["dt"], stuck[0], stuck[1], stuck[2],
+                                            True, b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"],
+                                            w["penalty"], w["thr_soft"], w["thr_hard"], 0, 48, 2)
+        qo, ao, do_, to = coracle.rollout("panda", q0, goal, steps, w["ctrl_every"], w["dt"], w["boxes"], None, True,
+                                          w["weights"], 48, 2, w["K"], w["u_lo"], w["u_hi"], w["thr_soft"], w["thr_hard"],
+                                          w["lam"], w["penalty"], stuck_lag=stuck[0], stuck_after=stuck[1],
+                                          stuck_eps=stuck[2], want_traj=True)
+        same = (alive.cpu().numpy() == ao) & (done.cpu().numpy() == do_)
+        assert same.mean() > 0.99
+        assert np.abs(qf.cpu().numpy()[same] - qo[same]).max() < 1e-4
+        tr = traj.cpu().numpy()
+        for b in np.nonzero(same)[0][:50]:
+            assert np.abs(tr[b, :do_[b]] - to[b, :do_[b]]).max() < 1e-4
+        # teacher-forced, bit-exact part: every appended state is not unsafe, and a dead trajectory's next state is
+        dn = done.cpu().numpy()
+        flat = np.concatenate([tr[b, :dn[b]] for b in range(len(dn)) if dn[b] > 0])
+        assert not coracle.collide("panda", flat, w["boxes"], None, True)["unsafe"].any()
+        assert (ao == 0).sum() > 0 and (do_ < steps).sum() > 0
+
+
+def test_host_buffer_api_matches_device_api():
+    from cbfrrt import ops, workloads as W
+    w = W.config(1, scale=1 / 8)   # 131072 magician states: several chunks on 3 streams
+    b8, s4 = _scene(w["boxes"], w["spheres"])
+    B, n = w["q"].shape
+    dev = ops.safety_filter(_t(w["q"]), _t(w["goal"]), b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]),
+                            w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], 1, 48, 2)
+    out = dict(safe=np.empty(B, np.uint8), unsafe=np.empty(B, np.uint8), datax=np.empty((B, 2 * n + 1), np.float32),
+               h=np.empty(B, np.float32), J=np.empty((B, n), np.float32), u=np.empty((B, n), np.float32),
+               r=np.empty(B, np.float32))
+    ops.safety_filter_host("magician", w["q"], w["boxes"], w["spheres"], True, w["weights"], 48, 2, w["goal"], w["K"],
+                           w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], out)
+    for k, t in zip(("safe", "unsafe", "datax", "h", "J", "u", "r"), dev):
+        assert np.array_equal(out[k], t.cpu().numpy()), k
+    # per-row goals + a subset of outputs
+    goal = W.sample_states("magician", B, 5)
+    dev = ops.valid_control(_t(w["q"]), _t(goal), b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]),
+                            w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], 1, 48, 2)
+    out = dict(safe=np.empty(B, np.uint8), u=np.empty((B, n), np.float32))
+    ops.safety_filter_host("magician", w["q"], w["boxes"], w["spheres"], True, w["weights"], 48, 2, goal, w["K"],
+                           w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], out)
+    assert np.array_equal(out["safe"], dev[0].cpu().numpy()) and np.array_equal(out["u"], dev[1].cpu().numpy())
+
+
+def test_full_size_config1_properties(coracle):
+    """BASELINE configs[1] at full size (2^20 Magician states): split invariance (bitwise), oracle parity on a
+    random 4096-row sample, and the QP feasibility / box constraints on every row."""
+    from cbfrrt import ops, workloads as W
+    w = W.config(1)
+    b8, s4 = _scene(w["boxes"], w["spheres"])
+    q = _t(w["q"])
+    common = (_t(w["goal"]), b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"],
+              w["thr_soft"], w["thr_hard"], 1, 48, 2)
+    full = ops.safety_filter(q, *common)
+    half = 333333
+    a, b = ops.safety_filter(q[:half], *common), ops.safety_filter(q[half:], *common)
+    for f, x, y in zip(full, a, b):
+        assert torch.equal(f, torch.cat([x, y]))
+    idx = np.random.default_rng(0).choice(q.shape[0], 4096, replace=False)
+    o = coracle.safety_filter("magician", w["q"][idx], w["boxes"], w["spheres"], True, w["weights"], 48, 2, w["goal"],
+                              w["K"], w["u_lo"], w["u_hi"], w["thr_soft"], w["thr_hard"], w["lam"], w["penalty"])
+    assert np.array_equal(full[0].cpu().numpy()[idx], o["safe"]) and np.array_equal(full[1].cpu().numpy()[idx], o["unsafe"])
+    assert rel_err(full[5].cpu().numpy()[idx], o["u"]) < TOL
+    safe, unsafe, datax, h, J, u, r = full
+    assert not (safe.bool() & unsafe.bool()).any()
+    assert (u <= _t(w["u_hi"]) + 1e-6).all() and (u >= _t(w["u_lo"]) - 1e-6).all() and (r >= 0).all()
+    g = w["lam"] * h + (J * u).sum(1) - r
+    assert (g < 1e-4).all()
+
+
+def test_python_api_drop_in_on_gpu(coracle):
+    """The reference-shaped host API end to end: ArmEnv / ArmMindis / NeuralMindisCBFController / steer."""
+    from cbfrrt.environment import ArmEnv
+    from cbfrrt.neural_cbf.systems import ArmMindis
+    from cbfrrt.neural_cbf.controllers import NeuralMindisCBFController
+    from cbfrrt.motion_planning.baseline import steer, steer_fused, edge_checking, edge_checking_batch
+    from cbfrrt import workloads as W
+    env = ArmEnv(["panda"], config_file="", include_floor=True)
+    robot = env.robot_list[0]
+    dyn = ArmMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.02, env=env, robot=robot)
+    torch.manual_seed(1)
+    ctrl = NeuralMindisCBFController(dyn, [{"m1": 5.76}], None, None, cbf_alpha=0.1, cbf_relaxation_penalty=5000.0,
+                                     safe_level=0.1, unsafe_level=0.1, cbf_hidden_layers=2, cbf_hidden_size=48,
+                                     use_neural_actor=False)
+    up, lo = dyn.state_limits
+    assert (up > lo).all() and abs(dyn.K[0, 0].item() - 0.9834722125784985) < 1e-12
+    x = dyn.sample_state_space(512)
+    safe, unsafe = dyn.safe_mask(x), dyn.unsafe_mask(x)
+    assert safe.dtype == torch.bool and safe.device == x.device and safe.shape == (512,)
+    boxes6 = np.concatenate([env.obs_positions, env.obs_sizes], 1)
+    o = coracle.collide("panda", x.numpy(), boxes6, None, True, 0.02, 0.0)
+    assert np.array_equal(safe.numpy(), o["safe"].astype(bool)) and np.array_equal(unsafe.numpy(), o["unsafe"].astype(bool))
+    assert torch.equal(dyn.boundary_mask(x), ~(safe | unsafe))
+    datax = dyn.complete_sample_with_observations(x, 512)
+    assert datax.shape == (512, 15) and np.array_equal(datax.numpy()[:, :8], o["datax"][:, :8])
+    u, t_dict = ctrl.u(datax)
+    assert u.shape == (512, 7) and isinstance(t_dict, dict) and {"nn_forward", "QP"} <= set(t_dict)
+    h, J, extra = ctrl.h_with_jacobian(datax)
+    assert h.shape == (512, 1) and J.shape == (512, 1, 7) and extra == {}
+    net = ctrl.h_nn  # torch autograd of the same module = the reference's h_with_jacobian
+    xg = datax[:, :8].clone().requires_grad_(True)
+    hh = net(xg)
+    Jh = torch.autograd.grad(hh.sum(), xg)[0]
+    Jref = Jh[:, :7] + Jh[:, 7:] * datax[:, 8:]
+    assert rel_err(h.numpy(), hh.detach().numpy(), floor=0.1) < TOL and rel_err(J[:, 0].numpy(), Jref.numpy(), floor=0.1) < TOL
+    (u2, r2), _ = ctrl.solve_CLF_QP(datax, relaxation_penalty=0.5)
+    assert u2.shape == (512, 7) and r2.shape == (512, 1)
+    # steer: reference loop on our ops == one fused launch
+    start = x[safe][0].numpy()
+    target = x[safe][1].numpy()
+    x_last, ok, td, x_list = steer(ctrl.u, dyn, target, start, RRT_step=30, device="cpu")
+    x_last2, ok2, td2, x_list2 = steer_fused(ctrl, dyn, target, start, RRT_step=30)
+    assert ok == ok2 and len(x_list) == len(x_list2) and np.abs(np.asarray(x_list[1:]) - np.asarray(x_list2[1:])).max() < 1e-4
+    assert len(x_list) > 5
+    # edge checking: reference loop == batched launch for the same K
+    eps = 0.05
+    K = int(np.linalg.norm(start - target) / eps)
+    v, fb = edge_checking_batch(start[None], target[None], dyn, K)
+    assert bool(v.item()) == edge_checking(start, target, dyn, eps)
+    assert robot.forward_kinematics([6, 7], torch.tensor(robot.q0))[1][0].shape == (3,)
+    assert np.allclose(robot.forward_kinematics([7], robot.q0)[0][0], (0.288556, -0.257364, 0.361447), atol=2e-6)

@@ -1,0 +1,129 @@
+"""CPU suite: pins the oracles against every known answer the reference's text yields and against
+each other (float32 contract C oracle vs independent float64 derivation)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+
+def test_fk_known_answers_q0_and_zero(models, coracle):
+    """Panda link origins at q = 0 and link8 at q0, computed by hand from panda.urdf."""
+    from oracle import oracle_f64 as o
+    m = models["panda"]
+    expect0 = {0: (0, 0, 0.333), 1: (0, 0, 0.333), 2: (0, 0, 0.649), 3: (0.0825, 0, 0.649), 4: (0, 0, 1.033),
+               5: (0, 0, 1.033), 6: (0.088, 0, 1.033), 7: (0.088, 0, 0.926)}
+    fr = o.fk(m, np.zeros(7))
+    pos, rot = coracle.fk("panda", np.zeros((1, 7), np.float32))
+    for l, e in expect0.items():
+        assert np.allclose(fr[l][:3, 3], e, atol=1e-9)
+        assert np.allclose(pos[0, l], e, atol=1e-6)
+    fr = o.fk(m, np.array(m["q0"]))
+    assert np.allclose(fr[7][:3, 3], (0.288556, -0.257364, 0.361447), atol=1e-6)
+    pos, _ = coracle.fk("panda", np.array([m["q0"]], np.float32))
+    assert np.allclose(pos[0, 7], (0.288556, -0.257364, 0.361447), atol=2e-6)
+
+
+def test_urdf_constants(models):
+    p, g = models["panda"], models["magician"]
+    assert p["n"] == 7 and p["n_links"] == 12 and p["body_joints"] == list(range(7)) and p["ee_joints"] == [9, 10]
+    assert np.allclose(p["q_lower"], [-2.9671, -1.8326, -2.9671, -3.1416, -2.9671, -0.0873, -2.9671])
+    assert np.allclose(p["q_upper"], [2.9671, 1.8326, 2.9671, 0.0, 2.9671, 3.8223, 2.9671])
+    assert np.allclose(p["v_max"], [2.175] * 4 + [2.61] * 3)
+    assert g["n"] == 4 and g["n_links"] == 4 and np.allclose(g["v_max"], [3.15] * 4)
+    assert np.allclose(g["q_upper"], [3.14159265, 1.570796325, 1.570796325, 3.14159265])
+    # magician joint origins carry globalScaling = 2 (environment/magician.py:20)
+    assert np.allclose(g["links"][0]["t64"], [0, 0, 0.048]) and np.allclose(g["links"][1]["t64"], [-0.0235, 0, 0.228])
+    assert np.allclose(g["q0"], [0, 0.707, 0.707, 0])
+
+
+def test_lqr_gain_known_values(golden):
+    from cbfrrt.neural_cbf.systems.utils import scalar_dare_gain, lqr
+    import scipy.linalg
+    assert abs(scalar_dare_gain(1 / 30) - 0.9834722125784985) < 1e-13
+    assert abs(scalar_dare_gain(0.01) - 0.9950124999218958) < 1e-13
+    for n, b in ((7, 1 / 30), (4, 0.01)):
+        A, B = np.eye(n), b * np.eye(n)
+        X = scipy.linalg.solve_discrete_are(A, B, np.eye(n), np.eye(n))
+        K_ref = np.linalg.inv(B.T @ X @ B + np.eye(n)) @ (B.T @ X @ A)  # reference utils.py:40-43
+        assert np.allclose(lqr(A, B, np.eye(n), np.eye(n)), K_ref, atol=1e-9)
+    # K produced by the reference's own compute_linearized_controller (golden, scipy DARE)
+    for name in ("panda", "magician"):
+        K = golden[name]["K"]
+        assert np.allclose(K, scalar_dare_gain(1 / 30) * np.eye(K.shape[0]), atol=1e-8)
+
+
+def test_contract_sincos_accuracy(coracle):
+    x = np.linspace(-7.0, 7.0, 200001).astype(np.float32)
+    s, c = coracle.sincos(x)
+    assert np.abs(s - np.sin(x.astype(np.float64))).max() < 2.5e-7
+    assert np.abs(c - np.cos(x.astype(np.float64))).max() < 2.5e-7
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_c_oracle_matches_f64_oracle(models, coracle, robot):
+    """float32-contract oracle vs the independent float64 derivation: identical booleans/indices away from
+    threshold ties, values within 1e-5 relative."""
+    from oracle import oracle_f64 as o
+    m = models[robot]
+    rng = np.random.default_rng(11)
+    q = rng.uniform(m["q_lower"], m["q_upper"], size=(300, m["n"])).astype(np.float32)
+    boxes = np.array([[0.3, 0.17, 0.3, 0.05, 0.05, 0.1], [-0.4, 0.23, 0.4, 0.05, 0.05, 0.1],
+                      [0.0, -0.23, 0.6, 0.05, 0.05, 0.1]])
+    sph = np.array([[0.3, -0.3, 0.5, 0.1]])
+    out = coracle.collide(robot, q, boxes, sph, True, 0.02, 0.0)
+    pos, rot = coracle.fk(robot, q)
+    n = m["n"]
+    for b in range(q.shape[0]):
+        fr = o.fk(m, q[b].astype(np.float64))
+        for l in range(m["n_links"]):
+            assert rel_err(pos[b, l], fr[l][:3, 3]) < 1e-5 and rel_err(rot[b, l], fr[l][:3, :3]) < 1e-5
+        r = o.evaluate(m, q[b].astype(np.float64), boxes, sph, True, 0.02)
+        near_tie = min(abs(r["soft_min"] - 0.02), abs(r["hard_min"]), abs(r["self_min"] - 0.01)) < 1e-5
+        if not near_tie:
+            assert bool(out["safe"][b]) == r["safe"] and bool(out["unsafe"][b]) == r["unsafe"]
+        assert abs(out["datax"][b, n] - r["o"]) < 1e-5
+        assert abs(out["mins"][b, 1] - r["soft_min"]) < 1e-5 and abs(out["mins"][b, 2] - r["hard_min"]) < 1e-5
+        assert abs(out["mins"][b, 0] - r["self_min"]) < 1e-5
+        if out["arg_obs"][b] == r["arg_obs"] and out["arg_link"][b] == m["spheres"][r["arg_sphere"]]["link"]:
+            assert rel_err(out["datax"][b, n + 1:], r["do_dq"]) < 1e-5
+
+
+def test_gradient_is_derivative_of_distance(models, coracle):
+    """do/dq returned with the observation is the derivative of o along q (central differences)."""
+    m = models["panda"]
+    rng = np.random.default_rng(5)
+    boxes = np.array([[0.35, 0.1, 0.4, 0.1, 0.1, 0.1], [-0.3, -0.3, 0.6, 0.08, 0.1, 0.15]])
+    q = rng.uniform(m["q_lower"], m["q_upper"], size=(200, 7)).astype(np.float32)
+    base = coracle.collide("panda", q, boxes, None, True)
+    eps, ok, tot = 1e-3, 0, 0
+    for j in range(7):
+        qp, qm = q.copy(), q.copy()
+        qp[:, j] += eps
+        qm[:, j] -= eps
+        op, om = coracle.collide("panda", qp, boxes, None, True), coracle.collide("panda", qm, boxes, None, True)
+        same = (op["arg_obs"] == base["arg_obs"]) & (om["arg_obs"] == base["arg_obs"]) & \
+               (op["arg_link"] == base["arg_link"]) & (om["arg_link"] == base["arg_link"])
+        fd = (op["datax"][:, 7] - om["datax"][:, 7]) / (2 * eps)
+        err = np.abs(fd - base["datax"][:, 8 + j])[same]
+        ok += (err < 5e-3).sum()
+        tot += same.sum()
+    assert tot > 500 and ok / tot > 0.97
+
+
+def test_edge_cases_empty_scene_and_no_floor(coracle):
+    q = np.zeros((3, 7), np.float32)
+    out = coracle.collide("panda", q, None, None, False)
+    assert np.isinf(out["datax"][:, 7]).all() and (out["arg_obs"] == -1).all() and (out["unsafe"] == 0).all()
+    out = coracle.collide("panda", q, None, None, True)
+    # link 0 rests 0.141 m above the floor: the kinematic constant wins at q = 0 (upright arm)
+    assert np.allclose(out["datax"][:, 7], 0.14099599) and (out["arg_obs"] == 0).all() and (out["arg_link"] == 0).all()
+    assert (out["datax"][:, 8:] == 0).all()
+
+
+def test_sampler_is_shard_invariant(coracle):
+    a = coracle.sample_states("panda", 7, 0, 1000)
+    b = np.concatenate([coracle.sample_states("panda", 7, 0, 400), coracle.sample_states("panda", 7, 400, 600)])
+    assert np.array_equal(a, b)
+    lo, hi = np.array([-2.9671, -1.8326, -2.9671, -3.1416, -2.9671, -0.0873, -2.9671]), \
+        np.array([2.9671, 1.8326, 2.9671, 0.0, 2.9671, 3.8223, 2.9671])
+    assert (a >= lo - 1e-6).all() and (a <= hi + 1e-6).all() and a.std(0).min() > 0.4

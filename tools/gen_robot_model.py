@@ -314,7 +314,45 @@ def build_robot(name):
             self_pairs.remove(p)
     print(name, "self-pair hit rates", {k: round(v / n_samp, 3) for k, v in hits.items()}, "dropped", dropped)
 
+    # ---- derived kernel tables
+    # spheres are sorted by link; sph_begin[l+1] .. sph_begin[l+2] is the range of link l (l = -1 .. n_links-1)
+    sph_begin = [0]
+    for l in range(-1, n_links):
+        sph_begin.append(sph_begin[-1] + sum(1 for s in spheres if s["link"] == l))
+    assert [s["link"] for s in spheres] == sorted(s["link"] for s in spheres)
+    # bit j set <=> body joint j moves link l
+    anc_mask = []
+    for l in range(n_links):
+        m, k = 0, l
+        while k >= 0:
+            if links[k]["qidx"] >= 0:
+                m |= 1 << links[k]["qidx"]
+            k = links[k]["parent"]
+        anc_mask.append(m)
+    # exact squared-distance thresholds for the self-collision test: the oracle's predicate
+    #   fl(fl(sqrtf(dsq) - r_i) - r_j) > 0.01f        (monotone non-decreasing in dsq)
+    # is equivalent to  dsq > X_ij  with  X_ij = the largest float32 for which the predicate is false.
+    def pred_false(x, ri, rj):
+        d = np.float32(np.float32(np.sqrt(np.float32(x))) - np.float32(ri)) - np.float32(rj)
+        return not (np.float32(d) > np.float32(0.01))
+    self_sphere_pairs = []
+    for a, b in self_pairs:
+        for i in by_link[a]:
+            for j in by_link[b]:
+                ri, rj = spheres[i]["r"], spheres[j]["r"]
+                lo_b, hi_b = 0, int(np.float32(4.0).view(np.uint32))
+                assert pred_false(np.uint32(lo_b).view(np.float32), ri, rj)
+                assert not pred_false(np.uint32(hi_b).view(np.float32), ri, rj)
+                while hi_b - lo_b > 1:
+                    mid = (lo_b + hi_b) // 2
+                    if pred_false(np.uint32(mid).view(np.float32), ri, rj):
+                        lo_b = mid
+                    else:
+                        hi_b = mid
+                self_sphere_pairs.append([i, j, float(np.uint32(lo_b).view(np.float32))])
+
     return dict(
+        sph_begin=sph_begin, anc_mask=anc_mask, self_sphere_pairs=self_sphere_pairs,
         name=name, scale=scale, n=n, n_links=n_links, body_joints=body_joints,
         ee_joints=[i for i, l in enumerate(links) if l["type"] == "prismatic"],
         q0=q0,
@@ -336,7 +374,7 @@ def cfloat(x):
 
 
 def emit_c_tables(robots, path, cuda):
-    q = "static constexpr" if cuda else "static const"
+    q = "__device__ constexpr" if cuda else "static const"
     L = []
     L.append("// GENERATED by tools/gen_robot_model.py from spec/robot_models.json -- do not edit.")
     L.append("// Robot model tables: FK chain constants + link sphere geometry (see DESIGN.md, 'Geometry model').")
@@ -367,6 +405,14 @@ def emit_c_tables(robots, path, cuda):
         L.append("};")
         L.append(f"{q} int {N}_SELF_PAIRS[{max(1, len(rb['self_pairs']))}][2] = {{" +
                  ", ".join("{%d, %d}" % tuple(p) for p in rb["self_pairs"]) + "};")
+        if cuda:
+            L.append(f"{q} int {N}_SPH_BEGIN[{nl + 2}] = {{" + ", ".join(str(v) for v in rb["sph_begin"]) + "};")
+            L.append(f"{q} int {N}_ANC_MASK[{nl}] = {{" + ", ".join(str(v) for v in rb["anc_mask"]) + "};")
+            sp = rb["self_sphere_pairs"]
+            L.append(f"#define {N}_NSELFSPH {len(sp)}")
+            L.append(f"{q} int {N}_SELFSPH_I[{len(sp)}] = {{" + ", ".join(str(v[0]) for v in sp) + "};")
+            L.append(f"{q} int {N}_SELFSPH_J[{len(sp)}] = {{" + ", ".join(str(v[1]) for v in sp) + "};")
+            L.append(f"{q} float {N}_SELFSPH_X[{len(sp)}] = {{" + ", ".join(cfloat(v[2]) for v in sp) + "};")
         L.append(f"{q} float {N}_QLO[{n}] = {{" + ", ".join(cfloat(v) for v in rb["q_lower"]) + "};")
         L.append(f"{q} float {N}_QHI[{n}] = {{" + ", ".join(cfloat(v) for v in rb["q_upper"]) + "};")
         L.append(f"{q} float {N}_VMAX[{n}] = {{" + ", ".join(cfloat(v) for v in rb["v_max"]) + "};")
