@@ -36,7 +36,7 @@ class FilterParams(C.Structure):
 
 class RolloutParams(C.Structure):
     _fields_ = [("steps", C.c_int32), ("ctrl_every", C.c_int32), ("dt", C.c_float), ("stuck_lag", C.c_int32),
-                ("stuck_after", C.c_int32), ("stuck_eps", C.c_float)]
+                ("stuck_after", C.c_int32), ("stuck_eps", C.c_float), ("keep_going", C.c_int32)]
 
 
 # every symbol declared in include/cbfrrt.h: (restype, argtypes)
@@ -56,6 +56,7 @@ SIGNATURES = {
     "cbfrrt_edge_validity": (C.c_int, [_I, C.POINTER(Scene), _P, _P, _L, C.c_int32, _F, _F, _P, _P, _P]),
     "cbfrrt_rollout": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, C.POINTER(FilterParams),
                                  C.POINTER(RolloutParams), _F, _F, _P, _P, _P, _P, _P]),
+    "cbfrrt_fma_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "cbfrrt_sample_states": (C.c_int, [_I, C.c_uint32, C.c_uint64, _L, _P, _P]),
     "cbfrrt_safety_filter_host": (C.c_int, [_I, _I, C.POINTER(HostScene), C.c_int32, C.c_int32, _P, _L, _P, _L, _P, _L,
                                             _P, _P, _P, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),

@@ -69,12 +69,12 @@ def steer_fused(controller, dynamics_model, new_state, nearest, RRT_step=10, dev
     return x_list[-1], bool(alive.item()), time_dict, x_list
 
 
-def _rollout(controller, dm, q0, steps, stuck=(0, 10, 0.1), want_traj=False):
+def _rollout(controller, dm, q0, steps, stuck=(0, 10, 0.1), want_traj=False, keep_going=False):
     b, s, fl = dm.env.scene
     lo, hi = controller._limits()
     ctrl_every = int(dm.controller_dt // dm.dt)
     return ops.rollout(q0, dm.goal_tensor(dm.device), int(steps), ctrl_every, float(dm.dt), int(stuck[0]),
-                       int(stuck[1]), float(stuck[2]), bool(want_traj), b, s, fl, controller._weights(),
+                       int(stuck[1]), float(stuck[2]), bool(want_traj), bool(keep_going), b, s, fl, controller._weights(),
                        dm.K.to(dm.device, torch.float32), lo, hi, float(controller.clf_lambda),
                        float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard),
                        dm.robot.robot_id, controller.h_hidden_size, controller.h_hidden_layers)

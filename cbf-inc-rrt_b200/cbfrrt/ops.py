@@ -284,7 +284,7 @@ def edge_validity(q_from: Tensor, q_to: Tensor, n_interp: int, boxes: Tensor, sp
 
 @torch.library.custom_op("cbfrrt::rollout", mutates_args=(), device_types="cuda")
 def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, stuck_lag: int, stuck_after: int,
-            stuck_eps: float, want_traj: bool, boxes: Tensor, spheres: Tensor, floor: int, weights: Tensor, K: Tensor,
+            stuck_eps: float, want_traj: bool, keep_going: bool, boxes: Tensor, spheres: Tensor, floor: int, weights: Tensor, K: Tensor,
             u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float, robot_id: int,
             hidden: int, layers: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """the steer loop in one launch -> q_final f32[T,n], alive u8[T], steps_done i32[T], traj f32[T,steps,n]
@@ -296,7 +296,7 @@ def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, st
     T, dev = q0.shape[0], q0.device
     net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, T, lam, penalty, hidden, layers)
     sc = _scene(boxes, spheres, floor)
-    rp = RolloutParams(steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps)
+    rp = RolloutParams(steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, int(keep_going))
     qf = torch.empty((T, n), dtype=torch.float32, device=dev)
     alive = torch.empty(T, dtype=torch.uint8, device=dev)
     done = torch.empty(T, dtype=torch.int32, device=dev)

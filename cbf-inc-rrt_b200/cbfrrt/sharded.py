@@ -1,0 +1,86 @@
+"""One process per GPU: shard a state sweep across ranks, all-gather validity masks and filtered controls.
+
+The path shards embarrassingly (independent states): scene, link model and MLP weights are
+replicated, rows are partitioned, and the ONLY collective is the all-gather of ``valid`` (u8) and ``u`` (f32 x n)
+that BASELINE.json's north_star names.  The reference has no counterpart (it fans out OS processes and merges
+pickles offline, motion_planning/scripts/rrt_mindis.sh:8-15).
+
+Partition: block-cyclic.  The G global rows are cut into blocks of ``block`` rows; block b belongs to rank
+b % world.  A rank computes its blocks in order; block j of every rank is gathered by one
+``all_gather_into_tensor`` whose output [world, block] is exactly the global rows
+[j*world*block, (j+1)*world*block) -- so the gathered buffers are in global row order without a permute, and
+the gather of block j overlaps the kernel of block j+1 on a second stream.
+"""
+from typing import Callable, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def block_layout(G: int, world: int, block: int):
+    """-> (blocks_per_rank, padded global size).  G is padded up to a multiple of world*block."""
+    per_round = world * block
+    rounds = (G + per_round - 1) // per_round
+    return rounds, rounds * per_round
+
+
+def local_global_rows(rank: int, world: int, block: int, rounds: int) -> torch.Tensor:
+    """global row index of every local row of ``rank`` (local rows are its blocks concatenated)."""
+    j = torch.arange(rounds).repeat_interleave(block)
+    i = torch.arange(block).repeat(rounds)
+    return j * (world * block) + rank * block + i
+
+
+class ShardedSweep:
+    """valid, u = sweep(q_local): every rank ends up with the full [G] mask and [G, n] controls.
+
+    compute(q_block) -> (valid u8[block], u f32[block, n]) is the per-block kernel (cbfrrt::valid_control on the
+    GPU; tests inject a CPU function and the gloo backend).
+    """
+
+    def __init__(self, compute: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]], n: int, block: int,
+                 group=None, device=None):
+        self.compute, self.n, self.block, self.group = compute, n, block, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.cuda = self.device.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self._bufs = {}
+
+    def _out(self, rounds):
+        key = rounds
+        if key not in self._bufs:
+            G = rounds * self.world * self.block
+            self._bufs[key] = (torch.empty(G, dtype=torch.uint8, device=self.device),
+                               torch.empty(G, self.n, dtype=torch.float32, device=self.device))
+        return self._bufs[key]
+
+    def __call__(self, q_local: torch.Tensor):
+        rounds = q_local.shape[0] // self.block
+        assert rounds * self.block == q_local.shape[0], "local rows must be a whole number of blocks"
+        valid_all, u_all = self._out(rounds)
+        per_round = self.world * self.block
+        for j in range(rounds):
+            v, u = self.compute(q_local[j * self.block:(j + 1) * self.block])
+            vo = valid_all[j * per_round:(j + 1) * per_round]
+            uo = u_all[j * per_round:(j + 1) * per_round]
+            if self.world == 1:
+                vo.copy_(v)
+                uo.copy_(u)
+                continue
+            if self.cuda:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ev)
+                    dist.all_gather_into_tensor(vo, v, group=self.group)
+                    dist.all_gather_into_tensor(uo.view(-1), u.reshape(-1), group=self.group)
+                    v.record_stream(self.comm_stream)
+                    u.record_stream(self.comm_stream)
+            else:
+                dist.all_gather_into_tensor(vo, v.contiguous(), group=self.group)
+                dist.all_gather_into_tensor(uo.view(-1), u.reshape(-1).contiguous(), group=self.group)
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        return valid_all, u_all

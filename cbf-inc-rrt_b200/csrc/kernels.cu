@@ -406,6 +406,7 @@ struct RolloutArgs {
     float dt;
     int stuck_lag, stuck_after;
     float stuck_eps;
+    int keep_going;
 };
 template <class RB, int H, int L>
 __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, const float* __restrict__ q0,
@@ -450,7 +451,10 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
                 // closed_loop_dynamics(update_observation=False) leaves o / do_dq at zero (arm_dynamics.py:491-493);
                 // they are not read before the next refresh, the controller only runs at t % ctrl_every == 0.
             }
-            if (cr.hard_min <= thr_hard) { ok = false; break; }  // tsa.py:251-253: colliding state is not appended
+            if (cr.hard_min <= thr_hard) {  // tsa.py:251-253: colliding state is not appended
+                ok = false;
+                if (!ra.keep_going) break;
+            }
 #pragma unroll
             for (int k = 0; k < N; ++k) q[k] = qn[k];
             if (tr) {
@@ -494,6 +498,20 @@ __global__ void __launch_bounds__(256) sample_kernel(uint32_t seed, unsigned lon
         });
         q[i] = fmaf(u, __fsub_rn(hi, lo), lo);
     }
+}
+
+// FP32 FMA throughput probe (roofline denominator; see include/cbfrrt.h)
+__global__ void fma_probe_kernel(int iters, float* sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    const float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456f) *sink = s;  // never true; keeps the chains alive
 }
 
 // ------------------------------------------------------------------ host side of the device-pointer ABI
@@ -776,11 +794,17 @@ int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* n
     rc = check_net(n, net, fp, T, na);
     if (rc) return rc;
     if (T == 0) return CBFRRT_OK;
-    const RolloutArgs ra{rp->steps, rp->ctrl_every, rp->dt, rp->stuck_lag, rp->stuck_after, rp->stuck_eps};
+    const RolloutArgs ra{rp->steps, rp->ctrl_every, rp->dt, rp->stuck_lag, rp->stuck_after, rp->stuck_eps, rp->keep_going};
     cudaStream_t st = (cudaStream_t)stream;
     return robot == CBFRRT_ROBOT_PANDA
                ? launch_rollout<Panda>(sc, na, q0, T, ra, thr_soft, thr_hard, q_final, alive, steps_done, traj, st)
                : launch_rollout<Magician>(sc, na, q0, T, ra, thr_soft, thr_hard, q_final, alive, steps_done, traj, st);
+}
+
+int cbfrrt_fma_probe(int32_t grid, int32_t block, int32_t iters, float* sink, void* stream) {
+    if (grid < 1 || block < 32 || block > 1024 || iters < 1 || !sink) return CBFRRT_ERR_BAD_SHAPE;
+    fma_probe_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
+    return finish_launch();
 }
 
 int cbfrrt_sample_states(int robot, uint32_t seed, uint64_t start_row, int64_t B, float* q, void* stream) {

@@ -95,6 +95,9 @@ typedef struct {
     int32_t stuck_lag;    /* 0 disables the stuck test; tsa.py:263 uses 9 (x_list[-1] vs x_list[-10]) */
     int32_t stuck_after;  /* test only when tstep > stuck_after (10) */
     float stuck_eps;      /* 0.1 */
+    int32_t keep_going;   /* 0: steer semantics (stop at the first unsafe state, tsa.py:251-253).
+                             1: fixed-work variant of BASELINE config 4 ("mask instead of early stop"): an unsafe
+                                state clears `alive` but the trajectory is simulated for all `steps` steps */
 } cbfrrt_rollout_params;
 
 /* ---- library info ------------------------------------------------------------------------------------- */
@@ -181,6 +184,11 @@ int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_host_scene *sc
                               int64_t goal_rows, const float *K, const float *u_lo, const float *u_hi,
                               float cbf_lambda, float relaxation_penalty, float thr_soft, float thr_hard,
                               uint8_t *safe, uint8_t *unsafe, float *datax, float *h, float *J, float *u, float *r);
+
+/* ---- measurement utility: FP32 FMA throughput probe (the roofline denominator of this path is the CUDA-core
+ * FMA rate, which MEASURED_PEAKS.json does not contain).  Launches grid x block threads, each running
+ * 8 independent chains of `iters` dependent FMAs; flops = grid*block*iters*16.  sink: device float[1]. */
+int cbfrrt_fma_probe(int32_t grid, int32_t block, int32_t iters, float *sink, void *stream);
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches evidence) */
 int64_t cbfrrt_launch_count(void);

@@ -105,6 +105,29 @@ def cbf_filter(n, weights, hidden, layers, datax, goal, K, u_lo, u_hi, lam, pena
     return out
 
 
+def qp(a, c, u_ref, u_lo, u_hi, penalty):
+    a, c, u_ref, u_lo, u_hi = _f(a), _f(c).reshape(-1), _f(u_ref), _f(u_lo), _f(u_hi)
+    B, n = a.shape
+    u, r = np.empty((B, n), np.float32), np.empty(B, np.float32)
+    rc = lib().oracle_qp(n, _p(a), _p(c), _p(u_ref), C.c_long(B), _p(u_lo), _p(u_hi), C.c_float(penalty), _p(u), _p(r))
+    assert rc == 0
+    return u, r
+
+
+def u_nominal(q, goal, K, u_lo, u_hi):
+    """clamp(-K (q - goal), lo, hi) in float32 with the oracle's operation order (filter_state)."""
+    q, goal, K = _f(q), _f(goal).reshape(-1, q.shape[1]), _f(K)
+    n = q.shape[1]
+    d = q - goal
+    acc = np.zeros_like(q)
+    for i in range(n):
+        a = np.zeros(q.shape[0], np.float32)
+        for k in range(n):
+            a = (a.astype(np.float64) + K[i, k].astype(np.float64) * d[:, k].astype(np.float64)).astype(np.float32)
+        acc[:, i] = -a
+    return np.clip(acc, _f(u_lo), _f(u_hi))
+
+
 def safety_filter(robot, q, boxes, spheres, floor, weights, hidden, layers, goal, K, u_lo, u_hi, thr_soft, thr_hard,
                   lam, penalty):
     q = _f(q)
@@ -139,7 +162,7 @@ def edge_validity(robot, q_from, q_to, n_interp, boxes, spheres=None, floor=True
 
 
 def rollout(robot, q0, goal, steps, ctrl_every, dt, boxes, spheres, floor, weights, hidden, layers, K, u_lo, u_hi,
-            thr_soft, thr_hard, lam, penalty, stuck_lag=0, stuck_after=10, stuck_eps=0.1, want_traj=False):
+            thr_soft, thr_hard, lam, penalty, stuck_lag=0, stuck_after=10, stuck_eps=0.1, want_traj=False, keep_going=False):
     q0 = _f(q0)
     n, L, _ = robot_info(robot)
     T = q0.shape[0]
@@ -153,7 +176,7 @@ def rollout(robot, q0, goal, steps, ctrl_every, dt, boxes, spheres, floor, weigh
     rc = lib().oracle_rollout(ROBOT_ID[robot], b8.shape[0], _p(b8), sp.shape[0], _p(sp), int(bool(floor)), hidden,
                               layers, _p(w), _p(q0), _p(goal), C.c_long(goal.shape[0]), C.c_long(T), int(steps),
                               int(ctrl_every), C.c_float(dt), int(stuck_lag), int(stuck_after), C.c_float(stuck_eps),
-                              _p(K), _p(u_lo), _p(u_hi), C.c_float(thr_soft),
+                              int(bool(keep_going)), _p(K), _p(u_lo), _p(u_hi), C.c_float(thr_soft),
                               C.c_float(thr_hard), C.c_float(lam), C.c_float(penalty), _p(qf), _p(alive), _p(done),
                               _p(traj))
     assert rc == 0

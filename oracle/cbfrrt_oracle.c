@@ -441,7 +441,7 @@ typedef struct {
     const float *q, *q2, *goal, *K, *u_lo, *u_hi, *datax_in, *u_ref;
     long q_stride, goal_rows;
     float thr_soft, thr_hard, lam, penalty, dt;
-    int Kint, steps, ctrl_every, stuck_lag, stuck_after;
+    int Kint, steps, ctrl_every, stuck_lag, stuck_after, keep_going;
     float stuck_eps, *traj;
     uint8_t *safe, *unsafe, *alive;
     float *datax, *h, *J, *u, *r, *mins, *pos, *rot, *q_final;
@@ -553,6 +553,22 @@ API int oracle_cbf_filter(int n, int hidden, int layers, const float *weights, c
     return 0;
 }
 
+/* the QP stage alone on caller-supplied data (double precision): a = Lg_V [B,n], c = Lf_V + lambda*V [B].
+ * Used to check the CUDA QP on exactly the (h, J) the CUDA MLP produced, which separates the QP's own error
+ * from the amplification of MLP rounding differences by an ill-conditioned QP (tiny |a_i| on a free axis). */
+API int oracle_qp(int n, const float *a, const float *c, const float *u_ref, long B, const float *u_lo,
+                  const float *u_hi, float penalty, float *u, float *r) {
+    if (n > MAXN) return -1;
+    for (long b = 0; b < B; ++b) {
+        double ad[MAXN], ur[MAXN], lo[MAXN], hi[MAXN], ud[MAXN], rd;
+        for (int k = 0; k < n; ++k) { ad[k] = a[b * n + k]; ur[k] = u_ref[b * n + k]; lo[k] = u_lo[k]; hi[k] = u_hi[k]; }
+        qp_exact(n, ad, ur, lo, hi, (double)c[b], penalty < 1e6f ? (double)penalty : 1e6, ud, &rd);
+        for (int k = 0; k < n; ++k) u[b * n + k] = (float)ud[k];
+        r[b] = (float)rd;
+    }
+    return 0;
+}
+
 /* fused q -> everything (the "safety filter" of BASELINE configs 1, 2, 5) */
 CLONES static void safety_range(long lo, long hi, void *p) {
     Ctx *c = (Ctx *)p; const int n = c->n;
@@ -656,7 +672,7 @@ CLONES static void rollout_range(long lo, long hi, void *p) {
                 d[n] = co.o;
                 for (int k = 0; k < n; ++k) d[n + 1 + k] = co.dodq[k];
             }
-            if (co.unsafe) { ok = 0; break; }
+            if (co.unsafe) { ok = 0; if (!c->keep_going) break; }
             for (int k = 0; k < n; ++k) d[k] = qn[k];
             if (tr) for (int k = 0; k < n; ++k) tr[t * n + k] = d[k];
             done = t + 1;
@@ -675,7 +691,7 @@ CLONES static void rollout_range(long lo, long hi, void *p) {
 API int oracle_rollout(int robot, int n_boxes, const float *boxes, int n_sph, const float *spheres, int floor,
                        int hidden, int layers, const float *weights, const float *q0, const float *goal, long goal_rows,
                        long T, int steps, int ctrl_every, float dt, int stuck_lag, int stuck_after, float stuck_eps,
-                       const float *K, const float *u_lo, const float *u_hi, float thr_soft, float thr_hard, float lam,
+                       int keep_going, const float *K, const float *u_lo, const float *u_hi, float thr_soft, float thr_hard, float lam,
                        float penalty, float *q_final, uint8_t *alive, int *steps_done, float *traj) {
     if (hidden > MAXH || layers > MAXL) return -1;
     if (stuck_lag > 0 && !traj) return -1;
@@ -683,7 +699,7 @@ API int oracle_rollout(int robot, int n_boxes, const float *boxes, int n_sph, co
     c.rb = &ROBOTS[robot]; c.n = c.rb->n; c.sc = (Scene){n_boxes, n_sph, floor, boxes, spheres};
     c.net = (Net){c.n + 1, hidden, layers, weights};
     c.q = q0; c.goal = goal; c.goal_rows = goal_rows; c.steps = steps; c.ctrl_every = ctrl_every; c.dt = dt;
-    c.stuck_lag = stuck_lag; c.stuck_after = stuck_after; c.stuck_eps = stuck_eps; c.traj = traj;
+    c.stuck_lag = stuck_lag; c.stuck_after = stuck_after; c.stuck_eps = stuck_eps; c.traj = traj; c.keep_going = keep_going;
     c.K = K; c.u_lo = u_lo; c.u_hi = u_hi; c.thr_soft = thr_soft; c.thr_hard = thr_hard; c.lam = lam; c.penalty = penalty;
     c.q_final = q_final; c.alive = alive; c.steps_done = steps_done;
     par_for(T, rollout_range, &c);

@@ -1,0 +1,75 @@
+"""TEST-ONLY stand-ins for the CUDA ops, backed by the C oracle, operating on CPU tensors.
+
+They let the CPU suite exercise the HOST logic of the reference-shaped API (shapes, dtypes, devices, return
+conventions, control flow of steer / edge_checking, sharding) without a GPU.  The product never sees them."""
+import numpy as np
+import torch
+
+from oracle import c_oracle
+
+NAME = {0: "panda", 1: "magician"}
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _scene(boxes8, spheres):
+    b = _np(boxes8)[:, :6] if boxes8.numel() else None
+    s = _np(spheres) if spheres.numel() else None
+    return b, s
+
+
+def install(monkeypatch):
+    from cbfrrt import ops
+
+    def fk(q, robot_id):
+        pos, rot = c_oracle.fk(NAME[robot_id], _np(q))
+        return torch.from_numpy(pos), torch.from_numpy(rot)
+
+    def collide(q, boxes, spheres, floor, thr_soft, thr_hard, robot_id):
+        b, s = _scene(boxes, spheres)
+        o = c_oracle.collide(NAME[robot_id], _np(q)[:, :ops.ROBOT_N[robot_id]], b, s, bool(floor), thr_soft, thr_hard)
+        return tuple(torch.from_numpy(o[k]) for k in ("safe", "unsafe", "datax", "arg_link", "arg_obs", "mins"))
+
+    def observe(*a):
+        return collide(*a)[:3]
+
+    def masks(*a):
+        return collide(*a)[:2]
+
+    def cbf_filter(datax, goal, weights, K, u_lo, u_hi, lam, penalty, hidden, layers, u_ref):
+        n = (datax.shape[1] - 1) // 2
+        o = c_oracle.cbf_filter(n, _np(weights), hidden, layers, _np(datax), _np(goal), _np(K), _np(u_lo), _np(u_hi), lam,
+                                penalty, u_ref=_np(u_ref) if u_ref.numel() else None)
+        return tuple(torch.from_numpy(o[k]) for k in ("h", "J", "u", "r"))
+
+    def qp(a, c, u_ref, u_lo, u_hi, penalty):
+        u, r = c_oracle.qp(_np(a), _np(c), _np(u_ref), _np(u_lo), _np(u_hi), penalty)
+        return torch.from_numpy(u), torch.from_numpy(r)
+
+    def edge_validity(q_from, q_to, n_interp, boxes, spheres, floor, thr_soft, thr_hard, robot_id):
+        b, s = _scene(boxes, spheres)
+        v, f = c_oracle.edge_validity(NAME[robot_id], _np(q_from), _np(q_to), n_interp, b, s, bool(floor), thr_soft, thr_hard)
+        return torch.from_numpy(v), torch.from_numpy(f)
+
+    def rollout(q0, goal, steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, want_traj, keep_going, boxes, spheres, floor,
+                weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id, hidden, layers):
+        b, s = _scene(boxes, spheres)
+        qf, alive, done, traj = c_oracle.rollout(NAME[robot_id], _np(q0), _np(goal), steps, ctrl_every, dt, b, s, bool(floor),
+                                                 _np(weights), hidden, layers, _np(K), _np(u_lo), _np(u_hi), thr_soft,
+                                                 thr_hard, lam, penalty, stuck_lag=stuck_lag, stuck_after=stuck_after,
+                                                 stuck_eps=stuck_eps, want_traj=want_traj, keep_going=keep_going)
+        return (torch.from_numpy(qf), torch.from_numpy(alive), torch.from_numpy(done),
+                torch.from_numpy(traj) if traj is not None else torch.empty(0))
+
+    def valid_control(q, goal, boxes, spheres, floor, weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id,
+                      hidden, layers):
+        b, s = _scene(boxes, spheres)
+        o = c_oracle.safety_filter(NAME[robot_id], _np(q), b, s, bool(floor), _np(weights), hidden, layers, _np(goal), _np(K),
+                                   _np(u_lo), _np(u_hi), thr_soft, thr_hard, lam, penalty)
+        return torch.from_numpy(o["safe"]), torch.from_numpy(o["u"])
+
+    for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp,
+                         edge_validity=edge_validity, rollout=rollout, valid_control=valid_control).items():
+        monkeypatch.setattr(ops, name, fn)

@@ -1,0 +1,209 @@
+"""CPU suite: host logic of the reference-shaped API (cbfrrt.environment / neural_cbf / motion_planning) with the
+CUDA ops replaced by oracle-backed fakes (tests/fake_ops.py).  Checks the drop-in contract of SURVEY.md 8b:
+signatures, shapes, dtypes, devices, return conventions and the control flow of steer / edge_checking."""
+import numpy as np
+import pytest
+import torch
+
+import fake_ops
+
+
+@pytest.fixture()
+def stack(monkeypatch, coracle):
+    fake_ops.install(monkeypatch)
+    from cbfrrt.environment import ArmEnv
+    from cbfrrt.neural_cbf.systems import ArmMindis
+    from cbfrrt.neural_cbf.controllers import NeuralMindisCBFController
+
+    def make(robot_name="panda"):
+        env = ArmEnv([robot_name], config_file="", include_floor=True, device="cpu")
+        robot = env.robot_list[0]
+        dyn = ArmMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.02, env=env, robot=robot)
+        torch.manual_seed(1)
+        ctrl = NeuralMindisCBFController(dyn, [{"m1": 5.76}], None, None, cbf_alpha=0.1, cbf_relaxation_penalty=5000.0,
+                                         safe_level=0.1, unsafe_level=0.1, cbf_hidden_layers=2, cbf_hidden_size=48,
+                                         use_neural_actor=False)
+        return env, robot, dyn, ctrl
+    return make
+
+
+def test_env_and_robot_attributes(stack):
+    env, robot, dyn, ctrl = stack("panda")
+    assert env.obstacle_ids == [0, 1, 2, 3] and env.obs_positions.shape == (3, 3) and env.include_floor
+    assert np.allclose(env.get_env_config(-1)[0][0], [0.3, 0.17, 0.3])               # arm_env.py:113-114
+    assert robot.body_joints == list(range(7)) and robot.ee_joints == [9, 10] and robot.n_joints == 12
+    assert robot.body_dim == 7 and robot.ee_dim == 2 and robot.body_range.shape == (7, 2)
+    assert str(robot) == "Franka_Panda" and robot.invalid_link == [7, 11]
+    env.reset_env((np.array([[0.4, 0.0, 0.5]]), np.array([[0.1, 0.1, 0.1]])))
+    assert env.obstacle_ids == [0, 1] and env.scene[0].shape == (1, 8)
+    with pytest.raises(NotImplementedError):
+        ArmEnv = type(env)
+        ArmEnv(["iiwa"], device="cpu")                                                 # arm_env.py:79-80
+    env2, robot2, dyn2, _ = stack("magician")
+    assert robot2.body_dim == 4 and str(robot2) == "Magician" and np.allclose(robot2.q0, [0, 0.707, 0.707, 0])
+    with pytest.raises(AttributeError):
+        env.p.getClosestPoints()
+
+
+def test_dynamics_properties_and_masks(stack, coracle):
+    env, robot, dyn, ctrl = stack("panda")
+    assert (dyn.n_dims, dyn.q_dims, dyn.n_controls, dyn.o_dims, dyn.state_aux_dims) == (7, 7, 7, 1, 7)
+    upper, lower = dyn.state_limits                                                    # (upper, lower) order
+    assert (upper > lower).all() and abs(upper[5].item() - 3.8223) < 1e-6
+    cu, cl = dyn.control_limits
+    assert torch.equal(cl, -cu) and abs(cu[0].item() - 2.175) < 1e-6
+    assert abs(dyn.K[0, 0].item() - 0.9834722117237553) < 1e-12  # reference value: B is float32 (golden K) and dyn.K.shape == (7, 7)
+    assert str(dyn) == "Franka_Panda_mindis_Dynamics"
+    x = dyn.sample_state_space(64)
+    assert x.shape == (64, 7) and (x <= upper).all() and (x >= lower).all()
+    safe, unsafe, bnd = dyn.safe_mask(x), dyn.unsafe_mask(x), dyn.boundary_mask(x)
+    assert safe.dtype == torch.bool and safe.shape == (64,) and torch.equal(bnd, ~(safe | unsafe))
+    assert not (safe & unsafe).any()
+    datax = dyn.complete_sample_with_observations(x, 64)
+    assert datax.shape == (64, 15) and torch.equal(datax[:, :7], x)
+    o = dyn._get_observation_with_state(x[0])
+    assert o.shape == (8,) and abs(o[0] - datax[0, 7].item()) < 1e-7
+    # goal mask: within 0.2 of the goal AND safe (arm_dynamics.py:234-262)
+    g = torch.tensor(robot.q0, dtype=torch.float32).reshape(1, -1)
+    assert dyn.goal_mask(g).item() == dyn.safe_mask(g).item()
+    assert not dyn.goal_mask(g + 0.2).item()
+    xs = dyn.sample_safe(5)
+    assert xs.shape == (5, 15) and dyn.safe_mask(xs).all()
+    with pytest.raises(RuntimeWarning):
+        dyn.sample_with_mask(5, lambda s: torch.zeros(s.shape[0], dtype=torch.bool), max_tries=2)
+
+
+def test_closed_loop_dynamics_conventions(stack):
+    env, robot, dyn, ctrl = stack("panda")
+    x = dyn.complete_sample_with_observations(dyn.sample_state_space(4), 4)
+    u = torch.ones(4, 7) * 0.5
+    nxt, times = dyn.closed_loop_dynamics(x, u, update_observation=False, return_time=True)
+    assert len(times) == 2 and nxt.shape == (4, 15)
+    assert torch.allclose(nxt[:, :7], x[:, :7] + 0.5 / 120)                           # returns x_next, not xdot
+    assert (nxt[:, 7:] == 0).all()                                                     # stale o/aux are zeros
+    nxt2 = dyn.closed_loop_dynamics(x, u, update_observation=True)
+    assert torch.equal(nxt2[:, :7], nxt[:, :7]) and (nxt2[:, 7] != 0).any()
+    f, g = dyn.control_affine_dynamics(x[:, :7])
+    assert f.shape == (4, 7, 1) and not f.any() and torch.equal(g[0], torch.eye(7))
+    dyn.set_goal(np.zeros(7))
+    dyn.set_intermediate_goals(np.ones((4, 7)))
+    un = dyn.u_nominal(x)
+    cu, cl = dyn.control_limits
+    assert torch.allclose(un, torch.clamp(-(x[:, :7] - 1.0) * dyn.K[0, 0].float(), cl, cu), atol=1e-6)
+
+
+def test_controller_conventions_and_reference_autograd(stack, golden):
+    env, robot, dyn, ctrl = stack("panda")
+    from conftest import golden_state_dict, rel_err
+    g = golden["panda"]
+    ctrl.load_weights({"h_nn." + k: torch.tensor(v) for k, v in golden_state_dict(g).items()})
+    assert set(ctrl.state_dict()) == {"h_nn." + k for k in golden_state_dict(g)}       # checkpoint key names
+    dyn.set_goal(g["shared_goal"])
+    datax = torch.tensor(g["datax"])
+    u, t_dict = ctrl.u(datax)                                                          # (u, t_dict) tuple
+    assert isinstance(t_dict, dict) and {"V_w_Jacobian", "lie_derivative", "nn_forward", "QP"} <= set(t_dict)
+    assert rel_err(u.numpy(), g["shared_u"]) < 1e-5
+    h, J, extra = ctrl.h_with_jacobian(datax)
+    assert h.shape == (96, 1) and J.shape == (96, 1, 7) and extra == {}
+    assert rel_err(h.numpy(), g["shared_h"], floor=0.1) < 1e-5 and rel_err(J.numpy(), g["shared_J"], floor=0.1) < 1e-5
+    assert torch.equal(ctrl.h(datax[:, :8]), h) and torch.equal(ctrl.V(datax), h)
+    V, Lf, Lg, td = ctrl.V_with_lie_derivatives(datax)
+    assert Lf.shape == (96, 1, 1) and not Lf.any() and torch.equal(Lg, J)
+    (u2, r2), td = ctrl.solve_CLF_QP(datax, relaxation_penalty=0.05)
+    assert r2.shape == (96, 1) and rel_err(u2.numpy(), g["shared_u_pen0.05"]) < 1e-5
+    uref = torch.zeros(96, 7)
+    (u3, _), _ = ctrl.solve_CLF_QP(datax, u_ref=uref)
+    inactive = (0.1 * h[:, 0] <= 0)
+    assert torch.equal(u3[inactive], uref[inactive])
+    with pytest.raises(AssertionError):
+        ctrl.solve_CLF_QP(datax, u_ref=torch.zeros(3, 7))
+    # per-row goals (batch_tsa.py:199)
+    dyn.set_intermediate_goals(g["rows_goal"])
+    u4, _ = ctrl.u(datax)
+    assert rel_err(u4.numpy(), g["rows_u"]) < 1e-5
+
+
+def test_generic_clf_controller_qp(stack):
+    """CLFController / CBFController with the quadratic V (clf_controller.py:141-167, cbf_controller.py:53-67)."""
+    env, robot, dyn, _ = stack("magician")
+    from cbfrrt.neural_cbf.controllers import CBFController
+    c = CBFController(dyn, [{"m1": 1.0}], None, cbf_lambda=1.0, cbf_relaxation_penalty=50.0, controller_period=1 / 30)
+    x = dyn.sample_state_space(32)
+    dyn.set_goal(np.zeros(4))
+    V, JV, _ = c.V_with_jacobian(x)
+    P = dyn.P.float()
+    assert torch.allclose(V, 0.5 * ((x @ P) * x).sum(1) - 1.0, atol=1e-5) and JV.shape == (32, 1, 4)
+    u, td = c.u(x)
+    Vv, Lf, Lg, _ = c.V_with_lie_derivatives(x)
+    cu, cl = dyn.control_limits
+    assert (u <= cu + 1e-6).all() and (u >= cl - 1e-6).all()
+    (uu, r), _ = c.solve_CLF_QP(x)
+    g = Lf[:, 0, 0] + (Lg[:, 0] * uu).sum(1) + 1.0 * Vv - r[:, 0]
+    assert (g < 1e-4).all() and (r >= 0).all()
+
+
+def test_steer_reference_loop_equals_fused(stack):
+    env, robot, dyn, ctrl = stack("panda")
+    from cbfrrt.motion_planning.baseline import steer, steer_fused, batch_steer, batch_steer_fused
+    x = dyn.sample_state_space(200)
+    safe = dyn.safe_mask(x)
+    xs = x[safe]
+    n_coll = 0
+    for i in range(6):
+        start, target = xs[2 * i].numpy(), xs[2 * i + 1].numpy()
+        x_last, ok, td, x_list = steer(ctrl.u, dyn, target, start, RRT_step=30, device="cpu")
+        x_last2, ok2, td2, x_list2 = steer_fused(ctrl, dyn, target, start, RRT_step=30)
+        assert ok == ok2 and len(x_list) == len(x_list2)
+        assert np.abs(np.asarray(x_list[1:]) - np.asarray(x_list2[1:])).max() < 1e-5 if len(x_list) > 1 else True
+        assert {"complete_sample", "cl_dynamics", "collision_checking", "nn_forward", "QP"} <= set(td)
+        assert np.array_equal(x_list[0], start) and 2 <= len(x_list) <= 31
+        n_coll += (not ok)
+    # nominal (line) steering uses the same loop with dynamics_model.u_nominal (tsa.py:179-181)
+    x_last, ok, td, x_list = steer(dyn.u_nominal, dyn, xs[1].numpy(), xs[0].numpy(), RRT_step=30, device="cpu")
+    assert len(x_list) >= 2 and "u" in td
+    # batched steer: same rows as the fused launch while nothing collides / sticks
+    starts, targets = xs[:8].numpy(), xs[8:16].numpy()
+    xb, oks, tdb, xs_list = batch_steer(ctrl.u, dyn, targets, starts, RRT_step=8, device="cpu")
+    qf, alive, done, _ = batch_steer_fused(ctrl, dyn, targets, starts, RRT_step=8)
+    assert xb.shape == (8, 7) and len(oks) == 8 and len(xs_list) == 8
+    keep = np.array(oks) & alive.numpy()
+    assert keep.sum() >= 4 and np.abs(xb[keep] - qf.numpy()[keep]).max() < 1e-5
+
+
+def test_edge_checking_reference_loop_equals_batched(stack):
+    env, robot, dyn, ctrl = stack("panda")
+    from cbfrrt.motion_planning.baseline import edge_checking, edge_checking_batch
+    x = dyn.sample_state_space(120)
+    xs = x[dyn.safe_mask(x)].numpy()
+    eps, agree, n_valid = 0.05, 0, 0
+    for i in range(10):
+        a, b = xs[i], xs[i] + 0.5 * (xs[i + 10] - xs[i])
+        K = int(np.linalg.norm(a - b) / eps)
+        ref = edge_checking(a, b, dyn, eps)
+        v, fb = edge_checking_batch(a[None], b[None], dyn, K)
+        agree += (bool(v.item()) == ref)
+        n_valid += ref
+        assert (fb.item() == -1) == bool(v.item())
+    # the reference interpolates in float64 on the host, the kernel in float32: allow one borderline flip
+    assert agree >= 9 and 0 < n_valid < 10
+
+
+def test_basic_robot_kinematics(stack, models):
+    env, robot, dyn, ctrl = stack("panda")
+    from oracle import oracle_f64 as o
+    q = np.array(robot.q0)
+    links = robot.forward_kinematics([0, 6, 7, 8, 11], q)
+    fr = o.fk(models["panda"], q)
+    for (p, R), l in zip(links, [0, 6, 7, 8, 11]):
+        assert np.allclose(p, fr[l][:3, 3], atol=2e-6) and np.allclose(R, fr[l][:3, :3], atol=2e-6)
+    assert np.allclose(robot.get_joint_position(robot.body_joints), q)
+    # Jacobian vs finite differences of the float64 FK
+    J_lin, J_ang = robot.get_jacobian(list(q), 7, [0.0, 0.0, 0.05])
+    assert J_lin.shape == (3, 7) and J_ang.shape == (3, 7)
+    def point(qq):
+        f = o.fk(models["panda"], qq)[7]
+        return f[:3, :3] @ np.array([0, 0, 0.05]) + f[:3, 3]
+    for j in range(7):
+        d = np.zeros(7); d[j] = 1e-6
+        assert np.allclose((point(q + d) - point(q - d)) / 2e-6, J_lin[:, j], atol=1e-5)
+    assert isinstance(robot.check_self_collision_free(), bool)
