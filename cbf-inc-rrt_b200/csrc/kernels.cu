@@ -6,10 +6,12 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/cbfrrt.h"
 #include "core.cuh"
 #include "mlp_qp.cuh"
+#include "mlp_tc.cuh"
 
 namespace cbfrrt {
 
@@ -63,7 +65,7 @@ struct NetArgs {
 };
 
 // dynamic smem carve-up (all offsets in floats, every region 16-byte aligned):
-//   [mbarrier 4][base_min reduce NT/32 + 4][boxes 8*n_boxes][spheres 4*n_spheres][weights][params][scratch H*NT]
+//   [mbarrier 4][base_min reduce 12][boxes 8*n_boxes][spheres 4*n_spheres][weights][params][scratch H*NT]
 struct Smem {
     uint64_t* bar;
     float* red;
@@ -74,13 +76,13 @@ struct Smem {
     float* scratch;
 };
 __host__ __device__ inline size_t smem_floats(int n_boxes, int n_spheres, int w_floats, int p_floats, int scr_floats) {
-    return 4 + 8 + (size_t)8 * n_boxes + (size_t)4 * n_spheres + w_floats + p_floats + scr_floats;
+    return 4 + 12 + (size_t)8 * n_boxes + (size_t)4 * n_spheres + w_floats + p_floats + scr_floats;
 }
 __device__ __forceinline__ Smem carve(float* base, int n_boxes, int n_spheres, int w_floats, int p_floats) {
     Smem s;
     s.bar = reinterpret_cast<uint64_t*>(base);
     s.red = base + 4;
-    s.boxes = base + 12;
+    s.boxes = base + 16;
     s.spheres = s.boxes + 8 * n_boxes;
     s.weights = s.spheres + 4 * n_spheres;
     s.params = s.weights + w_floats;
@@ -90,7 +92,7 @@ __device__ __forceinline__ Smem carve(float* base, int n_boxes, int n_spheres, i
 
 // Stage scene (+ optional weights) with TMA bulk copies signalled on one mbarrier; small parameter vectors are
 // copied by the threads.  Returns after everything is visible to the whole CTA.
-template <int N>
+template <int N, int NTH = NT>
 __device__ __forceinline__ void stage(const Smem& s, const SceneArgs& sc, const NetArgs* net, int w_floats) {
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -107,8 +109,8 @@ __device__ __forceinline__ void stage(const Smem& s, const SceneArgs& sc, const 
     }
     if (net) {
         using PL = ParamLayout<N>;
-        for (int i = tid; i < N * N; i += NT) s.params[PL::K + i] = net->K ? net->K[i] : 0.f;
-        for (int i = tid; i < N; i += NT) {
+        for (int i = tid; i < N * N; i += NTH) s.params[PL::K + i] = net->K ? net->K[i] : 0.f;
+        for (int i = tid; i < N; i += NTH) {
             s.params[PL::LO + i] = net->u_lo[i];
             s.params[PL::HI + i] = net->u_hi[i];
         }
@@ -117,16 +119,16 @@ __device__ __forceinline__ void stage(const Smem& s, const SceneArgs& sc, const 
     __syncthreads();
 }
 
-template <class RB>
+template <class RB, int NTH = NT>
 __device__ __forceinline__ float base_min_cta(const Smem& s, const SceneS& sc) {
-    float m = base_min_partial<RB>(sc, threadIdx.x, NT);
+    float m = base_min_partial<RB>(sc, threadIdx.x, NTH);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
     if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = m;
     __syncthreads();
     float r = s.red[0];
 #pragma unroll
-    for (int w = 1; w < NT / 32; ++w) r = fminf(r, s.red[w]);
+    for (int w = 1; w < NTH / 32; ++w) r = fminf(r, s.red[w]);
     return r;
 }
 
@@ -306,6 +308,91 @@ __global__ void __launch_bounds__(NT) safety_kernel(SceneArgs sc, NetArgs net, c
                                       net.penalty, h, J, u, r);
         write_filter<N>(fout, b, h, J, u, r);
     }
+}
+
+
+// ------------------------------------------------------------------ tensor-core (tcgen05) variants
+// Same contracts as filter_kernel / safety_kernel; the MLP of every 128-state tile runs as TF32x3 GEMMs on the
+// tensor cores (mlp_tc.cuh).  One CTA of 384 threads per SM = 3 tile groups sharing the staged weights; all 128
+// threads of a group take part in every tile of that group (idle rows are masked), because the MMAs, the TMEM
+// traffic and the barriers are group-wide.
+constexpr int NTC = tc::NT_TC;
+
+template <int N, int L>
+__device__ __forceinline__ void filter_tile_tc(tc::Ctx<L>& c, const float* prm, const float (&q)[N], float o,
+                                               const float (&dodq)[N], const float (&goal)[N], bool goal_is_uref,
+                                               float lam, float penalty, float& h, float (&J)[N], float (&u)[N], float& r) {
+    float x[N + 1], jac[N + 1];
+#pragma unroll
+    for (int k = 0; k < N; ++k) x[k] = q[k];
+    x[N] = o;
+    tc::mlp_h_jac<N + 1, L>(c, x, h, jac);
+    cbf_filter_post<N>(prm, q, dodq, goal, goal_is_uref, lam, penalty, h, jac, J, u, r);
+}
+
+template <int N, int L>
+__global__ void __launch_bounds__(NTC, 1) filter_kernel_tc(NetArgs net, const float* __restrict__ datax, long long B,
+                                                           FilterOutPtrs out) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, 0, 0, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
+    SceneArgs none{nullptr, nullptr, 0, 0, 0};
+    stage<N, NTC>(s, none, &net, 0);
+    tc::Ctx<L> c;
+    tc::setup<N + 1, L>(c, s.weights, net.weights);
+    const long long n_tiles = (B + tc::M_TILE - 1) / tc::M_TILE;
+    for (long long tile = (long long)blockIdx.x * tc::G + c.g; tile < n_tiles; tile += (long long)gridDim.x * tc::G) {
+        const long long b = tile * tc::M_TILE + c.t;
+        const bool active = b < B;
+        float q[N], dodq[N], g[N], J[N], u[N], h, r, o = 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { q[k] = 0.f; dodq[k] = 0.f; g[k] = 0.f; }
+        if (active) {
+            const float* d = datax + b * (2 * N + 1);
+#pragma unroll
+            for (int k = 0; k < N; ++k) { q[k] = __ldg(d + k); dodq[k] = __ldg(d + N + 1 + k); }
+            o = __ldg(d + N);
+            load_goal<N>(net, b, g);
+        }
+        filter_tile_tc<N, L>(c, s.params, q, o, dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
+        if (active) write_filter<N>(out, b, h, J, u, r);
+    }
+    tc::teardown<L>(c);
+}
+
+template <class RB, int L>
+__global__ void __launch_bounds__(NTC, 1) safety_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q,
+                                                           long long q_stride, long long B, float thr_soft, float thr_hard,
+                                                           CollideOutPtrs cout, FilterOutPtrs fout) {
+    constexpr int N = RB::N;
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
+    stage<N, NTC>(s, sc, &net, 0);
+    const SceneS sv = scene_view(s, sc);
+    const float base_min = base_min_cta<RB, NTC>(s, sv);
+    tc::Ctx<L> c;
+    tc::setup<N + 1, L>(c, s.weights, net.weights);
+    const long long n_tiles = (B + tc::M_TILE - 1) / tc::M_TILE;
+    for (long long tile = (long long)blockIdx.x * tc::G + c.g; tile < n_tiles; tile += (long long)gridDim.x * tc::G) {
+        const long long b = tile * tc::M_TILE + c.t;
+        const bool active = b < B;
+        float qq[N], g[N], J[N], u[N], h, r;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { qq[k] = 0.f; g[k] = 0.f; }
+        CollideResult<RB> cr;
+        cr.o = 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) cr.dodq[k] = 0.f;
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) qq[k] = __ldg(q + b * q_stride + k);
+            collide_state<RB, true, false>(qq, sv, base_min, cr);
+            write_collide<RB>(cout, b, qq, cr, thr_soft, thr_hard);
+            load_goal<N>(net, b, g);
+        }
+        filter_tile_tc<N, L>(c, s.params, qq, cr.o, cr.dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
+        if (active) write_filter<N>(fout, b, h, J, u, r);
+    }
+    tc::teardown<L>(c);
 }
 
 // edge validity: one thread per (edge, point); point k in [0, K] (K = end point).  A CTA owns EPB whole edges
@@ -542,6 +629,18 @@ static int grid_for(Kern kern, size_t smem, long long tiles) {
     return (int)g;
 }
 
+// tensor-core kernels: one 384-thread CTA per SM (it owns all 512 TMEM columns), 3 tiles of 128 rows per pass
+template <class Kern>
+static int grid_for_tc(Kern kern, size_t smem, long long rows) {
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    }
+    const long long tiles = (rows + tc::M_TILE - 1) / tc::M_TILE;
+    long long g = (tiles + tc::G - 1) / tc::G;
+    if (g > num_sms()) g = num_sms();
+    return (int)(g < 1 ? 1 : g);
+}
+
 static int finish_launch() {
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -606,8 +705,26 @@ static int launch_collide(const SceneArgs& sc, const float* q, long long qs, lon
     return finish_launch();
 }
 
+// CBFRRT_MLP=fma selects the FP32-FMA MLP kernels (A/B comparisons); default is the tcgen05 path
+static bool use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CBFRRT_MLP");
+        v = (e && e[0] == 'f') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 template <int N>
 static int launch_filter(const NetArgs& net, const float* datax, long long B, const FilterOutPtrs& out, cudaStream_t st) {
+    if (use_tc()) {
+        const size_t smem = 4 * smem_floats(0, 0, tc::Layout<2>::TOTAL, ParamLayout<N>::TOTAL, 0);
+        auto k = filter_kernel_tc<N, 2>;
+        const int grid = grid_for_tc(k, smem, B);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, NTC, smem, st>>>(net, datax, B, out);
+        return finish_launch();
+    }
     using LY = NetLayout<N + 1, 48, 2>;
     const size_t smem = 4 * smem_floats(0, 0, LY::TOTAL, ParamLayout<N>::TOTAL, 48 * NT);
     auto k = filter_kernel<N, 48, 2>;
@@ -620,6 +737,14 @@ static int launch_filter(const NetArgs& net, const float* datax, long long B, co
 template <class RB>
 static int launch_safety(const SceneArgs& sc, const NetArgs& net, const float* q, long long qs, long long B, float ts,
                          float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, cudaStream_t st) {
+    if (use_tc()) {
+        const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
+        auto k = safety_kernel_tc<RB, 2>;
+        const int grid = grid_for_tc(k, smem, B);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, NTC, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo);
+        return finish_launch();
+    }
     using LY = NetLayout<RB::N + 1, 48, 2>;
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<RB::N>::TOTAL, 48 * NT);
     auto k = safety_kernel<RB, 48, 2>;

@@ -209,18 +209,12 @@ __device__ __forceinline__ void qp_solve(const float (&a)[N], const float (&uref
     for (int i = 0; i < N; ++i) u[i] = fminf(fmaxf(fmaf(-hm, a[i], uref[i]), lo[i]), hi[i]);
 }
 
-// datax = [q | o | do/dq]  ->  h, J, u, r   (one controller.u call of the reference)
-template <int N, int H, int L, int NT>
-__device__ __forceinline__ void cbf_filter_state(const float* __restrict__ w, const float* __restrict__ prm,
-                                                 float* __restrict__ scr, const float (&q)[N], float o,
-                                                 const float (&dodq)[N], const float (&goal)[N], bool goal_is_uref,
-                                                 float lam, float penalty, float& h, float (&J)[N], float (&u)[N],
-                                                 float& r) {
-    float x[N + 1], jac[N + 1];
-#pragma unroll
-    for (int k = 0; k < N; ++k) x[k] = q[k];
-    x[N] = o;
-    mlp_h_jac<N + 1, H, L, NT>(w, scr, x, h, jac);
+// everything after the MLP: J = Jh_q + Jh_o do/dq, nominal control, QP
+template <int N>
+__device__ __forceinline__ void cbf_filter_post(const float* __restrict__ prm, const float (&q)[N], const float (&dodq)[N],
+                                                const float (&goal)[N], bool goal_is_uref, float lam, float penalty,
+                                                float h, const float (&jac)[N + 1], float (&J)[N], float (&u)[N],
+                                                float& r) {
 #pragma unroll
     for (int k = 0; k < N; ++k) J[k] = fmaf(jac[N], dodq[k], jac[k]);
     using PL = ParamLayout<N>;
@@ -234,6 +228,21 @@ __device__ __forceinline__ void cbf_filter_state(const float* __restrict__ w, co
         if (goal_is_uref) uref[i] = goal[i];  // caller-supplied u_ref is used verbatim (clf_controller.py:497-504)
     }
     qp_solve<N>(J, uref, prm + PL::LO, prm + PL::HI, lam * h, fminf(penalty, 1e6f), u, r);
+}
+
+// datax = [q | o | do/dq]  ->  h, J, u, r   (one controller.u call of the reference); FP32-FMA MLP
+template <int N, int H, int L, int NT>
+__device__ __forceinline__ void cbf_filter_state(const float* __restrict__ w, const float* __restrict__ prm,
+                                                 float* __restrict__ scr, const float (&q)[N], float o,
+                                                 const float (&dodq)[N], const float (&goal)[N], bool goal_is_uref,
+                                                 float lam, float penalty, float& h, float (&J)[N], float (&u)[N],
+                                                 float& r) {
+    float x[N + 1], jac[N + 1];
+#pragma unroll
+    for (int k = 0; k < N; ++k) x[k] = q[k];
+    x[N] = o;
+    mlp_h_jac<N + 1, H, L, NT>(w, scr, x, h, jac);
+    cbf_filter_post<N>(prm, q, dodq, goal, goal_is_uref, lam, penalty, h, jac, J, u, r);
 }
 
 }  // namespace cbfrrt

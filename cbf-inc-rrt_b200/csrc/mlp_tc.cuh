@@ -1,0 +1,374 @@
+// mlp_tc.cuh -- the barrier MLP (value + exact reverse-mode Jacobian) on the 5th-generation tensor cores.
+//
+// A group of 128 threads (4 warps) owns a tile of 128 states = the M dimension of one tcgen05.mma; a CTA runs
+// G = 3 such groups that share the staged weights (12 warps per SM, one CTA per SM, 480 of the 512 TMEM columns).
+// Every layer of
+//     h = w3 . relu(W2 relu(W1 relu(W0 x + b0) + b1) + b2) + b3        (neural_mindis_cbf_controller.py:41-53)
+// and of its reverse-mode Jacobian (:93-96) is a [128 x K] . [K x N] GEMM with K in {8, 48}, N in {16, 48}:
+//   * A operand (activations / back-propagated gradient) lives in TENSOR MEMORY: thread t writes its row with
+//     tcgen05.st 32x32b (lane t, one column per K element) -- no shared-memory round trip for activations;
+//   * B operand (weights) in shared memory, canonical no-swizzle K-major layout W4[k/4][n] (core matrix = 8 rows
+//     x 16 bytes).  kind::tf32 returned zeros for MN-major (transposed) B in every descriptor variant probed
+//     (tools/tc_probe.cu), so the backward GEMMs read a second, transposed copy of each weight matrix;
+//   * accumulator D [128 lanes x 48 columns] fp32 in TMEM, read back with tcgen05.ld 32x32b (thread t <-> lane t),
+//     bias / ReLU / ReLU-mask epilogue in registers;
+//   * kind::tf32 with the 3-term split  a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo  (hi = cvt.rna.tf32, lo = a - hi,
+//     exact in fp32): ~2^-22 relative per product, i.e. fp32-grade, which the 1e-5 tolerance on h / J / u needs
+//     (a single TF32 pass is 2^-11: measured 5.6e-3 absolute on |D| ~ 8 in tools/tc_probe.cu);
+//   * one thread per group issues the MMAs of a layer and commits them to the group's mbarrier.
+// The 1 x 48 output layer and the seed of the backward pass stay on the CUDA cores (N = 1 is not an MMA shape).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mlp_qp.cuh"
+
+namespace cbfrrt {
+namespace tc {
+
+constexpr int M_TILE = 128;
+constexpr int G = 3;                       // tile groups per CTA
+constexpr int NT_TC = G * M_TILE;          // 384 threads
+constexpr int H = 48;                      // hidden width (validated on the host: only 48 x 2 is built)
+constexpr int KIN = 16;                    // padded N of the last backward GEMM (dh/dx has N_IN <= 8 real columns)
+constexpr int COLS_PER_TILE = 160;         // D 0..47 | pad | A_hi 64..111 | A_lo 112..159
+constexpr int COL_D = 0, COL_AHI = 64, COL_ALO = 112;
+constexpr int TMEM_COLS = 512;
+
+// ---- shared-memory carve-up of the tensor-core MLP region (floats, every sub-region 16-byte aligned)
+template <int L>
+struct Layout {
+    static constexpr int MAT = H * H;                         // one 48 x 48 tile (hi or lo)
+    static constexpr int W_F = 0;                             // forward tiles  [l][hi|lo]  W4[k/4][n]
+    static constexpr int W_T = W_F + L * 2 * MAT;             // transposed tiles [l][hi|lo]  (W^T)4[j/4][k]
+    static constexpr int WIN_F = W_T + L * 2 * MAT;           // [hi|lo] [2][48] float4   (K = 8, N = 48)
+    static constexpr int WIN_T = WIN_F + 2 * 8 * H;           // [hi|lo] [12][16] float4  (K = 48, N = 16)
+    static constexpr int BIAS = WIN_T + 2 * KIN * H;          // b_in[48], b_l[48] x L, w_out[48], b_out (padded to 4)
+    static constexpr int MBAR = BIAS + (L + 2) * H + 4;       // G 64-bit mbarriers
+    static constexpr int TMEM_PTR = MBAR + 2 * G + 2;
+    static constexpr int TOTAL = (TMEM_PTR + 4 + 3) & ~3;
+};
+
+// ---- PTX wrappers
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // UMMA shared-memory descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), no swizzle
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t instr_desc(int n) {
+    // c_format F32 [4,6) = 1, a_format TF32 [7,10) = 2, b_format TF32 [10,13) = 2, A/B K-major, N>>3 [17,23), M>>4 [24,29)
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(M_TILE >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init1(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// barrier over the 128 threads of one tile group (named barriers 1..G; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(M_TILE) : "memory"); }
+// true if `pred` holds for any thread of the group
+__device__ __forceinline__ bool group_any(int g, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "bar.red.or.pred q, %2, %3, p;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"((uint32_t)pred), "r"(g + 1), "r"(M_TILE)
+        : "memory");
+    return r != 0;
+}
+
+// ---- per-thread view of its tile group
+template <int L>
+struct Ctx {
+    float* base;       // start of the TC region in shared memory
+    uint32_t tmem;     // TMEM address of column 0 of this group's slice (lane field = 0)
+    uint32_t lane;     // this thread's warp lane-quarter base, pre-shifted (<< 16)
+    uint32_t phase;    // parity of the next MMA-completion wait
+    int g, t;          // group index, row within the tile
+    __device__ __forceinline__ float* w_f(int l, int lo) const { return base + Layout<L>::W_F + (2 * l + lo) * Layout<L>::MAT; }
+    __device__ __forceinline__ float* w_t(int l, int lo) const { return base + Layout<L>::W_T + (2 * l + lo) * Layout<L>::MAT; }
+    __device__ __forceinline__ float* win_f(int lo) const { return base + Layout<L>::WIN_F + lo * 8 * H; }
+    __device__ __forceinline__ float* win_t(int lo) const { return base + Layout<L>::WIN_T + lo * KIN * H; }
+    __device__ __forceinline__ const float* bias(int l) const { return base + Layout<L>::BIAS + l * H; }  // 0: b_in, 1..L, L+1: w_out, L+2: b_out
+    __device__ __forceinline__ uint64_t* mbar() const { return reinterpret_cast<uint64_t*>(base + Layout<L>::MBAR) + g; }
+    __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(base + Layout<L>::TMEM_PTR); }
+};
+
+// tile index of element (n, k) in the K-major no-swizzle layout with NROWS rows:  W4[k/4][n]
+__device__ __forceinline__ int tile_idx(int n, int k, int nrows) { return ((k >> 2) * nrows + n) * 4 + (k & 3); }
+
+// Stage the packed fp32 weights (global memory, layout of include/cbfrrt.h) as hi / lo TF32 tiles (forward and
+// transposed), allocate TMEM, init the MMA mbarriers.  Called by all NT_TC threads once; ends with a __syncthreads().
+template <int N_IN, int L>
+__device__ __forceinline__ void setup(Ctx<L>& c, float* region, const float* __restrict__ wg) {
+    using LY = NetLayout<N_IN, H, L>;
+    const int tid = threadIdx.x;
+    c.base = region;
+    c.phase = 0;
+    c.g = tid / M_TILE;
+    c.t = tid % M_TILE;
+    for (int i = tid; i < H * 8; i += NT_TC) {               // input layer, forward: n = 0..47, k = 0..7
+        const int n = i / 8, k = i % 8;
+        const float w = (k < N_IN) ? __ldg(wg + LY::W_IN + n * LY::IN_PAD + k) : 0.f;
+        const float hi = rna_tf32(w);
+        c.win_f(0)[tile_idx(n, k, H)] = hi;
+        c.win_f(1)[tile_idx(n, k, H)] = w - hi;
+    }
+    for (int i = tid; i < KIN * H; i += NT_TC) {             // input layer, transposed: n' = 0..15 (input index), k' = 0..47
+        const int np = i / H, kp = i % H;
+        const float w = (np < N_IN) ? __ldg(wg + LY::W_IN + kp * LY::IN_PAD + np) : 0.f;
+        const float hi = rna_tf32(w);
+        c.win_t(0)[tile_idx(np, kp, KIN)] = hi;
+        c.win_t(1)[tile_idx(np, kp, KIN)] = w - hi;
+    }
+    for (int l = 0; l < L; ++l) {
+        const float* W = wg + LY::HID0 + l * LY::HID_STRIDE;
+        for (int i = tid; i < H * H; i += NT_TC) {
+            const int n = i / H, k = i % H;
+            const float w = __ldg(W + i);
+            const float hi = rna_tf32(w), lo = w - hi;
+            c.w_f(l, 0)[tile_idx(n, k, H)] = hi;
+            c.w_f(l, 1)[tile_idx(n, k, H)] = lo;
+            c.w_t(l, 0)[tile_idx(k, n, H)] = hi;             // (W^T)[k][n] = W[n][k]
+            c.w_t(l, 1)[tile_idx(k, n, H)] = lo;
+        }
+    }
+    float* b = region + Layout<L>::BIAS;
+    for (int i = tid; i < H; i += NT_TC) {
+        b[i] = __ldg(wg + LY::B_IN + i);
+        for (int l = 0; l < L; ++l) b[(l + 1) * H + i] = __ldg(wg + LY::HID0 + l * LY::HID_STRIDE + H * H + i);
+        b[(L + 1) * H + i] = __ldg(wg + LY::W_OUT + i);
+    }
+    if (tid == 0) {
+        b[(L + 2) * H] = __ldg(wg + LY::B_OUT);
+        for (int g = 0; g < G; ++g) mbar_init1(reinterpret_cast<uint64_t*>(region + Layout<L>::MBAR) + g);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) tmem_alloc(c.tmem_slot(), TMEM_COLS);      // warp 0 allocates (and later frees)
+    fence_proxy_async();                                     // weight tiles (generic proxy) -> tensor-core (async) proxy
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    c.tmem = *c.tmem_slot() + c.g * COLS_PER_TILE;
+    c.lane = (uint32_t)(c.t & ~31) << 16;
+}
+
+template <int L>
+__device__ __forceinline__ void teardown(Ctx<L>& c) {
+    fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(*c.tmem_slot(), TMEM_COLS);
+}
+
+// write this thread's K values as the hi / lo rows of the A operand in tensor memory
+template <int K, int L>
+__device__ __forceinline__ void store_a(const Ctx<L>& c, const float* v) {
+    static_assert(K == 8 || K % 16 == 0, "");
+    const uint32_t row = c.tmem + c.lane;
+    if constexpr (K == 8) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { hi[k] = rna_tf32(v[k]); lo[k] = v[k] - hi[k]; }
+        tmem_st8(row + COL_AHI, hi);
+        tmem_st8(row + COL_ALO, lo);
+    } else {
+#pragma unroll
+        for (int j = 0; j < K / 16; ++j) {   // 16 columns at a time keeps the hi / lo temporaries at 32 registers
+            float hi[16], lo[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { hi[k] = rna_tf32(v[16 * j + k]); lo[k] = v[16 * j + k] - hi[k]; }
+            tmem_st16(row + COL_AHI + 16 * j, hi);
+            tmem_st16(row + COL_ALO + 16 * j, lo);
+        }
+    }
+    tmem_st_wait();
+}
+
+// D[128 x N] = A[128 x K] . B^T with the 3-term split.  B tile: K-major no-swizzle with NROWS (= N) rows:
+// LBO = NROWS*16 B between K-chunks of 4, SBO = 128 B between 8-row groups, a K = 8 step advances 2 chunks.
+template <int K, int N, int L>
+__device__ __forceinline__ void gemm(Ctx<L>& c, const float* w_hi, const float* w_lo) {
+    fence_before_sync();
+    group_sync(c.g);
+    if (c.t == 0) {
+        fence_after_sync();
+        constexpr uint32_t idesc = instr_desc(N);
+        constexpr uint32_t B_LBO = N * 16, B_SBO = 128, B_STEP = 2 * N * 16;
+        const uint32_t b_hi = smem_addr(w_hi), b_lo = smem_addr(w_lo);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const uint32_t a0 = c.tmem + ((t == 1) ? COL_ALO : COL_AHI);
+            const uint32_t b0 = (t == 2) ? b_lo : b_hi;
+#pragma unroll
+            for (int ks = 0; ks < K / 8; ++ks)
+                mma_tf32_ts(c.tmem + COL_D, a0 + 8 * ks, smem_desc(b0 + ks * B_STEP, B_LBO, B_SBO), idesc, (t | ks) ? 1u : 0u);
+        }
+        mma_commit(c.mbar());
+    }
+    mbar_wait_parity(c.mbar(), c.phase);
+    c.phase ^= 1u;
+    fence_after_sync();
+}
+
+// read this thread's row (lane) of the accumulator: NCOL columns (multiple of 16)
+template <int NCOL, int L>
+__device__ __forceinline__ void load_d(const Ctx<L>& c, float* v) {
+    const uint32_t row = c.tmem + c.lane + COL_D;
+#pragma unroll
+    for (int j = 0; j < NCOL / 16; ++j) tmem_ld16(row + 16 * j, v + 16 * j);
+    tmem_ld_wait();
+}
+
+template <int L>
+__device__ __forceinline__ uint64_t bias_relu(const Ctx<L>& c, int layer, float (&v)[H]) {
+    uint64_t m = 0;
+    const float4* b4 = reinterpret_cast<const float4*>(c.bias(layer));
+#pragma unroll
+    for (int k4 = 0; k4 < H / 4; ++k4) {
+        const float4 b = b4[k4];
+        const float s0 = v[4 * k4] + b.x, s1 = v[4 * k4 + 1] + b.y, s2 = v[4 * k4 + 2] + b.z, s3 = v[4 * k4 + 3] + b.w;
+        m |= ((uint64_t)(s0 > 0.f) << (4 * k4)) | ((uint64_t)(s1 > 0.f) << (4 * k4 + 1)) |
+             ((uint64_t)(s2 > 0.f) << (4 * k4 + 2)) | ((uint64_t)(s3 > 0.f) << (4 * k4 + 3));
+        v[4 * k4] = fmaxf(s0, 0.f); v[4 * k4 + 1] = fmaxf(s1, 0.f); v[4 * k4 + 2] = fmaxf(s2, 0.f); v[4 * k4 + 3] = fmaxf(s3, 0.f);
+    }
+    return m;
+}
+
+// value h and Jacobian dh/dx for this thread's x = [q, o]; every thread of the tile group must call it (idle
+// rows pass zeros).  Same contract as mlp_h_jac (mlp_qp.cuh).
+template <int N_IN, int L>
+__device__ __forceinline__ void mlp_h_jac(Ctx<L>& c, const float (&x)[N_IN], float& h_out, float (&jac)[N_IN]) {
+    static_assert(N_IN <= 8, "first layer is one K = 8 MMA step");
+    float v[H];
+    uint64_t mask[L + 1];
+    // ---- input layer: K = 8 (zero padded), N = 48
+    {
+        float xin[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xin[k] = (k < N_IN) ? x[k < N_IN ? k : 0] : 0.f;
+        store_a<8>(c, xin);
+        gemm<8, H>(c, c.win_f(0), c.win_f(1));
+        load_d<H>(c, v);
+        mask[0] = bias_relu(c, 0, v);
+    }
+    // ---- hidden layers
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        store_a<H>(c, v);
+        gemm<H, H>(c, c.w_f(l, 0), c.w_f(l, 1));
+        load_d<H>(c, v);
+        mask[l + 1] = bias_relu(c, l + 1, v);
+    }
+    // ---- output layer (N = 1) and seed of the backward pass on the CUDA cores
+    {
+        const float4* w4 = reinterpret_cast<const float4*>(c.bias(L + 1));
+        float s0 = c.bias(L + 2)[0], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        const uint64_t m = mask[L];
+#pragma unroll
+        for (int k4 = 0; k4 < H / 4; ++k4) {
+            const float4 w = w4[k4];
+            s0 = fmaf(w.x, v[4 * k4], s0); s1 = fmaf(w.y, v[4 * k4 + 1], s1);
+            s2 = fmaf(w.z, v[4 * k4 + 2], s2); s3 = fmaf(w.w, v[4 * k4 + 3], s3);
+            v[4 * k4] = ((m >> (4 * k4)) & 1) ? w.x : 0.f;
+            v[4 * k4 + 1] = ((m >> (4 * k4 + 1)) & 1) ? w.y : 0.f;
+            v[4 * k4 + 2] = ((m >> (4 * k4 + 2)) & 1) ? w.z : 0.f;
+            v[4 * k4 + 3] = ((m >> (4 * k4 + 3)) & 1) ? w.w : 0.f;
+        }
+        h_out = (s0 + s1) + (s2 + s3);
+    }
+    // ---- backward through the hidden layers: g_prev = relu'_prev * (W^T g)
+#pragma unroll
+    for (int l = L - 1; l >= 0; --l) {
+        store_a<H>(c, v);
+        gemm<H, H>(c, c.w_t(l, 0), c.w_t(l, 1));
+        load_d<H>(c, v);
+        const uint64_t m = mask[l];
+#pragma unroll
+        for (int k = 0; k < H; ++k) v[k] = ((m >> k) & 1) ? v[k] : 0.f;
+    }
+    // ---- input layer backward: jac = W_in^T g   (N = KIN = 16 columns, the first N_IN are real)
+    store_a<H>(c, v);
+    gemm<H, KIN>(c, c.win_t(0), c.win_t(1));
+    float j16[KIN];
+    load_d<KIN>(c, j16);
+#pragma unroll
+    for (int k = 0; k < N_IN; ++k) jac[k] = j16[k];
+}
+
+}  // namespace tc
+}  // namespace cbfrrt

@@ -57,20 +57,21 @@ def rel_err(a, b, floor=1.0):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
 
 
-def assert_controls_match(coracle, u, r, h, J, o, uref, u_lo, u_hi, lam, penalty, tol=1e-5):
+def assert_controls_match(coracle, u, r, h, J, o, uref, u_lo, u_hi, lam, penalty, tol=1e-5, frac=0.995):
     """QP parity, conditioning-aware.
 
     (1) On EXACTLY the (h, J) the CUDA MLP produced, the CUDA controls must equal the exact (float64 KKT) QP
         solution within ``tol`` on every row.
     (2) Against the oracle's end-to-end controls (its own float32 MLP, different summation order) the same bound
-        must hold on >= 99.5 % of the rows and 1e-3 everywhere: when a free axis has a tiny |Lg_i| the QP divides
-        the ~1e-7 relative difference of the two MLP evaluations by |Lg_i|, which no arithmetic on either side
-        can avoid (DESIGN.md "Tolerances").
+        must hold on >= ``frac`` of the rows and 1e-3 everywhere: when a free axis has a tiny |Lg_i| the QP divides
+        the ~1e-7 (FMA path) / ~1e-6 (TF32x3 tensor-core path) relative difference of the two MLP evaluations by
+        |Lg_i|, which no arithmetic on either side can avoid (DESIGN.md "Tolerances").  frac = 0.995 on the
+        BASELINE configs; the stress inputs with do/dq ~ 3 N(0,1) use 0.97.
     """
     u, r, h, J = (np.asarray(x.cpu().numpy() if hasattr(x, "cpu") else x) for x in (u, r, h, J))
     ue, re_ = coracle.qp(J, lam * h.astype(np.float32), uref, u_lo, u_hi, penalty)
     assert rel_err(u, ue) < tol, rel_err(u, ue)
     assert rel_err(r, re_, floor=0.1) < tol
     e = np.max(np.abs(u.astype(np.float64) - o["u"]) / np.maximum(np.abs(o["u"]), 1.0), axis=1)
-    assert (e < tol).mean() >= 0.995 and e.max() < 1e-3, ((e < tol).mean(), e.max())
+    assert (e < tol).mean() >= frac and e.max() < 1e-3, ((e < tol).mean(), e.max())
     assert np.abs(r - o["r"]).max() < 1e-3

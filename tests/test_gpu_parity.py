@@ -145,14 +145,14 @@ def test_cbf_filter_matches_oracle(coracle, robot, B):
         o = coracle.cbf_filter(n, w["weights"], 48, 2, datax, goal_np, w["K"], w["u_lo"], w["u_hi"], lam, pen)
         assert rel_err(h.cpu().numpy(), o["h"], floor=0.1) < TOL and rel_err(J.cpu().numpy(), o["J"], floor=0.1) < TOL
         uref_n = coracle.u_nominal(datax[:, :n], goal_np, w["K"], w["u_lo"], w["u_hi"])
-        assert_controls_match(coracle, u, r, h, J, o, uref_n, w["u_lo"], w["u_hi"], lam, pen)
+        assert_controls_match(coracle, u, r, h, J, o, uref_n, w["u_lo"], w["u_hi"], lam, pen, frac=0.97)
         assert (np.abs(o["u"] - np.clip(-(datax[:, :n] - goal_np) @ w["K"].T, w["u_lo"], w["u_hi"])).max(1) > 1e-4).sum() > B // 20
     # caller-supplied u_ref (solve_CLF_QP(u_ref=...))
     uref = rng.uniform(-1, 1, (B, n)).astype(np.float32)
     h, J, u, r = ops.cbf_filter(_t(datax), _t(goal[:1]), _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), 1.0, 5000.0,
                                 48, 2, _t(uref))
     o = coracle.cbf_filter(n, w["weights"], 48, 2, datax, goal[:1], w["K"], w["u_lo"], w["u_hi"], 1.0, 5000.0, u_ref=uref)
-    assert_controls_match(coracle, u, r, h, J, o, uref, w["u_lo"], w["u_hi"], 1.0, 5000.0)
+    assert_controls_match(coracle, u, r, h, J, o, uref, w["u_lo"], w["u_hi"], 1.0, 5000.0, frac=0.97)
 
 
 def test_qp_op_matches_oracle_semantics(coracle):
