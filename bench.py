@@ -189,8 +189,9 @@ def main():
         q = torch.as_tensor(q_np, device=dev)
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
     b8, s4 = ops.pack_scene(w["boxes"][:, :3], w["boxes"][:, 3:], w["spheres"], device=dev)
+    gr = ops.build_grid(b8, s4) if b8.shape[0] + s4.shape[0] > 0 else ops.no_grid(dev)
     net, goal, K, lo, hi = ops.pack_weights(w["state_dict"], n, 48, 2, device=dev), t(w["goal"]), t(w["K"]), t(w["u_lo"]), t(w["u_hi"])
-    common = (goal, b8, s4, 1, net, K, lo, hi, w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
+    common = (goal, b8, s4, 1, gr, net, K, lo, hi, w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     if world == 1:

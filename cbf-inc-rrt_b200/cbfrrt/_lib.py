@@ -15,7 +15,7 @@ STATUS = {0: "ok", -1: "unknown robot id", -2: "bad shape or missing pointer",
 
 class Scene(C.Structure):
     _fields_ = [("n_boxes", C.c_int32), ("n_spheres", C.c_int32), ("floor", C.c_int32), ("_pad", C.c_int32),
-                ("boxes", C.c_void_p), ("spheres", C.c_void_p)]
+                ("boxes", C.c_void_p), ("spheres", C.c_void_p), ("grid", C.c_void_p)]
 
 
 class HostScene(C.Structure):
@@ -47,6 +47,8 @@ SIGNATURES = {
     "cbfrrt_last_cuda_error": (C.c_int, []),
     "cbfrrt_launch_count": (C.c_int64, []),
     "cbfrrt_robot_info": (C.c_int, [_I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "cbfrrt_grid_bytes": (C.c_int64, []),
+    "cbfrrt_grid_build": (C.c_int, [C.POINTER(Scene), _P, _P]),
     "cbfrrt_fk": (C.c_int, [_I, _P, _L, _L, _P, _P, _P]),
     "cbfrrt_collide": (C.c_int, [_I, C.POINTER(Scene), _P, _L, _L, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "cbfrrt_cbf_filter": (C.c_int, [_I, C.POINTER(CbfNet), _P, _L, C.POINTER(FilterParams), _P, _P, _P, _P, _P]),

@@ -121,8 +121,12 @@ class ArmEnv:
         self.obstacle_ids += list(range(first, first + self.obs_positions.shape[0] + self.obs_spheres.shape[0]))
         self.scene_boxes, self.scene_spheres = ops.pack_scene(self.obs_positions, self.obs_sizes, self.obs_spheres,
                                                               device=self.device)
+        # exact broad phase, rebuilt with the scene (one small kernel); CPU tensors (tests with fake ops) get none
+        n_obs = self.scene_boxes.shape[0] + self.scene_spheres.shape[0]
+        self.scene_grid = (ops.build_grid(self.scene_boxes, self.scene_spheres)
+                           if (self.device.type == "cuda" and n_obs > 0) else ops.no_grid(self.device))
 
     @property
     def scene(self):
-        """(boxes (O,8), spheres (P,4), floor) on the GPU, as the ops take them."""
-        return self.scene_boxes, self.scene_spheres, int(self.include_floor)
+        """(boxes (O,8), spheres (P,4), floor, grid) on the GPU, as the ops take them."""
+        return self.scene_boxes, self.scene_spheres, int(self.include_floor), self.scene_grid

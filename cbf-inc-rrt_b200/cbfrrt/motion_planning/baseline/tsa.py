@@ -70,11 +70,11 @@ def steer_fused(controller, dynamics_model, new_state, nearest, RRT_step=10, dev
 
 
 def _rollout(controller, dm, q0, steps, stuck=(0, 10, 0.1), want_traj=False, keep_going=False):
-    b, s, fl = dm.env.scene
+    b, s, fl, gr = dm.env.scene
     lo, hi = controller._limits()
     ctrl_every = int(dm.controller_dt // dm.dt)
     return ops.rollout(q0, dm.goal_tensor(dm.device), int(steps), ctrl_every, float(dm.dt), int(stuck[0]),
-                       int(stuck[1]), float(stuck[2]), bool(want_traj), bool(keep_going), b, s, fl, controller._weights(),
+                       int(stuck[1]), float(stuck[2]), bool(want_traj), bool(keep_going), b, s, fl, gr, controller._weights(),
                        dm.K.to(dm.device, torch.float32), lo, hi, float(controller.clf_lambda),
                        float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard),
                        dm.robot.robot_id, controller.h_hidden_size, controller.h_hidden_layers)
@@ -98,9 +98,9 @@ def edge_checking(state, new_state, dynamics_model, eps):
 def edge_checking_batch(states, new_states, dynamics_model, n_interp):
     """E edges x (n_interp + 1) points in one launch (cbfrrt::edge_validity) -> (valid bool[E], first_bad i32[E])."""
     dm = dynamics_model
-    b, s, fl = dm.env.scene
+    b, s, fl, gr = dm.env.scene
     qf = torch.as_tensor(np.asarray(states), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
     qt = torch.as_tensor(np.asarray(new_states), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
-    valid, first_bad = ops.edge_validity(qf, qt, int(n_interp), b, s, fl, float(dm.dis_threshold), float(dm.thr_hard),
+    valid, first_bad = ops.edge_validity(qf, qt, int(n_interp), b, s, fl, gr, float(dm.dis_threshold), float(dm.thr_hard),
                                          dm.robot.robot_id)
     return valid.bool(), first_bad

@@ -114,8 +114,8 @@ class ArmDynamics(ControlAffineSystem):
 
     def masks(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """(safe, unsafe) in one launch."""
-        b, s, fl = self._scene()
-        safe, unsafe = ops.masks(self._q_on_gpu(x), b, s, fl, float(self.dis_threshold), float(self.thr_hard),
+        b, s, fl, gr = self._scene()
+        safe, unsafe = ops.masks(self._q_on_gpu(x), b, s, fl, gr, float(self.dis_threshold), float(self.thr_hard),
                                  self.robot.robot_id)
         return safe.bool().to(x.device), unsafe.bool().to(x.device)
 
@@ -159,8 +159,8 @@ class ArmDynamics(ControlAffineSystem):
     def _get_sdf(self):
         """arm_dynamics.py:281-291: shortest link-obstacle distance at the current joint state."""
         q = torch.tensor(self.robot.get_joint_position(self.robot.body_joints), dtype=torch.float32).reshape(1, -1)
-        b, s, fl = self._scene()
-        datax = ops.observe(q.to(self.device), b, s, fl, float(self.dis_threshold), float(self.thr_hard),
+        b, s, fl, gr = self._scene()
+        datax = ops.observe(q.to(self.device), b, s, fl, gr, float(self.dis_threshold), float(self.thr_hard),
                             self.robot.robot_id)[2]
         return float(datax[0, self.q_dims].item())
 

@@ -32,8 +32,8 @@ class ArmMindis(ArmDynamics):
 
     def observe(self, x: torch.Tensor):
         """(safe, unsafe, datax) for the batch in one launch."""
-        b, s, fl = self._scene()
-        safe, unsafe, datax = ops.observe(self._q_on_gpu(x), b, s, fl, float(self.dis_threshold),
+        b, s, fl, gr = self._scene()
+        safe, unsafe, datax = ops.observe(self._q_on_gpu(x), b, s, fl, gr, float(self.dis_threshold),
                                           float(self.thr_hard), self.robot.robot_id)
         return safe.bool().to(x.device), unsafe.bool().to(x.device), datax.to(x.device).type_as(x)
 

@@ -45,13 +45,31 @@ def _f32c(t: Tensor) -> Tensor:
     return t.to(dtype=torch.float32).contiguous()
 
 
-def _scene(boxes8: Tensor, spheres: Tensor, floor: int) -> Scene:
+def build_grid(boxes8: Tensor, spheres: Tensor) -> Tensor:
+    """Nearest-candidate grid of a packed scene (include/cbfrrt.h cbfrrt_grid_build).  Returns a uint8 device
+    tensor to be passed as ``grid`` to the scene-consuming ops; an EMPTY tensor means brute force.  Results are
+    bit-identical either way."""
+    dev = boxes8.device
+    g = torch.empty(int(lib.cbfrrt_grid_bytes()), dtype=torch.uint8, device=dev)
+    sc = _scene(boxes8, spheres, 0, torch.empty(0, dtype=torch.uint8, device=dev))
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_grid_build(C.byref(sc), _ptr(g), _stream()), "cbfrrt_grid_build")
+    return g
+
+
+def no_grid(device) -> Tensor:
+    return torch.empty(0, dtype=torch.uint8, device=device)
+
+
+def _scene(boxes8: Tensor, spheres: Tensor, floor: int, grid: Tensor) -> Scene:
     if boxes8.numel() and (boxes8.dim() != 2 or boxes8.shape[1] != 8):
         raise ValueError("boxes must be packed as (Ob, 8): cx cy cz hx hy hz 0 0 (use pack_scene)")
     if spheres.numel() and (spheres.dim() != 2 or spheres.shape[1] != 4):
         raise ValueError("spheres must be (Os, 4): cx cy cz r")
+    if grid.numel() and (grid.dtype != torch.uint8 or grid.numel() != int(lib.cbfrrt_grid_bytes())):
+        raise ValueError("grid must be the uint8 tensor returned by build_grid (or empty)")
     return Scene(int(boxes8.shape[0]) if boxes8.numel() else 0, int(spheres.shape[0]) if spheres.numel() else 0,
-                 int(bool(floor)), 0, _ptr(boxes8).value, _ptr(spheres).value)
+                 int(bool(floor)), 0, _ptr(boxes8).value, _ptr(spheres).value, _ptr(grid).value)
 
 
 def pack_scene(positions, sizes, spheres=None, device="cuda"):
@@ -130,7 +148,7 @@ def fk(q: Tensor, robot_id: int) -> Tuple[Tensor, Tensor]:
 
 
 @torch.library.custom_op("cbfrrt::collide", mutates_args=(), device_types="cuda")
-def collide(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: float, thr_hard: float,
+def collide(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, thr_soft: float, thr_hard: float,
             robot_id: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """-> safe u8[B], unsafe u8[B], datax f32[B,2n+1], arg_link i32[B], arg_obs i32[B], mins f32[B,3]"""
     n = ROBOT_N[robot_id]
@@ -142,7 +160,7 @@ def collide(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: flo
     arg_link = torch.empty(B, dtype=torch.int32, device=dev)
     arg_obs = torch.empty(B, dtype=torch.int32, device=dev)
     mins = torch.empty((B, 3), dtype=torch.float32, device=dev)
-    sc = _scene(boxes, spheres, floor)
+    sc = _scene(boxes, spheres, floor, grid)
     with torch.cuda.device(dev):
         check(lib.cbfrrt_collide(robot_id, C.byref(sc), _ptr(q), qs, B, thr_soft, thr_hard, _ptr(safe), _ptr(unsafe),
                                  _ptr(datax), _ptr(arg_link), _ptr(arg_obs), _ptr(mins), _stream()), "cbfrrt_collide")
@@ -150,7 +168,7 @@ def collide(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: flo
 
 
 @torch.library.custom_op("cbfrrt::observe", mutates_args=(), device_types="cuda")
-def observe(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: float, thr_hard: float,
+def observe(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, thr_soft: float, thr_hard: float,
             robot_id: int) -> Tuple[Tensor, Tensor, Tensor]:
     """-> safe u8[B], unsafe u8[B], datax f32[B,2n+1]   (complete_sample_with_observations + masks)"""
     n = ROBOT_N[robot_id]
@@ -159,7 +177,7 @@ def observe(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: flo
     safe = torch.empty(B, dtype=torch.uint8, device=dev)
     unsafe = torch.empty(B, dtype=torch.uint8, device=dev)
     datax = torch.empty((B, 2 * n + 1), dtype=torch.float32, device=dev)
-    sc = _scene(boxes, spheres, floor)
+    sc = _scene(boxes, spheres, floor, grid)
     with torch.cuda.device(dev):
         check(lib.cbfrrt_collide(robot_id, C.byref(sc), _ptr(q), qs, B, thr_soft, thr_hard, _ptr(safe), _ptr(unsafe),
                                  _ptr(datax), None, None, None, _stream()), "cbfrrt_collide")
@@ -167,7 +185,7 @@ def observe(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: flo
 
 
 @torch.library.custom_op("cbfrrt::masks", mutates_args=(), device_types="cuda")
-def masks(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: float, thr_hard: float,
+def masks(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, thr_soft: float, thr_hard: float,
           robot_id: int) -> Tuple[Tensor, Tensor]:
     """-> safe u8[B], unsafe u8[B]   (safe_mask / unsafe_mask only: no arg-min, no gradient)"""
     n = ROBOT_N[robot_id]
@@ -175,7 +193,7 @@ def masks(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, thr_soft: float
     B, dev = q.shape[0], q.device
     safe = torch.empty(B, dtype=torch.uint8, device=dev)
     unsafe = torch.empty(B, dtype=torch.uint8, device=dev)
-    sc = _scene(boxes, spheres, floor)
+    sc = _scene(boxes, spheres, floor, grid)
     with torch.cuda.device(dev):
         check(lib.cbfrrt_collide(robot_id, C.byref(sc), _ptr(q), qs, B, thr_soft, thr_hard, _ptr(safe), _ptr(unsafe),
                                  None, None, None, None, _stream()), "cbfrrt_collide")
@@ -219,7 +237,7 @@ def qp(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty:
 
 
 @torch.library.custom_op("cbfrrt::safety_filter", mutates_args=(), device_types="cuda")
-def safety_filter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, weights: Tensor, K: Tensor,
+def safety_filter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor, K: Tensor,
                   u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float,
                   robot_id: int, hidden: int, layers: int
                   ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
@@ -228,7 +246,7 @@ def safety_filter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor
     q, qs = _rows(q, n)
     B, dev = q.shape[0], q.device
     net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers)
-    sc = _scene(boxes, spheres, floor)
+    sc = _scene(boxes, spheres, floor, grid)
     safe = torch.empty(B, dtype=torch.uint8, device=dev)
     unsafe = torch.empty(B, dtype=torch.uint8, device=dev)
     datax = torch.empty((B, 2 * n + 1), dtype=torch.float32, device=dev)
@@ -245,7 +263,7 @@ def safety_filter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor
 
 
 @torch.library.custom_op("cbfrrt::valid_control", mutates_args=(), device_types="cuda")
-def valid_control(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, weights: Tensor, K: Tensor,
+def valid_control(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor, K: Tensor,
                   u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float,
                   robot_id: int, hidden: int, layers: int) -> Tuple[Tensor, Tensor]:
     """fused q -> (valid u8[B], u f32[B,n]): the sweep outputs that are all-gathered across GPUs"""
@@ -253,7 +271,7 @@ def valid_control(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor
     q, qs = _rows(q, n)
     B, dev = q.shape[0], q.device
     net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers)
-    sc = _scene(boxes, spheres, floor)
+    sc = _scene(boxes, spheres, floor, grid)
     safe = torch.empty(B, dtype=torch.uint8, device=dev)
     u = torch.empty((B, n), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -266,7 +284,7 @@ def valid_control(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor
 
 @torch.library.custom_op("cbfrrt::edge_validity", mutates_args=(), device_types="cuda")
 def edge_validity(q_from: Tensor, q_to: Tensor, n_interp: int, boxes: Tensor, spheres: Tensor, floor: int,
-                  thr_soft: float, thr_hard: float, robot_id: int) -> Tuple[Tensor, Tensor]:
+                  grid: Tensor, thr_soft: float, thr_hard: float, robot_id: int) -> Tuple[Tensor, Tensor]:
     """-> valid u8[E], first_bad i32[E]"""
     n = ROBOT_N[robot_id]
     q_from, q_to = _f32c(q_from), _f32c(q_to)
@@ -275,7 +293,7 @@ def edge_validity(q_from: Tensor, q_to: Tensor, n_interp: int, boxes: Tensor, sp
     E, dev = q_from.shape[0], q_from.device
     valid = torch.empty(E, dtype=torch.uint8, device=dev)
     first_bad = torch.empty(E, dtype=torch.int32, device=dev)
-    sc = _scene(boxes, spheres, floor)
+    sc = _scene(boxes, spheres, floor, grid)
     with torch.cuda.device(dev):
         check(lib.cbfrrt_edge_validity(robot_id, C.byref(sc), _ptr(q_from), _ptr(q_to), E, n_interp, thr_soft, thr_hard,
                                        _ptr(valid), _ptr(first_bad), _stream()), "cbfrrt_edge_validity")
@@ -284,7 +302,7 @@ def edge_validity(q_from: Tensor, q_to: Tensor, n_interp: int, boxes: Tensor, sp
 
 @torch.library.custom_op("cbfrrt::rollout", mutates_args=(), device_types="cuda")
 def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, stuck_lag: int, stuck_after: int,
-            stuck_eps: float, want_traj: bool, keep_going: bool, boxes: Tensor, spheres: Tensor, floor: int, weights: Tensor, K: Tensor,
+            stuck_eps: float, want_traj: bool, keep_going: bool, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor, K: Tensor,
             u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float, robot_id: int,
             hidden: int, layers: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """the steer loop in one launch -> q_final f32[T,n], alive u8[T], steps_done i32[T], traj f32[T,steps,n]
@@ -295,7 +313,7 @@ def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, st
         raise ValueError(f"q0 must be (T, {n})")
     T, dev = q0.shape[0], q0.device
     net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, T, lam, penalty, hidden, layers)
-    sc = _scene(boxes, spheres, floor)
+    sc = _scene(boxes, spheres, floor, grid)
     rp = RolloutParams(steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, int(keep_going))
     qf = torch.empty((T, n), dtype=torch.float32, device=dev)
     alive = torch.empty(T, dtype=torch.uint8, device=dev)

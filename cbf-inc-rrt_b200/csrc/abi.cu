@@ -1,0 +1,183 @@
+// abi.cu -- the device-pointer C-ABI of libcbfrrt (include/cbfrrt.h): argument validation + dispatch to the
+// launchers.  Kernels live in kernels.cuh; the per-robot instantiations of the big ones are compiled in k_*.cu.
+#include "kernels.cuh"
+
+namespace cbfrrt {
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_last_cuda{0};
+std::mutex g_cfg_mu;
+std::map<std::pair<const void*, size_t>, int> g_cfg;
+}  // namespace cbfrrt
+
+using namespace cbfrrt;
+
+extern "C" {
+
+int cbfrrt_abi_version(void) { return CBFRRT_ABI_VERSION; }
+
+const char* cbfrrt_status_string(int s) {
+    switch (s) {
+        case CBFRRT_OK: return "ok";
+        case CBFRRT_ERR_BAD_ROBOT: return "unknown robot id";
+        case CBFRRT_ERR_BAD_SHAPE: return "bad shape or missing pointer";
+        case CBFRRT_ERR_UNSUPPORTED: return "unsupported network shape or scene size";
+        case CBFRRT_ERR_CUDA: return "CUDA launch/runtime failure";
+        case CBFRRT_ERR_ALIGNMENT: return "scene/weight buffer not 16-byte aligned";
+        default: return "unknown status";
+    }
+}
+
+int cbfrrt_last_cuda_error(void) { return g_last_cuda.load(); }
+int64_t cbfrrt_launch_count(void) { return g_launches.load(); }
+
+int cbfrrt_robot_info(int robot, int32_t* n, int32_t* n_links, int32_t* n_spheres) {
+    if (robot == CBFRRT_ROBOT_PANDA) { *n = Panda::N; *n_links = Panda::NLINKS; *n_spheres = Panda::NSPH; return CBFRRT_OK; }
+    if (robot == CBFRRT_ROBOT_MAGICIAN) { *n = Magician::N; *n_links = Magician::NLINKS; *n_spheres = Magician::NSPH; return CBFRRT_OK; }
+    return CBFRRT_ERR_BAD_ROBOT;
+}
+
+int64_t cbfrrt_grid_bytes(void) { return (int64_t)grid::BYTES; }
+
+int cbfrrt_grid_build(const cbfrrt_scene* scene, void* grid_out, void* stream) {
+    SceneArgs sc;
+    int rc = check_scene(scene, sc);
+    if (rc) return rc;
+    if (!grid_out) return CBFRRT_ERR_BAD_SHAPE;
+    if (!aligned16(grid_out)) return CBFRRT_ERR_ALIGNMENT;
+    grid::build_kernel<<<(grid::NCELLS + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(sc.boxes), sc.n_boxes, reinterpret_cast<const float4*>(sc.spheres), sc.n_spheres,
+        static_cast<uint16_t*>(grid_out));
+    return finish_launch();
+}
+
+int cbfrrt_fk(int robot, const float* q, int64_t q_stride, int64_t B, float* pos, float* rot, void* stream) {
+    if (B < 0 || !q || !pos || !rot) return CBFRRT_ERR_BAD_SHAPE;
+    if (B == 0) return CBFRRT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (robot == CBFRRT_ROBOT_PANDA) return q_stride < Panda::N ? CBFRRT_ERR_BAD_SHAPE : launch_fk<Panda>(q, q_stride, B, pos, rot, st);
+    if (robot == CBFRRT_ROBOT_MAGICIAN) return q_stride < Magician::N ? CBFRRT_ERR_BAD_SHAPE : launch_fk<Magician>(q, q_stride, B, pos, rot, st);
+    return CBFRRT_ERR_BAD_ROBOT;
+}
+
+int cbfrrt_collide(int robot, const cbfrrt_scene* scene, const float* q, int64_t q_stride, int64_t B, float thr_soft,
+                   float thr_hard, uint8_t* safe, uint8_t* unsafe, float* datax, int32_t* arg_link, int32_t* arg_obs,
+                   float* mins, void* stream) {
+    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
+    if (B < 0 || !q) return CBFRRT_ERR_BAD_SHAPE;
+    SceneArgs sc;
+    int rc = check_scene(scene, sc);
+    if (rc) return rc;
+    if (B == 0) return CBFRRT_OK;
+    CollideOutPtrs out{safe, unsafe, datax, arg_link, arg_obs, mins};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (robot == CBFRRT_ROBOT_PANDA) return q_stride < Panda::N ? CBFRRT_ERR_BAD_SHAPE : launch_collide_panda(sc, q, q_stride, B, thr_soft, thr_hard, out, st);
+    return q_stride < Magician::N ? CBFRRT_ERR_BAD_SHAPE : launch_collide_magician(sc, q, q_stride, B, thr_soft, thr_hard, out, st);
+}
+
+int cbfrrt_cbf_filter(int n, const cbfrrt_cbf_net* net, const float* datax, int64_t B, const cbfrrt_filter_params* fp,
+                      float* h, float* J, float* u, float* r, void* stream) {
+    if (B < 0 || !datax) return CBFRRT_ERR_BAD_SHAPE;
+    if (n != Panda::N && n != Magician::N) return CBFRRT_ERR_UNSUPPORTED;
+    NetArgs na;
+    int rc = check_net(n, net, fp, B, na);
+    if (rc) return rc;
+    if (B == 0) return CBFRRT_OK;
+    FilterOutPtrs out{h, J, u, r};
+    cudaStream_t st = (cudaStream_t)stream;
+    return n == Panda::N ? launch_filter<Panda::N>(na, datax, B, out, st) : launch_filter<Magician::N>(na, datax, B, out, st);
+}
+
+int cbfrrt_qp(int n, const float* a, const float* c, const float* u_ref, int64_t B, const float* u_lo, const float* u_hi,
+              float relaxation_penalty, float* u, float* r, void* stream) {
+    if (B < 0 || !a || !c || !u_ref || !u_lo || !u_hi || !u) return CBFRRT_ERR_BAD_SHAPE;
+    if (n < 1 || n > 8) return CBFRRT_ERR_UNSUPPORTED;
+    if (B == 0) return CBFRRT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = (B + 255) / 256;
+    const int grid = (int)(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
+    switch (n) {
+#define CBF_QP_CASE(NN) case NN: qp_kernel<NN><<<grid, 256, 0, st>>>(a, c, u_ref, B, u_lo, u_hi, relaxation_penalty, u, r); break;
+        CBF_QP_CASE(1) CBF_QP_CASE(2) CBF_QP_CASE(3) CBF_QP_CASE(4) CBF_QP_CASE(5) CBF_QP_CASE(6) CBF_QP_CASE(7) CBF_QP_CASE(8)
+#undef CBF_QP_CASE
+    }
+    return finish_launch();
+}
+
+int cbfrrt_safety_filter(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* net, const float* q,
+                         int64_t q_stride, int64_t B, const cbfrrt_filter_params* fp, float thr_soft, float thr_hard,
+                         uint8_t* safe, uint8_t* unsafe, float* datax, float* h, float* J, float* u, float* r,
+                         void* stream) {
+    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
+    if (B < 0 || !q) return CBFRRT_ERR_BAD_SHAPE;
+    const int n = robot == CBFRRT_ROBOT_PANDA ? Panda::N : Magician::N;
+    if (q_stride < n) return CBFRRT_ERR_BAD_SHAPE;
+    SceneArgs sc;
+    NetArgs na;
+    int rc = check_scene(scene, sc);
+    if (rc) return rc;
+    rc = check_net(n, net, fp, B, na);
+    if (rc) return rc;
+    if (B == 0) return CBFRRT_OK;
+    CollideOutPtrs co{safe, unsafe, datax, nullptr, nullptr, nullptr};
+    FilterOutPtrs fo{h, J, u, r};
+    cudaStream_t st = (cudaStream_t)stream;
+    return robot == CBFRRT_ROBOT_PANDA ? launch_safety_panda(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, st)
+                                       : launch_safety_magician(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, st);
+}
+
+int cbfrrt_edge_validity(int robot, const cbfrrt_scene* scene, const float* q_from, const float* q_to, int64_t E,
+                         int32_t n_interp, float thr_soft, float thr_hard, uint8_t* valid, int32_t* first_bad,
+                         void* stream) {
+    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
+    if (E < 0 || n_interp < 1 || !q_from || !q_to || !valid || !first_bad) return CBFRRT_ERR_BAD_SHAPE;
+    SceneArgs sc;
+    int rc = check_scene(scene, sc);
+    if (rc) return rc;
+    if (E == 0) return CBFRRT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    return robot == CBFRRT_ROBOT_PANDA ? launch_edges_panda(sc, q_from, q_to, E, n_interp, thr_soft, thr_hard, valid, first_bad, st)
+                                       : launch_edges_magician(sc, q_from, q_to, E, n_interp, thr_soft, thr_hard, valid, first_bad, st);
+}
+
+int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* net, const float* q0, int64_t T,
+                   const cbfrrt_filter_params* fp, const cbfrrt_rollout_params* rp, float thr_soft, float thr_hard,
+                   float* q_final, uint8_t* alive, int32_t* steps_done, float* traj, void* stream) {
+    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
+    if (T < 0 || !rp || rp->steps < 0 || rp->ctrl_every < 1 || !q0 || !q_final || !alive || !steps_done)
+        return CBFRRT_ERR_BAD_SHAPE;
+    if (rp->stuck_lag < 0 || (rp->stuck_lag > 0 && (!traj || rp->stuck_after < rp->stuck_lag))) return CBFRRT_ERR_BAD_SHAPE;
+    if (fp && fp->u_ref) return CBFRRT_ERR_UNSUPPORTED;  // the loop needs the nominal controller
+    const int n = robot == CBFRRT_ROBOT_PANDA ? Panda::N : Magician::N;
+    SceneArgs sc;
+    NetArgs na;
+    int rc = check_scene(scene, sc);
+    if (rc) return rc;
+    rc = check_net(n, net, fp, T, na);
+    if (rc) return rc;
+    if (T == 0) return CBFRRT_OK;
+    const RolloutArgs ra{rp->steps, rp->ctrl_every, rp->dt, rp->stuck_lag, rp->stuck_after, rp->stuck_eps, rp->keep_going};
+    cudaStream_t st = (cudaStream_t)stream;
+    return robot == CBFRRT_ROBOT_PANDA
+               ? launch_rollout_panda(sc, na, q0, T, ra, thr_soft, thr_hard, q_final, alive, steps_done, traj, st)
+               : launch_rollout_magician(sc, na, q0, T, ra, thr_soft, thr_hard, q_final, alive, steps_done, traj, st);
+}
+
+int cbfrrt_fma_probe(int32_t grid, int32_t block, int32_t iters, float* sink, void* stream) {
+    if (grid < 1 || block < 32 || block > 1024 || iters < 1 || !sink) return CBFRRT_ERR_BAD_SHAPE;
+    fma_probe_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
+    return finish_launch();
+}
+
+int cbfrrt_sample_states(int robot, uint32_t seed, uint64_t start_row, int64_t B, float* q, void* stream) {
+    if (B < 0 || !q) return CBFRRT_ERR_BAD_SHAPE;
+    if (B == 0) return CBFRRT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = (B * 8 + 255) / 256;
+    const int grid = (int)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
+    if (robot == CBFRRT_ROBOT_PANDA) sample_kernel<Panda><<<grid, 256, 0, st>>>(seed, start_row, B, q);
+    else if (robot == CBFRRT_ROBOT_MAGICIAN) sample_kernel<Magician><<<grid, 256, 0, st>>>(seed, start_row, B, q);
+    else return CBFRRT_ERR_BAD_ROBOT;
+    return finish_launch();
+}
+
+}  // extern "C"

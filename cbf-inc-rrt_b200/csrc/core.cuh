@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "robot_tables.cuh"
+#include "grid.cuh"
 
 namespace cbfrrt {
 
@@ -172,6 +173,7 @@ struct SceneS {
     const float4* boxes;    // 2 x float4 per box: (cx cy cz hx) (hy hz 0 0)
     const float4* spheres;  // (cx cy cz r)
     int n_boxes, n_spheres, floor;
+    const uint16_t* grid;   // nearest-candidate grid in global memory (grid.cuh) or nullptr = brute force
 };
 
 // exact per-pair formulas (oracle: sd_box / sd_sphere / normal_box / normal_sphere)
@@ -216,34 +218,80 @@ __device__ __forceinline__ void normal_sphere(float cx, float cy, float cz, floa
     }
 }
 
+// one box / one sphere obstacle against one link sphere: running (min dsq, min max3) resp. min (dist - rs)
+__device__ __forceinline__ void acc_box(float cx, float cy, float cz, float4 b0, float4 b1, float& D, float& M) {
+    const float ax = __fsub_rn(fabsf(__fsub_rn(cx, b0.x)), b0.w);
+    const float ay = __fsub_rn(fabsf(__fsub_rn(cy, b0.y)), b1.x);
+    const float az = __fsub_rn(fabsf(__fsub_rn(cz, b0.z)), b1.y);
+    const float qx = fmaxf(ax, 0.f), qy = fmaxf(ay, 0.f), qz = fmaxf(az, 0.f);
+    D = fminf(D, fmaf(qz, qz, fmaf(qy, qy, __fmul_rn(qx, qx))));
+    M = fminf(M, fmaxf(ax, fmaxf(ay, az)));
+}
+__device__ __forceinline__ void acc_sphere(float cx, float cy, float cz, float4 s, float& E) {
+    const float dx = __fsub_rn(cx, s.x), dy = __fsub_rn(cy, s.y), dz = __fsub_rn(cz, s.z);
+    E = fminf(E, __fsub_rn(__fsqrt_rn(fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)))), s.w));
+}
+
 // min over the scene's boxes and spheres of the signed distance of K spheres (centres C[k], radii r[k]) that
 // belong to one link -- restructuring (1) above.  out[k] = min_j sd(k, j)  (floor not included).
-template <int K>
+// With a nearest-candidate grid only the candidates of each centre's cell are swept (exact, see grid.cuh); a link
+// with a centre outside the grid region or in an overflowed cell takes the brute-force sweep.
+template <int K, bool GRID>
 __device__ __forceinline__ void sweep_scene(const SceneS& sc, const float (&C)[K][3], const float (&rad)[K],
                                             float (&out)[K]) {
     float D[K], M[K], E[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { D[k] = CBF_INF; M[k] = CBF_INF; E[k] = CBF_INF; }
-    for (int j = 0; j < sc.n_boxes; ++j) {
-        const float4 b0 = sc.boxes[2 * j], b1 = sc.boxes[2 * j + 1];
+    bool brute = true;
+    if constexpr (GRID) {
+        const uint16_t* rec[K];
+        brute = false;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const float ax = __fsub_rn(fabsf(__fsub_rn(C[k][0], b0.x)), b0.w);
-            const float ay = __fsub_rn(fabsf(__fsub_rn(C[k][1], b0.y)), b1.x);
-            const float az = __fsub_rn(fabsf(__fsub_rn(C[k][2], b0.z)), b1.y);
-            const float qx = fmaxf(ax, 0.f), qy = fmaxf(ay, 0.f), qz = fmaxf(az, 0.f);
-            const float dsq = fmaf(qz, qz, fmaf(qy, qy, __fmul_rn(qx, qx)));
-            D[k] = fminf(D[k], dsq);
-            M[k] = fminf(M[k], fmaxf(ax, fmaxf(ay, az)));
+            rec[k] = grid::lookup(sc.grid, C[k][0], C[k][1], C[k][2]);
+            brute = brute || (rec[k] == nullptr);
+        }
+        if (!brute) {
+            // first 16 bytes of a cell record = header + the first 6 candidates: one LDG.128 per sphere, issued for
+            // all K spheres before any of them is consumed; longer lists (rare) are read element by element
+            uint4 r0[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                r0[k] = __ldg(reinterpret_cast<const uint4*>(rec[k]));
+                brute = brute || ((r0[k].x & 0xffffu) == grid::OVERFLOW);
+            }
+            if (!brute) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int nb = r0[k].x & 0xffffu, nt = nb + (int)(r0[k].x >> 16);
+                    const uint32_t w[3] = {r0[k].y, r0[k].z, r0[k].w};
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        if (i < nt) {
+                            const int j = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
+                            if (i < nb) acc_box(C[k][0], C[k][1], C[k][2], sc.boxes[2 * j], sc.boxes[2 * j + 1], D[k], M[k]);
+                            else acc_sphere(C[k][0], C[k][1], C[k][2], sc.spheres[j], E[k]);
+                        }
+                    }
+                    for (int i = 6; i < nt; ++i) {
+                        const int j = __ldg(rec[k] + 2 + i);
+                        if (i < nb) acc_box(C[k][0], C[k][1], C[k][2], sc.boxes[2 * j], sc.boxes[2 * j + 1], D[k], M[k]);
+                        else acc_sphere(C[k][0], C[k][1], C[k][2], sc.spheres[j], E[k]);
+                    }
+                }
+            }
         }
     }
-    for (int j = 0; j < sc.n_spheres; ++j) {
-        const float4 s = sc.spheres[j];
+    if (brute) {
+        for (int j = 0; j < sc.n_boxes; ++j) {
+            const float4 b0 = sc.boxes[2 * j], b1 = sc.boxes[2 * j + 1];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float dx = __fsub_rn(C[k][0], s.x), dy = __fsub_rn(C[k][1], s.y), dz = __fsub_rn(C[k][2], s.z);
-            const float dsq = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
-            E[k] = fminf(E[k], __fsub_rn(__fsqrt_rn(dsq), s.w));
+            for (int k = 0; k < K; ++k) acc_box(C[k][0], C[k][1], C[k][2], b0, b1, D[k], M[k]);
+        }
+        for (int j = 0; j < sc.n_spheres; ++j) {
+            const float4 s = sc.spheres[j];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc_sphere(C[k][0], C[k][1], C[k][2], s, E[k]);
         }
     }
 #pragma unroll
@@ -268,7 +316,9 @@ struct CollideResult {
 
 // base link (-1) is static: its distance to every obstacle is a per-scene constant that the CTA computes once
 // (kernels.cu: base_min_cta) and passes in.  The floor is exempt for the base in both checks.
-template <class RB, bool WANT_GRAD, bool WANT_SELFMIN>
+// GRID: the scene carries a nearest-candidate grid (sc.grid != nullptr); grid-free instantiations keep the small-
+// scene kernels free of the look-up code and its registers.
+template <class RB, bool WANT_GRAD, bool WANT_SELFMIN, bool GRID>
 __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const SceneS& sc, float base_min,
                                               CollideResult<RB>& res) {
     constexpr int N = RB::N;
@@ -279,6 +329,8 @@ __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const Sce
     float jz[WANT_GRAD ? N : 1][3], jp[WANT_GRAD ? N : 1][3];
     // sphere centres kept for the self-collision predicate (only spheres that appear in a self pair)
     float SC[RB::NSPH][3];
+    bool self_ok = true;
+    float self_min = CBF_INF;
 
     Frame fr[RB::NLINKS];  // fully unrolled: only live frames stay in registers
     static_for<0, RB::NLINKS>([&](auto lc) {
@@ -310,7 +362,20 @@ __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const Sce
                 rad[k] = RB::sph(i, 3);
                 SC[i][0] = C[k][0]; SC[i][1] = C[k][1]; SC[i][2] = C[k][2];
             });
-            sweep_scene<K>(sc, C, rad, m);
+            // self collision, restructuring (2): pairs whose second sphere belongs to this link are tested now, so
+            // only the spheres of the (few) "first" links of a pair stay live along the chain
+            static_for<0, RB::NSELFSPH>([&](auto pc) {
+                constexpr int p = decltype(pc)::value;
+                constexpr int i = RB::self_i(p), j = RB::self_j(p);
+                if constexpr (j >= S0 && j < S1) {
+                    const float dx = __fsub_rn(SC[i][0], SC[j][0]), dy = __fsub_rn(SC[i][1], SC[j][1]), dz = __fsub_rn(SC[i][2], SC[j][2]);
+                    const float dsq = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+                    self_ok = self_ok && (dsq > RB::self_x(p));
+                    if constexpr (WANT_SELFMIN)
+                        self_min = fminf(self_min, __fsub_rn(__fsub_rn(__fsqrt_rn(dsq), RB::sph(i, 3)), RB::sph(j, 3)));
+                }
+            });
+            sweep_scene<K, GRID>(sc, C, rad, m);
             // merge in sphere order, floor candidate first (oracle iteration order; strict '<')
             static_for<0, K>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
@@ -336,19 +401,6 @@ __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const Sce
         }
     });
 
-    // self collision, restructuring (2)
-    bool self_ok = true;
-    float self_min = CBF_INF;
-    static_for<0, RB::NSELFSPH>([&](auto pc) {
-        constexpr int p = decltype(pc)::value;
-        constexpr int i = RB::self_i(p), j = RB::self_j(p);
-        const float dx = __fsub_rn(SC[i][0], SC[j][0]), dy = __fsub_rn(SC[i][1], SC[j][1]), dz = __fsub_rn(SC[i][2], SC[j][2]);
-        const float dsq = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
-        self_ok = self_ok && (dsq > RB::self_x(p));
-        if constexpr (WANT_SELFMIN)
-            self_min = fminf(self_min, __fsub_rn(__fsub_rn(__fsqrt_rn(dsq), RB::sph(i, 3)), RB::sph(j, 3)));
-    });
-
     res.o = o; res.soft_min = soft; res.hard_min = hard; res.self_ok = self_ok; res.self_min = self_min;
     res.arg_sphere = arg_s; res.arg_obs = -1;
 #pragma unroll
@@ -365,8 +417,17 @@ __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const Sce
             const float d = (link == 0) ? RB::LINK0_FLOOR : __fsub_rn(argC[2], r);
             if (d == o) arg_o = 0;
         }
+        // candidates of the winning sphere's cell (ascending indices, exact -- grid.cuh) or every obstacle
+        const uint16_t* rec = GRID ? grid::lookup(sc.grid, argC[0], argC[1], argC[2]) : nullptr;
+        int nb = sc.n_boxes, ns = sc.n_spheres;
+        if (rec) {
+            const uint32_t hdr = __ldg(reinterpret_cast<const unsigned int*>(rec));
+            if ((hdr & 0xffffu) == grid::OVERFLOW) rec = nullptr;
+            else { nb = hdr & 0xffffu; ns = hdr >> 16; }
+        }
         if (arg_o < 0) {
-            for (int j = 0; j < sc.n_boxes; ++j) {
+            for (int i = 0; i < nb; ++i) {
+                const int j = rec ? (int)__ldg(rec + 2 + i) : i;
                 const float4 b0 = sc.boxes[2 * j], b1 = sc.boxes[2 * j + 1];
                 if (sd_box_exact(argC[0], argC[1], argC[2], b0, b1, r) == o) {
                     arg_o = off + j;
@@ -376,7 +437,8 @@ __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const Sce
             }
         }
         if (arg_o < 0) {
-            for (int j = 0; j < sc.n_spheres; ++j) {
+            for (int i = 0; i < ns; ++i) {
+                const int j = rec ? (int)__ldg(rec + 2 + nb + i) : i;
                 const float4 s = sc.spheres[j];
                 if (sd_sphere_exact(argC[0], argC[1], argC[2], s, r) == o) {
                     arg_o = off + sc.n_boxes + j;

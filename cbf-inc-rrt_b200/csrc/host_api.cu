@@ -28,6 +28,7 @@ struct Ctx {
     int64_t cap_rows = 0;
     Lane lane[NSTREAM];
     float *boxes = nullptr, *spheres = nullptr, *weights = nullptr, *small = nullptr;  // small: goal(1 row) K lo hi
+    void* grid = nullptr;
     int64_t cap_boxes = 0, cap_spheres = 0, cap_weights = 0;
     std::mutex mu;
 };
@@ -44,6 +45,7 @@ int ensure(Ctx& c, int device, int64_t rows, int n, int64_t n_boxes, int64_t n_s
         c.device = device;
         for (auto& l : c.lane) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
         CK(cudaMalloc(&c.small, 4 * (8 + 64 + 8 + 8)));
+        CK(cudaMalloc(&c.grid, cbfrrt_grid_bytes()));
     }
     if (rows > c.cap_rows) {
         for (auto& l : c.lane) {
@@ -108,9 +110,16 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
     memcpy(small + 72, u_lo, 4 * n);
     memcpy(small + 80, u_hi, 4 * n);
     CK(cudaMemcpyAsync(c.small, small, sizeof small, cudaMemcpyHostToDevice, s0));
-    CK(cudaStreamSynchronize(s0));  // b8/small live on this stack frame
+    // the broad-phase grid pays off from a few tens of thousands of rows on (one 85 k-cell build kernel per call)
+    const bool use_grid = B >= 32768 && scene->n_boxes + scene->n_spheres > 0;
+    cbfrrt_scene dsc{scene->n_boxes, scene->n_spheres, scene->floor, 0, c.boxes, c.spheres, nullptr};
+    if (use_grid) {
+        rc = cbfrrt_grid_build(&dsc, c.grid, s0);
+        if (rc) return rc;
+        dsc.grid = c.grid;
+    }
+    CK(cudaStreamSynchronize(s0));  // b8/small live on this stack frame; lanes 1.. may now read scene + grid
 
-    cbfrrt_scene dsc{scene->n_boxes, scene->n_spheres, scene->floor, 0, c.boxes, c.spheres};
     cbfrrt_cbf_net net{n + 1, hidden, layers, 0, c.weights};
 
     int lane_i = 0;

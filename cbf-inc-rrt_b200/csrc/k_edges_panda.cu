@@ -1,0 +1,6 @@
+// k_edges_panda.cu -- instantiates the edges kernels for the Panda (see kernels.cuh)
+#include "kernels.cuh"
+
+namespace cbfrrt {
+int launch_edges_panda(const SceneArgs& sc, const float* qf, const float* qt, long long E, int K, float ts, float th, uint8_t* valid, int* first_bad, cudaStream_t st) { return launch_edges<Panda>(sc, qf, qt, E, K, ts, th, valid, first_bad, st); }
+}  // namespace cbfrrt

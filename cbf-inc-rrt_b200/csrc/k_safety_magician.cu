@@ -1,0 +1,6 @@
+// k_safety_magician.cu -- instantiates the safety kernels for the Magician (see kernels.cuh)
+#include "kernels.cuh"
+
+namespace cbfrrt {
+int launch_safety_magician(const SceneArgs& sc, const NetArgs& net, const float* q, long long qs, long long B, float ts, float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, cudaStream_t st) { return launch_safety<Magician>(sc, net, q, qs, B, ts, th, co, fo, st); }
+}  // namespace cbfrrt

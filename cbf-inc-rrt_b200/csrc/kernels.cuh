@@ -1,12 +1,17 @@
-// kernels.cu -- sm_100a kernels + the device-pointer C-ABI of libcbfrrt (include/cbfrrt.h).
+// kernels.cuh -- sm_100a kernels and their launchers (templates).  Included by the per-family translation units
+// (k_*.cu, compiled in parallel) and by abi.cu, which holds the device-pointer C-ABI of include/cbfrrt.h.
 //
 // Launch shape: CTAs of NT=128 threads, persistent grid (SMs x resident CTAs), grid-stride over tiles of NT
 // states so that the per-CTA staging (scene + weights by TMA bulk copy, base-link distance) is paid once.
+#pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <atomic>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "../../include/cbfrrt.h"
 #include "core.cuh"
@@ -16,6 +21,9 @@
 namespace cbfrrt {
 
 constexpr int NT = 128;
+#ifndef CBF_COLLIDE_MIN_CTAS
+#define CBF_COLLIDE_MIN_CTAS 4   // <= 128 registers: 16 warps per SM for the distance sweeps
+#endif
 
 // ------------------------------------------------------------------ TMA bulk copy + mbarrier (PTX)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -52,6 +60,7 @@ struct SceneArgs {
     const float* boxes;
     const float* spheres;
     int n_boxes, n_spheres, floor;
+    const uint16_t* grid;
 };
 struct NetArgs {
     const float* weights;  // packed, NetLayout<>::TOTAL floats
@@ -137,6 +146,7 @@ __device__ __forceinline__ SceneS scene_view(const Smem& s, const SceneArgs& sc)
     v.boxes = reinterpret_cast<const float4*>(s.boxes);
     v.spheres = reinterpret_cast<const float4*>(s.spheres);
     v.n_boxes = sc.n_boxes; v.n_spheres = sc.n_spheres; v.floor = sc.floor;
+    v.grid = sc.grid;
     return v;
 }
 
@@ -192,8 +202,8 @@ __device__ __forceinline__ void write_collide(const CollideOutPtrs& o, long long
     }
 }
 
-template <class RB, bool WANT_GRAD, bool WANT_SELFMIN>
-__global__ void __launch_bounds__(NT) collide_kernel(SceneArgs sc, const float* __restrict__ q, long long q_stride,
+template <class RB, bool WANT_GRAD, bool WANT_SELFMIN, bool GRID>
+__global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) collide_kernel(SceneArgs sc, const float* __restrict__ q, long long q_stride,
                                                      long long B, float thr_soft, float thr_hard, CollideOutPtrs out) {
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
@@ -205,7 +215,7 @@ __global__ void __launch_bounds__(NT) collide_kernel(SceneArgs sc, const float* 
 #pragma unroll
         for (int k = 0; k < RB::N; ++k) qq[k] = __ldg(q + b * q_stride + k);
         CollideResult<RB> r;
-        collide_state<RB, WANT_GRAD, WANT_SELFMIN>(qq, sv, base_min, r);
+        collide_state<RB, WANT_GRAD, WANT_SELFMIN, GRID>(qq, sv, base_min, r);
         write_collide<RB>(out, b, qq, r, thr_soft, thr_hard);
     }
 }
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(NT) filter_kernel(NetArgs net, const float* __
     extern __shared__ __align__(16) float smem_raw[];
     using LY = NetLayout<N + 1, H, L>;
     const Smem s = carve(smem_raw, 0, 0, LY::TOTAL, ParamLayout<N>::TOTAL);
-    SceneArgs none{nullptr, nullptr, 0, 0, 0};
+    SceneArgs none{nullptr, nullptr, 0, 0, 0, nullptr};
     stage<N>(s, none, &net, LY::TOTAL);
     float* scr = s.scratch + threadIdx.x;
     for (long long b = (long long)blockIdx.x * NT + threadIdx.x; b < B; b += (long long)gridDim.x * NT) {
@@ -283,7 +293,7 @@ __global__ void __launch_bounds__(256) qp_kernel(const float* __restrict__ a, co
     }
 }
 
-template <class RB, int H, int L>
+template <class RB, int H, int L, bool GRID>
 __global__ void __launch_bounds__(NT) safety_kernel(SceneArgs sc, NetArgs net, const float* __restrict__ q,
                                                     long long q_stride, long long B, float thr_soft, float thr_hard,
                                                     CollideOutPtrs cout, FilterOutPtrs fout) {
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(NT) safety_kernel(SceneArgs sc, NetArgs net, c
 #pragma unroll
         for (int k = 0; k < N; ++k) qq[k] = __ldg(q + b * q_stride + k);
         CollideResult<RB> cr;
-        collide_state<RB, true, false>(qq, sv, base_min, cr);
+        collide_state<RB, true, false, GRID>(qq, sv, base_min, cr);
         write_collide<RB>(cout, b, qq, cr, thr_soft, thr_hard);
         float g[N], J[N], u[N], h, r;
         load_goal<N>(net, b, g);
@@ -310,6 +320,15 @@ __global__ void __launch_bounds__(NT) safety_kernel(SceneArgs sc, NetArgs net, c
     }
 }
 
+
+// closed-loop rollouts (the steer loop): one thread per trajectory, the whole loop in one launch.
+struct RolloutArgs {
+    int steps, ctrl_every;
+    float dt;
+    int stuck_lag, stuck_after;
+    float stuck_eps;
+    int keep_going;
+};
 
 // ------------------------------------------------------------------ tensor-core (tcgen05) variants
 // Same contracts as filter_kernel / safety_kernel; the MLP of every 128-state tile runs as TF32x3 GEMMs on the
@@ -335,7 +354,7 @@ __global__ void __launch_bounds__(NTC, 1) filter_kernel_tc(NetArgs net, const fl
                                                            FilterOutPtrs out) {
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, 0, 0, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
-    SceneArgs none{nullptr, nullptr, 0, 0, 0};
+    SceneArgs none{nullptr, nullptr, 0, 0, 0, nullptr};
     stage<N, NTC>(s, none, &net, 0);
     tc::Ctx<L> c;
     tc::setup<N + 1, L>(c, s.weights, net.weights);
@@ -359,7 +378,7 @@ __global__ void __launch_bounds__(NTC, 1) filter_kernel_tc(NetArgs net, const fl
     tc::teardown<L>(c);
 }
 
-template <class RB, int L>
+template <class RB, int L, bool GRID>
 __global__ void __launch_bounds__(NTC, 1) safety_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q,
                                                            long long q_stride, long long B, float thr_soft, float thr_hard,
                                                            CollideOutPtrs cout, FilterOutPtrs fout) {
@@ -385,7 +404,7 @@ __global__ void __launch_bounds__(NTC, 1) safety_kernel_tc(SceneArgs sc, NetArgs
         if (active) {
 #pragma unroll
             for (int k = 0; k < N; ++k) qq[k] = __ldg(q + b * q_stride + k);
-            collide_state<RB, true, false>(qq, sv, base_min, cr);
+            collide_state<RB, true, false, GRID>(qq, sv, base_min, cr);
             write_collide<RB>(cout, b, qq, cr, thr_soft, thr_hard);
             load_goal<N>(net, b, g);
         }
@@ -395,10 +414,93 @@ __global__ void __launch_bounds__(NTC, 1) safety_kernel_tc(SceneArgs sc, NetArgs
     tc::teardown<L>(c);
 }
 
+// steer loop on the tensor-core path: the time loop is uniform over a tile group (a finished trajectory idles,
+// it does not leave), because the MLP rounds are group-wide; the group exits early once all its rows are finished.
+template <class RB, int L, bool GRID>
+__global__ void __launch_bounds__(NTC, 1) rollout_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q0,
+                                                            long long T, RolloutArgs ra, float thr_soft, float thr_hard,
+                                                            float* __restrict__ q_final, uint8_t* __restrict__ alive,
+                                                            int* __restrict__ steps_done, float* __restrict__ traj) {
+    constexpr int N = RB::N;
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
+    stage<N, NTC>(s, sc, &net, 0);
+    const SceneS sv = scene_view(s, sc);
+    const float base_min = base_min_cta<RB, NTC>(s, sv);
+    tc::Ctx<L> c;
+    tc::setup<N + 1, L>(c, s.weights, net.weights);
+    const long long n_tiles = (T + tc::M_TILE - 1) / tc::M_TILE;
+    for (long long tile = (long long)blockIdx.x * tc::G + c.g; tile < n_tiles; tile += (long long)gridDim.x * tc::G) {
+        const long long b = tile * tc::M_TILE + c.t;
+        const bool active = b < T;
+        float q[N], qn[N], g[N], u[N], dodq[N], o = 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { q[k] = 0.f; g[k] = 0.f; u[k] = 0.f; dodq[k] = 0.f; }
+        CollideResult<RB> cr;
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) q[k] = __ldg(q0 + b * N + k);
+            load_goal<N>(net, b, g);
+            collide_state<RB, true, false, GRID>(q, sv, base_min, cr);
+            o = cr.o;
+#pragma unroll
+            for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
+        }
+        bool ok = true, finished = !active;
+        int done = 0;
+        float* tr = (traj && active) ? traj + b * (long long)ra.steps * N : nullptr;
+        for (int t = 0; t < ra.steps; ++t) {
+            if (t % ra.ctrl_every == 0) {
+                if (!tc::group_any(c.g, !finished)) break;
+                float J[N], h, r, un[N];
+                filter_tile_tc<N, L>(c, s.params, q, o, dodq, g, false, net.lam, net.penalty, h, J, un, r);
+                if (!finished) {
+#pragma unroll
+                    for (int k = 0; k < N; ++k) u[k] = un[k];
+                }
+            }
+            if (finished) continue;
+#pragma unroll
+            for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);  // arm_dynamics.py:508 (step = 1)
+            collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
+            if ((t + 1) % ra.ctrl_every == 0) {
+                o = cr.o;
+#pragma unroll
+                for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
+            }
+            if (cr.hard_min <= thr_hard) {  // tsa.py:251-253: colliding state is not appended
+                ok = false;
+                if (!ra.keep_going) { finished = true; continue; }
+            }
+#pragma unroll
+            for (int k = 0; k < N; ++k) q[k] = qn[k];
+            if (tr) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) tr[t * N + k] = q[k];
+            }
+            done = t + 1;
+            if (ra.stuck_lag > 0 && t > ra.stuck_after) {  // tsa.py:263
+                const float* old = tr + (t - ra.stuck_lag) * N;
+                float dsq = 0.f;
+#pragma unroll
+                for (int k = 0; k < N; ++k) { const float d = __fsub_rn(q[k], old[k]); dsq = fmaf(d, d, dsq); }
+                if (__fsqrt_rn(dsq) < ra.stuck_eps) finished = true;
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) q_final[b * N + k] = q[k];
+            alive[b] = ok;
+            steps_done[b] = done;
+        }
+    }
+    tc::teardown<L>(c);
+}
+
 // edge validity: one thread per (edge, point); point k in [0, K] (K = end point).  A CTA owns EPB whole edges
 // (EPB * (K+1) <= NT threads active) and reduces "first failing index" with a shared-memory atomicMin.
-template <class RB>
-__global__ void __launch_bounds__(NT) edge_kernel(SceneArgs sc, const float* __restrict__ q_from,
+template <class RB, bool GRID>
+__global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_kernel(SceneArgs sc, const float* __restrict__ q_from,
                                                   const float* __restrict__ q_to, long long E, int K, int epb,
                                                   float thr_soft, float thr_hard, uint8_t* __restrict__ valid,
                                                   int* __restrict__ first_bad) {
@@ -431,7 +533,7 @@ __global__ void __launch_bounds__(NT) edge_kernel(SceneArgs sc, const float* __r
                 }
             }
             CollideResult<RB> r;
-            collide_state<RB, false, false>(c, sv, base_min, r);
+            collide_state<RB, false, false, GRID>(c, sv, base_min, r);
             const bool unsafe = r.hard_min <= thr_hard;
             const bool safe = r.self_ok && (r.soft_min > thr_soft) && !unsafe;
             if (!safe) atomicMin(&s_bad[le], k);
@@ -451,7 +553,7 @@ __global__ void __launch_bounds__(NT) edge_kernel(SceneArgs sc, const float* __r
 
 // long edges (K + 1 > NT): one warp-strided thread loop per edge is not needed by any reference caller; they
 // are handled by the thread-per-edge fallback below (sequential over k with early exit, tsa.py:281-285).
-template <class RB>
+template <class RB, bool GRID>
 __global__ void __launch_bounds__(NT) edge_seq_kernel(SceneArgs sc, const float* __restrict__ q_from,
                                                       const float* __restrict__ q_to, long long E, int K,
                                                       float thr_soft, float thr_hard, uint8_t* __restrict__ valid,
@@ -478,7 +580,7 @@ __global__ void __launch_bounds__(NT) edge_seq_kernel(SceneArgs sc, const float*
                 for (int i = 0; i < N; ++i) c[i] = fmaf(t, d[i], a[i]);
             }
             CollideResult<RB> r;
-            collide_state<RB, false, false>(c, sv, base_min, r);
+            collide_state<RB, false, false, GRID>(c, sv, base_min, r);
             const bool unsafe = r.hard_min <= thr_hard;
             if (!(r.self_ok && (r.soft_min > thr_soft) && !unsafe)) bad = k;
         }
@@ -487,15 +589,7 @@ __global__ void __launch_bounds__(NT) edge_seq_kernel(SceneArgs sc, const float*
     }
 }
 
-// closed-loop rollouts (the steer loop): one thread per trajectory, the whole loop in one launch.
-struct RolloutArgs {
-    int steps, ctrl_every;
-    float dt;
-    int stuck_lag, stuck_after;
-    float stuck_eps;
-    int keep_going;
-};
-template <class RB, int H, int L>
+template <class RB, int H, int L, bool GRID>
 __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, const float* __restrict__ q0,
                                                      long long T, RolloutArgs ra, float thr_soft, float thr_hard,
                                                      float* __restrict__ q_final, uint8_t* __restrict__ alive,
@@ -514,7 +608,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
         for (int k = 0; k < N; ++k) { q[k] = __ldg(q0 + b * N + k); u[k] = 0.f; }
         load_goal<N>(net, b, g);
         CollideResult<RB> cr;
-        collide_state<RB, true, false>(q, sv, base_min, cr);
+        collide_state<RB, true, false, GRID>(q, sv, base_min, cr);
         o = cr.o;
 #pragma unroll
         for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
@@ -529,7 +623,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
             }
 #pragma unroll
             for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);  // arm_dynamics.py:508 (step = 1)
-            collide_state<RB, true, false>(qn, sv, base_min, cr);
+            collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
             if ((t + 1) % ra.ctrl_every == 0) {
                 o = cr.o;
 #pragma unroll
@@ -588,7 +682,7 @@ __global__ void __launch_bounds__(256) sample_kernel(uint32_t seed, unsigned lon
 }
 
 // FP32 FMA throughput probe (roofline denominator; see include/cbfrrt.h)
-__global__ void fma_probe_kernel(int iters, float* sink) {
+static __global__ void fma_probe_kernel(int iters, float* sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
           a6 = a0 + 6.f, a7 = a0 + 7.f;
     const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
@@ -602,10 +696,10 @@ __global__ void fma_probe_kernel(int iters, float* sink) {
 }
 
 // ------------------------------------------------------------------ host side of the device-pointer ABI
-static std::atomic<long long> g_launches{0};
-static std::atomic<int> g_last_cuda{0};
+extern std::atomic<long long> g_launches;
+extern std::atomic<int> g_last_cuda;
 
-static int num_sms() {
+inline int num_sms() {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -616,13 +710,26 @@ static int num_sms() {
     return sms;
 }
 
+// resident CTAs per SM for (kernel, dynamic smem): the attribute / occupancy queries cost ~10 us of host time, so
+// they are made once per distinct configuration
+extern std::mutex g_cfg_mu;
+extern std::map<std::pair<const void*, size_t>, int> g_cfg;
+
 template <class Kern>
 static int grid_for(Kern kern, size_t smem, long long tiles) {
     int per_sm = 0;
-    if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mu);
+        const auto key = std::make_pair(reinterpret_cast<const void*>(kern), smem);
+        auto it = g_cfg.find(key);
+        if (it != g_cfg.end()) per_sm = it->second;
+        else {
+            if (smem > 48 * 1024 &&
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) return -1;
+            g_cfg[key] = per_sm;
+        }
     }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) return -1;
     long long g = (long long)num_sms() * per_sm;
     if (g > tiles) g = tiles;
     if (g < 1) g = 1;
@@ -632,8 +739,14 @@ static int grid_for(Kern kern, size_t smem, long long tiles) {
 // tensor-core kernels: one 384-thread CTA per SM (it owns all 512 TMEM columns), 3 tiles of 128 rows per pass
 template <class Kern>
 static int grid_for_tc(Kern kern, size_t smem, long long rows) {
-    if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mu);
+        const auto key = std::make_pair(reinterpret_cast<const void*>(kern), smem);
+        if (g_cfg.find(key) == g_cfg.end()) {
+            if (smem > 48 * 1024 &&
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            g_cfg[key] = 1;
+        }
     }
     const long long tiles = (rows + tc::M_TILE - 1) / tc::M_TILE;
     long long g = (tiles + tc::G - 1) / tc::G;
@@ -641,7 +754,7 @@ static int grid_for_tc(Kern kern, size_t smem, long long rows) {
     return (int)(g < 1 ? 1 : g);
 }
 
-static int finish_launch() {
+inline int finish_launch() {
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         g_last_cuda = (int)e;
@@ -651,18 +764,24 @@ static int finish_launch() {
     return CBFRRT_OK;
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+constexpr int GRID_MIN_OBSTACLES = 40;
 
-static int check_scene(const cbfrrt_scene* sc, SceneArgs& a) {
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int check_scene(const cbfrrt_scene* sc, SceneArgs& a) {
     if (!sc || sc->n_boxes < 0 || sc->n_spheres < 0) return CBFRRT_ERR_BAD_SHAPE;
     if (sc->n_boxes + sc->n_spheres > CBFRRT_MAX_OBSTACLES) return CBFRRT_ERR_UNSUPPORTED;
     if ((sc->n_boxes && !sc->boxes) || (sc->n_spheres && !sc->spheres)) return CBFRRT_ERR_BAD_SHAPE;
-    if (!aligned16(sc->boxes) || !aligned16(sc->spheres)) return CBFRRT_ERR_ALIGNMENT;
-    a = SceneArgs{sc->boxes, sc->spheres, sc->n_boxes, sc->n_spheres, sc->floor ? 1 : 0};
+    if (!aligned16(sc->boxes) || !aligned16(sc->spheres) || !aligned16(sc->grid)) return CBFRRT_ERR_ALIGNMENT;
+    // the grid's look-ups and gathers cost more than they save on small scenes (measured: slower at 16 obstacles,
+    // 1.7x faster at 64, 4.3x at 256): scenes below GRID_MIN_OBSTACLES are swept brute force even if a grid is given
+    const bool use_grid = sc->grid && sc->n_boxes + sc->n_spheres >= GRID_MIN_OBSTACLES;
+    a = SceneArgs{sc->boxes, sc->spheres, sc->n_boxes, sc->n_spheres, sc->floor ? 1 : 0,
+                  use_grid ? static_cast<const uint16_t*>(sc->grid) : nullptr};
     return CBFRRT_OK;
 }
 
-static int check_net(int n, const cbfrrt_cbf_net* net, const cbfrrt_filter_params* fp, long long B, NetArgs& a) {
+inline int check_net(int n, const cbfrrt_cbf_net* net, const cbfrrt_filter_params* fp, long long B, NetArgs& a) {
     if (!net || !fp || !net->weights || !fp->u_lo || !fp->u_hi) return CBFRRT_ERR_BAD_SHAPE;
     if (!fp->u_ref && (!fp->goal || !fp->K)) return CBFRRT_ERR_BAD_SHAPE;
     if (net->n_in != n + 1) return CBFRRT_ERR_BAD_SHAPE;
@@ -689,35 +808,38 @@ static int launch_collide(const SceneArgs& sc, const float* q, long long qs, lon
     const long long tiles = (B + NT - 1) / NT;
     const bool grad = out.datax || out.arg_link || out.arg_obs;
     int grid;
-    if (out.mins) {
-        auto k = collide_kernel<RB, true, true>;
-        if ((grid = grid_for(k, smem, tiles)) < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NT, smem, st>>>(sc, q, qs, B, ts, th, out);
-    } else if (grad) {
-        auto k = collide_kernel<RB, true, false>;
-        if ((grid = grid_for(k, smem, tiles)) < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NT, smem, st>>>(sc, q, qs, B, ts, th, out);
-    } else {
-        auto k = collide_kernel<RB, false, false>;
-        if ((grid = grid_for(k, smem, tiles)) < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NT, smem, st>>>(sc, q, qs, B, ts, th, out);
+#define CBF_LAUNCH_COLLIDE(G_, S_, U_)                                             \
+    {                                                                              \
+        auto k = collide_kernel<RB, G_, S_, U_>;                                   \
+        if ((grid = grid_for(k, smem, tiles)) < 0) return CBFRRT_ERR_CUDA;         \
+        k<<<grid, NT, smem, st>>>(sc, q, qs, B, ts, th, out);                      \
     }
+    const bool ug = sc.grid != nullptr;
+    if (out.mins) { if (ug) CBF_LAUNCH_COLLIDE(true, true, true) else CBF_LAUNCH_COLLIDE(true, true, false) }
+    else if (grad) { if (ug) CBF_LAUNCH_COLLIDE(true, false, true) else CBF_LAUNCH_COLLIDE(true, false, false) }
+    else { if (ug) CBF_LAUNCH_COLLIDE(false, false, true) else CBF_LAUNCH_COLLIDE(false, false, false) }
+#undef CBF_LAUNCH_COLLIDE
     return finish_launch();
 }
 
+// Batches of at most SMALL_BATCH rows (< 1 tile group per SM) are launch-latency bound: the tcgen05 kernels' per-CTA
+// set-up (two weight tilings, TMEM allocation) costs more than it saves there, so they take the FP32-FMA kernels
+// (measured on cfg0, 4096 rows: 59 us vs 75 us).  CBFRRT_MLP=tc forces the tensor-core kernels for any size.
+constexpr long long SMALL_BATCH = 16384;
 // CBFRRT_MLP=fma selects the FP32-FMA MLP kernels (A/B comparisons); default is the tcgen05 path
-static bool use_tc() {
+inline bool use_tc() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("CBFRRT_MLP");
-        v = (e && e[0] == 'f') ? 0 : 1;
+        v = (e && e[0] == 'f') ? 0 : ((e && e[0] == 't') ? 2 : 1);
     }
-    return v == 1;
+    return v >= 1;
 }
+inline bool force_tc() { use_tc(); const char* e = getenv("CBFRRT_MLP"); return e && e[0] == 't'; }
 
 template <int N>
 static int launch_filter(const NetArgs& net, const float* datax, long long B, const FilterOutPtrs& out, cudaStream_t st) {
-    if (use_tc()) {
+    if (use_tc() && (B > SMALL_BATCH || force_tc())) {
         const size_t smem = 4 * smem_floats(0, 0, tc::Layout<2>::TOTAL, ParamLayout<N>::TOTAL, 0);
         auto k = filter_kernel_tc<N, 2>;
         const int grid = grid_for_tc(k, smem, B);
@@ -737,9 +859,9 @@ static int launch_filter(const NetArgs& net, const float* datax, long long B, co
 template <class RB>
 static int launch_safety(const SceneArgs& sc, const NetArgs& net, const float* q, long long qs, long long B, float ts,
                          float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, cudaStream_t st) {
-    if (use_tc()) {
+    if (use_tc() && (B > SMALL_BATCH || force_tc())) {
         const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
-        auto k = safety_kernel_tc<RB, 2>;
+        auto k = sc.grid ? safety_kernel_tc<RB, 2, true> : safety_kernel_tc<RB, 2, false>;
         const int grid = grid_for_tc(k, smem, B);
         if (grid < 0) return CBFRRT_ERR_CUDA;
         k<<<grid, NTC, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo);
@@ -747,7 +869,7 @@ static int launch_safety(const SceneArgs& sc, const NetArgs& net, const float* q
     }
     using LY = NetLayout<RB::N + 1, 48, 2>;
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<RB::N>::TOTAL, 48 * NT);
-    auto k = safety_kernel<RB, 48, 2>;
+    auto k = sc.grid ? safety_kernel<RB, 48, 2, true> : safety_kernel<RB, 48, 2, false>;
     const int grid = grid_for(k, smem, (B + NT - 1) / NT);
     if (grid < 0) return CBFRRT_ERR_CUDA;
     k<<<grid, NT, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo);
@@ -760,12 +882,12 @@ static int launch_edges(const SceneArgs& sc, const float* qf, const float* qt, l
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
     if (K + 1 <= NT) {
         const int epb = NT / (K + 1);
-        auto k = edge_kernel<RB>;
+        auto k = sc.grid ? edge_kernel<RB, true> : edge_kernel<RB, false>;
         const int grid = grid_for(k, smem, (E + epb - 1) / epb);
         if (grid < 0) return CBFRRT_ERR_CUDA;
         k<<<grid, NT, smem, st>>>(sc, qf, qt, E, K, epb, ts, th, valid, first_bad);
     } else {
-        auto k = edge_seq_kernel<RB>;
+        auto k = sc.grid ? edge_seq_kernel<RB, true> : edge_seq_kernel<RB, false>;
         const int grid = grid_for(k, smem, (E + NT - 1) / NT);
         if (grid < 0) return CBFRRT_ERR_CUDA;
         k<<<grid, NT, smem, st>>>(sc, qf, qt, E, K, ts, th, valid, first_bad);
@@ -776,172 +898,36 @@ static int launch_edges(const SceneArgs& sc, const float* qf, const float* qt, l
 template <class RB>
 static int launch_rollout(const SceneArgs& sc, const NetArgs& net, const float* q0, long long T, const RolloutArgs& ra,
                           float ts, float th, float* qf, uint8_t* alive, int* done, float* traj, cudaStream_t st) {
+    if (use_tc() && (T > SMALL_BATCH || force_tc())) {
+        const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
+        auto k = sc.grid ? rollout_kernel_tc<RB, 2, true> : rollout_kernel_tc<RB, 2, false>;
+        const int grid = grid_for_tc(k, smem, T);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, NTC, smem, st>>>(sc, net, q0, T, ra, ts, th, qf, alive, done, traj);
+        return finish_launch();
+    }
     using LY = NetLayout<RB::N + 1, 48, 2>;
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<RB::N>::TOTAL, 48 * NT);
-    auto k = rollout_kernel<RB, 48, 2>;
+    auto k = sc.grid ? rollout_kernel<RB, 48, 2, true> : rollout_kernel<RB, 48, 2, false>;
     const int grid = grid_for(k, smem, (T + NT - 1) / NT);
     if (grid < 0) return CBFRRT_ERR_CUDA;
     k<<<grid, NT, smem, st>>>(sc, net, q0, T, ra, ts, th, qf, alive, done, traj);
     return finish_launch();
 }
 
+// ---- per-robot launch wrappers: each is defined in its own translation unit (k_<family>_<robot>.cu) so that the
+// big template instantiations compile in parallel
+#define CBF_DECLARE_ROBOT(R)                                                                                          \
+    int launch_collide_##R(const SceneArgs&, const float*, long long, long long, float, float, const CollideOutPtrs&,  \
+                           cudaStream_t);                                                                              \
+    int launch_safety_##R(const SceneArgs&, const NetArgs&, const float*, long long, long long, float, float,          \
+                          const CollideOutPtrs&, const FilterOutPtrs&, cudaStream_t);                                  \
+    int launch_edges_##R(const SceneArgs&, const float*, const float*, long long, int, float, float, uint8_t*, int*,   \
+                         cudaStream_t);                                                                                \
+    int launch_rollout_##R(const SceneArgs&, const NetArgs&, const float*, long long, const RolloutArgs&, float,       \
+                           float, float*, uint8_t*, int*, float*, cudaStream_t);
+CBF_DECLARE_ROBOT(panda)
+CBF_DECLARE_ROBOT(magician)
+#undef CBF_DECLARE_ROBOT
+
 }  // namespace cbfrrt
-
-using namespace cbfrrt;
-
-extern "C" {
-
-int cbfrrt_abi_version(void) { return CBFRRT_ABI_VERSION; }
-
-const char* cbfrrt_status_string(int s) {
-    switch (s) {
-        case CBFRRT_OK: return "ok";
-        case CBFRRT_ERR_BAD_ROBOT: return "unknown robot id";
-        case CBFRRT_ERR_BAD_SHAPE: return "bad shape or missing pointer";
-        case CBFRRT_ERR_UNSUPPORTED: return "unsupported network shape or scene size";
-        case CBFRRT_ERR_CUDA: return "CUDA launch/runtime failure";
-        case CBFRRT_ERR_ALIGNMENT: return "scene/weight buffer not 16-byte aligned";
-        default: return "unknown status";
-    }
-}
-
-int cbfrrt_last_cuda_error(void) { return g_last_cuda.load(); }
-int64_t cbfrrt_launch_count(void) { return g_launches.load(); }
-
-int cbfrrt_robot_info(int robot, int32_t* n, int32_t* n_links, int32_t* n_spheres) {
-    if (robot == CBFRRT_ROBOT_PANDA) { *n = Panda::N; *n_links = Panda::NLINKS; *n_spheres = Panda::NSPH; return CBFRRT_OK; }
-    if (robot == CBFRRT_ROBOT_MAGICIAN) { *n = Magician::N; *n_links = Magician::NLINKS; *n_spheres = Magician::NSPH; return CBFRRT_OK; }
-    return CBFRRT_ERR_BAD_ROBOT;
-}
-
-int cbfrrt_fk(int robot, const float* q, int64_t q_stride, int64_t B, float* pos, float* rot, void* stream) {
-    if (B < 0 || !q || !pos || !rot) return CBFRRT_ERR_BAD_SHAPE;
-    if (B == 0) return CBFRRT_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (robot == CBFRRT_ROBOT_PANDA) return q_stride < Panda::N ? CBFRRT_ERR_BAD_SHAPE : launch_fk<Panda>(q, q_stride, B, pos, rot, st);
-    if (robot == CBFRRT_ROBOT_MAGICIAN) return q_stride < Magician::N ? CBFRRT_ERR_BAD_SHAPE : launch_fk<Magician>(q, q_stride, B, pos, rot, st);
-    return CBFRRT_ERR_BAD_ROBOT;
-}
-
-int cbfrrt_collide(int robot, const cbfrrt_scene* scene, const float* q, int64_t q_stride, int64_t B, float thr_soft,
-                   float thr_hard, uint8_t* safe, uint8_t* unsafe, float* datax, int32_t* arg_link, int32_t* arg_obs,
-                   float* mins, void* stream) {
-    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
-    if (B < 0 || !q) return CBFRRT_ERR_BAD_SHAPE;
-    SceneArgs sc;
-    int rc = check_scene(scene, sc);
-    if (rc) return rc;
-    if (B == 0) return CBFRRT_OK;
-    CollideOutPtrs out{safe, unsafe, datax, arg_link, arg_obs, mins};
-    cudaStream_t st = (cudaStream_t)stream;
-    if (robot == CBFRRT_ROBOT_PANDA) return q_stride < Panda::N ? CBFRRT_ERR_BAD_SHAPE : launch_collide<Panda>(sc, q, q_stride, B, thr_soft, thr_hard, out, st);
-    return q_stride < Magician::N ? CBFRRT_ERR_BAD_SHAPE : launch_collide<Magician>(sc, q, q_stride, B, thr_soft, thr_hard, out, st);
-}
-
-int cbfrrt_cbf_filter(int n, const cbfrrt_cbf_net* net, const float* datax, int64_t B, const cbfrrt_filter_params* fp,
-                      float* h, float* J, float* u, float* r, void* stream) {
-    if (B < 0 || !datax) return CBFRRT_ERR_BAD_SHAPE;
-    if (n != Panda::N && n != Magician::N) return CBFRRT_ERR_UNSUPPORTED;
-    NetArgs na;
-    int rc = check_net(n, net, fp, B, na);
-    if (rc) return rc;
-    if (B == 0) return CBFRRT_OK;
-    FilterOutPtrs out{h, J, u, r};
-    cudaStream_t st = (cudaStream_t)stream;
-    return n == Panda::N ? launch_filter<Panda::N>(na, datax, B, out, st) : launch_filter<Magician::N>(na, datax, B, out, st);
-}
-
-int cbfrrt_qp(int n, const float* a, const float* c, const float* u_ref, int64_t B, const float* u_lo, const float* u_hi,
-              float relaxation_penalty, float* u, float* r, void* stream) {
-    if (B < 0 || !a || !c || !u_ref || !u_lo || !u_hi || !u) return CBFRRT_ERR_BAD_SHAPE;
-    if (n < 1 || n > 8) return CBFRRT_ERR_UNSUPPORTED;
-    if (B == 0) return CBFRRT_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long blocks = (B + 255) / 256;
-    const int grid = (int)(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
-    switch (n) {
-#define CBF_QP_CASE(NN) case NN: qp_kernel<NN><<<grid, 256, 0, st>>>(a, c, u_ref, B, u_lo, u_hi, relaxation_penalty, u, r); break;
-        CBF_QP_CASE(1) CBF_QP_CASE(2) CBF_QP_CASE(3) CBF_QP_CASE(4) CBF_QP_CASE(5) CBF_QP_CASE(6) CBF_QP_CASE(7) CBF_QP_CASE(8)
-#undef CBF_QP_CASE
-    }
-    return finish_launch();
-}
-
-int cbfrrt_safety_filter(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* net, const float* q,
-                         int64_t q_stride, int64_t B, const cbfrrt_filter_params* fp, float thr_soft, float thr_hard,
-                         uint8_t* safe, uint8_t* unsafe, float* datax, float* h, float* J, float* u, float* r,
-                         void* stream) {
-    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
-    if (B < 0 || !q) return CBFRRT_ERR_BAD_SHAPE;
-    const int n = robot == CBFRRT_ROBOT_PANDA ? Panda::N : Magician::N;
-    if (q_stride < n) return CBFRRT_ERR_BAD_SHAPE;
-    SceneArgs sc;
-    NetArgs na;
-    int rc = check_scene(scene, sc);
-    if (rc) return rc;
-    rc = check_net(n, net, fp, B, na);
-    if (rc) return rc;
-    if (B == 0) return CBFRRT_OK;
-    CollideOutPtrs co{safe, unsafe, datax, nullptr, nullptr, nullptr};
-    FilterOutPtrs fo{h, J, u, r};
-    cudaStream_t st = (cudaStream_t)stream;
-    return robot == CBFRRT_ROBOT_PANDA ? launch_safety<Panda>(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, st)
-                                       : launch_safety<Magician>(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, st);
-}
-
-int cbfrrt_edge_validity(int robot, const cbfrrt_scene* scene, const float* q_from, const float* q_to, int64_t E,
-                         int32_t n_interp, float thr_soft, float thr_hard, uint8_t* valid, int32_t* first_bad,
-                         void* stream) {
-    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
-    if (E < 0 || n_interp < 1 || !q_from || !q_to || !valid || !first_bad) return CBFRRT_ERR_BAD_SHAPE;
-    SceneArgs sc;
-    int rc = check_scene(scene, sc);
-    if (rc) return rc;
-    if (E == 0) return CBFRRT_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    return robot == CBFRRT_ROBOT_PANDA ? launch_edges<Panda>(sc, q_from, q_to, E, n_interp, thr_soft, thr_hard, valid, first_bad, st)
-                                       : launch_edges<Magician>(sc, q_from, q_to, E, n_interp, thr_soft, thr_hard, valid, first_bad, st);
-}
-
-int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* net, const float* q0, int64_t T,
-                   const cbfrrt_filter_params* fp, const cbfrrt_rollout_params* rp, float thr_soft, float thr_hard,
-                   float* q_final, uint8_t* alive, int32_t* steps_done, float* traj, void* stream) {
-    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
-    if (T < 0 || !rp || rp->steps < 0 || rp->ctrl_every < 1 || !q0 || !q_final || !alive || !steps_done)
-        return CBFRRT_ERR_BAD_SHAPE;
-    if (rp->stuck_lag < 0 || (rp->stuck_lag > 0 && (!traj || rp->stuck_after < rp->stuck_lag))) return CBFRRT_ERR_BAD_SHAPE;
-    if (fp && fp->u_ref) return CBFRRT_ERR_UNSUPPORTED;  // the loop needs the nominal controller
-    const int n = robot == CBFRRT_ROBOT_PANDA ? Panda::N : Magician::N;
-    SceneArgs sc;
-    NetArgs na;
-    int rc = check_scene(scene, sc);
-    if (rc) return rc;
-    rc = check_net(n, net, fp, T, na);
-    if (rc) return rc;
-    if (T == 0) return CBFRRT_OK;
-    const RolloutArgs ra{rp->steps, rp->ctrl_every, rp->dt, rp->stuck_lag, rp->stuck_after, rp->stuck_eps, rp->keep_going};
-    cudaStream_t st = (cudaStream_t)stream;
-    return robot == CBFRRT_ROBOT_PANDA
-               ? launch_rollout<Panda>(sc, na, q0, T, ra, thr_soft, thr_hard, q_final, alive, steps_done, traj, st)
-               : launch_rollout<Magician>(sc, na, q0, T, ra, thr_soft, thr_hard, q_final, alive, steps_done, traj, st);
-}
-
-int cbfrrt_fma_probe(int32_t grid, int32_t block, int32_t iters, float* sink, void* stream) {
-    if (grid < 1 || block < 32 || block > 1024 || iters < 1 || !sink) return CBFRRT_ERR_BAD_SHAPE;
-    fma_probe_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
-    return finish_launch();
-}
-
-int cbfrrt_sample_states(int robot, uint32_t seed, uint64_t start_row, int64_t B, float* q, void* stream) {
-    if (B < 0 || !q) return CBFRRT_ERR_BAD_SHAPE;
-    if (B == 0) return CBFRRT_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long blocks = (B * 8 + 255) / 256;
-    const int grid = (int)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
-    if (robot == CBFRRT_ROBOT_PANDA) sample_kernel<Panda><<<grid, 256, 0, st>>>(seed, start_row, B, q);
-    else if (robot == CBFRRT_ROBOT_MAGICIAN) sample_kernel<Magician><<<grid, 256, 0, st>>>(seed, start_row, B, q);
-    else return CBFRRT_ERR_BAD_ROBOT;
-    return finish_launch();
-}
-
-}  // extern "C"

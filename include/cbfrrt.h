@@ -62,6 +62,8 @@ typedef struct {
     int32_t _pad;
     const float *boxes;   /* device, [n_boxes, 8], 16-byte aligned */
     const float *spheres; /* device, [n_spheres, 4], 16-byte aligned */
+    const void *grid;     /* optional device buffer of cbfrrt_grid_bytes() bytes filled by cbfrrt_grid_build for
+                             THIS scene (exact broad phase: same results, far fewer pair tests); NULL = brute force */
 } cbfrrt_scene;
 
 typedef struct {
@@ -106,6 +108,13 @@ const char *cbfrrt_status_string(int status);
 int cbfrrt_last_cuda_error(void);
 /* n (dof), number of pybullet links (FK rows), number of link spheres */
 int cbfrrt_robot_info(int robot, int32_t *n, int32_t *n_links, int32_t *n_spheres);
+
+/* ---- scene acceleration structure (built once per ArmEnv.reset_env, environment/arm_env.py:63) --------------
+ * Nearest-candidate grid over the arm's workspace: per 5 cm cell, the obstacles that can be the closest one for
+ * some point of the cell.  Results with and without the grid are bit-identical (csrc/grid.cuh).  The caller owns
+ * the buffer (16-byte aligned, cbfrrt_grid_bytes() bytes) and must rebuild it whenever boxes / spheres change. */
+int64_t cbfrrt_grid_bytes(void);
+int cbfrrt_grid_build(const cbfrrt_scene *scene, void *grid, void *stream);
 
 /* ---- K1  forward kinematics ----------------------------------------------------------------------------
  * Replaces BasicRobot.forward_kinematics + set_joint_position (environment/basic_robot.py:55-68): world pose

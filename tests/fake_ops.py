@@ -27,7 +27,7 @@ def install(monkeypatch):
         pos, rot = c_oracle.fk(NAME[robot_id], _np(q))
         return torch.from_numpy(pos), torch.from_numpy(rot)
 
-    def collide(q, boxes, spheres, floor, thr_soft, thr_hard, robot_id):
+    def collide(q, boxes, spheres, floor, grid, thr_soft, thr_hard, robot_id):
         b, s = _scene(boxes, spheres)
         o = c_oracle.collide(NAME[robot_id], _np(q)[:, :ops.ROBOT_N[robot_id]], b, s, bool(floor), thr_soft, thr_hard)
         return tuple(torch.from_numpy(o[k]) for k in ("safe", "unsafe", "datax", "arg_link", "arg_obs", "mins"))
@@ -48,12 +48,12 @@ def install(monkeypatch):
         u, r = c_oracle.qp(_np(a), _np(c), _np(u_ref), _np(u_lo), _np(u_hi), penalty)
         return torch.from_numpy(u), torch.from_numpy(r)
 
-    def edge_validity(q_from, q_to, n_interp, boxes, spheres, floor, thr_soft, thr_hard, robot_id):
+    def edge_validity(q_from, q_to, n_interp, boxes, spheres, floor, grid, thr_soft, thr_hard, robot_id):
         b, s = _scene(boxes, spheres)
         v, f = c_oracle.edge_validity(NAME[robot_id], _np(q_from), _np(q_to), n_interp, b, s, bool(floor), thr_soft, thr_hard)
         return torch.from_numpy(v), torch.from_numpy(f)
 
-    def rollout(q0, goal, steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, want_traj, keep_going, boxes, spheres, floor,
+    def rollout(q0, goal, steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, want_traj, keep_going, boxes, spheres, floor, grid,
                 weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id, hidden, layers):
         b, s = _scene(boxes, spheres)
         qf, alive, done, traj = c_oracle.rollout(NAME[robot_id], _np(q0), _np(goal), steps, ctrl_every, dt, b, s, bool(floor),
@@ -63,7 +63,7 @@ def install(monkeypatch):
         return (torch.from_numpy(qf), torch.from_numpy(alive), torch.from_numpy(done),
                 torch.from_numpy(traj) if traj is not None else torch.empty(0))
 
-    def valid_control(q, goal, boxes, spheres, floor, weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id,
+    def valid_control(q, goal, boxes, spheres, floor, grid, weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id,
                       hidden, layers):
         b, s = _scene(boxes, spheres)
         o = c_oracle.safety_filter(NAME[robot_id], _np(q), b, s, bool(floor), _np(weights), hidden, layers, _np(goal), _np(K),

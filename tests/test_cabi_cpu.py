@@ -37,16 +37,18 @@ def test_robot_info_and_status_strings():
 def test_argument_validation_happens_before_cuda():
     from cbfrrt import _lib
     lib = _lib.lib
-    sc = _lib.Scene(0, 0, 1, 0, None, None)
+    sc = _lib.Scene(0, 0, 1, 0, None, None, None)
+    assert lib.cbfrrt_grid_bytes() == 44 * 44 * 44 * 24 * 2
+    assert lib.cbfrrt_grid_build(C.byref(sc), None, None) == -2
     buf = (C.c_float * 64)()
     p = C.cast(buf, C.c_void_p)
     assert lib.cbfrrt_fk(5, p, 7, 1, p, p, None) == -1                                   # bad robot
     assert lib.cbfrrt_fk(0, p, 7, -1, p, p, None) == -2                                  # negative batch
     assert lib.cbfrrt_fk(0, p, 3, 1, p, p, None) == -2                                   # stride < n
     assert lib.cbfrrt_collide(0, C.byref(sc), None, 7, 1, 0.02, 0.0, *([None] * 6), None) == -2
-    big = _lib.Scene(2000, 0, 1, 0, p, None)
+    big = _lib.Scene(2000, 0, 1, 0, p, None, None)
     assert lib.cbfrrt_collide(0, C.byref(big), p, 7, 1, 0.02, 0.0, *([None] * 6), None) == -3  # > MAX_OBSTACLES
-    mis = _lib.Scene(1, 0, 1, 0, C.c_void_p(p.value + 4), None)
+    mis = _lib.Scene(1, 0, 1, 0, C.c_void_p(p.value + 4), None, None)
     assert lib.cbfrrt_collide(0, C.byref(mis), p, 7, 1, 0.02, 0.0, *([None] * 6), None) == -5  # alignment
     net = _lib.CbfNet(8, 64, 2, 0, p)
     fp = _lib.FilterParams(p, 1, p, p, p, 0.1, 5000.0, None)

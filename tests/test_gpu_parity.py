@@ -18,10 +18,14 @@ def _t(a, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=DEV)
 
 
-def _scene(boxes6, spheres):
+def _scene(boxes6, spheres, grid=True):
+    """-> (boxes8, spheres4, grid): the broad-phase grid is ON by default, so every comparison below against the
+    brute-force oracle also proves that the grid changes nothing."""
     from cbfrrt import ops
     boxes6 = np.zeros((0, 6), np.float32) if boxes6 is None else np.asarray(boxes6, np.float32).reshape(-1, 6)
-    return ops.pack_scene(boxes6[:, :3], boxes6[:, 3:], spheres, device=DEV)
+    b8, s4 = ops.pack_scene(boxes6[:, :3], boxes6[:, 3:], spheres, device=DEV)
+    gr = ops.build_grid(b8, s4) if (grid and b8.shape[0] + s4.shape[0] > 0) else ops.no_grid(DEV)
+    return b8, s4, gr
 
 
 def _net(w):
@@ -65,8 +69,8 @@ def test_collide_bit_exact(coracle, robot, scene, B):
     from cbfrrt import ops, workloads as W
     boxes, sph, floor = _get_scene(scene)
     q = W.sample_states(robot, B, 17 + B)
-    b8, s4 = _scene(boxes, sph)
-    safe, unsafe, datax, arg_link, arg_obs, mins = ops.collide(_t(q), b8, s4, int(floor), 0.02, 0.0, ops.ROBOT_ID[robot])
+    b8, s4, gr = _scene(boxes, sph)
+    safe, unsafe, datax, arg_link, arg_obs, mins = ops.collide(_t(q), b8, s4, int(floor), gr, 0.02, 0.0, ops.ROBOT_ID[robot])
     o = coracle.collide(robot, q, boxes, sph, floor, 0.02, 0.0)
     n = q.shape[1]
     assert np.array_equal(safe.cpu().numpy(), o["safe"]) and np.array_equal(unsafe.cpu().numpy(), o["unsafe"])
@@ -76,20 +80,41 @@ def test_collide_bit_exact(coracle, robot, scene, B):
     assert rel_err(d[:, n + 1:], o["datax"][:, n + 1:]) < TOL          # do/dq
     assert np.array_equal(mins.cpu().numpy(), o["mins"])
     # the mask-only and observation-only instantiations agree with the full one
-    s2, u2 = ops.masks(_t(q), b8, s4, int(floor), 0.02, 0.0, ops.ROBOT_ID[robot])
-    s3, u3, d3 = ops.observe(_t(q), b8, s4, int(floor), 0.02, 0.0, ops.ROBOT_ID[robot])
+    s2, u2 = ops.masks(_t(q), b8, s4, int(floor), gr, 0.02, 0.0, ops.ROBOT_ID[robot])
+    s3, u3, d3 = ops.observe(_t(q), b8, s4, int(floor), gr, 0.02, 0.0, ops.ROBOT_ID[robot])
     assert torch.equal(s2, safe) and torch.equal(u2, unsafe) and torch.equal(s3, safe) and torch.equal(d3, datax)
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_grid_broadphase_is_exact(robot):
+    """every scene-consuming op gives bit-identical outputs with and without the nearest-candidate grid, incl.
+    dense scenes that overflow cells and states whose spheres leave the grid region"""
+    from cbfrrt import ops, workloads as W
+    rid = ops.ROBOT_ID[robot]
+    q = W.sample_states(robot, 20000, 4)
+    q[:50] *= 3.0        # far outside the joint limits: still a valid FK input, spheres anywhere
+    for boxes, sph in ((W.random_boxes(256, 2, 0.01, 0.05), None), (W.random_boxes(40, 3, 0.05, 0.3), W.random_spheres(24, 5, 0.05, 0.3)),
+                       (np.array([[0.0, 0.0, 2.5, 0.2, 0.2, 0.2]], np.float32), None)):
+        b8, s4, gr = _scene(boxes, sph)
+        a = ops.collide(_t(q), b8, s4, 1, gr, 0.02, 0.0, rid)
+        b = ops.collide(_t(q), b8, s4, 1, ops.no_grid(DEV), 0.02, 0.0, rid)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+        qf, qt = _t(q[:4000]), _t(q[4000:8000])
+        for x, y in zip(ops.edge_validity(qf, qt, 7, b8, s4, 1, gr, 0.02, 0.0, rid),
+                        ops.edge_validity(qf, qt, 7, b8, s4, 1, ops.no_grid(DEV), 0.02, 0.0, rid)):
+            assert torch.equal(x, y)
 
 
 def test_collide_thresholds_and_strided_rows(coracle):
     from cbfrrt import ops, workloads as W
     boxes, sph, floor = _get_scene("mixed")
     q = W.sample_states("panda", 3000, 1)
-    b8, s4 = _scene(boxes, sph)
+    b8, s4, gr = _scene(boxes, sph)
     wide = torch.zeros(3000, 15, device=DEV)
     wide[:, :7] = _t(q)
     for ts, th in ((0.05, 0.0), (0.02, 0.02), (0.0, -0.01)):
-        s, u = ops.masks(wide[:, :7], b8, s4, 1, ts, th, 0)   # x[:, :q_dims] view: row stride 15, no copy
+        s, u = ops.masks(wide[:, :7], b8, s4, 1, gr, ts, th, 0)   # x[:, :q_dims] view: row stride 15, no copy
         o = coracle.collide("panda", q, boxes, sph, True, ts, th)
         assert np.array_equal(s.cpu().numpy(), o["safe"]) and np.array_equal(u.cpu().numpy(), o["unsafe"])
 
@@ -99,14 +124,16 @@ def test_collide_many_obstacles_and_limit(coracle):
     from cbfrrt._lib import CbfrrtError
     q = W.sample_states("panda", 2048, 9)
     boxes, sph = W.random_boxes(700, 2, 0.01, 0.04), W.random_spheres(324, 5, 0.01, 0.04)   # 1024 = the maximum
-    b8, s4 = _scene(boxes, sph)
-    safe, unsafe, datax, al, ao, mins = ops.collide(_t(q), b8, s4, 1, 0.02, 0.0, 0)
+    b8, s4, gr = _scene(boxes, sph)
+    safe, unsafe, datax, al, ao, mins = ops.collide(_t(q), b8, s4, 1, gr, 0.02, 0.0, 0)
     o = coracle.collide("panda", q, boxes, sph, True, 0.02, 0.0)
     assert np.array_equal(safe.cpu().numpy(), o["safe"]) and np.array_equal(ao.cpu().numpy(), o["arg_obs"])
     assert np.array_equal(datax.cpu().numpy()[:, 7], o["datax"][:, 7])
-    b8big, _ = _scene(W.random_boxes(1025, 2, 0.01, 0.02), None)
+    b8big, _, _ = _scene(W.random_boxes(1025, 2, 0.01, 0.02), None, grid=False)
     with pytest.raises(CbfrrtError):
-        ops.masks(_t(q), b8big, s4[:0], 1, 0.02, 0.0, 0)
+        ops.masks(_t(q), b8big, s4[:0], 1, ops.no_grid(DEV), 0.02, 0.0, 0)
+    with pytest.raises(CbfrrtError):
+        ops.build_grid(b8big, s4[:0])
 
 
 @pytest.mark.parametrize("robot", ["panda", "magician"])
@@ -174,9 +201,9 @@ def test_safety_filter_fused_configs(coracle, cfg, scale):
     """BASELINE configs[0] in full (4096 Panda states, the reference's CPU-runnable case) and configs[1] at 1/64."""
     from cbfrrt import ops, workloads as W
     w = W.config(cfg, scale=scale)
-    b8, s4 = _scene(w["boxes"], w["spheres"])
+    b8, s4, gr = _scene(w["boxes"], w["spheres"])
     rid = ops.ROBOT_ID[w["robot"]]
-    args = (_t(w["q"]), _t(w["goal"]), b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"],
+    args = (_t(w["q"]), _t(w["goal"]), b8, s4, 1, gr, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"],
             w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
     safe, unsafe, datax, h, J, u, r = ops.safety_filter(*args)
     o = coracle.safety_filter(w["robot"], w["q"], w["boxes"], w["spheres"], True, w["weights"], 48, 2, w["goal"],
@@ -201,8 +228,8 @@ def test_edge_validity_bit_exact(coracle, robot, K):
     qf = W.sample_states(robot, E, 0)
     m_lo, m_hi = np.array(W.ROBOT_MODELS[robot]["q_lower"], np.float32), np.array(W.ROBOT_MODELS[robot]["q_upper"], np.float32)
     qt = np.clip(qf + np.random.default_rng(1).uniform(-0.35, 0.35, qf.shape).astype(np.float32), m_lo, m_hi)
-    b8, s4 = _scene(w["boxes"], w["spheres"])
-    valid, first_bad = ops.edge_validity(_t(qf), _t(qt), K, b8, s4, 1, 0.02, 0.0, ops.ROBOT_ID[robot])
+    b8, s4, gr = _scene(w["boxes"], w["spheres"])
+    valid, first_bad = ops.edge_validity(_t(qf), _t(qt), K, b8, s4, 1, gr, 0.02, 0.0, ops.ROBOT_ID[robot])
     vo, fo = coracle.edge_validity(robot, qf, qt, K, w["boxes"], w["spheres"], True, 0.02, 0.0)
     assert np.array_equal(valid.cpu().numpy(), vo) and np.array_equal(first_bad.cpu().numpy(), fo)
     assert 0 < vo.mean() < 1
@@ -213,15 +240,15 @@ def test_edge_validity_equals_pointwise_safe_mask():
     from cbfrrt import ops, workloads as W
     w = W.config(2, scale=1 / 1024)
     qf, qt, K = _t(w["q"]), _t(w["q_to"]), 32
-    b8, s4 = _scene(w["boxes"], w["spheres"])
-    valid, first_bad = ops.edge_validity(qf, qt, K, b8, s4, 1, 0.02, 0.0, 0)
+    b8, s4, gr = _scene(w["boxes"], w["spheres"])
+    valid, first_bad = ops.edge_validity(qf, qt, K, b8, s4, 1, gr, 0.02, 0.0, 0)
     bad = torch.full((qf.shape[0],), 1 << 30, device=DEV, dtype=torch.int64)
     for k in range(K + 1):
         # the interpolation contract is c = fmaf(k/K, q_to - q_from, q_from); float64 holds the product exactly
         t = np.float64(np.float32(k) / np.float32(K))
         d = (w["q_to"] - w["q"]).astype(np.float64)
         c = qt if k == K else _t((t * d + w["q"].astype(np.float64)).astype(np.float32))
-        s, _ = ops.masks(c, b8, s4, 1, 0.02, 0.0, 0)
+        s, _ = ops.masks(c, b8, s4, 1, gr, 0.02, 0.0, 0)
         bad = torch.where((s == 0) & (bad > k), torch.full_like(bad, k), bad)
     exp_valid = (bad == (1 << 30))
     assert torch.equal(valid.bool(), exp_valid)
@@ -246,13 +273,13 @@ def test_rollout_against_oracle(coracle):
     margin to that event is within tolerance."""
     from cbfrrt import ops, workloads as W
     w = W.config(3, scale=1 / 256)
-    b8, s4 = _scene(w["boxes"], w["spheres"])
+    b8, s4, gr = _scene(w["boxes"], w["spheres"])
     T = w["q"].shape[0]
     safe0 = coracle.collide("panda", w["q"], w["boxes"], None, True)["safe"].astype(bool)
     q0, goal = w["q"][safe0][:600], w["goal"][safe0][:600]
     for steps, stuck in ((30, (9, 10, 0.1)), (60, (0, 10, 0.1))):
         qf, alive, done, traj = ops.rollout(_t(q0), _t(goal), steps, w["ctrl_every"], w["dt"], stuck[0], stuck[1], stuck[2],
-                                            True, False, b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"],
+                                            True, False, b8, s4, 1, gr, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"],
                                             w["penalty"], w["thr_soft"], w["thr_hard"], 0, 48, 2)
         qo, ao, do_, to = coracle.rollout("panda", q0, goal, steps, w["ctrl_every"], w["dt"], w["boxes"], None, True,
                                           w["weights"], 48, 2, w["K"], w["u_lo"], w["u_hi"], w["thr_soft"], w["thr_hard"],
@@ -274,9 +301,9 @@ def test_rollout_against_oracle(coracle):
 def test_host_buffer_api_matches_device_api():
     from cbfrrt import ops, workloads as W
     w = W.config(1, scale=1 / 8)   # 131072 magician states: several chunks on 3 streams
-    b8, s4 = _scene(w["boxes"], w["spheres"])
+    b8, s4, gr = _scene(w["boxes"], w["spheres"])
     B, n = w["q"].shape
-    dev = ops.safety_filter(_t(w["q"]), _t(w["goal"]), b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]),
+    dev = ops.safety_filter(_t(w["q"]), _t(w["goal"]), b8, s4, 1, gr, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]),
                             w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], 1, 48, 2)
     out = dict(safe=np.empty(B, np.uint8), unsafe=np.empty(B, np.uint8), datax=np.empty((B, 2 * n + 1), np.float32),
                h=np.empty(B, np.float32), J=np.empty((B, n), np.float32), u=np.empty((B, n), np.float32),
@@ -287,7 +314,7 @@ def test_host_buffer_api_matches_device_api():
         assert np.array_equal(out[k], t.cpu().numpy()), k
     # per-row goals + a subset of outputs
     goal = W.sample_states("magician", B, 5)
-    dev = ops.valid_control(_t(w["q"]), _t(goal), b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]),
+    dev = ops.valid_control(_t(w["q"]), _t(goal), b8, s4, 1, gr, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]),
                             w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], 1, 48, 2)
     out = dict(safe=np.empty(B, np.uint8), u=np.empty((B, n), np.float32))
     ops.safety_filter_host("magician", w["q"], w["boxes"], w["spheres"], True, w["weights"], 48, 2, goal, w["K"],
@@ -300,9 +327,9 @@ def test_full_size_config1_properties(coracle):
     random 4096-row sample, and the QP feasibility / box constraints on every row."""
     from cbfrrt import ops, workloads as W
     w = W.config(1)
-    b8, s4 = _scene(w["boxes"], w["spheres"])
+    b8, s4, gr = _scene(w["boxes"], w["spheres"])
     q = _t(w["q"])
-    common = (_t(w["goal"]), b8, s4, 1, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"],
+    common = (_t(w["goal"]), b8, s4, 1, gr, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"],
               w["thr_soft"], w["thr_hard"], 1, 48, 2)
     full = ops.safety_filter(q, *common)
     half = 333333

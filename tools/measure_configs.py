@@ -57,6 +57,7 @@ def main():
         w = W.config(idx, scale=scale)
         rid, n = ops.ROBOT_ID[w["robot"]], w["n"]
         b8, s4 = ops.pack_scene(w["boxes"][:, :3], w["boxes"][:, 3:], w["spheres"], device=dev)
+        gr = ops.build_grid(b8, s4) if b8.shape[0] + s4.shape[0] > 0 else ops.no_grid(dev)
         net = ops.pack_weights(w["state_dict"], n, 48, 2, device=dev)
         K, lo, hi = t(w["K"]), t(w["u_lo"]), t(w["u_hi"])
         goal = t(w["goal"])
@@ -65,12 +66,12 @@ def main():
         if idx in (0, 1, 4):
             q = t(w["q"]) if w["q"] is not None else ops.sample_states(w["n_states"], 0, 0, rid, device=dev)
             B = q.shape[0]
-            common = (goal, b8, s4, 1, net, K, lo, hi, w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
+            common = (goal, b8, s4, 1, gr, net, K, lo, hi, w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
             variants = {"safety_filter(all outputs)": lambda: ops.safety_filter(q, *common),
                         "valid_control(valid,u)": lambda: ops.valid_control(q, *common),
-                        "observe(masks+datax)": lambda: ops.observe(q, b8, s4, 1, w["thr_soft"], w["thr_hard"], rid),
-                        "masks": lambda: ops.masks(q, b8, s4, 1, w["thr_soft"], w["thr_hard"], rid)}
-            datax = ops.observe(q, b8, s4, 1, w["thr_soft"], w["thr_hard"], rid)[2]
+                        "observe(masks+datax)": lambda: ops.observe(q, b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid),
+                        "masks": lambda: ops.masks(q, b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid)}
+            datax = ops.observe(q, b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid)[2]
             variants["cbf_filter(datax->h,J,u,r)"] = lambda: ops.cbf_filter(datax, goal, net, K, lo, hi, w["lam"], w["penalty"], 48, 2, torch.empty(0, device=dev))
             res["units"] = B
             res["unit"] = "states"
@@ -85,7 +86,7 @@ def main():
         elif idx == 2:
             qf, qt = t(w["q"]), t(w["q_to"])
             E = qf.shape[0]
-            fn = lambda: ops.edge_validity(qf, qt, w["n_interp"], b8, s4, 1, w["thr_soft"], w["thr_hard"], rid)
+            fn = lambda: ops.edge_validity(qf, qt, w["n_interp"], b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid)
             med, mn = timed(fn, args.iters, flush)
             res.update(units=E, unit="edges", edge_validity={"ms": med, "ms_min": mn, "per_s": E / (med * 1e-3),
                                                               "configs_per_s": E * (w["n_interp"] + 1) / (med * 1e-3)})
@@ -98,11 +99,11 @@ def main():
         elif idx == 3:
             q0 = t(w["q"])
             T = q0.shape[0]
-            safe = ops.masks(q0, b8, s4, 1, w["thr_soft"], w["thr_hard"], rid)[0].bool()   # "filtered to safe" 
+            safe = ops.masks(q0, b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid)[0].bool()   # "filtered to safe" 
             keep = q0[safe]
             q0 = keep.repeat((T + keep.shape[0] - 1) // keep.shape[0], 1)[:T].contiguous()
             res["safe_start_fraction"] = float(safe.float().mean().item())
-            fn = lambda: ops.rollout(q0, goal, w["steps"], w["ctrl_every"], w["dt"], 0, 10, 0.1, False, True, b8, s4, 1, net, K, lo, hi,
+            fn = lambda: ops.rollout(q0, goal, w["steps"], w["ctrl_every"], w["dt"], 0, 10, 0.1, False, True, b8, s4, 1, gr, net, K, lo, hi,
                                      w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
             med, mn = timed(fn, max(2, args.iters // 2), flush)
             qf, alive, done, _ = fn()
