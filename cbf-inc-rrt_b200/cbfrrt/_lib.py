@@ -34,6 +34,11 @@ class FilterParams(C.Structure):
                 ("u_ref", C.c_void_p)]
 
 
+class PeerOut(C.Structure):
+    _fields_ = [("n_peers", C.c_int32), ("_pad", C.c_int32), ("row_offset", C.c_int64), ("valid", C.c_void_p * 8),
+                ("u", C.c_void_p * 8)]
+
+
 class RolloutParams(C.Structure):
     _fields_ = [("steps", C.c_int32), ("ctrl_every", C.c_int32), ("dt", C.c_float), ("stuck_lag", C.c_int32),
                 ("stuck_after", C.c_int32), ("stuck_eps", C.c_float), ("keep_going", C.c_int32)]
@@ -55,6 +60,8 @@ SIGNATURES = {
     "cbfrrt_qp": (C.c_int, [_I, _P, _P, _P, _L, _P, _P, _F, _P, _P, _P]),
     "cbfrrt_safety_filter": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, _L, C.POINTER(FilterParams),
                                        _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cbfrrt_safety_filter_scatter": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, _L,
+                                               C.POINTER(FilterParams), _F, _F, C.POINTER(PeerOut), _P]),
     "cbfrrt_edge_validity": (C.c_int, [_I, C.POINTER(Scene), _P, _P, _L, C.c_int32, _F, _F, _P, _P, _P]),
     "cbfrrt_rollout": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, C.POINTER(FilterParams),
                                  C.POINTER(RolloutParams), _F, _F, _P, _P, _P, _P, _P]),

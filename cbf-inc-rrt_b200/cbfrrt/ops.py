@@ -14,7 +14,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import lib, check, Scene, CbfNet, FilterParams, RolloutParams
+from ._lib import lib, check, Scene, CbfNet, FilterParams, RolloutParams, PeerOut
 
 ROBOT_ID = _lib.ROBOT_ID
 ROBOT_N = {0: 7, 1: 4}
@@ -280,6 +280,28 @@ def valid_control(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor
               "cbfrrt_safety_filter")
     del keep
     return safe, u
+
+
+def valid_control_scatter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor,
+                          K: Tensor, u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float,
+                          thr_hard: float, robot_id: int, hidden: int, layers: int, valid_ptrs, u_ptrs,
+                          row_offset: int) -> None:
+    """Fused sweep + all-gather (include/cbfrrt.h cbfrrt_safety_filter_scatter): the (valid, u) rows of this rank
+    are stored at global row ``row_offset + b`` of every peer buffer in ``valid_ptrs`` / ``u_ptrs`` (raw device
+    pointers of NVLink peer mappings, e.g. torch symmetric memory ``buffer_ptrs``).  No output tensors."""
+    n = ROBOT_N[robot_id]
+    q, qs = _rows(q, n)
+    B, dev = q.shape[0], q.device
+    net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers)
+    sc = _scene(boxes, spheres, floor, grid)
+    po = PeerOut()
+    po.n_peers, po.row_offset = len(valid_ptrs), int(row_offset)
+    for i, (v, u) in enumerate(zip(valid_ptrs, u_ptrs)):
+        po.valid[i], po.u[i] = int(v), int(u)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_safety_filter_scatter(robot_id, C.byref(sc), C.byref(net), _ptr(q), qs, B, C.byref(fp), thr_soft,
+                                               thr_hard, C.byref(po), _stream()), "cbfrrt_safety_filter_scatter")
+    del keep
 
 
 @torch.library.custom_op("cbfrrt::edge_validity", mutates_args=(), device_types="cuda")

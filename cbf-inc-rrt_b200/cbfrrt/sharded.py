@@ -84,3 +84,32 @@ class ShardedSweep:
         if self.cuda and self.world > 1:
             torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         return valid_all, u_all
+
+
+class FusedSweep:
+    """Sweep + all-gather in ONE kernel per rank: the epilogue of the fused safety-filter kernel stores every
+    (valid, u) row into all ranks' replicated buffers over NVLink peer mappings (torch symmetric memory), then the
+    ranks meet at a barrier.  Contiguous sharding: rank r owns global rows [r*B, (r+1)*B).
+
+    launch(q_local, valid_ptrs, u_ptrs, row_offset) runs cbfrrt::valid_control_scatter with the scene / network of
+    the caller.  ``valid`` [G] u8 and ``u`` [G, n] f32 are this rank's replicas (valid after __call__ returns and
+    the stream is synchronised)."""
+
+    def __init__(self, launch, n: int, rows_per_rank: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.launch, self.n, self.B = launch, n, rows_per_rank
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        G = self.world * rows_per_rank
+        self.valid = symm_mem.empty(G, dtype=torch.uint8, device=device)
+        self.u = symm_mem.empty(G, n, dtype=torch.float32, device=device)
+        self.h_valid = symm_mem.rendezvous(self.valid, self.group)
+        self.h_u = symm_mem.rendezvous(self.u, self.group)
+        self.valid_ptrs = [int(p) for p in self.h_valid.buffer_ptrs]
+        self.u_ptrs = [int(p) for p in self.h_u.buffer_ptrs]
+
+    def __call__(self, q_local: torch.Tensor):
+        assert q_local.shape[0] == self.B
+        self.launch(q_local, self.valid_ptrs, self.u_ptrs, self.rank * self.B)
+        self.h_u.barrier(channel=0)     # all ranks' kernels (and their peer stores) are complete past this point
+        return self.valid, self.u

@@ -120,9 +120,41 @@ int cbfrrt_safety_filter(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_
     if (B == 0) return CBFRRT_OK;
     CollideOutPtrs co{safe, unsafe, datax, nullptr, nullptr, nullptr};
     FilterOutPtrs fo{h, J, u, r};
+    PeerOut po{};
     cudaStream_t st = (cudaStream_t)stream;
-    return robot == CBFRRT_ROBOT_PANDA ? launch_safety_panda(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, st)
-                                       : launch_safety_magician(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, st);
+    return robot == CBFRRT_ROBOT_PANDA ? launch_safety_panda(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, po, st)
+                                       : launch_safety_magician(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, po, st);
+}
+
+int cbfrrt_safety_filter_scatter(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* net, const float* q,
+                                 int64_t q_stride, int64_t B, const cbfrrt_filter_params* fp, float thr_soft,
+                                 float thr_hard, const cbfrrt_peer_out* peers, void* stream) {
+    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
+    if (B < 0 || !q || !peers || peers->n_peers < 1 || peers->n_peers > CBFRRT_MAX_PEERS || peers->row_offset < 0)
+        return CBFRRT_ERR_BAD_SHAPE;
+    const int n = robot == CBFRRT_ROBOT_PANDA ? Panda::N : Magician::N;
+    if (q_stride < n) return CBFRRT_ERR_BAD_SHAPE;
+    PeerOut po{};
+    po.n = peers->n_peers;
+    po.row_offset = peers->row_offset;
+    for (int p = 0; p < po.n; ++p) {
+        if (!peers->valid[p] || !peers->u[p]) return CBFRRT_ERR_BAD_SHAPE;
+        if (!aligned16(peers->u[p])) return CBFRRT_ERR_ALIGNMENT;
+        po.valid[p] = peers->valid[p];
+        po.u[p] = peers->u[p];
+    }
+    SceneArgs sc;
+    NetArgs na;
+    int rc = check_scene(scene, sc);
+    if (rc) return rc;
+    rc = check_net(n, net, fp, B, na);
+    if (rc) return rc;
+    if (B == 0) return CBFRRT_OK;
+    CollideOutPtrs co{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    FilterOutPtrs fo{nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st = (cudaStream_t)stream;
+    return robot == CBFRRT_ROBOT_PANDA ? launch_safety_panda(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, po, st)
+                                       : launch_safety_magician(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, po, st);
 }
 
 int cbfrrt_edge_validity(int robot, const cbfrrt_scene* scene, const float* q_from, const float* q_to, int64_t E,

@@ -228,6 +228,30 @@ __device__ __forceinline__ void load_goal(const NetArgs& net, long long b, float
     for (int k = 0; k < N; ++k) g[k] = __ldg(src + k);
 }
 
+// fused all-gather epilogue: peer-mapped replicas of the [G] mask and [G, n] controls (include/cbfrrt.h)
+struct PeerOut {
+    int n;
+    long long row_offset;
+    uint8_t* valid[CBFRRT_MAX_PEERS];
+    float* u[CBFRRT_MAX_PEERS];
+};
+
+template <int N>
+__device__ __forceinline__ void write_peers(const PeerOut& po, long long b, bool safe, const float (&u)[N]) {
+    const long long g = po.row_offset + b;
+    for (int p = 0; p < po.n; ++p) {
+        po.valid[p][g] = safe;
+        float* dst = po.u[p] + g * N;
+        if constexpr (N % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < N; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(u[k], u[k + 1], u[k + 2], u[k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) dst[k] = u[k];
+        }
+    }
+}
+
 struct FilterOutPtrs {
     float* h;
     float* J;
@@ -296,7 +320,7 @@ __global__ void __launch_bounds__(256) qp_kernel(const float* __restrict__ a, co
 template <class RB, int H, int L, bool GRID>
 __global__ void __launch_bounds__(NT) safety_kernel(SceneArgs sc, NetArgs net, const float* __restrict__ q,
                                                     long long q_stride, long long B, float thr_soft, float thr_hard,
-                                                    CollideOutPtrs cout, FilterOutPtrs fout) {
+                                                    CollideOutPtrs cout, FilterOutPtrs fout, PeerOut po) {
     constexpr int N = RB::N;
     extern __shared__ __align__(16) float smem_raw[];
     using LY = NetLayout<N + 1, H, L>;
@@ -317,6 +341,7 @@ __global__ void __launch_bounds__(NT) safety_kernel(SceneArgs sc, NetArgs net, c
         cbf_filter_state<N, H, L, NT>(s.weights, s.params, scr, qq, cr.o, cr.dodq, g, net.u_ref != nullptr, net.lam,
                                       net.penalty, h, J, u, r);
         write_filter<N>(fout, b, h, J, u, r);
+        if (po.n) write_peers<N>(po, b, cr.self_ok && (cr.soft_min > thr_soft) && !(cr.hard_min <= thr_hard), u);
     }
 }
 
@@ -381,7 +406,7 @@ __global__ void __launch_bounds__(NTC, 1) filter_kernel_tc(NetArgs net, const fl
 template <class RB, int L, bool GRID>
 __global__ void __launch_bounds__(NTC, 1) safety_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q,
                                                            long long q_stride, long long B, float thr_soft, float thr_hard,
-                                                           CollideOutPtrs cout, FilterOutPtrs fout) {
+                                                           CollideOutPtrs cout, FilterOutPtrs fout, PeerOut po) {
     constexpr int N = RB::N;
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
@@ -409,7 +434,10 @@ __global__ void __launch_bounds__(NTC, 1) safety_kernel_tc(SceneArgs sc, NetArgs
             load_goal<N>(net, b, g);
         }
         filter_tile_tc<N, L>(c, s.params, qq, cr.o, cr.dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
-        if (active) write_filter<N>(fout, b, h, J, u, r);
+        if (active) {
+            write_filter<N>(fout, b, h, J, u, r);
+            if (po.n) write_peers<N>(po, b, cr.self_ok && (cr.soft_min > thr_soft) && !(cr.hard_min <= thr_hard), u);
+        }
     }
     tc::teardown<L>(c);
 }
@@ -858,13 +886,13 @@ static int launch_filter(const NetArgs& net, const float* datax, long long B, co
 
 template <class RB>
 static int launch_safety(const SceneArgs& sc, const NetArgs& net, const float* q, long long qs, long long B, float ts,
-                         float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, cudaStream_t st) {
+                         float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, const PeerOut& po, cudaStream_t st) {
     if (use_tc() && (B > SMALL_BATCH || force_tc())) {
         const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
         auto k = sc.grid ? safety_kernel_tc<RB, 2, true> : safety_kernel_tc<RB, 2, false>;
         const int grid = grid_for_tc(k, smem, B);
         if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NTC, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo);
+        k<<<grid, NTC, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo, po);
         return finish_launch();
     }
     using LY = NetLayout<RB::N + 1, 48, 2>;
@@ -872,7 +900,7 @@ static int launch_safety(const SceneArgs& sc, const NetArgs& net, const float* q
     auto k = sc.grid ? safety_kernel<RB, 48, 2, true> : safety_kernel<RB, 48, 2, false>;
     const int grid = grid_for(k, smem, (B + NT - 1) / NT);
     if (grid < 0) return CBFRRT_ERR_CUDA;
-    k<<<grid, NT, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo);
+    k<<<grid, NT, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo, po);
     return finish_launch();
 }
 
@@ -921,7 +949,7 @@ static int launch_rollout(const SceneArgs& sc, const NetArgs& net, const float* 
     int launch_collide_##R(const SceneArgs&, const float*, long long, long long, float, float, const CollideOutPtrs&,  \
                            cudaStream_t);                                                                              \
     int launch_safety_##R(const SceneArgs&, const NetArgs&, const float*, long long, long long, float, float,          \
-                          const CollideOutPtrs&, const FilterOutPtrs&, cudaStream_t);                                  \
+                          const CollideOutPtrs&, const FilterOutPtrs&, const PeerOut&, cudaStream_t);                  \
     int launch_edges_##R(const SceneArgs&, const float*, const float*, long long, int, float, float, uint8_t*, int*,   \
                          cudaStream_t);                                                                                \
     int launch_rollout_##R(const SceneArgs&, const NetArgs&, const float*, long long, const RolloutArgs&, float,       \

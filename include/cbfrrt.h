@@ -153,6 +153,26 @@ int cbfrrt_safety_filter(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_
                          float thr_hard, uint8_t *safe, uint8_t *unsafe, float *datax, float *h, float *J,
                          float *u, float *r, void *stream);
 
+/* ---- fused sweep + all-gather: q -> (valid, u) written straight into every peer GPU's replicated result --------
+ * The multi-GPU exchange named by BASELINE.json ("all-gather validity masks and filtered controls") fused into the
+ * kernel epilogue: each state's mask byte and control row are stored at global row (row_offset + b) of EVERY
+ * rank's buffers through NVLink peer mappings (torch symmetric memory / cudaIpc / cuMem), so the transfer overlaps
+ * the sweep tile by tile and no collective is launched.  The caller synchronises the ranks afterwards (a barrier),
+ * exactly as after an all-gather.  valid[p] / u[p] must be mapped in this process for p < n_peers (the rank's
+ * own buffer included). */
+#define CBFRRT_MAX_PEERS 8
+typedef struct {
+    int32_t n_peers;
+    int32_t _pad;
+    int64_t row_offset;                 /* global index of this rank's first row */
+    uint8_t *valid[CBFRRT_MAX_PEERS];   /* each: device u8 [G]     */
+    float *u[CBFRRT_MAX_PEERS];         /* each: device f32 [G, n] */
+} cbfrrt_peer_out;
+
+int cbfrrt_safety_filter_scatter(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_net *net, const float *q,
+                                 int64_t q_stride, int64_t B, const cbfrrt_filter_params *fp, float thr_soft,
+                                 float thr_hard, const cbfrrt_peer_out *peers, void *stream);
+
 /* ---- K10 edge validity -----------------------------------------------------------------------------------
  * Replaces edge_checking (motion_planning/baseline/tsa.py:272-286) for E edges with a fixed number n_interp
  * of interpolation points: valid <=> safe(q_to) and safe(q_from + k/n_interp (q_to - q_from)), k=0..n_interp-1.

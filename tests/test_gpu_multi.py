@@ -1,0 +1,70 @@
+"""GPU suite, >= 2 GPUs: the fused sweep + all-gather (kernel epilogue stores into every rank's replica over NVLink
+peer mappings) and the NCCL block-cyclic path both reproduce the single-GPU result bit for bit."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, ret):
+    for p in (ROOT, os.path.join(ROOT, "cbf-inc-rrt_b200")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from cbfrrt import ops, workloads as W
+    from cbfrrt.sharded import FusedSweep, ShardedSweep, local_global_rows
+    w = W.config(1, scale=1 / 16)
+    n, rid, B = w["n"], 1, 20000
+    G = world * B
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev)
+    b8, s4 = ops.pack_scene(w["boxes"][:, :3], w["boxes"][:, 3:], w["spheres"], device=dev)
+    gr = ops.build_grid(b8, s4)
+    net = ops.pack_weights(w["state_dict"], n, 48, 2, device=dev)
+    common = (t(w["goal"]), b8, s4, 1, gr, net, t(w["K"]), t(w["u_lo"]), t(w["u_hi"]), w["lam"], w["penalty"],
+              w["thr_soft"], w["thr_hard"], rid, 48, 2)
+    q_all = ops.sample_states(G, 5, 0, rid, device=dev)              # counter-based: identical on every rank
+    ref_v, ref_u = ops.valid_control(q_all, *common)
+    ok = []
+    # fused epilogue exchange, contiguous shards
+    sweep = FusedSweep(lambda qb, vp, up, off: ops.valid_control_scatter(qb, *common, vp, up, off), n, B, dev)
+    for _ in range(2):
+        v, u = sweep(q_all[rank * B:(rank + 1) * B])
+        torch.cuda.synchronize()
+        ok.append(bool(torch.equal(v, ref_v) and torch.equal(u, ref_u)))
+    # NCCL all-gather, block-cyclic
+    block, rounds = 2500, B // 2500
+    rows = local_global_rows(rank, world, block, rounds).to(dev)
+    v, u = ShardedSweep(lambda qb: ops.valid_control(qb, *common), n, block, device=dev)(q_all[rows])
+    torch.cuda.synchronize()
+    # blocks of 2500 rows take the FP32-FMA kernels (small-batch rule), the 40000-row reference the tcgen05 ones:
+    # masks are bit-exact, controls agree to the 1e-5 tolerance of the two MLP paths
+    err = ((u - ref_u).abs() / ref_u.abs().clamp(min=1.0)).max().item()
+    ok.append(bool(torch.equal(v, ref_v) and err < 1e-3 and ((u - ref_u).abs() / ref_u.abs().clamp(min=1.0) < 1e-5).float().mean().item() > 0.995))
+    out = [None] * world
+    dist.all_gather_object(out, ok)
+    if rank == 0:
+        ret.put(out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_fused_and_nccl_exchange_match_single_gpu():
+    world = min(torch.cuda.device_count(), 4)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, 29620 + os.getpid() % 300, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = ret.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(all(o) for o in out), out
