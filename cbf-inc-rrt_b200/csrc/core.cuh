@@ -219,12 +219,15 @@ __device__ __forceinline__ void normal_sphere(float cx, float cy, float cz, floa
 }
 
 // one box / one sphere obstacle against one link sphere: running (min dsq, min max3) resp. min (dist - rs)
+// D accumulates 4 * dsq: max(a, 0) is taken as (a + |a|) = 2 max(a, 0) -- an FADD on the full-rate FMA pipe instead
+// of an FMNMX on the half-rate ALU pipe (the sweep is ALU-pipe bound, profiles/r1b_*).  Scaling by 2 / 4 is exact in
+// binary floating point, and sqrt(4 x) = 2 sqrt(x) exactly, so 0.5 * sqrt(D) below is bit-identical to sqrt(dsq).
 __device__ __forceinline__ void acc_box(float cx, float cy, float cz, float4 b0, float4 b1, float& D, float& M) {
     const float ax = __fsub_rn(fabsf(__fsub_rn(cx, b0.x)), b0.w);
     const float ay = __fsub_rn(fabsf(__fsub_rn(cy, b0.y)), b1.x);
     const float az = __fsub_rn(fabsf(__fsub_rn(cz, b0.z)), b1.y);
-    const float qx = fmaxf(ax, 0.f), qy = fmaxf(ay, 0.f), qz = fmaxf(az, 0.f);
-    D = fminf(D, fmaf(qz, qz, fmaf(qy, qy, __fmul_rn(qx, qx))));
+    const float tx = __fadd_rn(ax, fabsf(ax)), ty = __fadd_rn(ay, fabsf(ay)), tz = __fadd_rn(az, fabsf(az));
+    D = fminf(D, fmaf(tz, tz, fmaf(ty, ty, __fmul_rn(tx, tx))));
     M = fminf(M, fmaxf(ax, fmaxf(ay, az)));
 }
 __device__ __forceinline__ void acc_sphere(float cx, float cy, float cz, float4 s, float& E) {
@@ -297,7 +300,7 @@ __device__ __forceinline__ void sweep_scene(const SceneS& sc, const float (&C)[K
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         // boxes: e = sqrt(min dsq) + min(min max3, 0); with no boxes D = M = +inf -> e = +inf
-        const float e_box = __fadd_rn(__fsqrt_rn(D[k]), fminf(M[k], 0.f));
+        const float e_box = __fadd_rn(__fmul_rn(__fsqrt_rn(D[k]), 0.5f), fminf(M[k], 0.f));   // D holds 4 * dsq
         out[k] = __fsub_rn(fminf(e_box, E[k]), rad[k]);
     }
 }

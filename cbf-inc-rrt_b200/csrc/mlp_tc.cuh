@@ -66,18 +66,27 @@ __host__ __device__ constexpr uint32_t instr_desc(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(M_TILE >> 4) << 24);
 }
 // D[tmem] (+)= A[tmem] . B[smem]^T
+// Called by a WHOLE warp with warp-uniform operands; one elected lane issues.  Keeping the operands warp-uniform lets
+// ptxas hold the descriptors in uniform registers (a divergent `if (tid == 0)` costs an ELECT/R2UR loop per MMA).
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(smem_addr(bar))
+        : "memory");
 }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -126,11 +135,11 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"   // %3: suspend-time hint (ns): sleep, don't spin
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(smem_addr(bar)), "r"(parity)
+            : "r"(smem_addr(bar)), "r"(parity), "r"(20000u)
             : "memory");
     } while (!done);
 }
@@ -202,8 +211,10 @@ __device__ __forceinline__ void setup(Ctx<L>& c, float* region, const float* __r
             const int n = i / H, k = i % H;
             const float w = __ldg(W + i);
             const float hi = rna_tf32(w), lo = w - hi;
-            c.w_f(l, 0)[tile_idx(n, k, H)] = hi;
-            c.w_f(l, 1)[tile_idx(n, k, H)] = lo;
+            // forward tiles hold W / 2: the epilogue hands 2 * relu(s) = s + |s| to the next layer (one FADD on the
+            // FMA pipe instead of an FMNMX on the half-rate ALU pipe); halving is exact, also for the hi / lo split
+            c.w_f(l, 0)[tile_idx(n, k, H)] = 0.5f * hi;
+            c.w_f(l, 1)[tile_idx(n, k, H)] = 0.5f * lo;
             c.w_t(l, 0)[tile_idx(k, n, H)] = hi;             // (W^T)[k][n] = W[n][k]
             c.w_t(l, 1)[tile_idx(k, n, H)] = lo;
         }
@@ -236,23 +247,26 @@ __device__ __forceinline__ void teardown(Ctx<L>& c) {
 }
 
 // write this thread's K values as the hi / lo rows of the A operand in tensor memory
+// The "hi" operand is the raw fp32 value: the tensor core reads only the TF32 bits, i.e. hi = trunc_tf32(v), for free.
+// lo = v - trunc_tf32(v) (exact in fp32; one LOP3 + one FADD).  With the weights split by round-to-nearest at staging
+// time the 3-term product is accurate to ~2^-20 relative per term -- measured better than an fp32 FMA chain.
 template <int K, int L>
 __device__ __forceinline__ void store_a(const Ctx<L>& c, const float* v) {
     static_assert(K == 8 || K % 16 == 0, "");
     const uint32_t row = c.tmem + c.lane;
     if constexpr (K == 8) {
-        float hi[8], lo[8];
+        float lo[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { hi[k] = rna_tf32(v[k]); lo[k] = v[k] - hi[k]; }
-        tmem_st8(row + COL_AHI, hi);
+        for (int k = 0; k < 8; ++k) lo[k] = v[k] - __uint_as_float(__float_as_uint(v[k]) & 0xffffe000u);
+        tmem_st8(row + COL_AHI, v);
         tmem_st8(row + COL_ALO, lo);
     } else {
 #pragma unroll
-        for (int j = 0; j < K / 16; ++j) {   // 16 columns at a time keeps the hi / lo temporaries at 32 registers
-            float hi[16], lo[16];
+        for (int j = 0; j < K / 16; ++j) {
+            float lo[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { hi[k] = rna_tf32(v[16 * j + k]); lo[k] = v[16 * j + k] - hi[k]; }
-            tmem_st16(row + COL_AHI + 16 * j, hi);
+            for (int k = 0; k < 16; ++k) lo[k] = v[16 * j + k] - __uint_as_float(__float_as_uint(v[16 * j + k]) & 0xffffe000u);
+            tmem_st16(row + COL_AHI + 16 * j, v + 16 * j);
             tmem_st16(row + COL_ALO + 16 * j, lo);
         }
     }
@@ -265,7 +279,7 @@ template <int K, int N, int L>
 __device__ __forceinline__ void gemm(Ctx<L>& c, const float* w_hi, const float* w_lo) {
     fence_before_sync();
     group_sync(c.g);
-    if (c.t == 0) {
+    if (c.t < 32) {   // warp 0 of the group, warp-uniform: one elected lane issues (see mma_tf32_ts)
         fence_after_sync();
         constexpr uint32_t idesc = instr_desc(N);
         constexpr uint32_t B_LBO = N * 16, B_SBO = 128, B_STEP = 2 * N * 16;
@@ -294,19 +308,26 @@ __device__ __forceinline__ void load_d(const Ctx<L>& c, float* v) {
     tmem_ld_wait();
 }
 
+// epilogue of a forward layer: s = v + bias;  v <- 2 * relu(s) = s + |s|;  returns the ReLU mask (bit k = s_k > 0).
+// The mask bit is the sign of (0 - s): exactly (s > 0), also for s = +-0; one FADD + one funnel shift per element.
 template <int L>
-__device__ __forceinline__ uint64_t bias_relu(const Ctx<L>& c, int layer, float (&v)[H]) {
-    uint64_t m = 0;
+__device__ __forceinline__ uint64_t bias_relu2(const Ctx<L>& c, int layer, float (&v)[H]) {
+    static_assert(H == 48, "three 16-bit mask chains");
+    uint32_t m[3] = {0, 0, 0};   // independent funnel-shift chains (16 elements each) instead of one 48-long one
     const float4* b4 = reinterpret_cast<const float4*>(c.bias(layer));
 #pragma unroll
-    for (int k4 = 0; k4 < H / 4; ++k4) {
-        const float4 b = b4[k4];
-        const float s0 = v[4 * k4] + b.x, s1 = v[4 * k4 + 1] + b.y, s2 = v[4 * k4 + 2] + b.z, s3 = v[4 * k4 + 3] + b.w;
-        m |= ((uint64_t)(s0 > 0.f) << (4 * k4)) | ((uint64_t)(s1 > 0.f) << (4 * k4 + 1)) |
-             ((uint64_t)(s2 > 0.f) << (4 * k4 + 2)) | ((uint64_t)(s3 > 0.f) << (4 * k4 + 3));
-        v[4 * k4] = fmaxf(s0, 0.f); v[4 * k4 + 1] = fmaxf(s1, 0.f); v[4 * k4 + 2] = fmaxf(s2, 0.f); v[4 * k4 + 3] = fmaxf(s3, 0.f);
+    for (int i = 3; i >= 0; --i) {             // descending inside a chain: bit k lands at position k % 16
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const int k4 = 4 * w + i;
+            const float4 b = b4[k4];
+            const float s3 = v[4 * k4 + 3] + b.w, s2 = v[4 * k4 + 2] + b.z, s1 = v[4 * k4 + 1] + b.y, s0 = v[4 * k4] + b.x;
+            m[w] = __funnelshift_l(__float_as_uint(0.f - s3), m[w], 1); m[w] = __funnelshift_l(__float_as_uint(0.f - s2), m[w], 1);
+            m[w] = __funnelshift_l(__float_as_uint(0.f - s1), m[w], 1); m[w] = __funnelshift_l(__float_as_uint(0.f - s0), m[w], 1);
+            v[4 * k4] = s0 + fabsf(s0); v[4 * k4 + 1] = s1 + fabsf(s1); v[4 * k4 + 2] = s2 + fabsf(s2); v[4 * k4 + 3] = s3 + fabsf(s3);
+        }
     }
-    return m;
+    return ((uint64_t)m[2] << 32) | ((uint64_t)(m[1] << 16) | m[0]);
 }
 
 // value h and Jacobian dh/dx for this thread's x = [q, o]; every thread of the tile group must call it (idle
@@ -324,7 +345,7 @@ __device__ __forceinline__ void mlp_h_jac(Ctx<L>& c, const float (&x)[N_IN], flo
         store_a<8>(c, xin);
         gemm<8, H>(c, c.win_f(0), c.win_f(1));
         load_d<H>(c, v);
-        mask[0] = bias_relu(c, 0, v);
+        mask[0] = bias_relu2(c, 0, v);
     }
     // ---- hidden layers
 #pragma unroll
@@ -332,12 +353,12 @@ __device__ __forceinline__ void mlp_h_jac(Ctx<L>& c, const float (&x)[N_IN], flo
         store_a<H>(c, v);
         gemm<H, H>(c, c.w_f(l, 0), c.w_f(l, 1));
         load_d<H>(c, v);
-        mask[l + 1] = bias_relu(c, l + 1, v);
+        mask[l + 1] = bias_relu2(c, l + 1, v);
     }
     // ---- output layer (N = 1) and seed of the backward pass on the CUDA cores
     {
         const float4* w4 = reinterpret_cast<const float4*>(c.bias(L + 1));
-        float s0 = c.bias(L + 2)[0], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         const uint64_t m = mask[L];
 #pragma unroll
         for (int k4 = 0; k4 < H / 4; ++k4) {
@@ -349,7 +370,7 @@ __device__ __forceinline__ void mlp_h_jac(Ctx<L>& c, const float (&x)[N_IN], flo
             v[4 * k4 + 2] = ((m >> (4 * k4 + 2)) & 1) ? w.z : 0.f;
             v[4 * k4 + 3] = ((m >> (4 * k4 + 3)) & 1) ? w.w : 0.f;
         }
-        h_out = (s0 + s1) + (s2 + s3);
+        h_out = fmaf(0.5f, (s0 + s1) + (s2 + s3), c.bias(L + 2)[0]);   // v held 2 * relu(s)
     }
     // ---- backward through the hidden layers: g_prev = relu'_prev * (W^T g)
 #pragma unroll
