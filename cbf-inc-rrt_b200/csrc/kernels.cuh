@@ -803,7 +803,8 @@ inline int check_scene(const cbfrrt_scene* sc, SceneArgs& a) {
     if (!aligned16(sc->boxes) || !aligned16(sc->spheres) || !aligned16(sc->grid)) return CBFRRT_ERR_ALIGNMENT;
     // the grid's look-ups and gathers cost more than they save on small scenes (measured: slower at 16 obstacles,
     // 1.7x faster at 64, 4.3x at 256): scenes below GRID_MIN_OBSTACLES are swept brute force even if a grid is given
-    const bool use_grid = sc->grid && sc->n_boxes + sc->n_spheres >= GRID_MIN_OBSTACLES;
+    static const int grid_min = [] { const char* e = getenv("CBFRRT_GRID_MIN"); return e ? atoi(e) : GRID_MIN_OBSTACLES; }();
+    const bool use_grid = sc->grid && sc->n_boxes + sc->n_spheres >= grid_min;
     a = SceneArgs{sc->boxes, sc->spheres, sc->n_boxes, sc->n_spheres, sc->floor ? 1 : 0,
                   use_grid ? static_cast<const uint16_t*>(sc->grid) : nullptr};
     return CBFRRT_OK;

@@ -172,41 +172,94 @@ __device__ __forceinline__ float qp_g(const float (&a)[N], const float (&uref)[N
     return g;
 }
 
-// Exact KKT solution of the single-constraint CBF-QP.  u(mu) = clip(u_ref - mu a/2, lo, hi), 0 <= mu <= p;
-// g(mu) = c + a.u(mu) is non-increasing and piecewise linear with at most N breakpoints.  mu* = 0 if g(0) <= 0,
-// else the root of g in (0, p], found by evaluating g at every breakpoint (no sort: N^2 is 49) and
-// interpolating inside the bracketing segment (exact: g is linear there); if g(p) > 0 the constraint is relaxed
-// with mu = p and r = g(p).
+// Root of the dual constraint of ONE relaxed half-space constraint  c + a.u - r <= 0  (penalty p on r) for the
+// box-constrained projection  u(mu) = clip(t - mu a / 2, lo, hi):  g(mu) = c + a.u(mu) is non-increasing and
+// piecewise linear with at most 2N breakpoints (a coordinate can leave one bound and reach the other when the
+// target t lies outside the box).  Returns mu* = 0 if g(0) <= 0, p if g(p) > 0 (constraint relaxed), else the root,
+// found by evaluating g at every breakpoint (no sort: 2N * N is small) and interpolating inside the bracketing
+// segment (exact: g is linear there).
+template <int N>
+__device__ __forceinline__ float qp_mu(const float (&a)[N], const float (&t)[N], const float* __restrict__ lo,
+                                       const float* __restrict__ hi, float c, float p) {
+    const float g0 = qp_g<N>(a, t, lo, hi, c, 0.f);
+    if (!(g0 > 0.f)) return 0.f;
+    float mu_lo = 0.f, g_lo = g0;
+    float mu_hi = p, g_hi = qp_g<N>(a, t, lo, hi, c, p);
+    if (g_hi > 0.f) return p;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (a[i] != 0.f) {
+            const float inv = 2.f / a[i];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const float m = (t[i] - (s ? hi[i] : lo[i])) * inv;
+                if (m > mu_lo && m < mu_hi) {
+                    const float gm = qp_g<N>(a, t, lo, hi, c, m);
+                    if (gm > 0.f) { mu_lo = m; g_lo = gm; }
+                    else          { mu_hi = m; g_hi = gm; }
+                }
+            }
+        }
+    }
+    return (g_lo > g_hi) ? fmaf(mu_hi - mu_lo, g_lo / (g_lo - g_hi), mu_lo) : mu_hi;
+}
+
+// Exact KKT solution of the single-constraint CBF-QP
+//   min ||u-u_ref||^2 + p r   s.t.  c + a.u - r <= 0, r >= 0, lo <= u <= hi      (clf_controller.py:82-139)
 template <int N>
 __device__ __forceinline__ void qp_solve(const float (&a)[N], const float (&uref)[N], const float* __restrict__ lo,
                                          const float* __restrict__ hi, float c, float p, float (&u)[N], float& r) {
-    r = 0.f;
-    const float g0 = qp_g<N>(a, uref, lo, hi, c, 0.f);
-    float mu = 0.f;
-    if (g0 > 0.f) {
-        float mu_lo = 0.f, g_lo = g0;
-        float mu_hi = p, g_hi = qp_g<N>(a, uref, lo, hi, c, p);
-        if (g_hi > 0.f) {
-            mu = p;
-            r = g_hi;
-        } else {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                float m = -1.f;
-                if (a[i] > 0.f) m = 2.f * (uref[i] - lo[i]) / a[i];
-                else if (a[i] < 0.f) m = 2.f * (uref[i] - hi[i]) / a[i];
-                if (m > 0.f && m < p) {
-                    const float gm = qp_g<N>(a, uref, lo, hi, c, m);
-                    if (gm > 0.f) { if (m > mu_lo) { mu_lo = m; g_lo = gm; } }
-                    else          { if (m < mu_hi) { mu_hi = m; g_hi = gm; } }
-                }
-            }
-            mu = (g_lo > g_hi) ? fmaf(mu_hi - mu_lo, g_lo / (g_lo - g_hi), mu_lo) : mu_hi;
-        }
-    }
+    const float mu = qp_mu<N>(a, uref, lo, hi, c, p);
     const float hm = 0.5f * mu;
+    float g = c;
 #pragma unroll
-    for (int i = 0; i < N; ++i) u[i] = fminf(fmaxf(fmaf(-hm, a[i], uref[i]), lo[i]), hi[i]);
+    for (int i = 0; i < N; ++i) {
+        u[i] = fminf(fmaxf(fmaf(-hm, a[i], uref[i]), lo[i]), hi[i]);
+        g = fmaf(a[i], u[i], g);
+    }
+    r = (mu >= p) ? fmaxf(g, 0.f) : 0.f;
+}
+
+// S relaxed constraints (multi-scenario CLF/CBF-QP, clf_controller.py:86-139 with len(scenarios) > 1):
+//   min ||u-u_ref||^2 + p sum_i r_i   s.t.  c_i + a_i.u - r_i <= 0, r_i >= 0, lo <= u <= hi.
+// Batched dual active-set solver: the dual is concave in mu in [0,p]^S and u(mu) = clip(u_ref - sum_i mu_i a_i / 2);
+// cyclic exact coordinate maximisation -- every coordinate step is the exact active-set root find qp_mu above on the
+// target shifted by the other multipliers -- until no multiplier moves by more than tol.  S = 1 is one step.
+template <int N, int S>
+__device__ __forceinline__ int qp_solve_multi(const float (&a)[S][N], const float (&uref)[N], const float* __restrict__ lo,
+                                              const float* __restrict__ hi, const float (&c)[S], float p, int max_sweeps,
+                                              float tol, float (&u)[N], float (&r)[S]) {
+    float mu[S], t[N];
+#pragma unroll
+    for (int i = 0; i < S; ++i) mu[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < N; ++k) t[k] = uref[k];
+    int sweeps = 0;
+    for (; sweeps < max_sweeps; ++sweeps) {
+        float moved = 0.f;
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            float ti[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) ti[k] = fmaf(0.5f * mu[i], a[i][k], t[k]);   // remove constraint i's shift
+            const float m = qp_mu<N>(a[i], ti, lo, hi, c[i], p);
+            moved = fmaxf(moved, fabsf(m - mu[i]));
+            mu[i] = m;
+#pragma unroll
+            for (int k = 0; k < N; ++k) t[k] = fmaf(-0.5f * m, a[i][k], ti[k]);
+        }
+        if (moved <= tol) { ++sweeps; break; }
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) u[k] = fminf(fmaxf(t[k], lo[k]), hi[k]);
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        float g = c[i];
+#pragma unroll
+        for (int k = 0; k < N; ++k) g = fmaf(a[i][k], u[k], g);
+        r[i] = fmaxf(g, 0.f);
+    }
+    return sweeps;
 }
 
 // everything after the MLP: J = Jh_q + Jh_o do/dq, nominal control, QP

@@ -114,6 +114,15 @@ def qp(a, c, u_ref, u_lo, u_hi, penalty):
     return u, r
 
 
+def qp_multi(a, c, u_ref, u_lo, u_hi, penalty):
+    a, c, u_ref, u_lo, u_hi = _f(a), _f(c), _f(u_ref), _f(u_lo), _f(u_hi)
+    B, S, n = a.shape
+    u, r = np.empty((B, n), np.float32), np.empty((B, S), np.float32)
+    rc = lib().oracle_qp_multi(n, S, _p(a), _p(c), _p(u_ref), C.c_long(B), _p(u_lo), _p(u_hi), C.c_float(penalty), _p(u), _p(r))
+    assert rc == 0
+    return u, r
+
+
 def u_nominal(q, goal, K, u_lo, u_hi):
     """clamp(-K (q - goal), lo, hi) in float32 with the oracle's operation order (filter_state)."""
     q, goal, K = _f(q), _f(goal).reshape(-1, q.shape[1]), _f(K)

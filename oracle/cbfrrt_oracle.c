@@ -359,22 +359,18 @@ static double qp_g(int n, const double *a, const double *uref, const double *lo,
     return g;
 }
 
-static void qp_exact(int n, const double *a, const double *uref_in, const double *lo, const double *hi, double c,
-                     double p, double *u, double *r_out) {
-    double uref[MAXN];
-    for (int i = 0; i < n; ++i) uref[i] = uref_in[i];
-    double g0 = qp_g(n, a, uref, lo, hi, c, 0.0, u);
-    *r_out = 0.0;
-    if (g0 <= 0.0) return;
-    /* breakpoints of u(mu) */
-    double bp[MAXN + 2];
+/* multiplier of one relaxed constraint for the projection target `t` (may lie outside the box): 2n breakpoints */
+static double qp_mu_exact(int n, const double *a, const double *t, const double *lo, const double *hi, double c, double p) {
+    double g0 = qp_g(n, a, t, lo, hi, c, 0.0, 0);
+    if (!(g0 > 0.0)) return 0.0;
+    double bp[2 * MAXN + 2];
     int nb = 0;
     bp[nb++] = 0.0;
     for (int i = 0; i < n; ++i) {
-        double m = -1.0;
-        if (a[i] > 0.0) m = 2.0 * (uref[i] - lo[i]) / a[i];
-        else if (a[i] < 0.0) m = 2.0 * (uref[i] - hi[i]) / a[i];
-        if (m > 0.0 && m < p) bp[nb++] = m;
+        if (a[i] == 0.0) continue;
+        double m1 = 2.0 * (t[i] - lo[i]) / a[i], m2 = 2.0 * (t[i] - hi[i]) / a[i];
+        if (m1 > 0.0 && m1 < p) bp[nb++] = m1;
+        if (m2 > 0.0 && m2 < p) bp[nb++] = m2;
     }
     bp[nb++] = p;
     for (int i = 1; i < nb; ++i) { /* insertion sort */
@@ -385,17 +381,46 @@ static void qp_exact(int n, const double *a, const double *uref_in, const double
     }
     double mu_lo = 0.0, g_lo = g0;
     for (int k = 1; k < nb; ++k) {
-        double g_hi = qp_g(n, a, uref, lo, hi, c, bp[k], 0);
-        if (g_hi <= 0.0) {
-            double mu = bp[k];
-            if (g_lo > g_hi) mu = mu_lo + (bp[k] - mu_lo) * (g_lo / (g_lo - g_hi));
-            qp_g(n, a, uref, lo, hi, c, mu, u);
-            return;
-        }
+        double g_hi = qp_g(n, a, t, lo, hi, c, bp[k], 0);
+        if (g_hi <= 0.0) return (g_lo > g_hi) ? mu_lo + (bp[k] - mu_lo) * (g_lo / (g_lo - g_hi)) : bp[k];
         mu_lo = bp[k];
         g_lo = g_hi;
     }
-    *r_out = qp_g(n, a, uref, lo, hi, c, p, u); /* constraint relaxed: mu = p */
+    return p; /* g(p) > 0: constraint relaxed */
+}
+
+static void qp_exact(int n, const double *a, const double *uref, const double *lo, const double *hi, double c,
+                     double p, double *u, double *r_out) {
+    double mu = qp_mu_exact(n, a, uref, lo, hi, c, p);
+    double g = qp_g(n, a, uref, lo, hi, c, mu, u);
+    *r_out = (mu >= p && g > 0.0) ? g : 0.0;
+}
+
+/* S relaxed constraints: cyclic exact dual coordinate maximisation to machine precision (float64) */
+#define MAXS 8
+static int qp_multi_exact(int n, int S, const double *a /* [S][n] */, const double *uref, const double *lo,
+                          const double *hi, const double *c, double p, double *u, double *r) {
+    double mu[MAXS] = {0}, t[MAXN], ti[MAXN];
+    for (int k = 0; k < n; ++k) t[k] = uref[k];
+    int sweeps = 0;
+    for (; sweeps < 100000; ++sweeps) {
+        double moved = 0.0;
+        for (int i = 0; i < S; ++i) {
+            for (int k = 0; k < n; ++k) ti[k] = t[k] + 0.5 * mu[i] * a[i * n + k];
+            double m = qp_mu_exact(n, a + i * n, ti, lo, hi, c[i], p);
+            if (fabs(m - mu[i]) > moved) moved = fabs(m - mu[i]);
+            mu[i] = m;
+            for (int k = 0; k < n; ++k) t[k] = ti[k] - 0.5 * m * a[i * n + k];
+        }
+        if (moved <= 1e-13 * (1.0 + p)) break;
+    }
+    for (int k = 0; k < n; ++k) u[k] = t[k] < lo[k] ? lo[k] : (t[k] > hi[k] ? hi[k] : t[k]);
+    for (int i = 0; i < S; ++i) {
+        double g = c[i];
+        for (int k = 0; k < n; ++k) g += a[i * n + k] * u[k];
+        r[i] = g > 0.0 ? g : 0.0;
+    }
+    return sweeps;
 }
 
 /* ------------------------------------------------------------------ exported batch API (ctypes) */
@@ -565,6 +590,22 @@ API int oracle_qp(int n, const float *a, const float *c, const float *u_ref, lon
         qp_exact(n, ad, ur, lo, hi, (double)c[b], penalty < 1e6f ? (double)penalty : 1e6, ud, &rd);
         for (int k = 0; k < n; ++k) u[b * n + k] = (float)ud[k];
         r[b] = (float)rd;
+    }
+    return 0;
+}
+
+/* multi-scenario QP on caller-supplied data: a [B,S,n], c [B,S], u_ref [B,n] -> u [B,n], r [B,S] */
+API int oracle_qp_multi(int n, int S, const float *a, const float *c, const float *u_ref, long B, const float *u_lo,
+                        const float *u_hi, float penalty, float *u, float *r) {
+    if (n > MAXN || S > MAXS) return -1;
+    for (long b = 0; b < B; ++b) {
+        double ad[MAXS * MAXN], cd[MAXS], ur[MAXN], lo[MAXN], hi[MAXN], ud[MAXN], rd[MAXS];
+        for (int k = 0; k < S * n; ++k) ad[k] = a[b * S * n + k];
+        for (int i = 0; i < S; ++i) cd[i] = c[b * S + i];
+        for (int k = 0; k < n; ++k) { ur[k] = u_ref[b * n + k]; lo[k] = u_lo[k]; hi[k] = u_hi[k]; }
+        qp_multi_exact(n, S, ad, ur, lo, hi, cd, penalty < 1e6f ? (double)penalty : 1e6, ud, rd);
+        for (int k = 0; k < n; ++k) u[b * n + k] = (float)ud[k];
+        for (int i = 0; i < S; ++i) r[b * S + i] = (float)rd[i];
     }
     return 0;
 }
