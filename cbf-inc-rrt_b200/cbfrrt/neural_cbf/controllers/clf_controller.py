@@ -2,8 +2,8 @@
 
 The reference builds a CvxpyLayer (:82-139) and solves one SCS conic program per row (:354-404).  Here the same
 QP     min ||u - u_ref||^2 + p * sum r_i   s.t.  Lf_i + Lg_i u + lambda V - r_i <= 0,  r_i >= 0,  lo <= u <= hi
-is solved exactly (KKT closed form) for the whole batch by cbfrrt::qp.  Only n_scenarios == 1 is on the hot
-path of every shipped entry point; more scenarios raise NotImplementedError.
+is solved exactly for the whole batch: cbfrrt::qp (KKT closed form) for n_scenarios == 1 -- the hot path of every
+shipped entry point -- and cbfrrt::qp_multi (dual active-set coordinate solver, up to 4 scenarios) otherwise.
 """
 import time
 from typing import Optional, Tuple
@@ -28,6 +28,9 @@ class CLFController(Controller):
             self.safe_level = kwargs["safe_level"]
             self.unsafe_level = kwargs["unsafe_level"]
         self.clf_relaxation_penalty = clf_relaxation_penalty
+        # multi-scenario solver budget (cbfrrt_qp_multi): coordinate sweeps and multiplier tolerance
+        self.qp_max_sweeps = int(kwargs.get("qp_max_sweeps", 200))
+        self.qp_tol = float(kwargs.get("qp_tol", 1e-6))
 
     @property
     def device(self):
@@ -72,10 +75,14 @@ class CLFController(Controller):
 
     def _solve_CLF_QP_exact(self, x, u_ref, V, Lf_V, Lg_V, relaxation_penalty: float):
         """Batched exact solve on the GPU (replaces _solve_CLF_QP_cvxpylayers, clf_controller.py:354-404)."""
-        if self.n_scenarios != 1:
-            raise NotImplementedError("multi-scenario CLF-QP (n_scenarios > 1) is a 'next' row (SURVEY.md 8f)")
         dev = self.device
         upper, lower = self.dynamics_model.control_limits
+        if self.n_scenarios != 1:
+            a = Lg_V.to(dev, torch.float32)
+            c = (Lf_V[:, :, 0] + self.clf_lambda * V.reshape(-1, 1)).to(dev, torch.float32)
+            u, r, _ = ops.qp_multi(a, c, u_ref.to(dev, torch.float32), lower.to(dev, torch.float32),
+                                   upper.to(dev, torch.float32), float(relaxation_penalty), self.qp_max_sweeps, self.qp_tol)
+            return u.to(x.device).type_as(x), r.to(x.device).type_as(x)
         a = Lg_V[:, 0, :].to(dev, torch.float32)
         c = (Lf_V[:, 0, 0] + self.clf_lambda * V.reshape(-1)).to(dev, torch.float32)
         u, r = ops.qp(a, c, u_ref.to(dev, torch.float32), lower.to(dev, torch.float32), upper.to(dev, torch.float32),

@@ -236,6 +236,25 @@ def qp(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty:
     return u, r
 
 
+@torch.library.custom_op("cbfrrt::qp_multi", mutates_args=(), device_types="cuda")
+def qp_multi(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty: float, max_sweeps: int,
+             tol: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """a f32[B,S,n], c f32[B,S], u_ref f32[B,n] -> u f32[B,n], r f32[B,S], sweeps i32[B]   (S <= 4 scenarios)"""
+    a, c, u_ref, u_lo, u_hi = _f32c(a), _f32c(c), _f32c(u_ref), _f32c(u_lo), _f32c(u_hi)
+    if a.dim() != 3:
+        raise ValueError("qp_multi: a must be [B, S, n]")
+    B, S, n = a.shape
+    if u_ref.shape != (B, n) or c.shape != (B, S) or u_lo.numel() != n or u_hi.numel() != n:
+        raise ValueError("qp_multi: inconsistent shapes")
+    u = torch.empty((B, n), dtype=torch.float32, device=a.device)
+    r = torch.empty((B, S), dtype=torch.float32, device=a.device)
+    sweeps = torch.empty(B, dtype=torch.int32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.cbfrrt_qp_multi(n, S, _ptr(a), _ptr(c), _ptr(u_ref), B, _ptr(u_lo), _ptr(u_hi), penalty, max_sweeps,
+                                  tol, _ptr(u), _ptr(r), _ptr(sweeps), _stream()), "cbfrrt_qp_multi")
+    return u, r, sweeps
+
+
 @torch.library.custom_op("cbfrrt::safety_filter", mutates_args=(), device_types="cuda")
 def safety_filter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor, K: Tensor,
                   u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float,

@@ -224,11 +224,12 @@ __device__ __forceinline__ void qp_solve(const float (&a)[N], const float (&uref
 //   min ||u-u_ref||^2 + p sum_i r_i   s.t.  c_i + a_i.u - r_i <= 0, r_i >= 0, lo <= u <= hi.
 // Batched dual active-set solver: the dual is concave in mu in [0,p]^S and u(mu) = clip(u_ref - sum_i mu_i a_i / 2);
 // cyclic exact coordinate maximisation -- every coordinate step is the exact active-set root find qp_mu above on the
-// target shifted by the other multipliers -- until no multiplier moves by more than tol.  S = 1 is one step.
+// target shifted by the other multipliers -- until no multiplier moves by more than tol.  One constraint is one
+// step.  S is the compile-time capacity, n_con <= S the number of constraints present (the rest must be zero-filled).
 template <int N, int S>
 __device__ __forceinline__ int qp_solve_multi(const float (&a)[S][N], const float (&uref)[N], const float* __restrict__ lo,
-                                              const float* __restrict__ hi, const float (&c)[S], float p, int max_sweeps,
-                                              float tol, float (&u)[N], float (&r)[S]) {
+                                              const float* __restrict__ hi, const float (&c)[S], int n_con, float p,
+                                              int max_sweeps, float tol, float (&u)[N], float (&r)[S]) {
     float mu[S], t[N];
 #pragma unroll
     for (int i = 0; i < S; ++i) mu[i] = 0.f;
@@ -239,6 +240,7 @@ __device__ __forceinline__ int qp_solve_multi(const float (&a)[S][N], const floa
         float moved = 0.f;
 #pragma unroll
         for (int i = 0; i < S; ++i) {
+            if (i >= n_con) break;
             float ti[N];
 #pragma unroll
             for (int k = 0; k < N; ++k) ti[k] = fmaf(0.5f * mu[i], a[i][k], t[k]);   // remove constraint i's shift
@@ -257,7 +259,7 @@ __device__ __forceinline__ int qp_solve_multi(const float (&a)[S][N], const floa
         float g = c[i];
 #pragma unroll
         for (int k = 0; k < N; ++k) g = fmaf(a[i][k], u[k], g);
-        r[i] = fmaxf(g, 0.f);
+        r[i] = (mu[i] >= p) ? fmaxf(g, 0.f) : 0.f;      // r_i > 0 only when the multiplier saturates at p
     }
     return sweeps;
 }

@@ -418,7 +418,7 @@ static int qp_multi_exact(int n, int S, const double *a /* [S][n] */, const doub
     for (int i = 0; i < S; ++i) {
         double g = c[i];
         for (int k = 0; k < n; ++k) g += a[i * n + k] * u[k];
-        r[i] = g > 0.0 ? g : 0.0;
+        r[i] = (mu[i] >= p && g > 0.0) ? g : 0.0; /* r_i > 0 only when the multiplier saturates at p */
     }
     return sweeps;
 }

@@ -75,3 +75,29 @@ def assert_controls_match(coracle, u, r, h, J, o, uref, u_lo, u_hi, lam, penalty
     e = np.max(np.abs(u.astype(np.float64) - o["u"]) / np.maximum(np.abs(o["u"]), 1.0), axis=1)
     assert (e < tol).mean() >= frac and e.max() < 1e-3, ((e < tol).mean(), e.max())
     assert np.abs(r - o["r"]).max() < 1e-3
+
+
+def qp_kkt_residual(a, c, u_ref, lo, hi, p, u, tol=2e-5):
+    """Optimality certificate for one row of  min ||u-u_ref||^2 + p sum_i max(0, c_i + a_i.u)  over the box: the
+    smallest t for which multipliers mu exist with  mu_i = 0 (g_i < 0), = p (g_i > 0), in [0,p] (g_i = 0)  and
+    |2(u-u_ref) + mu^T a|_k <= t on free coordinates, >= -t at the lower bound, <= t at the upper bound.  KKT is
+    sufficient for this convex QP, so t ~ 0 proves u optimal without trusting any other solver.  (LP via HiGHS.)"""
+    from scipy.optimize import linprog
+    a, c, u_ref, u = (np.asarray(v, np.float64) for v in (a, c, u_ref, u))
+    S, n = a.shape
+    g = c + a @ u
+    scale = 1.0 + np.abs(c) + np.abs(a).sum(1)
+    bounds = [(0.0, 0.0) if g[i] < -tol * scale[i] else ((p, p) if g[i] > tol * scale[i] else (0.0, p)) for i in range(S)]
+    grad0 = 2.0 * (u - u_ref)
+    A, bvec = [], []
+    for k in range(n):
+        at_lo, at_hi = u[k] <= lo[k] + 1e-6, u[k] >= hi[k] - 1e-6
+        if not at_hi:   # gradient_k >= -t  ->  -(mu.a_k) - t <= grad0_k
+            A.append(np.concatenate([-a[:, k], [-1.0]])); bvec.append(grad0[k])
+        if not at_lo:   # gradient_k <= t
+            A.append(np.concatenate([a[:, k], [-1.0]])); bvec.append(-grad0[k])
+    if not A:
+        return 0.0
+    res = linprog(np.concatenate([np.zeros(S), [1.0]]), A_ub=np.array(A), b_ub=np.array(bvec), bounds=bounds + [(0, None)])
+    assert res.status == 0, res.message
+    return float(res.x[-1])

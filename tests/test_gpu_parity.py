@@ -196,6 +196,50 @@ def test_qp_op_matches_oracle_semantics(coracle):
     assert rel_err(u.cpu().numpy(), o["u"]) < 2e-5 and rel_err(r.cpu().numpy(), o["r"], floor=0.1) < 2e-5
 
 
+def test_qp_reference_outside_box(coracle):
+    """u_ref outside the control limits (caller-supplied u_ref, clf_controller.py:497-505)"""
+    from cbfrrt import ops
+    rng = np.random.default_rng(12)
+    B, n, p = 20000, 7, 1e3
+    lo, hi = -np.ones(n, np.float32), np.ones(n, np.float32)
+    a = rng.normal(size=(B, n)).astype(np.float32)
+    c = rng.normal(size=B).astype(np.float32)
+    ur = rng.uniform(-3, 3, size=(B, n)).astype(np.float32)
+    uo, ro = coracle.qp(a, c, ur, lo, hi, p)
+    u, r = ops.qp(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p)
+    assert rel_err(u.cpu().numpy(), uo) < 2e-5 and rel_err(r.cpu().numpy(), ro, floor=0.1) < 2e-5
+
+
+@pytest.mark.parametrize("n,S,p", [(4, 2, 50.0), (7, 3, 1e3), (7, 4, 0.05), (4, 4, 1e9), (7, 1, 50.0)])
+def test_qp_multi_matches_oracle(coracle, n, S, p):
+    """cbfrrt::qp_multi (dual active-set coordinate solver, fp32) vs the fp64 oracle + a KKT certificate on a sample"""
+    from cbfrrt import ops
+    from conftest import qp_kkt_residual
+    rng = np.random.default_rng(100 + n * S)
+    B = 20000
+    lo, hi = -np.ones(n, np.float32), np.ones(n, np.float32)
+    a = rng.normal(size=(B, S, n)).astype(np.float32)
+    c = rng.normal(scale=0.8, size=(B, S)).astype(np.float32)
+    ur = rng.uniform(-1.5, 1.5, size=(B, n)).astype(np.float32)
+    uo, ro = coracle.qp_multi(a, c, ur, lo, hi, p)
+    u, r, sweeps = ops.qp_multi(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p, 500, 1e-7 * min(p, 1e6))
+    u, r, sweeps = u.cpu().numpy(), r.cpu().numpy(), sweeps.cpu().numpy()
+    assert sweeps.max() < 500, "coordinate solver did not converge on some row"
+    err = np.abs(u - uo).max(1)
+    assert np.mean(err < 1e-4) > 0.995 and err.max() < 5e-3, (np.mean(err < 1e-4), err.max())
+    obj = lambda uu, rr: ((uu - ur) ** 2).sum(1) + min(p, 1e6) * rr.sum(1)
+    assert np.all(obj(u, r) <= obj(uo, ro) * (1 + 1e-4) + 1e-4)
+    g = c + np.einsum("bsk,bk->bs", a, u)
+    assert np.all(g - r <= 2e-5 * (1 + np.abs(c) + np.abs(a).sum(2))) and np.all(r >= 0)
+    pc = min(p, 1e6)
+    for b in range(0, B, 400):
+        assert qp_kkt_residual(a[b], c[b], ur[b], lo, hi, pc, u[b], tol=1e-4) <= 1e-3 * (1 + 1e-3 * pc), b
+    if S == 1:
+        u1, r1 = ops.qp(_t(a[:, 0]), _t(c[:, 0]), _t(ur), _t(lo), _t(hi), p)
+        assert np.array_equal(u1.cpu().numpy(), u) and np.array_equal(r1.cpu().numpy(), r[:, 0])
+        assert sweeps.max() <= 2
+
+
 @pytest.mark.parametrize("cfg,scale", [(0, 1.0), (1, 1 / 64)])
 def test_safety_filter_fused_configs(coracle, cfg, scale):
     """BASELINE configs[0] in full (4096 Panda states, the reference's CPU-runnable case) and configs[1] at 1/64."""

@@ -142,6 +142,26 @@ def test_generic_clf_controller_qp(stack):
     assert (g < 1e-4).all() and (r >= 0).all()
 
 
+def test_clf_controller_multi_scenario(stack):
+    """len(scenarios) > 1: one relaxed constraint per scenario (clf_controller.py:86-139); r has one column each and the
+    control satisfies every scenario's constraint up to its own relaxation."""
+    env, robot, dyn, _ = stack("magician")
+    from cbfrrt.neural_cbf.controllers import CBFController
+    scen = [{"m1": 1.0}, {"m1": 1.2}, {"m1": 0.8}]
+    c = CBFController(dyn, scen, None, cbf_lambda=1.0, cbf_relaxation_penalty=50.0, controller_period=1 / 30)
+    x = dyn.sample_state_space(48)
+    dyn.set_goal(np.zeros(4))
+    (u, r), _ = c.solve_CLF_QP(x)
+    assert u.shape == (48, 4) and r.shape == (48, 3)
+    V, Lf, Lg, _ = c.V_with_lie_derivatives(x)
+    g = Lf[:, :, 0] + torch.einsum("bsk,bk->bs", Lg, u) + V.reshape(-1, 1) - r
+    assert (g < 1e-4).all() and (r >= 0).all()
+    # identical scenarios (ArmDynamics ignores params): the answer equals the single-scenario controller's
+    c1 = CBFController(dyn, scen[:1], None, cbf_lambda=1.0, cbf_relaxation_penalty=50.0 * 3, controller_period=1 / 30)
+    (u1, r1), _ = c1.solve_CLF_QP(x)
+    assert torch.allclose(u, u1, atol=2e-5)
+
+
 def test_steer_reference_loop_equals_fused(stack):
     env, robot, dyn, ctrl = stack("panda")
     from cbfrrt.motion_planning.baseline import steer, steer_fused, batch_steer, batch_steer_fused

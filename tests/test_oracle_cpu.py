@@ -127,3 +127,53 @@ def test_sampler_is_shard_invariant(coracle):
     lo, hi = np.array([-2.9671, -1.8326, -2.9671, -3.1416, -2.9671, -0.0873, -2.9671]), \
         np.array([2.9671, 1.8326, 2.9671, 0.0, 2.9671, 3.8223, 2.9671])
     assert (a >= lo - 1e-6).all() and (a <= hi + 1e-6).all() and a.std(0).min() > 0.4
+
+
+def test_qp_multi_oracle_is_optimal(coracle):
+    """oracle_qp_multi (dual coordinate ascent, fp64) on the QP of clf_controller.py:86-139 with S scenarios: KKT
+    certificate for every row, and agreement with scipy SLSQP on the primal wherever SLSQP converges"""
+    from scipy.optimize import minimize
+    from conftest import qp_kkt_residual
+    rng = np.random.default_rng(7)
+    n_slsqp = 0
+    for n, S, p in ((4, 3, 50.0), (7, 4, 1e3), (4, 2, 0.05), (7, 2, 1e9)):
+        B = 60
+        lo, hi = -np.ones(n, np.float32), np.ones(n, np.float32)
+        a = rng.normal(size=(B, S, n)).astype(np.float32)
+        c = rng.normal(scale=0.8, size=(B, S)).astype(np.float32)
+        ur = rng.uniform(-1.5, 1.5, size=(B, n)).astype(np.float32)      # also outside the box
+        u, r = coracle.qp_multi(a, c, ur, lo, hi, p)
+        pc = min(p, 1e6)
+        for b in range(B):
+            g = c[b].astype(np.float64) + a[b].astype(np.float64) @ u[b]
+            np.testing.assert_allclose(r[b], np.maximum(g, 0), atol=1e-5 * (1 + np.abs(c[b]).max()))
+            assert np.all(u[b] >= lo) and np.all(u[b] <= hi)
+            assert qp_kkt_residual(a[b], c[b], ur[b], lo, hi, pc, u[b]) <= 1e-4 * (1 + pc * 1e-3), (n, S, p, b)
+            if p > 100:
+                continue
+            cons = [{"type": "ineq", "fun": (lambda z, i=i: -(c[b, i] + a[b, i] @ z[:n] - z[n + i]))} for i in range(S)]
+            u0 = np.clip(ur[b], lo, hi)
+            res = minimize(lambda z: np.sum((z[:n] - ur[b]) ** 2) + p * np.sum(z[n:]),
+                           np.concatenate([u0, np.maximum(0, c[b] + a[b] @ u0) + 0.1]), constraints=cons,
+                           bounds=[(-1, 1)] * n + [(0, None)] * S, method="SLSQP", options={"ftol": 1e-12, "maxiter": 500})
+            if res.success:
+                n_slsqp += 1
+                np.testing.assert_allclose(u[b], res.x[:n], atol=3e-4)
+    assert n_slsqp > 60
+
+
+def test_qp_single_reference_outside_box(coracle):
+    """u_ref outside the control box: a coordinate leaves one bound and can reach the other (2n breakpoints)"""
+    from conftest import qp_kkt_residual
+    rng = np.random.default_rng(11)
+    n, B, p = 4, 200, 1e3
+    lo, hi = -np.ones(n, np.float32), np.ones(n, np.float32)
+    a = rng.normal(size=(B, n)).astype(np.float32)
+    c = rng.normal(scale=1.0, size=B).astype(np.float32)
+    ur = rng.uniform(-3, 3, size=(B, n)).astype(np.float32)
+    u, r = coracle.qp(a, c, ur, lo, hi, p)
+    um, rm = coracle.qp_multi(a[:, None, :], c[:, None], ur, lo, hi, p)
+    np.testing.assert_array_equal(u, um)
+    np.testing.assert_array_equal(r, rm[:, 0])
+    for b in range(B):
+        assert qp_kkt_residual(a[b:b + 1], c[b:b + 1], ur[b], lo, hi, p, u[b]) <= 1e-3
