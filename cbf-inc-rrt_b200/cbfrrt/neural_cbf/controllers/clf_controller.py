@@ -28,8 +28,8 @@ class CLFController(Controller):
             self.safe_level = kwargs["safe_level"]
             self.unsafe_level = kwargs["unsafe_level"]
         self.clf_relaxation_penalty = clf_relaxation_penalty
-        # multi-scenario solver budget (cbfrrt_qp_multi): coordinate sweeps and multiplier tolerance
-        self.qp_max_sweeps = int(kwargs.get("qp_max_sweeps", 200))
+        # multi-scenario solver budget (cbfrrt_qp_multi): iterations and control-space tolerance
+        self.qp_max_sweeps = int(kwargs.get("qp_max_sweeps", 100))
         self.qp_tol = float(kwargs.get("qp_tol", 1e-6))
 
     @property

@@ -222,35 +222,131 @@ __device__ __forceinline__ void qp_solve(const float (&a)[N], const float (&uref
 
 // S relaxed constraints (multi-scenario CLF/CBF-QP, clf_controller.py:86-139 with len(scenarios) > 1):
 //   min ||u-u_ref||^2 + p sum_i r_i   s.t.  c_i + a_i.u - r_i <= 0, r_i >= 0, lo <= u <= hi.
-// Batched dual active-set solver: the dual is concave in mu in [0,p]^S and u(mu) = clip(u_ref - sum_i mu_i a_i / 2);
-// cyclic exact coordinate maximisation -- every coordinate step is the exact active-set root find qp_mu above on the
-// target shifted by the other multipliers -- until no multiplier moves by more than tol.  One constraint is one
-// step.  S is the compile-time capacity, n_con <= S the number of constraints present (the rest must be zero-filled).
+// Batched dual active-set solver.  The dual is concave and piecewise quadratic in mu in [0,p]^S with
+// u(mu) = clip(u_ref - sum_i mu_i a_i / 2).  One iteration =
+//   (1) a cyclic sweep of exact coordinate maximisations -- each the single-constraint root find qp_mu on the target
+//       shifted by the other multipliers;
+//   (2) up to 4 Newton steps on the current active set (free multipliers W, unclipped coordinates F):
+//       (A_WF A_WF^T / 2 + eps I) d = g_W, followed by an EXACT line search: along d the directional derivative is
+//       d.c + w.clip(t - alpha w / 2) with w = A^T d, i.e. qp_mu again with (a, c, p) := (w, d.c, alpha_max).
+// Both moves increase the dual monotonically; (1) guarantees convergence, (2) terminates finitely once the active set
+// is identified (2-5 iterations on random problems, including infeasible systems relaxed at p = 1e6).  Stops when the
+// control-space movement of an iteration is <= tol * (1 + |dual shift of t|).  One constraint is one sweep.
+// S is the compile-time capacity, n_con <= S the constraints present (the rest zero-filled).  Returns iterations.
 template <int N, int S>
 __device__ __forceinline__ int qp_solve_multi(const float (&a)[S][N], const float (&uref)[N], const float* __restrict__ lo,
                                               const float* __restrict__ hi, const float (&c)[S], int n_con, float p,
-                                              int max_sweeps, float tol, float (&u)[N], float (&r)[S]) {
-    float mu[S], t[N];
+                                              int max_iter, float tol, float (&u)[N], float (&r)[S]) {
+    constexpr float KINK = 1e-6f;       // coordinates sitting on a kink of the dual count as free in the Newton matrix
+    float mu[S], t[N], amx[S];
 #pragma unroll
-    for (int i = 0; i < S; ++i) mu[i] = 0.f;
+    for (int i = 0; i < S; ++i) {
+        mu[i] = 0.f;
+        amx[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) amx[i] = fmaxf(amx[i], fabsf(a[i][k]));
+    }
 #pragma unroll
     for (int k = 0; k < N; ++k) t[k] = uref[k];
-    int sweeps = 0;
-    for (; sweeps < max_sweeps; ++sweeps) {
-        float moved = 0.f;
+    int it = 0;
+    while (it < max_iter) {
+        ++it;
+        float moved = 0.f, shift = 0.f;
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-            if (i >= n_con) break;
-            float ti[N];
+            if (i < n_con) {
+                float ti[N];
 #pragma unroll
-            for (int k = 0; k < N; ++k) ti[k] = fmaf(0.5f * mu[i], a[i][k], t[k]);   // remove constraint i's shift
-            const float m = qp_mu<N>(a[i], ti, lo, hi, c[i], p);
-            moved = fmaxf(moved, fabsf(m - mu[i]));
-            mu[i] = m;
+                for (int k = 0; k < N; ++k) ti[k] = fmaf(0.5f * mu[i], a[i][k], t[k]);   // remove constraint i's shift
+                const float m = qp_mu<N>(a[i], ti, lo, hi, c[i], p);
+                moved = fmaxf(moved, fabsf(m - mu[i]) * 0.5f * amx[i]);
+                shift = fmaxf(shift, 0.5f * m * amx[i]);
+                mu[i] = m;
 #pragma unroll
-            for (int k = 0; k < N; ++k) t[k] = fmaf(-0.5f * m, a[i][k], ti[k]);
+                for (int k = 0; k < N; ++k) t[k] = fmaf(-0.5f * m, a[i][k], ti[k]);
+            }
         }
-        if (moved <= tol) { ++sweeps; break; }
+        const float stop = tol * (1.f + shift);
+        if (moved <= stop) break;
+        if (n_con < 2) continue;
+        for (int rep = 0; rep < 4; ++rep) {
+            float g[S], d[S], M[S][S];
+            bool inW[S], isF[N];
+            int nW = 0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) isF[k] = t[k] >= lo[k] - KINK && t[k] <= hi[k] + KINK;
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                g[i] = c[i];
+#pragma unroll
+                for (int k = 0; k < N; ++k) g[i] = fmaf(a[i][k], fminf(fmaxf(t[k], lo[k]), hi[k]), g[i]);
+                inW[i] = (mu[i] > 0.f && mu[i] < p) || (mu[i] <= 0.f && g[i] > 0.f) || (mu[i] >= p && g[i] < 0.f);
+                nW += inW[i];
+            }
+            if (nW < 2) break;
+            float tr = 0.f;
+#pragma unroll
+            for (int i = 0; i < S; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) acc = fmaf(isF[k] ? a[i][k] : 0.f, a[j][k], acc);
+                    const float v = (inW[i] && inW[j]) ? 0.5f * acc : (i == j ? 1.f : 0.f);
+                    M[i][j] = v;
+                    M[j][i] = v;
+                    if (i == j && inW[i]) tr += v;
+                }
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                if (inW[i]) M[i][i] += fmaf(1e-6f, tr, 1e-30f);
+                d[i] = inW[i] ? g[i] : 0.f;
+            }
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < S; ++i) {            // Gaussian elimination (SPD, no pivoting)
+                ok = ok && M[i][i] > 0.f;
+                const float inv = 1.f / M[i][i];
+#pragma unroll
+                for (int j = i + 1; j < S; ++j) {
+                    const float f = M[j][i] * inv;
+#pragma unroll
+                    for (int k = i + 1; k < S; ++k) M[j][k] = fmaf(-f, M[i][k], M[j][k]);
+                    d[j] = fmaf(-f, d[i], d[j]);
+                }
+            }
+            if (!ok) break;
+#pragma unroll
+            for (int i = S - 1; i >= 0; --i) {
+#pragma unroll
+                for (int j = i + 1; j < S; ++j) d[i] = fmaf(-M[i][j], d[j], d[i]);
+                d[i] = d[i] / M[i][i];
+            }
+            float amax = 3e38f, cc = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                if ((mu[i] <= 0.f && d[i] < 0.f) || (mu[i] >= p && d[i] > 0.f) || !(fabsf(d[i]) < 1e30f)) d[i] = 0.f;
+                if (d[i] > 0.f) { amax = fminf(amax, (p - mu[i]) / d[i]); any = true; }
+                if (d[i] < 0.f) { amax = fminf(amax, -mu[i] / d[i]); any = true; }
+                cc = fmaf(d[i], c[i], cc);
+            }
+            if (!any) break;
+            float w[N], wmax = 0.f;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                w[k] = 0.f;
+#pragma unroll
+                for (int i = 0; i < S; ++i) w[k] = fmaf(a[i][k], d[i], w[k]);
+                wmax = fmaxf(wmax, fabsf(w[k]));
+            }
+            const float al = qp_mu<N>(w, t, lo, hi, cc, amax);
+#pragma unroll
+            for (int i = 0; i < S; ++i) mu[i] = fminf(fmaxf(fmaf(al, d[i], mu[i]), 0.f), p);
+#pragma unroll
+            for (int k = 0; k < N; ++k) t[k] = fmaf(-0.5f * al, w[k], t[k]);
+            if (!(al * wmax > stop)) break;
+        }
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) u[k] = fminf(fmaxf(t[k], lo[k]), hi[k]);
@@ -259,9 +355,9 @@ __device__ __forceinline__ int qp_solve_multi(const float (&a)[S][N], const floa
         float g = c[i];
 #pragma unroll
         for (int k = 0; k < N; ++k) g = fmaf(a[i][k], u[k], g);
-        r[i] = (mu[i] >= p) ? fmaxf(g, 0.f) : 0.f;      // r_i > 0 only when the multiplier saturates at p
+        r[i] = fmaxf(g, 0.f);       // optimal relaxation for this u
     }
-    return sweeps;
+    return it;
 }
 
 // everything after the MLP: J = Jh_q + Jh_o do/dq, nominal control, QP

@@ -151,13 +151,15 @@ int cbfrrt_qp(int n, const float *a, const float *c, const float *u_ref, int64_t
  * Replaces CLFController._solve_CLF_QP_cvxpylayers (clf_controller.py:354-404; one relaxed constraint per scenario,
  * :86-139) when len(scenarios) = S > 1:
  *   min ||u-u_ref||^2 + p sum_i r_i  s.t. c_i + a_i.u - r_i <= 0, r_i >= 0, lo <= u <= hi
- * with a [B, S, n], c [B, S], u_ref [B, n] -> u [B, n], r [B, S] (optional), sweeps [B] (optional: coordinate sweeps
- * used per row).  Dual active-set solver: exact cyclic coordinate maximisation of the concave dual over mu in
- * [0,p]^S, every step the exact single-constraint root find; stops when no multiplier moves by more than tol or
- * after max_sweeps.  1 <= n <= 8, 1 <= S <= 4.  p is clamped to 1e6. */
+ * with a [B, S, n], c [B, S], u_ref [B, n] -> u [B, n], r [B, S] (optional), iters [B] (optional: iterations used
+ * per row; == max_iter marks a row that did not reach tol).  Dual active-set solver: the concave piecewise-quadratic
+ * dual over mu in [0,p]^S is maximised by iterations of (1) one cyclic sweep of exact coordinate maximisations (the
+ * single-constraint root find) and (2) Newton steps on the current active set with an exact line search; stops when
+ * the control-space movement of an iteration is <= tol * (1 + size of the dual shift).  1 <= n <= 8, 1 <= S <= 4.
+ * p is clamped to 1e6.  Typical: 2-5 iterations. */
 int cbfrrt_qp_multi(int n, int n_constraints, const float *a, const float *c, const float *u_ref, int64_t B,
-                    const float *u_lo, const float *u_hi, float relaxation_penalty, int max_sweeps, float tol,
-                    float *u, float *r, int32_t *sweeps, void *stream);
+                    const float *u_lo, const float *u_hi, float relaxation_penalty, int max_iter, float tol,
+                    float *u, float *r, int32_t *iters, void *stream);
 
 /* ---- fused q -> (masks, datax, h, J, u, r): one launch for sampled states ------------------------------ */
 int cbfrrt_safety_filter(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_net *net, const float *q,

@@ -114,13 +114,15 @@ def qp(a, c, u_ref, u_lo, u_hi, penalty):
     return u, r
 
 
-def qp_multi(a, c, u_ref, u_lo, u_hi, penalty):
+def qp_multi(a, c, u_ref, u_lo, u_hi, penalty, max_iter=2000, tol=1e-12, want_iters=False):
+    """float64 dual active-set solve of the S-scenario QP; iters == max_iter marks a row that did not converge"""
     a, c, u_ref, u_lo, u_hi = _f(a), _f(c), _f(u_ref), _f(u_lo), _f(u_hi)
     B, S, n = a.shape
-    u, r = np.empty((B, n), np.float32), np.empty((B, S), np.float32)
-    rc = lib().oracle_qp_multi(n, S, _p(a), _p(c), _p(u_ref), C.c_long(B), _p(u_lo), _p(u_hi), C.c_float(penalty), _p(u), _p(r))
+    u, r, it = np.empty((B, n), np.float32), np.empty((B, S), np.float32), np.empty(B, np.int32)
+    rc = lib().oracle_qp_multi(n, S, _p(a), _p(c), _p(u_ref), C.c_long(B), _p(u_lo), _p(u_hi), C.c_float(penalty),
+                               C.c_int(max_iter), C.c_double(tol), _p(u), _p(r), _p(it))
     assert rc == 0
-    return u, r
+    return (u, r, it) if want_iters else (u, r)
 
 
 def u_nominal(q, goal, K, u_lo, u_hi):

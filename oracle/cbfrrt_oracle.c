@@ -396,31 +396,112 @@ static void qp_exact(int n, const double *a, const double *uref, const double *l
     *r_out = (mu >= p && g > 0.0) ? g : 0.0;
 }
 
-/* S relaxed constraints: cyclic exact dual coordinate maximisation to machine precision (float64) */
+/* S relaxed constraints: maximise the concave piecewise-quadratic dual over mu in [0,p]^S (float64).
+ * Every iteration = one cyclic sweep of exact coordinate maximisations (each a single-constraint root find on the
+ * target shifted by the other multipliers) followed by one Newton step on the current active set (free multipliers
+ * W, unclipped coordinates F:  (A_WF A_WF^T / 2 + eps I) d = g_W ) with an EXACT line search -- along d the
+ * directional derivative is again c' + w.clip(t - alpha w / 2) with w = A^T d, i.e. the same root find.  Both moves
+ * are monotone in the dual, so the iteration inherits the convergence of coordinate ascent and the finite
+ * termination of Newton once the active set is identified.  Returns the iterations used (max_iter = not converged:
+ * only seen on infeasible systems with a huge penalty, where mu creeps along a flat dual ridge). */
 #define MAXS 8
+#define KINK_TOL 1e-9 /* coordinates sitting on a kink of the dual count as free: the step must not leave the kink */
+#ifndef NEWTON_REPS
+#define NEWTON_REPS 4
+#endif
 static int qp_multi_exact(int n, int S, const double *a /* [S][n] */, const double *uref, const double *lo,
-                          const double *hi, const double *c, double p, double *u, double *r) {
+                          const double *hi, const double *c, double p, int max_iter, double tol, double *u, double *r) {
     double mu[MAXS] = {0}, t[MAXN], ti[MAXN];
     for (int k = 0; k < n; ++k) t[k] = uref[k];
-    int sweeps = 0;
-    for (; sweeps < 100000; ++sweeps) {
-        double moved = 0.0;
+    int it = 0;
+    while (it < max_iter) {
+        ++it;
+        double moved = 0.0, shift = 0.0; /* control-space movement of this iteration, size of the dual shift of t */
         for (int i = 0; i < S; ++i) {
-            for (int k = 0; k < n; ++k) ti[k] = t[k] + 0.5 * mu[i] * a[i * n + k];
+            double amax_i = 0.0;
+            for (int k = 0; k < n; ++k) {
+                ti[k] = t[k] + 0.5 * mu[i] * a[i * n + k];
+                if (fabs(a[i * n + k]) > amax_i) amax_i = fabs(a[i * n + k]);
+            }
             double m = qp_mu_exact(n, a + i * n, ti, lo, hi, c[i], p);
-            if (fabs(m - mu[i]) > moved) moved = fabs(m - mu[i]);
+            double mv = fabs(m - mu[i]) * 0.5 * amax_i;
+            if (mv > moved) moved = mv;
+            if (0.5 * m * amax_i > shift) shift = 0.5 * m * amax_i;
             mu[i] = m;
             for (int k = 0; k < n; ++k) t[k] = ti[k] - 0.5 * m * a[i * n + k];
         }
-        if (moved <= 1e-13 * (1.0 + p)) break;
+        if (moved <= tol * (1.0 + shift)) break; /* relative: t = u_ref - A^T mu / 2 carries rounding of size eps * shift */
+        if (S < 2) continue;
+        /* Newton steps on the active set (a step that ends on a kink changes the set: try again, a few times) */
+        for (int rep = 0; rep < NEWTON_REPS; ++rep) {
+        double g[MAXS], d[MAXS], M[MAXS][MAXS], w[MAXN];
+        int inW[MAXS], nW = 0;
+        for (int i = 0; i < S; ++i) {
+            g[i] = c[i];
+            for (int k = 0; k < n; ++k) g[i] += a[i * n + k] * (t[k] < lo[k] ? lo[k] : (t[k] > hi[k] ? hi[k] : t[k]));
+            inW[i] = (mu[i] > 0.0 && mu[i] < p) || (mu[i] <= 0.0 && g[i] > 0.0) || (mu[i] >= p && g[i] < 0.0);
+            nW += inW[i];
+        }
+        if (nW < 2) break;
+        double tr = 0.0;
+        for (int i = 0; i < S; ++i)
+            for (int j = 0; j < S; ++j) {
+                double acc = 0.0;
+                if (inW[i] && inW[j])
+                    for (int k = 0; k < n; ++k)
+                        if (t[k] >= lo[k] - KINK_TOL && t[k] <= hi[k] + KINK_TOL) acc += a[i * n + k] * a[j * n + k];
+                M[i][j] = (inW[i] && inW[j]) ? 0.5 * acc : (i == j ? 1.0 : 0.0);
+                if (i == j && inW[i]) tr += M[i][i];
+            }
+        for (int i = 0; i < S; ++i) {
+            if (inW[i]) M[i][i] += 1e-9 * tr + 1e-300;
+            d[i] = inW[i] ? g[i] : 0.0;
+        }
+        int ok = 1;
+        for (int i = 0; i < S && ok; ++i) { /* Gaussian elimination, SPD */
+            if (!(M[i][i] > 0.0)) { ok = 0; break; }
+            for (int j = i + 1; j < S; ++j) {
+                double f = M[j][i] / M[i][i];
+                for (int k = i; k < S; ++k) M[j][k] -= f * M[i][k];
+                d[j] -= f * d[i];
+            }
+        }
+        if (!ok) break;
+        for (int i = S - 1; i >= 0; --i) {
+            for (int j = i + 1; j < S; ++j) d[i] -= M[i][j] * d[j];
+            d[i] /= M[i][i];
+        }
+        double amax = 1e300, cc = 0.0;
+        int any = 0;
+        for (int i = 0; i < S; ++i) {
+            if ((mu[i] <= 0.0 && d[i] < 0.0) || (mu[i] >= p && d[i] > 0.0)) d[i] = 0.0;
+            if (d[i] > 0.0) { double v = (p - mu[i]) / d[i]; if (v < amax) amax = v; any = 1; }
+            if (d[i] < 0.0) { double v = -mu[i] / d[i]; if (v < amax) amax = v; any = 1; }
+            cc += d[i] * c[i];
+        }
+        if (!any) break;
+        double wmax = 0.0;
+        for (int k = 0; k < n; ++k) {
+            w[k] = 0.0;
+            for (int i = 0; i < S; ++i) w[k] += a[i * n + k] * d[i];
+            if (fabs(w[k]) > wmax) wmax = fabs(w[k]);
+        }
+        double al = qp_mu_exact(n, w, t, lo, hi, cc, amax);
+        for (int i = 0; i < S; ++i) {
+            mu[i] += al * d[i];
+            mu[i] = mu[i] < 0.0 ? 0.0 : (mu[i] > p ? p : mu[i]);
+        }
+        for (int k = 0; k < n; ++k) t[k] -= 0.5 * al * w[k];
+        if (!(al * wmax > tol * (1.0 + shift))) break;
+        }
     }
     for (int k = 0; k < n; ++k) u[k] = t[k] < lo[k] ? lo[k] : (t[k] > hi[k] ? hi[k] : t[k]);
     for (int i = 0; i < S; ++i) {
         double g = c[i];
         for (int k = 0; k < n; ++k) g += a[i * n + k] * u[k];
-        r[i] = (mu[i] >= p && g > 0.0) ? g : 0.0; /* r_i > 0 only when the multiplier saturates at p */
+        r[i] = g > 0.0 ? g : 0.0; /* optimal relaxation for this u */
     }
-    return sweeps;
+    return it;
 }
 
 /* ------------------------------------------------------------------ exported batch API (ctypes) */
@@ -596,14 +677,15 @@ API int oracle_qp(int n, const float *a, const float *c, const float *u_ref, lon
 
 /* multi-scenario QP on caller-supplied data: a [B,S,n], c [B,S], u_ref [B,n] -> u [B,n], r [B,S] */
 API int oracle_qp_multi(int n, int S, const float *a, const float *c, const float *u_ref, long B, const float *u_lo,
-                        const float *u_hi, float penalty, float *u, float *r) {
+                        const float *u_hi, float penalty, int max_iter, double tol, float *u, float *r, int *iters) {
     if (n > MAXN || S > MAXS) return -1;
     for (long b = 0; b < B; ++b) {
         double ad[MAXS * MAXN], cd[MAXS], ur[MAXN], lo[MAXN], hi[MAXN], ud[MAXN], rd[MAXS];
         for (int k = 0; k < S * n; ++k) ad[k] = a[b * S * n + k];
         for (int i = 0; i < S; ++i) cd[i] = c[b * S + i];
         for (int k = 0; k < n; ++k) { ur[k] = u_ref[b * n + k]; lo[k] = u_lo[k]; hi[k] = u_hi[k]; }
-        qp_multi_exact(n, S, ad, ur, lo, hi, cd, penalty < 1e6f ? (double)penalty : 1e6, ud, rd);
+        int it = qp_multi_exact(n, S, ad, ur, lo, hi, cd, penalty < 1e6f ? (double)penalty : 1e6, max_iter, tol, ud, rd);
+        if (iters) iters[b] = it;
         for (int k = 0; k < n; ++k) u[b * n + k] = (float)ud[k];
         for (int i = 0; i < S; ++i) r[b * S + i] = (float)rd[i];
     }
