@@ -30,7 +30,7 @@ class CLFController(Controller):
         self.clf_relaxation_penalty = clf_relaxation_penalty
         # multi-scenario solver budget (cbfrrt_qp_multi): iterations and control-space tolerance
         self.qp_max_sweeps = int(kwargs.get("qp_max_sweeps", 100))
-        self.qp_tol = float(kwargs.get("qp_tol", 1e-6))
+        self.qp_tol = float(kwargs.get("qp_tol", 1e-9))
 
     @property
     def device(self):

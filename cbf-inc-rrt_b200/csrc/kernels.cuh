@@ -317,34 +317,36 @@ __global__ void __launch_bounds__(256) qp_kernel(const float* __restrict__ a, co
     }
 }
 
-// multi-scenario QP: a [B,S,n], c [B,S], u_ref [B,n] -> u [B,n], r [B,S], sweeps [B] (optional)
+// multi-scenario QP: a [B,S,n], c [B,S], u_ref [B,n] -> u [B,n], r [B,S], iters [B] (optional).  fp32 in / out, the
+// dual iteration runs in double (see qp_solve_multi).
 constexpr int QP_MAX_CON = 4;
 template <int N>
 __global__ void __launch_bounds__(128) qp_multi_kernel(const float* __restrict__ a, const float* __restrict__ c,
                                                        const float* __restrict__ u_ref, long long B, int S,
                                                        const float* __restrict__ u_lo, const float* __restrict__ u_hi,
-                                                       float penalty, int max_sweeps, float tol, float* __restrict__ u,
-                                                       float* __restrict__ r, int* __restrict__ sweeps) {
-    __shared__ float lim[2 * N];
+                                                       float penalty, int max_iter, float tol, float* __restrict__ u,
+                                                       float* __restrict__ r, int* __restrict__ iters) {
+    __shared__ double lim[2 * N];
     if (threadIdx.x < N) { lim[threadIdx.x] = u_lo[threadIdx.x]; lim[N + threadIdx.x] = u_hi[threadIdx.x]; }
     __syncthreads();
     for (long long b = (long long)blockIdx.x * 128 + threadIdx.x; b < B; b += (long long)gridDim.x * 128) {
-        float aa[QP_MAX_CON][N], cc[QP_MAX_CON], ur[N], uu[N], rr[QP_MAX_CON];
+        double aa[QP_MAX_CON][N], cc[QP_MAX_CON], ur[N], uu[N], rr[QP_MAX_CON];
 #pragma unroll
         for (int i = 0; i < QP_MAX_CON; ++i) {
-            cc[i] = i < S ? __ldg(c + b * S + i) : 0.f;
+            cc[i] = i < S ? (double)__ldg(c + b * S + i) : 0.0;
 #pragma unroll
-            for (int k = 0; k < N; ++k) aa[i][k] = i < S ? __ldg(a + (b * S + i) * N + k) : 0.f;
+            for (int k = 0; k < N; ++k) aa[i][k] = i < S ? (double)__ldg(a + (b * S + i) * N + k) : 0.0;
         }
 #pragma unroll
-        for (int k = 0; k < N; ++k) ur[k] = __ldg(u_ref + b * N + k);
-        const int it = qp_solve_multi<N, QP_MAX_CON>(aa, ur, lim, lim + N, cc, S, fminf(penalty, 1e6f), max_sweeps, tol, uu, rr);
+        for (int k = 0; k < N; ++k) ur[k] = (double)__ldg(u_ref + b * N + k);
+        const int it = qp_solve_multi<N, QP_MAX_CON, double>(aa, ur, lim, lim + N, cc, S, (double)fminf(penalty, 1e6f),
+                                                             max_iter, (double)tol, uu, rr);
 #pragma unroll
-        for (int k = 0; k < N; ++k) u[b * N + k] = uu[k];
+        for (int k = 0; k < N; ++k) u[b * N + k] = (float)uu[k];
 #pragma unroll
         for (int i = 0; i < QP_MAX_CON; ++i)
-            if (r && i < S) r[b * S + i] = rr[i];
-        if (sweeps) sweeps[b] = it;
+            if (r && i < S) r[b * S + i] = (float)rr[i];
+        if (iters) iters[b] = it;
     }
 }
 

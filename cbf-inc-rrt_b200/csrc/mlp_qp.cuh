@@ -159,15 +159,15 @@ struct ParamLayout {
     static constexpr int K = 0, LO = N * N, HI = N * N + N, TOTAL = ((N * N + 2 * N) + 3) & ~3;
 };
 
-template <int N>
-__device__ __forceinline__ float qp_g(const float (&a)[N], const float (&uref)[N], const float* __restrict__ lo,
-                                      const float* __restrict__ hi, float c, float mu) {
-    float g = c;
-    const float hm = 0.5f * mu;
+template <int N, typename T>
+__host__ __device__ __forceinline__ T qp_g(const T (&a)[N], const T (&uref)[N], const T* __restrict__ lo,
+                                      const T* __restrict__ hi, T c, T mu) {
+    T g = c;
+    const T hm = T(0.5) * mu;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const float v = fminf(fmaxf(fmaf(-hm, a[i], uref[i]), lo[i]), hi[i]);
-        g = fmaf(a[i], v, g);
+        const T v = fmin(fmax(fma(-hm, a[i], uref[i]), lo[i]), hi[i]);
+        g = fma(a[i], v, g);
     }
     return g;
 }
@@ -178,36 +178,36 @@ __device__ __forceinline__ float qp_g(const float (&a)[N], const float (&uref)[N
 // target t lies outside the box).  Returns mu* = 0 if g(0) <= 0, p if g(p) > 0 (constraint relaxed), else the root,
 // found by evaluating g at every breakpoint (no sort: 2N * N is small) and interpolating inside the bracketing
 // segment (exact: g is linear there).
-template <int N>
-__device__ __forceinline__ float qp_mu(const float (&a)[N], const float (&t)[N], const float* __restrict__ lo,
-                                       const float* __restrict__ hi, float c, float p) {
-    const float g0 = qp_g<N>(a, t, lo, hi, c, 0.f);
-    if (!(g0 > 0.f)) return 0.f;
-    float mu_lo = 0.f, g_lo = g0;
-    float mu_hi = p, g_hi = qp_g<N>(a, t, lo, hi, c, p);
-    if (g_hi > 0.f) return p;
+template <int N, typename T>
+__host__ __device__ __forceinline__ T qp_mu(const T (&a)[N], const T (&t)[N], const T* __restrict__ lo,
+                                       const T* __restrict__ hi, T c, T p) {
+    const T g0 = qp_g<N>(a, t, lo, hi, c, T(0.));
+    if (!(g0 > T(0.))) return T(0.);
+    T mu_lo = T(0.), g_lo = g0;
+    T mu_hi = p, g_hi = qp_g<N>(a, t, lo, hi, c, p);
+    if (g_hi > T(0.)) return p;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        if (a[i] != 0.f) {
-            const float inv = 2.f / a[i];
+        if (a[i] != T(0.)) {
+            const T inv = T(2.) / a[i];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                const float m = (t[i] - (s ? hi[i] : lo[i])) * inv;
+                const T m = (t[i] - (s ? hi[i] : lo[i])) * inv;
                 if (m > mu_lo && m < mu_hi) {
-                    const float gm = qp_g<N>(a, t, lo, hi, c, m);
-                    if (gm > 0.f) { mu_lo = m; g_lo = gm; }
+                    const T gm = qp_g<N>(a, t, lo, hi, c, m);
+                    if (gm > T(0.)) { mu_lo = m; g_lo = gm; }
                     else          { mu_hi = m; g_hi = gm; }
                 }
             }
         }
     }
-    return (g_lo > g_hi) ? fmaf(mu_hi - mu_lo, g_lo / (g_lo - g_hi), mu_lo) : mu_hi;
+    return (g_lo > g_hi) ? fma(mu_hi - mu_lo, g_lo / (g_lo - g_hi), mu_lo) : mu_hi;
 }
 
 // Exact KKT solution of the single-constraint CBF-QP
 //   min ||u-u_ref||^2 + p r   s.t.  c + a.u - r <= 0, r >= 0, lo <= u <= hi      (clf_controller.py:82-139)
 template <int N>
-__device__ __forceinline__ void qp_solve(const float (&a)[N], const float (&uref)[N], const float* __restrict__ lo,
+__host__ __device__ __forceinline__ void qp_solve(const float (&a)[N], const float (&uref)[N], const float* __restrict__ lo,
                                          const float* __restrict__ hi, float c, float p, float (&u)[N], float& r) {
     const float mu = qp_mu<N>(a, uref, lo, hi, c, p);
     const float hm = 0.5f * mu;
@@ -231,46 +231,49 @@ __device__ __forceinline__ void qp_solve(const float (&a)[N], const float (&uref
 //       d.c + w.clip(t - alpha w / 2) with w = A^T d, i.e. qp_mu again with (a, c, p) := (w, d.c, alpha_max).
 // Both moves increase the dual monotonically; (1) guarantees convergence, (2) terminates finitely once the active set
 // is identified (2-5 iterations on random problems, including infeasible systems relaxed at p = 1e6).  Stops when the
-// control-space movement of an iteration is <= tol * (1 + |dual shift of t|).  One constraint is one sweep.
+// control-space movement of an iteration is <= tol + (rounding floor of t = 32 eps |dual shift|).  One constraint is
+// one sweep.
 // S is the compile-time capacity, n_con <= S the constraints present (the rest zero-filled).  Returns iterations.
-template <int N, int S>
-__device__ __forceinline__ int qp_solve_multi(const float (&a)[S][N], const float (&uref)[N], const float* __restrict__ lo,
-                                              const float* __restrict__ hi, const float (&c)[S], int n_con, float p,
-                                              int max_iter, float tol, float (&u)[N], float (&r)[S]) {
-    constexpr float KINK = 1e-6f;       // coordinates sitting on a kink of the dual count as free in the Newton matrix
-    float mu[S], t[N], amx[S];
+// T = double in the shipped kernel: with saturated multipliers (mu = p up to 1e6) t = u_ref - A^T mu / 2 cancels
+// ~6 digits, which fp32 cannot afford at 1e-5; B200's FP64 pipe makes this tiny kernel cost nothing.
+template <int N, int S, typename T>
+__host__ __device__ __forceinline__ int qp_solve_multi(const T (&a)[S][N], const T (&uref)[N], const T* __restrict__ lo,
+                                              const T* __restrict__ hi, const T (&c)[S], int n_con, T p,
+                                              int max_iter, T tol, T (&u)[N], T (&r)[S]) {
+    const T KINK = sizeof(T) == 8 ? T(1e-9) : T(1e-6), REG = sizeof(T) == 8 ? T(1e-9) : T(1e-6);       // coordinates sitting on a kink of the dual count as free in the Newton matrix
+    T mu[S], t[N], amx[S];
 #pragma unroll
     for (int i = 0; i < S; ++i) {
-        mu[i] = 0.f;
-        amx[i] = 0.f;
+        mu[i] = T(0.);
+        amx[i] = T(0.);
 #pragma unroll
-        for (int k = 0; k < N; ++k) amx[i] = fmaxf(amx[i], fabsf(a[i][k]));
+        for (int k = 0; k < N; ++k) amx[i] = fmax(amx[i], fabs(a[i][k]));
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) t[k] = uref[k];
     int it = 0;
     while (it < max_iter) {
         ++it;
-        float moved = 0.f, shift = 0.f;
+        T moved = T(0.), shift = T(0.);
 #pragma unroll
         for (int i = 0; i < S; ++i) {
             if (i < n_con) {
-                float ti[N];
+                T ti[N];
 #pragma unroll
-                for (int k = 0; k < N; ++k) ti[k] = fmaf(0.5f * mu[i], a[i][k], t[k]);   // remove constraint i's shift
-                const float m = qp_mu<N>(a[i], ti, lo, hi, c[i], p);
-                moved = fmaxf(moved, fabsf(m - mu[i]) * 0.5f * amx[i]);
-                shift = fmaxf(shift, 0.5f * m * amx[i]);
+                for (int k = 0; k < N; ++k) ti[k] = fma(T(0.5) * mu[i], a[i][k], t[k]);   // remove constraint i's shift
+                const T m = qp_mu<N>(a[i], ti, lo, hi, c[i], p);
+                moved = fmax(moved, fabs(m - mu[i]) * T(0.5) * amx[i]);
+                shift = fmax(shift, T(0.5) * m * amx[i]);
                 mu[i] = m;
 #pragma unroll
-                for (int k = 0; k < N; ++k) t[k] = fmaf(-0.5f * m, a[i][k], ti[k]);
+                for (int k = 0; k < N; ++k) t[k] = fma(-T(0.5) * m, a[i][k], ti[k]);
             }
         }
-        const float stop = tol * (1.f + shift);
+        const T stop = tol * (T(1.) + shift);
         if (moved <= stop) break;
         if (n_con < 2) continue;
         for (int rep = 0; rep < 4; ++rep) {
-            float g[S], d[S], M[S][S];
+            T g[S], d[S], M[S][S];
             bool inW[S], isF[N];
             int nW = 0;
 #pragma unroll
@@ -279,83 +282,83 @@ __device__ __forceinline__ int qp_solve_multi(const float (&a)[S][N], const floa
             for (int i = 0; i < S; ++i) {
                 g[i] = c[i];
 #pragma unroll
-                for (int k = 0; k < N; ++k) g[i] = fmaf(a[i][k], fminf(fmaxf(t[k], lo[k]), hi[k]), g[i]);
-                inW[i] = (mu[i] > 0.f && mu[i] < p) || (mu[i] <= 0.f && g[i] > 0.f) || (mu[i] >= p && g[i] < 0.f);
+                for (int k = 0; k < N; ++k) g[i] = fma(a[i][k], fmin(fmax(t[k], lo[k]), hi[k]), g[i]);
+                inW[i] = (mu[i] > T(0.) && mu[i] < p) || (mu[i] <= T(0.) && g[i] > T(0.)) || (mu[i] >= p && g[i] < T(0.));
                 nW += inW[i];
             }
             if (nW < 2) break;
-            float tr = 0.f;
+            T tr = T(0.);
 #pragma unroll
             for (int i = 0; i < S; ++i)
 #pragma unroll
                 for (int j = 0; j <= i; ++j) {
-                    float acc = 0.f;
+                    T acc = T(0.);
 #pragma unroll
-                    for (int k = 0; k < N; ++k) acc = fmaf(isF[k] ? a[i][k] : 0.f, a[j][k], acc);
-                    const float v = (inW[i] && inW[j]) ? 0.5f * acc : (i == j ? 1.f : 0.f);
+                    for (int k = 0; k < N; ++k) acc = fma(isF[k] ? a[i][k] : T(0.), a[j][k], acc);
+                    const T v = (inW[i] && inW[j]) ? T(0.5) * acc : (i == j ? T(1.) : T(0.));
                     M[i][j] = v;
                     M[j][i] = v;
                     if (i == j && inW[i]) tr += v;
                 }
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                if (inW[i]) M[i][i] += fmaf(1e-6f, tr, 1e-30f);
-                d[i] = inW[i] ? g[i] : 0.f;
+                if (inW[i]) M[i][i] += fma(REG, tr, T(1e-30));
+                d[i] = inW[i] ? g[i] : T(0.);
             }
             bool ok = true;
 #pragma unroll
             for (int i = 0; i < S; ++i) {            // Gaussian elimination (SPD, no pivoting)
-                ok = ok && M[i][i] > 0.f;
-                const float inv = 1.f / M[i][i];
+                ok = ok && M[i][i] > T(0.);
+                const T inv = T(1.) / M[i][i];
 #pragma unroll
                 for (int j = i + 1; j < S; ++j) {
-                    const float f = M[j][i] * inv;
+                    const T f = M[j][i] * inv;
 #pragma unroll
-                    for (int k = i + 1; k < S; ++k) M[j][k] = fmaf(-f, M[i][k], M[j][k]);
-                    d[j] = fmaf(-f, d[i], d[j]);
+                    for (int k = i + 1; k < S; ++k) M[j][k] = fma(-f, M[i][k], M[j][k]);
+                    d[j] = fma(-f, d[i], d[j]);
                 }
             }
             if (!ok) break;
 #pragma unroll
             for (int i = S - 1; i >= 0; --i) {
 #pragma unroll
-                for (int j = i + 1; j < S; ++j) d[i] = fmaf(-M[i][j], d[j], d[i]);
+                for (int j = i + 1; j < S; ++j) d[i] = fma(-M[i][j], d[j], d[i]);
                 d[i] = d[i] / M[i][i];
             }
-            float amax = 3e38f, cc = 0.f;
+            T amax = T(3e38), cc = T(0.);
             bool any = false;
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                if ((mu[i] <= 0.f && d[i] < 0.f) || (mu[i] >= p && d[i] > 0.f) || !(fabsf(d[i]) < 1e30f)) d[i] = 0.f;
-                if (d[i] > 0.f) { amax = fminf(amax, (p - mu[i]) / d[i]); any = true; }
-                if (d[i] < 0.f) { amax = fminf(amax, -mu[i] / d[i]); any = true; }
-                cc = fmaf(d[i], c[i], cc);
+                if ((mu[i] <= T(0.) && d[i] < T(0.)) || (mu[i] >= p && d[i] > T(0.)) || !(fabs(d[i]) < T(1e30))) d[i] = T(0.);
+                if (d[i] > T(0.)) { amax = fmin(amax, (p - mu[i]) / d[i]); any = true; }
+                if (d[i] < T(0.)) { amax = fmin(amax, -mu[i] / d[i]); any = true; }
+                cc = fma(d[i], c[i], cc);
             }
             if (!any) break;
-            float w[N], wmax = 0.f;
+            T w[N], wmax = T(0.);
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                w[k] = 0.f;
+                w[k] = T(0.);
 #pragma unroll
-                for (int i = 0; i < S; ++i) w[k] = fmaf(a[i][k], d[i], w[k]);
-                wmax = fmaxf(wmax, fabsf(w[k]));
+                for (int i = 0; i < S; ++i) w[k] = fma(a[i][k], d[i], w[k]);
+                wmax = fmax(wmax, fabs(w[k]));
             }
-            const float al = qp_mu<N>(w, t, lo, hi, cc, amax);
+            const T al = qp_mu<N>(w, t, lo, hi, cc, amax);
 #pragma unroll
-            for (int i = 0; i < S; ++i) mu[i] = fminf(fmaxf(fmaf(al, d[i], mu[i]), 0.f), p);
+            for (int i = 0; i < S; ++i) mu[i] = fmin(fmax(fma(al, d[i], mu[i]), T(0.)), p);
 #pragma unroll
-            for (int k = 0; k < N; ++k) t[k] = fmaf(-0.5f * al, w[k], t[k]);
+            for (int k = 0; k < N; ++k) t[k] = fma(-T(0.5) * al, w[k], t[k]);
             if (!(al * wmax > stop)) break;
         }
     }
 #pragma unroll
-    for (int k = 0; k < N; ++k) u[k] = fminf(fmaxf(t[k], lo[k]), hi[k]);
+    for (int k = 0; k < N; ++k) u[k] = fmin(fmax(t[k], lo[k]), hi[k]);
 #pragma unroll
     for (int i = 0; i < S; ++i) {
-        float g = c[i];
+        T g = c[i];
 #pragma unroll
-        for (int k = 0; k < N; ++k) g = fmaf(a[i][k], u[k], g);
-        r[i] = fmaxf(g, 0.f);       // optimal relaxation for this u
+        for (int k = 0; k < N; ++k) g = fma(a[i][k], u[k], g);
+        r[i] = fmax(g, T(0.));       // optimal relaxation for this u
     }
     return it;
 }

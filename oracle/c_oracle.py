@@ -114,7 +114,7 @@ def qp(a, c, u_ref, u_lo, u_hi, penalty):
     return u, r
 
 
-def qp_multi(a, c, u_ref, u_lo, u_hi, penalty, max_iter=2000, tol=1e-12, want_iters=False):
+def qp_multi(a, c, u_ref, u_lo, u_hi, penalty, max_iter=2000, tol=1e-10, want_iters=False):
     """float64 dual active-set solve of the S-scenario QP; iters == max_iter marks a row that did not converge"""
     a, c, u_ref, u_lo, u_hi = _f(a), _f(c), _f(u_ref), _f(u_lo), _f(u_hi)
     B, S, n = a.shape

@@ -430,7 +430,8 @@ static int qp_multi_exact(int n, int S, const double *a /* [S][n] */, const doub
             mu[i] = m;
             for (int k = 0; k < n; ++k) t[k] = ti[k] - 0.5 * m * a[i * n + k];
         }
-        if (moved <= tol * (1.0 + shift)) break; /* relative: t = u_ref - A^T mu / 2 carries rounding of size eps * shift */
+        const double stop = tol + 4e-15 * shift; /* t = u_ref - A^T mu / 2 carries rounding of size eps * shift */
+        if (moved <= stop) break;
         if (S < 2) continue;
         /* Newton steps on the active set (a step that ends on a kink changes the set: try again, a few times) */
         for (int rep = 0; rep < NEWTON_REPS; ++rep) {
@@ -492,7 +493,7 @@ static int qp_multi_exact(int n, int S, const double *a /* [S][n] */, const doub
             mu[i] = mu[i] < 0.0 ? 0.0 : (mu[i] > p ? p : mu[i]);
         }
         for (int k = 0; k < n; ++k) t[k] -= 0.5 * al * w[k];
-        if (!(al * wmax > tol * (1.0 + shift))) break;
+        if (!(al * wmax > stop)) break;
         }
     }
     for (int k = 0; k < n; ++k) u[k] = t[k] < lo[k] ? lo[k] : (t[k] > hi[k] ? hi[k] : t[k]);

@@ -212,7 +212,7 @@ def test_qp_reference_outside_box(coracle):
 
 @pytest.mark.parametrize("n,S,p", [(4, 2, 50.0), (7, 3, 1e3), (7, 4, 0.05), (7, 2, 1e9), (4, 3, 5000.0), (7, 1, 50.0)])
 def test_qp_multi_matches_oracle(coracle, n, S, p):
-    """cbfrrt::qp_multi (dual active-set solver, fp32) vs the fp64 oracle + a KKT certificate on a sample of rows"""
+    """cbfrrt::qp_multi (dual active-set solver) vs the fp64 oracle + a KKT certificate on a sample of rows"""
     from cbfrrt import ops
     from conftest import qp_kkt_residual
     rng = np.random.default_rng(100 + n * S)
@@ -223,31 +223,28 @@ def test_qp_multi_matches_oracle(coracle, n, S, p):
     ur = rng.uniform(-1.5, 1.5, size=(B, n)).astype(np.float32)
     uo, ro, ito = coracle.qp_multi(a, c, ur, lo, hi, p, want_iters=True)
     assert ito.max() < 2000
-    u, r, iters = ops.qp_multi(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p, 100, 1e-6)
+    u, r, iters = ops.qp_multi(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p, 100, 1e-9)
     u, r, iters = u.cpu().numpy(), r.cpu().numpy(), iters.cpu().numpy()
-    assert iters.max() < 100, "solver did not converge on some row"
-    assert np.percentile(iters, 99) <= 8
+    assert iters.max() <= 12, "active set not identified within a handful of iterations"
     pc = min(p, 1e6)
-    # fp32 carries t = u_ref - A^T mu / 2; with saturated multipliers (mu = p) its rounding is ~ 6e-8 * p * |a|
-    tol = 1e-4 * max(1.0, pc * 1e-3)
-    err = np.abs(u - uo).max(1)
-    assert np.mean(err < tol) > 0.995 and err.max() < 50 * tol, (np.mean(err < tol), err.max())
-    obj = lambda uu, rr: ((uu - ur) ** 2).sum(1) + pc * rr.sum(1)
-    assert np.all(obj(u, r) <= obj(uo, ro) * (1 + 1e-4) + 1e-4 * max(1.0, pc * 1e-3))
+    assert rel_err(u, uo) < 1e-5
+    obj = lambda uu, rr: ((uu.astype(np.float64) - ur) ** 2).sum(1) + pc * rr.astype(np.float64).sum(1)
+    # p * r carries p * (fp32 rounding of the stored u in g ~ 1e-6) for constraints that are active but not relaxed
+    assert np.all(obj(u, r) <= obj(uo, ro) * (1 + 1e-5) + 1e-5 + 5e-6 * pc)
     g = c + np.einsum("bsk,bk->bs", a, u)
     assert np.all(g - r <= 2e-5 * (1 + np.abs(c) + np.abs(a).sum(2))) and np.all(r >= 0)
     if pc <= 1e3:
         for b in range(0, B, 400):
-            assert qp_kkt_residual(a[b], c[b], ur[b], lo, hi, pc, u[b], tol=1e-4) <= 2e-3 * max(1.0, pc * 1e-2), b
+            assert qp_kkt_residual(a[b], c[b], ur[b], lo, hi, pc, u[b], tol=1e-5) <= 1e-4 * max(1.0, pc * 1e-2), b
     if S == 1:
         u1, r1 = ops.qp(_t(a[:, 0]), _t(c[:, 0]), _t(ur), _t(lo), _t(hi), p)
-        assert np.array_equal(u1.cpu().numpy(), u) and np.allclose(r1.cpu().numpy(), r[:, 0], atol=1e-5)
+        assert rel_err(u1.cpu().numpy(), u) < 1e-5 and np.allclose(r1.cpu().numpy(), r[:, 0], atol=1e-5)
         assert iters.max() <= 2
 
 
 def test_qp_multi_infeasible_systems_relax(coracle):
     """S = n = 4 random constraints with the clamped 1e6 penalty: many rows are infeasible and must relax (mu = p);
-    fp32 cannot hold 1e-4 on u there (|t| ~ 1e5), so the check is convergence + objective within 1e-3 relative"""
+    the multipliers reach 1e5..1e6 while free coordinates stay O(1) (the reason the kernel iterates in double)"""
     from cbfrrt import ops
     rng = np.random.default_rng(9)
     B, n, S, p = 20000, 4, 4, 1e9
@@ -256,13 +253,14 @@ def test_qp_multi_infeasible_systems_relax(coracle):
     c = rng.normal(scale=0.8, size=(B, S)).astype(np.float32)
     ur = rng.uniform(-1.5, 1.5, size=(B, n)).astype(np.float32)
     uo, ro, ito = coracle.qp_multi(a, c, ur, lo, hi, p, want_iters=True)
-    u, r, iters = ops.qp_multi(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p, 100, 1e-6)
+    u, r, iters = ops.qp_multi(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p, 100, 1e-9)
     u, r, iters = u.cpu().numpy().astype(np.float64), r.cpu().numpy().astype(np.float64), iters.cpu().numpy()
-    assert ito.max() < 2000 and np.mean(iters < 100) > 0.99
+    assert ito.max() <= 12 and iters.max() <= 12
+    assert np.mean((ro > 1e-3).any(1)) > 0.1, "the case must actually exercise relaxed constraints"
+    err = np.abs(u - uo).max(1)
+    assert np.mean(err < 1e-5) > 0.999 and err.max() < 1e-3, (np.mean(err < 1e-5), err.max())
     obj = lambda uu, rr: ((uu - ur) ** 2).sum(1) + 1e6 * rr.sum(1)
-    ok = iters < 100
-    assert np.all(obj(u, r)[ok] <= obj(uo.astype(np.float64), ro.astype(np.float64))[ok] * (1 + 1e-3) + 50.0)
-    assert np.mean(np.abs(u - uo).max(1) < 1e-2) > 0.97
+    assert np.all(obj(u, r) <= obj(uo.astype(np.float64), ro.astype(np.float64)) * (1 + 1e-4) + 100.0)
 
 
 @pytest.mark.parametrize("cfg,scale", [(0, 1.0), (1, 1 / 64)])
