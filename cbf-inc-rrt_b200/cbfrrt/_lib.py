@@ -64,6 +64,7 @@ SIGNATURES = {
     "cbfrrt_safety_filter_scatter": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, _L,
                                                C.POINTER(FilterParams), _F, _F, C.POINTER(PeerOut), _P]),
     "cbfrrt_edge_validity": (C.c_int, [_I, C.POINTER(Scene), _P, _P, _L, C.c_int32, _F, _F, _P, _P, _P]),
+    "cbfrrt_edge_validity_var": (C.c_int, [_I, C.POINTER(Scene), _P, _P, _L, _P, _L, _F, _F, _P, _P, _P]),
     "cbfrrt_rollout": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, C.POINTER(FilterParams),
                                  C.POINTER(RolloutParams), _F, _F, _P, _P, _P, _P, _P]),
     "cbfrrt_fma_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P]),

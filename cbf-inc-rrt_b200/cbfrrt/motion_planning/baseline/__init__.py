@@ -1,4 +1,4 @@
-from .tsa import steer, steer_fused, edge_checking, edge_checking_batch
+from .tsa import steer, steer_fused, edge_checking, edge_checking_batch, edge_checking_eps, edge_checking_reference_loop
 from .batch_tsa import steer as batch_steer, steer_fused as batch_steer_fused
 
-__all__ = ["steer", "steer_fused", "edge_checking", "edge_checking_batch", "batch_steer", "batch_steer_fused"]
+__all__ = ["steer", "steer_fused", "edge_checking", "edge_checking_batch", "edge_checking_eps", "edge_checking_reference_loop", "batch_steer", "batch_steer_fused"]

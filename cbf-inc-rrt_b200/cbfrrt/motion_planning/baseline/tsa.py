@@ -1,10 +1,12 @@
 """steer / edge_checking -- mirror of motion_planning/baseline/tsa.py:217-286.
 
-Two flavours of each:
-  * ``steer`` / ``edge_checking``: the reference's host loops verbatim (same signature, same return values),
-    running on this package's dynamics_model / controller, i.e. every call inside the loop is a CUDA op;
-  * ``steer_fused`` / ``edge_checking_batch``: the whole loop in ONE launch (cbfrrt::rollout /
-    cbfrrt::edge_validity) with identical semantics -- what the planners should call.
+  * ``steer``: the reference's host loop verbatim (same signature, same return values), running on this package's
+    dynamics_model / controller, i.e. every call inside the loop is a CUDA op;
+  * ``steer_fused``: the whole loop in ONE launch (cbfrrt::rollout) with identical semantics;
+  * ``edge_checking``: the reference's signature and result; its K+1 safe_mask calls are one launch
+    (``edge_checking_reference_loop`` keeps the per-point loop for parity tests);
+  * ``edge_checking_eps`` / ``edge_checking_batch``: many edges per launch with per-edge K = int(d/eps)
+    (cbfrrt::edge_validity_var) or one K for all (cbfrrt::edge_validity) -- what the planners should call.
 Tree growth, nearest-neighbour search and BIT* queues stay host Python.
 """
 import time
@@ -81,7 +83,15 @@ def _rollout(controller, dm, q0, steps, stuck=(0, 10, 0.1), want_traj=False, kee
 
 
 def edge_checking(state, new_state, dynamics_model, eps):
-    """tsa.py:272-286, unchanged: K+1 single-state safe_mask calls with early exit."""
+    """tsa.py:272-286: safe(new_state) and safe(state + k/K (new_state - state)), k = 0..K-1, K = int(d / eps) -- the
+    reference's K+1 single-state safe_mask calls collapse into ONE launch over the edge's points."""
+    assert state.size == new_state.size
+    valid, _ = edge_checking_eps([state], [new_state], dynamics_model, eps)
+    return bool(valid[0])
+
+
+def edge_checking_reference_loop(state, new_state, dynamics_model, eps):
+    """the reference's loop verbatim in structure (one safe_mask call per point, early exit); kept for parity tests"""
     assert state.size == new_state.size
     if not dynamics_model.safe_mask(torch.Tensor(new_state).unsqueeze(0)):
         return False
@@ -93,6 +103,21 @@ def edge_checking(state, new_state, dynamics_model, eps):
         if not dynamics_model.safe_mask(torch.Tensor(c).unsqueeze(0)):
             return False
     return True
+
+
+def edge_checking_eps(states, new_states, dynamics_model, eps):
+    """E edges, each with its own K_e = int(|new - old| / eps) (tsa.py:277-279, computed in float64 on the host like
+    the reference), in one launch (cbfrrt::edge_validity_var) -> (valid bool[E], first_bad i32[E])."""
+    dm = dynamics_model
+    b, s, fl, gr = dm.env.scene
+    a64 = np.asarray(states, dtype=np.float64).reshape(-1, dm.q_dims)
+    b64 = np.asarray(new_states, dtype=np.float64).reshape(-1, dm.q_dims)
+    K = (np.linalg.norm(a64 - b64, axis=1) / eps).astype(np.int64)
+    qf = torch.as_tensor(a64, dtype=torch.float32).to(dm.device)
+    qt = torch.as_tensor(b64, dtype=torch.float32).to(dm.device)
+    valid, first_bad = ops.edge_validity_var(qf, qt, torch.from_numpy(K), b, s, fl, gr, float(dm.dis_threshold),
+                                             float(dm.thr_hard), dm.robot.robot_id)
+    return valid.bool(), first_bad
 
 
 def edge_checking_batch(states, new_states, dynamics_model, n_interp):

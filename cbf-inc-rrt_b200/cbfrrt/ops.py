@@ -341,6 +341,35 @@ def edge_validity(q_from: Tensor, q_to: Tensor, n_interp: int, boxes: Tensor, sp
     return valid, first_bad
 
 
+@torch.library.custom_op("cbfrrt::edge_validity_var", mutates_args=(), device_types="cuda")
+def edge_validity_var(q_from: Tensor, q_to: Tensor, n_interp: Tensor, boxes: Tensor, spheres: Tensor, floor: int,
+                      grid: Tensor, thr_soft: float, thr_hard: float, robot_id: int) -> Tuple[Tensor, Tensor]:
+    """edges with their own number of interpolation points n_interp i32/i64[E] (>= 0; tsa.py:277-279)
+    -> valid u8[E], first_bad i32[E]"""
+    n = ROBOT_N[robot_id]
+    q_from, q_to = _f32c(q_from), _f32c(q_to)
+    if q_from.shape != q_to.shape or q_from.dim() != 2 or q_from.shape[1] != n:
+        raise ValueError(f"q_from / q_to must both be (E, {n})")
+    E, dev = q_from.shape[0], q_from.device
+    if n_interp.numel() != E:
+        raise ValueError("n_interp must have one entry per edge")
+    k_host = n_interp.detach().reshape(-1).to("cpu", torch.int64)    # sizes the launch: the total must be known on the host
+    if E and int(k_host.min()) < 0:
+        raise ValueError("n_interp must be >= 0")
+    off_host = torch.zeros(E + 1, dtype=torch.int64)
+    torch.cumsum(k_host + 1, 0, out=off_host[1:])
+    off = off_host.to(dev, non_blocking=True)
+    valid = torch.empty(E, dtype=torch.uint8, device=dev)
+    first_bad = torch.empty(E, dtype=torch.int32, device=dev)
+    sc = _scene(boxes, spheres, floor, grid)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_edge_validity_var(robot_id, C.byref(sc), _ptr(q_from), _ptr(q_to), E, _ptr(off), int(off_host[-1]),
+                                           thr_soft, thr_hard, _ptr(valid), _ptr(first_bad), _stream()),
+              "cbfrrt_edge_validity_var")
+    del off
+    return valid, first_bad
+
+
 @torch.library.custom_op("cbfrrt::rollout", mutates_args=(), device_types="cuda")
 def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, stuck_lag: int, stuck_after: int,
             stuck_eps: float, want_traj: bool, keep_going: bool, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor, K: Tensor,

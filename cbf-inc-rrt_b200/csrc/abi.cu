@@ -188,6 +188,21 @@ int cbfrrt_edge_validity(int robot, const cbfrrt_scene* scene, const float* q_fr
                                        : launch_edges_magician(sc, q_from, q_to, E, n_interp, thr_soft, thr_hard, valid, first_bad, st);
 }
 
+int cbfrrt_edge_validity_var(int robot, const cbfrrt_scene* scene, const float* q_from, const float* q_to, int64_t E,
+                             const int64_t* point_offsets, int64_t n_points, float thr_soft, float thr_hard,
+                             uint8_t* valid, int32_t* first_bad, void* stream) {
+    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
+    if (E < 0 || n_points < E || !q_from || !q_to || !point_offsets || !valid || !first_bad) return CBFRRT_ERR_BAD_SHAPE;
+    SceneArgs sc;
+    int rc = check_scene(scene, sc);
+    if (rc) return rc;
+    if (E == 0) return CBFRRT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long* off = reinterpret_cast<const long long*>(point_offsets);
+    return robot == CBFRRT_ROBOT_PANDA ? launch_edges_var_panda(sc, q_from, q_to, E, off, n_points, thr_soft, thr_hard, valid, first_bad, st)
+                                       : launch_edges_var_magician(sc, q_from, q_to, E, off, n_points, thr_soft, thr_hard, valid, first_bad, st);
+}
+
 int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* net, const float* q0, int64_t T,
                    const cbfrrt_filter_params* fp, const cbfrrt_rollout_params* rp, float thr_soft, float thr_hard,
                    float* q_final, uint8_t* alive, int32_t* steps_done, float* traj, void* stream) {

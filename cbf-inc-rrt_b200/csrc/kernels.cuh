@@ -612,6 +612,61 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_kernel(SceneArg
     }
 }
 
+// edges of different lengths (tsa.py:277-279: K = int(|q_to - q_from| / eps) per edge): one thread per (edge, point)
+// over the concatenation of all edges' points; off [E+1] is the exclusive prefix sum of K_e + 1.  Consecutive threads
+// are consecutive points of one edge, so a warp's states are geometrically coherent.  first_bad must be preset to
+// EDGE_SENTINEL (edge_var_init), the reduction is a global atomicMin, edge_var_finish writes valid / maps the sentinel.
+constexpr int EDGE_SENTINEL = 0x7fffffff;
+static __global__ void edge_var_init(int* __restrict__ first_bad, long long E) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x)
+        first_bad[e] = EDGE_SENTINEL;
+}
+static __global__ void edge_var_finish(int* __restrict__ first_bad, uint8_t* __restrict__ valid, long long E) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+        const int bad = first_bad[e];
+        valid[e] = bad == EDGE_SENTINEL;
+        if (bad == EDGE_SENTINEL) first_bad[e] = -1;
+    }
+}
+template <class RB, bool GRID>
+__global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_var_kernel(SceneArgs sc, const float* __restrict__ q_from,
+                                                      const float* __restrict__ q_to, long long E,
+                                                      const long long* __restrict__ off, long long P, float thr_soft,
+                                                      float thr_hard, int* __restrict__ first_bad) {
+    constexpr int N = RB::N;
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
+    stage<N>(s, sc, nullptr, 0);
+    const SceneS sv = scene_view(s, sc);
+    const float base_min = base_min_cta<RB>(s, sv);
+    for (long long p = (long long)blockIdx.x * NT + threadIdx.x; p < P; p += (long long)gridDim.x * NT) {
+        long long lo = 0, hi = E;                       // largest e with off[e] <= p
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (__ldg(off + mid) <= p) lo = mid; else hi = mid;
+        }
+        const long long e = lo, o0 = __ldg(off + e);
+        const int K = (int)(__ldg(off + e + 1) - o0) - 1, k = (int)(p - o0);
+        float c[N];
+        if (k == K) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) c[i] = __ldg(q_to + e * N + i);
+        } else {
+            const float t = __fdiv_rn((float)k, (float)K);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const float a = __ldg(q_from + e * N + i), bb = __ldg(q_to + e * N + i);
+                c[i] = fmaf(t, __fsub_rn(bb, a), a);
+            }
+        }
+        CollideResult<RB> r;
+        collide_state<RB, false, false, GRID>(c, sv, base_min, r);
+        const bool unsafe = r.hard_min <= thr_hard;
+        const bool safe = r.self_ok && (r.soft_min > thr_soft) && !unsafe;
+        if (!safe) atomicMin(first_bad + e, k);
+    }
+}
+
 // long edges (K + 1 > NT): one warp-strided thread loop per edge is not needed by any reference caller; they
 // are handled by the thread-per-edge fallback below (sequential over k with early exit, tsa.py:281-285).
 template <class RB, bool GRID>
@@ -958,6 +1013,24 @@ static int launch_edges(const SceneArgs& sc, const float* qf, const float* qt, l
 }
 
 template <class RB>
+static int launch_edges_var(const SceneArgs& sc, const float* qf, const float* qt, long long E, const long long* off,
+                            long long P, float ts, float th, uint8_t* valid, int* first_bad, cudaStream_t st) {
+    const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
+    const int eg = (int)((E + 255) / 256 < 1184 ? (E + 255) / 256 : 1184);
+    edge_var_init<<<eg, 256, 0, st>>>(first_bad, E);
+    if (finish_launch()) return CBFRRT_ERR_CUDA;
+    if (P > 0) {
+        auto k = sc.grid ? edge_var_kernel<RB, true> : edge_var_kernel<RB, false>;
+        const int grid = grid_for(k, smem, (P + NT - 1) / NT);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, NT, smem, st>>>(sc, qf, qt, E, off, P, ts, th, first_bad);
+        if (finish_launch()) return CBFRRT_ERR_CUDA;
+    }
+    edge_var_finish<<<eg, 256, 0, st>>>(first_bad, valid, E);
+    return finish_launch();
+}
+
+template <class RB>
 static int launch_rollout(const SceneArgs& sc, const NetArgs& net, const float* q0, long long T, const RolloutArgs& ra,
                           float ts, float th, float* qf, uint8_t* alive, int* done, float* traj, cudaStream_t st) {
     if (use_tc() && (T > SMALL_BATCH || force_tc())) {
@@ -986,6 +1059,8 @@ static int launch_rollout(const SceneArgs& sc, const NetArgs& net, const float* 
                           const CollideOutPtrs&, const FilterOutPtrs&, const PeerOut&, cudaStream_t);                  \
     int launch_edges_##R(const SceneArgs&, const float*, const float*, long long, int, float, float, uint8_t*, int*,   \
                          cudaStream_t);                                                                                \
+    int launch_edges_var_##R(const SceneArgs&, const float*, const float*, long long, const long long*, long long,     \
+                             float, float, uint8_t*, int*, cudaStream_t);                                              \
     int launch_rollout_##R(const SceneArgs&, const NetArgs&, const float*, long long, const RolloutArgs&, float,       \
                            float, float*, uint8_t*, int*, float*, cudaStream_t);
 CBF_DECLARE_ROBOT(panda)

@@ -195,6 +195,14 @@ int cbfrrt_edge_validity(int robot, const cbfrrt_scene *scene, const float *q_fr
                          int32_t n_interp, float thr_soft, float thr_hard, uint8_t *valid, int32_t *first_bad,
                          void *stream);
 
+/* Same for edges of different lengths, as edge_checking computes them (tsa.py:277-279: K_e = int(|q_to - q_from| / eps),
+ * K_e = 0 checks only the end point).  point_offsets [E+1] (device, int64) is the exclusive prefix sum of K_e + 1,
+ * n_points = point_offsets[E] (passed by value so that the call does not synchronise).  Three launches (preset,
+ * one thread per (edge, point), finish); every point is evaluated (no early exit). */
+int cbfrrt_edge_validity_var(int robot, const cbfrrt_scene *scene, const float *q_from, const float *q_to, int64_t E,
+                             const int64_t *point_offsets, int64_t n_points, float thr_soft, float thr_hard,
+                             uint8_t *valid, int32_t *first_bad, void *stream);
+
 /* ---- K9 closed-loop rollouts ------------------------------------------------------------------------------
  * Replaces the steer loop (motion_planning/baseline/tsa.py:217-269, batch_tsa.py:191-231) built on
  * ArmDynamics.closed_loop_dynamics (arm_dynamics.py:474-523): control every ctrl_every steps, Euler every

@@ -172,6 +172,20 @@ def edge_validity(robot, q_from, q_to, n_interp, boxes, spheres=None, floor=True
     return valid, first_bad
 
 
+def edge_validity_var(robot, q_from, q_to, n_interp, boxes, spheres=None, floor=True, thr_soft=0.02, thr_hard=0.0):
+    """per-edge number of interpolation points n_interp[E] >= 0"""
+    q_from, q_to = _f(q_from), _f(q_to)
+    E = q_from.shape[0]
+    K = np.ascontiguousarray(n_interp, dtype=np.int32).reshape(E)
+    b8, sp = pack_scene(boxes, spheres)
+    valid = np.empty(E, np.uint8)
+    first_bad = np.empty(E, np.int32)
+    lib().oracle_edge_validity_var(ROBOT_ID[robot], b8.shape[0], _p(b8), sp.shape[0], _p(sp), int(bool(floor)), _p(q_from),
+                                   _p(q_to), C.c_long(E), _p(K), C.c_float(thr_soft), C.c_float(thr_hard),
+                                   _p(valid), _p(first_bad))
+    return valid, first_bad
+
+
 def rollout(robot, q0, goal, steps, ctrl_every, dt, boxes, spheres, floor, weights, hidden, layers, K, u_lo, u_hi,
             thr_soft, thr_hard, lam, penalty, stuck_lag=0, stuck_after=10, stuck_eps=0.1, want_traj=False, keep_going=False):
     q0 = _f(q0)

@@ -549,6 +549,7 @@ typedef struct {
     long q_stride, goal_rows;
     float thr_soft, thr_hard, lam, penalty, dt;
     int Kint, steps, ctrl_every, stuck_lag, stuck_after, keep_going;
+    const int *Kvar;
     float stuck_eps, *traj;
     uint8_t *safe, *unsafe, *alive;
     float *datax, *h, *J, *u, *r, *mins, *pos, *rot, *q_final;
@@ -737,8 +738,9 @@ API int oracle_safety_filter(int robot, int n_boxes, const float *boxes, int n_s
  * first_bad = smallest along-edge index that fails (k for interpolation points, K for the end point), -1 if valid.
  * Interpolation contract: t = (float)k / (float)K (one division), c_i = fmaf(t, q_to_i - q_from_i, q_from_i). */
 CLONES static void edge_range(long lo, long hi, void *p) {
-    Ctx *c = (Ctx *)p; const int n = c->n, K = c->Kint;
+    Ctx *c = (Ctx *)p; const int n = c->n;
     for (long e = lo; e < hi; ++e) {
+        const int K = c->Kvar ? c->Kvar[e] : c->Kint; /* per-edge K (tsa.py:277-279) or one K for all */
         int bad = -1;
         for (int k = 0; k <= K && bad < 0; ++k) {
             float x[MAXN];
@@ -762,6 +764,17 @@ API int oracle_edge_validity(int robot, int n_boxes, const float *boxes, int n_s
     Ctx c; memset(&c, 0, sizeof c);
     c.rb = &ROBOTS[robot]; c.n = c.rb->n; c.sc = (Scene){n_boxes, n_sph, floor, boxes, spheres};
     c.q = q_from; c.q2 = q_to; c.Kint = K; c.thr_soft = thr_soft; c.thr_hard = thr_hard; c.safe = valid;
+    c.first_bad = first_bad;
+    par_for(E, edge_range, &c);
+    return 0;
+}
+
+API int oracle_edge_validity_var(int robot, int n_boxes, const float *boxes, int n_sph, const float *spheres, int floor,
+                                 const float *q_from, const float *q_to, long E, const int *K, float thr_soft,
+                                 float thr_hard, uint8_t *valid, int *first_bad) {
+    Ctx c; memset(&c, 0, sizeof c);
+    c.rb = &ROBOTS[robot]; c.n = c.rb->n; c.sc = (Scene){n_boxes, n_sph, floor, boxes, spheres};
+    c.q = q_from; c.q2 = q_to; c.Kvar = K; c.thr_soft = thr_soft; c.thr_hard = thr_hard; c.safe = valid;
     c.first_bad = first_bad;
     par_for(E, edge_range, &c);
     return 0;

@@ -57,6 +57,12 @@ def install(monkeypatch):
         v, f = c_oracle.edge_validity(NAME[robot_id], _np(q_from), _np(q_to), n_interp, b, s, bool(floor), thr_soft, thr_hard)
         return torch.from_numpy(v), torch.from_numpy(f)
 
+    def edge_validity_var(q_from, q_to, n_interp, boxes, spheres, floor, grid, thr_soft, thr_hard, robot_id):
+        b, s = _scene(boxes, spheres)
+        v, f = c_oracle.edge_validity_var(NAME[robot_id], _np(q_from), _np(q_to), _np(n_interp), b, s, bool(floor), thr_soft,
+                                          thr_hard)
+        return torch.from_numpy(v), torch.from_numpy(f)
+
     def rollout(q0, goal, steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, want_traj, keep_going, boxes, spheres, floor, grid,
                 weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id, hidden, layers):
         b, s = _scene(boxes, spheres)
@@ -75,5 +81,5 @@ def install(monkeypatch):
         return torch.from_numpy(o["safe"]), torch.from_numpy(o["u"])
 
     for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp, qp_multi=qp_multi,
-                         edge_validity=edge_validity, rollout=rollout, valid_control=valid_control).items():
+                         edge_validity=edge_validity, edge_validity_var=edge_validity_var, rollout=rollout, valid_control=valid_control).items():
         monkeypatch.setattr(ops, name, fn)

@@ -302,6 +302,33 @@ def test_edge_validity_bit_exact(coracle, robot, K):
     assert 0 < vo.mean() < 1
 
 
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_edge_validity_per_edge_lengths_bit_exact(coracle, robot):
+    """cbfrrt::edge_validity_var: every edge with its own K_e = int(d/eps) (tsa.py:277-279), including K_e = 0"""
+    from cbfrrt import ops, workloads as W
+    E, n = 3000, (7 if robot == "panda" else 4)
+    rng = np.random.default_rng(21)
+    qf = W.sample_states(robot, E, 4)
+    m = W.ROBOT_MODELS[robot]
+    lo, hi = np.array(m["q_lower"], np.float32), np.array(m["q_upper"], np.float32)
+    qt = np.clip(qf + rng.uniform(-0.4, 0.4, size=qf.shape).astype(np.float32) * rng.uniform(0, 1, size=(E, 1)).astype(np.float32), lo, hi)
+    K = (np.linalg.norm(qf.astype(np.float64) - qt, axis=1) / 0.03).astype(np.int32)
+    K[:5] = 0
+    assert K.max() > 15 and (K == 0).sum() >= 5
+    boxes, spheres = W.random_boxes(12, 3, 0.03, 0.1), W.random_spheres(6, 4, 0.03, 0.08)
+    vo, fo = coracle.edge_validity_var(robot, qf, qt, K, boxes, spheres, True, 0.02, 0.0)
+    b8, s4 = ops.pack_scene(boxes[:, :3], boxes[:, 3:], spheres, device="cuda")
+    v, f = ops.edge_validity_var(_t(qf), _t(qt), torch.from_numpy(K), b8, s4, 1, ops.no_grid("cuda"), 0.02, 0.0,
+                                 ops.ROBOT_ID[robot])
+    assert np.array_equal(v.cpu().numpy(), vo) and np.array_equal(f.cpu().numpy(), fo)
+    assert 0.05 < vo.mean() < 0.95
+    # same K for all edges == the fixed-K entry point
+    v2, f2 = ops.edge_validity(_t(qf), _t(qt), 9, b8, s4, 1, ops.no_grid("cuda"), 0.02, 0.0, ops.ROBOT_ID[robot])
+    v3, f3 = ops.edge_validity_var(_t(qf), _t(qt), torch.full((E,), 9, dtype=torch.int32), b8, s4, 1, ops.no_grid("cuda"),
+                                   0.02, 0.0, ops.ROBOT_ID[robot])
+    assert torch.equal(v2, v3) and torch.equal(f2, f3)
+
+
 def test_edge_validity_equals_pointwise_safe_mask():
     """size-independent property: an edge is valid iff every interpolated configuration is safe (tsa.py:272-286)."""
     from cbfrrt import ops, workloads as W
@@ -465,6 +492,7 @@ def test_python_api_drop_in_on_gpu(coracle):
     eps = 0.05
     K = int(np.linalg.norm(start - target) / eps)
     v, fb = edge_checking_batch(start[None], target[None], dyn, K)
-    assert bool(v.item()) == edge_checking(start, target, dyn, eps)
+    from cbfrrt.motion_planning.baseline import edge_checking_reference_loop
+    assert bool(v.item()) == edge_checking(start, target, dyn, eps) == edge_checking_reference_loop(start, target, dyn, eps)
     assert robot.forward_kinematics([6, 7], torch.tensor(robot.q0))[1][0].shape == (3,)
     assert np.allclose(robot.forward_kinematics([7], robot.q0)[0][0], (0.288556, -0.257364, 0.361447), atol=2e-6)

@@ -192,18 +192,26 @@ def test_steer_reference_loop_equals_fused(stack):
 
 def test_edge_checking_reference_loop_equals_batched(stack):
     env, robot, dyn, ctrl = stack("panda")
-    from cbfrrt.motion_planning.baseline import edge_checking, edge_checking_batch
+    from cbfrrt.motion_planning.baseline import (edge_checking, edge_checking_batch, edge_checking_eps,
+                                                 edge_checking_reference_loop)
     x = dyn.sample_state_space(120)
     xs = x[dyn.safe_mask(x)].numpy()
     eps, agree, n_valid = 0.05, 0, 0
+    A = np.stack([xs[i] for i in range(10)])
+    Bq = np.stack([xs[i] + 0.5 * (xs[i + 10] - xs[i]) for i in range(10)])
+    Bq[3] = A[3] + 1e-3          # K = 0: only the end point is checked (tsa.py:279-281)
+    v_eps, fb_eps = edge_checking_eps(A, Bq, dyn, eps)
     for i in range(10):
-        a, b = xs[i], xs[i] + 0.5 * (xs[i + 10] - xs[i])
+        a, b = A[i], Bq[i]
         K = int(np.linalg.norm(a - b) / eps)
-        ref = edge_checking(a, b, dyn, eps)
-        v, fb = edge_checking_batch(a[None], b[None], dyn, K)
-        agree += (bool(v.item()) == ref)
+        ref = edge_checking_reference_loop(a, b, dyn, eps)
+        assert edge_checking(a, b, dyn, eps) == bool(v_eps[i])
+        if K >= 1:
+            v, fb = edge_checking_batch(a[None], b[None], dyn, K)
+            assert bool(v.item()) == bool(v_eps[i]) and fb.item() == fb_eps[i].item()
+        agree += (bool(v_eps[i]) == ref)
         n_valid += ref
-        assert (fb.item() == -1) == bool(v.item())
+        assert (fb_eps[i].item() == -1) == bool(v_eps[i])
     # the reference interpolates in float64 on the host, the kernel in float32: allow one borderline flip
     assert agree >= 9 and 0 < n_valid < 10
 

@@ -1,4 +1,4 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1f.json 2> gpurun_out/bench_r1f.err; cut -c1-600 gpurun_out/bench_r1f.json
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/plain_b.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1f.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/plain_b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:safety_kernel_tc -s 4 -c 1 -o gpurun_out/prof_safety_tc_r1f python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_f.log 2>&1
+ls -la gpurun_out/*.ncu-rep
