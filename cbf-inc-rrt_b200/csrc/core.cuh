@@ -37,6 +37,7 @@ struct Panda {
     __device__ static constexpr float sph(int i, int k) { return PANDA_SPH[i][k]; }
     __device__ static constexpr int sph_link(int i) { return PANDA_SPH_LINK[i]; }
     __device__ static constexpr int anc_mask(int l) { return PANDA_ANC_MASK[l]; }
+    __device__ static constexpr float ball(int l, int k) { return PANDA_LINK_BALL[l + 1][k]; }
     __device__ static constexpr int self_i(int p) { return PANDA_SELFSPH_I[p]; }
     __device__ static constexpr int self_j(int p) { return PANDA_SELFSPH_J[p]; }
     __device__ static constexpr float self_x(int p) { return PANDA_SELFSPH_X[p]; }
@@ -57,6 +58,7 @@ struct Magician {
     __device__ static constexpr float sph(int i, int k) { return MAGICIAN_SPH[i][k]; }
     __device__ static constexpr int sph_link(int i) { return MAGICIAN_SPH_LINK[i]; }
     __device__ static constexpr int anc_mask(int l) { return MAGICIAN_ANC_MASK[l]; }
+    __device__ static constexpr float ball(int l, int k) { return MAGICIAN_LINK_BALL[l + 1][k]; }
     __device__ static constexpr int self_i(int p) { return MAGICIAN_SELFSPH_I[p]; }
     __device__ static constexpr int self_j(int p) { return MAGICIAN_SELFSPH_J[p]; }
     __device__ static constexpr float self_x(int p) { return MAGICIAN_SELFSPH_X[p]; }
@@ -174,6 +176,7 @@ struct SceneS {
     const float4* spheres;  // (cx cy cz r)
     int n_boxes, n_spheres, floor;
     const uint16_t* grid;   // nearest-candidate grid in global memory (grid.cuh) or nullptr = brute force
+    float cull_floor;       // max(thr_soft, thr_hard): pair distances above max(this, running min) cannot matter
 };
 
 // exact per-pair formulas (oracle: sd_box / sd_sphere / normal_box / normal_sphere)
@@ -239,9 +242,18 @@ __device__ __forceinline__ void acc_sphere(float cx, float cy, float cz, float4 
 // belong to one link -- restructuring (1) above.  out[k] = min_j sd(k, j)  (floor not included).
 // With a nearest-candidate grid only the candidates of each centre's cell are swept (exact, see grid.cuh); a link
 // with a centre outside the grid region or in an overflowed cell takes the brute-force sweep.
-template <int K, bool GRID>
+//
+// CULL (exact branch-and-bound): the caller passes a ball (centre B, radius included in `reach`) that contains the K
+// spheres and reach = max(T, 0) + R_ball + slack, where T >= every threshold the results are compared with and >= the
+// running minimum.  An obstacle whose distance to B exceeds reach has pair distances > T for all K spheres: it can
+// change neither the running minimum (nor its arg-min, found later by re-evaluation) nor a mask, so it is skipped.
+// The test sweep over obstacles is warp-uniform (broadcast LDS) and leaves a per-lane bit mask; each lane then visits
+// only its own survivors (typically 5-10 % of the obstacles).
+constexpr int CULL_MIN_OBSTACLES = 4;
+template <int K, bool GRID, bool CULL>
 __device__ __forceinline__ void sweep_scene(const SceneS& sc, const float (&C)[K][3], const float (&rad)[K],
-                                            float (&out)[K]) {
+                                            float (&out)[K], float Bx = 0.f, float By = 0.f, float Bz = 0.f,
+                                            float reach = 0.f) {
     float D[K], M[K], E[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { D[k] = CBF_INF; M[k] = CBF_INF; E[k] = CBF_INF; }
@@ -285,7 +297,43 @@ __device__ __forceinline__ void sweep_scene(const SceneS& sc, const float (&C)[K
             }
         }
     }
-    if (brute) {
+    if (brute && CULL) {
+        const float r2 = __fmul_rn(reach, reach);
+        for (int j0 = 0; j0 < sc.n_boxes; j0 += 32) {
+            const int je = min(32, sc.n_boxes - j0);
+            unsigned keep = 0u;
+            for (int jj = 0; jj < je; ++jj) {
+                const float4 b0 = sc.boxes[2 * (j0 + jj)], b1 = sc.boxes[2 * (j0 + jj) + 1];
+                const float ax = fabsf(Bx - b0.x) - b0.w, ay = fabsf(By - b0.y) - b1.x, az = fabsf(Bz - b0.z) - b1.y;
+                const float qx = fmaxf(ax, 0.f), qy = fmaxf(ay, 0.f), qz = fmaxf(az, 0.f);
+                const float dsq = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
+                keep |= (dsq > r2) ? 0u : (1u << jj);
+            }
+            while (keep) {
+                const int j = j0 + __ffs(keep) - 1;
+                keep &= keep - 1;
+                const float4 b0 = sc.boxes[2 * j], b1 = sc.boxes[2 * j + 1];
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc_box(C[k][0], C[k][1], C[k][2], b0, b1, D[k], M[k]);
+            }
+        }
+        for (int j0 = 0; j0 < sc.n_spheres; j0 += 32) {
+            const int je = min(32, sc.n_spheres - j0);
+            unsigned keep = 0u;
+            for (int jj = 0; jj < je; ++jj) {
+                const float4 s = sc.spheres[j0 + jj];
+                const float dx = Bx - s.x, dy = By - s.y, dz = Bz - s.z, rr = reach + s.w;   // rr > 0: reach > 0, s.w >= 0
+                keep |= (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > rr * rr) ? 0u : (1u << jj);
+            }
+            while (keep) {
+                const int j = j0 + __ffs(keep) - 1;
+                keep &= keep - 1;
+                const float4 s = sc.spheres[j];
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc_sphere(C[k][0], C[k][1], C[k][2], s, E[k]);
+            }
+        }
+    } else if (brute) {
         for (int j = 0; j < sc.n_boxes; ++j) {
             const float4 b0 = sc.boxes[2 * j], b1 = sc.boxes[2 * j + 1];
 #pragma unroll
@@ -378,7 +426,29 @@ __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const Sce
                         self_min = fminf(self_min, __fsub_rn(__fsub_rn(__fsqrt_rn(dsq), RB::sph(i, 3)), RB::sph(j, 3)));
                 }
             });
-            sweep_scene<K, GRID>(sc, C, rad, m);
+            // culling pays when a ball test (about one pair evaluation) can save K >= 3 of them and there is more than a
+            // handful of obstacles; CULL_MIN_OBSTACLES is warp-uniform
+            if (!WANT_SELFMIN && !GRID && K >= 3 && sc.n_boxes + sc.n_spheres >= CULL_MIN_OBSTACLES) {
+                // bound for the exact culling test: running minimum incl. this link's floor candidates (merged
+                // for real, in oracle order, below), never below the thresholds the masks compare with
+                float tb = o;
+                if (sc.floor) {
+                    if constexpr (L == 0) tb = fminf(tb, RB::LINK0_FLOOR);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) tb = fminf(tb, C[k][2] - rad[k]);
+                    }
+                }
+                constexpr float b0 = RB::ball(L, 0), b1 = RB::ball(L, 1), b2 = RB::ball(L, 2);
+                float Bc[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    Bc[r] = fmaf(fr[L].R[3 * r + 2], b2, fmaf(fr[L].R[3 * r + 1], b1, fmaf(fr[L].R[3 * r + 0], b0, fr[L].p[r])));
+                const float reach = fmaxf(fmaxf(tb, sc.cull_floor), 0.f) + (RB::ball(L, 3) + 1e-4f);
+                sweep_scene<K, false, true>(sc, C, rad, m, Bc[0], Bc[1], Bc[2], reach);
+            } else {
+                sweep_scene<K, GRID, false>(sc, C, rad, m);
+            }
             // merge in sphere order, floor candidate first (oracle iteration order; strict '<')
             static_for<0, K>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;

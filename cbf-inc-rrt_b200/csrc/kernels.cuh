@@ -141,8 +141,9 @@ __device__ __forceinline__ float base_min_cta(const Smem& s, const SceneS& sc) {
     return r;
 }
 
-__device__ __forceinline__ SceneS scene_view(const Smem& s, const SceneArgs& sc) {
+__device__ __forceinline__ SceneS scene_view(const Smem& s, const SceneArgs& sc, float thr_soft, float thr_hard) {
     SceneS v;
+    v.cull_floor = fmaxf(thr_soft, thr_hard);
     v.boxes = reinterpret_cast<const float4*>(s.boxes);
     v.spheres = reinterpret_cast<const float4*>(s.spheres);
     v.n_boxes = sc.n_boxes; v.n_spheres = sc.n_spheres; v.floor = sc.floor;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) collide_kernel(Scene
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
     stage<RB::N>(s, sc, nullptr, 0);
-    const SceneS sv = scene_view(s, sc);
+    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB>(s, sv);
     for (long long b = (long long)blockIdx.x * NT + threadIdx.x; b < B; b += (long long)gridDim.x * NT) {
         float qq[RB::N];
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(NT) safety_kernel(SceneArgs sc, NetArgs net, c
     using LY = NetLayout<N + 1, H, L>;
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<N>::TOTAL);
     stage<N>(s, sc, &net, LY::TOTAL);
-    const SceneS sv = scene_view(s, sc);
+    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB>(s, sv);
     float* scr = s.scratch + threadIdx.x;
     for (long long b = (long long)blockIdx.x * NT + threadIdx.x; b < B; b += (long long)gridDim.x * NT) {
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(NTC, 1) safety_kernel_tc(SceneArgs sc, NetArgs
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
     stage<N, NTC>(s, sc, &net, 0);
-    const SceneS sv = scene_view(s, sc);
+    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB, NTC>(s, sv);
     tc::Ctx<L> c;
     tc::setup<N + 1, L>(c, s.weights, net.weights);
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(NTC, 1) rollout_kernel_tc(SceneArgs sc, NetArg
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
     stage<N, NTC>(s, sc, &net, 0);
-    const SceneS sv = scene_view(s, sc);
+    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB, NTC>(s, sv);
     tc::Ctx<L> c;
     tc::setup<N + 1, L>(c, s.weights, net.weights);
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_kernel(SceneArg
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
     __shared__ int s_bad[NT];
     stage<N>(s, sc, nullptr, 0);
-    const SceneS sv = scene_view(s, sc);
+    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB>(s, sv);
     const int pts = K + 1;
     const int le = threadIdx.x / pts, k = threadIdx.x - le * pts;
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_var_kernel(Scen
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
     stage<N>(s, sc, nullptr, 0);
-    const SceneS sv = scene_view(s, sc);
+    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB>(s, sv);
     for (long long p = (long long)blockIdx.x * NT + threadIdx.x; p < P; p += (long long)gridDim.x * NT) {
         long long lo = 0, hi = E;                       // largest e with off[e] <= p
@@ -678,7 +679,7 @@ __global__ void __launch_bounds__(NT) edge_seq_kernel(SceneArgs sc, const float*
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
     stage<N>(s, sc, nullptr, 0);
-    const SceneS sv = scene_view(s, sc);
+    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB>(s, sv);
     for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < E; e += (long long)gridDim.x * NT) {
         float a[N], d[N];
@@ -715,7 +716,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
     using LY = NetLayout<N + 1, H, L>;
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<N>::TOTAL);
     stage<N>(s, sc, &net, LY::TOTAL);
-    const SceneS sv = scene_view(s, sc);
+    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB>(s, sv);
     float* scr = s.scratch + threadIdx.x;
     for (long long b = (long long)blockIdx.x * NT + threadIdx.x; b < T; b += (long long)gridDim.x * NT) {

@@ -365,6 +365,26 @@ def build_robot(name):
     )
 
 
+def link_balls(spheres, n_links):
+    """per link (-1 .. n_links-1) a ball [cx, cy, cz, R] in the link frame that contains all of the link's spheres
+    (Badoiu-Clarkson iteration towards the farthest sphere; R padded).  Used by the kernels' exact culling test."""
+    balls = []
+    for l in range(-1, n_links):
+        P = np.array([s["c"] for s in spheres if s["link"] == l], dtype=np.float64)
+        r = np.array([s["r"] for s in spheres if s["link"] == l], dtype=np.float64)
+        if len(P) == 0:
+            balls.append([0.0, 0.0, 0.0, 0.0])
+            continue
+        c = P.mean(0)
+        for it in range(1, 4001):
+            i = int(np.argmax(np.linalg.norm(P - c, axis=1) + r))
+            c = c + (P[i] - c) / (it + 1)
+        c32 = np.float32(c).astype(np.float64)
+        rad = float((np.linalg.norm(P - c32, axis=1) + r).max() * (1 + 1e-6) + 1e-6)
+        balls.append([float(c32[0]), float(c32[1]), float(c32[2]), rad])
+    return balls
+
+
 # ----------------------------------------------------------------------------- emitters
 def cfloat(x):
     s = repr(float(np.float32(x)))
@@ -408,6 +428,10 @@ def emit_c_tables(robots, path, cuda):
         if cuda:
             L.append(f"{q} int {N}_SPH_BEGIN[{nl + 2}] = {{" + ", ".join(str(v) for v in rb["sph_begin"]) + "};")
             L.append(f"{q} int {N}_ANC_MASK[{nl}] = {{" + ", ".join(str(v) for v in rb["anc_mask"]) + "};")
+            L.append(f"{q} float {N}_LINK_BALL[{nl + 1}][4] = {{")
+            for bl in rb["link_balls"]:
+                L.append("  {" + ", ".join(cfloat(v) for v in bl) + "},")
+            L.append("};")
             sp = rb["self_sphere_pairs"]
             L.append(f"#define {N}_NSELFSPH {len(sp)}")
             L.append(f"{q} int {N}_SELFSPH_I[{len(sp)}] = {{" + ", ".join(str(v[0]) for v in sp) + "};")
@@ -433,7 +457,14 @@ def emit_py_tables(robots, path):
 
 
 def main():
-    robots = [build_robot("panda"), build_robot("magician")]
+    if "--from-spec" in sys.argv:     # re-derive the kernel tables from the committed spec (no meshes needed)
+        with open(f"{ROOT}/spec/robot_models.json") as f:
+            spec = json.load(f)
+        robots = [spec["panda"], spec["magician"]]
+    else:
+        robots = [build_robot("panda"), build_robot("magician")]
+    for rb in robots:
+        rb["link_balls"] = link_balls(rb["spheres"], rb["n_links"])
     os.makedirs(f"{ROOT}/spec", exist_ok=True)
     with open(f"{ROOT}/spec/robot_models.json", "w") as f:
         json.dump({r["name"]: r for r in robots}, f, indent=1)
