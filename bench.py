@@ -272,13 +272,21 @@ def main():
         hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback"
+    # DRAM traffic of one launch from the committed ncu --set full capture of this exact command
+    # (profiles/r1_ncu_full_safety_kernel_tc.csv: dram__bytes_read.sum + dram__bytes_write.sum); only valid for the
+    # default workload at N=1, else null
+    traffic = 41.3e6 if (world == 1 and cfg_idx == 1 and B == 1 << 20) else None
+    mlp_flops = 2 * 2 * ((n + 1) * 48 + 2 * 48 * 48 + 48)
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
-                "traffic": None, "peak_source": "cbfrrt_fma_probe in this run (FP32 FMA; not in MEASURED_PEAKS.json)",
+                "traffic": traffic, "peak_source": "cbfrrt_fma_probe in this run (FP32 FMA; not in MEASURED_PEAKS.json)",
                 "flops_per_state": flops_u, "bytes_per_state": bytes_u,
+                "frac_without_mlp": (flops_u - mlp_flops) * B / kernel_s / 1e12 / fp32_peak,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "peak_source": hbm_src},
                 "kernel": "safety_kernel_tc" if world == 1 else "safety_kernel_tc (valid+u, fused exchange)",
-                "note": "MLP on tcgen05 (TF32x3); flops = algorithmic FP32 count of SURVEY 8d, so frac can exceed the CUDA-core-only bound",
+                "note": "achieved = ALGORITHMIC flops of SURVEY 8d (brute-force pair sweep + FP32 MLP) / kernel time, "
+                        "against the CUDA-core FP32 peak; the kernel runs the MLP on tcgen05 (TF32x3) and culls pairs "
+                        "exactly, so frac may exceed the CUDA-core bound; frac_without_mlp counts only the geometry + QP",
                 "kernel_ms": kernel_s * 1e3}
 
     # ---- end to end through the host-buffer C-ABI (pinned host buffers; H2D + D2H inside the timed region)
