@@ -1,4 +1,5 @@
 from .tsa import steer, steer_fused, edge_checking, edge_checking_batch, edge_checking_eps, edge_checking_reference_loop
-from .batch_tsa import steer as batch_steer, steer_fused as batch_steer_fused
+from .batch_tsa import steer as batch_steer, steer_fused as batch_steer_fused, explore_nearest, explore_nearest_each
 
-__all__ = ["steer", "steer_fused", "edge_checking", "edge_checking_batch", "edge_checking_eps", "edge_checking_reference_loop", "batch_steer", "batch_steer_fused"]
+__all__ = ["steer", "steer_fused", "edge_checking", "edge_checking_batch", "edge_checking_eps",
+           "edge_checking_reference_loop", "batch_steer", "batch_steer_fused", "explore_nearest", "explore_nearest_each"]

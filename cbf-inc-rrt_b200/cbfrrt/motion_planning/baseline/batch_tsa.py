@@ -1,4 +1,4 @@
-"""Batched steer -- mirror of motion_planning/baseline/batch_tsa.py:191-231.
+"""Batched steer and the nearest-neighbour front-end -- mirror of motion_planning/baseline/batch_tsa.py:129-145,191-231.
 
 ``steer`` keeps the reference's host loop (per-step batched CUDA ops replace its per-row pybullet loops,
 arm_dynamics.py:274,497 and batch_tsa.py:225); ``steer_fused`` runs all rows and all steps in one launch.
@@ -8,7 +8,32 @@ import time
 import numpy as np
 import torch
 
+from ... import ops
 from .tsa import _rollout
+
+
+def explore_nearest(non_terminal_states, sample_states, batch, device="cuda"):
+    """The nearest-neighbour selection of global_explore (batch_tsa.py:129-145) on the GPU (cbfrrt::knn):
+      * tree smaller than ``batch`` (or freshly sampled states): one nearest node per sample (np.argmin per row);
+      * otherwise: the ``batch`` nearest nodes of sample_states[0] (np.argsort(dists)[:batch]), the sample repeated.
+    -> (nearest_idxs int64 (B,), min_dists float32 (B,), sample_states (B, n)) with the reference's shapes.
+    Ties go to the lowest node index, as np.argmin / a stable sort do."""
+    tree = torch.as_tensor(np.asarray(non_terminal_states), dtype=torch.float32, device=device)
+    samples = torch.as_tensor(np.asarray(sample_states), dtype=torch.float32, device=device).reshape(-1, tree.shape[1])
+    if tree.shape[0] < batch:
+        idx, dist = ops.knn(samples, tree, 1)
+        return idx[:, 0].cpu().numpy().astype(np.int64), dist[:, 0].cpu().numpy(), np.asarray(sample_states)
+    idx, dist = ops.knn(samples[:1], tree, int(batch))
+    rep = np.array([np.asarray(sample_states)[0] for _ in range(batch)])
+    return idx[0].cpu().numpy().astype(np.int64), dist[0].cpu().numpy(), rep
+
+
+def explore_nearest_each(non_terminal_states, sample_states, device="cuda"):
+    """first branch of global_explore (batch_tsa.py:129-137): one nearest node for every freshly sampled state"""
+    tree = torch.as_tensor(np.asarray(non_terminal_states), dtype=torch.float32, device=device)
+    samples = torch.as_tensor(np.asarray(sample_states), dtype=torch.float32, device=device).reshape(-1, tree.shape[1])
+    idx, dist = ops.knn(samples, tree, 1)
+    return idx[:, 0].cpu().numpy().astype(np.int64), dist[:, 0].cpu().numpy()
 
 
 @torch.no_grad()

@@ -370,6 +370,37 @@ def edge_validity_var(q_from: Tensor, q_to: Tensor, n_interp: Tensor, boxes: Ten
     return valid, first_bad
 
 
+@torch.library.custom_op("cbfrrt::knn", mutates_args=(), device_types="cuda")
+def knn(queries: Tensor, tree: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """queries f32[M,n], tree f32[N,n] -> idx i32[M,k], dist f32[M,k]: k nearest rows, ascending (distance, row)"""
+    queries, tree = _f32c(queries), _f32c(tree)
+    if queries.dim() != 2 or tree.dim() != 2 or queries.shape[1] != tree.shape[1]:
+        raise ValueError("knn: queries [M,n] and tree [N,n] must share n")
+    M, n = queries.shape
+    idx = torch.empty((M, k), dtype=torch.int32, device=queries.device)
+    dist = torch.empty((M, k), dtype=torch.float32, device=queries.device)
+    ws = torch.empty(max(1, 2 * M), dtype=torch.int64, device=queries.device)
+    with torch.cuda.device(queries.device):
+        check(lib.cbfrrt_knn(n, _ptr(queries), _ptr(tree), M, tree.shape[0], k, _ptr(idx), _ptr(dist), _ptr(ws), _stream()),
+              "cbfrrt_knn")
+    del ws
+    return idx, dist
+
+
+@torch.library.custom_op("cbfrrt::radius_mask", mutates_args=(), device_types="cuda")
+def radius_mask(queries: Tensor, points: Tensor, radius: float) -> Tensor:
+    """within u8[M,N] = ||queries[m] - points[j]|| <= radius   (bit_star.py:196-216)"""
+    queries, points = _f32c(queries), _f32c(points)
+    if queries.dim() != 2 or points.dim() != 2 or queries.shape[1] != points.shape[1]:
+        raise ValueError("radius_mask: queries [M,n] and points [N,n] must share n")
+    M, n = queries.shape
+    out = torch.empty((M, points.shape[0]), dtype=torch.uint8, device=queries.device)
+    with torch.cuda.device(queries.device):
+        check(lib.cbfrrt_radius_mask(n, _ptr(queries), _ptr(points), M, points.shape[0], radius, _ptr(out), _stream()),
+              "cbfrrt_radius_mask")
+    return out
+
+
 @torch.library.custom_op("cbfrrt::rollout", mutates_args=(), device_types="cuda")
 def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, stuck_lag: int, stuck_after: int,
             stuck_eps: float, want_traj: bool, keep_going: bool, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor, K: Tensor,

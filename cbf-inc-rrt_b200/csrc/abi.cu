@@ -1,6 +1,7 @@
 // abi.cu -- the device-pointer C-ABI of libcbfrrt (include/cbfrrt.h): argument validation + dispatch to the
 // launchers.  Kernels live in kernels.cuh; the per-robot instantiations of the big ones are compiled in k_*.cu.
 #include "kernels.cuh"
+#include "knn.cuh"
 
 namespace cbfrrt {
 std::atomic<long long> g_launches{0};
@@ -201,6 +202,49 @@ int cbfrrt_edge_validity_var(int robot, const cbfrrt_scene* scene, const float* 
     const long long* off = reinterpret_cast<const long long*>(point_offsets);
     return robot == CBFRRT_ROBOT_PANDA ? launch_edges_var_panda(sc, q_from, q_to, E, off, n_points, thr_soft, thr_hard, valid, first_bad, st)
                                        : launch_edges_var_magician(sc, q_from, q_to, E, off, n_points, thr_soft, thr_hard, valid, first_bad, st);
+}
+
+int cbfrrt_knn(int n, const float* queries, const float* tree, int64_t M, int64_t N_tree, int32_t k, int32_t* idx,
+               float* dist, void* workspace, void* stream) {
+    if (M < 0 || N_tree < 0 || k < 1 || !queries || !tree || !idx || !dist || !workspace) return CBFRRT_ERR_BAD_SHAPE;
+    if (n < 1 || n > 8 || N_tree > 0x7fffffffll) return CBFRRT_ERR_UNSUPPORTED;
+    if (M == 0) return CBFRRT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(workspace);
+    unsigned long long* lower = best + M;
+    const dim3 grid((unsigned)((N_tree + knn::CHUNK - 1) / knn::CHUNK), (unsigned)((M + knn::QT - 1) / knn::QT));
+    for (int r = 0; r < k; ++r) {
+        const cudaError_t me = cudaMemsetAsync(best, 0xff, (size_t)M * 8, st);
+        if (me != cudaSuccess) { g_last_cuda = (int)me; return CBFRRT_ERR_CUDA; }
+        if (N_tree > 0) {
+            const unsigned long long* lo = r ? lower : nullptr;
+            switch (n) {
+#define CBF_NN_CASE(NN) case NN: knn::nn_kernel<NN><<<grid, knn::QT, 0, st>>>(queries, tree, M, N_tree, lo, best); break;
+                CBF_NN_CASE(1) CBF_NN_CASE(2) CBF_NN_CASE(3) CBF_NN_CASE(4) CBF_NN_CASE(5) CBF_NN_CASE(6) CBF_NN_CASE(7) CBF_NN_CASE(8)
+#undef CBF_NN_CASE
+            }
+            if (finish_launch()) return CBFRRT_ERR_CUDA;
+        }
+        knn::nn_finish<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(best, lower, M, idx + r, dist + r, k);
+        if (finish_launch()) return CBFRRT_ERR_CUDA;
+    }
+    return CBFRRT_OK;
+}
+
+int cbfrrt_radius_mask(int n, const float* queries, const float* set, int64_t M, int64_t N_set, float radius,
+                       uint8_t* within, void* stream) {
+    if (M < 0 || N_set < 0 || !queries || !set || !within) return CBFRRT_ERR_BAD_SHAPE;
+    if (n < 1 || n > 8) return CBFRRT_ERR_UNSUPPORTED;
+    if (M == 0 || N_set == 0) return CBFRRT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = (M * N_set + 255) / 256;
+    const int grid = (int)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
+    switch (n) {
+#define CBF_RAD_CASE(NN) case NN: knn::radius_kernel<NN><<<grid, 256, 0, st>>>(queries, set, M, N_set, radius, within); break;
+        CBF_RAD_CASE(1) CBF_RAD_CASE(2) CBF_RAD_CASE(3) CBF_RAD_CASE(4) CBF_RAD_CASE(5) CBF_RAD_CASE(6) CBF_RAD_CASE(7) CBF_RAD_CASE(8)
+#undef CBF_RAD_CASE
+    }
+    return finish_launch();
 }
 
 int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* net, const float* q0, int64_t T,

@@ -203,6 +203,19 @@ int cbfrrt_edge_validity_var(int robot, const cbfrrt_scene *scene, const float *
                              const int64_t *point_offsets, int64_t n_points, float thr_soft, float thr_hard,
                              uint8_t *valid, int32_t *first_bad, void *stream);
 
+/* ---- planner front-end: nearest / k-nearest / radius queries in configuration space -------------------------
+ * Replaces the numpy distance matrices of the callers of the path: batch_tsa.global_explore
+ * (motion_planning/baseline/batch_tsa.py:135-145: np.argmin / np.argsort[:batch] of ||sample - node||),
+ * tsa.global_explore (tsa.py:151-153) and BITStarPlanner.expand_vertex (bit_star.py:196-216: nodes within r).
+ *   queries [M, n], tree [N_tree, n] (device, fp32, 1 <= n <= 8) -> idx [M, k] int32, dist [M, k] fp32: the k nearest
+ *   rows in ascending (squared distance, row) order -- ties to the lowest row like np.argmin / a stable argsort;
+ *   entries beyond N_tree are idx -1 / dist +inf.  workspace: 16 * M bytes of device memory.  k rounds of 2 launches.
+ *   radius_mask: within [M, N_set] uint8 = (||q_m - s_j|| <= radius). */
+int cbfrrt_knn(int n, const float *queries, const float *tree, int64_t M, int64_t N_tree, int32_t k, int32_t *idx,
+               float *dist, void *workspace, void *stream);
+int cbfrrt_radius_mask(int n, const float *queries, const float *set, int64_t M, int64_t N_set, float radius,
+                       uint8_t *within, void *stream);
+
 /* ---- K9 closed-loop rollouts ------------------------------------------------------------------------------
  * Replaces the steer loop (motion_planning/baseline/tsa.py:217-269, batch_tsa.py:191-231) built on
  * ArmDynamics.closed_loop_dynamics (arm_dynamics.py:474-523): control every ctrl_every steps, Euler every

@@ -186,6 +186,22 @@ def edge_validity_var(robot, q_from, q_to, n_interp, boxes, spheres=None, floor=
     return valid, first_bad
 
 
+def knn(queries, tree, k):
+    queries, tree = _f(queries), _f(tree)
+    M, n = queries.shape
+    idx, dist = np.empty((M, k), np.int32), np.empty((M, k), np.float32)
+    lib().oracle_knn(n, _p(queries), _p(tree), C.c_long(M), C.c_long(tree.shape[0]), int(k), _p(idx), _p(dist))
+    return idx, dist
+
+
+def radius_mask(queries, points, radius):
+    queries, points = _f(queries), _f(points)
+    M, n = queries.shape
+    out = np.empty((M, points.shape[0]), np.uint8)
+    lib().oracle_radius_mask(n, _p(queries), _p(points), C.c_long(M), C.c_long(points.shape[0]), C.c_float(radius), _p(out))
+    return out
+
+
 def rollout(robot, q0, goal, steps, ctrl_every, dt, boxes, spheres, floor, weights, hidden, layers, K, u_lo, u_hi,
             thr_soft, thr_hard, lam, penalty, stuck_lag=0, stuck_after=10, stuck_eps=0.1, want_traj=False, keep_going=False):
     q0 = _f(q0)

@@ -780,6 +780,39 @@ API int oracle_edge_validity_var(int robot, int n_boxes, const float *boxes, int
     return 0;
 }
 
+/* planner front-end (batch_tsa.py:135-145, tsa.py:151-153, bit_star.py:196-216): k nearest tree rows per query in
+ * ascending (squared distance, row) order; contract: d_k = q_k - t_k, dsq = fma chain starting from d_0*d_0 */
+static float knn_dsq(int n, const float *q, const float *t) {
+    float d = q[0] - t[0];
+    float acc = d * d;
+    for (int k = 1; k < n; ++k) { d = q[k] - t[k]; acc = fmaf(d, d, acc); }
+    return acc;
+}
+API int oracle_knn(int n, const float *queries, const float *tree, long M, long Nt, int k, int *idx, float *dist) {
+    for (long m = 0; m < M; ++m) {
+        float prev_d = -1.0f;
+        long prev_i = -1;
+        for (int r = 0; r < k; ++r) {
+            float bd = 0.0f;
+            long bi = -1;
+            for (long j = 0; j < Nt; ++j) {
+                float d = knn_dsq(n, queries + m * n, tree + j * n);
+                int after_prev = (d > prev_d) || (d == prev_d && j > prev_i);
+                if (after_prev && (bi < 0 || d < bd)) { bd = d; bi = j; }
+            }
+            idx[m * k + r] = (int)bi;
+            dist[m * k + r] = bi < 0 ? INFINITY : sqrtf(bd);
+            if (bi < 0) { prev_d = INFINITY; prev_i = Nt; } else { prev_d = bd; prev_i = bi; }
+        }
+    }
+    return 0;
+}
+API int oracle_radius_mask(int n, const float *queries, const float *set, long M, long Ns, float radius, uint8_t *within) {
+    for (long m = 0; m < M; ++m)
+        for (long j = 0; j < Ns; ++j) within[m * Ns + j] = sqrtf(knn_dsq(n, queries + m * n, set + j * n)) <= radius;
+    return 0;
+}
+
 /* closed-loop rollout = the steer loop (tsa.py:217-269; eval_obs_only_env.py:121-148):
  *   every ctrl_every-th step: u = CBF-QP(x);  every step: q' = q + u*dt (arm_dynamics.py:497-510), then the
  *   unsafe check on q' (tsa.py:251: a colliding state is NOT appended, no_collision = False, loop ends);

@@ -63,6 +63,13 @@ def install(monkeypatch):
                                           thr_hard)
         return torch.from_numpy(v), torch.from_numpy(f)
 
+    def knn(queries, tree, k):
+        i, d = c_oracle.knn(_np(queries), _np(tree), k)
+        return torch.from_numpy(i), torch.from_numpy(d)
+
+    def radius_mask(queries, points, radius):
+        return torch.from_numpy(c_oracle.radius_mask(_np(queries), _np(points), radius))
+
     def rollout(q0, goal, steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, want_traj, keep_going, boxes, spheres, floor, grid,
                 weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id, hidden, layers):
         b, s = _scene(boxes, spheres)
@@ -81,5 +88,5 @@ def install(monkeypatch):
         return torch.from_numpy(o["safe"]), torch.from_numpy(o["u"])
 
     for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp, qp_multi=qp_multi,
-                         edge_validity=edge_validity, edge_validity_var=edge_validity_var, rollout=rollout, valid_control=valid_control).items():
+                         edge_validity=edge_validity, edge_validity_var=edge_validity_var, knn=knn, radius_mask=radius_mask, rollout=rollout, valid_control=valid_control).items():
         monkeypatch.setattr(ops, name, fn)

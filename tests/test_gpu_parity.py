@@ -329,6 +329,23 @@ def test_edge_validity_per_edge_lengths_bit_exact(coracle, robot):
     assert torch.equal(v2, v3) and torch.equal(f2, f3)
 
 
+@pytest.mark.parametrize("n,M,N,k", [(7, 50, 20000, 1), (4, 300, 5000, 1), (7, 1, 30000, 50), (7, 3, 40, 64), (3, 129, 513, 5)])
+def test_knn_bit_exact(coracle, n, M, N, k):
+    """cbfrrt::knn (planner front-end, batch_tsa.py:135-145) vs the oracle: indices and distances bit-identical"""
+    from cbfrrt import ops
+    rng = np.random.default_rng(n * 1000 + M)
+    tree = rng.uniform(-2, 2, size=(N, n)).astype(np.float32)
+    q = rng.uniform(-2, 2, size=(M, n)).astype(np.float32)
+    tree[N // 2] = tree[3]
+    q[0] = tree[3]                                  # exact tie between rows 3 and N//2
+    io, do = coracle.knn(q, tree, k)
+    i, d = ops.knn(_t(q), _t(tree), k)
+    assert np.array_equal(i.cpu().numpy(), io) and np.array_equal(d.cpu().numpy(), do)
+    assert io[0, 0] == 3
+    w = ops.radius_mask(_t(q), _t(tree[:2000]), 1.5)
+    assert np.array_equal(w.cpu().numpy(), coracle.radius_mask(q, tree[:2000], 1.5))
+
+
 def test_edge_validity_equals_pointwise_safe_mask():
     """size-independent property: an edge is valid iff every interpolated configuration is safe (tsa.py:272-286)."""
     from cbfrrt import ops, workloads as W

@@ -216,6 +216,26 @@ def test_edge_checking_reference_loop_equals_batched(stack):
     assert agree >= 9 and 0 < n_valid < 10
 
 
+def test_explore_nearest_matches_reference_numpy(stack):
+    """explore_nearest == the three numpy branches of global_explore (batch_tsa.py:129-145)"""
+    env, robot, dyn, ctrl = stack("panda")
+    from cbfrrt.motion_planning.baseline import explore_nearest
+    rng = np.random.default_rng(0)
+    batch = 50
+    samples = dyn.sample_state_space(batch).numpy()
+    for n_tree in (7, 400):
+        tree = rng.uniform(-1, 1, size=(n_tree, 7)).astype(np.float32)
+        idxs, dists, ss = explore_nearest(tree, samples, batch, device="cpu")
+        if n_tree < batch:
+            d = np.linalg.norm(samples[:, None, :] - tree[None, :, :], axis=-1)
+            assert np.array_equal(idxs, np.argmin(d, axis=1)) and np.allclose(dists, d.min(1), rtol=1e-5)
+            assert ss.shape == samples.shape
+        else:
+            d = np.linalg.norm(tree - samples[0], axis=-1)
+            assert np.array_equal(idxs, np.argsort(d, kind="stable")[:batch]) and np.allclose(dists, np.sort(d)[:batch], rtol=1e-5)
+            assert ss.shape == (batch, 7) and (ss == samples[0]).all()
+
+
 def test_basic_robot_kinematics(stack, models):
     env, robot, dyn, ctrl = stack("panda")
     from oracle import oracle_f64 as o

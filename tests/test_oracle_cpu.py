@@ -178,3 +178,26 @@ def test_qp_single_reference_outside_box(coracle):
     np.testing.assert_allclose(r, rm[:, 0], atol=1e-6)
     for b in range(B):
         assert qp_kkt_residual(a[b:b + 1], c[b:b + 1], ur[b], lo, hi, p, u[b]) <= 1e-3
+
+
+def test_knn_oracle_matches_numpy(coracle):
+    """oracle_knn against the reference's numpy expressions (batch_tsa.py:135-145): argmin per row, argsort[:k]"""
+    rng = np.random.default_rng(3)
+    for n in (4, 7):
+        tree = rng.uniform(-2, 2, size=(700, n)).astype(np.float32)
+        samples = rng.uniform(-2, 2, size=(40, n)).astype(np.float32)
+        tree[100] = tree[7]                       # duplicate node: ties go to the lowest index
+        samples[0] = tree[7]
+        d = np.linalg.norm(samples[:, None, :].astype(np.float64) - tree[None, :, :], axis=-1)
+        idx, dist = coracle.knn(samples, tree, 1)
+        assert np.array_equal(idx[:, 0], np.argmin(d, axis=1)) and idx[0, 0] == 7
+        np.testing.assert_allclose(dist[:, 0], d.min(1), rtol=2e-6, atol=1e-7)
+        k = 50
+        idx, dist = coracle.knn(samples[1:2], tree, k)
+        order = np.argsort(d[1], kind="stable")[:k]
+        assert np.array_equal(idx[0], order)
+        np.testing.assert_allclose(dist[0], np.sort(d[1])[:k], rtol=2e-6)
+        idx, dist = coracle.knn(samples[:3], tree[:5], 8)          # k larger than the tree
+        assert (idx[:, 5:] == -1).all() and np.isinf(dist[:, 5:]).all() and (np.sort(idx[:, :5], 1) == np.arange(5)).all()
+        within = coracle.radius_mask(samples, tree, 1.3)
+        assert np.mean(within.astype(bool) == (d <= 1.3)) > 0.9999   # fp32 vs fp64 at the boundary
