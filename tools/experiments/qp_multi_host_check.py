@@ -6,7 +6,7 @@ def run(n,S,p,B=20000,seed=None,maxit=100,tol=1e-9):
     lo,hi=-np.ones(n,np.float32),np.ones(n,np.float32)
     a=rng.normal(size=(B,S,n)).astype(np.float32); c=rng.normal(scale=.8,size=(B,S)).astype(np.float32); ur=rng.uniform(-1.5,1.5,size=(B,n)).astype(np.float32)
     open('/tmp/qpm_in.bin','wb').write(a.tobytes()+c.tobytes()+ur.tobytes())
-    subprocess.check_call(['tools/scratch/qpm_host',str(n),str(S),str(B),str(p),str(maxit),str(tol),'/tmp/qpm_in.bin','/tmp/qpm_out.bin'])
+    subprocess.check_call(['tools/experiments/qp_multi_host',str(n),str(S),str(B),str(p),str(maxit),str(tol),'/tmp/qpm_in.bin','/tmp/qpm_out.bin'])
     raw=open('/tmp/qpm_out.bin','rb').read()
     u=np.frombuffer(raw[:B*n*4],np.float32).reshape(B,n); r=np.frombuffer(raw[B*n*4:B*n*4+B*S*4],np.float32).reshape(B,S); it=np.frombuffer(raw[B*n*4+B*S*4:],np.int32)
     uo,ro,ito=c_oracle.qp_multi(a,c,ur,lo,hi,p,want_iters=True)
