@@ -431,6 +431,20 @@ def test_host_buffer_api_matches_device_api():
     ops.safety_filter_host("magician", w["q"], w["boxes"], w["spheres"], True, w["weights"], 48, 2, goal, w["K"],
                            w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], out)
     assert np.array_equal(out["safe"], dev[0].cpu().numpy()) and np.array_equal(out["u"], dev[1].cpu().numpy())
+    # the library keeps scene / network resident between calls: a changed scene (same sizes) and a changed network
+    # must be re-uploaded, and going back must work too
+    boxes2 = w["boxes"].copy()
+    boxes2[:, 2] += 0.07
+    sd2, _ = W.make_state_dict(n, seed=9)
+    w2 = W.pack_weights_np(sd2, n)
+    b8b, s4b, grb = _scene(boxes2, w["spheres"])
+    net2 = ops.pack_weights(sd2, n, 48, 2, device="cuda")
+    for bx, b8_, wt, net_ in ((boxes2, b8b, w2, net2), (w["boxes"], b8, w["weights"], _net(w)), (boxes2, b8b, w["weights"], _net(w))):
+        dev = ops.valid_control(_t(w["q"]), _t(w["goal"]), b8_, s4, 1, gr, net_, _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]),
+                                w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], 1, 48, 2)
+        ops.safety_filter_host("magician", w["q"], bx, w["spheres"], True, wt, 48, 2, w["goal"], w["K"],
+                               w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], out)
+        assert np.array_equal(out["safe"], dev[0].cpu().numpy()) and np.array_equal(out["u"], dev[1].cpu().numpy())
 
 
 def test_full_size_config1_properties(coracle):
