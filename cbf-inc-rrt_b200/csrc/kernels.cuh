@@ -85,13 +85,13 @@ struct Smem {
     float* scratch;
 };
 __host__ __device__ inline size_t smem_floats(int n_boxes, int n_spheres, int w_floats, int p_floats, int scr_floats) {
-    return 4 + 12 + (size_t)8 * n_boxes + (size_t)4 * n_spheres + w_floats + p_floats + scr_floats;
+    return 32 + (size_t)8 * n_boxes + (size_t)4 * n_spheres + w_floats + p_floats + scr_floats;
 }
 __device__ __forceinline__ Smem carve(float* base, int n_boxes, int n_spheres, int w_floats, int p_floats) {
     Smem s;
     s.bar = reinterpret_cast<uint64_t*>(base);
-    s.red = base + 4;
-    s.boxes = base + 16;
+    s.red = base + 4;          // one float per warp of the CTA (<= 28 warps)
+    s.boxes = base + 32;
     s.spheres = s.boxes + 8 * n_boxes;
     s.weights = s.spheres + 4 * n_spheres;
     s.params = s.weights + w_floats;
@@ -394,31 +394,34 @@ struct RolloutArgs {
 // tensor cores (mlp_tc.cuh).  One CTA of 384 threads per SM = 3 tile groups sharing the staged weights; all 128
 // threads of a group take part in every tile of that group (idle rows are masked), because the MMAs, the TMEM
 // traffic and the barriers are group-wide.
-constexpr int NTC = tc::NT_TC;
+// tile groups per CTA: 4 (512 threads, 128 registers) when the geometry stage works out of shared memory, 3 (384
+// threads) for the broad-phase-grid variants, which need the L1 capacity of a fourth A_lo tile for the grid look-ups
+constexpr int tc_groups(bool grid) { return grid ? 3 : 4; }
 
-template <int N, int L>
-__device__ __forceinline__ void filter_tile_tc(tc::Ctx<L>& c, const float* prm, const float (&q)[N], float o,
+template <int N, int L, int GG>
+__device__ __forceinline__ void filter_tile_tc(tc::Ctx<L, GG>& c, const float* prm, const float (&q)[N], float o,
                                                const float (&dodq)[N], const float (&goal)[N], bool goal_is_uref,
                                                float lam, float penalty, float& h, float (&J)[N], float (&u)[N], float& r) {
     float x[N + 1], jac[N + 1];
 #pragma unroll
     for (int k = 0; k < N; ++k) x[k] = q[k];
     x[N] = o;
-    tc::mlp_h_jac<N + 1, L>(c, x, h, jac);
+    tc::mlp_h_jac<N + 1, L, GG>(c, x, h, jac);
     cbf_filter_post<N>(prm, q, dodq, goal, goal_is_uref, lam, penalty, h, jac, J, u, r);
 }
 
 template <int N, int L>
-__global__ void __launch_bounds__(NTC, 1) filter_kernel_tc(NetArgs net, const float* __restrict__ datax, long long B,
-                                                           FilterOutPtrs out) {
+__global__ void __launch_bounds__(4 * tc::M_TILE, 1) filter_kernel_tc(NetArgs net, const float* __restrict__ datax,
+                                                                      long long B, FilterOutPtrs out) {
+    constexpr int GG = 4, NTC = GG * tc::M_TILE;
     extern __shared__ __align__(16) float smem_raw[];
-    const Smem s = carve(smem_raw, 0, 0, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
+    const Smem s = carve(smem_raw, 0, 0, tc::Layout<L, GG>::TOTAL, ParamLayout<N>::TOTAL);
     SceneArgs none{nullptr, nullptr, 0, 0, 0, nullptr};
     stage<N, NTC>(s, none, &net, 0);
-    tc::Ctx<L> c;
-    tc::setup<N + 1, L>(c, s.weights, net.weights);
+    tc::Ctx<L, GG> c;
+    tc::setup<N + 1, L, GG>(c, s.weights, net.weights);
     const long long n_tiles = (B + tc::M_TILE - 1) / tc::M_TILE;
-    for (long long tile = (long long)blockIdx.x * tc::G + c.g; tile < n_tiles; tile += (long long)gridDim.x * tc::G) {
+    for (long long tile = (long long)blockIdx.x * GG + c.g; tile < n_tiles; tile += (long long)gridDim.x * GG) {
         const long long b = tile * tc::M_TILE + c.t;
         const bool active = b < B;
         float q[N], dodq[N], g[N], J[N], u[N], h, r, o = 0.f;
@@ -431,26 +434,27 @@ __global__ void __launch_bounds__(NTC, 1) filter_kernel_tc(NetArgs net, const fl
             o = __ldg(d + N);
             load_goal<N>(net, b, g);
         }
-        filter_tile_tc<N, L>(c, s.params, q, o, dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
+        filter_tile_tc<N, L, GG>(c, s.params, q, o, dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
         if (active) write_filter<N>(out, b, h, J, u, r);
     }
-    tc::teardown<L>(c);
+    tc::teardown<L, GG>(c);
 }
 
 template <class RB, int L, bool GRID>
-__global__ void __launch_bounds__(NTC, 1) safety_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q,
+__global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) safety_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q,
                                                            long long q_stride, long long B, float thr_soft, float thr_hard,
                                                            CollideOutPtrs cout, FilterOutPtrs fout, PeerOut po) {
     constexpr int N = RB::N;
+    constexpr int GG = tc_groups(GRID), NTC = GG * tc::M_TILE;
     extern __shared__ __align__(16) float smem_raw[];
-    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
+    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L, GG>::TOTAL, ParamLayout<N>::TOTAL);
     stage<N, NTC>(s, sc, &net, 0);
     const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB, NTC>(s, sv);
-    tc::Ctx<L> c;
-    tc::setup<N + 1, L>(c, s.weights, net.weights);
+    tc::Ctx<L, GG> c;
+    tc::setup<N + 1, L, GG>(c, s.weights, net.weights);
     const long long n_tiles = (B + tc::M_TILE - 1) / tc::M_TILE;
-    for (long long tile = (long long)blockIdx.x * tc::G + c.g; tile < n_tiles; tile += (long long)gridDim.x * tc::G) {
+    for (long long tile = (long long)blockIdx.x * GG + c.g; tile < n_tiles; tile += (long long)gridDim.x * GG) {
         const long long b = tile * tc::M_TILE + c.t;
         const bool active = b < B;
         float qq[N], g[N], J[N], u[N], h, r;
@@ -467,32 +471,33 @@ __global__ void __launch_bounds__(NTC, 1) safety_kernel_tc(SceneArgs sc, NetArgs
             write_collide<RB>(cout, b, qq, cr, thr_soft, thr_hard);
             load_goal<N>(net, b, g);
         }
-        filter_tile_tc<N, L>(c, s.params, qq, cr.o, cr.dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
+        filter_tile_tc<N, L, GG>(c, s.params, qq, cr.o, cr.dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
         if (active) {
             write_filter<N>(fout, b, h, J, u, r);
             if (po.n) write_peers<N>(po, b, cr.self_ok && (cr.soft_min > thr_soft) && !(cr.hard_min <= thr_hard), u);
         }
     }
-    tc::teardown<L>(c);
+    tc::teardown<L, GG>(c);
 }
 
 // steer loop on the tensor-core path: the time loop is uniform over a tile group (a finished trajectory idles,
 // it does not leave), because the MLP rounds are group-wide; the group exits early once all its rows are finished.
 template <class RB, int L, bool GRID>
-__global__ void __launch_bounds__(NTC, 1) rollout_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q0,
+__global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) rollout_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q0,
                                                             long long T, RolloutArgs ra, float thr_soft, float thr_hard,
                                                             float* __restrict__ q_final, uint8_t* __restrict__ alive,
                                                             int* __restrict__ steps_done, float* __restrict__ traj) {
     constexpr int N = RB::N;
+    constexpr int GG = tc_groups(GRID), NTC = GG * tc::M_TILE;
     extern __shared__ __align__(16) float smem_raw[];
-    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L>::TOTAL, ParamLayout<N>::TOTAL);
+    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L, GG>::TOTAL, ParamLayout<N>::TOTAL);
     stage<N, NTC>(s, sc, &net, 0);
     const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB, NTC>(s, sv);
-    tc::Ctx<L> c;
-    tc::setup<N + 1, L>(c, s.weights, net.weights);
+    tc::Ctx<L, GG> c;
+    tc::setup<N + 1, L, GG>(c, s.weights, net.weights);
     const long long n_tiles = (T + tc::M_TILE - 1) / tc::M_TILE;
-    for (long long tile = (long long)blockIdx.x * tc::G + c.g; tile < n_tiles; tile += (long long)gridDim.x * tc::G) {
+    for (long long tile = (long long)blockIdx.x * GG + c.g; tile < n_tiles; tile += (long long)gridDim.x * GG) {
         const long long b = tile * tc::M_TILE + c.t;
         const bool active = b < T;
         float q[N], qn[N], g[N], u[N], dodq[N], o = 0.f;
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(NTC, 1) rollout_kernel_tc(SceneArgs sc, NetArg
             if (t % ra.ctrl_every == 0) {
                 if (!tc::group_any(c.g, !finished)) break;
                 float J[N], h, r, un[N];
-                filter_tile_tc<N, L>(c, s.params, q, o, dodq, g, false, net.lam, net.penalty, h, J, un, r);
+                filter_tile_tc<N, L, GG>(c, s.params, q, o, dodq, g, false, net.lam, net.penalty, h, J, un, r);
                 if (!finished) {
 #pragma unroll
                     for (int k = 0; k < N; ++k) u[k] = un[k];
@@ -556,7 +561,7 @@ __global__ void __launch_bounds__(NTC, 1) rollout_kernel_tc(SceneArgs sc, NetArg
             steps_done[b] = done;
         }
     }
-    tc::teardown<L>(c);
+    tc::teardown<L, GG>(c);
 }
 
 // edge validity: one thread per (edge, point); point k in [0, K] (K = end point).  A CTA owns EPB whole edges
@@ -853,9 +858,12 @@ static int grid_for(Kern kern, size_t smem, long long tiles) {
     return (int)g;
 }
 
-// tensor-core kernels: one 384-thread CTA per SM (it owns all 512 TMEM columns), 3 tiles of 128 rows per pass
+// tensor-core kernels: one 512-thread CTA per SM (it owns all 512 TMEM columns), 4 tiles of 128 rows per pass.
+// Weights (84 KB) + the groups' A_lo tiles (96 KB) leave ~45 KB for the scene: scenes beyond that (> ~900 obstacles)
+// take the FP32-FMA kernels.
+constexpr size_t TC_SMEM_MAX = 227 * 1024;
 template <class Kern>
-static int grid_for_tc(Kern kern, size_t smem, long long rows) {
+static int grid_for_tc(Kern kern, size_t smem, long long rows, int groups) {
     {
         std::lock_guard<std::mutex> lock(g_cfg_mu);
         const auto key = std::make_pair(reinterpret_cast<const void*>(kern), smem);
@@ -866,7 +874,7 @@ static int grid_for_tc(Kern kern, size_t smem, long long rows) {
         }
     }
     const long long tiles = (rows + tc::M_TILE - 1) / tc::M_TILE;
-    long long g = (tiles + tc::G - 1) / tc::G;
+    long long g = (tiles + groups - 1) / groups;
     if (g > num_sms()) g = num_sms();
     return (int)(g < 1 ? 1 : g);
 }
@@ -958,11 +966,11 @@ inline bool force_tc() { use_tc(); const char* e = getenv("CBFRRT_MLP"); return 
 template <int N>
 static int launch_filter(const NetArgs& net, const float* datax, long long B, const FilterOutPtrs& out, cudaStream_t st) {
     if (use_tc() && (B > SMALL_BATCH || force_tc())) {
-        const size_t smem = 4 * smem_floats(0, 0, tc::Layout<2>::TOTAL, ParamLayout<N>::TOTAL, 0);
+        const size_t smem = 4 * smem_floats(0, 0, tc::Layout<2, 4>::TOTAL, ParamLayout<N>::TOTAL, 0);
         auto k = filter_kernel_tc<N, 2>;
-        const int grid = grid_for_tc(k, smem, B);
+        const int grid = grid_for_tc(k, smem, B, 4);
         if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NTC, smem, st>>>(net, datax, B, out);
+        k<<<grid, 4 * tc::M_TILE, smem, st>>>(net, datax, B, out);
         return finish_launch();
     }
     using LY = NetLayout<N + 1, 48, 2>;
@@ -977,12 +985,15 @@ static int launch_filter(const NetArgs& net, const float* datax, long long B, co
 template <class RB>
 static int launch_safety(const SceneArgs& sc, const NetArgs& net, const float* q, long long qs, long long B, float ts,
                          float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, const PeerOut& po, cudaStream_t st) {
-    if (use_tc() && (B > SMALL_BATCH || force_tc())) {
-        const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
+    const int gg = tc_groups(sc.grid != nullptr);
+    const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, sc.grid ? tc::Layout<2, 3>::TOTAL : tc::Layout<2, 4>::TOTAL,
+                                           ParamLayout<RB::N>::TOTAL, 0);
+    if (use_tc() && (B > SMALL_BATCH || force_tc()) && smem_tc <= TC_SMEM_MAX) {
+        const size_t smem = smem_tc;
         auto k = sc.grid ? safety_kernel_tc<RB, 2, true> : safety_kernel_tc<RB, 2, false>;
-        const int grid = grid_for_tc(k, smem, B);
+        const int grid = grid_for_tc(k, smem, B, gg);
         if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NTC, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo, po);
+        k<<<grid, gg * tc::M_TILE, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo, po);
         return finish_launch();
     }
     using LY = NetLayout<RB::N + 1, 48, 2>;
@@ -1034,12 +1045,15 @@ static int launch_edges_var(const SceneArgs& sc, const float* qf, const float* q
 template <class RB>
 static int launch_rollout(const SceneArgs& sc, const NetArgs& net, const float* q0, long long T, const RolloutArgs& ra,
                           float ts, float th, float* qf, uint8_t* alive, int* done, float* traj, cudaStream_t st) {
-    if (use_tc() && (T > SMALL_BATCH || force_tc())) {
-        const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
+    const int gg = tc_groups(sc.grid != nullptr);
+    const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, sc.grid ? tc::Layout<2, 3>::TOTAL : tc::Layout<2, 4>::TOTAL,
+                                           ParamLayout<RB::N>::TOTAL, 0);
+    if (use_tc() && (T > SMALL_BATCH || force_tc()) && smem_tc <= TC_SMEM_MAX) {
+        const size_t smem = smem_tc;
         auto k = sc.grid ? rollout_kernel_tc<RB, 2, true> : rollout_kernel_tc<RB, 2, false>;
-        const int grid = grid_for_tc(k, smem, T);
+        const int grid = grid_for_tc(k, smem, T, gg);
         if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NTC, smem, st>>>(sc, net, q0, T, ra, ts, th, qf, alive, done, traj);
+        k<<<grid, gg * tc::M_TILE, smem, st>>>(sc, net, q0, T, ra, ts, th, qf, alive, done, traj);
         return finish_launch();
     }
     using LY = NetLayout<RB::N + 1, 48, 2>;

@@ -1,12 +1,16 @@
 // mlp_tc.cuh -- the barrier MLP (value + exact reverse-mode Jacobian) on the 5th-generation tensor cores.
 //
 // A group of 128 threads (4 warps) owns a tile of 128 states = the M dimension of one tcgen05.mma; a CTA runs
-// G = 3 such groups that share the staged weights (12 warps per SM, one CTA per SM, 480 of the 512 TMEM columns).
+// GG such groups that share the staged weights, one CTA per SM, 128 TMEM columns per tile.  GG = 4 (16 warps per SM at
+// 128 registers) for the kernels whose geometry stage lives in shared memory; GG = 3 for the broad-phase-grid
+// variants, which need the L1 capacity that a fourth A_lo tile (24 KB) would take from the grid look-ups.
 // Every layer of
 //     h = w3 . relu(W2 relu(W1 relu(W0 x + b0) + b1) + b2) + b3        (neural_mindis_cbf_controller.py:41-53)
 // and of its reverse-mode Jacobian (:93-96) is a [128 x K] . [K x N] GEMM with K in {8, 48}, N in {16, 48}:
-//   * A operand (activations / back-propagated gradient) lives in TENSOR MEMORY: thread t writes its row with
-//     tcgen05.st 32x32b (lane t, one column per K element) -- no shared-memory round trip for activations;
+//   * A operand (activations / back-propagated gradient): the "hi" part lives in TENSOR MEMORY -- thread t writes its
+//     row with tcgen05.st 32x32b (lane t, one column per K element); the small "lo" part goes to a per-group
+//     shared-memory tile in the same K-major core-matrix layout as the weights (a third TMEM operand region would cap
+//     the CTA at 3 tiles = 3 warps per scheduler, and the kernel is issue/latency bound, not smem bound);
 //   * B operand (weights) in shared memory, canonical no-swizzle K-major layout W4[k/4][n] (core matrix = 8 rows
 //     x 16 bytes).  kind::tf32 returned zeros for MN-major (transposed) B in every descriptor variant probed
 //     (tools/tc_probe.cu), so the backward GEMMs read a second, transposed copy of each weight matrix;
@@ -27,16 +31,16 @@ namespace cbfrrt {
 namespace tc {
 
 constexpr int M_TILE = 128;
-constexpr int G = 3;                       // tile groups per CTA
-constexpr int NT_TC = G * M_TILE;          // 384 threads
+constexpr int G_MAX = 4;                   // tile groups per CTA: template parameter GG <= G_MAX (512 threads)
 constexpr int H = 48;                      // hidden width (validated on the host: only 48 x 2 is built)
 constexpr int KIN = 16;                    // padded N of the last backward GEMM (dh/dx has N_IN <= 8 real columns)
-constexpr int COLS_PER_TILE = 160;         // D 0..47 | pad | A_hi 64..111 | A_lo 112..159
-constexpr int COL_D = 0, COL_AHI = 64, COL_ALO = 112;
+constexpr int COLS_PER_TILE = 128;         // D 0..47 | pad | A_hi 64..111 | pad
+constexpr int COL_D = 0, COL_AHI = 64;
+constexpr int ALO_TILE = M_TILE * H;       // floats of one group's A_lo tile: [k/4][row] float4
 constexpr int TMEM_COLS = 512;
 
 // ---- shared-memory carve-up of the tensor-core MLP region (floats, every sub-region 16-byte aligned)
-template <int L>
+template <int L, int GG>
 struct Layout {
     static constexpr int MAT = H * H;                         // one 48 x 48 tile (hi or lo)
     static constexpr int W_F = 0;                             // forward tiles  [l][hi|lo]  W4[k/4][n]
@@ -44,9 +48,10 @@ struct Layout {
     static constexpr int WIN_F = W_T + L * 2 * MAT;           // [hi|lo] [2][48] float4   (K = 8, N = 48)
     static constexpr int WIN_T = WIN_F + 2 * 8 * H;           // [hi|lo] [12][16] float4  (K = 48, N = 16)
     static constexpr int BIAS = WIN_T + 2 * KIN * H;          // b_in[48], b_l[48] x L, w_out[48], b_out (padded to 4)
-    static constexpr int MBAR = BIAS + (L + 2) * H + 4;       // G 64-bit mbarriers
-    static constexpr int TMEM_PTR = MBAR + 2 * G + 2;
-    static constexpr int TOTAL = (TMEM_PTR + 4 + 3) & ~3;
+    static constexpr int MBAR = BIAS + (L + 2) * H + 4;       // GG 64-bit mbarriers
+    static constexpr int TMEM_PTR = MBAR + 2 * GG + 2;
+    static constexpr int A_LO = (TMEM_PTR + 4 + 31) & ~31;    // GG tiles of A_lo, 128-byte aligned
+    static constexpr int TOTAL = A_LO + GG * ALO_TILE;
 };
 
 // ---- PTX wrappers
@@ -77,6 +82,18 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T  (both operands through shared-memory descriptors)
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -162,43 +179,45 @@ __device__ __forceinline__ bool group_any(int g, bool pred) {
 }
 
 // ---- per-thread view of its tile group
-template <int L>
+template <int L, int GG>
 struct Ctx {
+    static constexpr int NT = GG * M_TILE;
     float* base;       // start of the TC region in shared memory
     uint32_t tmem;     // TMEM address of column 0 of this group's slice (lane field = 0)
     uint32_t lane;     // this thread's warp lane-quarter base, pre-shifted (<< 16)
     uint32_t phase;    // parity of the next MMA-completion wait
     int g, t;          // group index, row within the tile
-    __device__ __forceinline__ float* w_f(int l, int lo) const { return base + Layout<L>::W_F + (2 * l + lo) * Layout<L>::MAT; }
-    __device__ __forceinline__ float* w_t(int l, int lo) const { return base + Layout<L>::W_T + (2 * l + lo) * Layout<L>::MAT; }
-    __device__ __forceinline__ float* win_f(int lo) const { return base + Layout<L>::WIN_F + lo * 8 * H; }
-    __device__ __forceinline__ float* win_t(int lo) const { return base + Layout<L>::WIN_T + lo * KIN * H; }
-    __device__ __forceinline__ const float* bias(int l) const { return base + Layout<L>::BIAS + l * H; }  // 0: b_in, 1..L, L+1: w_out, L+2: b_out
-    __device__ __forceinline__ uint64_t* mbar() const { return reinterpret_cast<uint64_t*>(base + Layout<L>::MBAR) + g; }
-    __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(base + Layout<L>::TMEM_PTR); }
+    __device__ __forceinline__ float* w_f(int l, int lo) const { return base + Layout<L, GG>::W_F + (2 * l + lo) * Layout<L, GG>::MAT; }
+    __device__ __forceinline__ float* w_t(int l, int lo) const { return base + Layout<L, GG>::W_T + (2 * l + lo) * Layout<L, GG>::MAT; }
+    __device__ __forceinline__ float* win_f(int lo) const { return base + Layout<L, GG>::WIN_F + lo * 8 * H; }
+    __device__ __forceinline__ float* win_t(int lo) const { return base + Layout<L, GG>::WIN_T + lo * KIN * H; }
+    __device__ __forceinline__ const float* bias(int l) const { return base + Layout<L, GG>::BIAS + l * H; }  // 0: b_in, 1..L, L+1: w_out, L+2: b_out
+    __device__ __forceinline__ float4* alo() const { return reinterpret_cast<float4*>(base + Layout<L, GG>::A_LO + g * ALO_TILE); }
+    __device__ __forceinline__ uint64_t* mbar() const { return reinterpret_cast<uint64_t*>(base + Layout<L, GG>::MBAR) + g; }
+    __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(base + Layout<L, GG>::TMEM_PTR); }
 };
 
 // tile index of element (n, k) in the K-major no-swizzle layout with NROWS rows:  W4[k/4][n]
 __device__ __forceinline__ int tile_idx(int n, int k, int nrows) { return ((k >> 2) * nrows + n) * 4 + (k & 3); }
 
 // Stage the packed fp32 weights (global memory, layout of include/cbfrrt.h) as hi / lo TF32 tiles (forward and
-// transposed), allocate TMEM, init the MMA mbarriers.  Called by all NT_TC threads once; ends with a __syncthreads().
-template <int N_IN, int L>
-__device__ __forceinline__ void setup(Ctx<L>& c, float* region, const float* __restrict__ wg) {
+// transposed), allocate TMEM, init the MMA mbarriers.  Called by all GG * 128 threads once; ends with a __syncthreads().
+template <int N_IN, int L, int GG>
+__device__ __forceinline__ void setup(Ctx<L, GG>& c, float* region, const float* __restrict__ wg) {
     using LY = NetLayout<N_IN, H, L>;
     const int tid = threadIdx.x;
     c.base = region;
     c.phase = 0;
     c.g = tid / M_TILE;
     c.t = tid % M_TILE;
-    for (int i = tid; i < H * 8; i += NT_TC) {               // input layer, forward: n = 0..47, k = 0..7
+    for (int i = tid; i < H * 8; i += GG * M_TILE) {               // input layer, forward: n = 0..47, k = 0..7
         const int n = i / 8, k = i % 8;
         const float w = (k < N_IN) ? __ldg(wg + LY::W_IN + n * LY::IN_PAD + k) : 0.f;
         const float hi = rna_tf32(w);
         c.win_f(0)[tile_idx(n, k, H)] = hi;
         c.win_f(1)[tile_idx(n, k, H)] = w - hi;
     }
-    for (int i = tid; i < KIN * H; i += NT_TC) {             // input layer, transposed: n' = 0..15 (input index), k' = 0..47
+    for (int i = tid; i < KIN * H; i += GG * M_TILE) {             // input layer, transposed: n' = 0..15 (input index), k' = 0..47
         const int np = i / H, kp = i % H;
         const float w = (np < N_IN) ? __ldg(wg + LY::W_IN + kp * LY::IN_PAD + np) : 0.f;
         const float hi = rna_tf32(w);
@@ -207,7 +226,7 @@ __device__ __forceinline__ void setup(Ctx<L>& c, float* region, const float* __r
     }
     for (int l = 0; l < L; ++l) {
         const float* W = wg + LY::HID0 + l * LY::HID_STRIDE;
-        for (int i = tid; i < H * H; i += NT_TC) {
+        for (int i = tid; i < H * H; i += GG * M_TILE) {
             const int n = i / H, k = i % H;
             const float w = __ldg(W + i);
             const float hi = rna_tf32(w), lo = w - hi;
@@ -219,15 +238,15 @@ __device__ __forceinline__ void setup(Ctx<L>& c, float* region, const float* __r
             c.w_t(l, 1)[tile_idx(k, n, H)] = lo;
         }
     }
-    float* b = region + Layout<L>::BIAS;
-    for (int i = tid; i < H; i += NT_TC) {
+    float* b = region + Layout<L, GG>::BIAS;
+    for (int i = tid; i < H; i += GG * M_TILE) {
         b[i] = __ldg(wg + LY::B_IN + i);
         for (int l = 0; l < L; ++l) b[(l + 1) * H + i] = __ldg(wg + LY::HID0 + l * LY::HID_STRIDE + H * H + i);
         b[(L + 1) * H + i] = __ldg(wg + LY::W_OUT + i);
     }
     if (tid == 0) {
         b[(L + 2) * H] = __ldg(wg + LY::B_OUT);
-        for (int g = 0; g < G; ++g) mbar_init1(reinterpret_cast<uint64_t*>(region + Layout<L>::MBAR) + g);
+        for (int g = 0; g < GG; ++g) mbar_init1(reinterpret_cast<uint64_t*>(region + Layout<L, GG>::MBAR) + g);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) tmem_alloc(c.tmem_slot(), TMEM_COLS);      // warp 0 allocates (and later frees)
@@ -239,44 +258,45 @@ __device__ __forceinline__ void setup(Ctx<L>& c, float* region, const float* __r
     c.lane = (uint32_t)(c.t & ~31) << 16;
 }
 
-template <int L>
-__device__ __forceinline__ void teardown(Ctx<L>& c) {
+template <int L, int GG>
+__device__ __forceinline__ void teardown(Ctx<L, GG>& c) {
     fence_before_sync();
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc(*c.tmem_slot(), TMEM_COLS);
 }
 
-// write this thread's K values as the hi / lo rows of the A operand in tensor memory
+// write this thread's K values as the hi row (tensor memory) and the lo row (shared-memory tile) of the A operand
 // The "hi" operand is the raw fp32 value: the tensor core reads only the TF32 bits, i.e. hi = trunc_tf32(v), for free.
 // lo = v - trunc_tf32(v) (exact in fp32; one LOP3 + one FADD).  With the weights split by round-to-nearest at staging
 // time the 3-term product is accurate to ~2^-20 relative per term -- measured better than an fp32 FMA chain.
-template <int K, int L>
-__device__ __forceinline__ void store_a(const Ctx<L>& c, const float* v) {
+template <int K, int L, int GG>
+__device__ __forceinline__ void store_a(const Ctx<L, GG>& c, const float* v) {
     static_assert(K == 8 || K % 16 == 0, "");
     const uint32_t row = c.tmem + c.lane;
-    if constexpr (K == 8) {
-        float lo[8];
+    float4* alo = c.alo() + c.t;               // K-major tile [k/4][row]: consecutive rows are consecutive float4
 #pragma unroll
-        for (int k = 0; k < 8; ++k) lo[k] = v[k] - __uint_as_float(__float_as_uint(v[k]) & 0xffffe000u);
+    for (int kc = 0; kc < K / 4; ++kc) {
+        float4 lo;
+        lo.x = v[4 * kc] - __uint_as_float(__float_as_uint(v[4 * kc]) & 0xffffe000u);
+        lo.y = v[4 * kc + 1] - __uint_as_float(__float_as_uint(v[4 * kc + 1]) & 0xffffe000u);
+        lo.z = v[4 * kc + 2] - __uint_as_float(__float_as_uint(v[4 * kc + 2]) & 0xffffe000u);
+        lo.w = v[4 * kc + 3] - __uint_as_float(__float_as_uint(v[4 * kc + 3]) & 0xffffe000u);
+        alo[kc * M_TILE] = lo;
+    }
+    if constexpr (K == 8) {
         tmem_st8(row + COL_AHI, v);
-        tmem_st8(row + COL_ALO, lo);
     } else {
 #pragma unroll
-        for (int j = 0; j < K / 16; ++j) {
-            float lo[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) lo[k] = v[16 * j + k] - __uint_as_float(__float_as_uint(v[16 * j + k]) & 0xffffe000u);
-            tmem_st16(row + COL_AHI + 16 * j, v + 16 * j);
-            tmem_st16(row + COL_ALO + 16 * j, lo);
-        }
+        for (int j = 0; j < K / 16; ++j) tmem_st16(row + COL_AHI + 16 * j, v + 16 * j);
     }
+    fence_proxy_async();                       // A_lo tile (generic proxy) -> tensor core (async proxy)
     tmem_st_wait();
 }
 
 // D[128 x N] = A[128 x K] . B^T with the 3-term split.  B tile: K-major no-swizzle with NROWS (= N) rows:
 // LBO = NROWS*16 B between K-chunks of 4, SBO = 128 B between 8-row groups, a K = 8 step advances 2 chunks.
-template <int K, int N, int L>
-__device__ __forceinline__ void gemm(Ctx<L>& c, const float* w_hi, const float* w_lo) {
+template <int K, int N, int L, int GG>
+__device__ __forceinline__ void gemm(Ctx<L, GG>& c, const float* w_hi, const float* w_lo) {
     fence_before_sync();
     group_sync(c.g);
     if (c.t < 32) {   // warp 0 of the group, warp-uniform: one elected lane issues (see mma_tf32_ts)
@@ -284,14 +304,17 @@ __device__ __forceinline__ void gemm(Ctx<L>& c, const float* w_hi, const float* 
         constexpr uint32_t idesc = instr_desc(N);
         constexpr uint32_t B_LBO = N * 16, B_SBO = 128, B_STEP = 2 * N * 16;
         const uint32_t b_hi = smem_addr(w_hi), b_lo = smem_addr(w_lo);
+        const uint32_t a_hi = c.tmem + COL_AHI, a_lo = smem_addr(c.alo());
+        constexpr uint32_t A_LBO = M_TILE * 16, A_SBO = 128, A_STEP = 2 * M_TILE * 16;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const uint32_t a0 = c.tmem + ((t == 1) ? COL_ALO : COL_AHI);
-            const uint32_t b0 = (t == 2) ? b_lo : b_hi;
+        for (int ks = 0; ks < K / 8; ++ks)       // a_hi . w_hi
+            mma_tf32_ts(c.tmem + COL_D, a_hi + 8 * ks, smem_desc(b_hi + ks * B_STEP, B_LBO, B_SBO), idesc, ks ? 1u : 0u);
 #pragma unroll
-            for (int ks = 0; ks < K / 8; ++ks)
-                mma_tf32_ts(c.tmem + COL_D, a0 + 8 * ks, smem_desc(b0 + ks * B_STEP, B_LBO, B_SBO), idesc, (t | ks) ? 1u : 0u);
-        }
+        for (int ks = 0; ks < K / 8; ++ks)       // a_hi . w_lo
+            mma_tf32_ts(c.tmem + COL_D, a_hi + 8 * ks, smem_desc(b_lo + ks * B_STEP, B_LBO, B_SBO), idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < K / 8; ++ks)       // a_lo . w_hi  (A from shared memory)
+            mma_tf32_ss(c.tmem + COL_D, smem_desc(a_lo + ks * A_STEP, A_LBO, A_SBO), smem_desc(b_hi + ks * B_STEP, B_LBO, B_SBO), idesc, 1u);
         mma_commit(c.mbar());
     }
     mbar_wait_parity(c.mbar(), c.phase);
@@ -300,8 +323,8 @@ __device__ __forceinline__ void gemm(Ctx<L>& c, const float* w_hi, const float* 
 }
 
 // read this thread's row (lane) of the accumulator: NCOL columns (multiple of 16)
-template <int NCOL, int L>
-__device__ __forceinline__ void load_d(const Ctx<L>& c, float* v) {
+template <int NCOL, int L, int GG>
+__device__ __forceinline__ void load_d(const Ctx<L, GG>& c, float* v) {
     const uint32_t row = c.tmem + c.lane + COL_D;
 #pragma unroll
     for (int j = 0; j < NCOL / 16; ++j) tmem_ld16(row + 16 * j, v + 16 * j);
@@ -310,8 +333,8 @@ __device__ __forceinline__ void load_d(const Ctx<L>& c, float* v) {
 
 // epilogue of a forward layer: s = v + bias;  v <- 2 * relu(s) = s + |s|;  returns the ReLU mask (bit k = s_k > 0).
 // The mask bit is the sign of (0 - s): exactly (s > 0), also for s = +-0; one FADD + one funnel shift per element.
-template <int L>
-__device__ __forceinline__ uint64_t bias_relu2(const Ctx<L>& c, int layer, float (&v)[H]) {
+template <int L, int GG>
+__device__ __forceinline__ uint64_t bias_relu2(const Ctx<L, GG>& c, int layer, float (&v)[H]) {
     static_assert(H == 48, "three 16-bit mask chains");
     uint32_t m[3] = {0, 0, 0};   // independent funnel-shift chains (16 elements each) instead of one 48-long one
     const float4* b4 = reinterpret_cast<const float4*>(c.bias(layer));
@@ -332,8 +355,8 @@ __device__ __forceinline__ uint64_t bias_relu2(const Ctx<L>& c, int layer, float
 
 // value h and Jacobian dh/dx for this thread's x = [q, o]; every thread of the tile group must call it (idle
 // rows pass zeros).  Same contract as mlp_h_jac (mlp_qp.cuh).
-template <int N_IN, int L>
-__device__ __forceinline__ void mlp_h_jac(Ctx<L>& c, const float (&x)[N_IN], float& h_out, float (&jac)[N_IN]) {
+template <int N_IN, int L, int GG>
+__device__ __forceinline__ void mlp_h_jac(Ctx<L, GG>& c, const float (&x)[N_IN], float& h_out, float (&jac)[N_IN]) {
     static_assert(N_IN <= 8, "first layer is one K = 8 MMA step");
     float v[H];
     uint64_t mask[L + 1];
