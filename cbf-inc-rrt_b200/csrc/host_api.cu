@@ -92,12 +92,21 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
     Ctx& c = g_ctx[device];
     std::lock_guard<std::mutex> lock(c.mu);
 
-    // chunking: enough chunks to overlap copies with compute, big enough to fill the GPU (148 SMs x 512 rows)
-    // (measured on cfg1, PCIe Gen5: 8 chunks over 4 streams 0.65 ms, 4 chunks 0.67 ms, 2 chunks 0.81 ms, 1 chunk 1.08 ms)
-    static const int n_chunks = getenv("CBFRRT_HOST_CHUNKS") ? atoi(getenv("CBFRRT_HOST_CHUNKS")) : 2 * NSTREAM;
-    int64_t chunk = (B + n_chunks - 1) / (n_chunks > 0 ? n_chunks : 1);
-    const int64_t min_chunk = 148 * 512, max_chunk = 1 << 20;
-    if (chunk < min_chunk) chunk = min_chunk;
+    // chunking: ~8 chunks over NSTREAM streams overlap the copies with compute (measured on cfg1, PCIe Gen5: 8 chunks
+    // 0.65 ms, 4 chunks 0.67 ms, 2 chunks 0.81 ms, 1 chunk 1.08 ms); a chunk is a whole number of kernel waves
+    // (SMs x 4 tile groups x 128 rows) so that no launch ends with a mostly idle wave
+    static const int n_chunks_env = getenv("CBFRRT_HOST_CHUNKS") ? atoi(getenv("CBFRRT_HOST_CHUNKS")) : 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int64_t wave = (int64_t)sms * 512, max_chunk = 1 << 20;
+    int64_t chunk;
+    if (n_chunks_env > 0) {
+        chunk = (B + n_chunks_env - 1) / n_chunks_env;
+    } else {
+        int64_t waves_per_chunk = (B + 4 * wave) / (8 * wave);      // round(B / wave / 8)
+        if (waves_per_chunk < 1) waves_per_chunk = 1;
+        chunk = waves_per_chunk * wave;
+    }
     if (chunk > max_chunk) chunk = max_chunk;
     if (chunk > B) chunk = B;
     rc = ensure(c, device, chunk, n, scene->n_boxes, scene->n_spheres, n_weights);

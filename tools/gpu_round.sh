@@ -1,10 +1,3 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | cut -c1-330
-python tools/measure_configs.py > gpurun_out/configs_r1j.jsonl 2> gpurun_out/configs_r1j.err; tail -3 gpurun_out/configs_r1j.err
-python - <<'PY'
-import json
-for line in open("gpurun_out/configs_r1j.jsonl"):
-    r=json.loads(line)
-    print(r["config"], {k:(round(v["ms"],3) if isinstance(v,dict) and "ms" in v else v) for k,v in r.items() if isinstance(v,dict)})
-PY
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/plain_b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:safety_kernel_tc -s 4 -c 1 -o gpurun_out/prof_safety_tc_r1k python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_k.log 2>&1
+tail -1 gpurun_out/plain_b.log | cut -c1-300
