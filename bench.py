@@ -205,7 +205,10 @@ def main():
             sweep = FusedSweep(lambda qb, vp, up, off: ops.valid_control_scatter(qb, *common, vp, up, off), n, B, dev)
             def step():
                 return sweep(q)
-            launches_per_step, collective = 1, "fused: kernel epilogue stores (valid u8, u f32xn) into every rank's replica over NVLink peer mappings (symmetric memory) + barrier"
+            launches_per_step = 1
+            collective = ("fused: kernel epilogue stores (valid u8, u f32xn) into every rank's replica over NVLink ("
+                          + ("one multicast store per row, replicated by NVSwitch" if sweep.multicast else "per-peer stores")
+                          + ", symmetric memory) + barrier")
         except Exception as e:   # no P2P / symmetric memory: NCCL all-gather, block-cyclic, overlapped on a 2nd stream
             sys.stderr.write(f"[bench] symmetric memory unavailable ({e!r}); using NCCL all_gather\n")
             n_blocks = 4

@@ -11,6 +11,7 @@ b % world.  A rank computes its blocks in order; block j of every rank is gather
 [j*world*block, (j+1)*world*block) -- so the gathered buffers are in global row order without a permute, and
 the gather of block j overlaps the kernel of block j+1 on a second stream.
 """
+import os
 from typing import Callable, Tuple
 
 import torch
@@ -88,8 +89,12 @@ class ShardedSweep:
 
 class FusedSweep:
     """Sweep + all-gather in ONE kernel per rank: the epilogue of the fused safety-filter kernel stores every
-    (valid, u) row into all ranks' replicated buffers over NVLink peer mappings (torch symmetric memory), then the
-    ranks meet at a barrier.  Contiguous sharding: rank r owns global rows [r*B, (r+1)*B).
+    (valid, u) row into all ranks' replicated buffers over NVLink (torch symmetric memory), then the ranks meet at a
+    barrier.  Contiguous sharding: rank r owns global rows [r*B, (r+1)*B).
+
+    On NVSwitch systems the stores go to the buffers' MULTICAST address: one store per row, replicated to every rank
+    by the switch (NVLS) -- 1/world of the outbound traffic and store instructions of the per-peer form, which is
+    kept as the fallback (no multicast support, or CBFRRT_NO_MULTICAST=1).
 
     launch(q_local, valid_ptrs, u_ptrs, row_offset) runs cbfrrt::valid_control_scatter with the scene / network of
     the caller.  ``valid`` [G] u8 and ``u`` [G, n] f32 are this rank's replicas (valid after __call__ returns and
@@ -107,6 +112,11 @@ class FusedSweep:
         self.h_u = symm_mem.rendezvous(self.u, self.group)
         self.valid_ptrs = [int(p) for p in self.h_valid.buffer_ptrs]
         self.u_ptrs = [int(p) for p in self.h_u.buffer_ptrs]
+        mc_v = int(getattr(self.h_valid, "multicast_ptr", 0) or 0)
+        mc_u = int(getattr(self.h_u, "multicast_ptr", 0) or 0)
+        self.multicast = bool(mc_v and mc_u) and os.environ.get("CBFRRT_NO_MULTICAST", "0") != "1"
+        if self.multicast:
+            self.valid_ptrs, self.u_ptrs = [mc_v], [mc_u]
 
     def __call__(self, q_local: torch.Tensor):
         assert q_local.shape[0] == self.B

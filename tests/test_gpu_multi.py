@@ -33,12 +33,24 @@ def _worker(rank, world, port, ret):
     q_all = ops.sample_states(G, 5, 0, rid, device=dev)              # counter-based: identical on every rank
     ref_v, ref_u = ops.valid_control(q_all, *common)
     ok = []
-    # fused epilogue exchange, contiguous shards
-    sweep = FusedSweep(lambda qb, vp, up, off: ops.valid_control_scatter(qb, *common, vp, up, off), n, B, dev)
-    for _ in range(2):
-        v, u = sweep(q_all[rank * B:(rank + 1) * B])
-        torch.cuda.synchronize()
-        ok.append(bool(torch.equal(v, ref_v) and torch.equal(u, ref_u)))
+    # fused epilogue exchange, contiguous shards: multicast stores (NVSwitch) where available, then per-peer stores
+    modes = []
+    for no_mc in ("0", "1"):
+        os.environ["CBFRRT_NO_MULTICAST"] = no_mc
+        sweep = FusedSweep(lambda qb, vp, up, off: ops.valid_control_scatter(qb, *common, vp, up, off), n, B, dev)
+        modes.append(sweep.multicast)
+        for _ in range(2):
+            sweep.valid.zero_()
+            sweep.u.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            v, u = sweep(q_all[rank * B:(rank + 1) * B])
+            torch.cuda.synchronize()
+            ok.append(bool(torch.equal(v, ref_v) and torch.equal(u, ref_u)))
+        dist.barrier()
+    assert modes[1] is False
+    if rank == 0:
+        print("fused exchange modes tested (multicast, per-peer):", modes, flush=True)
     # NCCL all-gather, block-cyclic
     block, rounds = 2500, B // 2500
     rows = local_global_rows(rank, world, block, rounds).to(dev)
