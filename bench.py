@@ -144,6 +144,27 @@ def reference_arm(args, w):
     }))
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-rank runs: pin this rank's host threads (and so its first-touch pinned buffers of the e2e leg) to the CPUs
+    NVML reports as local to its GPU, so that the host<->device copies of 8 ranks do not all cross the socket link."""
+    if os.environ.get("CBFRRT_BENCH_NO_AFFINITY", "0") == "1":
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception as e:   # no NVML / restricted container: keep the default affinity
+        sys.stderr.write(f"[bench] cpu affinity not set ({e!r})\n")
+    return None
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -175,6 +196,7 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -336,7 +358,8 @@ def main():
             "config": {"workload": w["name"], "robot": robot, "states_per_gpu": B, "boxes": int(w["boxes"].shape[0]),
                        "spheres": int(w["spheres"].shape[0]), "floor": True, "mlp": "(n+1)-48-48-48-1",
                        "outputs": outputs, "l2": "flushed by a 256 MiB write between timed steps (outside the event pairs)",
-                       "collective": "none" if world == 1 else collective},
+                       "collective": "none" if world == 1 else collective,
+                       "host_cpus_bound": affinity},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step,
             "roofline": roofline, "cpu_baseline": cpu,
         }))
