@@ -527,3 +527,32 @@ def test_python_api_drop_in_on_gpu(coracle):
     assert bool(v.item()) == edge_checking(start, target, dyn, eps) == edge_checking_reference_loop(start, target, dyn, eps)
     assert robot.forward_kinematics([6, 7], torch.tensor(robot.q0))[1][0].shape == (3,)
     assert np.allclose(robot.forward_kinematics([7], robot.q0)[0][0], (0.288556, -0.257364, 0.361447), atol=2e-6)
+
+
+def test_batch_rrt_plan_on_gpu():
+    """the planner front-end end to end on the device ops: cbfrrt::knn -> cbfrrt::rollout -> cbfrrt::masks"""
+    from cbfrrt.environment import ArmEnv
+    from cbfrrt.neural_cbf.systems import ArmMindis
+    from cbfrrt.neural_cbf.controllers import NeuralMindisCBFController
+    from cbfrrt.motion_planning.baseline import batch_RRT_plan
+    env = ArmEnv(["panda"], config_file="", include_floor=True)
+    robot = env.robot_list[0]
+    dyn = ArmMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.02, env=env, robot=robot)
+    torch.manual_seed(1)
+    ctrl = NeuralMindisCBFController(dyn, [{"m1": 5.76}], None, None, cbf_alpha=0.1, cbf_relaxation_penalty=5000.0,
+                                     safe_level=0.1, unsafe_level=0.1, cbf_hidden_layers=2, cbf_hidden_size=48,
+                                     use_neural_actor=False)
+    x = dyn.sample_state_space(400)
+    xs = x[dyn.safe_mask(x).cpu()][:, :7].cpu().numpy()
+    init = xs[0]
+    goal = init + 0.3 * (xs[1] - init) / np.linalg.norm(xs[1] - init)
+    dyn.set_goal(goal)
+    res = batch_RRT_plan(env, dyn, init, goal, RRT_PARAM=20, controller=ctrl, T=400, model_eps=0.3, steer_type="cbf",
+                         batch=50, stop_when_success=True, rng=np.random.RandomState(0))
+    tree = res["search_tree"]
+    assert tree.states.shape[0] == len(tree.parents) > 50
+    pts = np.array([pt for xl in tree.x_list[1:] for pt in xl])
+    assert not dyn.unsafe_mask(torch.as_tensor(pts, dtype=torch.float32)).any()
+    assert np.array_equal(tree.non_terminal_states, tree.states[tree.non_terminal_idxes])
+    assert res["success"], "goal 0.3 rad from the start must be reached within 400 extensions"
+    assert np.allclose(res["path"][0], init) and np.linalg.norm(res["path"][-1] - goal) <= 0.2 + 1e-5

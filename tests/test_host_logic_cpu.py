@@ -236,6 +236,39 @@ def test_explore_nearest_matches_reference_numpy(stack):
             assert ss.shape == (batch, 7) and (ss == samples[0]).all()
 
 
+def test_batch_rrt_plan_builds_a_consistent_tree(stack):
+    """batch_RRT_plan / global_explore / SearchTree (batch_tsa.py:11-189, search_tree.py:6-92): result dict, tree
+    invariants, and every stored edge state hard-collision-free"""
+    env, robot, dyn, ctrl = stack("magician")
+    from cbfrrt.motion_planning.baseline import batch_RRT_plan, SearchTree
+    x = dyn.sample_state_space(200)
+    xs = x[dyn.safe_mask(x)][:, :4].numpy()
+    init = xs[0]
+    goal = init + 0.25 * (xs[1] - init) / np.linalg.norm(xs[1] - init)     # close by: reachable within a few extensions
+    dyn.set_goal(goal)
+    res = batch_RRT_plan(env, dyn, init, goal, RRT_PARAM=20, controller=ctrl, T=60, model_eps=0.3, steer_type="cbf",
+                         batch=8, stop_when_success=True, rng=np.random.RandomState(0))
+    assert set(res) >= {"success", "path", "edge_states", "nominal_path", "path_cost", "explored_nodes", "time_dict"}
+    tree = res["search_tree"]
+    n_nodes = tree.states.shape[0]
+    assert n_nodes == len(tree.parents) == len(tree.x_list) == len(tree.in_goal_region) and n_nodes > 8
+    assert all(p is None or 0 <= p < i for i, p in enumerate(tree.parents))
+    assert tree.non_terminal_states.shape[0] == len(tree.non_terminal_idxes)
+    assert np.array_equal(tree.non_terminal_states, tree.states[tree.non_terminal_idxes])
+    edge_pts = np.array([pt for xl in tree.x_list[1:] for pt in xl])
+    if len(edge_pts):
+        assert not dyn.unsafe_mask(torch.as_tensor(edge_pts, dtype=torch.float32)).any()
+    for i in range(1, n_nodes):                                      # an edge ends at its node
+        if tree.x_list[i]:
+            assert np.allclose(tree.x_list[i][-1], tree.states[i], atol=1e-6)
+    if res["success"]:
+        assert np.allclose(res["path"][0], init) and np.linalg.norm(res["path"][-1] - goal) <= 0.2 + 1e-6
+        assert len(res["path"]) == len(res["path_cost"]) == len(res["edge_states"]) and res["path_cost"][-1] == 0
+    # the tree's own path() contract (search_tree.py:24-47)
+    t = SearchTree(root=np.zeros(4))
+    assert t.path() == ([], [], [], [])
+
+
 def test_basic_robot_kinematics(stack, models):
     env, robot, dyn, ctrl = stack("panda")
     from oracle import oracle_f64 as o
