@@ -296,7 +296,10 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured"
     except Exception:
-        hbm_peak, hbm_src = 6650.0, "fallback"
+        peaks, hbm_peak, hbm_src = {}, 6650.0, "fallback"
+    tensor_peak = next((float(v) for k, v in peaks.items() if "bf16" in k.lower() and isinstance(v, (int, float))), None)
+    tensor_src = "measured (dense bf16, MEASURED_PEAKS.json)" if tensor_peak else "fallback (nominal dense bf16)"
+    tensor_peak = tensor_peak or 2250.0
     # DRAM traffic of one launch from the committed ncu --set full capture of this exact command
     # (profiles/r1d_ncu_full_safety_kernel_tc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum); only valid for the
     # default workload at N=1, else null
@@ -308,6 +311,9 @@ def main():
                 "frac_without_mlp": (flops_u - mlp_flops) * B / kernel_s / 1e12 / fp32_peak,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "peak_source": hbm_src},
+                "tensor": {"achieved": 3 * mlp_flops * B / kernel_s / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                           "frac": 3 * mlp_flops * B / kernel_s / 1e12 / tensor_peak, "peak_source": tensor_src,
+                           "note": "executed tcgen05 flops of the barrier network (3-term TF32 split = 3x algorithmic)"},
                 "kernel": "safety_kernel_tc" if world == 1 else "safety_kernel_tc (valid+u, fused exchange)",
                 "note": "achieved = ALGORITHMIC flops of SURVEY 8d (brute-force pair sweep + FP32 MLP) / kernel time, "
                         "against the CUDA-core FP32 peak; the kernel runs the MLP on tcgen05 (TF32x3) and culls pairs "
