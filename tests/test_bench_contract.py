@@ -1,0 +1,46 @@
+"""bench.py prints ONE JSON line with the keys the driver's contract names: the reference arm (CPU port of the path)
+is checked on the CPU suite, the GPU arm on the GPU suite (reduced workload so that it takes seconds)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+        "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
+
+
+def _run(*args):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().split("\n") if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--scale", "0.01")
+    assert BASE <= set(r) and r["impl"] == "reference" and r["unit"] == "states/s" and r["value"] > 0
+    assert r["cpu_baseline"]["kind"] == "port" and r["cpu_baseline"]["cores"] >= 1 and r["cpu_baseline"]["value"] == r["value"]
+    assert r["e2e"] == {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert r["config"]["workload"].startswith("cfg1") and r["vs_baseline"] is None
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line():
+    r = _run("--steps", "3", "--warmup", "3", "--scale", "0.125")
+    assert BASE | {"clocks", "roofline"} <= set(r) and "impl" not in r
+    assert r["n_gpus"] == 1 and r["steps"] == 3 and r["warmup"] >= 3 and r["higher_is_better"] and r["vs_baseline"] is None
+    assert r["gpu_launches"] == 3 and r["value"] > 1e8 and r["dtype"] == "f32" and r["data"] == "synthetic"
+    e = r["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 131072 * 16 and e["d2h_bytes_per_step"] == 131072 * 17
+    assert e["value"] < r["value"], "the host-buffer path cannot beat the device-resident one"
+    rf = r["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "hbm", "tensor"} <= set(rf)
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 20 < rf["peak"] < 90      # FP32 FMA TFLOP/s of a B200
+    c = r["cpu_baseline"]
+    assert c["kind"] == "port" and c["value"] > 0 and "sample" in c
+    assert set(r["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
