@@ -69,7 +69,7 @@ def _worker(rank, world, port, ret):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_fused_and_nccl_exchange_match_single_gpu():
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, 29620 + os.getpid() % 300, ret)) for r in range(world)]
