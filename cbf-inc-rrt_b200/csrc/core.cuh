@@ -431,12 +431,17 @@ __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const Sce
             if (!WANT_SELFMIN && !GRID && K >= 3 && sc.n_boxes + sc.n_spheres >= CULL_MIN_OBSTACLES) {
                 // bound for the exact culling test: running minimum incl. this link's floor candidates (merged
                 // for real, in oracle order, below), never below the thresholds the masks compare with
-                float tb = o;
-                if (sc.floor) {
-                    if constexpr (L == 0) tb = fminf(tb, RB::LINK0_FLOOR);
-                    else {
+                // (mask-only callers -- WANT_GRAD false: edges, masks, the non-refresh steps of a rollout -- never
+                // read the minimum itself, so for them the bound is just the mask thresholds)
+                float tb = -CBF_INF;
+                if constexpr (WANT_GRAD) {
+                    tb = o;
+                    if (sc.floor) {
+                        if constexpr (L == 0) tb = fminf(tb, RB::LINK0_FLOOR);
+                        else {
 #pragma unroll
-                        for (int k = 0; k < K; ++k) tb = fminf(tb, C[k][2] - rad[k]);
+                            for (int k = 0; k < K; ++k) tb = fminf(tb, C[k][2] - rad[k]);
+                        }
                     }
                 }
                 constexpr float b0 = RB::ball(L, 0), b1 = RB::ball(L, 1), b2 = RB::ball(L, 2);

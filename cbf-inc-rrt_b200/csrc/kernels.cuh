@@ -529,7 +529,11 @@ __global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) rollout_kerne
             if (finished) continue;
 #pragma unroll
             for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);  // arm_dynamics.py:508 (step = 1)
-            collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
+            if ((t + 1) % ra.ctrl_every == 0) {       // observation refresh: minimum + gradient needed
+                collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
+            } else {                                  // only the collision test is read: mask-only evaluation
+                collide_state<RB, false, false, GRID>(qn, sv, base_min, cr);
+            }
             if ((t + 1) % ra.ctrl_every == 0) {
                 o = cr.o;
 #pragma unroll
@@ -745,7 +749,11 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
             }
 #pragma unroll
             for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);  // arm_dynamics.py:508 (step = 1)
-            collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
+            if ((t + 1) % ra.ctrl_every == 0) {       // observation refresh: minimum + gradient needed
+                collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
+            } else {                                  // only the collision test is read: mask-only evaluation
+                collide_state<RB, false, false, GRID>(qn, sv, base_min, cr);
+            }
             if ((t + 1) % ra.ctrl_every == 0) {
                 o = cr.o;
 #pragma unroll

@@ -1,3 +1,9 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1o.json 2> gpurun_out/bench_r1o.err; cut -c1-300 gpurun_out/bench_r1o.json
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/measure_configs.py --only cfg0,cfg1,cfg3 > gpurun_out/configs_r1p.jsonl 2> gpurun_out/configs_r1p.err; tail -3 gpurun_out/configs_r1p.err
+python - <<'PY'
+import json
+for line in open("gpurun_out/configs_r1p.jsonl"):
+    r=json.loads(line)
+    print(r["config"], {k:(round(v["ms"],3) if isinstance(v,dict) and "ms" in v else v) for k,v in r.items() if isinstance(v,dict)})
+PY
