@@ -369,7 +369,9 @@ struct CollideResult {
 // (kernels.cu: base_min_cta) and passes in.  The floor is exempt for the base in both checks.
 // GRID: the scene carries a nearest-candidate grid (sc.grid != nullptr); grid-free instantiations keep the small-
 // scene kernels free of the look-up code and its registers.
-template <class RB, bool WANT_GRAD, bool WANT_SELFMIN, bool GRID>
+// WANT_SELF = false skips the self-collision predicate (res.self_ok stays true): the unsafe test of the steer loop
+// (tsa.py:251, hard check only) does not read it.
+template <class RB, bool WANT_GRAD, bool WANT_SELFMIN, bool GRID, bool WANT_SELF = true>
 __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const SceneS& sc, float base_min,
                                               CollideResult<RB>& res) {
     constexpr int N = RB::N;
@@ -418,7 +420,7 @@ __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const Sce
             static_for<0, RB::NSELFSPH>([&](auto pc) {
                 constexpr int p = decltype(pc)::value;
                 constexpr int i = RB::self_i(p), j = RB::self_j(p);
-                if constexpr (j >= S0 && j < S1) {
+                if constexpr (WANT_SELF && j >= S0 && j < S1) {
                     const float dx = __fsub_rn(SC[i][0], SC[j][0]), dy = __fsub_rn(SC[i][1], SC[j][1]), dz = __fsub_rn(SC[i][2], SC[j][2]);
                     const float dsq = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
                     self_ok = self_ok && (dsq > RB::self_x(p));

@@ -531,8 +531,8 @@ __global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) rollout_kerne
             for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);  // arm_dynamics.py:508 (step = 1)
             if ((t + 1) % ra.ctrl_every == 0) {       // observation refresh: minimum + gradient needed
                 collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
-            } else {                                  // only the collision test is read: mask-only evaluation
-                collide_state<RB, false, false, GRID>(qn, sv, base_min, cr);
+            } else {                                  // only the hard collision test is read: mask-only, no self test
+                collide_state<RB, false, false, GRID, false>(qn, sv, base_min, cr);
             }
             if ((t + 1) % ra.ctrl_every == 0) {
                 o = cr.o;
@@ -751,8 +751,8 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
             for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);  // arm_dynamics.py:508 (step = 1)
             if ((t + 1) % ra.ctrl_every == 0) {       // observation refresh: minimum + gradient needed
                 collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
-            } else {                                  // only the collision test is read: mask-only evaluation
-                collide_state<RB, false, false, GRID>(qn, sv, base_min, cr);
+            } else {                                  // only the hard collision test is read: mask-only, no self test
+                collide_state<RB, false, false, GRID, false>(qn, sv, base_min, cr);
             }
             if ((t + 1) % ra.ctrl_every == 0) {
                 o = cr.o;
