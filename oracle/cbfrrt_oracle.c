@@ -21,7 +21,11 @@
  *   nominal control                      neural_cbf/systems/arm_dynamics.py:124-161
  *   CBF-QP                               neural_cbf/controllers/clf_controller.py:82-139,354-404
  *   Euler step / steer loop              neural_cbf/systems/arm_dynamics.py:474-523, motion_planning/baseline/tsa.py:217-269
- *   edge check                           motion_planning/baseline/tsa.py:272-286
+ *   edge check                           motion_planning/baseline/tsa.py:272-286 (fixed K and per-edge K = int(d/eps))
+ *   multi-scenario QP (S > 1)            neural_cbf/controllers/clf_controller.py:86-139 (float64 dual active-set solve,
+ *                                        certified by KKT residuals and SLSQP in tests/test_oracle_cpu.py)
+ *   nearest / k-nearest / radius         motion_planning/baseline/batch_tsa.py:135-145, tsa.py:151-153, bit_star.py:196-216
+ *                                        (checked against the reference's numpy expressions in tests/test_oracle_cpu.py)
  *
  * DETERMINISTIC FLOAT32 CONTRACT (DESIGN.md "Deterministic-math contract"): every geometric quantity that
  * feeds a boolean or an index is computed with exactly the operation sequence written below -- single
