@@ -1,12 +1,17 @@
 """PyTorch custom ops (namespace ``cbfrrt::``) over the C-ABI of libcbfrrt.so.
 
 CUDA-only registration: there is no CPU kernel, no Triton path and no dispatch table -- calling an op with CPU
-tensors raises NotImplementedError from the dispatcher.  PyTorch is plumbing here (device memory, current
-stream); every op is one call into include/cbfrrt.h with raw device pointers.
+tensors raises NotImplementedError.  PyTorch is plumbing here (device memory, current stream); every op is one call
+into include/cbfrrt.h with raw device pointers.
+
+Every op is registered with torch.library (``torch.ops.cbfrrt.<name>``, also ``ops.registered[<name>]``); the
+module-level functions of the same names call the implementations DIRECTLY, because the dispatcher costs 20-30 us
+per call -- most of the host time of a planner-sized (1-50 state) call.
 
 Reference call sites each op replaces are listed in include/cbfrrt.h.
 """
 import ctypes as C
+import functools
 from typing import Tuple
 
 import numpy as np
@@ -427,6 +432,32 @@ def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, st
                                  _stream()), "cbfrrt_rollout")
     del keep
     return qf, alive, done, traj
+
+
+# ----------------------------------------------------------------------------- direct entry points
+registered = {}
+
+
+def _direct(op, cpu_ok=()):
+    impl = op._init_fn
+
+    @functools.wraps(impl)
+    def call(*args, **kwargs):
+        for i, a in enumerate(args):
+            if isinstance(a, Tensor) and not a.is_cuda and i not in cpu_ok:
+                raise NotImplementedError(f"cbfrrt::{impl.__name__} needs CUDA tensors (argument {i} is on {a.device}); "
+                                          "there is no CPU path")
+        return impl(*args, **kwargs)
+
+    call.op = op
+    return call
+
+
+for _name in ("fk", "collide", "observe", "masks", "cbf_filter", "qp", "qp_multi", "safety_filter", "valid_control",
+              "edge_validity", "edge_validity_var", "knn", "radius_mask", "rollout"):
+    registered[_name] = globals()[_name]
+    globals()[_name] = _direct(registered[_name], cpu_ok=(2,) if _name == "edge_validity_var" else ())
+del _name
 
 
 def sample_states(B: int, seed: int, start_row: int, robot_id: int, device="cuda") -> Tensor:

@@ -561,3 +561,15 @@ def test_batch_rrt_plan_on_gpu():
     # the nominal (LQR) steer heads straight for the goal 0.3 rad away (0.05 rad per goal-biased extension): must be
     # found; the randomly initialised barrier network of this test may legitimately hold the CBF-filtered steer back
     assert res["success"]
+
+
+def test_registered_ops_equal_direct_calls():
+    """torch.ops.cbfrrt.* (dispatcher) and the module-level direct entry points run the same implementation"""
+    from cbfrrt import ops, workloads as W
+    q = _t(W.sample_states("panda", 300, 3))
+    a, b = ops.fk(q, 0), torch.ops.cbfrrt.fk(q, 0)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert set(ops.registered) >= {"fk", "collide", "safety_filter", "rollout", "knn", "qp_multi", "edge_validity_var"}
+    assert ops.fk.op is ops.registered["fk"]
+    with pytest.raises(NotImplementedError):
+        ops.fk(q.cpu(), 0)
