@@ -1,9 +1,3 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
-python tools/measure_configs.py --only cfg3 > gpurun_out/configs_r1q.jsonl 2> gpurun_out/configs_r1q.err; tail -3 gpurun_out/configs_r1q.err
-python - <<'PY'
-import json
-for line in open("gpurun_out/configs_r1q.jsonl"):
-    r=json.loads(line)
-    print(r["config"], {k:(round(v["ms"],3) if isinstance(v,dict) and "ms" in v else v) for k,v in r.items() if isinstance(v,dict)})
-PY
+python tools/experiments/small_one.py > gpurun_out/plain_s.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:safety_kernel -s 4 -c 1 -o gpurun_out/prof_small_r1 python tools/experiments/small_one.py > gpurun_out/ncu_small.log 2>&1
+ls -la gpurun_out/prof_small_r1.ncu-rep
