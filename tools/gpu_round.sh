@@ -1,5 +1,5 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8
-python tools/experiments/small_batch_sweep.py 2>&1 | grep -E " (1024|4096|8192|16384) "
-CBFRRT_COMPACT=0 python tools/experiments/small_batch_sweep.py 2>&1 | grep -E " (1024|4096|8192) " | sed 's/^/nocompact /'
-python tools/measure_configs.py --only cfg0 2>/dev/null | python -c "import json,sys; r=json.loads(sys.stdin.readline()); print(r['config'], {k:round(v['ms'],4) for k,v in r.items() if isinstance(v,dict) and 'ms' in v})"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1z.json 2> gpurun_out/bench_r1z.err; cut -c1-260 gpurun_out/bench_r1z.json
+python tools/measure_configs.py --cpu > gpurun_out/configs_r1z.jsonl 2> gpurun_out/configs_r1z.err; tail -2 gpurun_out/configs_r1z.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
