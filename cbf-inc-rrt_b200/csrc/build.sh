@@ -8,7 +8,7 @@ OUT="$HERE/../cbfrrt/_lib"
 OBJ="$OUT/obj"
 mkdir -p "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -diag-suppress 20091"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -diag-suppress 20091 ${EXTRA_NVCC_FLAGS:-}"
 pids=()
 for src in "$HERE"/abi.cu "$HERE"/host_api.cu "$HERE"/k_*.cu; do
   name=$(basename "$src" .cu)

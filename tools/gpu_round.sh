@@ -1,5 +1,6 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1z.json 2> gpurun_out/bench_r1z.err; cut -c1-260 gpurun_out/bench_r1z.json
-python tools/measure_configs.py --cpu > gpurun_out/configs_r1z.jsonl 2> gpurun_out/configs_r1z.err; tail -2 gpurun_out/configs_r1z.err
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "collide or safety or full_size or rollout" 2>&1 | tail -2
+python tools/measure_configs.py --only cfg1,cfg3 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    r=json.loads(l); print(r['config'], {k:round(v['ms'],3) for k,v in r.items() if isinstance(v,dict) and 'ms' in v})"
