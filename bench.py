@@ -245,6 +245,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clock ramp: a fresh process starts with the GPU idle, and a handful of sub-millisecond warm-up steps is too short
+    # for the SM clock to reach its sustained value -- run the step untimed for 0.3 s first, then the W warm-up steps
+    t_ramp = time.time() + 0.3
+    while time.time() < t_ramp:
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
     for _ in range(args.warmup):
         step()
         flush.zero_()
