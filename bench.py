@@ -246,12 +246,11 @@ def main():
         torch.cuda.synchronize()
 
     # clock ramp: a fresh process starts with the GPU idle, and a handful of sub-millisecond warm-up steps is too short
-    # for the SM clock to reach its sustained value -- run the step untimed for 0.3 s first, then the W warm-up steps
-    t_ramp = time.time() + 0.3
-    while time.time() < t_ramp:
-        for _ in range(10):
-            step()
-        torch.cuda.synchronize()
+    # for the SM clock to reach its sustained value -- run the step untimed for about 0.3 s first, then the W warm-up steps
+    # (a fixed count, identical on every rank: the multi-GPU step ends in a barrier)
+    for _ in range(min(20000, max(50, int(0.3 / (B * 4.5e-10))))):
+        step()
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         step()
         flush.zero_()
