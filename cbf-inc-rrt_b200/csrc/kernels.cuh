@@ -568,64 +568,12 @@ __global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) rollout_kerne
     tc::teardown<L, GG>(c);
 }
 
-// edge validity: one thread per (edge, point); point k in [0, K] (K = end point).  A CTA owns EPB whole edges
-// (EPB * (K+1) <= NT threads active) and reduces "first failing index" with a shared-memory atomicMin.
-template <class RB, bool GRID>
-__global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_kernel(SceneArgs sc, const float* __restrict__ q_from,
-                                                  const float* __restrict__ q_to, long long E, int K, int epb,
-                                                  float thr_soft, float thr_hard, uint8_t* __restrict__ valid,
-                                                  int* __restrict__ first_bad) {
-    constexpr int N = RB::N;
-    extern __shared__ __align__(16) float smem_raw[];
-    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
-    __shared__ int s_bad[NT];
-    stage<N>(s, sc, nullptr, 0);
-    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
-    const float base_min = base_min_cta<RB>(s, sv);
-    const int pts = K + 1;
-    const int le = threadIdx.x / pts, k = threadIdx.x - le * pts;
-    const bool active = le < epb;
-    const long long n_groups = (E + epb - 1) / epb;
-    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const long long e = grp * epb + le;
-        if (threadIdx.x < epb) s_bad[threadIdx.x] = 0x7fffffff;
-        __syncthreads();
-        if (active && e < E) {
-            float c[N];
-            if (k == K) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) c[i] = __ldg(q_to + e * N + i);
-            } else {
-                const float t = __fdiv_rn((float)k, (float)K);
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const float a = __ldg(q_from + e * N + i), bb = __ldg(q_to + e * N + i);
-                    c[i] = fmaf(t, __fsub_rn(bb, a), a);
-                }
-            }
-            CollideResult<RB> r;
-            collide_state<RB, false, false, GRID>(c, sv, base_min, r);
-            const bool unsafe = r.hard_min <= thr_hard;
-            const bool safe = r.self_ok && (r.soft_min > thr_soft) && !unsafe;
-            if (!safe) atomicMin(&s_bad[le], k);
-        }
-        __syncthreads();
-        if (threadIdx.x < epb) {
-            const long long ee = grp * epb + threadIdx.x;
-            if (ee < E) {
-                const int bad = s_bad[threadIdx.x];
-                valid[ee] = bad == 0x7fffffff;
-                first_bad[ee] = bad == 0x7fffffff ? -1 : bad;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// edges of different lengths (tsa.py:277-279: K = int(|q_to - q_from| / eps) per edge): one thread per (edge, point)
-// over the concatenation of all edges' points; off [E+1] is the exclusive prefix sum of K_e + 1.  Consecutive threads
-// are consecutive points of one edge, so a warp's states are geometrically coherent.  first_bad must be preset to
-// EDGE_SENTINEL (edge_var_init), the reduction is a global atomicMin, edge_var_finish writes valid / maps the sentinel.
+// edge validity (tsa.py:272-286): one thread per (edge, point) over the concatenation of all edges' points -- every
+// lane busy whatever the edge lengths (a CTA-owns-whole-edges layout idles 23 % of the lanes at 33 points per edge and
+// measured 14 % slower on cfg2).  Edges have a common K (off == nullptr: e = p / (K+1)) or their own K_e = int(|q_to -
+// q_from| / eps) (tsa.py:277-279: off [E+1] = exclusive prefix sum of K_e + 1).  Consecutive threads are consecutive
+// points of one edge, so a warp's states are geometrically coherent.  first_bad must be preset to EDGE_SENTINEL
+// (edge_var_init), the reduction is a global atomicMin, edge_var_finish writes valid / maps the sentinel.
 constexpr int EDGE_SENTINEL = 0x7fffffff;
 static __global__ void edge_var_init(int* __restrict__ first_bad, long long E) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x)
@@ -641,8 +589,8 @@ static __global__ void edge_var_finish(int* __restrict__ first_bad, uint8_t* __r
 template <class RB, bool GRID>
 __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_var_kernel(SceneArgs sc, const float* __restrict__ q_from,
                                                       const float* __restrict__ q_to, long long E,
-                                                      const long long* __restrict__ off, long long P, float thr_soft,
-                                                      float thr_hard, int* __restrict__ first_bad) {
+                                                      const long long* __restrict__ off, int K_all, long long P,
+                                                      float thr_soft, float thr_hard, int* __restrict__ first_bad) {
     constexpr int N = RB::N;
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
@@ -650,13 +598,23 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_var_kernel(Scen
     const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB>(s, sv);
     for (long long p = (long long)blockIdx.x * NT + threadIdx.x; p < P; p += (long long)gridDim.x * NT) {
-        long long lo = 0, hi = E;                       // largest e with off[e] <= p
-        while (hi - lo > 1) {
-            const long long mid = (lo + hi) >> 1;
-            if (__ldg(off + mid) <= p) lo = mid; else hi = mid;
+        long long e;
+        int K, k;
+        if (off == nullptr) {                               // common K
+            K = K_all;
+            e = p / (K + 1);
+            k = (int)(p - e * (K + 1));
+        } else {
+            long long lo = 0, hi = E;                       // largest e with off[e] <= p
+            while (hi - lo > 1) {
+                const long long mid = (lo + hi) >> 1;
+                if (__ldg(off + mid) <= p) lo = mid; else hi = mid;
+            }
+            e = lo;
+            const long long o0 = __ldg(off + e);
+            K = (int)(__ldg(off + e + 1) - o0) - 1;
+            k = (int)(p - o0);
         }
-        const long long e = lo, o0 = __ldg(off + e);
-        const int K = (int)(__ldg(off + e + 1) - o0) - 1, k = (int)(p - o0);
         float c[N];
         if (k == K) {
 #pragma unroll
@@ -674,44 +632,6 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_var_kernel(Scen
         const bool unsafe = r.hard_min <= thr_hard;
         const bool safe = r.self_ok && (r.soft_min > thr_soft) && !unsafe;
         if (!safe) atomicMin(first_bad + e, k);
-    }
-}
-
-// long edges (K + 1 > NT): one warp-strided thread loop per edge is not needed by any reference caller; they
-// are handled by the thread-per-edge fallback below (sequential over k with early exit, tsa.py:281-285).
-template <class RB, bool GRID>
-__global__ void __launch_bounds__(NT) edge_seq_kernel(SceneArgs sc, const float* __restrict__ q_from,
-                                                      const float* __restrict__ q_to, long long E, int K,
-                                                      float thr_soft, float thr_hard, uint8_t* __restrict__ valid,
-                                                      int* __restrict__ first_bad) {
-    constexpr int N = RB::N;
-    extern __shared__ __align__(16) float smem_raw[];
-    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
-    stage<N>(s, sc, nullptr, 0);
-    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
-    const float base_min = base_min_cta<RB>(s, sv);
-    for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < E; e += (long long)gridDim.x * NT) {
-        float a[N], d[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) { a[i] = __ldg(q_from + e * N + i); d[i] = __fsub_rn(__ldg(q_to + e * N + i), a[i]); }
-        int bad = -1;
-        for (int k = 0; k <= K && bad < 0; ++k) {
-            float c[N];
-            if (k == K) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) c[i] = __ldg(q_to + e * N + i);
-            } else {
-                const float t = __fdiv_rn((float)k, (float)K);
-#pragma unroll
-                for (int i = 0; i < N; ++i) c[i] = fmaf(t, d[i], a[i]);
-            }
-            CollideResult<RB> r;
-            collide_state<RB, false, false, GRID>(c, sv, base_min, r);
-            const bool unsafe = r.hard_min <= thr_hard;
-            if (!(r.self_ok && (r.soft_min > thr_soft) && !unsafe)) bad = k;
-        }
-        valid[e] = bad < 0;
-        first_bad[e] = bad;
     }
 }
 
@@ -1014,27 +934,18 @@ static int launch_safety(const SceneArgs& sc, const NetArgs& net, const float* q
 }
 
 template <class RB>
+static int launch_edges_var(const SceneArgs& sc, const float* qf, const float* qt, long long E, const long long* off,
+                            int K_all, long long P, float ts, float th, uint8_t* valid, int* first_bad, cudaStream_t st);
+
+template <class RB>
 static int launch_edges(const SceneArgs& sc, const float* qf, const float* qt, long long E, int K, float ts, float th,
                         uint8_t* valid, int* first_bad, cudaStream_t st) {
-    const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
-    if (K + 1 <= NT) {
-        const int epb = NT / (K + 1);
-        auto k = sc.grid ? edge_kernel<RB, true> : edge_kernel<RB, false>;
-        const int grid = grid_for(k, smem, (E + epb - 1) / epb);
-        if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NT, smem, st>>>(sc, qf, qt, E, K, epb, ts, th, valid, first_bad);
-    } else {
-        auto k = sc.grid ? edge_seq_kernel<RB, true> : edge_seq_kernel<RB, false>;
-        const int grid = grid_for(k, smem, (E + NT - 1) / NT);
-        if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NT, smem, st>>>(sc, qf, qt, E, K, ts, th, valid, first_bad);
-    }
-    return finish_launch();
+    return launch_edges_var<RB>(sc, qf, qt, E, nullptr, K, E * (long long)(K + 1), ts, th, valid, first_bad, st);
 }
 
 template <class RB>
 static int launch_edges_var(const SceneArgs& sc, const float* qf, const float* qt, long long E, const long long* off,
-                            long long P, float ts, float th, uint8_t* valid, int* first_bad, cudaStream_t st) {
+                            int K_all, long long P, float ts, float th, uint8_t* valid, int* first_bad, cudaStream_t st) {
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
     const int eg = (int)((E + 255) / 256 < 1184 ? (E + 255) / 256 : 1184);
     edge_var_init<<<eg, 256, 0, st>>>(first_bad, E);
@@ -1043,7 +954,7 @@ static int launch_edges_var(const SceneArgs& sc, const float* qf, const float* q
         auto k = sc.grid ? edge_var_kernel<RB, true> : edge_var_kernel<RB, false>;
         const int grid = grid_for(k, smem, (P + NT - 1) / NT);
         if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NT, smem, st>>>(sc, qf, qt, E, off, P, ts, th, first_bad);
+        k<<<grid, NT, smem, st>>>(sc, qf, qt, E, off, K_all, P, ts, th, first_bad);
         if (finish_launch()) return CBFRRT_ERR_CUDA;
     }
     edge_var_finish<<<eg, 256, 0, st>>>(first_bad, valid, E);

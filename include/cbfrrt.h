@@ -192,7 +192,8 @@ int cbfrrt_safety_filter_scatter(int robot, const cbfrrt_scene *scene, const cbf
 /* ---- K10 edge validity -----------------------------------------------------------------------------------
  * Replaces edge_checking (motion_planning/baseline/tsa.py:272-286) for E edges with a fixed number n_interp
  * of interpolation points: valid <=> safe(q_to) and safe(q_from + k/n_interp (q_to - q_from)), k=0..n_interp-1.
- * first_bad = smallest failing along-edge index (k, or n_interp for the end point), -1 if the edge is valid. */
+ * first_bad = smallest failing along-edge index (k, or n_interp for the end point), -1 if the edge is valid.
+ * Three launches (preset, one thread per (edge, point), finish); every point is evaluated. */
 int cbfrrt_edge_validity(int robot, const cbfrrt_scene *scene, const float *q_from, const float *q_to, int64_t E,
                          int32_t n_interp, float thr_soft, float thr_hard, uint8_t *valid, int32_t *first_bad,
                          void *stream);
