@@ -226,7 +226,7 @@ __host__ __device__ __forceinline__ void qp_solve(const float (&a)[N], const flo
 // u(mu) = clip(u_ref - sum_i mu_i a_i / 2).  One iteration =
 //   (1) a cyclic sweep of exact coordinate maximisations -- each the single-constraint root find qp_mu on the target
 //       shifted by the other multipliers;
-//   (2) up to 4 Newton steps on the current active set (free multipliers W, unclipped coordinates F):
+//   (2) up to S + 2 Newton steps on the current active set (free multipliers W, unclipped coordinates F):
 //       (A_WF A_WF^T / 2 + eps I) d = g_W, followed by an EXACT line search: along d the directional derivative is
 //       d.c + w.clip(t - alpha w / 2) with w = A^T d, i.e. qp_mu again with (a, c, p) := (w, d.c, alpha_max).
 // Both moves increase the dual monotonically; (1) guarantees convergence, (2) terminates finitely once the active set
@@ -269,10 +269,10 @@ __host__ __device__ __forceinline__ int qp_solve_multi(const T (&a)[S][N], const
                 for (int k = 0; k < N; ++k) t[k] = fma(-T(0.5) * m, a[i][k], ti[k]);
             }
         }
-        const T stop = tol * (T(1.) + shift);
+        const T stop = fma(sizeof(T) == 8 ? T(4e-15) : T(2e-6), shift, tol);   // tol + rounding floor of t
         if (moved <= stop) break;
         if (n_con < 2) continue;
-        for (int rep = 0; rep < 4; ++rep) {
+        for (int rep = 0; rep < S + 2; ++rep) {
             T g[S], d[S], M[S][S];
             bool inW[S], isF[N];
             int nW = 0;
@@ -348,7 +348,8 @@ __host__ __device__ __forceinline__ int qp_solve_multi(const T (&a)[S][N], const
             for (int i = 0; i < S; ++i) mu[i] = fmin(fmax(fma(al, d[i], mu[i]), T(0.)), p);
 #pragma unroll
             for (int k = 0; k < N; ++k) t[k] = fma(-T(0.5) * al, w[k], t[k]);
-            if (!(al * wmax > stop)) break;
+            // a step cut short by a multiplier bound changes the active set: go on, however small it was in u
+            if (al < amax && !(al * wmax > stop)) break;
         }
     }
 #pragma unroll

@@ -411,7 +411,7 @@ static void qp_exact(int n, const double *a, const double *uref, const double *l
 #define MAXS 8
 #define KINK_TOL 1e-9 /* coordinates sitting on a kink of the dual count as free: the step must not leave the kink */
 #ifndef NEWTON_REPS
-#define NEWTON_REPS 4
+#define NEWTON_REPS 6
 #endif
 static int qp_multi_exact(int n, int S, const double *a /* [S][n] */, const double *uref, const double *lo,
                           const double *hi, const double *c, double p, int max_iter, double tol, double *u, double *r) {
@@ -497,7 +497,7 @@ static int qp_multi_exact(int n, int S, const double *a /* [S][n] */, const doub
             mu[i] = mu[i] < 0.0 ? 0.0 : (mu[i] > p ? p : mu[i]);
         }
         for (int k = 0; k < n; ++k) t[k] -= 0.5 * al * w[k];
-        if (!(al * wmax > stop)) break;
+        if (al < amax && !(al * wmax > stop)) break; /* a step cut short by a multiplier bound changed the active set */
         }
     }
     for (int k = 0; k < n; ++k) u[k] = t[k] < lo[k] ? lo[k] : (t[k] > hi[k] ? hi[k] : t[k]);

@@ -101,3 +101,16 @@ def qp_kkt_residual(a, c, u_ref, lo, hi, p, u, tol=2e-5):
     res = linprog(np.concatenate([np.zeros(S), [1.0]]), A_ub=np.array(A), b_ub=np.array(bvec), bounds=bounds + [(0, None)])
     assert res.status == 0, res.message
     return float(res.x[-1])
+
+
+def degenerate_qp_batch(seed=3, n=4, S=3, B=2000):
+    """multi-constraint QP rows with duplicate, zero and (anti-)parallel constraint rows"""
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(B, S, n)).astype(np.float32)
+    c = rng.normal(scale=0.8, size=(B, S)).astype(np.float32)
+    ur = rng.uniform(-1.5, 1.5, size=(B, n)).astype(np.float32)
+    a[:500, 1] = a[:500, 0]                      # duplicate rows (singular Newton matrix)
+    c[:250, 1] = c[:250, 0]
+    a[500:1000, 2] = 0                           # zero row: a positive c can only be relaxed
+    a[1000:1200] = -a[1000:1200, :1] * np.array([1, -1, 1], np.float32)[None, :, None]   # parallel / anti-parallel
+    return a, c, ur

@@ -573,3 +573,18 @@ def test_registered_ops_equal_direct_calls():
     assert ops.fk.op is ops.registered["fk"]
     with pytest.raises(NotImplementedError):
         ops.fk(q.cpu(), 0)
+
+
+def test_qp_multi_degenerate_constraints_gpu(coracle):
+    """duplicate / zero / (anti-)parallel constraint rows on the device solver: same controls as the oracle"""
+    from cbfrrt import ops
+    from conftest import degenerate_qp_batch
+    a, c, ur = degenerate_qp_batch()
+    lo, hi = -np.ones(4, np.float32), np.ones(4, np.float32)
+    for p in (50.0, 1e9):
+        uo, ro = coracle.qp_multi(a, c, ur, lo, hi, p, max_iter=300)
+        u, r, it = ops.qp_multi(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p, 100, 1e-9)
+        u, r = u.cpu().numpy(), r.cpu().numpy()
+        assert np.isfinite(u).all() and np.isfinite(r).all()
+        assert rel_err(u, uo) < 1e-5 and np.allclose(r, ro, atol=1e-4 + 1e-6 * min(p, 1e6))
+        assert it.cpu().numpy().max() <= 12

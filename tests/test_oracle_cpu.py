@@ -201,3 +201,18 @@ def test_knn_oracle_matches_numpy(coracle):
         assert (idx[:, 5:] == -1).all() and np.isinf(dist[:, 5:]).all() and (np.sort(idx[:, :5], 1) == np.arange(5)).all()
         within = coracle.radius_mask(samples, tree, 1.3)
         assert np.mean(within.astype(bool) == (d <= 1.3)) > 0.9999   # fp32 vs fp64 at the boundary
+
+
+def test_qp_multi_degenerate_constraints(coracle):
+    """duplicate / zero / (anti-)parallel constraint rows (singular Newton matrices, flat dual ridges): finite, feasible,
+    KKT-optimal controls within a handful of iterations"""
+    from conftest import qp_kkt_residual, degenerate_qp_batch
+    a, c, ur = degenerate_qp_batch()
+    lo, hi = -np.ones(4, np.float32), np.ones(4, np.float32)
+    for p in (50.0, 1e9):
+        u, r, it = coracle.qp_multi(a, c, ur, lo, hi, p, max_iter=300, want_iters=True)
+        assert np.isfinite(u).all() and np.isfinite(r).all() and (np.abs(u) <= 1).all() and (r >= 0).all()
+        assert it.max() <= 12, it.max()
+        np.testing.assert_allclose(r[500:1000, 2], np.maximum(c[500:1000, 2], 0), atol=1e-5)
+        rows = list(range(0, a.shape[0], 9)) + list(np.where(it > 12)[0])
+        assert max(qp_kkt_residual(a[b], c[b], ur[b], lo, hi, min(p, 1e6), u[b]) for b in rows) < 1e-4 * max(1, min(p, 1e6) * 1e-3)
