@@ -114,3 +114,19 @@ def degenerate_qp_batch(seed=3, n=4, S=3, B=2000):
     a[500:1000, 2] = 0                           # zero row: a positive c can only be relaxed
     a[1000:1200] = -a[1000:1200, :1] * np.array([1, -1, 1], np.float32)[None, :, None]   # parallel / anti-parallel
     return a, c, ur
+
+
+def edge_case_qp_batch(seed=8, n=7, B=3000):
+    """single-constraint QP rows with zero / partly zero / tiny / huge gradients and u_ref on the box, asymmetric limits"""
+    rng = np.random.default_rng(seed)
+    lo = -np.abs(rng.normal(1, 0.3, n)).astype(np.float32)
+    hi = np.abs(rng.normal(1, 0.3, n)).astype(np.float32)
+    a = rng.normal(size=(B, n)).astype(np.float32)
+    c = rng.normal(size=B).astype(np.float32)
+    ur = rng.uniform(-2, 2, size=(B, n)).astype(np.float32)
+    a[:300] = 0
+    a[300:600, ::2] = 0
+    ur[600:900] = np.where(rng.random((300, n)) < 0.5, lo, hi)
+    a[900:1000] *= 1e-6
+    a[1000:1100] *= 1e4
+    return a, c, ur, lo, hi

@@ -588,3 +588,20 @@ def test_qp_multi_degenerate_constraints_gpu(coracle):
         assert np.isfinite(u).all() and np.isfinite(r).all()
         assert rel_err(u, uo) < 1e-5 and np.allclose(r, ro, atol=1e-4 + 1e-6 * min(p, 1e6))
         assert it.cpu().numpy().max() <= 12
+
+
+def test_qp_single_edge_cases_gpu(coracle):
+    """cbfrrt::qp on zero / partly zero / tiny / huge gradients, u_ref on the box, asymmetric limits"""
+    from cbfrrt import ops
+    from conftest import edge_case_qp_batch
+    a, c, ur, lo, hi = edge_case_qp_batch()
+    for p in (0.0, 0.05, 5000.0, 1e9):
+        uo, ro = coracle.qp(a, c, ur, lo, hi, p)
+        u, r = ops.qp(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p)
+        u, r = u.cpu().numpy(), r.cpu().numpy()
+        assert np.isfinite(u).all() and np.isfinite(r).all() and (u >= lo).all() and (u <= hi).all() and (r >= 0).all()
+        well = np.r_[0:900, 1100:len(c)]               # rows whose gradient is O(1): fp32 holds 2e-5
+        assert rel_err(u[well], uo[well]) < 2e-5 and rel_err(r[well], ro[well], floor=0.1) < 2e-5
+        # tiny / huge gradients: the answer is only as good as fp32 carries the constraint value c + a.u
+        g = c[900:1100].astype(np.float64) + np.einsum("bk,bk->b", a[900:1100].astype(np.float64), u[900:1100])
+        assert np.all(g - r[900:1100] <= 1e-5 * (1 + np.abs(c[900:1100]) + np.abs(a[900:1100]).sum(1)))

@@ -216,3 +216,16 @@ def test_qp_multi_degenerate_constraints(coracle):
         np.testing.assert_allclose(r[500:1000, 2], np.maximum(c[500:1000, 2], 0), atol=1e-5)
         rows = list(range(0, a.shape[0], 9)) + list(np.where(it > 12)[0])
         assert max(qp_kkt_residual(a[b], c[b], ur[b], lo, hi, min(p, 1e6), u[b]) for b in rows) < 1e-4 * max(1, min(p, 1e6) * 1e-3)
+
+
+def test_qp_single_edge_cases(coracle):
+    """zero / partly zero / tiny / huge gradients, u_ref on the box, asymmetric limits, penalties 0 .. 1e9 (clamped):
+    finite, inside the box, r >= 0, KKT-optimal"""
+    from conftest import qp_kkt_residual, edge_case_qp_batch
+    a, c, ur, lo, hi = edge_case_qp_batch()
+    for p in (0.0, 0.05, 5000.0, 1e9):
+        u, r = coracle.qp(a, c, ur, lo, hi, p)
+        assert np.isfinite(u).all() and np.isfinite(r).all() and (u >= lo).all() and (u <= hi).all() and (r >= 0).all()
+        if p > 0:
+            np.testing.assert_allclose(r[:300], np.maximum(c[:300], 0), atol=1e-6)      # a = 0: only relaxation helps
+        assert max(qp_kkt_residual(a[b:b + 1], c[b:b + 1], ur[b], lo, hi, min(p, 1e6), u[b]) for b in range(0, len(c), 3)) < 1e-5
