@@ -605,3 +605,37 @@ def test_qp_single_edge_cases_gpu(coracle):
         # tiny / huge gradients: the answer is only as good as fp32 carries the constraint value c + a.u
         g = c[900:1100].astype(np.float64) + np.einsum("bk,bk->b", a[900:1100].astype(np.float64), u[900:1100])
         assert np.all(g - r[900:1100] <= 1e-5 * (1 + np.abs(c[900:1100]) + np.abs(a[900:1100]).sum(1)))
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+@pytest.mark.parametrize("use_grid", [False, True])
+def test_collide_degenerate_scene_elements(coracle, robot, use_grid):
+    """zero-size boxes, a box that swallows part of the arm (sphere centres INSIDE: negative distances, interior
+    normals), exact duplicates (arg-min ties -> lowest index), zero-radius spheres, obstacles outside the grid region"""
+    from cbfrrt import ops, workloads as W
+    rid, n = ops.ROBOT_ID[robot], (7 if robot == "panda" else 4)
+    rng = np.random.default_rng(31)
+    boxes = [[0.35, 0.0, 0.45, 0.25, 0.3, 0.3],          # big: the arm reaches into it
+             [0.2, 0.3, 0.2, 0.0, 0.0, 0.0],              # a point
+             [-0.3, 0.2, 0.6, 0.1, 0.0, 0.1],             # a plate
+             [0.35, 0.0, 0.45, 0.25, 0.3, 0.3],           # exact duplicate of box 0
+             [3.0, 3.0, 3.0, 0.1, 0.1, 0.1]]              # outside the grid region
+    spheres = [[0.0, -0.4, 0.5, 0.0], [0.0, -0.4, 0.5, 0.0], [-0.4, -0.3, 0.3, 0.15], [5.0, 0.0, 0.0, 1.0]]
+    if use_grid:                                          # the grid is only used from 40 obstacles on
+        extra = W.random_boxes(40, 8, 0.01, 0.04)
+        extra[:, :3] += np.array([0.0, 0.0, 0.9], np.float32)
+        boxes = boxes + extra.tolist()
+    boxes, spheres = np.array(boxes, np.float32), np.array(spheres, np.float32)
+    q = W.sample_states(robot, 30000, 17)
+    b8, s4 = ops.pack_scene(boxes[:, :3], boxes[:, 3:], spheres, device="cuda")
+    gr = ops.build_grid(b8, s4) if use_grid else ops.no_grid("cuda")
+    for floor in (1, 0):
+        o = coracle.collide(robot, q, boxes, spheres, bool(floor), 0.02, 0.0)
+        safe, unsafe, datax, arg_link, arg_obs, mins = ops.collide(_t(q), b8, s4, floor, gr, 0.02, 0.0, rid)
+        assert np.array_equal(safe.cpu().numpy(), o["safe"]) and np.array_equal(unsafe.cpu().numpy(), o["unsafe"])
+        assert np.array_equal(datax.cpu().numpy()[:, n], o["datax"][:, n])
+        assert np.array_equal(arg_link.cpu().numpy(), o["arg_link"]) and np.array_equal(arg_obs.cpu().numpy(), o["arg_obs"])
+        assert rel_err(datax.cpu().numpy()[:, n + 1:], o["datax"][:, n + 1:]) < 1e-5
+        assert (o["datax"][:, n] < 0).mean() > 0.02, "the case must contain penetrating states"
+        off = 1 if floor else 0
+        assert not np.any(o["arg_obs"] == off + 3), "a duplicate never wins against its lower-index twin"
