@@ -639,3 +639,33 @@ def test_collide_degenerate_scene_elements(coracle, robot, use_grid):
         assert (o["datax"][:, n] < 0).mean() > 0.02, "the case must contain penetrating states"
         off = 1 if floor else 0
         assert not np.any(o["arg_obs"] == off + 3), "a duplicate never wins against its lower-index twin"
+
+
+@pytest.mark.parametrize("keep_going", [False, True])
+def test_rollout_variants_tensor_core_path(coracle, keep_going):
+    """Magician, 20000 trajectories (tcgen05 kernels), 25 steps with ctrl_every = 3 (steps not a multiple), no stored
+    trajectory, keep_going on / off, per-row goals; steps = 0 is a no-op"""
+    from cbfrrt import ops, workloads as W
+    w = W.config(1, scale=1e-9)
+    b8, s4, gr = _scene(w["boxes"], w["spheres"])
+    T = 20000
+    q0 = W.sample_states("magician", T, 41)
+    goal = W.sample_states("magician", T, 42)
+    args = (b8, s4, 1, gr, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"], w["thr_soft"],
+            w["thr_hard"], 1, 48, 2)
+    qf, alive, done, traj = ops.rollout(_t(q0), _t(goal), 25, 3, 1 / 120, 0, 10, 0.1, False, keep_going, *args)
+    assert traj.numel() == 0
+    qo, ao, do_, _ = coracle.rollout("magician", q0, goal, 25, 3, 1 / 120, w["boxes"], None, True, w["weights"], 48, 2,
+                                     w["K"], w["u_lo"], w["u_hi"], w["thr_soft"], w["thr_hard"], w["lam"], w["penalty"],
+                                     keep_going=keep_going)
+    same = (alive.cpu().numpy() == ao) & (done.cpu().numpy() == do_)
+    assert same.mean() > 0.995
+    # an ill-conditioned QP (a free axis with a tiny |Lg_i|) amplifies the 1e-7 difference of the two MLP evaluations
+    # and the closed loop carries it along: 1e-4 on all but a few rows, bounded everywhere (DESIGN.md section 6)
+    err = np.abs(qf.cpu().numpy()[same] - qo[same]).max(1)
+    assert np.mean(err < 1e-4) > 0.995 and err.max() < 5e-2, (np.mean(err < 1e-4), err.max())
+    assert (ao == 0).sum() > 100 and (ao == 1).sum() > 100
+    if keep_going:
+        assert (do_[ao == 0] == 25).mean() > 0.5 or (do_ <= 25).all()
+    q1, a1, d1, _ = ops.rollout(_t(q0), _t(goal), 0, 3, 1 / 120, 0, 10, 0.1, False, keep_going, *args)
+    assert torch.equal(q1.cpu(), torch.from_numpy(q0)) and (d1 == 0).all() and a1.all()
