@@ -29,6 +29,17 @@ def test_reference_arm_line():
     assert r["config"]["workload"].startswith("cfg1") and r["vs_baseline"] is None
 
 
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: rank 0 alone runs the reference arm and prints it, the other ranks exit 0 without output"""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300),
+                          os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+                          "--scale", "0.01"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().split("\n") if l.startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["impl"] == "reference" and json.loads(lines[0])["n_gpus"] == 2
+
+
 @pytest.mark.gpu
 def test_gpu_arm_line():
     r = _run("--steps", "3", "--warmup", "3", "--scale", "0.125")
