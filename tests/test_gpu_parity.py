@@ -669,3 +669,26 @@ def test_rollout_variants_tensor_core_path(coracle, keep_going):
         assert (do_[ao == 0] == 25).mean() > 0.5 or (do_ <= 25).all()
     q1, a1, d1, _ = ops.rollout(_t(q0), _t(goal), 0, 3, 1 / 120, 0, 10, 0.1, False, keep_going, *args)
     assert torch.equal(q1.cpu(), torch.from_numpy(q0)) and (d1 == 0).all() and a1.all()
+
+
+@pytest.mark.parametrize("cfg", [1, 4])
+def test_full_size_obstacle_permutation_invariance(cfg):
+    """BASELINE configs 1 (2^20 Magician states, 16 boxes, culled brute force) and 4 (2^21-state slice, 256 boxes,
+    grid broad phase): minima and masks are bit-identical under a permutation of the obstacles, the arg-min follows it"""
+    from cbfrrt import ops, workloads as W
+    w = W.config(cfg, scale=1.0 if cfg == 1 else 1 / 32)
+    rid, n = ops.ROBOT_ID[w["robot"]], w["n"]
+    q = _t(w["q"]) if w["q"] is not None else ops.sample_states(w["n_states"], w["sample_seed"], 0, rid, device="cuda")
+    boxes = w["boxes"]
+    perm = np.random.default_rng(5).permutation(len(boxes))
+    res = []
+    for bx in (boxes, boxes[perm]):
+        b8, s4 = ops.pack_scene(bx[:, :3], bx[:, 3:], w["spheres"], device="cuda")
+        gr = ops.build_grid(b8, s4)
+        res.append(ops.collide(q, b8, s4, 1, gr, 0.02, 0.0, rid))
+    (s0, u0, d0, l0, o0, _), (s1, u1, d1, l1, o1, _) = res
+    assert torch.equal(s0, s1) and torch.equal(u0, u1) and torch.equal(d0[:, n], d1[:, n]) and torch.equal(l0, l1)
+    is_box = (o0 >= 1) & (o0 <= len(boxes))
+    p = torch.as_tensor(perm, device="cuda")
+    assert torch.equal(p[(o1[is_box] - 1).long()], (o0[is_box] - 1).long())
+    assert is_box.float().mean() > 0.3 and 0.02 < s0.float().mean() < 0.98

@@ -229,3 +229,24 @@ def test_qp_single_edge_cases(coracle):
         if p > 0:
             np.testing.assert_allclose(r[:300], np.maximum(c[:300], 0), atol=1e-6)      # a = 0: only relaxation helps
         assert max(qp_kkt_residual(a[b:b + 1], c[b:b + 1], ur[b], lo, hi, min(p, 1e6), u[b]) for b in range(0, len(c), 3)) < 1e-5
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_scene_permutation_and_monotonicity_properties(coracle, robot):
+    """size-independent properties of the distance stage: the minimum and the masks do not depend on the obstacle
+    order (the arg-min follows the permutation), and adding an obstacle can only lower the minimum / clear `safe`"""
+    from cbfrrt import workloads as W
+    q = W.sample_states(robot, 3000, 23)
+    boxes, spheres = W.random_boxes(9, 12, 0.03, 0.12), W.random_spheres(4, 13, 0.03, 0.1)
+    n = q.shape[1]
+    base = coracle.collide(robot, q, boxes, spheres, True, 0.02, 0.0)
+    perm = np.random.default_rng(1).permutation(len(boxes))
+    pr = coracle.collide(robot, q, boxes[perm], spheres, True, 0.02, 0.0)
+    assert np.array_equal(base["safe"], pr["safe"]) and np.array_equal(base["unsafe"], pr["unsafe"])
+    assert np.array_equal(base["datax"][:, n], pr["datax"][:, n])
+    is_box = (base["arg_obs"] >= 1) & (base["arg_obs"] <= len(boxes))
+    assert np.array_equal(perm[pr["arg_obs"][is_box] - 1], base["arg_obs"][is_box] - 1)
+    more = coracle.collide(robot, q, np.concatenate([boxes, W.random_boxes(3, 14, 0.05, 0.15)]), spheres, True, 0.02, 0.0)
+    assert np.all(more["datax"][:, n] <= base["datax"][:, n]) and not np.any(more["safe"] & ~base["safe"])
+    assert not np.any(base["unsafe"] & ~more["unsafe"])
+    assert np.any(more["datax"][:, n] < base["datax"][:, n])
