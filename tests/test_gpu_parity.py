@@ -692,3 +692,22 @@ def test_full_size_obstacle_permutation_invariance(cfg):
     p = torch.as_tensor(perm, device="cuda")
     assert torch.equal(p[(o1[is_box] - 1).long()], (o0[is_box] - 1).long())
     assert is_box.float().mean() > 0.3 and 0.02 < s0.float().mean() < 0.98
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_geometry_contract_fixture_gpu(robot):
+    """the CUDA kernels against the committed geometry fixture (tests/golden/geometry_contract_*.npz): masks, minimum,
+    arg-min and FK bit-identical, gradient within 1e-5"""
+    import os
+    from cbfrrt import ops
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"geometry_contract_{robot}.npz"))
+    rid, n = ops.ROBOT_ID[robot], g["q"].shape[1]
+    b8, s4 = ops.pack_scene(g["boxes"][:, :3], g["boxes"][:, 3:], g["spheres"], device="cuda")
+    for floor in (1, 0):
+        safe, unsafe, datax, arg_link, arg_obs, _ = ops.collide(_t(g["q"]), b8, s4, floor, ops.no_grid("cuda"), 0.02, 0.0, rid)
+        assert np.array_equal(safe.cpu().numpy(), g[f"safe_floor{floor}"]) and np.array_equal(unsafe.cpu().numpy(), g[f"unsafe_floor{floor}"])
+        assert np.array_equal(datax.cpu().numpy()[:, :n + 1], g[f"datax_floor{floor}"][:, :n + 1])
+        assert np.array_equal(arg_link.cpu().numpy(), g[f"arg_link_floor{floor}"]) and np.array_equal(arg_obs.cpu().numpy(), g[f"arg_obs_floor{floor}"])
+        assert rel_err(datax.cpu().numpy()[:, n + 1:], g[f"datax_floor{floor}"][:, n + 1:]) < 1e-5
+    pos, rot = ops.fk(_t(g["q"][:50]), rid)
+    assert np.array_equal(pos.cpu().numpy(), g["fk_pos"]) and np.array_equal(rot.cpu().numpy().reshape(g["fk_rot"].shape), g["fk_rot"])

@@ -250,3 +250,17 @@ def test_scene_permutation_and_monotonicity_properties(coracle, robot):
     assert np.all(more["datax"][:, n] <= base["datax"][:, n]) and not np.any(more["safe"] & ~base["safe"])
     assert not np.any(base["unsafe"] & ~more["unsafe"])
     assert np.any(more["datax"][:, n] < base["datax"][:, n])
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_geometry_contract_fixture(coracle, robot):
+    """tests/golden/geometry_contract_*.npz (make_geometry_golden.py): the sphere model, the exemption rules and the
+    float32 operation order have not drifted -- bit for bit"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"geometry_contract_{robot}.npz"))
+    for floor in (1, 0):
+        o = coracle.collide(robot, g["q"], g["boxes"], g["spheres"], bool(floor), 0.02, 0.0)
+        for k in ("safe", "unsafe", "datax", "arg_link", "arg_obs"):
+            assert np.array_equal(o[k], g[f"{k}_floor{floor}"]), (k, floor)
+    pos, rot = coracle.fk(robot, g["q"][:50])
+    assert np.array_equal(pos, g["fk_pos"]) and np.array_equal(rot, g["fk_rot"])
