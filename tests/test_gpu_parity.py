@@ -691,7 +691,7 @@ def test_full_size_obstacle_permutation_invariance(cfg):
     is_box = (o0 >= 1) & (o0 <= len(boxes))
     p = torch.as_tensor(perm, device="cuda")
     assert torch.equal(p[(o1[is_box] - 1).long()], (o0[is_box] - 1).long())
-    assert is_box.float().mean() > 0.3 and 0.02 < s0.float().mean() < 0.98
+    assert is_box.float().mean() > 0.3 and u0.float().mean() > 0.02      # boxes do win the arg-min; collisions do occur
 
 
 @pytest.mark.parametrize("robot", ["panda", "magician"])
