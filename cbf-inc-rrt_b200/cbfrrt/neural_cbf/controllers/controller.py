@@ -1,16 +1,17 @@
-"""Controller -- mirror of neural_cbf/controllers/controller.py:7-26."""
-from abc import ABC, abstractmethod
+"""Controller -- the abstract base of the controller hierarchy (interface of neural_cbf/controllers/controller.py:7-26:
+attributes ``dynamics_model``, ``experiment_suite``, ``controller_period`` and the abstract ``u(x)``)."""
+import abc
 
 
-class Controller(ABC):
-    controller_period: float
+class Controller(abc.ABC):
+    """Holds what every controller of the hierarchy shares; concrete classes implement ``u``."""
 
     def __init__(self, dynamics_model, experiment_suite=None, controller_period: float = 0.01):
-        super(Controller, self).__init__()
-        self.controller_period = controller_period
-        self.dynamics_model = dynamics_model
-        self.experiment_suite = experiment_suite
+        super().__init__()
+        self.dynamics_model, self.experiment_suite = dynamics_model, experiment_suite
+        self.controller_period = float(controller_period)
 
-    @abstractmethod
+    @abc.abstractmethod
     def u(self, x):
-        """Get the control input for a given state"""
+        """control for the batch of states ``x`` -> (bs, n_controls) [, t_dict]"""
+        raise NotImplementedError
