@@ -307,9 +307,9 @@ def main():
     tensor_src = "measured (dense bf16, MEASURED_PEAKS.json)" if tensor_peak else "fallback (nominal dense bf16)"
     tensor_peak = tensor_peak or 2250.0
     # DRAM traffic of one launch from the committed ncu --set full capture of this exact command
-    # (profiles/r1d_ncu_full_safety_kernel_tc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum); only valid for the
+    # (profiles/r1e_ncu_full_safety_kernel_tc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum); only valid for the
     # default workload at N=1, else null
-    traffic = 44.6e6 if (world == 1 and cfg_idx == 1 and B == 1 << 20) else None
+    traffic = 45.3e6 if (world == 1 and cfg_idx == 1 and B == 1 << 20) else None
     mlp_flops = 2 * 2 * ((n + 1) * 48 + 2 * 48 * 48 + 48)
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
                 "traffic": traffic, "peak_source": "cbfrrt_fma_probe in this run (FP32 FMA; not in MEASURED_PEAKS.json)",

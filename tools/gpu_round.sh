@@ -1,7 +1,5 @@
-# one GPU round: the GPU test suite, the bench line, per-config timings, smoke
+# one GPU round: ncu --set full capture of the bench kernel (after a plain run), then the GPU test suite
 set -x
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/plain_b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:safety_kernel_tc -s 40 -c 1 -o gpurun_out/prof_safety_tc_r1e python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_e.log 2>&1
+ls -la gpurun_out/prof_safety_tc_r1e.ncu-rep
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; cut -c1-260 gpurun_out/bench_final.json
-python tools/measure_configs.py --cpu > gpurun_out/configs_final.jsonl 2> gpurun_out/configs_final.err; tail -2 gpurun_out/configs_final.err
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/plain_b.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
