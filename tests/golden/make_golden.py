@@ -12,6 +12,8 @@ that and records inputs/outputs of the reference's own functions:
   neural_cbf/controllers/neural_mindis_cbf_controller.py:41-53,71-102    h, h_with_jacobian (autograd)
   neural_cbf/controllers/clf_controller.py:169-218                       V_with_lie_derivatives
   neural_cbf/controllers/clf_controller.py:354-404,461-535               solve_CLF_QP / u  (parameter assembly)
+  neural_cbf/systems/arm_dynamics.py:474-523                             closed_loop_dynamics (Euler step, no refresh)
+  neural_cbf/systems/control_affine_system.py:200-216                    out_of_bounds_mask
 
 What is stubbed and therefore NOT pinned by these vectors:
   * pybullet: the `robot`/`env` objects handed to ArmMindis are fakes exposing only joint limits, velocity
@@ -174,6 +176,9 @@ class _FakeRobot:
         self.body_range = np.array([(model["q_lower"][i], model["q_upper"][i]) for i in range(model["n"])])
         self.q0 = np.array(model["q0"])
 
+    def set_joint_position(self, joints, q):       # pybullet resetJointState: irrelevant to the arithmetic recorded here
+        pass
+
 
 class _FakeEnv:
     def __init__(self, model):
@@ -235,6 +240,14 @@ def main():
                         f"{tag}_V": V.detach().numpy(), f"{tag}_Lf": Lf.detach().numpy(),
                         f"{tag}_Lg": Lg.detach().numpy(), f"{tag}_u_ref": u_ref.detach().numpy(),
                         f"{tag}_u": u.detach().numpy(), f"{tag}_r": r.detach().numpy()})
+        # Euler step of closed_loop_dynamics without the observation refresh (arm_dynamics.py:474-523, pure torch once
+        # set_joint_position is a no-op) and the out-of-bounds mask (control_affine_system.py:200-216)
+        dyn.set_goal(goal_shared)
+        x_next = dyn.closed_loop_dynamics(datax, torch.tensor(out["shared_u"]).float(), update_observation=False)
+        x_wide = datax.clone()
+        x_wide[::5, 0] += 10.0
+        x_wide = x_wide[:, :n]        # the reference indexes the limits with the column index: q columns only
+        out.update(cld_x_next=x_next.detach().numpy(), oob_x=x_wide.numpy(), oob_mask=dyn.out_of_bounds_mask(x_wide).numpy())
         # state limits come back as (upper, lower): arm_dynamics.py:107-109
         s_up, s_lo = dyn.state_limits
         np.savez(os.path.join(HERE, f"ref_controller_{name}.npz"), datax=datax.numpy(), K=K,

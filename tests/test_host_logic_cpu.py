@@ -269,6 +269,20 @@ def test_batch_rrt_plan_builds_a_consistent_tree(stack):
     assert t.path() == ([], [], [], [])
 
 
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_dynamics_mirrors_match_reference_python(stack, golden, robot):
+    """closed_loop_dynamics without observation refresh (arm_dynamics.py:474-523) and out_of_bounds_mask
+    (control_affine_system.py:200-216) against the outputs of the reference's own code (tests/golden/make_golden.py)"""
+    env, rb, dyn, ctrl = stack(robot)
+    g = golden[robot]
+    x = torch.tensor(g["datax"])
+    x_next = dyn.closed_loop_dynamics(x, torch.tensor(g["shared_u"]).float(), update_observation=False)
+    assert x_next.shape == g["cld_x_next"].shape and torch.equal(x_next, torch.tensor(g["cld_x_next"]))
+    assert torch.equal(dyn.out_of_bounds_mask(torch.tensor(g["oob_x"])), torch.tensor(g["oob_mask"]))
+    up, lo = dyn.state_limits
+    assert np.allclose(up.numpy(), g["x_upper"]) and np.allclose(lo.numpy(), g["x_lower"])
+
+
 def test_basic_robot_kinematics(stack, models):
     env, robot, dyn, ctrl = stack("panda")
     from oracle import oracle_f64 as o
