@@ -25,10 +25,15 @@ def _load_reference_planner():
     pkg.__path__ = [BASE]
     sys.modules["ref_baseline"] = pkg
     mods = {}
-    for name in ("search_tree", "tsa", "batch_tsa"):
+    for name in ("search_tree", "tsa", "batch_tsa", "bit_star"):
         spec = importlib.util.spec_from_file_location(f"ref_baseline.{name}", os.path.join(BASE, f"{name}.py"))
         mod = importlib.util.module_from_spec(spec)
         sys.modules[spec.name] = mod
+        if name == "bit_star":       # it imports its siblings by their absolute names
+            for sib in ("tsa", "search_tree"):
+                sys.modules[f"motion_planning.baseline.{sib}"] = mods[sib]
+            sys.modules.setdefault("motion_planning", types.ModuleType("motion_planning"))
+            sys.modules.setdefault("motion_planning.baseline", types.ModuleType("motion_planning.baseline"))
         spec.loader.exec_module(mod)
         mods[name] = mod
     return mods
@@ -100,3 +105,27 @@ def test_reference_rrt_plan_runs_on_our_objects(world):
     pts = np.array([np.asarray(p)[:4] for e in res2["all_edge"][1:] for p in e])
     if len(pts):
         assert not dyn.unsafe_mask(torch.as_tensor(pts, dtype=torch.float32)).any()
+
+
+def test_reference_bit_star_runs_on_our_objects(world):
+    """BITStarPlanner (bit_star.py:12-305): is_point_free -> safe_mask, is_edge_free -> edge_checking, sampling bounds from
+    state_limits; a found path is re-validated edge by edge with this package's one-launch edge_checking"""
+    env, dyn, ctrl, xs, ref = world
+    from cbfrrt.motion_planning.baseline import edge_checking
+    init = xs[2]
+    goal = init + 0.4 * (xs[3] - init) / np.linalg.norm(xs[3] - init)
+    if not bool(dyn.safe_mask(torch.as_tensor(goal[None], dtype=torch.float32)).item()):
+        goal = xs[3]
+    np.random.seed(1)
+    planner = ref["bit_star"].BITStarPlanner(dyn, init, goal, batch_size=40, T=400, edge_eps=0.05)
+    vertices, edges, cost, T, dt = planner.plan(time_budget=120)
+    assert planner.dimension == 4 and planner.n_free_points > 2 and len(vertices) >= 1
+    assert cost < float("inf"), "a straight 0.4 rad move in free space must be found"
+    path = planner.get_best_path()
+    assert np.allclose(path[0], init) and np.allclose(path[-1], goal)
+    for a, b in zip(path[:-1], path[1:]):
+        assert edge_checking(np.array(a), np.array(b), dyn, 0.05)
+    # the module-level wrapper also executes the path with the nominal steer (bit_star.py:308-351)
+    np.random.seed(1)
+    res = ref["bit_star"].BITStar(env, dyn, init, goal, batch_size=40, T=400, EPS=0.05, time_budget=120)
+    assert res["success"] and len(res["path"]) >= 2 and res["explored_nodes"] >= 40
