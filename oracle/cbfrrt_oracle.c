@@ -9,7 +9,9 @@
  * 1.0.19 -> SCS 3.2.0; none is installed here and the reference ships no golden vectors.  Pinned pieces:
  * URDF constants, FK at q=0/q0 (hand-computed), LQR gain K (scipy DARE), and the MLP + Jacobian +
  * Lie-derivative + nominal-control code, which IS checked against the reference's own Python executed in
- * the dev container (tests/golden/make_golden.py).
+ * the dev container (tests/golden/make_golden.py), and the reference's loops AROUND the physics engine (link ranges,
+ * exemptions, arg-min, do/dq assembly), which are run unmodified on a stand-in client backed by this repo's sphere
+ * model and compared with this file (tests/test_reference_systems_cpu.py).  Unpinned: Bullet's own geometry.
  *
  * Reference code followed (file:line under /root/reference):
  *   FK of the URDF chain                 environment/basic_robot.py:55-68, utils/robot/{franka_panda/panda,magician/urdf/demo}.urdf
