@@ -36,7 +36,8 @@ def reference_classes():
         pybullet_data.getDataPath = lambda: ""
         from environment import ArmEnv              # noqa: E402  (reference code)
         from neural_cbf.systems import ArmMindis    # noqa: E402  (reference code)
-        yield ArmEnv, ArmMindis
+        from neural_cbf.controllers.neural_mindis_cbf_controller import NeuralMindisCBFController  # noqa: E402
+        yield ArmEnv, ArmMindis, NeuralMindisCBFController, mg
     finally:
         sys.meta_path.remove(finder)
         sys.path.remove(REF)
@@ -48,7 +49,7 @@ def reference_classes():
 
 @pytest.mark.parametrize("robot,floor", [("panda", True), ("magician", True), ("panda", False)])
 def test_reference_masks_and_observation_loops(reference_classes, coracle, tmp_path, robot, floor):
-    ArmEnv, ArmMindis = reference_classes
+    ArmEnv, ArmMindis = reference_classes[:2]
     from cbfrrt import workloads as W
     rng = np.random.default_rng(4)
     positions = rng.uniform([-0.5, -0.5, 0.05], [0.5, 0.5, 0.9], size=(1, 5, 3))
@@ -86,3 +87,61 @@ def test_reference_masks_and_observation_loops(reference_classes, coracle, tmp_p
     assert np.allclose(up.numpy(), W.ROBOT_MODELS[robot]["q_upper"]) and np.allclose(lo.numpy(), W.ROBOT_MODELS[robot]["q_lower"])
     cu, cl = dyn.control_limits
     assert np.allclose(cu.numpy(), W.ROBOT_MODELS[robot]["v_max"]) and torch.equal(cl, -cu)
+
+
+def test_whole_reference_stack_steers_like_this_package(reference_classes, coracle, tmp_path, monkeypatch):
+    """The reference's planner `steer` on the reference's dynamics + controller (stand-in physics client, the QP layer
+    replaced by a float64 SLSQP solve) against this package's one-launch steer on its own classes (oracle-backed ops):
+    same barrier weights, same scene -> the same trajectory, collision flag and length."""
+    ArmEnv, ArmMindis, RefController, mg = reference_classes
+    import importlib.util
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    spec = importlib.util.spec_from_file_location("ref_tsa_for_stack", os.path.join(REF, "motion_planning", "baseline", "tsa.py"),
+                                                  submodule_search_locations=None)
+    pkg = __import__("types").ModuleType("ref_stack_pkg")
+    pkg.__path__ = [os.path.join(REF, "motion_planning", "baseline")]
+    sys.modules["ref_stack_pkg"] = pkg
+    spec = importlib.util.spec_from_file_location("ref_stack_pkg.tsa", os.path.join(REF, "motion_planning", "baseline", "tsa.py"))
+    ref_tsa = importlib.util.module_from_spec(spec)
+    sys.modules["ref_stack_pkg.tsa"] = ref_tsa
+    spec.loader.exec_module(ref_tsa)
+
+    positions = np.array([[[0.35, 0.2, 0.35], [-0.3, 0.3, 0.5], [0.1, -0.4, 0.25], [0.3, -0.25, 0.7]]])
+    sizes = np.array([[[0.06, 0.05, 0.1], [0.05, 0.08, 0.05], [0.07, 0.05, 0.12], [0.04, 0.06, 0.05]]])
+    cfg = tmp_path / "env.npz"
+    np.savez(cfg, obstacle_positions=positions, obstacle_sizes=sizes)
+    # ---- the reference stack
+    r_env = ArmEnv(["magician"], config_file=str(cfg), GUI=False, include_floor=True)
+    r_env.reset_env(r_env.get_env_config(0), enable_object=False)
+    r_dyn = ArmMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.02, env=r_env, robot=r_env.robot_list[0])
+    up, lo = r_dyn.control_limits
+    mg.QP_LIMITS.update(lam=0.1, lo=lo.double().numpy(), hi=up.double().numpy())
+    torch.manual_seed(1)
+    r_ctrl = RefController(r_dyn, [{"m1": 5.76}], None, None, cbf_alpha=0.1, cbf_relaxation_penalty=5000.0, safe_level=0.1,
+                           unsafe_level=0.1, cbf_hidden_layers=2, cbf_hidden_size=48, use_neural_actor=False)
+    # ---- this package's stack with the same weights and scene
+    from cbfrrt.environment import ArmEnv as MyEnv
+    from cbfrrt.neural_cbf.systems import ArmMindis as MyMindis
+    from cbfrrt.neural_cbf.controllers import NeuralMindisCBFController as MyController
+    from cbfrrt.motion_planning.baseline import steer_fused
+    m_env = MyEnv(["magician"], config_file="", include_floor=True, device="cpu")
+    m_env.reset_env((positions[0], sizes[0]))
+    m_dyn = MyMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.02, env=m_env, robot=m_env.robot_list[0])
+    m_ctrl = MyController(m_dyn, [{"m1": 5.76}], None, None, cbf_alpha=0.1, cbf_relaxation_penalty=5000.0, safe_level=0.1,
+                          unsafe_level=0.1, cbf_hidden_layers=2, cbf_hidden_size=48, use_neural_actor=False)
+    m_ctrl.load_weights({"h_nn." + k: v for k, v in r_ctrl.h_nn.state_dict().items()})
+    x = m_dyn.sample_state_space(200)
+    xs = x[m_dyn.safe_mask(x)][:, :4].numpy()
+    compared = 0
+    for i in range(5):
+        start, target = xs[i].astype(np.float32), xs[i + 15].astype(np.float32)
+        r_last, r_ok, _, r_list = ref_tsa.steer(r_ctrl.u, r_dyn, target, start, RRT_step=20, device="cpu")
+        m_last, m_ok, _, m_list = steer_fused(m_ctrl, m_dyn, target, start, RRT_step=20)
+        assert r_ok == m_ok and len(r_list) == len(m_list), (i, r_ok, m_ok, len(r_list), len(m_list))
+        if len(r_list) > 1:
+            a = np.asarray([np.asarray(p)[:4] for p in r_list[1:]], dtype=np.float64)
+            b = np.asarray([np.asarray(p)[:4] for p in m_list[1:]], dtype=np.float64)
+            assert np.abs(a - b).max() < 2e-4, (i, np.abs(a - b).max())
+            compared += len(a)
+    assert compared >= 40
