@@ -130,3 +130,26 @@ def edge_case_qp_batch(seed=8, n=7, B=3000):
     a[900:1000] *= 1e-6
     a[1000:1100] *= 1e4
     return a, c, ur, lo, hi
+
+
+def check_against_reference_systems_golden(robot, collide_fn):
+    """tests/golden/ref_systems_*.npz (outputs of the reference's own ArmMindis loops on the stand-in physics client,
+    float64): collide_fn(q, boxes6, floor) -> dict(safe, unsafe, datax, mins) of the implementation under test (float32).
+    Masks must agree on every state not within 1e-5 of a threshold, o within 2e-6, do/dq within 1e-4."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"ref_systems_{robot}.npz"))
+    q = g["q"]
+    n = q.shape[1]
+    boxes = np.concatenate([g["positions"], g["sizes"]], 1).astype(np.float32)
+    for floor in (1, 0):
+        o = collide_fn(q, boxes, bool(floor))
+        self_min, soft_min, hard_min = o["mins"][:, 0], o["mins"][:, 1], o["mins"][:, 2]
+        clear = (np.abs(soft_min - 0.02) > 1e-5) & (np.abs(hard_min) > 1e-5) & (np.abs(self_min - 0.01) > 1e-5)
+        assert clear.mean() > 0.97
+        assert np.array_equal(g[f"safe_floor{floor}"][clear], np.asarray(o["safe"])[clear].astype(bool)), floor
+        assert np.array_equal(g[f"unsafe_floor{floor}"][clear], np.asarray(o["unsafe"])[clear].astype(bool)), floor
+        ref = g[f"datax_floor{floor}"]
+        assert np.array_equal(ref[:, :n], q)
+        assert np.abs(ref[:, n] - o["datax"][:, n]).max() < 2e-6
+        scale = np.maximum(np.abs(ref[:, n + 1:]), 0.1)
+        assert (np.abs(ref[:, n + 1:] - o["datax"][:, n + 1:]) / scale).max() < 1e-4
+        assert 0.05 < g[f"safe_floor{floor}"].mean() < 0.95

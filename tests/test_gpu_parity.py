@@ -711,3 +711,19 @@ def test_geometry_contract_fixture_gpu(robot):
         assert rel_err(datax.cpu().numpy()[:, n + 1:], g[f"datax_floor{floor}"][:, n + 1:]) < 1e-5
     pos, rot = ops.fk(_t(g["q"][:50]), rid)
     assert np.array_equal(pos.cpu().numpy(), g["fk_pos"]) and np.array_equal(rot.cpu().numpy().reshape(g["fk_rot"].shape), g["fk_rot"])
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_kernels_match_reference_systems_golden(robot):
+    """the CUDA kernels against the outputs of the reference's own safe_mask / unsafe_mask /
+    complete_sample_with_observations loops, recorded on the stand-in physics client (tests/golden/ref_systems_*.npz)"""
+    from cbfrrt import ops
+    from conftest import check_against_reference_systems_golden
+    rid = ops.ROBOT_ID[robot]
+
+    def collide(q, boxes, floor):
+        b8, s4 = ops.pack_scene(boxes[:, :3], boxes[:, 3:], None, device="cuda")
+        safe, unsafe, datax, _, _, mins = ops.collide(_t(q), b8, s4, int(floor), ops.no_grid("cuda"), 0.02, 0.0, rid)
+        return dict(safe=safe.cpu().numpy(), unsafe=unsafe.cpu().numpy(), datax=datax.cpu().numpy(), mins=mins.cpu().numpy())
+
+    check_against_reference_systems_golden(robot, collide)

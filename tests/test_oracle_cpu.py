@@ -264,3 +264,11 @@ def test_geometry_contract_fixture(coracle, robot):
             assert np.array_equal(o[k], g[f"{k}_floor{floor}"]), (k, floor)
     pos, rot = coracle.fk(robot, g["q"][:50])
     assert np.array_equal(pos, g["fk_pos"]) and np.array_equal(rot, g["fk_rot"])
+
+
+@pytest.mark.parametrize("robot", ["panda", "magician"])
+def test_oracle_matches_reference_systems_golden(coracle, robot):
+    """the C oracle against the outputs of the reference's own safe_mask / unsafe_mask /
+    complete_sample_with_observations loops (tests/golden/make_ref_systems_golden.py)"""
+    from conftest import check_against_reference_systems_golden
+    check_against_reference_systems_golden(robot, lambda q, boxes, floor: coracle.collide(robot, q, boxes, None, floor, 0.02, 0.0))
