@@ -87,6 +87,39 @@ def test_reference_masks_and_observation_loops(reference_classes, coracle, tmp_p
     assert np.allclose(up.numpy(), W.ROBOT_MODELS[robot]["q_upper"]) and np.allclose(lo.numpy(), W.ROBOT_MODELS[robot]["q_lower"])
     cu, cl = dyn.control_limits
     assert np.allclose(cu.numpy(), W.ROBOT_MODELS[robot]["v_max"]) and torch.equal(cl, -cu)
+    # goal / boundary masks and one closed-loop step with observation refresh (arm_dynamics.py:234-262,474-523,
+    # control_affine_system.py:254-268) against this package's mirrors on the oracle-backed ops
+    import fake_ops
+
+    class _MP:
+        def setattr(self, obj, name, val):
+            setattr(obj, name, val)
+    from cbfrrt import ops as _ops
+    saved = {k: getattr(_ops, k) for k in dir(_ops) if not k.startswith("__")}
+    try:
+        fake_ops.install(_MP())
+        from cbfrrt.environment import ArmEnv as MyEnv
+        from cbfrrt.neural_cbf.systems import ArmMindis as MyMindis
+        m_env = MyEnv([robot], config_file="", include_floor=floor, device="cpu")
+        m_env.reset_env((positions[0], sizes[0]))
+        m_dyn = MyMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.02, env=m_env, robot=m_env.robot_list[0])
+        goal = q[np.argmax(ref_safe)].astype(np.float64)
+        dyn.set_goal(goal)
+        m_dyn.set_goal(goal)
+        xg = torch.tensor(np.concatenate([q[:40], goal[None].astype(np.float32) + 0.01], 0))
+        assert torch.equal(dyn.goal_mask(xg), m_dyn.goal_mask(xg)) and bool(dyn.goal_mask(xg)[-1])
+        ok = torch.tensor(clear[:40])
+        assert torch.equal(dyn.boundary_mask(x[:40])[ok], m_dyn.boundary_mask(x[:40])[ok])
+        u = torch.tensor(np.random.default_rng(3).uniform(-1, 1, size=(40, n)).astype(np.float32))
+        r_next = dyn.closed_loop_dynamics(torch.tensor(ref_datax[:40]), u)
+        m_next = m_dyn.closed_loop_dynamics(torch.tensor(ref_datax[:40]), u)
+        assert r_next.shape == m_next.shape == (40, 2 * n + 1)
+        assert torch.equal(r_next[:, :n], m_next[:, :n]) and (r_next[:, n] - m_next[:, n]).abs().max() < 2e-6
+        sc = torch.clamp(r_next[:, n + 1:].abs(), min=0.1)
+        assert ((r_next[:, n + 1:] - m_next[:, n + 1:]).abs() / sc).max() < 1e-4
+    finally:
+        for k, v in saved.items():
+            setattr(_ops, k, v)
 
 
 def test_whole_reference_stack_steers_like_this_package(reference_classes, coracle, tmp_path, monkeypatch):
