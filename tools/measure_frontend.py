@@ -1,0 +1,62 @@
+#!/usr/bin/env python3
+"""Device-resident timings of the planner front-end and the stand-alone QP entry points (1 GPU): cbfrrt::knn,
+cbfrrt::radius_mask, cbfrrt::qp, cbfrrt::qp_multi, cbfrrt::edge_validity_var.  One JSON line per measurement."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "cbf-inc-rrt_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+from cbfrrt import ops, workloads as W  # noqa: E402
+
+dev = torch.device("cuda", 0)
+rng = np.random.default_rng(0)
+t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
+
+
+def timed(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def main():
+    out = []
+    tree = t(rng.uniform(-2, 2, size=(100000, 7)))
+    for M, k in ((50, 1), (1, 50), (4096, 1)):
+        q = t(rng.uniform(-2, 2, size=(M, 7)))
+        out.append(dict(op="knn", queries=M, tree=100000, k=k, ms=timed(lambda: ops.knn(q, tree, k))))
+    q = t(rng.uniform(-2, 2, size=(200, 7)))
+    out.append(dict(op="radius_mask", queries=200, points=100000, ms=timed(lambda: ops.radius_mask(q, tree, 1.0))))
+    B, n = 1 << 20, 7
+    lo, hi = t(-np.ones(n)), t(np.ones(n))
+    a1, c1, ur = t(rng.normal(size=(B, n))), t(rng.normal(size=B)), t(rng.uniform(-1.5, 1.5, size=(B, n)))
+    out.append(dict(op="qp", rows=B, n=n, ms=timed(lambda: ops.qp(a1, c1, ur, lo, hi, 5000.0))))
+    for S in (2, 4):
+        a, c = t(rng.normal(size=(B, S, n))), t(rng.normal(scale=0.8, size=(B, S)))
+        out.append(dict(op="qp_multi", rows=B, n=n, constraints=S, ms=timed(lambda: ops.qp_multi(a, c, ur, lo, hi, 5000.0, 100, 1e-9))))
+    w = W.config(3, scale=1 / 4)
+    rid = ops.ROBOT_ID[w["robot"]]
+    b8, s4 = ops.pack_scene(w["boxes"][:, :3], w["boxes"][:, 3:], w["spheres"], device=dev)
+    E = 1 << 18
+    qf = t(W.sample_states("panda", E, 0))
+    qt = t(np.clip(qf.cpu().numpy() + rng.uniform(-0.35, 0.35, size=(E, 7)).astype(np.float32), -2.8, 2.8))
+    K = torch.from_numpy((np.linalg.norm((qf - qt).cpu().numpy(), axis=1) / 0.03).astype(np.int64))
+    ms = timed(lambda: ops.edge_validity_var(qf, qt, K, b8, s4, 1, ops.no_grid(dev), 0.02, 0.0, rid), iters=5)
+    out.append(dict(op="edge_validity_var", edges=E, points=int(K.sum() + E), boxes=int(b8.shape[0]), ms=ms))
+    for r in out:
+        print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
