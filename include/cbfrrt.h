@@ -156,7 +156,8 @@ int cbfrrt_qp(int n, const float *a, const float *c, const float *u_ref, int64_t
  * dual over mu in [0,p]^S is maximised by iterations of (1) one cyclic sweep of exact coordinate maximisations (the
  * single-constraint root find) and (2) Newton steps on the current active set with an exact line search; stops when
  * the control-space movement of an iteration is <= tol * (1 + size of the dual shift).  1 <= n <= 8, 1 <= S <= 4.
- * p is clamped to 1e6.  Typical: 2-5 iterations. */
+ * p is clamped to 1e6.  Typical: 2-5 iterations.  With more constraints than unclipped controls (S > n) a few rows in
+ * 10 000 zig-zag between active sets and exhaust max_iter; they are reported through `iters`. */
 int cbfrrt_qp_multi(int n, int n_constraints, const float *a, const float *c, const float *u_ref, int64_t B,
                     const float *u_lo, const float *u_hi, float relaxation_penalty, int max_iter, float tol,
                     float *u, float *r, int32_t *iters, void *stream);
