@@ -129,3 +129,36 @@ def test_reference_bit_star_runs_on_our_objects(world):
     np.random.seed(1)
     res = ref["bit_star"].BITStar(env, dyn, init, goal, batch_size=40, T=400, EPS=0.05, time_budget=120)
     assert res["success"] and len(res["path"]) >= 2 and res["explored_nodes"] >= 40
+
+
+def test_reference_datamodule_sampling_runs_on_our_objects(world, monkeypatch):
+    """EpisodicDataModule.sample_fixed (neural_cbf/datamodules/episodic_datamodule.py:146-194), the caller of the
+    sampled-state sweeps (sample_safe / sample_unsafe / sample_boundary + the four masks), loaded unmodified"""
+    env, dyn, ctrl, xs, ref = world
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as mg
+    finder = mg._StubFinder()
+    sys.meta_path.insert(0, finder)
+    stub_sys = types.ModuleType("neural_cbf.systems")
+    stub_sys.ControlAffineSystem = object
+    monkeypatch.setitem(sys.modules, "neural_cbf", types.ModuleType("neural_cbf"))
+    monkeypatch.setitem(sys.modules, "neural_cbf.systems", stub_sys)
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "ref_datamodule", os.path.join(REF, "neural_cbf", "datamodules", "episodic_datamodule.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.meta_path.remove(finder)
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("pytorch_lightning", "matplotlib"):
+                del sys.modules[k]
+    up, lo = dyn.state_limits
+    dm = mod.EpisodicDataModule(dyn, [(float(a), float(b)) for a, b in zip(lo, up)], max_episode=1, fixed_samples=200,
+                                quotas={"safe": 0.3, "unsafe": 0.3, "boundary": 0.2}, batch_size=16)
+    dyn.set_goal(xs[0])
+    samples, masks = dm.sample_fixed()
+    assert samples.shape == (160, 2 * 4 + 1) and set(masks) == {"safe", "unsafe", "goal", "boundary"}
+    assert masks["safe"][:60].all() and masks["unsafe"][60:120].all() and masks["boundary"][120:].all()
+    assert not (masks["safe"] & masks["unsafe"]).any()
+    assert torch.equal(masks["boundary"], ~(masks["safe"] | masks["unsafe"]))
