@@ -391,7 +391,7 @@ struct RolloutArgs {
 
 // ------------------------------------------------------------------ tensor-core (tcgen05) variants
 // Same contracts as filter_kernel / safety_kernel; the MLP of every 128-state tile runs as TF32x3 GEMMs on the
-// tensor cores (mlp_tc.cuh).  One CTA of 384 threads per SM = 3 tile groups sharing the staged weights; all 128
+// tensor cores (mlp_tc.cuh).  One CTA per SM of GG tile groups (see tc_groups) sharing the staged weights; all 128
 // threads of a group take part in every tile of that group (idle rows are masked), because the MMAs, the TMEM
 // traffic and the barriers are group-wide.
 // tile groups per CTA: 4 (512 threads, 128 registers) when the geometry stage works out of shared memory, 3 (384
