@@ -127,3 +127,23 @@ class NeuralMindisCBFController(NeuralObsCBFController):
               if k.startswith("h_nn.") or k.split(".")[0] in self.h_layers}
         self.h_nn.load_state_dict(sd)
         self._packed = None
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, **kwargs):
+        """Reads a Lightning ``.ckpt`` as the reference's evaluation scripts do
+        (motion_planning/evaluation/eval_rrt_mindis_cbfsteer.py:33-50, neural_cbf/evaluation/eval_arm_mindis.py:88):
+        a ``torch.save`` dict with ``state_dict`` (keys h_nn.*) and optionally ``hyper_parameters``
+        (neural_obs_cbf_controller.py:81-82); keyword arguments override the stored hyper-parameters, as in Lightning.
+        ``dynamics_model`` and ``scenarios`` must be passed (they are never stored in the checkpoint)."""
+        ckpt = torch.load(checkpoint_path, map_location="cpu" if map_location is None else map_location,
+                          weights_only=False)
+        if "state_dict" not in ckpt:
+            raise KeyError(f"{checkpoint_path}: not a Lightning checkpoint (no 'state_dict')")
+        hparams = {k: v for k, v in dict(ckpt.get("hyper_parameters", {})).items()
+                   if k in ("cbf_alpha", "cbf_relaxation_penalty", "safe_level", "unsafe_level", "cbf_hidden_layers",
+                            "cbf_hidden_size", "use_neural_actor", "loss_config", "learn_shape_epochs")}
+        hparams.update(kwargs)
+        controller = cls(**hparams)
+        controller.load_weights(ckpt["state_dict"])
+        return controller
+

@@ -12,7 +12,7 @@ input's device, as the reference returns masks "type_as(x)" (arm_dynamics.py:197
 """
 import time
 import warnings
-from typing import Dict, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -141,7 +141,7 @@ class ArmDynamics(ControlAffineSystem):
 
     def goal_mask(self, x, velocity_limit: bool = False):
         """arm_dynamics.py:234-262: within 0.2 rad (L2) of the goal and safe."""
-        goal = torch.tensor(self.goal_state[:self.q_dims]).type_as(x).to(x.device)
+        goal = torch.as_tensor(self.goal_state[:self.q_dims]).type_as(x).to(x.device)
         goal_mask = (x[:, :self.q_dims] - goal).norm(dim=1) <= 0.2
         if velocity_limit:
             goal_mask.logical_and_(x[:, 2].abs() <= 0.1)
@@ -166,7 +166,7 @@ class ArmDynamics(ControlAffineSystem):
 
     # ---- samplers (arm_dynamics.py:293-325)
     def sample_goal(self, num_samples: int, eps=0.02) -> torch.Tensor:
-        x = torch.Tensor(num_samples, self.n_dims).uniform_(-1.0, 1.0) * eps + torch.tensor(self.goal_state).float()
+        x = torch.Tensor(num_samples, self.n_dims).uniform_(-1.0, 1.0) * eps + torch.as_tensor(self.goal_state).float()
         return self.complete_sample_with_observations(x, num_samples)
 
     def sample_safe(self, num_samples: int, max_tries: int = 100) -> torch.Tensor:
@@ -201,6 +201,45 @@ class ArmDynamics(ControlAffineSystem):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             return torch.tensor(self.goal_state)
+
+    # ---- data-collection simulator (arm_dynamics.py:382-471): nominal controller + uniform control noise, held for
+    # controller_period / dt steps, Euler with ``collect_dataset`` (10 sub-steps per stored state), observation
+    # refreshed at every stored state.  One batched launch per stored state instead of bs pybullet loops.
+    def noisy_simulator(self, x_init: torch.Tensor, num_steps: int, collect_dataset: bool = False,
+                        noise_level=1e-2, use_motor_control: bool = False) -> torch.Tensor:
+        assert collect_dataset
+        return self.simulate(x_init, num_steps, controller=self.u_nominal, guard=self.out_of_bounds_mask,
+                             noise_level=noise_level, use_motor_control=use_motor_control,
+                             collect_dataset=collect_dataset)
+
+    def simulate(self, x_init: torch.Tensor, num_steps: int, collect_dataset: bool, controller: Callable,
+                 controller_period: Optional[float] = None, guard: Optional[Callable] = None,
+                 noise_level: float = 0, use_motor_control: bool = False,
+                 params: Optional[Scenario] = None) -> torch.Tensor:
+        """-> (bs, num_steps, n + o_dims + aux) trajectories (arm_dynamics.py:400-471)."""
+        assert controller.__name__ == "u_nominal"
+        assert collect_dataset == True  # noqa: E712  (the reference's own guard, :431)
+        init_states = self.complete_sample_with_observations(x_init, x_init.shape[0])
+        x_sim = torch.zeros(x_init.shape[0], num_steps, init_states.shape[-1]).type_as(x_init)
+        u = torch.zeros(x_init.shape[0], self.n_controls).type_as(x_init)
+        if controller_period is None:
+            controller_period = self.dt
+        controller_update_freq = int(controller_period / self.dt)
+        x_sim[:, 0, :] = init_states
+        upper_u_lim, lower_u_lim = self.control_limits
+        for tstep in range(1, num_steps):
+            x_current = x_sim[:, tstep - 1, :]
+            if tstep == 1 or tstep % controller_update_freq == 0:
+                u = controller(x_current)
+                if isinstance(u, tuple):
+                    u = u[0]
+                if noise_level > 0:
+                    u += torch.mul(torch.Tensor(x_init.shape[0], self.n_controls).uniform_(-noise_level, noise_level)
+                                   .type_as(x_init), upper_u_lim.type_as(x_init))
+                    u = torch.max(torch.min(u, upper_u_lim.type_as(u)), lower_u_lim.type_as(u))
+            x_sim[:, tstep, :] = self.closed_loop_dynamics(x_current, u, use_motor_control=use_motor_control,
+                                                           collect_dataset=collect_dataset)
+        return x_sim
 
     # ---- Euler step (arm_dynamics.py:474-523).  NOTE: returns x_next, not xdot (:480-485).
     def closed_loop_dynamics(self, x: torch.Tensor, u: torch.Tensor, collect_dataset: bool = False,
