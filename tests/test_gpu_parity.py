@@ -569,6 +569,45 @@ def test_batch_rrt_plan_on_gpu():
     assert res["success"]
 
 
+def test_dataset_and_problem_generation_on_gpu(coracle, tmp_path):
+    """SURVEY 8f rank 4 on the device ops: EpisodicDataModule.prepare_data (fixed quotas + noisy nominal rollouts) and
+    propose_test_cases; every stored row / label is checked against the oracle in the scene it was drawn in."""
+    import random
+    from cbfrrt.environment import ArmEnv
+    from cbfrrt.neural_cbf.systems import ArmMindis
+    from cbfrrt.neural_cbf.datamodules import EpisodicDataModule
+    from cbfrrt.motion_planning.evaluation import propose_test_cases
+    np.random.seed(5)
+    env = ArmEnv(["panda"], config_file="", include_floor=True)
+    dyn = ArmMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.05, env=env, robot=env.robot_list[0])
+    up, lo = dyn.state_limits
+    dm = EpisodicDataModule(dyn, [(float(a), float(b)) for a, b in zip(lo, up)], max_episode=1, trajectories_per_episode=8,
+                            trajectory_length=6, fixed_samples=1000, noise_level=0.1, batch_size=64,
+                            quotas={"safe": 0.3, "unsafe": 0.3, "boundary": 0.2, "goal": 0.1}, data_root=str(tmp_path))
+    random.seed(0), np.random.seed(0), torch.manual_seed(0)
+    samples, masks = dm.sample_fixed()
+    assert samples.shape == (900, 15) and masks["safe"][:300].all() and masks["unsafe"][300:600].all()
+    boxes6 = np.concatenate([env.obs_positions, env.obs_sizes], 1)
+    o = coracle.collide("panda", samples[:, :7].numpy(), boxes6, None, True, 0.05, 0.0)
+    assert np.array_equal(masks["safe"].numpy(), o["safe"].astype(bool))
+    assert np.array_equal(masks["unsafe"].numpy(), o["unsafe"].astype(bool))
+    assert np.array_equal(samples.numpy()[:, :8], o["datax"][:, :8])
+    assert rel_err(samples.numpy()[:, 8:], o["datax"][:, 8:], floor=1.0) < TOL
+    x_sim, sim_masks = dm.sample_trajectories(dyn.noisy_simulator)     # resets the scene to a random training scene
+    assert x_sim.shape == (8 * 6, 15)
+    boxes6 = np.concatenate([env.obs_positions, env.obs_sizes], 1)
+    o = coracle.collide("panda", x_sim[:, :7].numpy(), boxes6, None, True, 0.05, 0.0)
+    assert np.array_equal(sim_masks["safe"].numpy(), o["safe"].astype(bool))
+    assert np.array_equal(sim_masks["boundary"].numpy(), ~(o["safe"].astype(bool) | o["unsafe"].astype(bool)))
+    assert np.array_equal(x_sim.numpy()[:, :8], o["datax"][:, :8])
+    dm.prepare_data()
+    data = torch.load(dm.dataset_path())
+    assert data["x_training"].shape[0] + data["x_validation"].shape[0] == 900 + 48
+    pos, siz, start, goal = propose_test_cases(dyn, obstacle_num=8)
+    o = coracle.collide("panda", np.stack([start, goal]).astype(np.float32), np.concatenate([pos, siz], 1), None, True, 0.05, 0.0)
+    assert o["safe"].all() and np.linalg.norm(start - goal) > 0.7
+
+
 def test_registered_ops_equal_direct_calls():
     """torch.ops.cbfrrt.* (dispatcher) and the module-level direct entry points run the same implementation"""
     from cbfrrt import ops, workloads as W
