@@ -73,11 +73,15 @@ class CLFController(Controller):
     def u_reference(self, x: torch.Tensor) -> torch.Tensor:
         return self.dynamics_model.u_nominal(x)
 
-    def _solve_CLF_QP_exact(self, x, u_ref, V, Lf_V, Lg_V, relaxation_penalty: float):
-        """Batched exact solve on the GPU (replaces _solve_CLF_QP_cvxpylayers, clf_controller.py:354-404)."""
+    def _solve_CLF_QP_exact(self, x, u_ref, V, Lf_V, Lg_V, relaxation_penalty: float, requires_grad: bool = False):
+        """Batched exact solve on the GPU (replaces _solve_CLF_QP_cvxpylayers, clf_controller.py:354-404).  With
+        ``requires_grad`` the single-scenario solve is differentiable w.r.t. V, Lf_V, Lg_V and u_ref like the
+        reference's CvxpyLayer (closed-form active-set sensitivities, cbfrrt::qp_backward)."""
         dev = self.device
         upper, lower = self.dynamics_model.control_limits
         if self.n_scenarios != 1:
+            if requires_grad:
+                raise NotImplementedError("differentiable solve is built for n_scenarios == 1 (cbfrrt::qp_backward)")
             a = Lg_V.to(dev, torch.float32)
             c = (Lf_V[:, :, 0] + self.clf_lambda * V.reshape(-1, 1)).to(dev, torch.float32)
             u, r, _ = ops.qp_multi(a, c, u_ref.to(dev, torch.float32), lower.to(dev, torch.float32),
@@ -85,8 +89,9 @@ class CLFController(Controller):
             return u.to(x.device).type_as(x), r.to(x.device).type_as(x)
         a = Lg_V[:, 0, :].to(dev, torch.float32)
         c = (Lf_V[:, 0, 0] + self.clf_lambda * V.reshape(-1)).to(dev, torch.float32)
-        u, r = ops.qp(a, c, u_ref.to(dev, torch.float32), lower.to(dev, torch.float32), upper.to(dev, torch.float32),
-                      float(relaxation_penalty))
+        solve = ops.qp_diff if requires_grad else ops.qp
+        u, r = solve(a, c, u_ref.to(dev, torch.float32), lower.to(dev, torch.float32), upper.to(dev, torch.float32),
+                     float(relaxation_penalty))
         return u.to(x.device).type_as(x), r.reshape(-1, 1).to(x.device).type_as(x)
 
     def solve_CLF_QP(self, x, relaxation_penalty: Optional[float] = None, u_ref: Optional[torch.Tensor] = None,
@@ -105,7 +110,7 @@ class CLFController(Controller):
             u_ref = self.u_reference(x)
         if relaxation_penalty is None:
             relaxation_penalty = self.clf_relaxation_penalty
-        sol = self._solve_CLF_QP_exact(x, u_ref, V, Lf_V, Lg_V, relaxation_penalty)
+        sol = self._solve_CLF_QP_exact(x, u_ref, V, Lf_V, Lg_V, relaxation_penalty, requires_grad=requires_grad)
         t_dict["QP"] = time.time() - b
         return sol, t_dict
 

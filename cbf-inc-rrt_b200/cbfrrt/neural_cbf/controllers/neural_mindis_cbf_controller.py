@@ -107,12 +107,36 @@ class NeuralMindisCBFController(NeuralObsCBFController):
         if u_ref is not None:
             assert u_ref.shape[0] == x.shape[0], f"u_ref must have {x.shape[0]} rows, but got {u_ref.shape[0]}"
             assert u_ref.shape[1] == self.dynamics_model.n_controls
+        if requires_grad:
+            return self._solve_CLF_QP_differentiable(x, relaxation_penalty, u_ref), \
+                {"V_w_Jacobian": 0.0, "lie_derivative": 0.0, "nn_forward": 0.0, "QP": time.time() - t0}
         h, J, u, r = self._filter(x, relaxation_penalty, u_ref)
         u = u.to(x.device).type_as(x)
         r = r.reshape(-1, 1).expand(-1, self.n_scenarios).contiguous().to(x.device).type_as(x)
         t = time.time() - t0
         # the four reference timers (clf_controller.py:186-218,487-528); the fused launch is booked on nn_forward
         return (u, r), {"V_w_Jacobian": 0.0, "lie_derivative": 0.0, "nn_forward": t, "QP": 0.0}
+
+    def _solve_CLF_QP_differentiable(self, x, relaxation_penalty, u_ref):
+        """The training-time form of the same filter (the reference: autograd through h_nn for h and J, :83-102, then
+        backpropagation through the CvxpyLayer, clf_controller.py:354-404): h and J = Jh_q + Jh_o do/dq from torch
+        autograd on ``h_nn`` (graph kept, so gradients reach the weights through both), the QP by cbfrrt::qp with its
+        closed-form reverse mode cbfrrt::qp_backward (``ops.qp_diff``).  Inference never takes this path."""
+        dm, dev = self.dynamics_model, self.device
+        n = dm.n_dims
+        d = x.to(dev, torch.float32)
+        net = self.h_nn.to(dev)
+        with torch.enable_grad():
+            xin = d[:, :n + 1].detach().requires_grad_(True)
+            h = net(xin)
+            Jh = torch.autograd.grad(h.sum(), xin, create_graph=True)[0]
+            J = Jh[:, :n] + Jh[:, n:] * d[:, n + 1:]
+            lo, hi = self._limits()
+            ur = dm.u_nominal(d) if u_ref is None else u_ref.to(dev, torch.float32)
+            pen = self.clf_relaxation_penalty if relaxation_penalty is None else relaxation_penalty
+            u, r = ops.qp_diff(J, float(self.clf_lambda) * h.reshape(-1), ur, lo, hi, float(pen))
+        return (u.to(x.device).type_as(x),
+                r.reshape(-1, 1).expand(-1, self.n_scenarios).contiguous().to(x.device).type_as(x))
 
     def u(self, datax: torch.Tensor, u_nominal=None):
         sol, t_dict = self.solve_CLF_QP(datax)

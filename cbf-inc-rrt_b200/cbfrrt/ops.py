@@ -241,6 +241,26 @@ def qp(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty:
     return u, r
 
 
+@torch.library.custom_op("cbfrrt::qp_backward", mutates_args=(), device_types="cuda")
+def qp_backward(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty: float, grad_u: Tensor,
+                grad_r: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """reverse mode of ``qp``: (dL/du f32[B,n], dL/dr f32[B] or empty) -> dL/da f32[B,n], dL/dc f32[B], dL/du_ref f32[B,n]"""
+    a, c, u_ref, u_lo, u_hi = _f32c(a), _f32c(c).reshape(-1), _f32c(u_ref), _f32c(u_lo), _f32c(u_hi)
+    B, n = a.shape
+    grad_u = _f32c(grad_u)
+    grad_r = _f32c(grad_r).reshape(-1)
+    if u_ref.shape != a.shape or grad_u.shape != a.shape or c.numel() != B or grad_r.numel() not in (0, B) \
+            or u_lo.numel() != n or u_hi.numel() != n:
+        raise ValueError("qp_backward: inconsistent shapes")
+    ga = torch.empty((B, n), dtype=torch.float32, device=a.device)
+    gc = torch.empty(B, dtype=torch.float32, device=a.device)
+    gt = torch.empty((B, n), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.cbfrrt_qp_backward(n, _ptr(a), _ptr(c), _ptr(u_ref), B, _ptr(u_lo), _ptr(u_hi), penalty, _ptr(grad_u),
+                                     _ptr(grad_r), _ptr(ga), _ptr(gc), _ptr(gt), _stream()), "cbfrrt_qp_backward")
+    return ga, gc, gt
+
+
 @torch.library.custom_op("cbfrrt::qp_multi", mutates_args=(), device_types="cuda")
 def qp_multi(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty: float, max_sweeps: int,
              tol: float) -> Tuple[Tensor, Tensor, Tensor]:
@@ -453,11 +473,35 @@ def _direct(op, cpu_ok=()):
     return call
 
 
-for _name in ("fk", "collide", "observe", "masks", "cbf_filter", "qp", "qp_multi", "safety_filter", "valid_control",
+for _name in ("fk", "collide", "observe", "masks", "cbf_filter", "qp", "qp_backward", "qp_multi", "safety_filter", "valid_control",
               "edge_validity", "edge_validity_var", "knn", "radius_mask", "rollout"):
     registered[_name] = globals()[_name]
     globals()[_name] = _direct(registered[_name], cpu_ok=(2,) if _name == "edge_validity_var" else ())
 del _name
+
+
+class _DifferentiableQP(torch.autograd.Function):
+    """``qp`` with the closed-form reverse mode ``qp_backward`` (no gradient for the limits and the penalty)."""
+
+    @staticmethod
+    def forward(ctx, a, c, u_ref, u_lo, u_hi, penalty):
+        ctx.save_for_backward(a, c, u_ref, u_lo, u_hi)
+        ctx.penalty = float(penalty)
+        return qp(a, c, u_ref, u_lo, u_hi, float(penalty))
+
+    @staticmethod
+    def backward(ctx, grad_u, grad_r):
+        a, c, u_ref, u_lo, u_hi = ctx.saved_tensors
+        empty = torch.empty(0, dtype=torch.float32, device=a.device)
+        gu = torch.zeros_like(a, dtype=torch.float32) if grad_u is None else grad_u
+        ga, gc, gt = qp_backward(a, c, u_ref, u_lo, u_hi, ctx.penalty, gu, empty if grad_r is None else grad_r)
+        return ga.to(a.dtype).reshape(a.shape), gc.to(c.dtype).reshape(c.shape), gt.to(u_ref.dtype), None, None, None
+
+
+def qp_diff(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty: float) -> Tuple[Tensor, Tensor]:
+    """differentiable single-constraint QP: (u [B,n], r [B]) with gradients w.r.t. a = Lg_V, c = Lf_V + lam V, u_ref
+    -- what the reference gets from its CvxpyLayer (clf_controller.py:354-404, requires_grad=True)."""
+    return _DifferentiableQP.apply(a, c, u_ref, u_lo, u_hi, penalty)
 
 
 def sample_states(B: int, seed: int, start_row: int, robot_id: int, device="cuda") -> Tensor:

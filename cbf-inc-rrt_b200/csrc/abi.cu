@@ -104,6 +104,24 @@ int cbfrrt_qp(int n, const float* a, const float* c, const float* u_ref, int64_t
     return finish_launch();
 }
 
+int cbfrrt_qp_backward(int n, const float* a, const float* c, const float* u_ref, int64_t B, const float* u_lo,
+                       const float* u_hi, float relaxation_penalty, const float* grad_u, const float* grad_r,
+                       float* grad_a, float* grad_c, float* grad_u_ref, void* stream) {
+    if (B < 0 || !u_lo || !u_hi) return CBFRRT_ERR_BAD_SHAPE;
+    if (n < 1 || n > 8) return CBFRRT_ERR_UNSUPPORTED;
+    if (B == 0) return CBFRRT_OK;
+    if (!a || !c || !u_ref || !grad_u) return CBFRRT_ERR_BAD_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = (B + 255) / 256;
+    const int grid = (int)(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
+    switch (n) {
+#define CBF_QP_CASE(NN) case NN: qp_backward_kernel<NN><<<grid, 256, 0, st>>>(a, c, u_ref, B, u_lo, u_hi, relaxation_penalty, grad_u, grad_r, grad_a, grad_c, grad_u_ref); break;
+        CBF_QP_CASE(1) CBF_QP_CASE(2) CBF_QP_CASE(3) CBF_QP_CASE(4) CBF_QP_CASE(5) CBF_QP_CASE(6) CBF_QP_CASE(7) CBF_QP_CASE(8)
+#undef CBF_QP_CASE
+    }
+    return finish_launch();
+}
+
 int cbfrrt_qp_multi(int n, int n_constraints, const float* a, const float* c, const float* u_ref, int64_t B,
                     const float* u_lo, const float* u_hi, float relaxation_penalty, int max_sweeps, float tol, float* u,
                     float* r, int32_t* sweeps, void* stream) {

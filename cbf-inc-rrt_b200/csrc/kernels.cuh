@@ -318,6 +318,35 @@ __global__ void __launch_bounds__(256) qp_kernel(const float* __restrict__ a, co
     }
 }
 
+// reverse mode of the stand-alone QP: (a, c, u_ref, dL/du, dL/dr) -> (dL/da, dL/dc, dL/du_ref).  fp32 in / out, the
+// sensitivities are evaluated in double (qp_backward).  HBM-bound: (3n+2) floats in, (2n+1) floats out per row.
+template <int N>
+__global__ void __launch_bounds__(256) qp_backward_kernel(const float* __restrict__ a, const float* __restrict__ c,
+                                                          const float* __restrict__ u_ref, long long B,
+                                                          const float* __restrict__ u_lo, const float* __restrict__ u_hi,
+                                                          float penalty, const float* __restrict__ grad_u,
+                                                          const float* __restrict__ grad_r, float* __restrict__ grad_a,
+                                                          float* __restrict__ grad_c, float* __restrict__ grad_u_ref) {
+    __shared__ double lim[2 * N];
+    if (threadIdx.x < N) { lim[threadIdx.x] = u_lo[threadIdx.x]; lim[N + threadIdx.x] = u_hi[threadIdx.x]; }
+    __syncthreads();
+    for (long long b = (long long)blockIdx.x * 256 + threadIdx.x; b < B; b += (long long)gridDim.x * 256) {
+        double aa[N], ur[N], gu[N], ga[N], gt[N], gc;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            aa[k] = __ldg(a + b * N + k); ur[k] = __ldg(u_ref + b * N + k); gu[k] = __ldg(grad_u + b * N + k);
+        }
+        qp_backward<N, double>(aa, ur, lim, lim + N, (double)__ldg(c + b), (double)fminf(penalty, 1e6f), gu,
+                               grad_r ? (double)__ldg(grad_r + b) : 0.0, ga, gc, gt);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (grad_a) grad_a[b * N + k] = (float)ga[k];
+            if (grad_u_ref) grad_u_ref[b * N + k] = (float)gt[k];
+        }
+        if (grad_c) grad_c[b] = (float)gc;
+    }
+}
+
 // multi-scenario QP: a [B,S,n], c [B,S], u_ref [B,n] -> u [B,n], r [B,S], iters [B] (optional).  fp32 in / out, the
 // dual iteration runs in double (see qp_solve_multi).
 constexpr int QP_MAX_CON = 4;

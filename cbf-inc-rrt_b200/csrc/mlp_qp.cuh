@@ -220,6 +220,100 @@ __host__ __device__ __forceinline__ void qp_solve(const float (&a)[N], const flo
     r = (mu >= p) ? fmaxf(g, 0.f) : 0.f;
 }
 
+// qp_mu in double at (nearly) float cost: the breakpoint search runs in float and only proposes an active set; the
+// multiplier is then recomputed in double from that set (mu = 2 (c + a_F.t_F + a_C.b_C) / |a_F|^2) and accepted only if
+// it reproduces the set and lies in (0, p) -- by monotonicity of g that is THE root.  Anything else (a float
+// misclassification next to a kink, |a_F| = 0) falls back to the full double search.
+template <int N>
+__host__ __device__ __forceinline__ double qp_mu_refined(const double (&a)[N], const double (&t)[N],
+                                                     const double* __restrict__ lo, const double* __restrict__ hi,
+                                                     double c, double p) {
+    if (!(qp_g<N>(a, t, lo, hi, c, 0.) > 0.)) return 0.;
+    if (qp_g<N>(a, t, lo, hi, c, p) > 0.) return p;
+    float af[N], tf[N], lf[N], hf[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { af[i] = (float)a[i]; tf[i] = (float)t[i]; lf[i] = (float)lo[i]; hf[i] = (float)hi[i]; }
+    double mu = (double)qp_mu<N, float>(af, tf, lf, hf, (float)c, (float)p);
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        double Nn = c, S = 0.;
+        unsigned set = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double v = fma(-0.5 * mu, a[i], t[i]);
+            if (v > lo[i] && v < hi[i]) { set |= 1u << i; Nn = fma(a[i], t[i], Nn); S = fma(a[i], a[i], S); }
+            else Nn = fma(a[i], v <= lo[i] ? lo[i] : hi[i], Nn);
+        }
+        if (!(S > 0.)) break;
+        const double m2 = 2. * Nn / S;
+        unsigned set2 = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double v = fma(-0.5 * m2, a[i], t[i]);
+            if (v > lo[i] && v < hi[i]) set2 |= 1u << i;
+            else if ((v <= lo[i]) != (fma(-0.5 * mu, a[i], t[i]) <= lo[i])) set2 |= 1u << 31;   // other bound: reject
+        }
+        if (set2 == set && m2 > 0. && m2 < p) return m2;
+        mu = m2;
+        if (!(m2 > 0. && m2 < p)) break;
+    }
+    return qp_mu<N, double>(a, t, lo, hi, c, p);
+}
+template <int N>
+__host__ __device__ __forceinline__ float qp_mu_refined(const float (&a)[N], const float (&t)[N], const float* __restrict__ lo,
+                                                    const float* __restrict__ hi, float c, float p) {
+    return qp_mu<N, float>(a, t, lo, hi, c, p);
+}
+
+// Reverse mode of the single-constraint CBF-QP: what backpropagation through the reference's CvxpyLayer returns
+// (clf_controller.py:82-139, params Lf_V / Lg_V / V / u_ref; used with requires_grad=True, :461-528), from the
+// closed-form sensitivities of the KKT solution instead of diffcp's differentiated cone program.
+// With F = {i : lo_i < u_ref_i - mu a_i / 2 < hi_i} (unclipped coordinates), the solution is one of three pieces:
+//   mu = 0          (constraint inactive)   u_F = u_ref_F, r = 0
+//   0 < mu < p      (constraint tight)      mu = 2 (c + a_F.u_ref_F + a_C.b_C) / |a_F|^2, u_F = u_ref_F - mu a_F / 2, r = 0
+//   mu = p          (constraint relaxed)    u_F = u_ref_F - p a_F / 2, r = c + a.u
+// and each piece is differentiated in place (gu = dL/du, gr = dL/dr  ->  ga = dL/da, gc = dL/dc, gt = dL/du_ref).
+// At a kink (measure zero) the clipped / inactive side is taken.  T = double: the sensitivities divide by |a_F|^2.
+template <int N, typename T>
+__host__ __device__ __forceinline__ void qp_backward(const T (&a)[N], const T (&uref)[N], const T* __restrict__ lo,
+                                                const T* __restrict__ hi, T c, T p, const T (&gu)[N], T gr,
+                                                T (&ga)[N], T& gc, T (&gt)[N]) {
+    const T mu = qp_mu_refined<N>(a, uref, lo, hi, c, p);
+    const T hm = T(0.5) * mu;
+    bool fr[N];
+    T u[N], S = T(0.), G = T(0.), g = c;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const T v = fma(-hm, a[i], uref[i]);
+        fr[i] = v > lo[i] && v < hi[i];
+        u[i] = fmin(fmax(v, lo[i]), hi[i]);
+        g = fma(a[i], u[i], g);
+        if (fr[i]) { S = fma(a[i], a[i], S); G = fma(gu[i], a[i], G); }
+    }
+    if (!(mu > T(0.))) {                        // inactive
+        gc = T(0.);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { ga[i] = T(0.); gt[i] = fr[i] ? gu[i] : T(0.); }
+    } else if (mu >= p) {                       // relaxed: r = g(p) (r = 0 and no r-gradient if g(p) <= 0)
+        const T grr = g > T(0.) ? gr : T(0.);
+        gc = grr;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const T gi = fr[i] ? fma(grr, a[i], gu[i]) : T(0.);
+            gt[i] = gi;
+            ga[i] = fma(grr, u[i], -hm * gi);
+        }
+    } else {                                    // tight: mu is a function of (a, c, u_ref)
+        const T k = S > T(0.) ? G / S : T(0.);  // = -dL/dmu * 2 / |a_F|^2
+        gc = -k;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            gt[i] = fr[i] ? fma(-k, a[i], gu[i]) : T(0.);
+            ga[i] = fr[i] ? fma(-k, u[i] - hm * a[i], -hm * gu[i]) : -k * u[i];
+        }
+    }
+}
+
 // S relaxed constraints (multi-scenario CLF/CBF-QP, clf_controller.py:86-139 with len(scenarios) > 1):
 //   min ||u-u_ref||^2 + p sum_i r_i   s.t.  c_i + a_i.u - r_i <= 0, r_i >= 0, lo <= u <= hi.
 // Batched dual active-set solver.  The dual is concave and piecewise quadratic in mu in [0,p]^S with

@@ -147,6 +147,17 @@ int cbfrrt_cbf_filter(int n, const cbfrrt_cbf_net *net, const float *datax, int6
 int cbfrrt_qp(int n, const float *a, const float *c, const float *u_ref, int64_t B, const float *u_lo,
               const float *u_hi, float relaxation_penalty, float *u, float *r, void *stream);
 
+/* ---- K8 reverse mode: gradients of the single-constraint CLF/CBF-QP solution -------------------------------
+ * Replaces backpropagation through the CvxpyLayer (clf_controller.py:82-139; solve_CLF_QP(requires_grad=True)
+ * :461-528 -> diffcp's derivative of the cone program) by the closed-form sensitivities of the KKT solution on its
+ * active set.  Inputs as cbfrrt_qp plus grad_u = dL/du [B, n] and grad_r = dL/dr [B] (NULL = 0); outputs (each
+ * optional) grad_a = dL/dLg_V [B, n], grad_c = dL/d(Lf_V + lambda V) [B] (so dL/dLf_V = grad_c, dL/dV = lambda
+ * grad_c), grad_u_ref [B, n].  fp32 in / out, double inside.  At a kink of the solution map (a coordinate exactly
+ * on its bound, the constraint exactly touching) the clipped / inactive side is differentiated. */
+int cbfrrt_qp_backward(int n, const float *a, const float *c, const float *u_ref, int64_t B, const float *u_lo,
+                       const float *u_hi, float relaxation_penalty, const float *grad_u, const float *grad_r,
+                       float *grad_a, float *grad_c, float *grad_u_ref, void *stream);
+
 /* ---- K8 for n_scenarios > 1: batched multi-constraint CLF/CBF-QP ---------------------------------------------
  * Replaces CLFController._solve_CLF_QP_cvxpylayers (clf_controller.py:354-404; one relaxed constraint per scenario,
  * :86-139) when len(scenarios) = S > 1:

@@ -114,6 +114,19 @@ def qp(a, c, u_ref, u_lo, u_hi, penalty):
     return u, r
 
 
+def qp_backward(a, c, u_ref, u_lo, u_hi, penalty, grad_u, grad_r=None, want_margin=False):
+    """float64 adjoint of the single-constraint QP on its active set -> (dL/da, dL/dc, dL/du_ref[, kink margin])"""
+    a, c, u_ref, u_lo, u_hi, grad_u = _f(a), _f(c).reshape(-1), _f(u_ref), _f(u_lo), _f(u_hi), _f(grad_u)
+    B, n = a.shape
+    gr = _f(grad_r).reshape(-1) if grad_r is not None else None
+    ga, gc, gt = np.empty((B, n), np.float32), np.empty(B, np.float32), np.empty((B, n), np.float32)
+    mg = np.empty(B, np.float32)
+    rc = lib().oracle_qp_backward(n, _p(a), _p(c), _p(u_ref), C.c_long(B), _p(u_lo), _p(u_hi), C.c_float(penalty),
+                                  _p(grad_u), _p(gr) if gr is not None else None, _p(ga), _p(gc), _p(gt), _p(mg))
+    assert rc == 0
+    return (ga, gc, gt, mg) if want_margin else (ga, gc, gt)
+
+
 def qp_multi(a, c, u_ref, u_lo, u_hi, penalty, max_iter=2000, tol=1e-10, want_iters=False):
     """float64 dual active-set solve of the S-scenario QP; iters == max_iter marks a row that did not converge"""
     a, c, u_ref, u_lo, u_hi = _f(a), _f(c), _f(u_ref), _f(u_lo), _f(u_hi)

@@ -683,6 +683,72 @@ API int oracle_qp(int n, const float *a, const float *c, const float *u_ref, lon
     return 0;
 }
 
+/* reverse mode of the single-constraint QP (double): what backpropagation through the reference's CvxpyLayer yields
+ * (clf_controller.py:82-139, solve_CLF_QP(requires_grad=True) :461-528), written from the KKT system on the active
+ * set.  F = unclipped coordinates at the solution.
+ *   inactive (mu = 0):    du_F = du_ref_F
+ *   tight (0 < mu < p):   a.u + c = 0 and u_F = u_ref_F - mu a_F / 2  =>  differentiate both, eliminate dmu
+ *   relaxed (mu = p):     u_F = u_ref_F - p a_F / 2,  r = c + a.u
+ * margin [B] (optional): distance of the row from the nearest kink of the solution map (min over coordinates of the
+ * distance of the unclipped value to its bounds, |g(0)|, |g(p)|, mu, p - mu) -- tests skip rows sitting on a kink. */
+API int oracle_qp_backward(int n, const float *a, const float *c, const float *u_ref, long B, const float *u_lo,
+                           const float *u_hi, float penalty, const float *grad_u, const float *grad_r, float *grad_a,
+                           float *grad_c, float *grad_u_ref, float *margin) {
+    if (n > MAXN) return -1;
+    const double p = penalty < 1e6f ? (double)penalty : 1e6;
+    for (long b = 0; b < B; ++b) {
+        double ad[MAXN], ur[MAXN], lo[MAXN], hi[MAXN], u[MAXN], gu[MAXN];
+        int fr[MAXN];
+        for (int k = 0; k < n; ++k) {
+            ad[k] = a[b * n + k]; ur[k] = u_ref[b * n + k]; lo[k] = u_lo[k]; hi[k] = u_hi[k]; gu[k] = grad_u[b * n + k];
+        }
+        const double cc = c[b], gr = grad_r ? (double)grad_r[b] : 0.0;
+        const double mu = qp_mu_exact(n, ad, ur, lo, hi, cc, p);
+        const double g = qp_g(n, ad, ur, lo, hi, cc, mu, u);
+        double S = 0.0, G = 0.0, mg = 1e30;
+        for (int k = 0; k < n; ++k) {
+            const double v = ur[k] - 0.5 * mu * ad[k];
+            fr[k] = v > lo[k] && v < hi[k];
+            if (fr[k]) { S += ad[k] * ad[k]; G += gu[k] * ad[k]; }
+            if (fabs(v - lo[k]) < mg) mg = fabs(v - lo[k]);
+            if (fabs(v - hi[k]) < mg) mg = fabs(v - hi[k]);
+        }
+        const double g0 = qp_g(n, ad, ur, lo, hi, cc, 0.0, 0), gp = qp_g(n, ad, ur, lo, hi, cc, p, 0);
+        if (fabs(g0) < mg) mg = fabs(g0);
+        if (fabs(gp) < mg) mg = fabs(gp);
+        if (margin) margin[b] = (float)mg;
+        double ga[MAXN], gt[MAXN], gc;
+        if (!(mu > 0.0)) {
+            gc = 0.0;
+            for (int k = 0; k < n; ++k) { ga[k] = 0.0; gt[k] = fr[k] ? gu[k] : 0.0; }
+        } else if (mu >= p) {
+            const double grr = g > 0.0 ? gr : 0.0;
+            gc = grr;
+            for (int k = 0; k < n; ++k) {
+                const double gk = fr[k] ? gu[k] + grr * ad[k] : 0.0;
+                gt[k] = gk;
+                ga[k] = grr * u[k] - 0.5 * p * gk;
+            }
+        } else {
+            /* unknowns (du_F, dmu):  du_F + a_F dmu / 2 = du_ref_F - mu da_F / 2 ;  a_F.du_F = -dc - u.da
+             * adjoint: lambda solves the transposed system for the seed gu_F */
+            const double lam = S > 0.0 ? G / S : 0.0;            /* multiplier of the tightness equation */
+            gc = -lam;
+            for (int k = 0; k < n; ++k) {
+                const double w = fr[k] ? gu[k] - lam * ad[k] : 0.0; /* adjoint of the stationarity rows */
+                gt[k] = w;
+                ga[k] = -lam * u[k] - 0.5 * mu * w;
+            }
+        }
+        for (int k = 0; k < n; ++k) {
+            if (grad_a) grad_a[b * n + k] = (float)ga[k];
+            if (grad_u_ref) grad_u_ref[b * n + k] = (float)gt[k];
+        }
+        if (grad_c) grad_c[b] = (float)gc;
+    }
+    return 0;
+}
+
 /* multi-scenario QP on caller-supplied data: a [B,S,n], c [B,S], u_ref [B,n] -> u [B,n], r [B,S] */
 API int oracle_qp_multi(int n, int S, const float *a, const float *c, const float *u_ref, long B, const float *u_lo,
                         const float *u_hi, float penalty, int max_iter, double tol, float *u, float *r, int *iters) {

@@ -48,6 +48,11 @@ def install(monkeypatch):
         u, r = c_oracle.qp(_np(a), _np(c), _np(u_ref), _np(u_lo), _np(u_hi), penalty)
         return torch.from_numpy(u), torch.from_numpy(r)
 
+    def qp_backward(a, c, u_ref, u_lo, u_hi, penalty, grad_u, grad_r):
+        ga, gc, gt = c_oracle.qp_backward(_np(a), _np(c), _np(u_ref), _np(u_lo), _np(u_hi), penalty, _np(grad_u),
+                                          _np(grad_r) if grad_r.numel() else None)
+        return torch.from_numpy(ga), torch.from_numpy(gc), torch.from_numpy(gt)
+
     def qp_multi(a, c, u_ref, u_lo, u_hi, penalty, max_sweeps, tol):
         u, r = c_oracle.qp_multi(_np(a), _np(c), _np(u_ref), _np(u_lo), _np(u_hi), penalty)
         return torch.from_numpy(u), torch.from_numpy(r), torch.zeros(a.shape[0], dtype=torch.int32)
@@ -87,6 +92,6 @@ def install(monkeypatch):
                                    _np(u_lo), _np(u_hi), thr_soft, thr_hard, lam, penalty)
         return torch.from_numpy(o["safe"]), torch.from_numpy(o["u"])
 
-    for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp, qp_multi=qp_multi,
+    for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp, qp_backward=qp_backward, qp_multi=qp_multi,
                          edge_validity=edge_validity, edge_validity_var=edge_validity_var, knn=knn, radius_mask=radius_mask, rollout=rollout, valid_control=valid_control).items():
         monkeypatch.setattr(ops, name, fn)

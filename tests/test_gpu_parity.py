@@ -210,6 +210,87 @@ def test_qp_reference_outside_box(coracle):
     assert rel_err(u.cpu().numpy(), uo) < 2e-5 and rel_err(r.cpu().numpy(), ro, floor=0.1) < 2e-5
 
 
+@pytest.mark.parametrize("n,p", [(7, 5000.0), (4, 5000.0), (7, 0.5), (1, 2.0), (2, 50.0), (3, 1e3), (5, 0.05), (6, 1e9),
+                                 (8, 5000.0)])
+def test_qp_backward_matches_oracle(coracle, n, p):
+    """cbfrrt::qp_backward (closed-form reverse mode of the single-constraint QP) vs the fp64 oracle adjoint, which the
+    CPU suite pins against finite differences (tests/test_qp_backward_cpu.py).  1e-5 relative to the row's gradient
+    scale on every row; rows within 1e-6 of a kink of the solution map (where the two may pick different one-sided
+    derivatives) are the only ones allowed to differ and must be rare."""
+    from cbfrrt import ops
+    rng = np.random.default_rng(200 + n)
+    B = 50000
+    lo, hi = -rng.uniform(0.5, 2.0, n).astype(np.float32), rng.uniform(0.5, 2.0, n).astype(np.float32)
+    a = rng.normal(size=(B, n)).astype(np.float32)
+    c = rng.normal(scale=2.0, size=B).astype(np.float32)
+    ur = rng.uniform(-2.5, 2.5, size=(B, n)).astype(np.float32)
+    gu = rng.normal(size=(B, n)).astype(np.float32)
+    gr = rng.normal(size=B).astype(np.float32)
+    ga_o, gc_o, gt_o, margin = coracle.qp_backward(a, c, ur, lo, hi, p, gu, gr, want_margin=True)
+    ga, gc, gt = (x.cpu().numpy() for x in ops.qp_backward(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p, _t(gu), _t(gr)))
+    ok = margin > 1e-6
+    assert ok.mean() > 0.999
+    scale = np.maximum(1.0, np.maximum(np.abs(ga_o).max(1), np.maximum(np.abs(gt_o).max(1), np.abs(gc_o))))
+    for got, want in ((ga, ga_o), (gt, gt_o), (gc[:, None], gc_o[:, None])):
+        err = np.abs(got.astype(np.float64) - want).max(1) / scale
+        assert err[ok].max() < TOL, (n, p, err[ok].max())
+    # all three pieces of the solution map occur in the batch (or the two the penalty allows)
+    u, r = coracle.qp(a, c, ur, lo, hi, p)
+    g0 = c + np.sum(a * np.clip(ur, lo, hi), 1)
+    assert (g0 <= 0).sum() > 100 and ((g0 > 0) & (r == 0)).sum() + (r > 0).sum() > 100
+    # grad_r omitted = zeros; optional outputs; empty batch
+    ga0, gc0, gt0 = ops.qp_backward(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p, _t(gu), torch.empty(0, device="cuda"))
+    ga_z, gc_z, gt_z = coracle.qp_backward(a, c, ur, lo, hi, p, gu, None)
+    assert rel_err(ga0.cpu().numpy()[ok], ga_z[ok], floor=10.0) < TOL and rel_err(gc0.cpu().numpy()[ok], gc_z[ok], floor=10.0) < TOL
+    e = ops.qp_backward(_t(a[:0]), _t(c[:0]), _t(ur[:0]), _t(lo), _t(hi), p, _t(gu[:0]), _t(gr[:0]))
+    assert e[0].shape == (0, n) and e[1].shape == (0,)
+
+
+def test_differentiable_filter_on_gpu(coracle):
+    """solve_CLF_QP(requires_grad=True): torch autograd through h_nn for (h, J) + cbfrrt::qp / qp_backward.  Same
+    controls as the fused inference launch; parameter gradients equal those of an all-torch float64 restatement
+    (the QP piece differentiated by torch on the oracle's active set)."""
+    from cbfrrt.environment import ArmEnv
+    from cbfrrt.neural_cbf.systems import ArmMindis
+    from cbfrrt.neural_cbf.controllers import NeuralMindisCBFController
+    env = ArmEnv(["panda"], config_file="", include_floor=True)
+    dyn = ArmMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.02, env=env, robot=env.robot_list[0])
+    torch.manual_seed(1)
+    ctrl = NeuralMindisCBFController(dyn, [{"m1": 5.76}], None, None, cbf_alpha=0.1, cbf_relaxation_penalty=5000.0,
+                                     safe_level=0.1, unsafe_level=0.1, cbf_hidden_layers=2, cbf_hidden_size=48)
+    with torch.no_grad():
+        ctrl.h_nn.output_linear.bias += 30.0          # make the barrier constraint bite
+    x = dyn.sample_safe(256)
+    (u0, r0), _ = ctrl.solve_CLF_QP(x)
+    (u1, r1), _ = ctrl.solve_CLF_QP(x, requires_grad=True)
+    assert u1.requires_grad and rel_err(u1.detach().numpy(), u0.numpy()) < 2e-5
+    assert (u0 - dyn.u_nominal(x)).abs().max() > 1e-3
+    w = torch.linspace(-1, 1, 7)
+    ((u1 * w).sum() + 0.01 * r1.sum()).backward()
+    got = {k: p.grad.detach().cpu().double().clone() for k, p in ctrl.h_nn.named_parameters()}
+    # float64 restatement: same network in double, QP adjoint from the oracle injected as the cotangent of (J, c)
+    net64 = torch.nn.Sequential(*[torch.nn.Linear(m.in_features, m.out_features) if isinstance(m, torch.nn.Linear)
+                                  else torch.nn.ReLU() for m in ctrl.h_nn]).double()
+    with torch.no_grad():
+        for (_, a_), (_, b_) in zip(ctrl.h_nn.state_dict().items(), net64.state_dict().items()):
+            b_.copy_(a_.detach().cpu().double())
+    d = x.double()
+    xin = d[:, :8].clone().requires_grad_(True)
+    h = net64(xin)
+    Jh = torch.autograd.grad(h.sum(), xin, create_graph=True)[0]
+    J = Jh[:, :7] + Jh[:, 7:] * d[:, 8:]
+    up, lo_ = dyn.control_limits
+    gu = np.tile(w.numpy(), (256, 1)).astype(np.float32)
+    ga, gc, gt, margin = coracle.qp_backward(J.detach().numpy(), 0.1 * h.detach().numpy()[:, 0], dyn.u_nominal(x).numpy(),
+                                             lo_.numpy(), up.numpy(), 5000.0, gu, np.full(256, 0.01, np.float32),
+                                             want_margin=True)
+    assert (margin > 1e-6).all()
+    ((J * torch.from_numpy(ga).double()).sum() + (0.1 * h[:, 0] * torch.from_numpy(gc).double()).sum()).backward()
+    for (k, g), (_, p64) in zip(got.items(), net64.named_parameters()):
+        ref = p64.grad
+        assert float((g - ref).abs().max()) < 1e-3 * max(1.0, float(ref.abs().max())), k
+
+
 @pytest.mark.parametrize("n,S,p", [(4, 2, 50.0), (7, 3, 1e3), (7, 4, 0.05), (7, 2, 1e9), (4, 3, 5000.0), (7, 1, 50.0),
                                    (1, 2, 50.0), (2, 4, 5000.0), (8, 3, 1e3), (3, 2, 1e9), (5, 4, 50.0), (6, 2, 0.05)])
 def test_qp_multi_matches_oracle(coracle, n, S, p):

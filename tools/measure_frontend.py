@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Device-resident timings of the planner front-end and the stand-alone QP entry points (1 GPU): cbfrrt::knn,
-cbfrrt::radius_mask, cbfrrt::qp, cbfrrt::qp_multi, cbfrrt::edge_validity_var.  One JSON line per measurement."""
+cbfrrt::radius_mask, cbfrrt::qp, cbfrrt::qp_backward, cbfrrt::qp_multi, cbfrrt::edge_validity_var.  One JSON line per measurement."""
 import json
 import os
 import sys
@@ -42,6 +42,10 @@ def main():
     lo, hi = t(-np.ones(n)), t(np.ones(n))
     a1, c1, ur = t(rng.normal(size=(B, n))), t(rng.normal(size=B)), t(rng.uniform(-1.5, 1.5, size=(B, n)))
     out.append(dict(op="qp", rows=B, n=n, ms=timed(lambda: ops.qp(a1, c1, ur, lo, hi, 5000.0))))
+    gu, gr = t(rng.normal(size=(B, n))), t(rng.normal(size=B))
+    ms = timed(lambda: ops.qp_backward(a1, c1, ur, lo, hi, 5000.0, gu, gr))
+    out.append(dict(op="qp_backward", rows=B, n=n, ms=ms, algorithmic_bytes_per_row=4 * (3 * n + 2) + 4 * (2 * n + 1),
+                    gb_per_s=B * (4 * (3 * n + 2) + 4 * (2 * n + 1)) / ms / 1e6))
     for S in (2, 4):
         a, c = t(rng.normal(size=(B, S, n))), t(rng.normal(scale=0.8, size=(B, S)))
         out.append(dict(op="qp_multi", rows=B, n=n, constraints=S, ms=timed(lambda: ops.qp_multi(a, c, ur, lo, hi, 5000.0, 100, 1e-9))))
