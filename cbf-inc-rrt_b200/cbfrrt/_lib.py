@@ -62,6 +62,7 @@ SIGNATURES = {
     "cbfrrt_knn": (C.c_int, [_I, _P, _P, _L, _L, C.c_int32, _P, _P, _P, _P]),
     "cbfrrt_radius_mask": (C.c_int, [_I, _P, _P, _L, _L, _F, _P, _P]),
     "cbfrrt_qp_multi": (C.c_int, [_I, _I, _P, _P, _P, _L, _P, _P, _F, _I, _F, _P, _P, _P, _P]),
+    "cbfrrt_qp_multi_backward": (C.c_int, [_I, _I, _P, _P, _P, _L, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P]),
     "cbfrrt_safety_filter": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, _L, C.POINTER(FilterParams),
                                        _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cbfrrt_safety_filter_scatter": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, _L,

@@ -75,17 +75,16 @@ class CLFController(Controller):
 
     def _solve_CLF_QP_exact(self, x, u_ref, V, Lf_V, Lg_V, relaxation_penalty: float, requires_grad: bool = False):
         """Batched exact solve on the GPU (replaces _solve_CLF_QP_cvxpylayers, clf_controller.py:354-404).  With
-        ``requires_grad`` the single-scenario solve is differentiable w.r.t. V, Lf_V, Lg_V and u_ref like the
-        reference's CvxpyLayer (closed-form active-set sensitivities, cbfrrt::qp_backward)."""
+        ``requires_grad`` the solve is differentiable w.r.t. V, Lf_V, Lg_V and u_ref like the reference's CvxpyLayer
+        (closed-form active-set sensitivities: cbfrrt::qp_backward, cbfrrt::qp_multi_backward)."""
         dev = self.device
         upper, lower = self.dynamics_model.control_limits
         if self.n_scenarios != 1:
-            if requires_grad:
-                raise NotImplementedError("differentiable solve is built for n_scenarios == 1 (cbfrrt::qp_backward)")
             a = Lg_V.to(dev, torch.float32)
             c = (Lf_V[:, :, 0] + self.clf_lambda * V.reshape(-1, 1)).to(dev, torch.float32)
-            u, r, _ = ops.qp_multi(a, c, u_ref.to(dev, torch.float32), lower.to(dev, torch.float32),
-                                   upper.to(dev, torch.float32), float(relaxation_penalty), self.qp_max_sweeps, self.qp_tol)
+            solve = ops.qp_multi_diff if requires_grad else ops.qp_multi
+            u, r = solve(a, c, u_ref.to(dev, torch.float32), lower.to(dev, torch.float32), upper.to(dev, torch.float32),
+                         float(relaxation_penalty), self.qp_max_sweeps, self.qp_tol)[:2]
             return u.to(x.device).type_as(x), r.to(x.device).type_as(x)
         a = Lg_V[:, 0, :].to(dev, torch.float32)
         c = (Lf_V[:, 0, 0] + self.clf_lambda * V.reshape(-1)).to(dev, torch.float32)

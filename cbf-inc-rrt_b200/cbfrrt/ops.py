@@ -280,6 +280,27 @@ def qp_multi(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, pe
     return u, r, sweeps
 
 
+@torch.library.custom_op("cbfrrt::qp_multi_backward", mutates_args=(), device_types="cuda")
+def qp_multi_backward(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty: float, max_sweeps: int,
+                      tol: float, grad_u: Tensor, grad_r: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """reverse mode of ``qp_multi``: (dL/du f32[B,n], dL/dr f32[B,S] or empty) -> dL/da [B,S,n], dL/dc [B,S], dL/du_ref [B,n]"""
+    a, c, u_ref, u_lo, u_hi, grad_u, grad_r = (_f32c(x) for x in (a, c, u_ref, u_lo, u_hi, grad_u, grad_r))
+    if a.dim() != 3:
+        raise ValueError("qp_multi_backward: a must be [B, S, n]")
+    B, S, n = a.shape
+    if u_ref.shape != (B, n) or grad_u.shape != (B, n) or c.shape != (B, S) or grad_r.numel() not in (0, B * S) \
+            or u_lo.numel() != n or u_hi.numel() != n:
+        raise ValueError("qp_multi_backward: inconsistent shapes")
+    ga = torch.empty((B, S, n), dtype=torch.float32, device=a.device)
+    gc = torch.empty((B, S), dtype=torch.float32, device=a.device)
+    gt = torch.empty((B, n), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.cbfrrt_qp_multi_backward(n, S, _ptr(a), _ptr(c), _ptr(u_ref), B, _ptr(u_lo), _ptr(u_hi), penalty,
+                                           max_sweeps, tol, _ptr(grad_u), _ptr(grad_r), _ptr(ga), _ptr(gc), _ptr(gt),
+                                           _stream()), "cbfrrt_qp_multi_backward")
+    return ga, gc, gt
+
+
 @torch.library.custom_op("cbfrrt::safety_filter", mutates_args=(), device_types="cuda")
 def safety_filter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor, K: Tensor,
                   u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float,
@@ -473,7 +494,7 @@ def _direct(op, cpu_ok=()):
     return call
 
 
-for _name in ("fk", "collide", "observe", "masks", "cbf_filter", "qp", "qp_backward", "qp_multi", "safety_filter", "valid_control",
+for _name in ("fk", "collide", "observe", "masks", "cbf_filter", "qp", "qp_backward", "qp_multi", "qp_multi_backward", "safety_filter", "valid_control",
               "edge_validity", "edge_validity_var", "knn", "radius_mask", "rollout"):
     registered[_name] = globals()[_name]
     globals()[_name] = _direct(registered[_name], cpu_ok=(2,) if _name == "edge_validity_var" else ())
@@ -496,6 +517,31 @@ class _DifferentiableQP(torch.autograd.Function):
         gu = torch.zeros_like(a, dtype=torch.float32) if grad_u is None else grad_u
         ga, gc, gt = qp_backward(a, c, u_ref, u_lo, u_hi, ctx.penalty, gu, empty if grad_r is None else grad_r)
         return ga.to(a.dtype).reshape(a.shape), gc.to(c.dtype).reshape(c.shape), gt.to(u_ref.dtype), None, None, None
+
+
+class _DifferentiableMultiQP(torch.autograd.Function):
+    """``qp_multi`` with the reverse mode ``qp_multi_backward``"""
+
+    @staticmethod
+    def forward(ctx, a, c, u_ref, u_lo, u_hi, penalty, max_sweeps, tol):
+        ctx.save_for_backward(a, c, u_ref, u_lo, u_hi)
+        ctx.args = (float(penalty), int(max_sweeps), float(tol))
+        u, r, _ = qp_multi(a, c, u_ref, u_lo, u_hi, *ctx.args)
+        return u, r
+
+    @staticmethod
+    def backward(ctx, grad_u, grad_r):
+        a, c, u_ref, u_lo, u_hi = ctx.saved_tensors
+        empty = torch.empty(0, dtype=torch.float32, device=a.device)
+        gu = torch.zeros_like(u_ref, dtype=torch.float32) if grad_u is None else grad_u
+        ga, gc, gt = qp_multi_backward(a, c, u_ref, u_lo, u_hi, *ctx.args, gu, empty if grad_r is None else grad_r)
+        return ga.to(a.dtype), gc.to(c.dtype), gt.to(u_ref.dtype), None, None, None, None, None
+
+
+def qp_multi_diff(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty: float, max_sweeps: int = 100,
+                  tol: float = 1e-9) -> Tuple[Tensor, Tensor]:
+    """differentiable multi-scenario QP: (u [B,n], r [B,S]) with gradients w.r.t. a [B,S,n], c [B,S], u_ref [B,n]"""
+    return _DifferentiableMultiQP.apply(a, c, u_ref, u_lo, u_hi, penalty, max_sweeps, tol)
 
 
 def qp_diff(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty: float) -> Tuple[Tensor, Tensor]:

@@ -139,6 +139,25 @@ int cbfrrt_qp_multi(int n, int n_constraints, const float* a, const float* c, co
     return finish_launch();
 }
 
+int cbfrrt_qp_multi_backward(int n, int n_constraints, const float* a, const float* c, const float* u_ref, int64_t B,
+                             const float* u_lo, const float* u_hi, float relaxation_penalty, int max_iter, float tol,
+                             const float* grad_u, const float* grad_r, float* grad_a, float* grad_c, float* grad_u_ref,
+                             void* stream) {
+    if (B < 0 || !u_lo || !u_hi || max_iter < 1 || !(tol >= 0.f)) return CBFRRT_ERR_BAD_SHAPE;
+    if (n < 1 || n > 8 || n_constraints < 1 || n_constraints > QP_MAX_CON) return CBFRRT_ERR_UNSUPPORTED;
+    if (B == 0) return CBFRRT_OK;
+    if (!a || !c || !u_ref || !grad_u) return CBFRRT_ERR_BAD_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = (B + 127) / 128;
+    const int grid = (int)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
+    switch (n) {
+#define CBF_QP_CASE(NN) case NN: qp_multi_backward_kernel<NN><<<grid, 128, 0, st>>>(a, c, u_ref, B, n_constraints, u_lo, u_hi, relaxation_penalty, max_iter, tol, grad_u, grad_r, grad_a, grad_c, grad_u_ref); break;
+        CBF_QP_CASE(1) CBF_QP_CASE(2) CBF_QP_CASE(3) CBF_QP_CASE(4) CBF_QP_CASE(5) CBF_QP_CASE(6) CBF_QP_CASE(7) CBF_QP_CASE(8)
+#undef CBF_QP_CASE
+    }
+    return finish_launch();
+}
+
 int cbfrrt_safety_filter(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* net, const float* q,
                          int64_t q_stride, int64_t B, const cbfrrt_filter_params* fp, float thr_soft, float thr_hard,
                          uint8_t* safe, uint8_t* unsafe, float* datax, float* h, float* J, float* u, float* r,

@@ -380,6 +380,49 @@ __global__ void __launch_bounds__(128) qp_multi_kernel(const float* __restrict__
     }
 }
 
+// reverse mode of the multi-scenario QP: re-solves the row (stateless ABI: no multipliers are carried over from the
+// forward call) and applies qp_multi_adjoint.  grad_a [B,S,n], grad_c [B,S], grad_u_ref [B,n]; all double inside.
+template <int N>
+__global__ void __launch_bounds__(128) qp_multi_backward_kernel(const float* __restrict__ a, const float* __restrict__ c,
+                                                                const float* __restrict__ u_ref, long long B, int S,
+                                                                const float* __restrict__ u_lo, const float* __restrict__ u_hi,
+                                                                float penalty, int max_iter, float tol,
+                                                                const float* __restrict__ grad_u, const float* __restrict__ grad_r,
+                                                                float* __restrict__ grad_a, float* __restrict__ grad_c,
+                                                                float* __restrict__ grad_u_ref) {
+    __shared__ double lim[2 * N];
+    if (threadIdx.x < N) { lim[threadIdx.x] = u_lo[threadIdx.x]; lim[N + threadIdx.x] = u_hi[threadIdx.x]; }
+    __syncthreads();
+    for (long long b = (long long)blockIdx.x * 128 + threadIdx.x; b < B; b += (long long)gridDim.x * 128) {
+        double aa[QP_MAX_CON][N], cc[QP_MAX_CON], ur[N], uu[N], rr[QP_MAX_CON], gu[N], gr[QP_MAX_CON];
+#pragma unroll
+        for (int i = 0; i < QP_MAX_CON; ++i) {
+            cc[i] = i < S ? (double)__ldg(c + b * S + i) : 0.0;
+            gr[i] = (i < S && grad_r) ? (double)__ldg(grad_r + b * S + i) : 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) aa[i][k] = i < S ? (double)__ldg(a + (b * S + i) * N + k) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) { ur[k] = (double)__ldg(u_ref + b * N + k); gu[k] = (double)__ldg(grad_u + b * N + k); }
+        const double p = (double)fminf(penalty, 1e6f);
+        qp_solve_multi<N, QP_MAX_CON, double>(aa, ur, lim, lim + N, cc, S, p, max_iter, (double)tol, uu, rr);
+        double ga[QP_MAX_CON][N], gc[QP_MAX_CON], gt[N];
+        qp_multi_adjoint<N, QP_MAX_CON, double>(aa, ur, lim, lim + N, cc, S, p, uu, gu, gr, ga, gc, gt);
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (grad_u_ref) grad_u_ref[b * N + k] = (float)gt[k];
+#pragma unroll
+        for (int i = 0; i < QP_MAX_CON; ++i) {
+            if (i < S) {
+                if (grad_c) grad_c[b * S + i] = (float)gc[i];
+#pragma unroll
+                for (int k = 0; k < N; ++k)
+                    if (grad_a) grad_a[(b * S + i) * N + k] = (float)ga[i][k];
+            }
+        }
+    }
+}
+
 template <class RB, int H, int L, bool GRID>
 __global__ void __launch_bounds__(NT) safety_kernel(SceneArgs sc, NetArgs net, const float* __restrict__ q,
                                                     long long q_stride, long long B, float thr_soft, float thr_hard,

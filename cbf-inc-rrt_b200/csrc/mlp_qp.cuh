@@ -458,6 +458,97 @@ __host__ __device__ __forceinline__ int qp_solve_multi(const T (&a)[S][N], const
     return it;
 }
 
+// Reverse mode of the S-constraint QP at its solution u (from qp_solve_multi).  Active sets are read off the solution:
+// F = unclipped coordinates; per constraint g_i = c_i + a_i.u:  relaxed P (g_i > 0, mu_i = p, r_i = g_i), tight W
+// (g_i = 0, 0 < mu_i < p), inactive Z (g_i < 0).  On that set
+//     u_F = t_F - (A_WF^T mu_W + p sum_P a_i,F) / 2,        A_W u + c_W = 0,
+// and with M = A_WF A_WF^T, cotangent w_F = gu_F + sum_P gr_i a_i,F:
+//     lambda = -M^-1 A_WF w_F,  v_F = w_F + A_WF^T lambda,  mu_W = M^-1 A_WF (2 (t_F - u_F) - p sum_P a_i,F)
+//     dL/dt_F = v_F;   dL/dc_W = lambda, dL/dc_P = gr_P;   dL/da_i = lambda_i u - mu_i v_F / 2  (W),  gr_i u - p v_F / 2  (P).
+// S = 1 reduces to qp_backward.  M is regularised like the Newton matrix of the solver (duplicate tight constraints).
+template <int N, int S, typename T>
+__host__ __device__ __forceinline__ void qp_multi_adjoint(const T (&a)[S][N], const T (&uref)[N], const T* __restrict__ lo,
+                                                     const T* __restrict__ hi, const T (&c)[S], int n_con, T p,
+                                                     const T (&u)[N], const T (&gu)[N], const T (&gr)[S],
+                                                     T (&ga)[S][N], T (&gc)[S], T (&gt)[N]) {
+    bool fr[N];
+    int kind[S];                                 // 0 inactive, 1 tight, 2 relaxed
+    T w[N], sp[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { fr[k] = u[k] > lo[k] && u[k] < hi[k]; w[k] = fr[k] ? gu[k] : T(0.); sp[k] = T(0.); }
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        T g = c[i], sc = T(1.) + fabs(c[i]);
+#pragma unroll
+        for (int k = 0; k < N; ++k) { g = fma(a[i][k], u[k], g); sc += fabs(a[i][k]); }
+        sc *= T(1e-6);
+        kind[i] = i < n_con ? (g > sc ? 2 : (g >= -sc ? 1 : 0)) : 0;
+        if (kind[i] == 2) {
+#pragma unroll
+            for (int k = 0; k < N; ++k)
+                if (fr[k]) { w[k] = fma(gr[i], a[i][k], w[k]); sp[k] += a[i][k]; }
+        }
+    }
+    T M[S][S], lam[S], mu[S], tr = T(0.);
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        T r1 = T(0.), r2 = T(0.);
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (fr[k]) { r1 = fma(-a[i][k], w[k], r1); r2 = fma(a[i][k], T(2.) * (uref[k] - u[k]) - p * sp[k], r2); }
+        lam[i] = kind[i] == 1 ? r1 : T(0.);
+        mu[i] = kind[i] == 1 ? r2 : T(0.);
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            T acc = T(0.);
+#pragma unroll
+            for (int k = 0; k < N; ++k)
+                if (fr[k]) acc = fma(a[i][k], a[j][k], acc);
+            M[i][j] = (kind[i] == 1 && kind[j] == 1) ? acc : (i == j ? T(1.) : T(0.));
+        }
+        if (kind[i] == 1) tr += M[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+        if (kind[i] == 1) M[i][i] += T(1e-12) * tr + T(1e-300);
+#pragma unroll
+    for (int i = 0; i < S; ++i) {                // Gaussian elimination (SPD), two right-hand sides
+        const T inv = T(1.) / M[i][i];
+#pragma unroll
+        for (int j = i + 1; j < S; ++j) {
+            const T f = M[j][i] * inv;
+#pragma unroll
+            for (int k = i; k < S; ++k) M[j][k] = fma(-f, M[i][k], M[j][k]);
+            lam[j] = fma(-f, lam[i], lam[j]);
+            mu[j] = fma(-f, mu[i], mu[j]);
+        }
+    }
+#pragma unroll
+    for (int i = S - 1; i >= 0; --i) {
+#pragma unroll
+        for (int j = i + 1; j < S; ++j) { lam[i] = fma(-M[i][j], lam[j], lam[i]); mu[i] = fma(-M[i][j], mu[j], mu[i]); }
+        lam[i] /= M[i][i];
+        mu[i] /= M[i][i];
+    }
+    T v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        v[k] = w[k];
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+            if (kind[i] == 1 && fr[k]) v[k] = fma(a[i][k], lam[i], v[k]);
+        gt[k] = v[k];
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        const T head = kind[i] == 1 ? lam[i] : (kind[i] == 2 ? gr[i] : T(0.));
+        const T half = kind[i] == 1 ? T(0.5) * mu[i] : (kind[i] == 2 ? T(0.5) * p : T(0.));
+        gc[i] = head;
+#pragma unroll
+        for (int k = 0; k < N; ++k) ga[i][k] = fma(head, u[k], -half * v[k]);
+    }
+}
+
 // everything after the MLP: J = Jh_q + Jh_o do/dq, nominal control, QP
 template <int N>
 __device__ __forceinline__ void cbf_filter_post(const float* __restrict__ prm, const float (&q)[N], const float (&dodq)[N],

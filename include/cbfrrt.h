@@ -173,6 +173,15 @@ int cbfrrt_qp_multi(int n, int n_constraints, const float *a, const float *c, co
                     const float *u_lo, const float *u_hi, float relaxation_penalty, int max_iter, float tol,
                     float *u, float *r, int32_t *iters, void *stream);
 
+/* Reverse mode of cbfrrt_qp_multi (same role as cbfrrt_qp_backward for len(scenarios) > 1): grad_u [B, n], grad_r
+ * [B, S] (NULL = 0) -> grad_a [B, S, n], grad_c [B, S], grad_u_ref [B, n] (each optional).  Stateless: the row is
+ * solved again inside the call (same max_iter / tol as the forward call), the active sets are read off the solution
+ * (unclipped coordinates; tight / relaxed / inactive constraints) and the KKT system on them is differentiated. */
+int cbfrrt_qp_multi_backward(int n, int n_constraints, const float *a, const float *c, const float *u_ref, int64_t B,
+                             const float *u_lo, const float *u_hi, float relaxation_penalty, int max_iter, float tol,
+                             const float *grad_u, const float *grad_r, float *grad_a, float *grad_c,
+                             float *grad_u_ref, void *stream);
+
 /* ---- fused q -> (masks, datax, h, J, u, r): one launch for sampled states ------------------------------ */
 int cbfrrt_safety_filter(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_net *net, const float *q,
                          int64_t q_stride, int64_t B, const cbfrrt_filter_params *fp, float thr_soft,

@@ -138,6 +138,20 @@ def qp_multi(a, c, u_ref, u_lo, u_hi, penalty, max_iter=2000, tol=1e-10, want_it
     return (u, r, it) if want_iters else (u, r)
 
 
+def qp_multi_backward(a, c, u_ref, u_lo, u_hi, penalty, grad_u, grad_r=None, want_margin=False):
+    """float64 adjoint of the S-constraint QP on its active set -> (dL/da [B,S,n], dL/dc [B,S], dL/du_ref [B,n][, margin])"""
+    a, c, u_ref, u_lo, u_hi, grad_u = _f(a), _f(c), _f(u_ref), _f(u_lo), _f(u_hi), _f(grad_u)
+    B, S, n = a.shape
+    gr = _f(grad_r).reshape(B, S) if grad_r is not None else None
+    ga, gc, gt = np.empty((B, S, n), np.float32), np.empty((B, S), np.float32), np.empty((B, n), np.float32)
+    mg = np.empty(B, np.float32)
+    rc = lib().oracle_qp_multi_backward(n, S, _p(a), _p(c), _p(u_ref), C.c_long(B), _p(u_lo), _p(u_hi),
+                                        C.c_float(penalty), _p(grad_u), _p(gr) if gr is not None else None, _p(ga),
+                                        _p(gc), _p(gt), _p(mg))
+    assert rc == 0
+    return (ga, gc, gt, mg) if want_margin else (ga, gc, gt)
+
+
 def u_nominal(q, goal, K, u_lo, u_hi):
     """clamp(-K (q - goal), lo, hi) in float32 with the oracle's operation order (filter_state)."""
     q, goal, K = _f(q), _f(goal).reshape(-1, q.shape[1]), _f(K)

@@ -416,7 +416,8 @@ static void qp_exact(int n, const double *a, const double *uref, const double *l
 #define NEWTON_REPS 6
 #endif
 static int qp_multi_exact(int n, int S, const double *a /* [S][n] */, const double *uref, const double *lo,
-                          const double *hi, const double *c, double p, int max_iter, double tol, double *u, double *r) {
+                          const double *hi, const double *c, double p, int max_iter, double tol, double *u, double *r,
+                          double *mu_out) {
     double mu[MAXS] = {0}, t[MAXN], ti[MAXN];
     for (int k = 0; k < n; ++k) t[k] = uref[k];
     int it = 0;
@@ -507,6 +508,7 @@ static int qp_multi_exact(int n, int S, const double *a /* [S][n] */, const doub
         double g = c[i];
         for (int k = 0; k < n; ++k) g += a[i * n + k] * u[k];
         r[i] = g > 0.0 ? g : 0.0; /* optimal relaxation for this u */
+        if (mu_out) mu_out[i] = mu[i];
     }
     return it;
 }
@@ -537,6 +539,83 @@ static void par_for(long B, range_fn fn, void *ctx) {
 #define CLONES __attribute__((target_clones("default", "fma"), flatten))
 #define API __attribute__((visibility("default")))
 API void oracle_set_threads(int t) { g_threads = t < 1 ? 1 : t; }
+
+/* reverse mode of the S-constraint QP (double).  Active sets from the MULTIPLIERS of the converged dual solve
+ * (inactive mu_i = 0, tight 0 < mu_i < p, relaxed mu_i = p) and from the unclipped point v = u_ref - A^T mu / 2
+ * (free coordinates lo < v < hi).  Adjoint of the KKT system on that set:
+ *     stationarity  u_F + A_WF^T mu_W / 2 = u_ref_F - p sum_P a_i,F / 2        (adjoint variable  v_F)
+ *     tightness     A_W u + c_W = 0                                            (adjoint variable  lambda)
+ *  => (A_WF A_WF^T) lambda = -A_WF w_F,  w_F = gu_F + sum_P gr_i a_i,F,  v_F = w_F + A_WF^T lambda.
+ * margin: distance of the row from the nearest change of active set. */
+API int oracle_qp_multi_backward(int n, int S, const float *a, const float *c, const float *u_ref, long B,
+                                 const float *u_lo, const float *u_hi, float penalty, const float *grad_u,
+                                 const float *grad_r, float *grad_a, float *grad_c, float *grad_u_ref, float *margin) {
+    if (n > MAXN || S > MAXS) return -1;
+    const double p = penalty < 1e6f ? (double)penalty : 1e6;
+    for (long b = 0; b < B; ++b) {
+        double ad[MAXS * MAXN], cd[MAXS], ur[MAXN], lo[MAXN], hi[MAXN], u[MAXN], r[MAXS], mu[MAXS], gu[MAXN], gr[MAXS];
+        for (int k = 0; k < S * n; ++k) ad[k] = a[b * S * n + k];
+        for (int i = 0; i < S; ++i) { cd[i] = c[b * S + i]; gr[i] = grad_r ? (double)grad_r[b * S + i] : 0.0; }
+        for (int k = 0; k < n; ++k) { ur[k] = u_ref[b * n + k]; lo[k] = u_lo[k]; hi[k] = u_hi[k]; gu[k] = grad_u[b * n + k]; }
+        qp_multi_exact(n, S, ad, ur, lo, hi, cd, p, 5000, 1e-13, u, r, mu);
+        int fr[MAXN], W[MAXS], nW = 0, P[MAXS];
+        double w[MAXN], mg = 1e30;
+        for (int k = 0; k < n; ++k) {
+            double v = ur[k];
+            for (int i = 0; i < S; ++i) v -= 0.5 * mu[i] * ad[i * n + k];
+            fr[k] = v > lo[k] && v < hi[k];
+            w[k] = fr[k] ? gu[k] : 0.0;
+            if (fabs(v - lo[k]) < mg) mg = fabs(v - lo[k]);
+            if (fabs(v - hi[k]) < mg) mg = fabs(v - hi[k]);
+        }
+        for (int i = 0; i < S; ++i) {
+            double g = cd[i];
+            for (int k = 0; k < n; ++k) g += ad[i * n + k] * u[k];
+            P[i] = mu[i] >= p;
+            if (mu[i] > 0.0 && mu[i] < p) { W[nW++] = i; if (mu[i] < mg) mg = mu[i]; if (p - mu[i] < mg) mg = p - mu[i]; }
+            else if (fabs(g) < mg) mg = fabs(g);
+            if (P[i])
+                for (int k = 0; k < n; ++k) if (fr[k]) w[k] += gr[i] * ad[i * n + k];
+        }
+        if (margin) margin[b] = (float)mg;
+        double M[MAXS][MAXS], lam[MAXS];
+        for (int x = 0; x < nW; ++x) {
+            lam[x] = 0.0;
+            for (int k = 0; k < n; ++k) if (fr[k]) lam[x] -= ad[W[x] * n + k] * w[k];
+            for (int y = 0; y < nW; ++y) {
+                M[x][y] = 0.0;
+                for (int k = 0; k < n; ++k) if (fr[k]) M[x][y] += ad[W[x] * n + k] * ad[W[y] * n + k];
+            }
+        }
+        for (int x = 0; x < nW; ++x) { /* elimination without pivoting: M is a Gram matrix */
+            if (!(M[x][x] > 0.0)) M[x][x] = 1e-300;
+            for (int y = x + 1; y < nW; ++y) {
+                double f = M[y][x] / M[x][x];
+                for (int z = x; z < nW; ++z) M[y][z] -= f * M[x][z];
+                lam[y] -= f * lam[x];
+            }
+        }
+        for (int x = nW - 1; x >= 0; --x) {
+            for (int y = x + 1; y < nW; ++y) lam[x] -= M[x][y] * lam[y];
+            lam[x] /= M[x][x];
+        }
+        double v[MAXN];
+        for (int k = 0; k < n; ++k) {
+            v[k] = w[k];
+            if (fr[k]) for (int x = 0; x < nW; ++x) v[k] += ad[W[x] * n + k] * lam[x];
+            if (grad_u_ref) grad_u_ref[b * n + k] = (float)v[k];
+        }
+        for (int i = 0; i < S; ++i) {
+            double head = 0.0, half = 0.0;
+            for (int x = 0; x < nW; ++x) if (W[x] == i) { head = lam[x]; half = 0.5 * mu[i]; }
+            if (P[i]) { head = r[i] > 0.0 ? gr[i] : 0.0; half = 0.5 * p; }
+            if (grad_c) grad_c[b * S + i] = (float)head;
+            for (int k = 0; k < n; ++k)
+                if (grad_a) grad_a[(b * S + i) * n + k] = (float)(head * u[k] - half * v[k]);
+        }
+    }
+    return 0;
+}
 
 API int oracle_robot_info(int robot, int *n, int *n_links, int *n_spheres) {
     if (robot < 0 || robot > 1) return -1;
@@ -758,7 +837,7 @@ API int oracle_qp_multi(int n, int S, const float *a, const float *c, const floa
         for (int k = 0; k < S * n; ++k) ad[k] = a[b * S * n + k];
         for (int i = 0; i < S; ++i) cd[i] = c[b * S + i];
         for (int k = 0; k < n; ++k) { ur[k] = u_ref[b * n + k]; lo[k] = u_lo[k]; hi[k] = u_hi[k]; }
-        int it = qp_multi_exact(n, S, ad, ur, lo, hi, cd, penalty < 1e6f ? (double)penalty : 1e6, max_iter, tol, ud, rd);
+        int it = qp_multi_exact(n, S, ad, ur, lo, hi, cd, penalty < 1e6f ? (double)penalty : 1e6, max_iter, tol, ud, rd, 0);
         if (iters) iters[b] = it;
         for (int k = 0; k < n; ++k) u[b * n + k] = (float)ud[k];
         for (int i = 0; i < S; ++i) r[b * S + i] = (float)rd[i];

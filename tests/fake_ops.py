@@ -57,6 +57,11 @@ def install(monkeypatch):
         u, r = c_oracle.qp_multi(_np(a), _np(c), _np(u_ref), _np(u_lo), _np(u_hi), penalty)
         return torch.from_numpy(u), torch.from_numpy(r), torch.zeros(a.shape[0], dtype=torch.int32)
 
+    def qp_multi_backward(a, c, u_ref, u_lo, u_hi, penalty, max_sweeps, tol, grad_u, grad_r):
+        ga, gc, gt = c_oracle.qp_multi_backward(_np(a), _np(c), _np(u_ref), _np(u_lo), _np(u_hi), penalty, _np(grad_u),
+                                                _np(grad_r) if grad_r.numel() else None)
+        return torch.from_numpy(ga), torch.from_numpy(gc), torch.from_numpy(gt)
+
     def edge_validity(q_from, q_to, n_interp, boxes, spheres, floor, grid, thr_soft, thr_hard, robot_id):
         b, s = _scene(boxes, spheres)
         v, f = c_oracle.edge_validity(NAME[robot_id], _np(q_from), _np(q_to), n_interp, b, s, bool(floor), thr_soft, thr_hard)
@@ -92,6 +97,6 @@ def install(monkeypatch):
                                    _np(u_lo), _np(u_hi), thr_soft, thr_hard, lam, penalty)
         return torch.from_numpy(o["safe"]), torch.from_numpy(o["u"])
 
-    for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp, qp_backward=qp_backward, qp_multi=qp_multi,
+    for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp, qp_backward=qp_backward, qp_multi=qp_multi, qp_multi_backward=qp_multi_backward,
                          edge_validity=edge_validity, edge_validity_var=edge_validity_var, knn=knn, radius_mask=radius_mask, rollout=rollout, valid_control=valid_control).items():
         monkeypatch.setattr(ops, name, fn)

@@ -246,6 +246,34 @@ def test_qp_backward_matches_oracle(coracle, n, p):
     assert e[0].shape == (0, n) and e[1].shape == (0,)
 
 
+@pytest.mark.parametrize("n,S,p", [(7, 2, 50.0), (7, 3, 1e3), (4, 2, 0.5), (7, 4, 0.05), (7, 2, 1e9), (8, 3, 1e3), (7, 1, 50.0),
+                                   (5, 4, 50.0), (4, 3, 5000.0)])
+def test_qp_multi_backward_matches_oracle(coracle, n, S, p):
+    """cbfrrt::qp_multi_backward vs the fp64 oracle adjoint (pinned against finite differences of an independent KKT solve
+    in the CPU suite).  S <= n: with more tight constraints than free controls the sensitivities are not unique."""
+    from cbfrrt import ops
+    rng = np.random.default_rng(300 + n * S)
+    B = 20000
+    f = lambda x: np.ascontiguousarray(x, np.float32)
+    lo, hi = f(-rng.uniform(0.5, 2.0, n)), f(rng.uniform(0.5, 2.0, n))
+    a, c, ur = f(rng.normal(size=(B, S, n))), f(rng.normal(scale=0.8, size=(B, S))), f(rng.uniform(-2.0, 2.0, size=(B, n)))
+    gu, gr = f(rng.normal(size=(B, n))), f(rng.normal(size=(B, S)))
+    ga_o, gc_o, gt_o, margin = coracle.qp_multi_backward(a, c, ur, lo, hi, p, gu, gr, want_margin=True)
+    ga, gc, gt = (x.cpu().numpy() for x in ops.qp_multi_backward(_t(a), _t(c), _t(ur), _t(lo), _t(hi), p, 100, 1e-9, _t(gu), _t(gr)))
+    ok = margin > 1e-5
+    assert ok.mean() > 0.999
+    scale = np.maximum(1.0, np.maximum(np.abs(ga_o).max((1, 2)), np.maximum(np.abs(gt_o).max(1), np.abs(gc_o).max(1))))
+    err = np.maximum(np.abs(ga - ga_o).max((1, 2)), np.maximum(np.abs(gt - gt_o).max(1), np.abs(gc - gc_o).max(1))) / scale
+    assert err[ok].max() < TOL, (n, S, p, err[ok].max())
+    # autograd wrapper: same numbers through torch.autograd.Function
+    A, Cc, T = (_t(x).requires_grad_(True) for x in (a[:256], c[:256], ur[:256]))
+    u, r = ops.qp_multi_diff(A, Cc, T, _t(lo), _t(hi), p)
+    ((u * _t(gu[:256])).sum() + (r * _t(gr[:256])).sum()).backward()
+    assert np.array_equal(A.grad.cpu().numpy(), ga[:256]) and np.array_equal(T.grad.cpu().numpy(), gt[:256])
+    e = ops.qp_multi_backward(_t(a[:0]), _t(c[:0]), _t(ur[:0]), _t(lo), _t(hi), p, 100, 1e-9, _t(gu[:0]), _t(gr[:0]))
+    assert e[0].shape == (0, S, n)
+
+
 def test_differentiable_filter_on_gpu(coracle):
     """solve_CLF_QP(requires_grad=True): torch autograd through h_nn for (h, J) + cbfrrt::qp / qp_backward.  Same
     controls as the fused inference launch; parameter gradients equal those of an all-torch float64 restatement

@@ -171,3 +171,127 @@ def test_device_code_built_for_the_host_matches_the_oracle(coracle, tmp_path):
         scale = np.maximum(1.0, np.maximum(np.abs(ga_o).max(1), np.maximum(np.abs(gt_o).max(1), np.abs(gc_o))))
         err = np.maximum(np.abs(ga - ga_o).max(1), np.maximum(np.abs(gt - gt_o).max(1), np.abs(gc - gc_o))) / scale
         assert ok.mean() > 0.999 and err[ok].max() < 1e-6, (n, p, err[ok].max())
+
+
+# ------------------------------------------------------------------------------------------ S > 1 constraints
+def kkt_solve64(a, c, t, lo, hi, p, F, clipped_at, W, P):
+    """float64 solve of the KKT system on a GIVEN active set (free coordinates F, clipped ones at ``clipped_at``,
+    tight constraints W, relaxed constraints P): unknowns (u_F, mu_W).  Independent of the adjoint formulas."""
+    n = len(t)
+    u = clipped_at.copy()
+    nF, nW = int(F.sum()), len(W)
+    K = np.zeros((nF + nW, nF + nW))
+    rhs = np.zeros(nF + nW)
+    K[:nF, :nF] = np.eye(nF)
+    AW = a[W][:, F] if nW else np.zeros((0, nF))
+    K[:nF, nF:] = 0.5 * AW.T
+    K[nF:, :nF] = AW
+    rhs[:nF] = t[F] - 0.5 * p * a[P][:, F].sum(0) if len(P) else t[F]
+    if nW:
+        rhs[nF:] = -c[W] - a[W][:, ~F] @ clipped_at[~F]
+    sol = np.linalg.solve(K, rhs)
+    u[F] = sol[:nF]
+    r = np.zeros(len(c))
+    if len(P):
+        r[P] = c[P] + a[P] @ u
+    return u, r, sol[nF:]
+
+
+@pytest.mark.parametrize("n,S,penalty", [(7, 2, 50.0), (7, 3, 5000.0), (4, 2, 0.5), (7, 4, 2.0), (3, 2, 50.0)])
+def test_multi_adjoint_equals_finite_differences(coracle, n, S, penalty):
+    rng = np.random.default_rng(31 * n + S)
+    B = 300
+    f = lambda x: np.asarray(x, np.float32)
+    lo, hi = f(-rng.uniform(0.5, 2.0, n)), f(rng.uniform(0.5, 2.0, n))
+    a, c, t = f(rng.normal(size=(B, S, n))), f(rng.normal(scale=0.8, size=(B, S))), f(rng.uniform(-2.0, 2.0, size=(B, n)))
+    gu, gr = f(rng.normal(size=(B, n))), f(rng.normal(size=(B, S)))
+    ga, gc, gt, margin = coracle.qp_multi_backward(a, c, t, lo, hi, penalty, gu, gr, want_margin=True)
+    uo, ro = coracle.qp_multi(a, c, t, lo, hi, penalty, max_iter=5000, tol=1e-13)
+    lo64, hi64 = lo.astype(np.float64), hi.astype(np.float64)
+    eps, checked, seen = 1e-6, 0, {"tight": 0, "relaxed": 0, "two_tight": 0}
+    for b in range(B):
+        if margin[b] < 2e-3:
+            continue
+        a64, c64, t64 = a[b].astype(np.float64), c[b].astype(np.float64), t[b].astype(np.float64)
+        u64 = uo[b].astype(np.float64)
+        F = (u64 > lo64 + 1e-6) & (u64 < hi64 - 1e-6)
+        clipped_at = np.where(u64 <= lo64 + 1e-6, lo64, hi64)
+        g = c64 + a64 @ u64
+        P = [i for i in range(S) if ro[b, i] > 1e-5]
+        W = [i for i in range(S) if ro[b, i] <= 1e-5 and abs(g[i]) < 1e-5]
+        if len(W) > F.sum():
+            continue
+        u0, r0, mu0 = kkt_solve64(a64, c64, t64, lo64, hi64, min(penalty, 1e6), F, clipped_at, W, P)
+        assert np.abs(u0 - u64).max() < 1e-5 and np.all(mu0 > 0) and np.all(mu0 < min(penalty, 1e6))
+        seen["tight"] += len(W) >= 1
+        seen["two_tight"] += len(W) >= 2
+        seen["relaxed"] += len(P) >= 1
+
+        def loss(av, cv, tv):
+            u, r, _ = kkt_solve64(av, cv, tv, lo64, hi64, min(penalty, 1e6), F, clipped_at, W, P)
+            return float(gu[b].astype(np.float64) @ u + gr[b].astype(np.float64) @ r)
+        fd_a, fd_c, fd_t = np.zeros((S, n)), np.zeros(S), np.zeros(n)
+        for i in range(S):
+            d = np.zeros(S); d[i] = eps
+            fd_c[i] = (loss(a64, c64 + d, t64) - loss(a64, c64 - d, t64)) / (2 * eps)
+            for k in range(n):
+                d2 = np.zeros((S, n)); d2[i, k] = eps
+                fd_a[i, k] = (loss(a64 + d2, c64, t64) - loss(a64 - d2, c64, t64)) / (2 * eps)
+        for k in range(n):
+            d = np.zeros(n); d[k] = eps
+            fd_t[k] = (loss(a64, c64, t64 + d) - loss(a64, c64, t64 - d)) / (2 * eps)
+        scale = max(1.0, np.abs(fd_a).max(), np.abs(fd_c).max(), np.abs(fd_t).max())
+        assert np.abs(ga[b] - fd_a).max() < 3e-5 * scale, (b, ga[b], fd_a)
+        assert np.abs(gc[b] - fd_c).max() < 3e-5 * scale, (b, gc[b], fd_c)
+        assert np.abs(gt[b] - fd_t).max() < 3e-5 * scale, (b, gt[b], fd_t)
+        checked += 1
+    assert checked > 0.6 * B and seen["tight"] > 20
+    if penalty <= 2.0:
+        assert seen["relaxed"] > 20
+    if penalty >= 50.0 and n >= 4:
+        assert seen["two_tight"] > 5
+
+
+def test_multi_adjoint_reduces_to_single(coracle):
+    a, c, t, lo, hi, p = cases(7, 500, 8, 50.0)
+    rng = np.random.default_rng(2)
+    gu, gr = rng.normal(size=a.shape).astype(np.float32), rng.normal(size=len(c)).astype(np.float32)
+    ga1, gc1, gt1, m1 = coracle.qp_backward(a, c, t, lo, hi, p, gu, gr, want_margin=True)
+    gaS, gcS, gtS, mS = coracle.qp_multi_backward(a[:, None], c[:, None], t, lo, hi, p, gu, gr[:, None], want_margin=True)
+    ok = (m1 > 1e-4) & (mS > 1e-4)
+    assert ok.mean() > 0.99
+    assert np.abs(gaS[ok, 0] - ga1[ok]).max() < 1e-4 and np.abs(gcS[ok, 0] - gc1[ok]).max() < 1e-4
+    assert np.abs(gtS[ok] - gt1[ok]).max() < 1e-4
+
+
+def test_multi_device_code_built_for_the_host_matches_the_oracle(coracle, tmp_path):
+    """qp_solve_multi + qp_multi_adjoint (csrc/mlp_qp.cuh, __host__ __device__) compiled for the CPU vs the oracle adjoint
+    (which classifies the active set from the multipliers; the device code reads it off the solution)"""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "qp_multi_backward_host")
+    subprocess.check_call([nvcc, "-O2", "-w", "-o", exe, os.path.join(root, "tools", "experiments", "qp_multi_backward_host.cu")])
+    f = lambda x: np.ascontiguousarray(x, np.float32)
+    for n, S, p in [(7, 2, 50.0), (7, 4, 0.05), (4, 3, 5000.0), (8, 3, 1e9)]:
+        rng = np.random.default_rng(300 + n * S)
+        B = 5000
+        lo, hi = f(-rng.uniform(0.5, 2.0, n)), f(rng.uniform(0.5, 2.0, n))
+        a, c, ur = f(rng.normal(size=(B, S, n))), f(rng.normal(scale=0.8, size=(B, S))), f(rng.uniform(-2.0, 2.0, size=(B, n)))
+        gu, gr = f(rng.normal(size=(B, n))), f(rng.normal(size=(B, S)))
+        with open(tmp_path / "in", "wb") as fh:
+            for x in (a, c, ur, gu, gr, lo, hi):
+                fh.write(x.tobytes())
+        subprocess.check_call([exe, str(n), str(S), str(B), repr(p), str(tmp_path / "in"), str(tmp_path / "out")])
+        out = np.fromfile(tmp_path / "out", np.float32)
+        ga, gc, gt = (out[:B * S * n].reshape(B, S, n), out[B * S * n:B * S * n + B * S].reshape(B, S),
+                      out[B * S * n + B * S:].reshape(B, n))
+        ga_o, gc_o, gt_o, margin = coracle.qp_multi_backward(a, c, ur, lo, hi, p, gu, gr, want_margin=True)
+        scale = np.maximum(1.0, np.maximum(np.abs(ga_o).max((1, 2)), np.maximum(np.abs(gt_o).max(1), np.abs(gc_o).max(1))))
+        err = np.maximum(np.abs(ga - ga_o).max((1, 2)), np.maximum(np.abs(gt - gt_o).max(1), np.abs(gc - gc_o).max(1))) / scale
+        ok = margin > 1e-5
+        assert ok.mean() > 0.999 and err[ok].max() < 1e-5, (n, S, p, err[ok].max())

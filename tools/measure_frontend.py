@@ -49,6 +49,9 @@ def main():
     for S in (2, 4):
         a, c = t(rng.normal(size=(B, S, n))), t(rng.normal(scale=0.8, size=(B, S)))
         out.append(dict(op="qp_multi", rows=B, n=n, constraints=S, ms=timed(lambda: ops.qp_multi(a, c, ur, lo, hi, 5000.0, 100, 1e-9))))
+        grS = t(rng.normal(size=(B, S)))
+        out.append(dict(op="qp_multi_backward", rows=B, n=n, constraints=S,
+                        ms=timed(lambda: ops.qp_multi_backward(a, c, ur, lo, hi, 5000.0, 100, 1e-9, gu, grS))))
     w = W.config(3, scale=1 / 4)
     rid = ops.ROBOT_ID[w["robot"]]
     b8, s4 = ops.pack_scene(w["boxes"][:, :3], w["boxes"][:, 3:], w["spheres"], device=dev)
