@@ -59,6 +59,7 @@ SIGNATURES = {
     "cbfrrt_cbf_filter": (C.c_int, [_I, C.POINTER(CbfNet), _P, _L, C.POINTER(FilterParams), _P, _P, _P, _P, _P]),
     "cbfrrt_qp": (C.c_int, [_I, _P, _P, _P, _L, _P, _P, _F, _P, _P, _P]),
     "cbfrrt_qp_backward": (C.c_int, [_I, _P, _P, _P, _L, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
+    "cbfrrt_knn_workspace_bytes": (C.c_int64, [_L, _L, C.c_int32]),
     "cbfrrt_knn": (C.c_int, [_I, _P, _P, _L, _L, C.c_int32, _P, _P, _P, _P]),
     "cbfrrt_radius_mask": (C.c_int, [_I, _P, _P, _L, _L, _F, _P, _P]),
     "cbfrrt_qp_multi": (C.c_int, [_I, _I, _P, _P, _P, _L, _P, _P, _F, _I, _F, _P, _P, _P, _P]),

@@ -425,7 +425,7 @@ def knn(queries: Tensor, tree: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     M, n = queries.shape
     idx = torch.empty((M, k), dtype=torch.int32, device=queries.device)
     dist = torch.empty((M, k), dtype=torch.float32, device=queries.device)
-    ws = torch.empty(max(1, 2 * M), dtype=torch.int64, device=queries.device)
+    ws = torch.empty(int(lib.cbfrrt_knn_workspace_bytes(M, tree.shape[0], k)) // 8, dtype=torch.int64, device=queries.device)
     with torch.cuda.device(queries.device):
         check(lib.cbfrrt_knn(n, _ptr(queries), _ptr(tree), M, tree.shape[0], k, _ptr(idx), _ptr(dist), _ptr(ws), _stream()),
               "cbfrrt_knn")

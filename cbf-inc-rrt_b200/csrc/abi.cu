@@ -241,12 +241,33 @@ int cbfrrt_edge_validity_var(int robot, const cbfrrt_scene* scene, const float* 
                                        : launch_edges_var_magician(sc, q_from, q_to, E, off, n_points, thr_soft, thr_hard, valid, first_bad, st);
 }
 
+int64_t cbfrrt_knn_workspace_bytes(int64_t M, int64_t N_tree, int32_t k) {
+    if (M < 0 || N_tree < 0 || k < 1) return -1;
+    int64_t bytes = 16 * (M > 0 ? M : 1);
+    if (k > 1 && k <= knn::TOPK_MAXK && N_tree > 0)
+        bytes += 8 * M * ((N_tree + knn::TOPK_CHUNK - 1) / knn::TOPK_CHUNK) * (int64_t)k;
+    return bytes;
+}
+
 int cbfrrt_knn(int n, const float* queries, const float* tree, int64_t M, int64_t N_tree, int32_t k, int32_t* idx,
                float* dist, void* workspace, void* stream) {
     if (M < 0 || N_tree < 0 || k < 1 || !queries || !tree || !idx || !dist || !workspace) return CBFRRT_ERR_BAD_SHAPE;
     if (n < 1 || n > 8 || N_tree > 0x7fffffffll) return CBFRRT_ERR_UNSUPPORTED;
     if (M == 0) return CBFRRT_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (k > 1 && k <= knn::TOPK_MAXK && N_tree > 0 && M <= 65535) {   // two launches: per-chunk candidates, per-query merge
+        unsigned long long* cand = reinterpret_cast<unsigned long long*>(workspace) + 2 * M;
+        const long long n_chunks = (N_tree + knn::TOPK_CHUNK - 1) / knn::TOPK_CHUNK;
+        const dim3 grid((unsigned)n_chunks, (unsigned)M);
+        switch (n) {
+#define CBF_NN_CASE(NN) case NN: knn::topk_chunk_kernel<NN><<<grid, 256, 0, st>>>(queries, tree, N_tree, k, cand); break;
+            CBF_NN_CASE(1) CBF_NN_CASE(2) CBF_NN_CASE(3) CBF_NN_CASE(4) CBF_NN_CASE(5) CBF_NN_CASE(6) CBF_NN_CASE(7) CBF_NN_CASE(8)
+#undef CBF_NN_CASE
+        }
+        if (finish_launch()) return CBFRRT_ERR_CUDA;
+        knn::topk_merge_kernel<<<(unsigned)M, 1024, 0, st>>>(cand, n_chunks * k, k, idx, dist);
+        return finish_launch();
+    }
     unsigned long long* best = reinterpret_cast<unsigned long long*>(workspace);
     unsigned long long* lower = best + M;
     const dim3 grid((unsigned)((N_tree + knn::CHUNK - 1) / knn::CHUNK), (unsigned)((M + knn::QT - 1) / knn::QT));

@@ -233,8 +233,11 @@ int cbfrrt_edge_validity_var(int robot, const cbfrrt_scene *scene, const float *
  * tsa.global_explore (tsa.py:151-153) and BITStarPlanner.expand_vertex (bit_star.py:196-216: nodes within r).
  *   queries [M, n], tree [N_tree, n] (device, fp32, 1 <= n <= 8) -> idx [M, k] int32, dist [M, k] fp32: the k nearest
  *   rows in ascending (squared distance, row) order -- ties to the lowest row like np.argmin / a stable argsort;
- *   entries beyond N_tree are idx -1 / dist +inf.  workspace: 16 * M bytes of device memory.  k rounds of 2 launches.
+ *   entries beyond N_tree are idx -1 / dist +inf.  workspace: cbfrrt_knn_workspace_bytes(M, N_tree, k) bytes of device
+ *   memory (16 * M for k = 1).  k = 1: one reduction launch; 1 < k <= 1024 (and M <= 65535): two launches (per-chunk
+ *   shared-memory sort keeping k candidates, per-query merge); larger k: k rounds of the reduction.
  *   radius_mask: within [M, N_set] uint8 = (||q_m - s_j|| <= radius). */
+int64_t cbfrrt_knn_workspace_bytes(int64_t M, int64_t N_tree, int32_t k);
 int cbfrrt_knn(int n, const float *queries, const float *tree, int64_t M, int64_t N_tree, int32_t k, int32_t *idx,
                float *dist, void *workspace, void *stream);
 int cbfrrt_radius_mask(int n, const float *queries, const float *set, int64_t M, int64_t N_set, float radius,
