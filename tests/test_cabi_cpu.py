@@ -57,6 +57,16 @@ def test_argument_validation_happens_before_cuda():
     fp = _lib.FilterParams(p, 3, p, p, p, 0.1, 5000.0, None)
     assert lib.cbfrrt_cbf_filter(7, C.byref(net), p, 5, C.byref(fp), p, p, p, p, None) == -2   # goal_rows not in {1,B}
     assert lib.cbfrrt_qp(9, p, p, p, 1, p, p, 1.0, p, p, None) == -3
+    assert lib.cbfrrt_qp_backward(9, p, p, p, 1, p, p, 1.0, p, p, p, p, p, None) == -3
+    assert lib.cbfrrt_qp_backward(7, None, p, p, 1, p, p, 1.0, p, p, p, p, p, None) == -2
+    assert lib.cbfrrt_qp_backward(7, None, None, None, 0, p, p, 1.0, None, None, None, None, None, None) == 0
+    assert lib.cbfrrt_qp_multi_backward(7, 5, p, p, p, 1, p, p, 1.0, 10, 1e-9, p, p, p, p, p, None) == -3   # > 4 constraints
+    assert lib.cbfrrt_qp_multi_backward(7, 2, p, p, p, 1, p, p, 1.0, 0, 1e-9, p, p, p, p, p, None) == -2    # max_iter < 1
+    # knn workspace: 16 M bytes for k = 1, + 8 M ceil(N / 1024) k for the two-launch k-nearest path
+    assert lib.cbfrrt_knn_workspace_bytes(50, 100000, 1) == 800
+    assert lib.cbfrrt_knn_workspace_bytes(1, 100000, 50) == 16 + 8 * 98 * 50
+    assert lib.cbfrrt_knn_workspace_bytes(3, 40, 64) == 48 + 8 * 3 * 64
+    assert lib.cbfrrt_knn_workspace_bytes(2, 10, 5000) == 32 and lib.cbfrrt_knn_workspace_bytes(-1, 1, 1) == -1
     # B == 0 is a valid no-op everywhere
     assert lib.cbfrrt_fk(0, p, 7, 0, p, p, None) == 0
     assert lib.cbfrrt_collide(0, C.byref(sc), p, 7, 0, 0.02, 0.0, *([None] * 6), None) == 0

@@ -61,6 +61,30 @@ def main():
     K = torch.from_numpy((np.linalg.norm((qf - qt).cpu().numpy(), axis=1) / 0.03).astype(np.int64))
     ms = timed(lambda: ops.edge_validity_var(qf, qt, K, b8, s4, 1, ops.no_grid(dev), 0.02, 0.0, rid), iters=5)
     out.append(dict(op="edge_validity_var", edges=E, points=int(K.sum() + E), boxes=int(b8.shape[0]), ms=ms))
+    # data collection: EpisodicDataModule.sample_fixed and the noisy nominal rollouts on the batched ops
+    import random
+    import time
+    from cbfrrt.environment import ArmEnv
+    from cbfrrt.neural_cbf.systems import ArmMindis
+    from cbfrrt.neural_cbf.datamodules import EpisodicDataModule
+    np.random.seed(5), random.seed(0), torch.manual_seed(0)
+    env = ArmEnv(["panda"], config_file="", include_floor=True)
+    dyn = ArmMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.05, env=env, robot=env.robot_list[0])
+    up, lo_ = dyn.state_limits
+    dm = EpisodicDataModule(dyn, [(float(x), float(y)) for x, y in zip(lo_, up)], max_episode=1, trajectories_per_episode=16,
+                            trajectory_length=400, fixed_samples=200000, noise_level=0.1,
+                            quotas={"safe": 0.3, "unsafe": 0.3, "boundary": 0.2, "goal": 0.1})
+    dm.sample_fixed()                                   # warm-up
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    x, m = dm.sample_fixed()
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    out.append(dict(op="EpisodicDataModule.sample_fixed", robot="panda", boxes=int(env.obs_positions.shape[0]), rows=int(x.shape[0]),
+                    wall_ms=dt * 1e3, labelled_rows_per_s=x.shape[0] / dt, note="host wall clock incl. rejection sampling and the 4 masks"))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    xs, ms = dm.sample_trajectories(dyn.noisy_simulator)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    out.append(dict(op="EpisodicDataModule.sample_trajectories", trajectories=16, stored_states_per_trajectory=400, rows=int(xs.shape[0]),
+                    wall_ms=dt * 1e3, stored_states_per_s=xs.shape[0] / dt, note="host wall clock; one observe launch per stored step"))
     for r in out:
         print(json.dumps(r))
 
