@@ -275,3 +275,51 @@ def test_lightning_checkpoint_loads(stack, tmp_path):
     with pytest.raises(KeyError):
         NeuralMindisCBFController.load_from_checkpoint(str(tmp_path / "bad.ckpt"), dynamics_model=dyn,
                                                        scenarios=[{"m1": 5.76}], **KW)
+
+
+# ---------------------------------------------------------------------------------------------------- evaluation
+def test_planner_evaluation_over_a_problem_file(stack, tmp_path):
+    """eval_rrt_all.py:20-71 / eval_batchrrt_vanilla.py / eval_batchrrt_mindis_cbfsteer.py on a refined problem pickle
+    written by this package: per-problem protocol, result list with the reference's keys, summary, result pickle"""
+    from cbfrrt.motion_planning.evaluation import (generate_refined_test_cases, read_problem_stream, collect_problems,
+                                                   save_collected, eval_rrt_all, eval_batchrrt_mindis, summarize)
+    from cbfrrt.motion_planning.baseline import batch_RRT_plan
+    from cbfrrt.neural_cbf.controllers import NeuralMindisCBFController
+    env, dyn = stack()
+
+    def solver(env_, init_state, goal_state, dynamics_model):          # the filter of generate_problem_env.py:46-48
+        return batch_RRT_plan(env_, dynamics_model, init_state, goal_state, RRT_PARAM=20, T=200, model_eps=0.3,
+                              steer_type="line", batch=10, stop_when_success=True, rng=np.random.RandomState(0))
+
+    raw = str(tmp_path / "raw.pkl")
+    n = generate_refined_test_cases(dyn, lambda *a: {k: v for k, v in solver(*a).items() if k != "search_tree"}, raw,
+                                    problem_num=3, obstacle_num=4, seed=7, max_proposals=12)
+    assert n >= 1
+    refined = str(tmp_path / "magician_easy.pkl")
+    save_collected(refined, collect_problems(read_problem_stream(raw), 0.0, 1e9))
+    out = str(tmp_path / "time_magician_easy_23_20_20_0_100.pkl")
+    result, summary = eval_rrt_all("magician", "batchrrt_vanilla", refined, out_file=out, seed=23, device="cpu",
+                                   simulation_dt=1 / 120, controller_period=1 / 30, RRT_STEP=20, goal_biasing=0.3,
+                                   max_node=1500, start_idx=0, end_idx=100)
+    assert len(result) == n and summary["problems"] == n and 0.0 <= summary["success_rate"] <= 1.0
+    for sol in result:
+        assert set(sol) == {"success", "path", "edge_states", "nominal_path", "path_cost", "explored_nodes", "time_dict"}
+        assert sol["explored_nodes"] >= 1 and sol["time_dict"]["total_time"] > 0
+    assert summary["success_rate"] > 0                 # problems the line-steer planner solved once are solved again
+    import pickle
+    with open(out, "rb") as fh:
+        assert len(pickle.load(fh)) == n
+    # CBF steer with a caller-built controller (no checkpoint ships with the reference) and from a checkpoint directory
+    env2, dyn2 = stack(config_file=refined)
+    torch.manual_seed(1)
+    ctrl = NeuralMindisCBFController(dyn2, [{"name": 1}], None, None, **KW)
+    from cbfrrt.motion_planning.evaluation import get_test_cases
+    p, s, a, b = get_test_cases(refined, 0, 1)
+    kw = dict(simulation_dt=1 / 120, controller_period=1 / 30, RRT_STEP=20, goal_biasing=0.3, max_node=40, start_idx=0,
+              end_idx=1, cbf_alpha=0.1)
+    res = eval_batchrrt_mindis(3, env2, env2.robot_list[0], None, p, s, a, b, controller=ctrl, batch=5, **kw)
+    assert len(res) == 1 and res[0]["explored_nodes"] >= 5 and summarize(res)["problems"] == 1
+    os.makedirs(tmp_path / "ckpt")
+    torch.save({"state_dict": ctrl.state_dict()}, str(tmp_path / "ckpt" / "epoch=1.ckpt"))
+    res2 = eval_batchrrt_mindis(3, env2, env2.robot_list[0], str(tmp_path / "ckpt"), p, s, a, b, batch=5, **kw)
+    assert res2[0]["explored_nodes"] == res[0]["explored_nodes"] and res2[0]["success"] == res[0]["success"]

@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""End-to-end planning on the device ops, the reference's evaluation protocol (motion_planning/evaluation/
+generate_problem_env.py + eval_rrt_all.py): propose problems (8 boxes), keep those a line-steer batched RRT solves,
+write them in the reference's pickle formats, then evaluate the batched planners over the refined file.
+The CBF network is randomly initialised (no checkpoint ships with the reference): its success rate says nothing about
+a trained barrier; the timings per explored node are the point.  One JSON line per method."""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "cbf-inc-rrt_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--robot", default="panda")
+    ap.add_argument("--problems", type=int, default=8)
+    ap.add_argument("--obstacles", type=int, default=8)
+    ap.add_argument("--max-node", type=int, default=500)
+    ap.add_argument("--rrt-step", type=int, default=180)
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--budget-s", type=float, default=40.0, help="stop proposing problems after this many seconds")
+    a = ap.parse_args()
+    from cbfrrt.environment import ArmEnv
+    from cbfrrt.neural_cbf.systems import ArmMindis
+    from cbfrrt.neural_cbf.controllers import NeuralMindisCBFController
+    from cbfrrt.motion_planning.baseline import batch_RRT_plan
+    from cbfrrt.motion_planning.evaluation import (generate_refined_test_cases, read_problem_stream, collect_problems,
+                                                   save_collected, get_test_cases, eval_batchrrt_vanilla,
+                                                   eval_batchrrt_mindis, summarize)
+    np.random.seed(5)
+    env = ArmEnv([a.robot], config_file="", include_floor=True, device=a.device)
+    dyn = ArmMindis({"name": 1}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.05, env=env, robot=env.robot_list[0])
+    t_start = time.time()
+
+    def solver(env_, init_state, goal_state, dm):
+        if time.time() - t_start > a.budget_s:
+            return {"success": True, "time_dict": {"total_time": 1e-9}, "explored_nodes": 0, "path": [], "budget": True}
+        s = batch_RRT_plan(env_, dm, init_state, goal_state, RRT_PARAM=a.rrt_step, T=a.max_node, model_eps=0.2,
+                           steer_type="line", batch=10, stop_when_success=True)
+        return {k: v for k, v in s.items() if k != "search_tree"}
+
+    with tempfile.TemporaryDirectory() as d:
+        raw, refined = os.path.join(d, "raw.pkl"), os.path.join(d, f"{a.robot}_easy.pkl")
+        t0 = time.time()
+        n = generate_refined_test_cases(dyn, solver, raw, problem_num=a.problems, obstacle_num=a.obstacles, seed=1234,
+                                        max_proposals=4 * a.problems)
+        records = [r for r in read_problem_stream(raw) if not r.get("budget")]
+        print(json.dumps({"stage": "generate_refined_test_cases", "robot": a.robot, "obstacles": a.obstacles,
+                          "problems_kept": len(records), "wall_s": time.time() - t0}))
+        if not records:
+            return
+        save_collected(refined, collect_problems(records, 0.0, 1e9))
+        env2 = ArmEnv([a.robot], config_file=refined, include_floor=True, device=a.device)
+        pos, siz, starts, goals = get_test_cases(refined, 0, len(records))
+        kw = dict(simulation_dt=1 / 120, controller_period=1 / 30, RRT_STEP=a.rrt_step, goal_biasing=0.2,
+                  max_node=a.max_node, start_idx=0, end_idx=len(records), cbf_alpha=0.1)
+        res = eval_batchrrt_vanilla(23, env2, env2.robot_list[0], pos, siz, starts, goals, **kw)
+        s = summarize(res)
+        s.update(method="batchrrt_vanilla (line steer, batch 10)", ms_per_explored_node=1e3 * s["total_time"] / max(1, sum(r["explored_nodes"] for r in res)))
+        print(json.dumps(s))
+        dyn2 = ArmMindis({"name": 1}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.02, env=env2, robot=env2.robot_list[0])
+        torch.manual_seed(1)
+        ctrl = NeuralMindisCBFController(dyn2, [{"name": 1}], None, None, cbf_alpha=0.1, cbf_relaxation_penalty=500,
+                                         safe_level=0.01, unsafe_level=0.01, cbf_hidden_layers=2, cbf_hidden_size=48)
+        for batch in (1, 10, 50):
+            res = eval_batchrrt_mindis(23, env2, env2.robot_list[0], None, pos, siz, starts, goals, controller=ctrl,
+                                       batch=batch, **kw)
+            s = summarize(res)
+            s.update(method=f"batchrrt_mindis (fused CBF steer, batch {batch}, random-init network)",
+                     ms_per_explored_node=1e3 * s["total_time"] / max(1, sum(r["explored_nodes"] for r in res)))
+            print(json.dumps(s))
+
+
+if __name__ == "__main__":
+    main()
