@@ -115,6 +115,20 @@ def _steer_batch(dynamics_model, controller, steer_type, sample_states, current_
     return qf.cpu().numpy(), [bool(a) for a in alive.cpu().numpy()], edges
 
 
+def _goal_test(dynamics_model, states):
+    """dynamics_model.goal_mask (arm_dynamics.py:234-262: within 0.2 rad of the goal AND safe) for the new states of a
+    batch: the distance part is evaluated first, in the same float32 torch expression, and the safe_mask launch is made
+    only for the rows inside the goal ball -- none, for most expansions."""
+    dm = dynamics_model
+    x = torch.as_tensor(np.asarray(states), dtype=torch.float32).reshape(-1, dm.q_dims)
+    goal = torch.as_tensor(dm.goal_state[:dm.q_dims]).type_as(x)
+    near = (x[:, :dm.q_dims] - goal).norm(dim=1) <= 0.2
+    done = torch.zeros(x.shape[0], dtype=torch.bool)
+    if bool(near.any()):
+        done[near] = dm.safe_mask(x[near]).cpu()
+    return done.numpy()
+
+
 def global_explore(search_tree, dynamics_model, sample_states=None, steer_type="line", controller=None, batch=50,
                    RRT_PARAM=20, rng=None):
     """One batched RRT expansion (batch_tsa.py:99-189).  Yields, per expanded sample,
@@ -142,13 +156,14 @@ def global_explore(search_tree, dynamics_model, sample_states=None, steer_type="
     new_states, no_collisions = current, [True] * len(parents)
     for _ in range(RRT_PARAM // 20):
         new_states, no_collisions, edges = _steer_batch(dm, controller, steer_type, sample_states, current, 20)
-        done = dm.goal_mask(torch.as_tensor(new_states, dtype=torch.float32)).cpu().numpy()
+        done = _goal_test(dm, new_states)
         for i in range(len(parents)):
             parents[i] = insert_new_state(search_tree, new_states[i], sample_states[i], edges[i], parents[i],
                                           no_collisions[i], bool(done[i]), expanded_by_rrt=True)
         current = new_states
     t2 = time.time()
-    done = dm.goal_mask(torch.as_tensor(new_states, dtype=torch.float32)).cpu().numpy()
+    if RRT_PARAM // 20 == 0:
+        done = _goal_test(dm, new_states)    # (otherwise: the goal test of the last segment, same states)
     for i in range(len(parents)):
         t_dict = {"explore_1": (t1 - t0) / len(parents), "total_steer": (t2 - t1) / len(parents),
                   "total_explore": (time.time() - t0) / len(parents)}

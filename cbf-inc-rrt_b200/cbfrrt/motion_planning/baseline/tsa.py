@@ -77,7 +77,7 @@ def _rollout(controller, dm, q0, steps, stuck=(0, 10, 0.1), want_traj=False, kee
     ctrl_every = int(dm.controller_dt // dm.dt)
     return ops.rollout(q0, dm.goal_tensor(dm.device), int(steps), ctrl_every, float(dm.dt), int(stuck[0]),
                        int(stuck[1]), float(stuck[2]), bool(want_traj), bool(keep_going), b, s, fl, gr, controller._weights(),
-                       dm.K.to(dm.device, torch.float32), lo, hi, float(controller.clf_lambda),
+                       dm.K_on(dm.device), lo, hi, float(controller.clf_lambda),
                        float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard),
                        dm.robot.robot_id, controller.h_hidden_size, controller.h_hidden_layers)
 

@@ -64,7 +64,7 @@ class NeuralMindisCBFController(NeuralObsCBFController):
         if d.shape[1] != 2 * dm.n_dims + 1:
             raise ValueError(f"datax must be (bs, {2 * dm.n_dims + 1}) = [q | o | do/dq]")
         lo, hi = self._limits()
-        K = dm.K.to(dev, torch.float32)
+        K = dm.K_on(dev)
         pen = self.clf_relaxation_penalty if relaxation_penalty is None else relaxation_penalty
         uref = torch.empty(0, device=dev) if u_ref is None else u_ref.to(dev, torch.float32)
         return ops.cbf_filter(d, dm.goal_tensor(dev), self._weights(), K, lo, hi, float(self.clf_lambda), float(pen),

@@ -111,6 +111,15 @@ class ControlAffineSystem(ABC):
     def u_eq(self):
         return torch.zeros((1, self.n_controls))
 
+    def K_on(self, device) -> torch.Tensor:
+        """float32 copy of the LQR gain on ``device``, uploaded once per gain (the planners call the filter thousands of
+        times per problem with the same K)."""
+        key = (id(self.K), self.K._version, str(device))
+        if getattr(self, "_K_dev_key", None) != key:
+            self._K_dev = self.K.to(device, torch.float32).contiguous()
+            self._K_dev_key = key
+        return self._K_dev
+
     # ---- samplers (control_affine_system.py:291-354)
     def sample_state_space(self, num_samples: int) -> torch.Tensor:
         x_max, x_min = self.state_limits
