@@ -93,6 +93,45 @@ class CLFController(Controller):
                      float(relaxation_penalty))
         return u.to(x.device).type_as(x), r.reshape(-1, 1).to(x.device).type_as(x)
 
+    # ---- the reference's other back-ends, same signatures and return conventions, all on the exact batched solver
+    def _solve_CLF_QP_cvxpylayers(self, x, u_ref, V, Lf_V, Lg_V, relaxation_penalty: float):
+        """clf_controller.py:354-404 (differentiable layer; penalty clamped to 1e6, :380)"""
+        return self._solve_CLF_QP_exact(x, u_ref, V, Lf_V, Lg_V, relaxation_penalty,
+                                        requires_grad=torch.is_grad_enabled() and any(
+                                            t.requires_grad for t in (u_ref, V, Lf_V, Lg_V)))
+
+    @torch.no_grad()
+    def _solve_CLF_QP_gurobi(self, x, u_ref, V, Lf_V, Lg_V, relaxation_penalty: float):
+        """clf_controller.py:226-352: the same relaxed QP per row.  Rows with a NaN / inf in x, Lf_V or Lg_V are skipped
+        (u = 0, r = 0) like the reference's (:281-290).  Difference: the penalty is clamped at 1e6 by the library, so a
+        hard constraint (penalty = inf) that is infeasible inside the control box comes back relaxed (r > 0) where
+        Gurobi reports infeasibility (r = NaN, :325-331)."""
+        bad = ~(torch.isfinite(x).all(dim=1) & torch.isfinite(Lg_V.reshape(x.shape[0], -1)).all(dim=1)
+                & torch.isfinite(Lf_V.reshape(x.shape[0], -1)).all(dim=1))
+        clean = lambda t: torch.where(bad.reshape(-1, *[1] * (t.dim() - 1)), torch.zeros_like(t), t)
+        u, r = self._solve_CLF_QP_exact(x, clean(u_ref), clean(V), clean(Lf_V), clean(Lg_V), min(relaxation_penalty, 1e6))
+        u[bad] = 0.0
+        r[bad] = 0.0
+        return u, r
+
+    @torch.no_grad()
+    def _solve_CLF_QP_qpsolver(self, x, u_ref, V, Lf_V, Lg_V, relaxation_penalty: float, use_constraint: bool = False):
+        """clf_controller.py:405-459 (OSQP through qpsolvers, one scenario).  ``use_constraint=False``: the penalty
+        form min ||u - u_ref||^2 + p Lg.u over the box, i.e. u = clip(u_ref - p Lg / 2) (:431-435), r = 0.
+        ``use_constraint=True``: the hard-constrained QP (:423-429); when any row of the batch is infeasible inside the
+        box the reference's solver fails on the stacked problem and the whole batch falls back to the penalty form
+        (:449-452) -- reproduced here from the relaxation the exact solver reports at p = 1e6."""
+        assert self.n_scenarios == 1
+        upper, lower = self.dynamics_model.control_limits
+        if use_constraint:
+            u, r = self._solve_CLF_QP_exact(x, u_ref, V, Lf_V, Lg_V, 1e6)
+            scale = 1.0 + Lf_V.reshape(x.shape[0], -1).abs().sum(1) + Lg_V.reshape(x.shape[0], -1).abs().sum(1)
+            if bool((r.reshape(-1) <= 1e-6 * scale.to(r.device)).all()):
+                return u, torch.zeros_like(V)
+        u = u_ref - 0.5 * relaxation_penalty * Lg_V[:, 0, :].type_as(u_ref)
+        u = torch.max(torch.min(u, upper.type_as(u).to(u.device)), lower.type_as(u).to(u.device))
+        return u.type_as(x), torch.zeros_like(V)
+
     def solve_CLF_QP(self, x, relaxation_penalty: Optional[float] = None, u_ref: Optional[torch.Tensor] = None,
                      requires_grad: bool = False, strict_solution: bool = False) -> Tuple[tuple, dict]:
         """clf_controller.py:461-528 -> ((u, r), t_dict)"""

@@ -295,3 +295,48 @@ def test_multi_device_code_built_for_the_host_matches_the_oracle(coracle, tmp_pa
         err = np.maximum(np.abs(ga - ga_o).max((1, 2)), np.maximum(np.abs(gt - gt_o).max(1), np.abs(gc - gc_o).max(1))) / scale
         ok = margin > 1e-5
         assert ok.mean() > 0.999 and err[ok].max() < 1e-5, (n, S, p, err[ok].max())
+
+
+def test_alternative_backends_keep_the_reference_signatures(monkeypatch, coracle):
+    """_solve_CLF_QP_cvxpylayers / _gurobi / _qpsolver (clf_controller.py:226-459): same arguments, same (u, r) shapes,
+    the documented semantics of each, all on the exact solver"""
+    fake_ops.install(monkeypatch)
+    from cbfrrt.environment import ArmEnv
+    from cbfrrt.neural_cbf.systems import ArmMindis
+    from cbfrrt.neural_cbf.controllers import NeuralMindisCBFController
+    env = ArmEnv(["magician"], config_file="", include_floor=True, device="cpu")
+    dyn = ArmMindis({"m1": 5.76}, dt=1 / 120, controller_dt=1 / 30, dis_threshold=0.02, env=env, robot=env.robot_list[0])
+    torch.manual_seed(1)
+    ctrl = NeuralMindisCBFController(dyn, [{"m1": 5.76}], None, None, cbf_alpha=0.1, cbf_relaxation_penalty=5000.0,
+                                     safe_level=0.1, unsafe_level=0.1, cbf_hidden_layers=2, cbf_hidden_size=48)
+    with torch.no_grad():
+        ctrl.h_nn.output_linear.bias += 30.0
+    x = dyn.sample_safe(24)
+    V, Lf, Lg, _ = ctrl.V_with_lie_derivatives(x)
+    u_ref = dyn.u_nominal(x)
+    (u0, r0), _ = ctrl.solve_CLF_QP(x)
+    u1, r1 = ctrl._solve_CLF_QP_cvxpylayers(x, u_ref, V, Lf, Lg, 5000.0)
+    assert u1.shape == (24, 4) and r1.shape == (24, 1) and torch.allclose(u1, u0, atol=2e-5) and torch.allclose(r1, r0, atol=2e-4)
+    u2, r2 = ctrl._solve_CLF_QP_gurobi(x, u_ref, V, Lf, Lg, 5000.0)
+    assert torch.allclose(u2, u1, atol=1e-6) and torch.allclose(r2, r1, atol=1e-6)
+    xb = x.clone(); xb[3, 0] = float("nan")
+    Lgb = Lg.clone(); Lgb[5, 0, 1] = float("inf")
+    u3, r3 = ctrl._solve_CLF_QP_gurobi(xb, u_ref, V, Lf, Lgb, 5000.0)
+    assert (u3[3] == 0).all() and (u3[5] == 0).all() and r3[3] == 0 and torch.allclose(u3[6:], u1[6:], atol=1e-6)
+    # penalty form of the OSQP path: u = clip(u_ref - p Lg / 2), r = 0
+    up, lo = dyn.control_limits
+    u4, r4 = ctrl._solve_CLF_QP_qpsolver(x, u_ref, V, Lf, Lg, 0.3)
+    exp = torch.max(torch.min(u_ref - 0.15 * Lg[:, 0, :], up), lo)
+    assert torch.allclose(u4, exp, atol=1e-6) and r4.shape == V.shape and (r4 == 0).all()
+    # hard-constrained form: feasible batch -> the constrained optimum (== relaxed QP with a huge penalty, r = 0)
+    u5, r5 = ctrl._solve_CLF_QP_qpsolver(x, u_ref, V, Lf, Lg, 0.3, use_constraint=True)
+    ub, rb = ctrl._solve_CLF_QP_exact(x, u_ref, V, Lf, Lg, 1e6)
+    if float(rb.max()) <= 1e-6:
+        assert torch.allclose(u5, ub, atol=1e-6)
+        g = (Lf[:, 0, 0] + (Lg[:, 0, :] * u5).sum(1) + 0.1 * V.reshape(-1))
+        assert float(g.max()) <= 1e-4
+    else:                         # an infeasible row: whole batch falls back to the penalty form (:449-452)
+        assert torch.allclose(u5, exp, atol=1e-6)
+    # an infeasible hard constraint forces the fallback
+    u6, _ = ctrl._solve_CLF_QP_qpsolver(x, u_ref, V + 1e4, Lf, Lg, 0.3, use_constraint=True)
+    assert torch.allclose(u6, exp, atol=1e-6)
