@@ -115,6 +115,27 @@ def cpu_port_run(w, rows, threads):
     return rows / (time.perf_counter() - t0)
 
 
+def cpu_sequential_run(w, rows=2048):
+    """The reference's loop SHAPE (SURVEY 8d "reference-faithful sequential mode"): one call per state, single thread --
+    arm_dynamics.py:199-201 / :274-276 loop over the batch in Python and clf_controller solves one QP per row.  Here each
+    iteration is one oracle call on a batch of 1 (exact QP), so this prices the per-state call overhead of that structure
+    around a C core, not pybullet / SCS themselves (absent here)."""
+    from oracle import c_oracle
+    c_oracle.set_threads(1)
+    rows = int(min(rows, w["q"].shape[0]))
+    q = w["q"]
+    args_ = (w["boxes"], w["spheres"], True, w["weights"], w["hidden"], w["layers"], w["goal"], w["K"], w["u_lo"], w["u_hi"],
+             w["thr_soft"], w["thr_hard"], w["lam"], w["penalty"])
+    for i in range(min(64, rows)):
+        c_oracle.safety_filter(w["robot"], q[i:i + 1], *args_)
+    t0 = time.perf_counter()
+    for i in range(rows):
+        c_oracle.safety_filter(w["robot"], q[i:i + 1], *args_)
+    dt = time.perf_counter() - t0
+    return {"value": rows / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{rows} states of {w['name']}, one call per state (per-state Python loop around the C port)"}
+
+
 def reference_arm(args, w):
     """--impl reference: the CPU port of the reference's path (oracle/cbfrrt_oracle.c, all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -138,7 +159,8 @@ def reference_arm(args, w):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "note": "reference cannot run here (pybullet/cvxpylayers/SCS absent); "
                    "this is the repo's C port of its CPU path (oracle/cbfrrt_oracle.c) on all host threads"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "sequential": cpu_sequential_run(w)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -360,7 +382,8 @@ def main():
         cpu_port_run(w, 4096, threads)
         vals = [cpu_port_run(w, rows, threads) for _ in range(3)]
         cpu = {"value": float(np.median(vals)), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{rows} of {B} states of {w['name']}, median of 3 (oracle/cbfrrt_oracle.c, pthreads)"}
+               "sample": f"{rows} of {B} states of {w['name']}, median of 3 (oracle/cbfrrt_oracle.c, pthreads)",
+               "sequential": cpu_sequential_run(w)}
 
     if rank == 0:
         print(json.dumps({
