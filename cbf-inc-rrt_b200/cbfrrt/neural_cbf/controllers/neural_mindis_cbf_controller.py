@@ -163,7 +163,9 @@ class NeuralMindisCBFController(NeuralObsCBFController):
                           weights_only=False)
         if "state_dict" not in ckpt:
             raise KeyError(f"{checkpoint_path}: not a Lightning checkpoint (no 'state_dict')")
-        hparams = {k: v for k, v in dict(ckpt.get("hyper_parameters", {})).items()
+        stored = ckpt.get("hyper_parameters", {})
+        stored = dict(stored) if isinstance(stored, dict) else dict(vars(stored))     # Lightning dict or a raw Namespace
+        hparams = {k: v for k, v in stored.items()
                    if k in ("cbf_alpha", "cbf_relaxation_penalty", "safe_level", "unsafe_level", "cbf_hidden_layers",
                             "cbf_hidden_size", "use_neural_actor", "loss_config", "learn_shape_epochs")}
         hparams.update(kwargs)
