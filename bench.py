@@ -1,62 +1,89 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the CBF-INC-RRT hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg1|cfg0|cfg2|cfg3|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg4|cfg1|cfg0]
 
 A "step" = one pass of the fused hot path (FK -> link/obstacle distances + masks -> min-distance observation and
-gradient -> barrier MLP + state-Jacobian -> CBF-QP) over one batch of synthetic states.  Default workload =
-BASELINE.json configs[1]: Magician 4-DoF, 16 box obstacles + floor, 2^20 sampled states per GPU (weak scaling;
-rank r takes the seeded sample r).  Prints ONE JSON line (rank 0).
+gradient -> barrier MLP + state-Jacobian -> CBF-QP) over one batch of synthetic states.
 
-  value        states/s with inputs resident in HBM (CUDA events around the launches of the timed steps, L2 flushed
-               between steps, max over ranks); for N > 1 the step includes the NCCL all-gather of the validity
-               masks and filtered controls (block-cyclic, overlapped on a second stream).
-  e2e          the same metric through the host-buffer C-ABI call (cbfrrt_safety_filter_host): pinned host
-               buffers, H2D of q and D2H of (safe, u) inside the timed region.
-  roofline     the path is FP32 CUDA-core bound: achieved algorithmic TFLOP/s of the fused kernel
-               against the FMA rate measured in this run by cbfrrt_fma_probe; the HBM fraction (algorithmic bytes
-               against MEASURED_PEAKS.json) is reported beside it.
-  cpu_baseline the oracle port of the reference's CPU path on this box's host cores, bounded sample.
-  --impl reference   times only that CPU port (the reference itself cannot run: pybullet / SCS are absent).
+Default workload = BASELINE.json configs[4] (the config the metric and the north-star targets are quoted on): Franka
+Panda, 256 box obstacles + floor, 2^26 = 64 M sampled states, outputs `valid` (u8) and the filtered control `u`
+(f32 x 7) per state.  STRONG scaling: the 64 M states are split over the N ranks (contiguous blocks, sampled on the
+device by the counter-based sampler, so the result does not depend on N); for N > 1 every rank ends the step with the
+full [64 M] mask and [64 M, 7] controls (exchange fused into the kernel epilogue over NVLink, or NCCL all-gather).
+`--workload cfg1` (Magician, 16 boxes, 2^20 states per GPU, weak scaling, all outputs) and `cfg0` are kept.
+Prints ONE JSON line (rank 0).
+
+  value        states/s with inputs resident in HBM (CUDA events around the launches of the timed steps, max over ranks)
+  e2e          the same metric through the host-buffer C-ABI call (cbfrrt_safety_filter_host): pinned host buffers,
+               H2D of q and D2H of (valid, u) inside the timed region
+  roofline     per pipe, never mixed: FP32 CUDA-core work against the FMA rate measured in this run
+               (cbfrrt_fma_probe), tcgen05 work against a dense TF32 matmul measured in this run, HBM bytes against
+               MEASURED_PEAKS.json; `frac` is the largest of the three and `bound` names it
+  cpu_baseline the oracle port of the reference's CPU path on this box's host cores, bounded sample
+  --impl reference   times only that CPU port (the reference itself cannot run: pybullet / SCS are absent); it does not
+               load the CUDA library
 """
 import argparse
+import importlib
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "cbf-inc-rrt_b200")):
+PKG = os.path.join(ROOT, "cbf-inc-rrt_b200")
+for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
 METRIC = "collision-checked + CBF-QP-filtered states/sec (fused safety filter)"
 UNIT = "states/s"
+CFG = {"cfg0": 0, "cfg1": 1, "cfg4": 4}
+TARGETS_8GPU = {"collision_checked_franka_configs_per_s": 1e9, "cbf_qp_filtered_control_steps_per_s": 1e8}
 
 
-# ----------------------------------------------------------------------------- algorithmic cost model (DESIGN.md)
-def algorithmic_cost(robot, n_boxes, n_spheres, floor, outputs="all"):
-    """SURVEY.md 8d formulas -> (flops per state, HBM bytes per state) for the fused q -> (masks, datax, h, J, u, r)."""
-    from cbfrrt._robot_tables import ROBOT_MODELS
-    m = ROBOT_MODELS[robot]
+def load_workloads(native: bool):
+    """cbfrrt.workloads.  native=False (reference arm): through a stub parent package, so that neither
+    cbfrrt/__init__.py nor libcbfrrt.so is loaded -- the module itself is numpy / torch-CPU only."""
+    if native:
+        from cbfrrt import workloads
+        return workloads
+    stub = types.ModuleType("cbfrrt")
+    stub.__path__ = [os.path.join(PKG, "cbfrrt")]
+    sys.modules["cbfrrt"] = stub
+    return importlib.import_module("cbfrrt.workloads")
+
+
+# ----------------------------------------------------------------------------- algorithmic cost model (DESIGN.md 4.5)
+def algorithmic_cost(W, robot, n_boxes, n_spheres, floor, outputs, pairs_per_state=None, lookups_per_state=0):
+    """-> dict of algorithmic work per state, one entry per pipe.
+
+    fp32: FK 78/frame + sphere centres 15/sphere + pair evaluations 22/box 10/sphere 3/floor + self pairs 10 + gradient
+    12 n + QP 2n(3n+4)  (SURVEY.md 8d).  `pairs_per_state` = exact pair evaluations the broad phase leaves (measured on
+    the device for this scene); None = brute force, every link sphere against every obstacle.  `lookups_per_state` =
+    broad-phase look-ups (index arithmetic ~12 flop each).  The barrier network (forward + reverse mode) is counted on
+    the tensor pipe when the tcgen05 kernels run it: executed flops = 3 x algorithmic (TF32 3-term split).
+    hbm: compulsory bytes: q in, outputs out; scene / weights / grid are read once per CTA."""
+    m = W.ROBOT_MODELS[robot]
     n, F, S = m["n"], m["n_links"], len(m["spheres"])
-    fk = 78 * F
-    centres = 15 * S
-    pairs = S * (22 * n_boxes + 10 * n_spheres + 3 * int(floor))
-    self_pairs = 10 * len(m["self_sphere_pairs"])
-    grad = 12 * n
-    mlp = 2 * 2 * ((n + 1) * 48 + 2 * 48 * 48 + 48)   # forward + reverse mode
+    brute = S * (22 * n_boxes + 10 * n_spheres)
+    pair_flops = brute if pairs_per_state is None else 22.0 * pairs_per_state
+    geom = 78 * F + 15 * S + pair_flops + 3 * S * int(floor) + 12 * lookups_per_state \
+        + 10 * len(m["self_sphere_pairs"]) + 12 * n
     qp = 2 * n * (3 * n + 4)
-    flops = fk + centres + pairs + self_pairs + grad + mlp + qp
+    mlp = 2 * 2 * ((n + 1) * 48 + 2 * 48 * 48 + 48)   # forward + reverse mode
     if outputs == "all":
         byts = 4 * n + 1 + 1 + 4 * (2 * n + 1) + 4 + 4 * n + 4 * n + 4
     else:  # valid + u
         byts = 4 * n + 1 + 4 * n
-    return flops, byts
+    return {"fp32": geom + qp, "fp32_brute_force": 78 * F + 15 * S + brute + 3 * S * int(floor)
+            + 10 * len(m["self_sphere_pairs"]) + 12 * n + qp, "mlp": mlp, "bytes": byts}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -105,25 +132,33 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU port (oracle) leg
-def cpu_port_run(w, rows, threads):
+def host_states(w, rows):
+    """the first `rows` states of the workload on the host (config 5: the oracle's copy of the counter-based sampler,
+    bit-identical to the device sampler)"""
+    if w["q"] is not None:
+        return w["q"][:rows]
+    from oracle import c_oracle
+    return c_oracle.sample_states(w["robot"], w["sample_seed"], 0, rows)
+
+
+def cpu_port_run(w, q, threads):
     from oracle import c_oracle
     c_oracle.set_threads(threads)
-    q = w["q"][:rows]
     t0 = time.perf_counter()
     c_oracle.safety_filter(w["robot"], q, w["boxes"], w["spheres"], True, w["weights"], w["hidden"], w["layers"],
                            w["goal"], w["K"], w["u_lo"], w["u_hi"], w["thr_soft"], w["thr_hard"], w["lam"], w["penalty"])
-    return rows / (time.perf_counter() - t0)
+    return q.shape[0] / (time.perf_counter() - t0)
 
 
-def cpu_sequential_run(w, rows=2048):
+def cpu_sequential_run(w, rows=1024):
     """The reference's loop SHAPE (SURVEY 8d "reference-faithful sequential mode"): one call per state, single thread --
     arm_dynamics.py:199-201 / :274-276 loop over the batch in Python and clf_controller solves one QP per row.  Here each
     iteration is one oracle call on a batch of 1 (exact QP), so this prices the per-state call overhead of that structure
     around a C core, not pybullet / SCS themselves (absent here)."""
     from oracle import c_oracle
     c_oracle.set_threads(1)
-    rows = int(min(rows, w["q"].shape[0]))
-    q = w["q"]
+    q = host_states(w, rows)
+    rows = q.shape[0]
     args_ = (w["boxes"], w["spheres"], True, w["weights"], w["hidden"], w["layers"], w["goal"], w["K"], w["u_lo"], w["u_hi"],
              w["thr_soft"], w["thr_hard"], w["lam"], w["penalty"])
     for i in range(min(64, rows)):
@@ -136,31 +171,52 @@ def cpu_sequential_run(w, rows=2048):
             "sample": f"{rows} states of {w['name']}, one call per state (per-state Python loop around the C port)"}
 
 
-def reference_arm(args, w):
-    """--impl reference: the CPU port of the reference's path (oracle/cbfrrt_oracle.c, all host threads)."""
+def cpu_sample_rows(w):
+    """bounded CPU sample: about 1-2 s of work per pass on a 16-thread host (the 256-box brute-force sweep of the oracle
+    costs ~200 kflop per state)"""
+    total = w["q"].shape[0] if w["q"] is not None else w["n_states"]
+    return int(min(total, 1 << 18 if w["boxes"].shape[0] <= 32 else 1 << 16))
+
+
+def workload_config(w, extra=None):
+    total = w["q"].shape[0] if w["q"] is not None else w["n_states"]
+    c = {"workload": w["name"], "robot": w["robot"], "states": int(total), "boxes": int(w["boxes"].shape[0]),
+         "spheres": int(w["spheres"].shape[0]), "floor": True, "obstacles": w["obstacles"], "mlp": "(n+1)-48-48-48-1"}
+    c.update(extra or {})
+    return c
+
+
+def reference_arm(args):
+    """--impl reference: the CPU port of the reference's path (oracle/cbfrrt_oracle.c, all host threads).  The CUDA
+    library is not loaded by this arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    W = load_workloads(native=False)
+    w = W.config(CFG[args.workload], scale=args.scale)
     threads = os.cpu_count() or 1
-    rows = min(w["q"].shape[0], 1 << 18)
-    cpu_port_run(w, min(rows, 8192), threads)  # warm caches / page in the library
-    vals = []
+    q = host_states(w, cpu_sample_rows(w))
+    rows = q.shape[0]
+    cpu_port_run(w, q[:min(rows, 4096)], threads)  # page in the library
     for _ in range(max(1, args.warmup)):
-        cpu_port_run(w, rows, threads)
+        cpu_port_run(w, q, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        vals.append(cpu_port_run(w, rows, threads))
+        cpu_port_run(w, q, threads)
     dt = time.perf_counter() - t0
     v = rows * args.steps / dt
-    sample = f"{rows} of {w['q'].shape[0]} states of {w['name']} per step"
+    total = w["q"].shape[0] if w["q"] is not None else w["n_states"]
+    sample = f"the first {rows} of {total} states of {w['name']} per step"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["name"], "note": "reference cannot run here (pybullet/cvxpylayers/SCS absent); "
-                   "this is the repo's C port of its CPU path (oracle/cbfrrt_oracle.c) on all host threads"},
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong" if CFG[args.workload] == 4 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(w, {"outputs": "valid+u" if CFG[args.workload] == 4 else "all",
+                                       "note": "reference cannot run here (pybullet/cvxpylayers/SCS absent); this is the repo's "
+                                               "C port of its CPU path (oracle/cbfrrt_oracle.c) on all host threads; per-state "
+                                               "rate on a bounded sample"}),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "sequential": cpu_sequential_run(w)},
+                         "sequential": cpu_sequential_run(w, 256 if w["boxes"].shape[0] > 32 else 1024)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -187,6 +243,60 @@ def bind_to_gpu_numa_node(gpu_index):
     return None
 
 
+def timed_events(torch, fn, iters, flush):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+        flush.zero_()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in ev]
+
+
+def other_configs(torch, ops, W, dev, flush, iters=3):
+    """device-resident timings of the other BASELINE configs (N = 1 only; extra keys, not the headline)"""
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
+    out = {}
+    for idx in (1, 2, 3):
+        w = W.config(idx)
+        rid, n = ops.ROBOT_ID[w["robot"]], w["n"]
+        b8, s4 = ops.pack_scene(w["boxes"][:, :3], w["boxes"][:, 3:], w["spheres"], device=dev)
+        gr = ops.build_grid(b8, s4)
+        net, K, lo, hi, goal = ops.pack_weights(w["state_dict"], n, 48, 2, device=dev), t(w["K"]), t(w["u_lo"]), t(w["u_hi"]), t(w["goal"])
+        res = {"obstacles": w["obstacles"]}
+        if idx == 1:
+            q = t(w["q"])
+            fn = lambda: ops.safety_filter(q, goal, b8, s4, 1, gr, net, K, lo, hi, w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
+            fn(); fn()
+            ms = float(np.median(timed_events(torch, fn, iters, flush)))
+            res.update(ms=ms, states_per_s=q.shape[0] / (ms * 1e-3), outputs="all")
+        elif idx == 2:
+            qf, qt = t(w["q"]), t(w["q_to"])
+            fn = lambda: ops.edge_validity(qf, qt, w["n_interp"], b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid)
+            fn()
+            ms = float(np.median(timed_events(torch, fn, iters, flush)))
+            v = fn()[0]
+            res.update(ms=ms, edges_per_s=qf.shape[0] / (ms * 1e-3), configs_per_s=qf.shape[0] * (w["n_interp"] + 1) / (ms * 1e-3),
+                       valid_fraction=float(v.float().mean().item()))
+        else:
+            q0 = t(w["q"])
+            T = q0.shape[0]
+            safe = ops.masks(q0, b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid)[0].bool()   # "filtered to safe" (SURVEY 8d)
+            keep = q0[safe]
+            q0 = keep.repeat((T + keep.shape[0] - 1) // keep.shape[0], 1)[:T].contiguous()
+            fn = lambda: ops.rollout(q0, goal, w["steps"], w["ctrl_every"], w["dt"], 0, 10, 0.1, False, True, b8, s4, 1, gr, net, K, lo, hi,
+                                     w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
+            fn()
+            ms = float(np.median(timed_events(torch, fn, iters, flush)))
+            res.update(ms=ms, sim_steps_per_s=T * w["steps"] / (ms * 1e-3), qp_steps_per_s=T * w["steps"] / w["ctrl_every"] / (ms * 1e-3),
+                       safe_start_fraction=float(safe.float().mean().item()))
+        out[w["name"]] = res
+        del w
+        torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -194,25 +304,26 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cbfrrt")
-    ap.add_argument("--workload", default="cfg1")
+    ap.add_argument("--workload", default="cfg4", choices=sorted(CFG))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
-    from cbfrrt import workloads as W
-    cfg_idx = {"cfg0": 0, "cfg1": 1, "cfg4": 4}[args.workload]
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    cfg_idx = CFG[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    if args.impl == "reference":
-        reference_arm(args, W.config(cfg_idx, scale=args.scale))
-        return
-
     import torch
     import torch.distributed as dist
+    W = load_workloads(native=True)
     from cbfrrt import ops
     from cbfrrt.sharded import ShardedSweep
 
@@ -224,13 +335,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     w = W.config(cfg_idx, scale=args.scale)
     robot, rid, n = w["robot"], ops.ROBOT_ID[w["robot"]], w["n"]
-    if w["q"] is None:   # cfg4: sampled on the device, shard-invariant
-        B = w["n_states"] // world if cfg_idx == 4 else w["n_states"]
+    strong = cfg_idx == 4
+    if strong:   # config 5: G states in total, split over the ranks; sampled on the device, shard-invariant
+        G = (w["n_states"] // (world * 128)) * world * 128
+        B = G // world
         q = ops.sample_states(B, w["sample_seed"], rank * B, rid, device=dev)
-    else:
+        outputs = "valid+u"
+    else:        # weak scaling: every rank its own seeded sample of the config's size
         B = w["q"].shape[0]
-        q_np = w["q"] if rank == 0 else W.sample_states(robot, B, 1000 + rank)   # weak scaling: own sample per rank
+        G = B * world
+        q_np = w["q"] if rank == 0 else W.sample_states(robot, B, 1000 + rank)
         q = torch.as_tensor(q_np, device=dev)
+        outputs = "all" if world == 1 else "valid+u"
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
     b8, s4 = ops.pack_scene(w["boxes"][:, :3], w["boxes"][:, 3:], w["spheres"], device=dev)
     gr = ops.build_grid(b8, s4) if b8.shape[0] + s4.shape[0] > 0 else ops.no_grid(dev)
@@ -238,20 +354,26 @@ def main():
     common = (goal, b8, s4, 1, gr, net, K, lo, hi, w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    collective = "none"
     if world == 1:
-        def step():
-            return ops.safety_filter(q, *common)
-        launches_per_step, outputs = 1, "all"
+        if outputs == "all":
+            def step():
+                return ops.safety_filter(q, *common)
+        else:
+            valid_out = torch.empty(B, dtype=torch.uint8, device=dev)
+            u_out = torch.empty((B, n), dtype=torch.float32, device=dev)
+            def step():
+                return ops.valid_control_into(q, *common, valid_out, u_out)
+        launches_per_step = 1
     else:
-        outputs = "valid+u"
-        try:   # fused epilogue all-gather over NVLink peer mappings (one kernel + one barrier per step)
+        try:   # fused epilogue all-gather over NVLink peer mappings (one kernel + barriers per step)
             from cbfrrt.sharded import FusedSweep
-            sweep = FusedSweep(lambda qb, vp, up, off: ops.valid_control_scatter(qb, *common, vp, up, off), n, B, dev)
+            sweep = FusedSweep(lambda qb, vp, up, off, mc: ops.valid_control_scatter(qb, *common, vp, up, off, mc), n, B, dev)
             def step():
                 return sweep(q)
             launches_per_step = 1
             collective = ("fused: kernel epilogue stores (valid u8, u f32xn) into every rank's replica over NVLink ("
-                          + ("one multicast store per row, replicated by NVSwitch" if sweep.multicast else "per-peer stores")
+                          + ("multimem.st to the NVSwitch multicast address, replicated by the switch" if sweep.multicast else "per-peer stores")
                           + ", symmetric memory) + barrier")
         except Exception as e:   # no P2P / symmetric memory: NCCL all-gather, block-cyclic, overlapped on a 2nd stream
             sys.stderr.write(f"[bench] symmetric memory unavailable ({e!r}); using NCCL all_gather\n")
@@ -267,10 +389,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # clock ramp: a fresh process starts with the GPU idle, and a handful of sub-millisecond warm-up steps is too short
-    # for the SM clock to reach its sustained value -- run the step untimed for about 0.3 s first, then the W warm-up steps
+    # clock ramp: a fresh process starts with the GPU idle, and a handful of short warm-up steps is too short for the SM
+    # clock to reach its sustained value -- run the step untimed for about 0.5 s first, then the W warm-up steps
     # (a fixed count, identical on every rank: the multi-GPU step ends in a barrier)
-    for _ in range(min(20000, max(50, int(0.3 / (B * 4.5e-10))))):
+    for _ in range(int(min(20000, max(3, 0.5 / (B * 1.0e-9))))):
         step()
     torch.cuda.synchronize()
     for _ in range(args.warmup):
@@ -298,11 +420,18 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
-    units_per_step = B * world
-    value = units_per_step * args.steps / (ms * 1e-3)
+    value = G * args.steps / (ms * 1e-3)
+    valid_fraction = None
+    if strong:
+        res = step()
+        torch.cuda.synchronize()
+        vloc = res[0][rank * B:(rank + 1) * B] if res[0].shape[0] == G and world > 1 else res[0]
+        valid_fraction = float(vloc[: 1 << 22].float().mean().item())
 
-    # ---- roofline of the dominant (only) kernel: launch duration measured above (one launch per step at N=1)
-    flops_u, bytes_u = algorithmic_cost(robot, w["boxes"].shape[0], w["spheres"].shape[0], True, outputs)
+    # ---- roofline of the dominant (only) kernel, per pipe: launch duration measured above (one launch per step)
+    stats = ops.broadphase_stats(q[: 1 << 20], b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid, want_grad=True)
+    cost = algorithmic_cost(W, robot, w["boxes"].shape[0], w["spheres"].shape[0], True, outputs,
+                            pairs_per_state=stats["pairs_per_state"], lookups_per_state=stats["lookups_per_state"])
     sink = torch.zeros(1, device=dev)
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     grid, blockdim, iters = sms * 8, 256, 1 << 15
@@ -317,86 +446,117 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     fp32_peak = 3 * grid * blockdim * iters * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    # dense TF32 rate of this GPU (cuBLAS through torch.matmul, 8192^3, best of 5): the tensor-pipe denominator
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a_ = torch.randn(8192, 8192, device=dev)
+    b_ = torch.randn(8192, 8192, device=dev)
+    (a_ @ b_)
+    tt = []
+    for _ in range(5):
+        e0.record(); (a_ @ b_); e1.record(); torch.cuda.synchronize()
+        tt.append(e0.elapsed_time(e1))
+    tf32_peak = 2 * 8192 ** 3 / (min(tt) * 1e-3) / 1e12
+    del a_, b_
+    torch.backends.cuda.matmul.allow_tf32 = False
     kernel_s = ms * 1e-3 / args.steps
-    ach_tf = flops_u * B / kernel_s / 1e12
-    ach_gbs = bytes_u * B / kernel_s / 1e9
+    rows_per_launch = B
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured"
+        hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
     except Exception:
-        peaks, hbm_peak, hbm_src = {}, 6650.0, "fallback"
-    tensor_peak = next((float(v) for k, v in peaks.items() if "bf16" in k.lower() and isinstance(v, (int, float))), None)
-    tensor_src = "measured (dense bf16, MEASURED_PEAKS.json)" if tensor_peak else "fallback (nominal dense bf16)"
-    tensor_peak = tensor_peak or 2250.0
-    # DRAM traffic of one launch from the committed ncu --set full capture of this exact command
-    # (profiles/r1e_ncu_full_safety_kernel_tc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum); only valid for the
-    # default workload at N=1, else null
-    traffic = 45.3e6 if (world == 1 and cfg_idx == 1 and B == 1 << 20) else None
-    mlp_flops = 2 * 2 * ((n + 1) * 48 + 2 * 48 * 48 + 48)
-    roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
-                "traffic": traffic, "peak_source": "cbfrrt_fma_probe in this run (FP32 FMA; not in MEASURED_PEAKS.json)",
-                "flops_per_state": flops_u, "bytes_per_state": bytes_u,
-                "frac_without_mlp": (flops_u - mlp_flops) * B / kernel_s / 1e12 / fp32_peak,
-                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                        "peak_source": hbm_src},
-                "tensor": {"achieved": 3 * mlp_flops * B / kernel_s / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
-                           "frac": 3 * mlp_flops * B / kernel_s / 1e12 / tensor_peak, "peak_source": tensor_src,
-                           "note": "executed tcgen05 flops of the barrier network (3-term TF32 split = 3x algorithmic)"},
-                "kernel": "safety_kernel_tc" if world == 1 else "safety_kernel_tc (valid+u, fused exchange)",
-                "note": "achieved = ALGORITHMIC flops of SURVEY 8d (brute-force pair sweep + FP32 MLP) / kernel time, "
-                        "against the CUDA-core FP32 peak; the kernel runs the MLP on tcgen05 (TF32x3) and culls pairs "
-                        "exactly, so frac may exceed the CUDA-core bound; frac_without_mlp counts only the geometry + QP",
-                "kernel_ms": kernel_s * 1e3}
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    tc_path = B > 16384
+    pipes = {
+        "fp32": {"achieved": cost["fp32"] * rows_per_launch / kernel_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                 "peak_source": "cbfrrt_fma_probe in this run (FP32 FMA rate; not in MEASURED_PEAKS.json)",
+                 "work_per_state": cost["fp32"]},
+        "tensor": {"achieved": (3 * cost["mlp"] if tc_path else 0) * rows_per_launch / kernel_s / 1e12, "peak": tf32_peak,
+                   "unit": "TFLOP/s", "peak_source": "torch.matmul TF32 8192^3 in this run (cuBLAS)",
+                   "work_per_state": 3 * cost["mlp"],
+                   "note": "executed tcgen05 flops of the barrier network: 3-term TF32 split = 3 x the algorithmic 2*MACs"},
+        "hbm": {"achieved": cost["bytes"] * rows_per_launch / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "peak_source": hbm_src, "work_per_state": cost["bytes"]},
+    }
+    for p in pipes.values():
+        p["frac"] = p["achieved"] / p["peak"]
+    bound = max(pipes, key=lambda k: pipes[k]["frac"])
+    traffic = None   # per launch, from the committed ncu --set full capture of this command (profiles/); filled in below
+    tr_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tr_file) and world == 1:
+        traffic = json.load(open(tr_file)).get(w["name"])
+    roofline = {"bound": bound, "achieved": pipes[bound]["achieved"], "peak": pipes[bound]["peak"], "unit": pipes[bound]["unit"],
+                "frac": pipes[bound]["frac"], "traffic": traffic, "pipes": pipes,
+                "kernel": ("safety_kernel_tc" if tc_path else "safety_kernel") + f"<{robot}, grid={bool(stats['grid'])}>",
+                "kernel_ms": kernel_s * 1e3, "rows_per_launch": rows_per_launch, "broad_phase": stats,
+                "fp32_work_per_state_brute_force_formula": cost["fp32_brute_force"],
+                "note": "per pipe, never summed: fp32 = algorithmic CUDA-core flops of the path as built (FK, centres, broad-"
+                        "phase look-ups, the exact pair evaluations the broad phase leaves -- counted on the device for this "
+                        "scene --, self pairs, gradient, QP) / kernel time against the measured FMA rate; tensor = executed "
+                        "tcgen05 flops against a measured dense TF32 matmul; hbm = compulsory bytes against the measured "
+                        "copy bandwidth.  frac = the largest.  SURVEY 8d's brute-force pair formula is kept beside it."}
 
     # ---- end to end through the host-buffer C-ABI (pinned host buffers; H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
-        q_host = torch.empty((B, n), dtype=torch.float32).pin_memory()
-        q_host.copy_(q.cpu())
-        safe_h = torch.empty(B, dtype=torch.uint8).pin_memory()
-        u_h = torch.empty((B, n), dtype=torch.float32).pin_memory()
+        q_host = torch.empty((B, n), dtype=torch.float32, pin_memory=True)
+        q_host.copy_(q)
+        safe_h = torch.empty(B, dtype=torch.uint8, pin_memory=True)
+        u_h = torch.empty((B, n), dtype=torch.float32, pin_memory=True)
         out = {"safe": safe_h.numpy(), "u": u_h.numpy()}
+        q_host_np = q_host.numpy()
         def e2e_step():
-            ops.safety_filter_host(robot, q_host.numpy(), w["boxes"], w["spheres"], True, w["weights"], 48, 2, w["goal"],
+            ops.safety_filter_host(robot, q_host_np, w["boxes"], w["spheres"], True, w["weights"], 48, 2, w["goal"],
                                    w["K"], w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"],
                                    out, device=local_rank)
-        for _ in range(args.warmup):
+        e2e_steps = max(3, min(args.steps, int(2.0 / max(B * 1.5e-9, 1e-4))))
+        for _ in range(min(args.warmup, 3)):
             e2e_step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             e2e_step()
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": units_per_step * args.steps / float(dt.item()), "unit": UNIT,
+        e2e = {"value": G * e2e_steps / float(dt.item()), "unit": UNIT, "steps": e2e_steps,
                "h2d_bytes_per_step": int(B * n * 4), "d2h_bytes_per_step": int(B * (1 + 4 * n)),
-               "api": "cbfrrt_safety_filter_host (C-ABI, pinned host q -> safe,u)"}
+               "api": "cbfrrt_safety_filter_host (C-ABI, pinned host q -> valid,u; bytes are per rank)"}
+        del q_host, safe_h, u_h
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and w["q"] is not None:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rows = min(B, 1 << 17)
-        cpu_port_run(w, 4096, threads)
-        vals = [cpu_port_run(w, rows, threads) for _ in range(3)]
+        qs = host_states(w, cpu_sample_rows(w))
+        cpu_port_run(w, qs[:4096], threads)
+        vals = [cpu_port_run(w, qs, threads) for _ in range(3)]
         cpu = {"value": float(np.median(vals)), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{rows} of {B} states of {w['name']}, median of 3 (oracle/cbfrrt_oracle.c, pthreads)",
-               "sequential": cpu_sequential_run(w)}
+               "sample": f"the first {qs.shape[0]} of {G} states of {w['name']}, median of 3 (oracle/cbfrrt_oracle.c, pthreads)",
+               "sequential": cpu_sequential_run(w, 256 if w["boxes"].shape[0] > 32 else 1024)}
+
+    others = None
+    if rank == 0 and world == 1 and strong and not args.no_other_configs and args.scale == 1.0:
+        del q
+        torch.cuda.empty_cache()
+        others = other_configs(torch, ops, W, dev, flush)
 
     if rank == 0:
+        targets = None
+        if strong:
+            targets = {k: {"target_8gpu": v, "value_at_this_n": value, "n_gpus": world, "met_at_this_n": bool(value >= v)}
+                       for k, v in TARGETS_8GPU.items()}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "robot": robot, "states_per_gpu": B, "boxes": int(w["boxes"].shape[0]),
-                       "spheres": int(w["spheres"].shape[0]), "floor": True, "mlp": "(n+1)-48-48-48-1",
-                       "outputs": outputs, "l2": "flushed by a 256 MiB write between timed steps (outside the event pairs)",
-                       "collective": "none" if world == 1 else collective,
-                       "host_cpus_bound": affinity},
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, {
+                "states": int(G), "states_per_gpu": int(B), "outputs": outputs, "valid_fraction": valid_fraction,
+                "l2": "per-GPU inputs + outputs exceed the 126 MB L2; a 256 MiB write also flushes it between timed steps "
+                      "(outside the event pairs)",
+                "collective": collective, "host_cpus_bound": affinity}),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "targets": targets, "other_configs": others,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -15,7 +15,7 @@ STATUS = {0: "ok", -1: "unknown robot id", -2: "bad shape or missing pointer",
 
 class Scene(C.Structure):
     _fields_ = [("n_boxes", C.c_int32), ("n_spheres", C.c_int32), ("floor", C.c_int32), ("_pad", C.c_int32),
-                ("boxes", C.c_void_p), ("spheres", C.c_void_p), ("grid", C.c_void_p)]
+                ("boxes", C.c_void_p), ("spheres", C.c_void_p), ("grid", C.c_void_p), ("stats", C.c_void_p)]
 
 
 class HostScene(C.Structure):
@@ -35,13 +35,14 @@ class FilterParams(C.Structure):
 
 
 class PeerOut(C.Structure):
-    _fields_ = [("n_peers", C.c_int32), ("_pad", C.c_int32), ("row_offset", C.c_int64), ("valid", C.c_void_p * 8),
+    _fields_ = [("n_peers", C.c_int32), ("multicast", C.c_int32), ("row_offset", C.c_int64), ("valid", C.c_void_p * 8),
                 ("u", C.c_void_p * 8)]
 
 
 class RolloutParams(C.Structure):
     _fields_ = [("steps", C.c_int32), ("ctrl_every", C.c_int32), ("dt", C.c_float), ("stuck_lag", C.c_int32),
-                ("stuck_after", C.c_int32), ("stuck_eps", C.c_float), ("keep_going", C.c_int32)]
+                ("stuck_after", C.c_int32), ("stuck_eps", C.c_float), ("keep_going", C.c_int32),
+                ("stuck_mode", C.c_int32)]
 
 
 # every symbol declared in include/cbfrrt.h: (restype, argtypes)
@@ -51,6 +52,8 @@ SIGNATURES = {
     "cbfrrt_status_string": (C.c_char_p, [_I]),
     "cbfrrt_last_cuda_error": (C.c_int, []),
     "cbfrrt_launch_count": (C.c_int64, []),
+    "cbfrrt_set_mlp_path": (C.c_int, [_I]),
+    "cbfrrt_get_mlp_path": (C.c_int, []),
     "cbfrrt_robot_info": (C.c_int, [_I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cbfrrt_grid_bytes": (C.c_int64, []),
     "cbfrrt_grid_build": (C.c_int, [C.POINTER(Scene), _P, _P]),

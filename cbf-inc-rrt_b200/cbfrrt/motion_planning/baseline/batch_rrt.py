@@ -13,7 +13,7 @@ import time
 import numpy as np
 import torch
 
-from .batch_tsa import explore_nearest, explore_nearest_each, steer as batch_steer
+from .batch_tsa import explore_nearest, explore_nearest_each, steer as batch_steer, steer_fused_reference
 from .tsa import _rollout
 
 
@@ -106,13 +106,9 @@ def _steer_batch(dynamics_model, controller, steer_type, sample_states, current_
     if steer_type != "cbf":
         raise ValueError("Unknown steer_type, must be one of {'line', 'cbf'}.")
     assert hasattr(controller, "u")
-    dm.set_intermediate_goals(np.asarray(sample_states))
-    q0 = torch.as_tensor(np.asarray(current_states), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
-    # stuck test of the batched steer (batch_tsa.py:226): ||x_t - x_{t-9}|| < 3e-2 once more than 10 states are stored
-    qf, alive, done, traj = _rollout(controller, dm, q0, rrt_step, stuck=(9, 10, 3e-2), want_traj=True)
-    done, traj = done.cpu().numpy(), traj.cpu().numpy()
-    edges = [[row for row in traj[i, :done[i]]] for i in range(traj.shape[0])]
-    return qf.cpu().numpy(), [bool(a) for a in alive.cpu().numpy()], edges
+    # the reference's batched steer semantics (batch_tsa.py:191-231: stuck rows count as collisions, dead rows keep
+    # integrating, x_last = running state) in one launch -- same nodes and flags as the 'line' branch's host loop
+    return steer_fused_reference(controller, dm, sample_states, current_states, RRT_step=rrt_step)
 
 
 def _goal_test(dynamics_model, states):

@@ -83,3 +83,34 @@ def steer_fused(controller, dynamics_model, sample_states, nearests, RRT_step=10
     q0 = torch.as_tensor(np.asarray(nearests), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
     qf, alive, done, traj = _rollout(controller, dm, q0, RRT_step, want_traj=want_traj)
     return qf, alive.bool(), done, (traj if want_traj else None)
+
+
+@torch.no_grad()
+def steer_fused_reference(controller, dynamics_model, sample_states, nearests, RRT_step=10):
+    """The batched steer of the reference (batch_tsa.py:191-231) with ITS semantics in one launch
+    -> (x_last (B,n) numpy, no_collisions [bool]*B, xs_list) exactly as ``steer(controller.u, ...)`` returns them:
+
+      * the stuck test runs before the append, on the stored list (more than 10 states: xs[-1] vs xs[-10], 3e-2), and a
+        stuck row is reported as a collision (``no_collisions[i] = False``, batch_tsa.py:226-227);
+      * a dead row (stuck or unsafe) never appends again, but its state keeps integrating: x_last is the running
+        x_current of every row, dead or alive (batch_tsa.py:231);
+      * the loop ends early once EVERY row is dead (batch_tsa.py:229-230): x_last is then the state after that step.
+        That is the one batch-wide dependency of the reference's loop; it is reproduced by a second launch truncated at
+        the step where the last row died (rare: all rows of a batch must die).
+    Kernel: cbfrrt_rollout with stuck_mode = 1, keep_going = 1 (include/cbfrrt.h)."""
+    dm = dynamics_model
+    dm.set_intermediate_goals(np.asarray(sample_states))
+    q0 = torch.as_tensor(np.asarray(nearests), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
+    steps = int(RRT_step)
+    qf, alive, done, traj = _rollout(controller, dm, q0, steps, stuck=(9, 10, 3e-2), want_traj=True, keep_going=True,
+                                     stuck_mode=1)
+    alive_np, done_np = alive.cpu().numpy().astype(bool), done.cpu().numpy()
+    if steps > 0 and not alive_np.any():
+        last_death = int(done_np.max())          # a row that died at step t (0-based) has appended exactly t states
+        if last_death + 1 < steps:
+            qf, alive, done, traj = _rollout(controller, dm, q0, last_death + 1, stuck=(9, 10, 3e-2), want_traj=True,
+                                             keep_going=True, stuck_mode=1)
+            alive_np, done_np = alive.cpu().numpy().astype(bool), done.cpu().numpy()
+    traj_np = traj.cpu().numpy()
+    xs_list = [[row for row in traj_np[i, :done_np[i]]] for i in range(traj_np.shape[0])]
+    return qf.cpu().numpy(), [bool(a) for a in alive_np], xs_list

@@ -71,7 +71,7 @@ def steer_fused(controller, dynamics_model, new_state, nearest, RRT_step=10, dev
     return x_list[-1], bool(alive.item()), time_dict, x_list
 
 
-def _rollout(controller, dm, q0, steps, stuck=(0, 10, 0.1), want_traj=False, keep_going=False):
+def _rollout(controller, dm, q0, steps, stuck=(0, 10, 0.1), want_traj=False, keep_going=False, stuck_mode=0):
     b, s, fl, gr = dm.env.scene
     lo, hi = controller._limits()
     ctrl_every = int(dm.controller_dt // dm.dt)
@@ -79,7 +79,7 @@ def _rollout(controller, dm, q0, steps, stuck=(0, 10, 0.1), want_traj=False, kee
                        int(stuck[1]), float(stuck[2]), bool(want_traj), bool(keep_going), b, s, fl, gr, controller._weights(),
                        dm.K_on(dm.device), lo, hi, float(controller.clf_lambda),
                        float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard),
-                       dm.robot.robot_id, controller.h_hidden_size, controller.h_hidden_layers)
+                       dm.robot.robot_id, controller.h_hidden_size, controller.h_hidden_layers, int(stuck_mode))
 
 
 def edge_checking(state, new_state, dynamics_model, eps):

@@ -66,7 +66,7 @@ def no_grid(device) -> Tensor:
     return torch.empty(0, dtype=torch.uint8, device=device)
 
 
-def _scene(boxes8: Tensor, spheres: Tensor, floor: int, grid: Tensor) -> Scene:
+def _scene(boxes8: Tensor, spheres: Tensor, floor: int, grid: Tensor, stats: Tensor = None) -> Scene:
     if boxes8.numel() and (boxes8.dim() != 2 or boxes8.shape[1] != 8):
         raise ValueError("boxes must be packed as (Ob, 8): cx cy cz hx hy hz 0 0 (use pack_scene)")
     if spheres.numel() and (spheres.dim() != 2 or spheres.shape[1] != 4):
@@ -74,7 +74,8 @@ def _scene(boxes8: Tensor, spheres: Tensor, floor: int, grid: Tensor) -> Scene:
     if grid.numel() and (grid.dtype != torch.uint8 or grid.numel() != int(lib.cbfrrt_grid_bytes())):
         raise ValueError("grid must be the uint8 tensor returned by build_grid (or empty)")
     return Scene(int(boxes8.shape[0]) if boxes8.numel() else 0, int(spheres.shape[0]) if spheres.numel() else 0,
-                 int(bool(floor)), 0, _ptr(boxes8).value, _ptr(spheres).value, _ptr(grid).value)
+                 int(bool(floor)), 0, _ptr(boxes8).value, _ptr(spheres).value, _ptr(grid).value,
+                 _ptr(stats).value if stats is not None else None)
 
 
 def pack_scene(positions, sizes, spheres=None, device="cuda"):
@@ -97,26 +98,8 @@ def packed_weight_count(n: int, hidden: int, layers: int) -> int:
 def pack_weights(state_dict, n: int, hidden: int, layers: int, device="cuda") -> Tensor:
     """h_nn state_dict (keys input_linear / layer_{i}_linear / output_linear, with or without the ``h_nn.``
     prefix; neural_mindis_cbf_controller.py:44-53) -> packed float32 buffer described in include/cbfrrt.h."""
-    def get(name):
-        for k in (name, "h_nn." + name):
-            if k in state_dict:
-                v = state_dict[k]
-                return v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
-        raise KeyError(name)
-
-    in_pad = (n + 1 + 3) & ~3
-    out = np.zeros(packed_weight_count(n, hidden, layers), np.float32)
-    w_in = np.zeros((hidden, in_pad), np.float32)
-    w_in[:, :n + 1] = get("input_linear.weight")
-    o = 0
-    out[o:o + hidden * in_pad] = w_in.ravel(); o += hidden * in_pad
-    out[o:o + hidden] = get("input_linear.bias"); o += hidden
-    for i in range(layers):
-        out[o:o + hidden * hidden] = get(f"layer_{i}_linear.weight").ravel(); o += hidden * hidden
-        out[o:o + hidden] = get(f"layer_{i}_linear.bias"); o += hidden
-    out[o:o + hidden] = get("output_linear.weight").ravel(); o += hidden
-    out[o] = float(np.asarray(get("output_linear.bias")).ravel()[0])
-    return torch.from_numpy(out).to(device)
+    from .workloads import pack_weights_np
+    return torch.from_numpy(pack_weights_np(state_dict, n, hidden, layers)).to(device)
 
 
 def _net_params(n, W, K, lo, hi, goal, B, lam, penalty, hidden, layers, u_ref=None):
@@ -347,20 +330,68 @@ def valid_control(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor
     return safe, u
 
 
+def valid_control_into(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor,
+                       K: Tensor, u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float,
+                       robot_id: int, hidden: int, layers: int, valid_out: Tensor, u_out: Tensor) -> Tuple[Tensor, Tensor]:
+    """``valid_control`` into caller-owned outputs (valid u8[B], u f32[B,n]): sweeps of tens of millions of states
+    reuse their 2 GB result buffers instead of allocating per call"""
+    n = ROBOT_N[robot_id]
+    q, qs = _rows(q, n)
+    B, dev = q.shape[0], q.device
+    if (valid_out.dtype != torch.uint8 or valid_out.numel() != B or u_out.dtype != torch.float32 or tuple(u_out.shape) != (B, n)
+            or not valid_out.is_contiguous() or not u_out.is_contiguous() or valid_out.device != dev or u_out.device != dev):
+        raise ValueError("valid_control_into: outputs must be contiguous (B,) uint8 and (B, n) float32 on q's device")
+    net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers)
+    sc = _scene(boxes, spheres, floor, grid)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_safety_filter(robot_id, C.byref(sc), C.byref(net), _ptr(q), qs, B, C.byref(fp), thr_soft,
+                                       thr_hard, _ptr(valid_out), None, None, None, None, _ptr(u_out), None, _stream()),
+              "cbfrrt_safety_filter")
+    del keep
+    return valid_out, u_out
+
+
+def broadphase_stats(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, thr_soft: float, thr_hard: float,
+                     robot_id: int, want_grad: bool = True) -> dict:
+    """Measured work of the broad phase on these states (cbfrrt_scene.stats): per state, the link spheres swept exactly,
+    the exact sphere-obstacle pair evaluations and the field look-ups.  want_grad: the observation caller (masks + datax)
+    or the mask-only caller.  Used by bench.py for the per-pipe roofline."""
+    n = ROBOT_N[robot_id]
+    q, qs = _rows(q, n)
+    B, dev = q.shape[0], q.device
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    safe = torch.empty(B, dtype=torch.uint8, device=dev)
+    unsafe = torch.empty(B, dtype=torch.uint8, device=dev)
+    datax = torch.empty((B, 2 * n + 1), dtype=torch.float32, device=dev) if want_grad else None
+    sc = _scene(boxes, spheres, floor, grid, stats)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_collide(robot_id, C.byref(sc), _ptr(q), qs, B, thr_soft, thr_hard, _ptr(safe), _ptr(unsafe),
+                                 _ptr(datax) if want_grad else None, None, None, None, _stream()), "cbfrrt_collide")
+    st = stats.cpu().numpy().astype(np.float64)
+    states = max(st[0], 1.0)
+    n_obs = (int(boxes.shape[0]) if boxes.numel() else 0) + (int(spheres.shape[0]) if spheres.numel() else 0)
+    field = st[3] > 0
+    return {"grid": bool(field), "states": int(st[0]), "spheres_swept_per_state": st[1] / states if field else None,
+            "pairs_per_state": st[2] / states if field else None, "lookups_per_state": st[3] / states,
+            "obstacles": n_obs}
+
+
 def valid_control_scatter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor,
                           K: Tensor, u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float,
                           thr_hard: float, robot_id: int, hidden: int, layers: int, valid_ptrs, u_ptrs,
-                          row_offset: int) -> None:
+                          row_offset: int, multicast: bool = False) -> None:
     """Fused sweep + all-gather (include/cbfrrt.h cbfrrt_safety_filter_scatter): the (valid, u) rows of this rank
     are stored at global row ``row_offset + b`` of every peer buffer in ``valid_ptrs`` / ``u_ptrs`` (raw device
-    pointers of NVLink peer mappings, e.g. torch symmetric memory ``buffer_ptrs``).  No output tensors."""
+    pointers of NVLink peer mappings, e.g. torch symmetric memory ``buffer_ptrs``).  multicast=True: the single pointer
+    pair is the buffers' NVSwitch multicast address and the kernel stores with multimem.st (B and row_offset must be
+    multiples of 128).  No output tensors."""
     n = ROBOT_N[robot_id]
     q, qs = _rows(q, n)
     B, dev = q.shape[0], q.device
     net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers)
     sc = _scene(boxes, spheres, floor, grid)
     po = PeerOut()
-    po.n_peers, po.row_offset = len(valid_ptrs), int(row_offset)
+    po.n_peers, po.multicast, po.row_offset = len(valid_ptrs), int(bool(multicast)), int(row_offset)
     for i, (v, u) in enumerate(zip(valid_ptrs, u_ptrs)):
         po.valid[i], po.u[i] = int(v), int(u)
     with torch.cuda.device(dev):
@@ -451,9 +482,10 @@ def radius_mask(queries: Tensor, points: Tensor, radius: float) -> Tensor:
 def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, stuck_lag: int, stuck_after: int,
             stuck_eps: float, want_traj: bool, keep_going: bool, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor, K: Tensor,
             u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float, robot_id: int,
-            hidden: int, layers: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+            hidden: int, layers: int, stuck_mode: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """the steer loop in one launch -> q_final f32[T,n], alive u8[T], steps_done i32[T], traj f32[T,steps,n]
-    (traj is (0,) unless want_traj or the stuck test is on)"""
+    (traj is (0,) unless want_traj or the stuck test is on).  stuck_mode 0: tsa.py steer, 1: batch_tsa.py steer
+    (include/cbfrrt.h cbfrrt_rollout_params)"""
     n = ROBOT_N[robot_id]
     q0 = _f32c(q0)
     if q0.dim() != 2 or q0.shape[1] != n:
@@ -461,7 +493,7 @@ def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, st
     T, dev = q0.shape[0], q0.device
     net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, T, lam, penalty, hidden, layers)
     sc = _scene(boxes, spheres, floor, grid)
-    rp = RolloutParams(steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, int(keep_going))
+    rp = RolloutParams(steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, int(keep_going), int(stuck_mode))
     qf = torch.empty((T, n), dtype=torch.float32, device=dev)
     alive = torch.empty(T, dtype=torch.uint8, device=dev)
     done = torch.empty(T, dtype=torch.int32, device=dev)
@@ -578,6 +610,19 @@ def safety_filter_host(robot: str, q: np.ndarray, boxes6: np.ndarray, spheres: n
                                         thr_hard, p("safe"), p("unsafe"), p("datax"), p("h"), p("J"), p("u"), p("r")),
           "cbfrrt_safety_filter_host")
     return out
+
+
+MLP_PATHS = {"auto": 0, "fma": 1, "tc": 2}
+
+
+def set_mlp_path(path: str) -> None:
+    """'auto' (tcgen05 kernels above 16 384 rows, FP32-FMA below), 'fma' or 'tc' for every size (include/cbfrrt.h
+    cbfrrt_set_mlp_path).  Process-wide."""
+    check(lib.cbfrrt_set_mlp_path(MLP_PATHS[path]), "cbfrrt_set_mlp_path")
+
+
+def get_mlp_path() -> str:
+    return {v: k for k, v in MLP_PATHS.items()}[int(lib.cbfrrt_get_mlp_path())]
 
 
 def launch_count() -> int:

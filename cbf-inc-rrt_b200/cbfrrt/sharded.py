@@ -96,9 +96,15 @@ class FusedSweep:
     by the switch (NVLS) -- 1/world of the outbound traffic and store instructions of the per-peer form, which is
     kept as the fallback (no multicast support, or CBFRRT_NO_MULTICAST=1).
 
-    launch(q_local, valid_ptrs, u_ptrs, row_offset) runs cbfrrt::valid_control_scatter with the scene / network of
-    the caller.  ``valid`` [G] u8 and ``u`` [G, n] f32 are this rank's replicas (valid after __call__ returns and
-    the stream is synchronised)."""
+    launch(q_local, valid_ptrs, u_ptrs, row_offset, multicast) runs cbfrrt::valid_control_scatter with the scene /
+    network of the caller.  ``valid`` [G] u8 and ``u`` [G, n] f32 are this rank's replicas (valid after __call__
+    returns and the stream is synchronised).
+
+    Ordering contract: a step begins with a barrier too -- no rank's kernel may store into the replicas while another
+    rank still reads the previous step's rows (write-after-read across ranks).  Both barriers are stream-ordered
+    symmetric-memory barriers: whatever the caller enqueued on the current stream to consume step i is complete on
+    every rank before any store of step i+1 is issued.  The multicast form needs rows_per_rank % 128 == 0 (the mask
+    bytes of 32 rows travel as packed words); otherwise the per-peer form is used."""
 
     def __init__(self, launch, n: int, rows_per_rank: int, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -114,12 +120,14 @@ class FusedSweep:
         self.u_ptrs = [int(p) for p in self.h_u.buffer_ptrs]
         mc_v = int(getattr(self.h_valid, "multicast_ptr", 0) or 0)
         mc_u = int(getattr(self.h_u, "multicast_ptr", 0) or 0)
-        self.multicast = bool(mc_v and mc_u) and os.environ.get("CBFRRT_NO_MULTICAST", "0") != "1"
+        self.multicast = (bool(mc_v and mc_u) and os.environ.get("CBFRRT_NO_MULTICAST", "0") != "1"
+                          and rows_per_rank % 128 == 0)
         if self.multicast:
             self.valid_ptrs, self.u_ptrs = [mc_v], [mc_u]
 
     def __call__(self, q_local: torch.Tensor):
         assert q_local.shape[0] == self.B
-        self.launch(q_local, self.valid_ptrs, self.u_ptrs, self.rank * self.B)
+        self.h_u.barrier(channel=1)     # every rank is done reading the previous step's rows
+        self.launch(q_local, self.valid_ptrs, self.u_ptrs, self.rank * self.B, self.multicast)
         self.h_u.barrier(channel=0)     # all ranks' kernels (and their peer stores) are complete past this point
         return self.valid, self.u

@@ -3,10 +3,19 @@
 Everything is generated from seeds with numpy / torch on the host (the reference ships no checkpoints, problem
 sets or datasets); config 5 samples its states on the device with the counter-based sampler so that results do
 not depend on the shard count.  Returned dicts hold plain numpy arrays so that the CUDA path, the oracle and the
-host-buffer C-ABI can all consume the same inputs.
+host-buffer C-ABI can all consume the same inputs.  This module touches neither the CUDA library nor torch.cuda
+(bench.py's --impl reference arm loads it without mapping libcbfrrt.so).
 
 Deviations from the reference (stated in every result): sphere obstacles, 64/256-obstacle scenes, batches
 >= 4096, seeded random MLP weights, a fixed number of interpolation points per edge.
+
+Obstacle distributions (`OBSTACLES` below; also printed in bench.py's `config`).  Box half extents follow SURVEY 8d /
+generate_problem_env.py:62-78 (U(.05,.25) m; spheres r ~ U(.05,.2)) wherever the scene stays usable.  The PLACEMENT
+region is the reference's 1 m^3 box U([-.5,-.5,0],[.5,.5,1]) only for its own problem size (config 4: 8 boxes); with
+16 / 64 / 256 obstacles that box leaves 0.03 % / 0.06 % / 0.00 % of the sampled configurations collision-free
+(measured with the oracle on 20 000 states), so those scenes are spread over the arm's whole reach, and the
+256-box scene uses half extents U(.02,.08).  Free-space fractions (safe_mask true, 20 000 states): cfg1 22 %,
+cfg2 17 % of the states / 8 % of the edges, cfg3 12 %, cfg4 18 %.
 """
 from collections import OrderedDict
 
@@ -14,7 +23,6 @@ import numpy as np
 import torch
 
 from ._robot_tables import ROBOT_MODELS
-from .neural_cbf.systems.utils import scalar_dare_gain
 
 DT, CONTROLLER_DT = 1.0 / 120.0, 1.0 / 30.0   # eval_rrt_mindis_cbfsteer.py:24-31
 THR_SOFT, THR_HARD = 0.02, 0.0                 # dis_threshold (eval_rrt_mindis_cbfsteer.py:27)
@@ -38,9 +46,43 @@ def make_state_dict(n: int, seed: int = 1, hidden: int = HIDDEN, layers: int = L
     return {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}, net
 
 
+def scalar_dare_gain(b: float) -> float:
+    """LQR gain of x+ = x + b u, Q = R = 1 (control_affine_system.py:125-157, utils.py:18-49): same closed form as
+    cbfrrt.neural_cbf.systems.utils.scalar_dare_gain, repeated here so that this module stays free of the package's
+    CUDA-backed imports."""
+    b2 = b * b
+    x = (b2 + np.sqrt(b2 * b2 + 4.0 * b2)) / (2.0 * b2)
+    return b * x / (1.0 + b2 * x)
+
+
+def packed_weight_count(n: int, hidden: int, layers: int) -> int:
+    in_pad = (n + 1 + 3) & ~3
+    return hidden * in_pad + hidden + layers * (hidden * hidden + hidden) + hidden + 4
+
+
 def pack_weights_np(sd, n: int, hidden: int = HIDDEN, layers: int = LAYERS) -> np.ndarray:
-    from .ops import pack_weights
-    return pack_weights(sd, n, hidden, layers, device="cpu").numpy()
+    """h_nn state_dict (keys input_linear / layer_{i}_linear / output_linear, with or without the ``h_nn.`` prefix;
+    neural_mindis_cbf_controller.py:44-53) -> the packed float32 buffer described in include/cbfrrt.h."""
+    def get(name):
+        for k in (name, "h_nn." + name):
+            if k in sd:
+                v = sd[k]
+                return v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        raise KeyError(name)
+
+    in_pad = (n + 1 + 3) & ~3
+    out = np.zeros(packed_weight_count(n, hidden, layers), np.float32)
+    w_in = np.zeros((hidden, in_pad), np.float32)
+    w_in[:, :n + 1] = get("input_linear.weight")
+    o = 0
+    out[o:o + hidden * in_pad] = w_in.ravel(); o += hidden * in_pad
+    out[o:o + hidden] = get("input_linear.bias"); o += hidden
+    for i in range(layers):
+        out[o:o + hidden * hidden] = get(f"layer_{i}_linear.weight").ravel(); o += hidden * hidden
+        out[o:o + hidden] = get(f"layer_{i}_linear.bias"); o += hidden
+    out[o:o + hidden] = get("output_linear.weight").ravel(); o += hidden
+    out[o] = float(np.asarray(get("output_linear.bias")).ravel()[0])
+    return out
 
 
 def sample_states(robot: str, B: int, seed: int) -> np.ndarray:
@@ -51,13 +93,36 @@ def sample_states(robot: str, B: int, seed: int) -> np.ndarray:
     return (lo + (hi - lo) * rng.random((B, m["n"]), dtype=np.float32)).astype(np.float32)
 
 
-def random_boxes(n_boxes: int, seed: int, h_lo: float, h_hi: float) -> np.ndarray:
-    """centres U([-.5,-.5,0],[.5,.5,1]) (generate_problem_env.py:65-78); half extents U(h_lo, h_hi); boxes that
+REF_REGION = ((-0.5, -0.5, 0.0), (0.5, 0.5, 1.0))      # generate_problem_env.py:65-78
+PANDA_REACH = ((-1.2, -1.2, 0.0), (1.2, 1.2, 1.5))     # shoulder at z = 0.333 m + 0.855 m reach + hand
+MAGICIAN_REACH = ((-0.8, -0.8, 0.0), (0.8, 0.8, 1.0))  # 2 x scaled Dobot (environment/magician.py:20)
+
+# per BASELINE config: (n_boxes, box half-extent range, n_spheres, sphere radius range, placement region)
+OBSTACLES = {
+    1: dict(n_boxes=16, h=(0.05, 0.25), n_spheres=0, r=(0.0, 0.0), region=MAGICIAN_REACH),
+    2: dict(n_boxes=32, h=(0.05, 0.25), n_spheres=32, r=(0.05, 0.2), region=PANDA_REACH),
+    3: dict(n_boxes=8, h=(0.05, 0.25), n_spheres=0, r=(0.0, 0.0), region=REF_REGION),
+    4: dict(n_boxes=256, h=(0.02, 0.08), n_spheres=0, r=(0.0, 0.0), region=PANDA_REACH),
+}
+
+
+def obstacle_note(idx: int) -> str:
+    if idx not in OBSTACLES:
+        return "floor + first default box of arm_env.py:113-114"
+    o = OBSTACLES[idx]
+    s = f"{o['n_boxes']} boxes, half extents U{o['h']} m"
+    if o["n_spheres"]:
+        s += f" + {o['n_spheres']} spheres, r U{o['r']} m"
+    return s + f", centres U({o['region'][0]}, {o['region'][1]}), obstacles overlapping the base column rejected"
+
+
+def random_boxes(n_boxes: int, seed: int, h_lo: float, h_hi: float, region=REF_REGION) -> np.ndarray:
+    """centres U(region) (default: generate_problem_env.py:65-78); half extents U(h_lo, h_hi); boxes that
     would swallow the robot base (a 0.2 m column up to z = 0.4) are rejected.  -> (n_boxes, 6)"""
     rng = np.random.default_rng(seed)
     out = []
     while len(out) < n_boxes:
-        c = rng.uniform((-0.5, -0.5, 0.0), (0.5, 0.5, 1.0))
+        c = rng.uniform(region[0], region[1])
         h = rng.uniform(h_lo, h_hi, size=3)
         if abs(c[0]) - h[0] < 0.2 and abs(c[1]) - h[1] < 0.2 and c[2] - h[2] < 0.4:
             continue
@@ -65,16 +130,24 @@ def random_boxes(n_boxes: int, seed: int, h_lo: float, h_hi: float) -> np.ndarra
     return np.array(out, dtype=np.float32).reshape(-1, 6)
 
 
-def random_spheres(n_sph: int, seed: int, r_lo: float, r_hi: float) -> np.ndarray:
+def random_spheres(n_sph: int, seed: int, r_lo: float, r_hi: float, region=REF_REGION) -> np.ndarray:
     rng = np.random.default_rng(seed)
     out = []
     while len(out) < n_sph:
-        c = rng.uniform((-0.5, -0.5, 0.0), (0.5, 0.5, 1.0))
+        c = rng.uniform(region[0], region[1])
         r = rng.uniform(r_lo, r_hi)
         if np.hypot(c[0], c[1]) - r < 0.2 and c[2] - r < 0.4:
             continue
         out.append(np.concatenate([c, [r]]))
     return np.array(out, dtype=np.float32).reshape(-1, 4)
+
+
+def scene(idx: int):
+    """(boxes (Ob,6), spheres (Os,4)) of BASELINE config idx (seeds 2 / 5 as in SURVEY 8d)"""
+    o = OBSTACLES[idx]
+    boxes = random_boxes(o["n_boxes"], 2, o["h"][0], o["h"][1], o["region"])
+    sph = random_spheres(o["n_spheres"], 5, o["r"][0], o["r"][1], o["region"]) if o["n_spheres"] else np.zeros((0, 4), np.float32)
+    return boxes, sph
 
 
 def controller_constants(robot: str):
@@ -96,7 +169,7 @@ def config(idx: int, scale: float = 1.0):
     elif idx == 1:
         robot, B = "magician", max(1, int((1 << 20) * scale))
         w = dict(robot=robot, name="cfg1_magician_16obs_1M", q=sample_states(robot, B, 0),
-                 boxes=random_boxes(16, 2, 0.03, 0.12), spheres=np.zeros((0, 4), np.float32), floor=True,
+                 boxes=scene(1)[0], spheres=scene(1)[1], floor=True,
                  goal=sample_states(robot, 1, 3))
     elif idx == 2:
         robot, E = "panda", max(1, int((1 << 22) * scale))
@@ -105,17 +178,16 @@ def config(idx: int, scale: float = 1.0):
         lo, hi = np.array(m["q_lower"], np.float32), np.array(m["q_upper"], np.float32)
         step = np.random.default_rng(1).uniform(-0.35, 0.35, size=q_from.shape).astype(np.float32)
         w = dict(robot=robot, name="cfg2_panda_64obs_4Medges_x32", q=q_from, q_to=np.clip(q_from + step, lo, hi),
-                 n_interp=32, boxes=random_boxes(32, 2, 0.02, 0.08), spheres=random_spheres(32, 5, 0.02, 0.08),
+                 n_interp=32, boxes=scene(2)[0], spheres=scene(2)[1],
                  floor=True, goal=np.array(m["q0"], np.float32).reshape(1, -1))
     elif idx == 3:
         robot, T = "panda", max(1, int((1 << 18) * scale))
         w = dict(robot=robot, name="cfg3_panda_rollout_262k_x200", q=sample_states(robot, T, 0),
-                 goal=sample_states(robot, T, 1), steps=200, boxes=random_boxes(8, 2, 0.05, 0.12),
-                 spheres=np.zeros((0, 4), np.float32), floor=True)
+                 goal=sample_states(robot, T, 1), steps=200, boxes=scene(3)[0], spheres=scene(3)[1], floor=True)
     elif idx == 4:
         robot, B = "panda", max(1, int((1 << 26) * scale))
         w = dict(robot=robot, name="cfg4_panda_256obs_64M", q=None, n_states=B, sample_seed=0,
-                 boxes=random_boxes(256, 2, 0.01, 0.05), spheres=np.zeros((0, 4), np.float32), floor=True,
+                 boxes=scene(4)[0], spheres=scene(4)[1], floor=True,
                  goal=np.array(ROBOT_MODELS[robot]["q0"], np.float32).reshape(1, -1))
     else:
         raise ValueError(idx)
@@ -125,4 +197,5 @@ def config(idx: int, scale: float = 1.0):
     w["state_dict"] = sd
     w["weights"] = pack_weights_np(sd, n)
     w["n"] = n
+    w["obstacles"] = obstacle_note(idx)
     return w

@@ -7,7 +7,12 @@ namespace cbfrrt {
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_last_cuda{0};
 std::mutex g_cfg_mu;
-std::map<std::pair<const void*, size_t>, int> g_cfg;
+std::map<CfgKey, int> g_cfg;
+static int mlp_path_from_env() {
+    const char* e = getenv("CBFRRT_MLP");
+    return (e && e[0] == 'f') ? CBFRRT_MLP_FMA : ((e && e[0] == 't') ? CBFRRT_MLP_TC : CBFRRT_MLP_AUTO);
+}
+std::atomic<int> g_mlp_path{mlp_path_from_env()};
 }  // namespace cbfrrt
 
 using namespace cbfrrt;
@@ -29,6 +34,13 @@ const char* cbfrrt_status_string(int s) {
 }
 
 int cbfrrt_last_cuda_error(void) { return g_last_cuda.load(); }
+
+int cbfrrt_set_mlp_path(int path) {
+    if (path != CBFRRT_MLP_AUTO && path != CBFRRT_MLP_FMA && path != CBFRRT_MLP_TC) return CBFRRT_ERR_BAD_SHAPE;
+    g_mlp_path.store(path);
+    return CBFRRT_OK;
+}
+int cbfrrt_get_mlp_path(void) { return g_mlp_path.load(); }
 int64_t cbfrrt_launch_count(void) { return g_launches.load(); }
 
 int cbfrrt_robot_info(int robot, int32_t* n, int32_t* n_links, int32_t* n_spheres) {
@@ -45,9 +57,13 @@ int cbfrrt_grid_build(const cbfrrt_scene* scene, void* grid_out, void* stream) {
     if (rc) return rc;
     if (!grid_out) return CBFRRT_ERR_BAD_SHAPE;
     if (!aligned16(grid_out)) return CBFRRT_ERR_ALIGNMENT;
-    grid::build_kernel<<<(grid::NCELLS + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    grid::build_kernel<0><<<(grid::NCELLS + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(sc.boxes), sc.n_boxes, reinterpret_cast<const float4*>(sc.spheres), sc.n_spheres,
         static_cast<uint16_t*>(grid_out));
+    if (finish_launch()) return CBFRRT_ERR_CUDA;
+    grid::field_kernel<0><<<(grid::FNCELLS + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(sc.boxes), sc.n_boxes, reinterpret_cast<const float4*>(sc.spheres), sc.n_spheres,
+        reinterpret_cast<float*>(static_cast<unsigned char*>(grid_out) + grid::REC_BYTES));
     return finish_launch();
 }
 
@@ -191,7 +207,10 @@ int cbfrrt_safety_filter_scatter(int robot, const cbfrrt_scene* scene, const cbf
     if (q_stride < n) return CBFRRT_ERR_BAD_SHAPE;
     PeerOut po{};
     po.n = peers->n_peers;
+    po.multicast = peers->multicast ? 1 : 0;
     po.row_offset = peers->row_offset;
+    // multicast mode packs the mask bytes of 32 consecutive rows into words: whole, aligned 128-row tiles only
+    if (po.multicast && (po.n != 1 || B % 128 != 0 || peers->row_offset % 128 != 0)) return CBFRRT_ERR_BAD_SHAPE;
     for (int p = 0; p < po.n; ++p) {
         if (!peers->valid[p] || !peers->u[p]) return CBFRRT_ERR_BAD_SHAPE;
         if (!aligned16(peers->u[p])) return CBFRRT_ERR_ALIGNMENT;
@@ -312,6 +331,7 @@ int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* n
     if (T < 0 || !rp || rp->steps < 0 || rp->ctrl_every < 1 || !q0 || !q_final || !alive || !steps_done)
         return CBFRRT_ERR_BAD_SHAPE;
     if (rp->stuck_lag < 0 || (rp->stuck_lag > 0 && (!traj || rp->stuck_after < rp->stuck_lag))) return CBFRRT_ERR_BAD_SHAPE;
+    if (rp->stuck_mode != 0 && rp->stuck_mode != 1) return CBFRRT_ERR_BAD_SHAPE;
     if (fp && fp->u_ref) return CBFRRT_ERR_UNSUPPORTED;  // the loop needs the nominal controller
     const int n = robot == CBFRRT_ROBOT_PANDA ? Panda::N : Magician::N;
     SceneArgs sc;
@@ -321,7 +341,7 @@ int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* n
     rc = check_net(n, net, fp, T, na);
     if (rc) return rc;
     if (T == 0) return CBFRRT_OK;
-    const RolloutArgs ra{rp->steps, rp->ctrl_every, rp->dt, rp->stuck_lag, rp->stuck_after, rp->stuck_eps, rp->keep_going};
+    const RolloutArgs ra{rp->steps, rp->ctrl_every, rp->dt, rp->stuck_lag, rp->stuck_after, rp->stuck_eps, rp->keep_going, rp->stuck_mode};
     cudaStream_t st = (cudaStream_t)stream;
     return robot == CBFRRT_ROBOT_PANDA
                ? launch_rollout_panda(sc, na, q0, T, ra, thr_soft, thr_hard, q_final, alive, steps_done, traj, st)
@@ -330,7 +350,7 @@ int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* n
 
 int cbfrrt_fma_probe(int32_t grid, int32_t block, int32_t iters, float* sink, void* stream) {
     if (grid < 1 || block < 32 || block > 1024 || iters < 1 || !sink) return CBFRRT_ERR_BAD_SHAPE;
-    fma_probe_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
+    fma_probe_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
     return finish_launch();
 }
 

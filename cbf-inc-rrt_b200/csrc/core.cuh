@@ -36,6 +36,7 @@ struct Panda {
     __device__ static constexpr int sph_end(int l) { return PANDA_SPH_BEGIN[l + 2]; }
     __device__ static constexpr float sph(int i, int k) { return PANDA_SPH[i][k]; }
     __device__ static constexpr int sph_link(int i) { return PANDA_SPH_LINK[i]; }
+    __device__ static float rad_dyn(int i) { return PANDA_SPH[i][3]; }           // run-time index: a global-memory read
     __device__ static constexpr int anc_mask(int l) { return PANDA_ANC_MASK[l]; }
     __device__ static constexpr float ball(int l, int k) { return PANDA_LINK_BALL[l + 1][k]; }
     __device__ static constexpr int self_i(int p) { return PANDA_SELFSPH_I[p]; }
@@ -57,6 +58,7 @@ struct Magician {
     __device__ static constexpr int sph_end(int l) { return MAGICIAN_SPH_BEGIN[l + 2]; }
     __device__ static constexpr float sph(int i, int k) { return MAGICIAN_SPH[i][k]; }
     __device__ static constexpr int sph_link(int i) { return MAGICIAN_SPH_LINK[i]; }
+    __device__ static float rad_dyn(int i) { return MAGICIAN_SPH[i][3]; }
     __device__ static constexpr int anc_mask(int l) { return MAGICIAN_ANC_MASK[l]; }
     __device__ static constexpr float ball(int l, int k) { return MAGICIAN_LINK_BALL[l + 1][k]; }
     __device__ static constexpr int self_i(int p) { return MAGICIAN_SELFSPH_I[p]; }
@@ -177,6 +179,7 @@ struct SceneS {
     int n_boxes, n_spheres, floor;
     const uint16_t* grid;   // nearest-candidate grid in global memory (grid.cuh) or nullptr = brute force
     float cull_floor;       // max(thr_soft, thr_hard): pair distances above max(this, running min) cannot matter
+    float thr_min;          // min(thr_soft, thr_hard): a pair distance at or below it decides both masks
 };
 
 // exact per-pair formulas (oracle: sd_box / sd_sphere / normal_box / normal_sphere)
@@ -363,7 +366,12 @@ struct CollideResult {
     float self_min;  // only when WANT_SELFMIN
     int arg_sphere, arg_obs;
     float dodq[RB::N];
+    unsigned n_refined, n_pairs;   // broad-phase statistics (field path): spheres swept exactly, pair evaluations
 };
+
+template <class RB, bool WANT_GRAD, bool WANT_SELF>
+__device__ __forceinline__ void collide_state_field(const float (&q)[RB::N], const SceneS& sc, float base_min,
+                                                    CollideResult<RB>& res);   // distance-bound field path, below
 
 // base link (-1) is static: its distance to every obstacle is a per-scene constant that the CTA computes once
 // (kernels.cu: base_min_cta) and passes in.  The floor is exempt for the base in both checks.
@@ -375,6 +383,11 @@ template <class RB, bool WANT_GRAD, bool WANT_SELFMIN, bool GRID, bool WANT_SELF
 __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const SceneS& sc, float base_min,
                                               CollideResult<RB>& res) {
     constexpr int N = RB::N;
+    res.n_refined = 0u; res.n_pairs = 0u;
+    if constexpr (GRID && !WANT_SELFMIN) {           // distance-bound field: exact sweeps only where they can matter
+        collide_state_field<RB, WANT_GRAD, WANT_SELF>(q, sc, base_min, res);
+        return;
+    }
     float o = CBF_INF, soft = base_min, hard = base_min;
     int arg_s = -1;
     float argC[3] = {0.f, 0.f, 0.f};
@@ -529,6 +542,221 @@ __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const Sce
         }
         res.arg_obs = arg_o;
         // n^T (z_j x (C - p_j)) for the joints that move the arg-min link (arm_mindis.py:56-69)
+        const int mask = RB::anc_mask(link);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float rx = __fsub_rn(argC[0], jp[j][0]), ry = __fsub_rn(argC[1], jp[j][1]), rz = __fsub_rn(argC[2], jp[j][2]);
+            const float cx = fmaf(jz[j][1], rz, -__fmul_rn(jz[j][2], ry));
+            const float cy = fmaf(jz[j][2], rx, -__fmul_rn(jz[j][0], rz));
+            const float cz = fmaf(jz[j][0], ry, -__fmul_rn(jz[j][1], rx));
+            const float g = fmaf(nrm[2], cz, fmaf(nrm[1], cy, __fmul_rn(nrm[0], cx)));
+            res.dodq[j] = ((mask >> j) & 1) ? g : 0.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ distance-bound field path (grid.cuh)
+// exact  min_j e_j(c)  over the scene for ONE sphere centre: the candidates of the centre's 5 cm cell (ascending
+// obstacle order, exact per-pair formulas), brute force when the centre is outside the region or its cell overflowed.
+// Same restructuring (1) as sweep_scene: running (min 4 dsq, min max3) and one sqrt at the end.
+__device__ __forceinline__ float scene_min_exact(const SceneS& sc, float cx, float cy, float cz, unsigned& n_pairs) {
+    float D = CBF_INF, M = CBF_INF, E = CBF_INF;
+    const uint16_t* rec = grid::lookup(sc.grid, cx, cy, cz);
+    uint4 r0 = make_uint4(grid::OVERFLOW, 0u, 0u, 0u);
+    if (rec) r0 = __ldg(reinterpret_cast<const uint4*>(rec));
+    if ((r0.x & 0xffffu) != grid::OVERFLOW) {
+        const int nb = r0.x & 0xffffu, nt = nb + (int)(r0.x >> 16);
+        n_pairs += nt;
+        const uint32_t w[3] = {r0.y, r0.z, r0.w};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i < nt) {
+                const int j = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
+                if (i < nb) acc_box(cx, cy, cz, sc.boxes[2 * j], sc.boxes[2 * j + 1], D, M);
+                else acc_sphere(cx, cy, cz, sc.spheres[j], E);
+            }
+        }
+        for (int i = 6; i < nt; ++i) {
+            const int j = __ldg(rec + 2 + i);
+            if (i < nb) acc_box(cx, cy, cz, sc.boxes[2 * j], sc.boxes[2 * j + 1], D, M);
+            else acc_sphere(cx, cy, cz, sc.spheres[j], E);
+        }
+    } else {
+        n_pairs += sc.n_boxes + sc.n_spheres;
+        for (int j = 0; j < sc.n_boxes; ++j) acc_box(cx, cy, cz, sc.boxes[2 * j], sc.boxes[2 * j + 1], D, M);
+        for (int j = 0; j < sc.n_spheres; ++j) acc_sphere(cx, cy, cz, sc.spheres[j], E);
+    }
+    const float e_box = __fadd_rn(__fmul_rn(__fsqrt_rn(D), 0.5f), fminf(M, 0.f));   // D holds 4 * dsq
+    return fminf(e_box, E);
+}
+
+// collide_state on the distance-bound field (sc.grid != nullptr).  Pass A walks the chain once: frames, sphere centres
+// (kept in a per-thread indexed array for pass B), the exact floor candidates in oracle order, the self-collision
+// predicate, and ONE 4-byte field look-up per sphere.  From the look-ups every sphere's obstacle term
+// m_i = min_j e_j(C_i) - r_i is bracketed:  lo_i <= m_i <= hi_i.  Pass B sweeps exactly (scene_min_exact) only the
+// spheres with lo_i <= B, in ascending sphere order, where
+//     B = min(min_k hi_k, max(o_floor, thr_soft, thr_hard))        observation callers (WANT_GRAD)
+//     B = min(min_k hi_k, max(thr_soft, thr_hard))                 mask-only callers
+// Why that is exact.  M* = min_i m_i <= min_k hi_k, so with B = min_k hi_k every sphere that attains M* (ties included)
+// is swept and a skipped sphere is strictly above M*.  When B is the second term, a skipped sphere has
+// m_i > max(o_floor, thresholds): it can neither win or tie the observation minimum (which is <= o_floor) nor move a
+// mask.  Mask-only callers stop even earlier: min_k hi_k <= min(thr_soft, thr_hard) already proves unsafe and not safe.
+// The merge reproduces the oracle's scan order (sphere-major, floor candidate before the obstacle term, strict '<').
+template <class RB, bool WANT_GRAD, bool WANT_SELF>
+__device__ __forceinline__ void collide_state_field(const float (&q)[RB::N], const SceneS& sc, float base_min,
+                                                    CollideResult<RB>& res) {
+    constexpr int N = RB::N, NS = RB::NSPH;
+    constexpr float WIDEN = grid::FIELD_HALF_DIAG + grid::SLACK;
+    const float* __restrict__ field = grid::field_of(sc.grid);
+    float Cx[NS], Cy[NS], Cz[NS];            // indexed dynamically in pass B -> local memory (L1 / L2 resident)
+    float fc[NS];                            // field samples (static indices: registers)
+    float o_fl = CBF_INF, soft_fl = CBF_INF, hard_fl = CBF_INF;
+    int arg_fl = -1;
+    float jz[WANT_GRAD ? N : 1][3], jp[WANT_GRAD ? N : 1][3];
+    float SC[NS][3];
+    bool self_ok = true;
+    unsigned outside = 0u;
+
+    Frame fr[RB::NLINKS];
+    static_for<0, RB::NLINKS>([&](auto lc) {
+        constexpr int L = decltype(lc)::value;
+        constexpr int P = RB::parent(L);
+        float sq = 0.f, cq = 1.f;
+        if constexpr (RB::qidx(L) >= 0) det_sincosf(q[RB::qidx(L)], sq, cq);
+        if constexpr (P < 0) {
+            const Frame base = identity_frame();
+            child_frame<RB, L>(base, true, sq, cq, fr[L]);
+        } else {
+            child_frame<RB, L>(fr[P], false, sq, cq, fr[L]);
+        }
+        if constexpr (WANT_GRAD && RB::qidx(L) >= 0) {
+            constexpr int J = RB::qidx(L);
+            jz[J][0] = fr[L].R[2]; jz[J][1] = fr[L].R[5]; jz[J][2] = fr[L].R[8];
+            jp[J][0] = fr[L].p[0]; jp[J][1] = fr[L].p[1]; jp[J][2] = fr[L].p[2];
+        }
+        constexpr int S0 = RB::sph_begin(L), S1 = RB::sph_end(L), K = S1 - S0;
+        if constexpr (K > 0) {
+            static_for<0, K>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                constexpr int i = S0 + k;
+                constexpr float c0 = RB::sph(i, 0), c1 = RB::sph(i, 1), c2 = RB::sph(i, 2), rad = RB::sph(i, 3);
+                float C[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    C[r] = fmaf(fr[L].R[3 * r + 2], c2, fmaf(fr[L].R[3 * r + 1], c1, fmaf(fr[L].R[3 * r + 0], c0, fr[L].p[r])));
+                SC[i][0] = C[0]; SC[i][1] = C[1]; SC[i][2] = C[2];
+                Cx[i] = C[0]; Cy[i] = C[1]; Cz[i] = C[2];
+                const int cell = grid::field_index(C[0], C[1], C[2]);
+                fc[i] = __ldg(field + max(cell, 0));
+                if (cell < 0) outside |= 1u << i;
+                // floor candidates, exact and in oracle order (same exemptions as collide_state)
+                if (sc.floor) {
+                    if constexpr (L == 0) {
+                        if constexpr (k == 0) {
+                            const float d = RB::LINK0_FLOOR;
+                            if (d < o_fl) { o_fl = d; arg_fl = i; }
+                            hard_fl = fminf(hard_fl, d);
+                        }
+                    } else {
+                        const float d = __fsub_rn(C[2], rad);
+                        if (d < o_fl) { o_fl = d; arg_fl = i; }
+                        soft_fl = fminf(soft_fl, d);
+                        if constexpr (L != 1) hard_fl = fminf(hard_fl, d);
+                    }
+                }
+            });
+            static_for<0, RB::NSELFSPH>([&](auto pc) {
+                constexpr int p = decltype(pc)::value;
+                constexpr int i = RB::self_i(p), j = RB::self_j(p);
+                if constexpr (WANT_SELF && j >= S0 && j < S1) {
+                    const float dx = __fsub_rn(SC[i][0], SC[j][0]), dy = __fsub_rn(SC[i][1], SC[j][1]), dz = __fsub_rn(SC[i][2], SC[j][2]);
+                    const float dsq = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+                    self_ok = self_ok && (dsq > RB::self_x(p));
+                }
+            });
+        }
+    });
+
+    // brackets of the obstacle terms and the pruning bound
+    constexpr int FIRST = RB::sph_begin(0);          // spheres of the static base link are not part of the sweep
+    float best_hi = CBF_INF;
+    static_for<FIRST, NS>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const float hi = ((outside >> i) & 1u) ? CBF_INF : fc[i] + (WIDEN - RB::sph(i, 3));
+        best_hi = fminf(best_hi, hi);
+    });
+    float M = CBF_INF;
+    int argM = -1;
+    unsigned need = 0u;
+    bool decided = false;
+    if constexpr (!WANT_GRAD) decided = best_hi <= sc.thr_min;       // some pair is at or below both thresholds
+    if (decided) {
+        M = best_hi;
+    } else {
+        const float B = WANT_GRAD ? fminf(best_hi, fmaxf(o_fl, sc.cull_floor)) : fminf(best_hi, sc.cull_floor);
+        static_for<FIRST, NS>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const float lo = fc[i] - (WIDEN + RB::sph(i, 3));
+            if (lo <= B || ((outside >> i) & 1u)) need |= 1u << i;
+        });
+    }
+    unsigned n_ref = __popc(need), n_pairs = 0u;
+    while (need) {                                   // ascending sphere order: strict '<' keeps the first minimum
+        const int i = __ffs(need) - 1;
+        need &= need - 1;
+        const float m = __fsub_rn(scene_min_exact(sc, Cx[i], Cy[i], Cz[i], n_pairs), RB::rad_dyn(i));
+        if (m < M) { M = m; argM = i; }
+    }
+    res.n_refined = n_ref; res.n_pairs = n_pairs;
+
+    res.soft_min = fminf(fminf(base_min, soft_fl), M);
+    res.hard_min = fminf(fminf(base_min, hard_fl), M);
+    res.self_ok = self_ok; res.self_min = CBF_INF;
+    // observation minimum: first element of the oracle's scan that attains it
+    const bool obs_wins = (M < o_fl) || (M == o_fl && argM >= 0 && argM < arg_fl);
+    const float o = obs_wins ? M : o_fl;
+    const int arg_s = obs_wins ? argM : arg_fl;
+    res.o = o; res.arg_sphere = arg_s; res.arg_obs = -1;
+#pragma unroll
+    for (int k = 0; k < N; ++k) res.dodq[k] = 0.f;
+    if constexpr (WANT_GRAD) {
+        if (arg_s < 0) return;
+        const float argC[3] = {Cx[arg_s], Cy[arg_s], Cz[arg_s]};
+        const int link = RB::sph_link(arg_s);
+        const float r = RB::rad_dyn(arg_s);
+        const int off = sc.floor ? 1 : 0;
+        float nrm[3] = {0.f, 0.f, 1.f};
+        int arg_o = obs_wins ? -1 : 0;               // the floor is obstacle 0
+        if (arg_o < 0) {
+            const uint16_t* rec = grid::lookup(sc.grid, argC[0], argC[1], argC[2]);
+            int nb = sc.n_boxes, ns = sc.n_spheres;
+            if (rec) {
+                const uint32_t hdr = __ldg(reinterpret_cast<const unsigned int*>(rec));
+                if ((hdr & 0xffffu) == grid::OVERFLOW) rec = nullptr;
+                else { nb = hdr & 0xffffu; ns = hdr >> 16; }
+            }
+            for (int t = 0; t < nb; ++t) {
+                const int j = rec ? (int)__ldg(rec + 2 + t) : t;
+                const float4 b0 = sc.boxes[2 * j], b1 = sc.boxes[2 * j + 1];
+                if (sd_box_exact(argC[0], argC[1], argC[2], b0, b1, r) == o) {
+                    arg_o = off + j;
+                    normal_box(argC[0], argC[1], argC[2], b0, b1, nrm);
+                    break;
+                }
+            }
+            if (arg_o < 0) {
+                for (int t = 0; t < ns; ++t) {
+                    const int j = rec ? (int)__ldg(rec + 2 + nb + t) : t;
+                    const float4 sp = sc.spheres[j];
+                    if (sd_sphere_exact(argC[0], argC[1], argC[2], sp, r) == o) {
+                        arg_o = off + sc.n_boxes + j;
+                        normal_sphere(argC[0], argC[1], argC[2], sp, nrm);
+                        break;
+                    }
+                }
+            }
+        }
+        res.arg_obs = arg_o;
         const int mask = RB::anc_mask(link);
 #pragma unroll
         for (int j = 0; j < N; ++j) {

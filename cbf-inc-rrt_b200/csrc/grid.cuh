@@ -14,6 +14,16 @@
 //
 // With 5 cm cells the BASELINE scenes keep 1.6 (16 obstacles) / 2.2 (64) / 3.6 (256) candidates per cell on average
 // instead of 16 / 64 / 256 pair evaluations per sphere.
+//
+// DISTANCE-BOUND FIELD (second part of the same buffer).  The callers of the sweep never need the per-sphere minima,
+// only  M* = min over the link spheres of (min_j e_j(centre) - radius)  (+ which sphere attains it) and its position
+// relative to the mask thresholds.  f(p) = min_j e_j(p) is 1-Lipschitz, so one stored sample per 2.5 cm cell,
+// F[c] = f(cell centre), bounds it everywhere in the cell:  |f(p) - F[c]| <= half diagonal (+ slack for fp32 rounding).
+// A state therefore needs ONE 4-byte look-up per link sphere to get [lo_i, hi_i] for every sphere, and the exact
+// candidate sweep only for the spheres whose interval can still contain the minimum (lo_i <= min_k hi_k) -- typically
+// 3-6 of 32 -- or can still change a mask.  Skipped spheres are provably strictly above the minimum, so minima,
+// arg-min indices (first index on ties) and booleans stay bit-identical to the brute-force oracle (core.cuh:
+// collide_state_field).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,7 +40,13 @@ constexpr int MAXC = 22;                    // candidates kept per cell
 constexpr int STRIDE = 24;                  // u16 per cell: [n_box_cand, n_sph_cand, cand 0 .. 21]; 48 B = 3 x 16 B
 constexpr int OVERFLOW = 0xffff;            // n_box_cand == OVERFLOW: brute force for this cell
 constexpr float SLACK = 1e-4f;
-constexpr size_t BYTES = (size_t)NCELLS * STRIDE * sizeof(uint16_t);
+constexpr size_t REC_BYTES = (size_t)NCELLS * STRIDE * sizeof(uint16_t);      // 4 088 832, a multiple of 16
+// distance-bound field: 2.5 cm cells over the same region
+constexpr float FCELL = 0.025f, FINV_CELL = 40.0f;
+constexpr int FNX = 88, FNY = 88, FNZ = 88;
+constexpr int FNCELLS = FNX * FNY * FNZ;
+constexpr float FIELD_HALF_DIAG = 0.0216507f;   // 0.5 * sqrt(3) * FCELL, rounded up
+constexpr size_t BYTES = REC_BYTES + (size_t)FNCELLS * sizeof(float);
 
 __device__ __forceinline__ float sd_box_pt(float px, float py, float pz, float4 b0, float4 b1) {
     const float ax = fabsf(px - b0.x) - b0.w, ay = fabsf(py - b0.y) - b1.x, az = fabsf(pz - b0.z) - b1.y;
@@ -39,7 +55,8 @@ __device__ __forceinline__ float sd_box_pt(float px, float py, float pz, float4 
 }
 
 // one thread per cell; boxes / spheres are read from global memory (built once per scene)
-static __global__ void __launch_bounds__(128) build_kernel(const float4* __restrict__ boxes, int n_boxes,
+template <int = 0>
+__global__ void __launch_bounds__(128) build_kernel(const float4* __restrict__ boxes, int n_boxes,
                                                     const float4* __restrict__ spheres, int n_spheres,
                                                     uint16_t* __restrict__ out) {
     const int cell = blockIdx.x * 128 + threadIdx.x;
@@ -88,6 +105,36 @@ static __global__ void __launch_bounds__(128) build_kernel(const float4* __restr
     }
     o[0] = overflow ? (uint16_t)OVERFLOW : (uint16_t)nb;
     o[1] = (uint16_t)ns;
+}
+
+// F[c] = min over ALL obstacles (inside or outside the region) of the signed distance at the centre of field cell c
+template <int = 0>
+__global__ void __launch_bounds__(128) field_kernel(const float4* __restrict__ boxes, int n_boxes,
+                                                    const float4* __restrict__ spheres, int n_spheres,
+                                                    float* __restrict__ out) {
+    const int cell = blockIdx.x * 128 + threadIdx.x;
+    if (cell >= FNCELLS) return;
+    const int ix = cell % FNX, iy = (cell / FNX) % FNY, iz = cell / (FNX * FNY);
+    const float cx = OX + (ix + 0.5f) * FCELL, cy = OY + (iy + 0.5f) * FCELL, cz = OZ + (iz + 0.5f) * FCELL;
+    float f = __int_as_float(0x7f800000);
+    for (int j = 0; j < n_boxes; ++j) f = fminf(f, sd_box_pt(cx, cy, cz, __ldg(boxes + 2 * j), __ldg(boxes + 2 * j + 1)));
+    for (int j = 0; j < n_spheres; ++j) {
+        const float4 s = __ldg(spheres + j);
+        const float dx = cx - s.x, dy = cy - s.y, dz = cz - s.z;
+        f = fminf(f, sqrtf(dx * dx + dy * dy + dz * dz) - s.w);
+    }
+    out[cell] = f;
+}
+
+__device__ __forceinline__ const float* field_of(const uint16_t* __restrict__ g) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(g) + REC_BYTES);
+}
+// index of the field cell of the point, or -1 when the point lies outside the region
+__device__ __forceinline__ int field_index(float px, float py, float pz) {
+    const int ix = __float2int_rd(fmaf(px, FINV_CELL, -OX * FINV_CELL)), iy = __float2int_rd(fmaf(py, FINV_CELL, -OY * FINV_CELL)),
+              iz = __float2int_rd(fmaf(pz, FINV_CELL, -OZ * FINV_CELL));
+    const bool in = ((unsigned)ix < (unsigned)FNX) & ((unsigned)iy < (unsigned)FNY) & ((unsigned)iz < (unsigned)FNZ);
+    return in ? (iz * FNY + iy) * FNX + ix : -1;
 }
 
 // cell record of the point, or nullptr when the point lies outside the region

@@ -43,35 +43,46 @@ Ctx g_ctx[16];
         if ((x) != cudaSuccess) return CBFRRT_ERR_CUDA; \
     } while (0)
 
+template <class T>
+int grow(T*& p, size_t bytes) {
+    if (p) cudaFree(p);
+    p = nullptr;                       // never leave a dangling pointer behind a failed allocation
+    return cudaMalloc(&p, bytes) == cudaSuccess ? CBFRRT_OK : CBFRRT_ERR_CUDA;
+}
+
+// (re)allocates the arena of `device`; every capacity is committed only after its allocations succeeded, so a failed
+// call leaves the context consistent (smaller capacities, null pointers) for the next one
 int ensure(Ctx& c, int device, int64_t rows, int n, int64_t n_boxes, int64_t n_spheres, int64_t n_weights) {
     if (c.device != device) {
+        for (auto& l : c.lane)
+            if (!l.st) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+        if (!c.small) CK(cudaMalloc(&c.small, 4 * (8 + 64 + 8 + 8)));
+        if (!c.grid) CK(cudaMalloc(&c.grid, cbfrrt_grid_bytes()));
         c.device = device;
-        for (auto& l : c.lane) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
-        CK(cudaMalloc(&c.small, 4 * (8 + 64 + 8 + 8)));
-        CK(cudaMalloc(&c.grid, cbfrrt_grid_bytes()));
     }
     if (rows > c.cap_rows) {
+        c.cap_rows = 0;
         for (auto& l : c.lane) {
-            cudaFree(l.q); cudaFree(l.goal); cudaFree(l.datax); cudaFree(l.h); cudaFree(l.J); cudaFree(l.u);
-            cudaFree(l.r); cudaFree(l.safe); cudaFree(l.unsafe);
-            CK(cudaMalloc(&l.q, rows * 8 * 4));
-            CK(cudaMalloc(&l.goal, rows * 8 * 4));
-            CK(cudaMalloc(&l.datax, rows * 17 * 4));
-            CK(cudaMalloc(&l.h, rows * 4));
-            CK(cudaMalloc(&l.J, rows * 8 * 4));
-            CK(cudaMalloc(&l.u, rows * 8 * 4));
-            CK(cudaMalloc(&l.r, rows * 4));
-            CK(cudaMalloc(&l.safe, rows));
-            CK(cudaMalloc(&l.unsafe, rows));
+            if (grow(l.q, rows * 8 * 4) || grow(l.goal, rows * 8 * 4) || grow(l.datax, rows * 17 * 4) ||
+                grow(l.h, rows * 4) || grow(l.J, rows * 8 * 4) || grow(l.u, rows * 8 * 4) || grow(l.r, rows * 4) ||
+                grow(l.safe, rows) || grow(l.unsafe, rows))
+                return CBFRRT_ERR_CUDA;
         }
         c.cap_rows = rows;
     }
     if (n_boxes > c.cap_boxes || n_spheres > c.cap_spheres || n_weights > c.cap_weights) c.resident.clear();
-    if (n_boxes > c.cap_boxes) { cudaFree(c.boxes); CK(cudaMalloc(&c.boxes, n_boxes * 32)); c.cap_boxes = n_boxes; }
-    if (n_spheres > c.cap_spheres) { cudaFree(c.spheres); CK(cudaMalloc(&c.spheres, n_spheres * 16)); c.cap_spheres = n_spheres; }
-    if (n_weights > c.cap_weights) { cudaFree(c.weights); CK(cudaMalloc(&c.weights, n_weights * 4)); c.cap_weights = n_weights; }
+    if (n_boxes > c.cap_boxes) { c.cap_boxes = 0; if (grow(c.boxes, n_boxes * 32)) return CBFRRT_ERR_CUDA; c.cap_boxes = n_boxes; }
+    if (n_spheres > c.cap_spheres) { c.cap_spheres = 0; if (grow(c.spheres, n_spheres * 16)) return CBFRRT_ERR_CUDA; c.cap_spheres = n_spheres; }
+    if (n_weights > c.cap_weights) { c.cap_weights = 0; if (grow(c.weights, n_weights * 4)) return CBFRRT_ERR_CUDA; c.cap_weights = n_weights; }
     return CBFRRT_OK;
 }
+
+// restores the caller's current device on every exit path
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 }  // namespace
 
@@ -87,8 +98,17 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
     if (device < 0 || device >= 16 || B < 0 || !scene || !weights || !q || !goal || !K || !u_lo || !u_hi)
         return CBFRRT_ERR_BAD_SHAPE;
     if (goal_rows != 1 && goal_rows != B) return CBFRRT_ERR_BAD_SHAPE;
+    if (hidden < 4 || hidden > 64 || hidden % 4 || layers < 0 || layers > 8) return CBFRRT_ERR_UNSUPPORTED;
+    // packed weight count of include/cbfrrt.h: a short buffer would make the kernels read past the staged copy
+    const int64_t in_pad = (n + 1 + 3) & ~3;
+    if (n_weights != (int64_t)hidden * in_pad + hidden + (int64_t)layers * (hidden * hidden + hidden) + hidden + 4)
+        return CBFRRT_ERR_BAD_SHAPE;
+    if (scene->n_boxes < 0 || scene->n_spheres < 0 || (scene->n_boxes && !scene->boxes) || (scene->n_spheres && !scene->spheres))
+        return CBFRRT_ERR_BAD_SHAPE;
     if (B == 0) return CBFRRT_OK;
-    CK(cudaSetDevice(device));
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device >= n_dev) return CBFRRT_ERR_BAD_SHAPE;
+    DeviceGuard guard(device);
     Ctx& c = g_ctx[device];
     std::lock_guard<std::mutex> lock(c.mu);
 
@@ -136,7 +156,7 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
         memcpy(w, weights, (size_t)n_weights * 4); w += (size_t)n_weights * 4;
         memcpy(w, small, sizeof small);
     }
-    cbfrrt_scene dsc{scene->n_boxes, scene->n_spheres, scene->floor, 0, c.boxes, c.spheres, nullptr};
+    cbfrrt_scene dsc{scene->n_boxes, scene->n_spheres, scene->floor, 0, c.boxes, c.spheres, nullptr, nullptr};
     if (image != c.resident || (use_grid && !c.resident_grid)) {
         c.resident.clear();
         if (scene->n_boxes) CK(cudaMemcpyAsync(c.boxes, b8.data(), b8.size() * 4, cudaMemcpyHostToDevice, s0));
@@ -155,29 +175,39 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
 
     cbfrrt_cbf_net net{n + 1, hidden, layers, 0, c.weights};
 
+    // an error inside the loop must not leave the other lanes' asynchronous copies into the caller's buffers in flight
+    auto fail = [&](int code) {
+        for (auto& l : c.lane) cudaStreamSynchronize(l.st);
+        return code;
+    };
+#define CKL(x)                                          \
+    do {                                                \
+        if ((x) != cudaSuccess) return fail(CBFRRT_ERR_CUDA); \
+    } while (0)
     int lane_i = 0;
     for (int64_t off = 0; off < B; off += chunk, lane_i = (lane_i + 1) % NSTREAM) {
         Lane& l = c.lane[lane_i];
         const int64_t rows = (B - off < chunk) ? (B - off) : chunk;
-        CK(cudaMemcpyAsync(l.q, q + off * n, rows * n * 4, cudaMemcpyHostToDevice, l.st));
+        CKL(cudaMemcpyAsync(l.q, q + off * n, rows * n * 4, cudaMemcpyHostToDevice, l.st));
         cbfrrt_filter_params fp{c.small, 1, c.small + 8, c.small + 72, c.small + 80, cbf_lambda, relaxation_penalty, nullptr};
         if (goal_rows != 1) {
-            CK(cudaMemcpyAsync(l.goal, goal + off * n, rows * n * 4, cudaMemcpyHostToDevice, l.st));
+            CKL(cudaMemcpyAsync(l.goal, goal + off * n, rows * n * 4, cudaMemcpyHostToDevice, l.st));
             fp.goal = l.goal;
             fp.goal_rows = rows;
         }
         rc = cbfrrt_safety_filter(robot, &dsc, &net, l.q, n, rows, &fp, thr_soft, thr_hard, safe ? l.safe : nullptr,
                                   unsafe ? l.unsafe : nullptr, datax ? l.datax : nullptr, h ? l.h : nullptr,
                                   J ? l.J : nullptr, u ? l.u : nullptr, r ? l.r : nullptr, l.st);
-        if (rc) return rc;
-        if (safe) CK(cudaMemcpyAsync(safe + off, l.safe, rows, cudaMemcpyDeviceToHost, l.st));
-        if (unsafe) CK(cudaMemcpyAsync(unsafe + off, l.unsafe, rows, cudaMemcpyDeviceToHost, l.st));
-        if (datax) CK(cudaMemcpyAsync(datax + off * (2 * n + 1), l.datax, rows * (2 * n + 1) * 4, cudaMemcpyDeviceToHost, l.st));
-        if (h) CK(cudaMemcpyAsync(h + off, l.h, rows * 4, cudaMemcpyDeviceToHost, l.st));
-        if (J) CK(cudaMemcpyAsync(J + off * n, l.J, rows * n * 4, cudaMemcpyDeviceToHost, l.st));
-        if (u) CK(cudaMemcpyAsync(u + off * n, l.u, rows * n * 4, cudaMemcpyDeviceToHost, l.st));
-        if (r) CK(cudaMemcpyAsync(r + off, l.r, rows * 4, cudaMemcpyDeviceToHost, l.st));
+        if (rc) return fail(rc);
+        if (safe) CKL(cudaMemcpyAsync(safe + off, l.safe, rows, cudaMemcpyDeviceToHost, l.st));
+        if (unsafe) CKL(cudaMemcpyAsync(unsafe + off, l.unsafe, rows, cudaMemcpyDeviceToHost, l.st));
+        if (datax) CKL(cudaMemcpyAsync(datax + off * (2 * n + 1), l.datax, rows * (2 * n + 1) * 4, cudaMemcpyDeviceToHost, l.st));
+        if (h) CKL(cudaMemcpyAsync(h + off, l.h, rows * 4, cudaMemcpyDeviceToHost, l.st));
+        if (J) CKL(cudaMemcpyAsync(J + off * n, l.J, rows * n * 4, cudaMemcpyDeviceToHost, l.st));
+        if (u) CKL(cudaMemcpyAsync(u + off * n, l.u, rows * n * 4, cudaMemcpyDeviceToHost, l.st));
+        if (r) CKL(cudaMemcpyAsync(r + off, l.r, rows * 4, cudaMemcpyDeviceToHost, l.st));
     }
-    for (auto& l : c.lane) CK(cudaStreamSynchronize(l.st));
+    for (auto& l : c.lane) CKL(cudaStreamSynchronize(l.st));
     return CBFRRT_OK;
+#undef CKL
 }

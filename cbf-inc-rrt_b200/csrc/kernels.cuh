@@ -61,6 +61,7 @@ struct SceneArgs {
     const float* spheres;
     int n_boxes, n_spheres, floor;
     const uint16_t* grid;
+    unsigned long long* stats;   // optional [4]: states, exactly swept spheres, exact pair evaluations, field look-ups
 };
 struct NetArgs {
     const float* weights;  // packed, NetLayout<>::TOTAL floats
@@ -144,6 +145,7 @@ __device__ __forceinline__ float base_min_cta(const Smem& s, const SceneS& sc) {
 __device__ __forceinline__ SceneS scene_view(const Smem& s, const SceneArgs& sc, float thr_soft, float thr_hard) {
     SceneS v;
     v.cull_floor = fmaxf(thr_soft, thr_hard);
+    v.thr_min = fminf(thr_soft, thr_hard);
     v.boxes = reinterpret_cast<const float4*>(s.boxes);
     v.spheres = reinterpret_cast<const float4*>(s.spheres);
     v.n_boxes = sc.n_boxes; v.n_spheres = sc.n_spheres; v.floor = sc.floor;
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) collide_kernel(Scene
     stage<RB::N>(s, sc, nullptr, 0);
     const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB>(s, sv);
+    unsigned long long n_states = 0, n_ref = 0, n_pairs = 0;
     for (long long b = (long long)blockIdx.x * NT + threadIdx.x; b < B; b += (long long)gridDim.x * NT) {
         float qq[RB::N];
 #pragma unroll
@@ -218,6 +221,13 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) collide_kernel(Scene
         CollideResult<RB> r;
         collide_state<RB, WANT_GRAD, WANT_SELFMIN, GRID>(qq, sv, base_min, r);
         write_collide<RB>(out, b, qq, r, thr_soft, thr_hard);
+        n_states += 1; n_ref += r.n_refined; n_pairs += r.n_pairs;
+    }
+    if (sc.stats) {   // broad-phase statistics for the roofline accounting (bench.py); off (nullptr) in every other call
+        atomicAdd(sc.stats + 0, n_states);
+        atomicAdd(sc.stats + 1, n_ref);
+        atomicAdd(sc.stats + 2, n_pairs);
+        if (GRID && !WANT_SELFMIN) atomicAdd(sc.stats + 3, n_states * (unsigned long long)(RB::NSPH - RB::sph_begin(0)));
     }
 }
 
@@ -232,14 +242,46 @@ __device__ __forceinline__ void load_goal(const NetArgs& net, long long b, float
 // fused all-gather epilogue: peer-mapped replicas of the [G] mask and [G, n] controls (include/cbfrrt.h)
 struct PeerOut {
     int n;
+    int multicast;      // 1: valid[0] / u[0] are NVSwitch multicast addresses -> multimem.st (PTX ISA: multimem
+                        //    addresses may only be accessed by multimem.*); rows of a warp are 32 consecutive, aligned rows
     long long row_offset;
     uint8_t* valid[CBFRRT_MAX_PEERS];
     float* u[CBFRRT_MAX_PEERS];
 };
 
+// multimem.st: one store, replicated by the switch into every rank's replica (NVLS).  ptxas lowers it to
+// STG.E.STRONG.SYS on sm_100a -- the multicast happens in the fabric, by address -- so it shows as `multimem.st` in the
+// PTX only (tests/test_cabi_cpu.py compiles this header to PTX and checks).
+__device__ __forceinline__ void multimem_st_f32(float* addr, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <int N>
 __device__ __forceinline__ void write_peers(const PeerOut& po, long long b, bool safe, const float (&u)[N]) {
     const long long g = po.row_offset + b;
+    if (po.multicast) {
+        // mask bytes: multimem.st has no sub-word form, so the 32 rows of the warp are packed into 8 words (4 mask bytes
+        // each) and lanes 0..7 store one word each.  The ABI guarantees full, 32-row-aligned warps in this mode.
+        const unsigned bal = __ballot_sync(0xffffffffu, safe);
+        const int lane = threadIdx.x & 31;
+        if (lane < 8) {
+            const unsigned nib = (bal >> (4 * lane)) & 0xfu;
+            const unsigned word = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+            multimem_st_f32(reinterpret_cast<float*>(po.valid[0] + (g - lane) + 4 * lane), __uint_as_float(word));
+        }
+        float* dst = po.u[0] + g * N;
+        if constexpr (N % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < N; k += 4) multimem_st_v4(dst + k, u[k], u[k + 1], u[k + 2], u[k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) multimem_st_f32(dst + k, u[k]);
+        }
+        return;
+    }
     for (int p = 0; p < po.n; ++p) {
         po.valid[p][g] = safe;
         float* dst = po.u[p] + g * N;
@@ -281,7 +323,7 @@ __global__ void __launch_bounds__(NT) filter_kernel(NetArgs net, const float* __
     extern __shared__ __align__(16) float smem_raw[];
     using LY = NetLayout<N + 1, H, L>;
     const Smem s = carve(smem_raw, 0, 0, LY::TOTAL, ParamLayout<N>::TOTAL);
-    SceneArgs none{nullptr, nullptr, 0, 0, 0, nullptr};
+    SceneArgs none{nullptr, nullptr, 0, 0, 0, nullptr, nullptr};
     stage<N>(s, none, &net, LY::TOTAL);
     float* scr = s.scratch + threadIdx.x;
     for (long long b = (long long)blockIdx.x * NT + threadIdx.x; b < B; b += (long long)gridDim.x * NT) {
@@ -459,7 +501,65 @@ struct RolloutArgs {
     int stuck_lag, stuck_after;
     float stuck_eps;
     int keep_going;
+    int stuck_mode;   // 0: single steer (tsa.py:263), 1: batched steer (batch_tsa.py:225-229), see include/cbfrrt.h
 };
+
+// What happens to a trajectory after the Euler step t produced qn (unsafe = hard collision test of qn).  Shared by the
+// FP32-FMA and the tcgen05 rollout kernels.  Returns true when the trajectory is finished.
+//   stuck_mode 0 (tsa.py:251-266): an unsafe qn is not appended (ok = 0, stop unless keep_going); otherwise q <- qn is
+//     appended and the stuck test compares the states appended at steps t and t - stuck_lag when t > stuck_after.
+//   stuck_mode 1 (batch_tsa.py:225-229): the stuck test runs BEFORE the append, on the list as it stands (more than
+//     stuck_after states stored: last vs the one stuck_lag before it); stuck OR unsafe clears ok and the row stops
+//     appending for good, but x_current keeps integrating (q <- qn always; q_final is that running state).  Without
+//     keep_going the row stops at its death instead.
+template <int N>
+__device__ __forceinline__ bool rollout_after_step(const RolloutArgs& ra, int t, bool unsafe, float (&q)[N],
+                                                   const float (&qn)[N], float* __restrict__ tr, bool& ok, bool& dead,
+                                                   int& done) {
+    if (ra.stuck_mode == 1) {
+        if (!dead) {
+            bool stuck = false;
+            if (ra.stuck_lag > 0 && done > ra.stuck_after) {
+                const float* a = tr + (done - 1) * N;
+                const float* b = tr + (done - 1 - ra.stuck_lag) * N;
+                float dsq = 0.f;
+#pragma unroll
+                for (int k = 0; k < N; ++k) { const float d = __fsub_rn(a[k], b[k]); dsq = fmaf(d, d, dsq); }
+                stuck = __fsqrt_rn(dsq) < ra.stuck_eps;
+            }
+            if (stuck || unsafe) { ok = false; dead = true; }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) q[k] = qn[k];
+        if (!dead) {
+            if (tr) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) tr[done * N + k] = q[k];
+            }
+            ++done;
+        }
+        return dead && !ra.keep_going;
+    }
+    if (unsafe) {  // tsa.py:251-253: colliding state is not appended
+        ok = false;
+        if (!ra.keep_going) return true;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) q[k] = qn[k];
+    if (tr) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) tr[t * N + k] = q[k];
+    }
+    done = t + 1;
+    if (ra.stuck_lag > 0 && t > ra.stuck_after) {  // tsa.py:263
+        const float* old = tr + (t - ra.stuck_lag) * N;
+        float dsq = 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { const float d = __fsub_rn(q[k], old[k]); dsq = fmaf(d, d, dsq); }
+        if (__fsqrt_rn(dsq) < ra.stuck_eps) return true;
+    }
+    return false;
+}
 
 // ------------------------------------------------------------------ tensor-core (tcgen05) variants
 // Same contracts as filter_kernel / safety_kernel; the MLP of every 128-state tile runs as TF32x3 GEMMs on the
@@ -488,7 +588,7 @@ __global__ void __launch_bounds__(4 * tc::M_TILE, 1) filter_kernel_tc(NetArgs ne
     constexpr int GG = 4, NTC = GG * tc::M_TILE;
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, 0, 0, tc::Layout<L, GG>::TOTAL, ParamLayout<N>::TOTAL);
-    SceneArgs none{nullptr, nullptr, 0, 0, 0, nullptr};
+    SceneArgs none{nullptr, nullptr, 0, 0, 0, nullptr, nullptr};
     stage<N, NTC>(s, none, &net, 0);
     tc::Ctx<L, GG> c;
     tc::setup<N + 1, L, GG>(c, s.weights, net.weights);
@@ -512,12 +612,12 @@ __global__ void __launch_bounds__(4 * tc::M_TILE, 1) filter_kernel_tc(NetArgs ne
     tc::teardown<L, GG>(c);
 }
 
-template <class RB, int L, bool GRID>
-__global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) safety_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q,
+template <class RB, int L, bool GRID, int GG>
+__global__ void __launch_bounds__(GG * tc::M_TILE, 1) safety_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q,
                                                            long long q_stride, long long B, float thr_soft, float thr_hard,
                                                            CollideOutPtrs cout, FilterOutPtrs fout, PeerOut po) {
     constexpr int N = RB::N;
-    constexpr int GG = tc_groups(GRID), NTC = GG * tc::M_TILE;
+    constexpr int NTC = GG * tc::M_TILE;
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L, GG>::TOTAL, ParamLayout<N>::TOTAL);
     stage<N, NTC>(s, sc, &net, 0);
@@ -585,7 +685,7 @@ __global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) rollout_kerne
 #pragma unroll
             for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
         }
-        bool ok = true, finished = !active;
+        bool ok = true, finished = !active, dead = false;
         int done = 0;
         float* tr = (traj && active) ? traj + b * (long long)ra.steps * N : nullptr;
         for (int t = 0; t < ra.steps; ++t) {
@@ -611,24 +711,7 @@ __global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) rollout_kerne
 #pragma unroll
                 for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
             }
-            if (cr.hard_min <= thr_hard) {  // tsa.py:251-253: colliding state is not appended
-                ok = false;
-                if (!ra.keep_going) { finished = true; continue; }
-            }
-#pragma unroll
-            for (int k = 0; k < N; ++k) q[k] = qn[k];
-            if (tr) {
-#pragma unroll
-                for (int k = 0; k < N; ++k) tr[t * N + k] = q[k];
-            }
-            done = t + 1;
-            if (ra.stuck_lag > 0 && t > ra.stuck_after) {  // tsa.py:263
-                const float* old = tr + (t - ra.stuck_lag) * N;
-                float dsq = 0.f;
-#pragma unroll
-                for (int k = 0; k < N; ++k) { const float d = __fsub_rn(q[k], old[k]); dsq = fmaf(d, d, dsq); }
-                if (__fsqrt_rn(dsq) < ra.stuck_eps) finished = true;
-            }
+            if (rollout_after_step<N>(ra, t, cr.hard_min <= thr_hard, q, qn, tr, ok, dead, done)) finished = true;
         }
         if (active) {
 #pragma unroll
@@ -647,11 +730,13 @@ __global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) rollout_kerne
 // points of one edge, so a warp's states are geometrically coherent.  first_bad must be preset to EDGE_SENTINEL
 // (edge_var_init), the reduction is a global atomicMin, edge_var_finish writes valid / maps the sentinel.
 constexpr int EDGE_SENTINEL = 0x7fffffff;
-static __global__ void edge_var_init(int* __restrict__ first_bad, long long E) {
+template <int = 0>
+__global__ void edge_var_init(int* __restrict__ first_bad, long long E) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x)
         first_bad[e] = EDGE_SENTINEL;
 }
-static __global__ void edge_var_finish(int* __restrict__ first_bad, uint8_t* __restrict__ valid, long long E) {
+template <int = 0>
+__global__ void edge_var_finish(int* __restrict__ first_bad, uint8_t* __restrict__ valid, long long E) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
         const int bad = first_bad[e];
         valid[e] = bad == EDGE_SENTINEL;
@@ -730,7 +815,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
         o = cr.o;
 #pragma unroll
         for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
-        bool ok = true;
+        bool ok = true, dead = false;
         int done = 0;
         float* tr = traj ? traj + b * (long long)ra.steps * N : nullptr;
         for (int t = 0; t < ra.steps; ++t) {
@@ -754,24 +839,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
                 // closed_loop_dynamics(update_observation=False) leaves o / do_dq at zero (arm_dynamics.py:491-493);
                 // they are not read before the next refresh, the controller only runs at t % ctrl_every == 0.
             }
-            if (cr.hard_min <= thr_hard) {  // tsa.py:251-253: colliding state is not appended
-                ok = false;
-                if (!ra.keep_going) break;
-            }
-#pragma unroll
-            for (int k = 0; k < N; ++k) q[k] = qn[k];
-            if (tr) {
-#pragma unroll
-                for (int k = 0; k < N; ++k) tr[t * N + k] = q[k];
-            }
-            done = t + 1;
-            if (ra.stuck_lag > 0 && t > ra.stuck_after) {  // tsa.py:263
-                const float* old = tr + (t - ra.stuck_lag) * N;
-                float dsq = 0.f;
-#pragma unroll
-                for (int k = 0; k < N; ++k) { const float d = __fsub_rn(q[k], old[k]); dsq = fmaf(d, d, dsq); }
-                if (__fsqrt_rn(dsq) < ra.stuck_eps) break;
-            }
+            if (rollout_after_step<N>(ra, t, cr.hard_min <= thr_hard, q, qn, tr, ok, dead, done)) break;
         }
 #pragma unroll
         for (int k = 0; k < N; ++k) q_final[b * N + k] = q[k];
@@ -804,7 +872,8 @@ __global__ void __launch_bounds__(256) sample_kernel(uint32_t seed, unsigned lon
 }
 
 // FP32 FMA throughput probe (roofline denominator; see include/cbfrrt.h)
-static __global__ void fma_probe_kernel(int iters, float* sink) {
+template <int = 0>
+__global__ void fma_probe_kernel(int iters, float* sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
           a6 = a0 + 6.f, a7 = a0 + 7.f;
     const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
@@ -821,28 +890,47 @@ static __global__ void fma_probe_kernel(int iters, float* sink) {
 extern std::atomic<long long> g_launches;
 extern std::atomic<int> g_last_cuda;
 
-inline int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
 }
 
-// resident CTAs per SM for (kernel, dynamic smem): the attribute / occupancy queries cost ~10 us of host time, so
-// they are made once per distinct configuration
+// SM count of the CURRENT device (one process may drive several GPUs through cbfrrt_safety_filter_host)
+inline int num_sms() {
+    static std::atomic<int> sms[64];
+    const int dev = current_device() & 63;
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+        sms[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// resident CTAs per SM for (device, kernel, dynamic smem): the attribute / occupancy queries cost ~10 us of host time,
+// so they are made once per distinct configuration.  The opt-in to > 48 KB of dynamic shared memory is a per-device
+// function attribute, hence the device in the key.
+struct CfgKey {
+    int dev;
+    const void* kern;
+    size_t smem;
+    bool operator<(const CfgKey& o) const {
+        if (dev != o.dev) return dev < o.dev;
+        if (kern != o.kern) return kern < o.kern;
+        return smem < o.smem;
+    }
+};
 extern std::mutex g_cfg_mu;
-extern std::map<std::pair<const void*, size_t>, int> g_cfg;
+extern std::map<CfgKey, int> g_cfg;
 
 template <class Kern>
 static int grid_for(Kern kern, size_t smem, long long tiles) {
     int per_sm = 0;
     {
         std::lock_guard<std::mutex> lock(g_cfg_mu);
-        const auto key = std::make_pair(reinterpret_cast<const void*>(kern), smem);
+        const CfgKey key{current_device(), reinterpret_cast<const void*>(kern), smem};
         auto it = g_cfg.find(key);
         if (it != g_cfg.end()) per_sm = it->second;
         else {
@@ -866,7 +954,7 @@ template <class Kern>
 static int grid_for_tc(Kern kern, size_t smem, long long rows, int groups) {
     {
         std::lock_guard<std::mutex> lock(g_cfg_mu);
-        const auto key = std::make_pair(reinterpret_cast<const void*>(kern), smem);
+        const CfgKey key{current_device(), reinterpret_cast<const void*>(kern), smem};
         if (g_cfg.find(key) == g_cfg.end()) {
             if (smem > 48 * 1024 &&
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
@@ -903,7 +991,7 @@ inline int check_scene(const cbfrrt_scene* sc, SceneArgs& a) {
     static const int grid_min = [] { const char* e = getenv("CBFRRT_GRID_MIN"); return e ? atoi(e) : GRID_MIN_OBSTACLES; }();
     const bool use_grid = sc->grid && sc->n_boxes + sc->n_spheres >= grid_min;
     a = SceneArgs{sc->boxes, sc->spheres, sc->n_boxes, sc->n_spheres, sc->floor ? 1 : 0,
-                  use_grid ? static_cast<const uint16_t*>(sc->grid) : nullptr};
+                  use_grid ? static_cast<const uint16_t*>(sc->grid) : nullptr, static_cast<unsigned long long*>(sc->stats)};
     return CBFRRT_OK;
 }
 
@@ -952,16 +1040,12 @@ static int launch_collide(const SceneArgs& sc, const float* q, long long qs, lon
 // set-up (two weight tilings, TMEM allocation) costs more than it saves there, so they take the FP32-FMA kernels
 // (measured on cfg0, 4096 rows: 59 us vs 75 us).  CBFRRT_MLP=tc forces the tensor-core kernels for any size.
 constexpr long long SMALL_BATCH = 16384;
-// CBFRRT_MLP=fma selects the FP32-FMA MLP kernels (A/B comparisons); default is the tcgen05 path
-inline bool use_tc() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("CBFRRT_MLP");
-        v = (e && e[0] == 'f') ? 0 : ((e && e[0] == 't') ? 2 : 1);
-    }
-    return v >= 1;
-}
-inline bool force_tc() { use_tc(); const char* e = getenv("CBFRRT_MLP"); return e && e[0] == 't'; }
+// MLP path: CBFRRT_MLP_AUTO (tcgen05 kernels above SMALL_BATCH rows, FP32-FMA kernels below), _FMA or _TC for every
+// size.  Set through cbfrrt_set_mlp_path() (include/cbfrrt.h); the environment variable CBFRRT_MLP=fma|tc only gives
+// the initial value.  Read at every launch, so one process can exercise both paths (the parity tests do).
+extern std::atomic<int> g_mlp_path;
+inline bool use_tc() { return g_mlp_path.load(std::memory_order_relaxed) != CBFRRT_MLP_FMA; }
+inline bool force_tc() { return g_mlp_path.load(std::memory_order_relaxed) == CBFRRT_MLP_TC; }
 
 template <int N>
 static int launch_filter(const NetArgs& net, const float* datax, long long B, const FilterOutPtrs& out, cudaStream_t st) {
@@ -985,12 +1069,13 @@ static int launch_filter(const NetArgs& net, const float* datax, long long B, co
 template <class RB>
 static int launch_safety(const SceneArgs& sc, const NetArgs& net, const float* q, long long qs, long long B, float ts,
                          float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, const PeerOut& po, cudaStream_t st) {
-    const int gg = tc_groups(sc.grid != nullptr);
-    const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, sc.grid ? tc::Layout<2, 3>::TOTAL : tc::Layout<2, 4>::TOTAL,
+    static const int gg_grid = [] { const char* e = getenv("CBFRRT_TC_GROUPS_GRID"); return (e && atoi(e) == 4) ? 4 : 3; }();
+    const int gg = sc.grid ? gg_grid : 4;
+    const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, gg == 3 ? tc::Layout<2, 3>::TOTAL : tc::Layout<2, 4>::TOTAL,
                                            ParamLayout<RB::N>::TOTAL, 0);
     if (use_tc() && (B > SMALL_BATCH || force_tc()) && smem_tc <= TC_SMEM_MAX) {
         const size_t smem = smem_tc;
-        auto k = sc.grid ? safety_kernel_tc<RB, 2, true> : safety_kernel_tc<RB, 2, false>;
+        auto k = sc.grid ? (gg == 3 ? safety_kernel_tc<RB, 2, true, 3> : safety_kernel_tc<RB, 2, true, 4>) : safety_kernel_tc<RB, 2, false, 4>;
         const int grid = grid_for_tc(k, smem, B, gg);
         if (grid < 0) return CBFRRT_ERR_CUDA;
         k<<<grid, gg * tc::M_TILE, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo, po);
@@ -1020,7 +1105,7 @@ static int launch_edges_var(const SceneArgs& sc, const float* qf, const float* q
                             int K_all, long long P, float ts, float th, uint8_t* valid, int* first_bad, cudaStream_t st) {
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
     const int eg = (int)((E + 255) / 256 < 1184 ? (E + 255) / 256 : 1184);
-    edge_var_init<<<eg, 256, 0, st>>>(first_bad, E);
+    edge_var_init<0><<<eg, 256, 0, st>>>(first_bad, E);
     if (finish_launch()) return CBFRRT_ERR_CUDA;
     if (P > 0) {
         auto k = sc.grid ? edge_var_kernel<RB, true> : edge_var_kernel<RB, false>;
@@ -1029,7 +1114,7 @@ static int launch_edges_var(const SceneArgs& sc, const float* qf, const float* q
         k<<<grid, NT, smem, st>>>(sc, qf, qt, E, off, K_all, P, ts, th, first_bad);
         if (finish_launch()) return CBFRRT_ERR_CUDA;
     }
-    edge_var_finish<<<eg, 256, 0, st>>>(first_bad, valid, E);
+    edge_var_finish<0><<<eg, 256, 0, st>>>(first_bad, valid, E);
     return finish_launch();
 }
 

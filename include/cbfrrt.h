@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CBFRRT_ABI_VERSION 1
+#define CBFRRT_ABI_VERSION 2
 
 typedef enum {
     CBFRRT_OK = 0,
@@ -64,6 +64,9 @@ typedef struct {
     const float *spheres; /* device, [n_spheres, 4], 16-byte aligned */
     const void *grid;     /* optional device buffer of cbfrrt_grid_bytes() bytes filled by cbfrrt_grid_build for
                              THIS scene (exact broad phase: same results, far fewer pair tests); NULL = brute force */
+    void *stats;          /* optional device uint64[4], ACCUMULATED by cbfrrt_collide only (NULL = off): states,
+                             exactly swept link spheres, exact sphere-obstacle pair evaluations, field look-ups --
+                             the measured work of the broad phase, for roofline accounting */
 } cbfrrt_scene;
 
 typedef struct {
@@ -100,6 +103,15 @@ typedef struct {
     int32_t keep_going;   /* 0: steer semantics (stop at the first unsafe state, tsa.py:251-253).
                              1: fixed-work variant of BASELINE config 4 ("mask instead of early stop"): an unsafe
                                 state clears `alive` but the trajectory is simulated for all `steps` steps */
+    int32_t stuck_mode;   /* 0: single steer (tsa.py:251-266): the new state is appended, then the stuck test compares
+                                the states appended at steps t and t - stuck_lag when t > stuck_after; a stuck row stops
+                                with alive = 1.
+                             1: batched steer (batch_tsa.py:225-229): the stuck test runs BEFORE the append on the list as
+                                it stands (more than stuck_after states stored: the last one against the one stuck_lag
+                                before it; the reference uses lag 9, after 10, eps 3e-2); stuck OR unsafe clears `alive`
+                                and the row never appends again, while its state keeps integrating when keep_going = 1
+                                (q_final = that running state, as the reference returns x_current) or stops at its
+                                death when keep_going = 0. */
 } cbfrrt_rollout_params;
 
 /* ---- library info ------------------------------------------------------------------------------------- */
@@ -108,6 +120,16 @@ const char *cbfrrt_status_string(int status);
 int cbfrrt_last_cuda_error(void);
 /* n (dof), number of pybullet links (FK rows), number of link spheres */
 int cbfrrt_robot_info(int robot, int32_t *n, int32_t *n_links, int32_t *n_spheres);
+
+/* ---- barrier-network path selection -----------------------------------------------------------------------
+ * The MLP of cbf_filter / safety_filter / rollout has two implementations with the same contract (1e-5 against the
+ * oracle): tcgen05 tensor-core kernels (TF32x3) and FP32-FMA kernels.  AUTO (default) takes the tensor-core kernels
+ * above 16 384 rows and the FP32-FMA kernels below (launch-latency bound sizes).  FMA / TC force one path for every
+ * size (A/B measurements, and the parity tests, which cover both).  Process-wide; initial value from the environment
+ * variable CBFRRT_MLP=fma|tc.  Returns CBFRRT_ERR_BAD_SHAPE for an unknown value. */
+typedef enum { CBFRRT_MLP_AUTO = 0, CBFRRT_MLP_FMA = 1, CBFRRT_MLP_TC = 2 } cbfrrt_mlp_path;
+int cbfrrt_set_mlp_path(int path);
+int cbfrrt_get_mlp_path(void);
 
 /* ---- scene acceleration structure (built once per ArmEnv.reset_env, environment/arm_env.py:63) --------------
  * Nearest-candidate grid over the arm's workspace: per 5 cm cell, the obstacles that can be the closest one for
@@ -194,13 +216,18 @@ int cbfrrt_safety_filter(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_
  * rank's buffers through NVLink peer mappings (torch symmetric memory / cudaIpc / cuMem), so the transfer overlaps
  * the sweep tile by tile and no collective is launched.  The caller synchronises the ranks afterwards (a barrier),
  * exactly as after an all-gather.  valid[p] / u[p] must be mapped in this process for p < n_peers (the rank's
- * own buffer included).  On NVSwitch systems pass n_peers = 1 with the buffers' MULTICAST addresses (cuMulticast /
- * torch symmetric memory multicast_ptr): one store per row is then replicated to every rank by the switch (NVLS),
- * 1/N of the outbound traffic of the per-peer form (measured: 0.44 vs 0.51 ms per step at 8 GPUs). */
+ * own buffer included).  On NVSwitch systems pass n_peers = 1, multicast = 1 with the buffers' MULTICAST addresses
+ * (cuMulticast / torch symmetric memory multicast_ptr): one multimem.st per row is then replicated to every rank by
+ * the switch (NVLS), 1/N of the outbound traffic of the per-peer form (measured: 0.44 vs 0.51 ms per step at 8 GPUs).
+ * Ordering contract for a caller that reuses the replicas step after step: synchronise the ranks BEFORE the launch too
+ * (every rank has finished reading the previous step's rows), or alternate between two sets of buffers. */
 #define CBFRRT_MAX_PEERS 8
 typedef struct {
     int32_t n_peers;
-    int32_t _pad;
+    int32_t multicast;                  /* 1: n_peers == 1 and valid[0] / u[0] are MULTICAST addresses; the kernel then uses
+                                           multimem.st (the only access PTX allows on a multimem address), packing the mask
+                                           bytes of 32 consecutive rows into words: B and row_offset must be multiples of 128.
+                                           0: ordinary (peer-mapped) pointers, plain stores */
     int64_t row_offset;                 /* global index of this rank's first row */
     uint8_t *valid[CBFRRT_MAX_PEERS];   /* each: device u8 [G]     */
     float *u[CBFRRT_MAX_PEERS];         /* each: device f32 [G, n] */

@@ -105,6 +105,25 @@ def cbf_filter(n, weights, hidden, layers, datax, goal, K, u_lo, u_hi, lam, pena
     return out
 
 
+def cbf_filter_f64(n, weights, hidden, layers, datax, goal, K, u_lo, u_hi, lam, penalty, u_ref=None):
+    """float64 end-to-end truth of the filter stage + what a tolerance statement needs (oracle_cbf_filter_f64):
+    h, J, u, r (float64), margin = distance to the nearest ReLU kink in pre-activation units, kappa_c / kappa_a =
+    first-order conditioning of the QP solution w.r.t. c = lambda h and a = J, regime (0 inactive / 1 tight / 2 relaxed)."""
+    datax = _f(datax)
+    B = datax.shape[0]
+    goal = _f(goal).reshape(-1, n)
+    u_ref = _f(u_ref) if u_ref is not None else None
+    w, K, u_lo, u_hi = _f(weights), _f(K), _f(u_lo), _f(u_hi)
+    out = dict(h=np.empty(B), J=np.empty((B, n)), u=np.empty((B, n)), r=np.empty(B), margin=np.empty(B),
+               kappa_c=np.empty(B), kappa_a=np.empty(B), regime=np.empty(B, np.int32))
+    rc = lib().oracle_cbf_filter_f64(n, hidden, layers, _p(w), _p(datax), C.c_long(B), _p(goal), C.c_long(goal.shape[0]),
+                                     _p(u_ref), _p(K), _p(u_lo), _p(u_hi), C.c_float(lam), C.c_float(penalty),
+                                     _p(out["h"]), _p(out["J"]), _p(out["u"]), _p(out["r"]), _p(out["margin"]),
+                                     _p(out["kappa_c"]), _p(out["kappa_a"]), _p(out["regime"]))
+    assert rc == 0
+    return out
+
+
 def qp(a, c, u_ref, u_lo, u_hi, penalty):
     a, c, u_ref, u_lo, u_hi = _f(a), _f(c).reshape(-1), _f(u_ref), _f(u_lo), _f(u_hi)
     B, n = a.shape
@@ -230,7 +249,8 @@ def radius_mask(queries, points, radius):
 
 
 def rollout(robot, q0, goal, steps, ctrl_every, dt, boxes, spheres, floor, weights, hidden, layers, K, u_lo, u_hi,
-            thr_soft, thr_hard, lam, penalty, stuck_lag=0, stuck_after=10, stuck_eps=0.1, want_traj=False, keep_going=False):
+            thr_soft, thr_hard, lam, penalty, stuck_lag=0, stuck_after=10, stuck_eps=0.1, want_traj=False, keep_going=False,
+            stuck_mode=0):
     q0 = _f(q0)
     n, L, _ = robot_info(robot)
     T = q0.shape[0]
@@ -246,7 +266,7 @@ def rollout(robot, q0, goal, steps, ctrl_every, dt, boxes, spheres, floor, weigh
                               int(ctrl_every), C.c_float(dt), int(stuck_lag), int(stuck_after), C.c_float(stuck_eps),
                               int(bool(keep_going)), _p(K), _p(u_lo), _p(u_hi), C.c_float(thr_soft),
                               C.c_float(thr_hard), C.c_float(lam), C.c_float(penalty), _p(qf), _p(alive), _p(done),
-                              _p(traj))
+                              _p(traj), int(stuck_mode))
     assert rc == 0
     return qf, alive, done, traj
 

@@ -633,7 +633,7 @@ typedef struct {
     const float *q, *q2, *goal, *K, *u_lo, *u_hi, *datax_in, *u_ref;
     long q_stride, goal_rows;
     float thr_soft, thr_hard, lam, penalty, dt;
-    int Kint, steps, ctrl_every, stuck_lag, stuck_after, keep_going;
+    int Kint, steps, ctrl_every, stuck_lag, stuck_after, keep_going, stuck_mode;
     const int *Kvar;
     float stuck_eps, *traj;
     uint8_t *safe, *unsafe, *alive;
@@ -743,6 +743,106 @@ API int oracle_cbf_filter(int n, int hidden, int layers, const float *weights, c
     c.n = n; c.net = (Net){n + 1, hidden, layers, weights}; c.datax_in = datax; c.goal = goal; c.goal_rows = goal_rows;
     c.u_ref = u_ref; c.K = K; c.u_lo = u_lo; c.u_hi = u_hi; c.lam = lam; c.penalty = penalty; c.h = h; c.J = J; c.u = u; c.r = r;
     par_for(B, filter_range, &c);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ float64 END-TO-END truth of the filter stage
+ * datax (the float32 inputs, taken as exact) -> h, J, u, r with the network, its reverse-mode Jacobian, J = Jh_q +
+ * Jh_o do/dq, the nominal control and the exact KKT solution ALL in double.  Besides the values it returns what a
+ * tolerance statement needs:
+ *   margin [B]   smallest |pre-activation| over all hidden neurons: the distance (in pre-activation units) to the
+ *                nearest ReLU kink.  J is DISCONTINUOUS across a kink, so two correct fp32 evaluations whose
+ *                pre-activations differ by more than `margin` may return Jacobians of different linear pieces;
+ *   kappa_c, kappa_a [B]   first-order conditioning of the QP solution:  |du|_inf <= kappa_c |dc| + kappa_a |da|_inf
+ *                for perturbations of c = lambda h and a = J on the current active set (F = unclipped coordinates,
+ *                S = |a_F|^2):  inactive (mu = 0): 0, 0;  relaxed (mu = p): 0, p/2;
+ *                tight: kappa_c = |a_F|_inf / S,  kappa_a = (|a_F|_inf / S)(sum_F |t_k| + sum_C |b_k| + mu |a_F|_1) + mu/2;
+ *   regime [B]   0 inactive, 1 tight, 2 relaxed.
+ * (neural_mindis_cbf_controller.py:71-102, clf_controller.py:82-139,461-535, arm_dynamics.py:124-161) */
+typedef struct {
+    int n; Net net; const float *datax, *goal, *u_ref, *K, *u_lo, *u_hi; long goal_rows; double lam, p;
+    double *h, *J, *u, *r, *margin, *kc, *ka; int *regime;
+} Ctx64;
+static void filter64_range(long lo_, long hi_, void *pp) {
+    Ctx64 *c = (Ctx64 *)pp; const int n = c->n, H = c->net.hidden, L = c->net.layers, IN = n + 1, INP = (IN + 3) & ~3;
+    const float *w = c->net.w;
+    for (long b = lo_; b < hi_; ++b) {
+        const float *d = c->datax + b * (2 * n + 1);
+        double act[MAXL + 1][MAXH], margin = INFINITY;
+        const float *W = w, *bi = w + H * INP;
+        for (int j = 0; j < H; ++j) {
+            double a = bi[j];
+            for (int k = 0; k < IN; ++k) a += (double)W[j * INP + k] * (double)d[k];
+            if (fabs(a) < margin) margin = fabs(a);
+            act[0][j] = a > 0. ? a : 0.;
+        }
+        const float *wl = w + H * INP + H;
+        for (int l = 0; l < L; ++l) {
+            const float *Wl = wl + (size_t)l * (H * H + H), *bl = Wl + H * H;
+            for (int j = 0; j < H; ++j) {
+                double a = bl[j];
+                for (int k = 0; k < H; ++k) a += (double)Wl[j * H + k] * act[l][k];
+                if (fabs(a) < margin) margin = fabs(a);
+                act[l + 1][j] = a > 0. ? a : 0.;
+            }
+        }
+        const float *wo = wl + (size_t)L * (H * H + H), *bo = wo + H;
+        double h = bo[0];
+        for (int k = 0; k < H; ++k) h += (double)wo[k] * act[L][k];
+        double g[MAXH], gp[MAXH], jac[MAXN + 1];
+        for (int k = 0; k < H; ++k) g[k] = act[L][k] > 0. ? (double)wo[k] : 0.;
+        for (int l = L - 1; l >= 0; --l) {
+            const float *Wl = wl + (size_t)l * (H * H + H);
+            for (int k = 0; k < H; ++k) gp[k] = 0.;
+            for (int j = 0; j < H; ++j)
+                for (int k = 0; k < H; ++k) gp[k] += (double)Wl[j * H + k] * g[j];
+            for (int k = 0; k < H; ++k) g[k] = act[l][k] > 0. ? gp[k] : 0.;
+        }
+        for (int k = 0; k < IN; ++k) {
+            double a = 0.;
+            for (int j = 0; j < H; ++j) a += (double)W[j * INP + k] * g[j];
+            jac[k] = a;
+        }
+        double a[MAXN], t[MAXN], lo[MAXN], hi[MAXN], u[MAXN], r;
+        for (int k = 0; k < n; ++k) a[k] = jac[k] + jac[n] * (double)d[n + 1 + k];
+        const float *goal = c->goal ? c->goal + (c->goal_rows == 1 ? 0 : b * n) : 0;
+        for (int i = 0; i < n; ++i) {
+            lo[i] = c->u_lo[i]; hi[i] = c->u_hi[i];
+            if (c->u_ref) t[i] = c->u_ref[b * n + i];
+            else {
+                double acc = 0.;
+                for (int k = 0; k < n; ++k) acc += (double)c->K[i * n + k] * ((double)d[k] - (double)goal[k]);
+                t[i] = -acc < lo[i] ? lo[i] : (-acc > hi[i] ? hi[i] : -acc);
+            }
+        }
+        const double cc = c->lam * h;
+        const double mu = qp_mu_exact(n, a, t, lo, hi, cc, c->p);
+        const double gg = qp_g(n, a, t, lo, hi, cc, mu, u);
+        r = (mu >= c->p && gg > 0.) ? gg : 0.;
+        double S = 0., ainf = 0., a1 = 0., st = 0.;
+        for (int k = 0; k < n; ++k) {
+            const double v = t[k] - 0.5 * mu * a[k];
+            if (v > lo[k] && v < hi[k]) { S += a[k] * a[k]; a1 += fabs(a[k]); st += fabs(t[k]); if (fabs(a[k]) > ainf) ainf = fabs(a[k]); }
+            else st += fabs(u[k]);
+        }
+        int regime = mu <= 0. ? 0 : (mu >= c->p ? 2 : 1);
+        double kc = 0., ka = 0.;
+        if (regime == 2) ka = 0.5 * c->p;
+        else if (regime == 1 && S > 0.) { kc = ainf / S; ka = (ainf / S) * (st + mu * a1) + 0.5 * mu; }
+        c->h[b] = h; c->r[b] = r; c->margin[b] = margin; c->kc[b] = kc; c->ka[b] = ka; c->regime[b] = regime;
+        for (int k = 0; k < n; ++k) { c->J[b * n + k] = a[k]; c->u[b * n + k] = u[k]; }
+    }
+}
+API int oracle_cbf_filter_f64(int n, int hidden, int layers, const float *weights, const float *datax, long B,
+                              const float *goal, long goal_rows, const float *u_ref, const float *K, const float *u_lo,
+                              const float *u_hi, float lam, float penalty, double *h, double *J, double *u, double *r,
+                              double *margin, double *kappa_c, double *kappa_a, int *regime) {
+    if (hidden > MAXH || layers > MAXL || n > MAXN) return -1;
+    Ctx64 c; memset(&c, 0, sizeof c);
+    c.n = n; c.net = (Net){n + 1, hidden, layers, weights}; c.datax = datax; c.goal = goal; c.goal_rows = goal_rows;
+    c.u_ref = u_ref; c.K = K; c.u_lo = u_lo; c.u_hi = u_hi; c.lam = lam; c.p = penalty < 1e6f ? (double)penalty : 1e6;
+    c.h = h; c.J = J; c.u = u; c.r = r; c.margin = margin; c.kc = kappa_c; c.ka = kappa_a; c.regime = regime;
+    par_for(B, filter64_range, &c);
     return 0;
 }
 
@@ -969,7 +1069,8 @@ API int oracle_radius_mask(int n, const float *queries, const float *set, long M
  *   unsafe check on q' (tsa.py:251: a colliding state is NOT appended, no_collision = False, loop ends);
  *   the observation (o, do/dq) is refreshed when (t+1) % ctrl_every == 0 (tsa.py:242-245);
  *   stuck test (tsa.py:263): stop when t > stuck_after and ||x_t - x_{t-stuck_lag}|| < stuck_eps.
- * q_final = x_list[-1], alive = no_collision, steps_done = number of appended states, traj = x_list[1:]. */
+ * q_final = x_list[-1], alive = no_collision, steps_done = number of appended states, traj = x_list[1:].
+ * stuck_mode 1 = the batched steer of batch_tsa.py:191-231 (see the branch below). */
 CLONES static void rollout_range(long lo, long hi, void *p) {
     Ctx *c = (Ctx *)p; const int n = c->n;
     for (long b = lo; b < hi; ++b) {
@@ -979,7 +1080,7 @@ CLONES static void rollout_range(long lo, long hi, void *p) {
         collide_state(c->rb, &c->sc, d, c->thr_soft, c->thr_hard, &co);
         d[n] = co.o;
         for (int k = 0; k < n; ++k) d[n + 1 + k] = co.dodq[k];
-        int ok = 1, done = 0;
+        int ok = 1, done = 0, dead = 0;
         float *tr = c->traj ? c->traj + b * (long)c->steps * n : 0;
         for (int t = 0; t < c->steps; ++t) {
             if (t % c->ctrl_every == 0) {
@@ -992,6 +1093,27 @@ CLONES static void rollout_range(long lo, long hi, void *p) {
             if ((t + 1) % c->ctrl_every == 0) {
                 d[n] = co.o;
                 for (int k = 0; k < n; ++k) d[n + 1 + k] = co.dodq[k];
+            }
+            if (c->stuck_mode == 1) {
+                /* batched steer (batch_tsa.py:225-229): stuck test BEFORE the append on the stored list (more than
+                 * stuck_after states: the last against the one stuck_lag before it); stuck OR unsafe kills the row for
+                 * good (no_collisions[i] = False, nothing appended any more) while x_current keeps integrating */
+                if (!dead) {
+                    int stuck = 0;
+                    if (c->stuck_lag > 0 && done > c->stuck_after) {
+                        const float *a = tr + (done - 1) * n, *o2 = tr + (done - 1 - c->stuck_lag) * n;
+                        float dsq = 0.f;
+                        for (int k = 0; k < n; ++k) { float e = a[k] - o2[k]; dsq = fmaf(e, e, dsq); }
+                        stuck = sqrtf(dsq) < c->stuck_eps;
+                    }
+                    if (stuck || co.unsafe) { ok = 0; dead = 1; }
+                }
+                for (int k = 0; k < n; ++k) d[k] = qn[k];
+                if (!dead) {
+                    if (tr) for (int k = 0; k < n; ++k) tr[done * n + k] = d[k];
+                    ++done;
+                } else if (!c->keep_going) break;
+                continue;
             }
             if (co.unsafe) { ok = 0; if (!c->keep_going) break; }
             for (int k = 0; k < n; ++k) d[k] = qn[k];
@@ -1013,14 +1135,14 @@ API int oracle_rollout(int robot, int n_boxes, const float *boxes, int n_sph, co
                        int hidden, int layers, const float *weights, const float *q0, const float *goal, long goal_rows,
                        long T, int steps, int ctrl_every, float dt, int stuck_lag, int stuck_after, float stuck_eps,
                        int keep_going, const float *K, const float *u_lo, const float *u_hi, float thr_soft, float thr_hard, float lam,
-                       float penalty, float *q_final, uint8_t *alive, int *steps_done, float *traj) {
+                       float penalty, float *q_final, uint8_t *alive, int *steps_done, float *traj, int stuck_mode) {
     if (hidden > MAXH || layers > MAXL) return -1;
     if (stuck_lag > 0 && !traj) return -1;
     Ctx c; memset(&c, 0, sizeof c);
     c.rb = &ROBOTS[robot]; c.n = c.rb->n; c.sc = (Scene){n_boxes, n_sph, floor, boxes, spheres};
     c.net = (Net){c.n + 1, hidden, layers, weights};
     c.q = q0; c.goal = goal; c.goal_rows = goal_rows; c.steps = steps; c.ctrl_every = ctrl_every; c.dt = dt;
-    c.stuck_lag = stuck_lag; c.stuck_after = stuck_after; c.stuck_eps = stuck_eps; c.traj = traj; c.keep_going = keep_going;
+    c.stuck_lag = stuck_lag; c.stuck_after = stuck_after; c.stuck_eps = stuck_eps; c.traj = traj; c.keep_going = keep_going; c.stuck_mode = stuck_mode;
     c.K = K; c.u_lo = u_lo; c.u_hi = u_hi; c.thr_soft = thr_soft; c.thr_hard = thr_hard; c.lam = lam; c.penalty = penalty;
     c.q_final = q_final; c.alive = alive; c.steps_done = steps_done;
     par_for(T, rollout_range, &c);

@@ -77,6 +77,65 @@ def assert_controls_match(coracle, u, r, h, J, o, uref, u_lo, u_hi, lam, penalty
     assert np.abs(r - o["r"]).max() < 1e-3
 
 
+KINK_MARGIN = 1e-5    # |pre-activation| below which a row counts as "on a ReLU kink" (float64 truth, pre-activation units)
+
+
+def assert_filter_matches_truth(coracle, n, weights, datax, goal, K, u_lo, u_hi, lam, penalty, h, J, u, r, u_ref=None,
+                                tol=1e-5, name="", max_kink_frac=0.02):
+    """Parity of the filter stage against the float64 END-TO-END truth (oracle_cbf_filter_f64: network, reverse-mode
+    Jacobian, nominal control and exact KKT solution in double on the same float32 inputs).  The statement, row by row:
+
+      h   continuous in the inputs:  |h - h64| <= tol * max(|h64|, 0.1)                      on EVERY row;
+      J   piecewise constant in the inputs, DISCONTINUOUS across ReLU kinks: within tol * max(|J64|, 0.1) on every row
+          whose smallest |pre-activation| (truth) exceeds KINK_MARGIN; the rows inside the margin (a fraction
+          <= max_kink_frac, printed) may legitimately return the Jacobian of the neighbouring linear piece -- the
+          reference's own float32 torch evaluation is in the same position -- and are only held to the h bound and to (a);
+      u,r (a) backward error: on EXACTLY the (h, J) the device produced, (u, r) equal the exact float64 KKT solution within
+              tol on EVERY row (no conditioning enters);
+          (b) forward error against the truth, on the rows outside the kink margin:
+              |u - u64|_inf <= tol * max(1, |u64|_inf) + 2 (kappa_c |lam (h - h64)| + kappa_a |J - J64|_inf),
+              kappa_c / kappa_a = first-order conditioning of the QP solution on its active set (a free axis with a tiny
+              |Lg_i| divides the network's rounding difference by |Lg_i|); the fraction of rows under the PLAIN tol bound
+              is printed and must be >= 0.97.
+    Returns the report dict."""
+    to_np = lambda x: np.asarray(x.cpu().numpy() if hasattr(x, "cpu") else x)
+    h, J, u, r = (to_np(x).astype(np.float64) for x in (h, J, u, r))
+    t = coracle.cbf_filter_f64(n, weights, 48, 2, datax, goal, K, u_lo, u_hi, lam, penalty, u_ref=u_ref)
+    B = h.shape[0]
+    away = t["margin"] > KINK_MARGIN
+    eh = np.abs(h - t["h"]) / np.maximum(np.abs(t["h"]), 0.1)
+    eJ = np.max(np.abs(J - t["J"]) / np.maximum(np.abs(t["J"]), 0.1), axis=1)
+    assert eh.max() < tol, (name, "h", eh.max())
+    assert (~away).mean() <= max_kink_frac, (name, "rows on a ReLU kink", (~away).mean())
+    assert eJ[away].max() < tol, (name, "J away from kinks", eJ[away].max(), int(np.argmax(np.where(away, eJ, 0))))
+    # (a) backward error on the device's own (h, J)
+    if u_ref is None:
+        uref_n = coracle.u_nominal(np.asarray(datax)[:, :n], goal, K, u_lo, u_hi)
+    else:
+        uref_n = np.asarray(u_ref, np.float32)
+    ue, re_ = coracle.qp(J.astype(np.float32), (np.float32(lam) * h.astype(np.float32)), uref_n, u_lo, u_hi, penalty)
+    assert rel_err(u, ue) < tol, (name, "u on own (h, J)", rel_err(u, ue))
+    assert rel_err(r, re_, floor=0.1) < tol, (name, "r on own (h, J)")
+    # (b) forward error against the truth, conditioning-aware
+    eu = np.max(np.abs(u - t["u"]), axis=1)
+    plain = tol * np.maximum(1.0, np.max(np.abs(t["u"]), axis=1))
+    dJ = np.max(np.abs(J - t["J"]), axis=1)
+    bound = plain + 2.0 * (t["kappa_c"] * np.abs(lam * (h - t["h"])) + t["kappa_a"] * dJ)
+    ratio = eu[away] / bound[away]
+    rep = {"rows": int(B), "kink_rows": int((~away).sum()), "kink_rows_with_J_mismatch": int((eJ[~away] >= tol).sum()),
+           "h_max": float(eh.max()), "J_max_away": float(eJ[away].max()),
+           "u_frac_under_plain_tol": float((eu[away] <= plain[away]).mean()), "u_max_err": float(eu[away].max()),
+           "u_max_err_over_bound": float(ratio.max()), "kappa_a_max": float(t["kappa_a"].max()),
+           "regimes": np.bincount(t["regime"], minlength=3).tolist()}
+    print(f"[filter parity vs float64 truth] {name}: {rep}")
+    assert ratio.max() <= 1.0, (name, "u beyond the conditioning bound", rep)
+    assert rep["u_frac_under_plain_tol"] >= 0.97, (name, rep)
+    er = np.abs(r - t["r"])
+    assert (er[away] <= tol * np.maximum(1.0, np.abs(t["r"][away])) + 2.0 * (np.abs(lam * (h - t["h"]))[away] + dJ[away] * np.abs(t["u"][away]).sum(1)
+            + np.abs(t["J"][away]).sum(1) * eu[away])).all(), (name, "r")
+    return rep
+
+
 def qp_kkt_residual(a, c, u_ref, lo, hi, p, u, tol=2e-5):
     """Optimality certificate for one row of  min ||u-u_ref||^2 + p sum_i max(0, c_i + a_i.u)  over the box: the
     smallest t for which multipliers mu exist with  mu_i = 0 (g_i < 0), = p (g_i > 0), in [0,p] (g_i = 0)  and

@@ -81,12 +81,12 @@ def install(monkeypatch):
         return torch.from_numpy(c_oracle.radius_mask(_np(queries), _np(points), radius))
 
     def rollout(q0, goal, steps, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, want_traj, keep_going, boxes, spheres, floor, grid,
-                weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id, hidden, layers):
+                weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id, hidden, layers, stuck_mode=0):
         b, s = _scene(boxes, spheres)
         qf, alive, done, traj = c_oracle.rollout(NAME[robot_id], _np(q0), _np(goal), steps, ctrl_every, dt, b, s, bool(floor),
                                                  _np(weights), hidden, layers, _np(K), _np(u_lo), _np(u_hi), thr_soft,
                                                  thr_hard, lam, penalty, stuck_lag=stuck_lag, stuck_after=stuck_after,
-                                                 stuck_eps=stuck_eps, want_traj=want_traj, keep_going=keep_going)
+                                                 stuck_eps=stuck_eps, want_traj=want_traj, keep_going=keep_going, stuck_mode=stuck_mode)
         return (torch.from_numpy(qf), torch.from_numpy(alive), torch.from_numpy(done),
                 torch.from_numpy(traj) if traj is not None else torch.empty(0))
 

@@ -26,7 +26,18 @@ def test_reference_arm_line():
     assert BASE <= set(r) and r["impl"] == "reference" and r["unit"] == "states/s" and r["value"] > 0
     assert r["cpu_baseline"]["kind"] == "port" and r["cpu_baseline"]["cores"] >= 1 and r["cpu_baseline"]["value"] == r["value"]
     assert r["e2e"] == {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert r["config"]["workload"].startswith("cfg1") and r["vs_baseline"] is None
+    assert r["config"]["workload"].startswith("cfg4") and r["vs_baseline"] is None and r["scaling"] == "strong"
+    assert "obstacles" in r["config"] and r["config"]["boxes"] == 256
+
+
+def test_reference_arm_does_not_load_the_cuda_library():
+    """the reference arm computes through the oracle only; it must not even map libcbfrrt.so"""
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--scale', '0.001'];"
+            "runpy.run_path(%r, run_name='__main__');"
+            "maps = open('/proc/self/maps').read(); assert 'libcbfrrt_oracle' in maps; assert 'libcbfrrt.so' not in maps, 'CUDA library mapped'"
+            % os.path.join(ROOT, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
 
 
 def test_reference_arm_under_torchrun_prints_once():
@@ -42,7 +53,7 @@ def test_reference_arm_under_torchrun_prints_once():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    r = _run("--steps", "3", "--warmup", "3", "--scale", "0.125")
+    r = _run("--steps", "3", "--warmup", "3", "--workload", "cfg1", "--scale", "0.125")
     assert BASE | {"clocks", "roofline"} <= set(r) and "impl" not in r
     assert r["n_gpus"] == 1 and r["steps"] == 3 and r["warmup"] >= 3 and r["higher_is_better"] and r["vs_baseline"] is None
     # structure only: three timed steps on a shared box are too noisy for performance thresholds
@@ -50,8 +61,22 @@ def test_gpu_arm_line():
     e = r["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 131072 * 16 and e["d2h_bytes_per_step"] == 131072 * 17, e
     rf = r["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "hbm", "tensor"} <= set(rf), rf
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "pipes"} <= set(rf) and set(rf["pipes"]) == {"fp32", "tensor", "hbm"}, rf
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["peak"] > 0
+    assert rf["frac"] == max(p["frac"] for p in rf["pipes"].values()) and rf["bound"] in rf["pipes"]
     c = r["cpu_baseline"]
     assert c["kind"] == "port" and c["value"] > 0 and "sample" in c
     assert set(r["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+@pytest.mark.gpu
+def test_gpu_arm_default_workload_line():
+    """the default (headline) workload: BASELINE configs[4], strong scaling, valid + u; shrunk 1/64 here"""
+    r = _run("--steps", "3", "--warmup", "3", "--scale", str(1 / 64), "--no-other-configs")
+    assert r["config"]["workload"].startswith("cfg4") and r["scaling"] == "strong" and r["config"]["outputs"] == "valid+u"
+    assert r["config"]["states"] == 1 << 20 and r["gpu_launches"] == 3 and r["value"] > 0
+    assert 0.05 < r["config"]["valid_fraction"] < 0.5
+    assert r["e2e"]["h2d_bytes_per_step"] == (1 << 20) * 28 and r["e2e"]["d2h_bytes_per_step"] == (1 << 20) * 29
+    bp = r["roofline"]["broad_phase"]
+    assert bp["grid"] and 0 < bp["spheres_swept_per_state"] < 28 and bp["pairs_per_state"] < 100
+    assert set(r["targets"]) == {"collision_checked_franka_configs_per_s", "cbf_qp_filtered_control_steps_per_s"}

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(_lib.lib, n), f"{n} declared in include/cbfrrt.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in cbfrrt/_lib.py"
-    assert _lib.lib.cbfrrt_abi_version() == 1
+    assert _lib.lib.cbfrrt_abi_version() == 2
 
 
 def test_robot_info_and_status_strings():
@@ -38,7 +38,7 @@ def test_argument_validation_happens_before_cuda():
     from cbfrrt import _lib
     lib = _lib.lib
     sc = _lib.Scene(0, 0, 1, 0, None, None, None)
-    assert lib.cbfrrt_grid_bytes() == 44 * 44 * 44 * 24 * 2
+    assert lib.cbfrrt_grid_bytes() == 44 * 44 * 44 * 24 * 2 + 88 * 88 * 88 * 4   # candidate records + distance-bound field
     assert lib.cbfrrt_grid_build(C.byref(sc), None, None) == -2
     buf = (C.c_float * 64)()
     p = C.cast(buf, C.c_void_p)

@@ -22,7 +22,7 @@ def _worker(rank, world, port, ret):
     from cbfrrt import ops, workloads as W
     from cbfrrt.sharded import FusedSweep, ShardedSweep, local_global_rows
     w = W.config(1, scale=1 / 16)
-    n, rid, B = w["n"], 1, 20000
+    n, rid, B = w["n"], 1, 20096      # a multiple of 128: the multicast form packs the mask bytes of 32-row groups into words
     G = world * B
     t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev)
     b8, s4 = ops.pack_scene(w["boxes"][:, :3], w["boxes"][:, 3:], w["spheres"], device=dev)
@@ -37,7 +37,7 @@ def _worker(rank, world, port, ret):
     modes = []
     for no_mc in ("0", "1"):
         os.environ["CBFRRT_NO_MULTICAST"] = no_mc
-        sweep = FusedSweep(lambda qb, vp, up, off: ops.valid_control_scatter(qb, *common, vp, up, off), n, B, dev)
+        sweep = FusedSweep(lambda qb, vp, up, off, mc: ops.valid_control_scatter(qb, *common, vp, up, off, mc), n, B, dev)
         modes.append(sweep.multicast)
         for _ in range(2):
             sweep.valid.zero_()
@@ -49,10 +49,21 @@ def _worker(rank, world, port, ret):
             ok.append(bool(torch.equal(v, ref_v) and torch.equal(u, ref_u)))
         dist.barrier()
     assert modes[1] is False
+    # rows per rank not a multiple of 128: the sweep must fall back to per-peer stores by itself and still be exact
+    os.environ["CBFRRT_NO_MULTICAST"] = "0"
+    B2 = 19999
+    q2 = ops.sample_states(world * B2, 6, 0, rid, device=dev)
+    ref_v2, ref_u2 = ops.valid_control(q2, *common)
+    sweep2 = FusedSweep(lambda qb, vp, up, off, mc: ops.valid_control_scatter(qb, *common, vp, up, off, mc), n, B2, dev)
+    assert sweep2.multicast is False
+    v, u = sweep2(q2[rank * B2:(rank + 1) * B2])
+    torch.cuda.synchronize()
+    ok.append(bool(torch.equal(v, ref_v2) and torch.equal(u, ref_u2)))
+    dist.barrier()
     if rank == 0:
         print("fused exchange modes tested (multicast, per-peer):", modes, flush=True)
     # NCCL all-gather, block-cyclic
-    block, rounds = 2500, B // 2500
+    block, rounds = 2512, B // 2512
     rows = local_global_rows(rank, world, block, rounds).to(dev)
     v, u = ShardedSweep(lambda qb: ops.valid_control(qb, *common), n, block, device=dev)(q_all[rows])
     torch.cuda.synchronize()
@@ -80,3 +91,40 @@ def test_fused_and_nccl_exchange_match_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(all(o) for o in out), out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_host_api_two_devices_one_process():
+    """cbfrrt_safety_filter_host driving two GPUs from ONE process: the > 48 KB dynamic shared-memory opt-in and the SM
+    count are per device (a cache keyed by kernel only would fail the second device's first large launch), and the
+    caller's current device is left as it was"""
+    import numpy as np
+    for p in (ROOT, os.path.join(ROOT, "cbf-inc-rrt_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from cbfrrt import ops, workloads as W
+    w = W.config(1, scale=1 / 16)
+    B, n = w["q"].shape
+    outs = []
+    torch.cuda.set_device(0)
+    for dev in (0, 1, 0):
+        out = dict(safe=np.empty(B, np.uint8), u=np.empty((B, n), np.float32), h=np.empty(B, np.float32))
+        ops.safety_filter_host("magician", w["q"], w["boxes"], w["spheres"], True, w["weights"], 48, 2, w["goal"], w["K"],
+                               w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], out, device=dev)
+        assert torch.cuda.current_device() == 0
+        outs.append(out)
+    for k in ("safe", "u", "h"):
+        assert np.array_equal(outs[0][k], outs[1][k]) and np.array_equal(outs[0][k], outs[2][k])
+    # the device-pointer ABI on the second device as well (tcgen05 kernel, ~180 KB of dynamic shared memory)
+    res = []
+    for d in (0, 1):
+        dv = torch.device("cuda", d)
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dv)
+        b8, s4 = ops.pack_scene(w["boxes"][:, :3], w["boxes"][:, 3:], w["spheres"], device=dv)
+        gr = ops.build_grid(b8, s4)
+        net = ops.pack_weights(w["state_dict"], n, 48, 2, device=dv)
+        v, u = ops.valid_control(t(w["q"]), t(w["goal"]), b8, s4, 1, gr, net, t(w["K"]), t(w["u_lo"]), t(w["u_hi"]), w["lam"],
+                                 w["penalty"], w["thr_soft"], w["thr_hard"], 1, 48, 2)
+        res.append((v.cpu(), u.cpu()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][0].numpy(), outs[0]["safe"]) and np.array_equal(res[0][1].numpy(), outs[0]["u"])

@@ -190,6 +190,36 @@ def test_steer_reference_loop_equals_fused(stack):
     assert keep.sum() >= 4 and np.abs(xb[keep] - qf.numpy()[keep]).max() < 1e-5
 
 
+def test_batched_steer_reference_semantics_fused(stack):
+    """the one-launch batched steer with the reference's semantics (batch_tsa.py:191-231: stuck rows become
+    collisions, dead rows keep integrating, early exit when the whole batch is dead) against the host-loop mirror that
+    the reference's own batch_tsa.steer is pinned to (test_reference_planner_cpu)"""
+    env, robot, dyn, ctrl = stack("panda")
+    from cbfrrt.motion_planning.baseline import batch_steer, batch_steer_fused_reference
+    x = dyn.sample_state_space(400)
+    xs = x[dyn.safe_mask(x)].numpy()[:, :7]
+    assert xs.shape[0] >= 40
+    seen = {"dead": 0, "stuck": 0, "all_dead": 0}
+    cases = [(xs[:12], xs[12:24], 40), (xs[24:36], xs[24:36] + 0.02, 40),            # ordinary / targets next to the start (stuck)
+             (xs[:6], np.repeat(np.array([[0., 1.7, 0., -0.1, 0., 3.7, 0.]], np.float32), 6, 0), 60)]  # a pose that folds onto the floor
+    for starts, targets, steps in cases:
+        xb, oks, _, xs_list = batch_steer(ctrl.u, dyn, targets, starts, RRT_step=steps, device="cpu")
+        xf, okf, lists_f = batch_steer_fused_reference(ctrl, dyn, targets, starts, RRT_step=steps)
+        assert list(oks) == list(okf)
+        assert [len(a) for a in xs_list] == [len(b) for b in lists_f]
+        assert np.abs(xb - xf).max() < 1e-4
+        for a, b in zip(xs_list, lists_f):
+            if len(a):
+                assert np.abs(np.asarray(a)[:, :7] - np.asarray(b)).max() < 1e-4
+        seen["dead"] += sum(not o for o in oks)
+        seen["all_dead"] += int(not any(oks))
+        # a stuck row: died although its next state was not unsafe -- identify via the stored list (>= 11 states, last two 9 apart close)
+        for ok, lst in zip(oks, xs_list):
+            if not ok and len(lst) > 10 and np.linalg.norm(np.asarray(lst[-1]) - np.asarray(lst[-10])) < 3e-2:
+                seen["stuck"] += 1
+    assert seen["dead"] > 0 and seen["stuck"] > 0, seen
+
+
 def test_edge_checking_reference_loop_equals_batched(stack):
     env, robot, dyn, ctrl = stack("panda")
     from cbfrrt.motion_planning.baseline import (edge_checking, edge_checking_batch, edge_checking_eps,
@@ -258,8 +288,8 @@ def test_batch_rrt_plan_builds_a_consistent_tree(stack):
     edge_pts = np.array([pt for xl in tree.x_list[1:] for pt in xl])
     if len(edge_pts):
         assert not dyn.unsafe_mask(torch.as_tensor(edge_pts, dtype=torch.float32)).any()
-    for i in range(1, n_nodes):                                      # an edge ends at its node
-        if tree.x_list[i]:
+    for i in range(1, n_nodes):     # an edge ends at its node -- for rows that stayed alive; a dead row's node is the
+        if tree.x_list[i] and tree.freesp[i]:   # reference's running x_current (batch_tsa.py:231), beyond its stored edge
             assert np.allclose(tree.x_list[i][-1], tree.states[i], atol=1e-6)
     if res["success"]:
         assert np.allclose(res["path"][0], init) and np.linalg.norm(res["path"][-1] - goal) <= 0.2 + 1e-6
