@@ -566,9 +566,10 @@ __device__ __forceinline__ bool rollout_after_step(const RolloutArgs& ra, int t,
 // tensor cores (mlp_tc.cuh).  One CTA per SM of GG tile groups (see tc_groups) sharing the staged weights; all 128
 // threads of a group take part in every tile of that group (idle rows are masked), because the MMAs, the TMEM
 // traffic and the barriers are group-wide.
-// tile groups per CTA: 4 (512 threads, 128 registers) when the geometry stage works out of shared memory, 3 (384
-// threads) for the broad-phase-grid variants, which need the L1 capacity of a fourth A_lo tile for the grid look-ups
-constexpr int tc_groups(bool grid) { return grid ? 3 : 4; }
+// tile groups per CTA: 4 (512 threads, 128 registers, 16 warps per SM).  (Round 1 ran the broad-phase-grid variants with
+// 3 groups to leave L1 to the per-sphere candidate gathers; with the distance-bound field the geometry stage is
+// latency bound and the fourth group wins: cfg4 valid+u 5.96 -> 5.33 ms per 2^23 states, profiles/r2c_*.)
+constexpr int tc_groups(bool) { return 4; }
 
 template <int N, int L, int GG>
 __device__ __forceinline__ void filter_tile_tc(tc::Ctx<L, GG>& c, const float* prm, const float (&q)[N], float o,
@@ -612,12 +613,44 @@ __global__ void __launch_bounds__(4 * tc::M_TILE, 1) filter_kernel_tc(NetArgs ne
     tc::teardown<L, GG>(c);
 }
 
+// ---- coalesced tile I/O of the tensor-core safety kernel.  A tile is 128 CONSECUTIVE rows, so every per-row array of
+// the tile is one contiguous, 16-byte aligned block in global memory (128 x 28 B of q, 128 x 60 B of datax, ...).  Rows
+// are exchanged through the group's A_lo tile, which is idle between the last GEMM of a tile and the first hidden-layer
+// store of the next: thread t parks its row (odd row length: conflict-free), one group barrier, then the 128 threads
+// stream the block as float4 -- full 128-byte lines instead of 28-byte-strided scalar accesses (round 1: 79 % of the L2
+// sectors "excessive"), and 16-byte multimem.st to the NVSwitch multicast address in the fused exchange.
+// Layout of the group's A_lo tile in floats: [0,1024) first-layer A_lo | [1024,1920) q rows | [2048,6144) output rows.
+template <int W>
+__device__ __forceinline__ void park_row(float* __restrict__ stg, int t, const float (&v)[W]) {
+    if constexpr (W % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < W; k += 4) *reinterpret_cast<float4*>(stg + t * W + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) stg[t * W + k] = v[k];
+    }
+}
+// stream 128 rows of W floats (or n16 16-byte words) from the staging block to dst; MC: multimem.st to a multicast address
+template <bool MC>
+__device__ __forceinline__ void flush_block(const float* __restrict__ stg, int t, float* __restrict__ dst, int n16) {
+    const float4* s4 = reinterpret_cast<const float4*>(stg);
+    for (int i = t; i < n16; i += tc::M_TILE) {
+        const float4 v = s4[i];
+        if constexpr (MC) multimem_st_v4(dst + 4 * i, v.x, v.y, v.z, v.w);
+        else *reinterpret_cast<float4*>(dst + 4 * i) = v;
+    }
+}
+constexpr int VEC_Q = 1, VEC_OUT = 2, VEC_PEER = 4;   // which pointer sets are 16-byte aligned (checked on the host)
+
 template <class RB, int L, bool GRID, int GG>
 __global__ void __launch_bounds__(GG * tc::M_TILE, 1) safety_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q,
                                                            long long q_stride, long long B, float thr_soft, float thr_hard,
-                                                           CollideOutPtrs cout, FilterOutPtrs fout, PeerOut po) {
-    constexpr int N = RB::N;
+                                                           CollideOutPtrs cout, FilterOutPtrs fout, PeerOut po, int vec) {
+    constexpr int N = RB::N, DX = 2 * N + 1, MT = tc::M_TILE;
     constexpr int NTC = GG * tc::M_TILE;
+    // output staging offsets (floats) inside [2048, 6144) of the group's A_lo tile
+    constexpr int O_DX = 2048, O_U = O_DX + MT * DX, O_J = O_U + MT * N, O_H = O_J + MT * N, O_R = O_H + MT, O_B = O_R + MT;
+    static_assert(O_B + 2 * MT / 4 <= tc::ALO_TILE && 1024 + MT * N <= 2048, "staging does not fit the A_lo tile");
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, tc::Layout<L, GG>::TOTAL, ParamLayout<N>::TOTAL);
     stage<N, NTC>(s, sc, &net, 0);
@@ -625,28 +658,81 @@ __global__ void __launch_bounds__(GG * tc::M_TILE, 1) safety_kernel_tc(SceneArgs
     const float base_min = base_min_cta<RB, NTC>(s, sv);
     tc::Ctx<L, GG> c;
     tc::setup<N + 1, L, GG>(c, s.weights, net.weights);
+    float* const alo = reinterpret_cast<float*>(c.alo());
+    const bool want_valid_stage = cout.safe != nullptr || po.n > 0;
     const long long n_tiles = (B + tc::M_TILE - 1) / tc::M_TILE;
     for (long long tile = (long long)blockIdx.x * GG + c.g; tile < n_tiles; tile += (long long)gridDim.x * GG) {
-        const long long b = tile * tc::M_TILE + c.t;
-        const bool active = b < B;
+        const long long b0 = tile * tc::M_TILE, b = b0 + c.t;
+        const bool active = b < B, full = b0 + tc::M_TILE <= B;      // full: uniform over the group
         float qq[N], g[N], J[N], u[N], h, r;
 #pragma unroll
         for (int k = 0; k < N; ++k) { qq[k] = 0.f; g[k] = 0.f; }
         CollideResult<RB> cr;
-        cr.o = 0.f;
+        cr.o = 0.f; cr.soft_min = 0.f; cr.hard_min = 0.f; cr.self_ok = false;
 #pragma unroll
         for (int k = 0; k < N; ++k) cr.dodq[k] = 0.f;
-        if (active) {
+        if (full && (vec & VEC_Q)) {                                   // coalesced load of the tile's 128 x N floats
+            const float4* src = reinterpret_cast<const float4*>(q + b0 * N);
+            float4* dst = reinterpret_cast<float4*>(alo + 1024);
+            for (int i = c.t; i < MT * N / 4; i += MT) dst[i] = __ldg(src + i);
+            tc::group_sync(c.g);
+#pragma unroll
+            for (int k = 0; k < N; ++k) qq[k] = alo[1024 + c.t * N + k];
+        } else if (active) {
 #pragma unroll
             for (int k = 0; k < N; ++k) qq[k] = __ldg(q + b * q_stride + k);
+        }
+        if (active) {
             collide_state<RB, true, false, GRID>(qq, sv, base_min, cr);
-            write_collide<RB>(cout, b, qq, cr, thr_soft, thr_hard);
             load_goal<N>(net, b, g);
         }
         filter_tile_tc<N, L, GG>(c, s.params, qq, cr.o, cr.dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
-        if (active) {
-            write_filter<N>(fout, b, h, J, u, r);
-            if (po.n) write_peers<N>(po, b, cr.self_ok && (cr.soft_min > thr_soft) && !(cr.hard_min <= thr_hard), u);
+        const bool unsafe = cr.hard_min <= thr_hard;
+        const bool safe = cr.self_ok && (cr.soft_min > thr_soft) && !unsafe;
+        const bool out_fast = full && (vec & VEC_OUT), peer_fast = full && po.n > 0 && (vec & VEC_PEER);
+        if (out_fast || peer_fast) {
+            if (cout.datax && out_fast) {
+                float row[DX];
+#pragma unroll
+                for (int k = 0; k < N; ++k) { row[k] = qq[k]; row[N + 1 + k] = cr.dodq[k]; }
+                row[N] = cr.o;
+                park_row<DX>(alo + O_DX, c.t, row);
+            }
+            if ((fout.u && out_fast) || peer_fast) park_row<N>(alo + O_U, c.t, u);
+            if (fout.J && out_fast) park_row<N>(alo + O_J, c.t, J);
+            if (fout.h && out_fast) alo[O_H + c.t] = h;
+            if (fout.r && out_fast) alo[O_R + c.t] = r;
+            if (want_valid_stage) reinterpret_cast<uint8_t*>(alo + O_B)[c.t] = safe;
+            if (cout.unsafe && out_fast) reinterpret_cast<uint8_t*>(alo + O_B)[MT + c.t] = unsafe;
+            tc::group_sync(c.g);
+            if (out_fast) {
+                if (cout.datax) flush_block<false>(alo + O_DX, c.t, cout.datax + b0 * DX, MT * DX / 4);
+                if (fout.u) flush_block<false>(alo + O_U, c.t, fout.u + b0 * N, MT * N / 4);
+                if (fout.J) flush_block<false>(alo + O_J, c.t, fout.J + b0 * N, MT * N / 4);
+                if (fout.h) flush_block<false>(alo + O_H, c.t, fout.h + b0, MT / 4);
+                if (fout.r) flush_block<false>(alo + O_R, c.t, fout.r + b0, MT / 4);
+                if (cout.safe) flush_block<false>(alo + O_B, c.t, reinterpret_cast<float*>(cout.safe + b0), MT / 16);
+                if (cout.unsafe) flush_block<false>(alo + O_B + MT / 4, c.t, reinterpret_cast<float*>(cout.unsafe + b0), MT / 16);
+            }
+            if (peer_fast) {
+                const long long g0 = po.row_offset + b0;
+                if (po.multicast) {
+                    flush_block<true>(alo + O_U, c.t, po.u[0] + g0 * N, MT * N / 4);
+                    flush_block<true>(alo + O_B, c.t, reinterpret_cast<float*>(po.valid[0] + g0), MT / 16);
+                } else {
+                    for (int p = 0; p < po.n; ++p) {
+                        flush_block<false>(alo + O_U, c.t, po.u[p] + g0 * N, MT * N / 4);
+                        flush_block<false>(alo + O_B, c.t, reinterpret_cast<float*>(po.valid[p] + g0), MT / 16);
+                    }
+                }
+            }
+        }
+        if (active) {   // tail tile / unaligned pointers: per-row stores
+            if (!out_fast) {
+                write_collide<RB>(cout, b, qq, cr, thr_soft, thr_hard);
+                write_filter<N>(fout, b, h, J, u, r);
+            }
+            if (po.n && !peer_fast) write_peers<N>(po, b, safe, u);
         }
     }
     tc::teardown<L, GG>(c);
@@ -986,13 +1072,25 @@ inline int check_scene(const cbfrrt_scene* sc, SceneArgs& a) {
     if (sc->n_boxes + sc->n_spheres > CBFRRT_MAX_OBSTACLES) return CBFRRT_ERR_UNSUPPORTED;
     if ((sc->n_boxes && !sc->boxes) || (sc->n_spheres && !sc->spheres)) return CBFRRT_ERR_BAD_SHAPE;
     if (!aligned16(sc->boxes) || !aligned16(sc->spheres) || !aligned16(sc->grid)) return CBFRRT_ERR_ALIGNMENT;
-    // the grid's look-ups and gathers cost more than they save on small scenes (measured: slower at 16 obstacles,
-    // 1.7x faster at 64, 4.3x at 256): scenes below GRID_MIN_OBSTACLES are swept brute force even if a grid is given
-    static const int grid_min = [] { const char* e = getenv("CBFRRT_GRID_MIN"); return e ? atoi(e) : GRID_MIN_OBSTACLES; }();
-    const bool use_grid = sc->grid && sc->n_boxes + sc->n_spheres >= grid_min;
     a = SceneArgs{sc->boxes, sc->spheres, sc->n_boxes, sc->n_spheres, sc->floor ? 1 : 0,
-                  use_grid ? static_cast<const uint16_t*>(sc->grid) : nullptr, static_cast<unsigned long long*>(sc->stats)};
+                  static_cast<const uint16_t*>(sc->grid), static_cast<unsigned long long*>(sc->stats)};
     return CBFRRT_OK;
+}
+
+// When to use the broad phase a caller supplied (results are bit-identical either way).  Measured on B200
+// (profiles/r2c_configs_*.jsonl): with >= 40 obstacles the distance-bound field always wins (256 boxes: masks 2.5x,
+// valid+u 1.8x over the round-1 candidate grid); below that the shared-memory sweep with ball culling has no global
+// loads at all and wins where calls are long dependent chains (rollouts, 8 boxes: 17 vs 35 ms) and ties on the fused
+// kernel, while planner-sized launches (<= SMALL_BATCH rows: cold instruction cache, one wave) are faster on the field
+// path's much smaller instruction stream (4096 states, 1 box: 68 -> 42 us).  CBFRRT_GRID_MIN overrides the threshold.
+constexpr long long SMALL_BATCH = 16384;
+inline SceneArgs scene_for(const SceneArgs& sc, long long rows, bool is_rollout) {
+    static const int grid_min = [] { const char* e = getenv("CBFRRT_GRID_MIN"); return e ? atoi(e) : GRID_MIN_OBSTACLES; }();
+    SceneArgs a = sc;
+    const int n_obs = sc.n_boxes + sc.n_spheres;
+    const bool use = sc.grid && (n_obs >= grid_min || (!is_rollout && rows <= SMALL_BATCH && n_obs >= 1));
+    if (!use) a.grid = nullptr;
+    return a;
 }
 
 inline int check_net(int n, const cbfrrt_cbf_net* net, const cbfrrt_filter_params* fp, long long B, NetArgs& a) {
@@ -1016,8 +1114,9 @@ static int launch_fk(const float* q, long long qs, long long B, float* pos, floa
 }
 
 template <class RB>
-static int launch_collide(const SceneArgs& sc, const float* q, long long qs, long long B, float ts, float th,
+static int launch_collide(const SceneArgs& sc_in, const float* q, long long qs, long long B, float ts, float th,
                           const CollideOutPtrs& out, cudaStream_t st) {
+    const SceneArgs sc = scene_for(sc_in, B, false);
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
     const long long tiles = (B + NT - 1) / NT;
     const bool grad = out.datax || out.arg_link || out.arg_obs;
@@ -1038,8 +1137,7 @@ static int launch_collide(const SceneArgs& sc, const float* q, long long qs, lon
 
 // Batches of at most SMALL_BATCH rows (< 1 tile group per SM) are launch-latency bound: the tcgen05 kernels' per-CTA
 // set-up (two weight tilings, TMEM allocation) costs more than it saves there, so they take the FP32-FMA kernels
-// (measured on cfg0, 4096 rows: 59 us vs 75 us).  CBFRRT_MLP=tc forces the tensor-core kernels for any size.
-constexpr long long SMALL_BATCH = 16384;
+// (measured on cfg0, 4096 rows: 59 us vs 75 us).  cbfrrt_set_mlp_path(CBFRRT_MLP_TC) forces the tensor-core kernels.
 // MLP path: CBFRRT_MLP_AUTO (tcgen05 kernels above SMALL_BATCH rows, FP32-FMA kernels below), _FMA or _TC for every
 // size.  Set through cbfrrt_set_mlp_path() (include/cbfrrt.h); the environment variable CBFRRT_MLP=fma|tc only gives
 // the initial value.  Read at every launch, so one process can exercise both paths (the parity tests do).
@@ -1067,18 +1165,32 @@ static int launch_filter(const NetArgs& net, const float* datax, long long B, co
 }
 
 template <class RB>
-static int launch_safety(const SceneArgs& sc, const NetArgs& net, const float* q, long long qs, long long B, float ts,
+static int launch_safety(const SceneArgs& sc_in, const NetArgs& net, const float* q, long long qs, long long B, float ts,
                          float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, const PeerOut& po, cudaStream_t st) {
-    static const int gg_grid = [] { const char* e = getenv("CBFRRT_TC_GROUPS_GRID"); return (e && atoi(e) == 4) ? 4 : 3; }();
-    const int gg = sc.grid ? gg_grid : 4;
-    const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, gg == 3 ? tc::Layout<2, 3>::TOTAL : tc::Layout<2, 4>::TOTAL,
-                                           ParamLayout<RB::N>::TOTAL, 0);
+    const SceneArgs sc = scene_for(sc_in, B, false);
+    const int gg = 4;
+    const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2, 4>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
     if (use_tc() && (B > SMALL_BATCH || force_tc()) && smem_tc <= TC_SMEM_MAX) {
         const size_t smem = smem_tc;
-        auto k = sc.grid ? (gg == 3 ? safety_kernel_tc<RB, 2, true, 3> : safety_kernel_tc<RB, 2, true, 4>) : safety_kernel_tc<RB, 2, false, 4>;
+        auto k = sc.grid ? safety_kernel_tc<RB, 2, true, 4> : safety_kernel_tc<RB, 2, false, 4>;
         const int grid = grid_for_tc(k, smem, B, gg);
         if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, gg * tc::M_TILE, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo, po);
+        // which pointer sets allow 16-byte tile accesses (see the kernel): rows are contiguous and every base aligned
+        // Measured (profiles/r2e_configs.jsonl vs r2c_*_gg4): for LOCAL outputs the staged form is 5 % slower than the
+        // per-row stores (cfg4 valid+u 5.33 -> 5.62 ms per 2^23 states: two more group barriers per tile, and the L2 absorbs
+        // the partial lines), so it is used only where it pays -- the NVLink stores of the fused exchange, where a
+        // 4-byte store is a whole fabric packet.  CBFRRT_TILE_IO=1 switches it on for q / local outputs too (A/B runs).
+        static const bool tile_io = [] { const char* e = getenv("CBFRRT_TILE_IO"); return e && e[0] == '1'; }();
+        int vec = 0;
+        if (tile_io && qs == RB::N && aligned16(q)) vec |= VEC_Q;
+        if (tile_io && aligned16(co.safe) && aligned16(co.unsafe) && aligned16(co.datax) && aligned16(fo.h) && aligned16(fo.J) &&
+            aligned16(fo.u) && aligned16(fo.r) && !co.arg_link && !co.arg_obs && !co.mins) vec |= VEC_OUT;
+        if (po.n > 0 && po.row_offset % 16 == 0) {
+            bool ok = true;
+            for (int p = 0; p < po.n; ++p) ok = ok && aligned16(po.valid[p]) && aligned16(po.u[p]);
+            if (ok) vec |= VEC_PEER;
+        }
+        k<<<grid, gg * tc::M_TILE, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo, po, vec);
         return finish_launch();
     }
     using LY = NetLayout<RB::N + 1, 48, 2>;
@@ -1101,8 +1213,9 @@ static int launch_edges(const SceneArgs& sc, const float* qf, const float* qt, l
 }
 
 template <class RB>
-static int launch_edges_var(const SceneArgs& sc, const float* qf, const float* qt, long long E, const long long* off,
+static int launch_edges_var(const SceneArgs& sc_in, const float* qf, const float* qt, long long E, const long long* off,
                             int K_all, long long P, float ts, float th, uint8_t* valid, int* first_bad, cudaStream_t st) {
+    const SceneArgs sc = scene_for(sc_in, P, false);
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
     const int eg = (int)((E + 255) / 256 < 1184 ? (E + 255) / 256 : 1184);
     edge_var_init<0><<<eg, 256, 0, st>>>(first_bad, E);
@@ -1119,11 +1232,11 @@ static int launch_edges_var(const SceneArgs& sc, const float* qf, const float* q
 }
 
 template <class RB>
-static int launch_rollout(const SceneArgs& sc, const NetArgs& net, const float* q0, long long T, const RolloutArgs& ra,
+static int launch_rollout(const SceneArgs& sc_in, const NetArgs& net, const float* q0, long long T, const RolloutArgs& ra,
                           float ts, float th, float* qf, uint8_t* alive, int* done, float* traj, cudaStream_t st) {
-    const int gg = tc_groups(sc.grid != nullptr);
-    const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, sc.grid ? tc::Layout<2, 3>::TOTAL : tc::Layout<2, 4>::TOTAL,
-                                           ParamLayout<RB::N>::TOTAL, 0);
+    const SceneArgs sc = scene_for(sc_in, T, true);
+    const int gg = 4;
+    const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2, 4>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
     if (use_tc() && (T > SMALL_BATCH || force_tc()) && smem_tc <= TC_SMEM_MAX) {
         const size_t smem = smem_tc;
         auto k = sc.grid ? rollout_kernel_tc<RB, 2, true> : rollout_kernel_tc<RB, 2, false>;
