@@ -39,6 +39,12 @@ class PeerOut(C.Structure):
                 ("u", C.c_void_p * 8)]
 
 
+class LidarNet(C.Structure):
+    _fields_ = ([(k, C.c_int32) for k in ("n", "n_sensors", "point_dims", "per_feature_dim", "feature_dim", "hidden", "layers", "_pad")]
+                + [(k, C.c_void_p) for k in ("w1t", "w2t", "w3t", "bias", "fc2_w", "fc2_b", "fc3_w", "fc3_b", "e1_w", "e1_b", "e2_w",
+                                             "e2_b", "e4_w", "e4_b", "h_in_w", "h_in_b", "h_hid_w", "h_hid_b", "h_out_w", "h_out_b")])
+
+
 class RolloutParams(C.Structure):
     _fields_ = [("steps", C.c_int32), ("ctrl_every", C.c_int32), ("dt", C.c_float), ("stuck_lag", C.c_int32),
                 ("stuck_after", C.c_int32), ("stuck_eps", C.c_float), ("keep_going", C.c_int32),
@@ -76,6 +82,8 @@ SIGNATURES = {
     "cbfrrt_rollout": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, C.POINTER(FilterParams),
                                  C.POINTER(RolloutParams), _F, _F, _P, _P, _P, _P, _P]),
     "cbfrrt_fma_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "cbfrrt_lidar_workspace_bytes": (C.c_int64, [C.POINTER(LidarNet), _L, C.c_int32]),
+    "cbfrrt_lidar_cbf": (C.c_int, [C.POINTER(LidarNet), _P, _P, _L, _P, _P, _P, _P, C.c_int32, _L, _F, _P, _P, _P, _P]),
     "cbfrrt_sample_states": (C.c_int, [_I, C.c_uint32, C.c_uint64, _L, _P, _P]),
     "cbfrrt_safety_filter_host": (C.c_int, [_I, _I, C.POINTER(HostScene), C.c_int32, C.c_int32, _P, _L, _P, _L, _P, _L,
                                             _P, _P, _P, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),

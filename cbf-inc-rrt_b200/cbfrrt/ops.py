@@ -19,7 +19,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import lib, check, Scene, CbfNet, FilterParams, RolloutParams, PeerOut
+from ._lib import lib, check, Scene, CbfNet, FilterParams, RolloutParams, PeerOut, LidarNet
 
 ROBOT_ID = _lib.ROBOT_ID
 ROBOT_N = {0: 7, 1: 4}
@@ -322,11 +322,13 @@ def valid_control(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor
     sc = _scene(boxes, spheres, floor, grid)
     safe = torch.empty(B, dtype=torch.uint8, device=dev)
     u = torch.empty((B, n), dtype=torch.float32, device=dev)
+    # network shapes other than 48 x 2 run as two launches and need the observation rows in between
+    datax = None if (hidden, layers) == (48, 2) else torch.empty((B, 2 * n + 1), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib.cbfrrt_safety_filter(robot_id, C.byref(sc), C.byref(net), _ptr(q), qs, B, C.byref(fp), thr_soft,
-                                       thr_hard, _ptr(safe), None, None, None, None, _ptr(u), None, _stream()),
+                                       thr_hard, _ptr(safe), None, _ptr(datax), None, None, _ptr(u), None, _stream()),
               "cbfrrt_safety_filter")
-    del keep
+    del keep, datax
     return safe, u
 
 
@@ -610,6 +612,102 @@ def safety_filter_host(robot: str, q: np.ndarray, boxes6: np.ndarray, spheres: n
                                         thr_hard, p("safe"), p("unsafe"), p("datax"), p("h"), p("J"), p("u"), p("r")),
           "cbfrrt_safety_filter_host")
     return out
+
+
+# ----------------------------------------------------------------------------- LiDAR / PointNet barrier
+def _rna_tf32(w: np.ndarray) -> np.ndarray:
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) onto 10 mantissa bits"""
+    u = np.ascontiguousarray(w, np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _tf32_tiles(w: np.ndarray) -> np.ndarray:
+    """W [n_out, K] (torch layout, K % 4 == 0) -> [hi | lo] tiles in the tensor core's no-swizzle K-major layout
+    W4[k/4][n] (core matrix = 8 rows x 16 bytes): hi = rna_tf32(W), lo = W - hi (exact in float32)"""
+    w = np.ascontiguousarray(w, np.float32)
+    hi = _rna_tf32(w)
+    lo = (w - hi).astype(np.float32)
+    t = lambda m: m.reshape(m.shape[0], m.shape[1] // 4, 4).transpose(1, 0, 2).reshape(-1)
+    return np.concatenate([t(hi), t(lo)])
+
+
+class PackedLidarNet:
+    """device copy of the LiDAR barrier's networks in the layout of include/cbfrrt.h (cbfrrt_lidar_net)"""
+
+    def __init__(self, struct, tensors, meta):
+        self.struct, self._tensors, self.meta = struct, tensors, meta
+
+
+def pack_lidar_net(pc_head: dict, encoder: dict, h_nn: dict, n: int, n_sensors: int, point_dims: int = 6,
+                   device="cuda") -> PackedLidarNet:
+    """state dicts of the reference's modules -> PackedLidarNet.
+    pc_head: PointNetfeat (pointnet.py:20-48; keys backbone_nn.fc11 / fc2 / fc3, backbone_fc.fc2 / fc3), encoder:
+    PointNetVanillaEncoder (pointnet.py:78-90; encoder_nn.fc1 / fc2 / fc4), h_nn: input_linear / layer_i_linear /
+    output_linear (neural_lidar_cbf_controller.py:66-95)."""
+    g = lambda d, k: np.ascontiguousarray(d[k].detach().cpu().numpy() if isinstance(d[k], torch.Tensor) else d[k], np.float32)
+    w1 = g(pc_head, "backbone_nn.fc11.weight")
+    if w1.shape != (64, point_dims + n_sensors) or point_dims + n_sensors > 16:
+        raise ValueError(f"backbone_nn.fc11 must be (64, {point_dims + n_sensors}), got {w1.shape}")
+    w1p = np.zeros((64, 16), np.float32)
+    w1p[:, :w1.shape[1]] = w1
+    w2, w3 = g(pc_head, "backbone_nn.fc2.weight"), g(pc_head, "backbone_nn.fc3.weight")
+    if w2.shape != (128, 64) or w3.shape != (512, 128):
+        raise ValueError("backbone_nn must be 64 -> 128 -> 512 (pointnet.py:24-26)")
+    layers = sum(1 for k in h_nn if k.endswith("_linear.weight") and k.startswith("layer_"))
+    hidden = g(h_nn, "input_linear.weight").shape[0]
+    arrs = {
+        "w1t": _tf32_tiles(w1p), "w2t": _tf32_tiles(w2),
+        "w3t": np.concatenate([_tf32_tiles(w3[c * 64:(c + 1) * 64]) for c in range(8)]),
+        "bias": np.concatenate([g(pc_head, "backbone_nn.fc11.bias"), g(pc_head, "backbone_nn.fc2.bias"), g(pc_head, "backbone_nn.fc3.bias")]),
+        "fc2_w": g(pc_head, "backbone_fc.fc2.weight"), "fc2_b": g(pc_head, "backbone_fc.fc2.bias"),
+        "fc3_w": g(pc_head, "backbone_fc.fc3.weight"), "fc3_b": g(pc_head, "backbone_fc.fc3.bias"),
+        "e1_w": g(encoder, "encoder_nn.fc1.weight"), "e1_b": g(encoder, "encoder_nn.fc1.bias"),
+        "e2_w": g(encoder, "encoder_nn.fc2.weight"), "e2_b": g(encoder, "encoder_nn.fc2.bias"),
+        "e4_w": g(encoder, "encoder_nn.fc4.weight"), "e4_b": g(encoder, "encoder_nn.fc4.bias"),
+        "h_in_w": g(h_nn, "input_linear.weight"), "h_in_b": g(h_nn, "input_linear.bias"),
+        "h_hid_w": (np.concatenate([g(h_nn, f"layer_{i}_linear.weight").ravel() for i in range(layers)]) if layers else np.zeros(4, np.float32)),
+        "h_hid_b": (np.concatenate([g(h_nn, f"layer_{i}_linear.bias").ravel() for i in range(layers)]) if layers else np.zeros(4, np.float32)),
+        "h_out_w": g(h_nn, "output_linear.weight"), "h_out_b": g(h_nn, "output_linear.bias"),
+    }
+    pf, fd = arrs["fc3_w"].shape[0], arrs["e4_w"].shape[0]
+    if arrs["e1_w"].shape[1] != n_sensors * pf or arrs["h_in_w"].shape[1] != n + fd:
+        raise ValueError("encoder / h_nn input widths do not match n_sensors * per_feature_dim / n + feature_dim")
+    tensors = {k: torch.from_numpy(np.ascontiguousarray(v.ravel())).to(device) for k, v in arrs.items()}
+    st = LidarNet(n, n_sensors, point_dims, pf, fd, hidden, layers, 0, *[tensors[k].data_ptr() for k in (
+        "w1t", "w2t", "w3t", "bias", "fc2_w", "fc2_b", "fc3_w", "fc3_b", "e1_w", "e1_b", "e2_w", "e2_b", "e4_w", "e4_b",
+        "h_in_w", "h_in_b", "h_hid_w", "h_hid_b", "h_out_w", "h_out_b")])
+    return PackedLidarNet(st, tensors, dict(n=n, n_sensors=n_sensors, point_dims=point_dims, per_feature_dim=pf, feature_dim=fd,
+                                            hidden=hidden, layers=layers))
+
+
+def lidar_cbf(net: PackedLidarNet, q: Tensor, cloud: Tensor, frames: Tensor, sampled_index: Tensor, J_p: Tensor = None,
+              J_R: Tensor = None, delta: float = 0.0):
+    """LiDAR barrier value (and, with the frame Jacobians, its one-sided numerical Jacobian) for B states in one call
+    (include/cbfrrt.h cbfrrt_lidar_cbf).  q [B,n], cloud [B,P,pd], frames [B,S,12], sampled_index i32 [S,R]
+    -> h [B]  or  (h [B], J [B,n]) when J_p [B,S,3,n], J_R [B,S,9,n] and delta are given."""
+    m = net.meta
+    q, cloud, frames = _f32c(q), _f32c(cloud), _f32c(frames)
+    for t in (q, cloud, frames, sampled_index):
+        if not t.is_cuda:
+            raise NotImplementedError("cbfrrt::lidar_cbf needs CUDA tensors; there is no CPU path")
+    B, dev = q.shape[0], q.device
+    sampled_index = sampled_index.to(torch.int32).contiguous()
+    if (q.shape != (B, m["n"]) or cloud.dim() != 3 or cloud.shape[0] != B or cloud.shape[2] != m["point_dims"]
+            or tuple(frames.shape) != (B, m["n_sensors"], 12) or sampled_index.dim() != 2 or sampled_index.shape[0] != m["n_sensors"]):
+        raise ValueError("lidar_cbf: inconsistent shapes")
+    want_j = J_p is not None
+    if want_j:
+        J_p, J_R = _f32c(J_p).reshape(B, m["n_sensors"], 3, m["n"]), _f32c(J_R).reshape(B, m["n_sensors"], 9, m["n"])
+    ws = torch.empty(int(lib.cbfrrt_lidar_workspace_bytes(C.byref(net.struct), B, int(want_j))), dtype=torch.uint8, device=dev)
+    h = torch.empty(B, dtype=torch.float32, device=dev)
+    J = torch.empty((B, m["n"]), dtype=torch.float32, device=dev) if want_j else None
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_lidar_cbf(C.byref(net.struct), _ptr(q), _ptr(cloud), cloud.shape[1], _ptr(frames),
+                                   _ptr(J_p) if want_j else None, _ptr(J_R) if want_j else None, _ptr(sampled_index),
+                                   int(sampled_index.shape[1]), B, float(delta), _ptr(ws), _ptr(h), _ptr(J) if want_j else None,
+                                   _stream()), "cbfrrt_lidar_cbf")
+    del ws
+    return (h, J) if want_j else h
 
 
 MLP_PATHS = {"auto": 0, "fma": 1, "tc": 2}

@@ -101,6 +101,9 @@ int cbfrrt_cbf_filter(int n, const cbfrrt_cbf_net* net, const float* datax, int6
     if (B == 0) return CBFRRT_OK;
     FilterOutPtrs out{h, J, u, r};
     cudaStream_t st = (cudaStream_t)stream;
+    if (!net_is_fast(net))
+        return n == Panda::N ? launch_filter_generic<Panda::N>(na, net->hidden, net->layers, datax, B, out, st)
+                             : launch_filter_generic<Magician::N>(na, net->hidden, net->layers, datax, B, out, st);
     return n == Panda::N ? launch_filter<Panda::N>(na, datax, B, out, st) : launch_filter<Magician::N>(na, datax, B, out, st);
 }
 
@@ -193,6 +196,16 @@ int cbfrrt_safety_filter(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_
     FilterOutPtrs fo{h, J, u, r};
     PeerOut po{};
     cudaStream_t st = (cudaStream_t)stream;
+    if (!net_is_fast(net)) {
+        // other network shapes: two launches (observation, then the generic filter on it).  The library never
+        // allocates, so the observation rows need the caller's datax buffer.
+        if (!datax) return CBFRRT_ERR_UNSUPPORTED;
+        rc = robot == CBFRRT_ROBOT_PANDA ? launch_collide_panda(sc, q, q_stride, B, thr_soft, thr_hard, co, st)
+                                         : launch_collide_magician(sc, q, q_stride, B, thr_soft, thr_hard, co, st);
+        if (rc) return rc;
+        return n == Panda::N ? launch_filter_generic<Panda::N>(na, net->hidden, net->layers, datax, B, fo, st)
+                             : launch_filter_generic<Magician::N>(na, net->hidden, net->layers, datax, B, fo, st);
+    }
     return robot == CBFRRT_ROBOT_PANDA ? launch_safety_panda(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, po, st)
                                        : launch_safety_magician(sc, na, q, q_stride, B, thr_soft, thr_hard, co, fo, po, st);
 }
@@ -223,6 +236,7 @@ int cbfrrt_safety_filter_scatter(int robot, const cbfrrt_scene* scene, const cbf
     if (rc) return rc;
     rc = check_net(n, net, fp, B, na);
     if (rc) return rc;
+    if (!net_is_fast(net)) return CBFRRT_ERR_UNSUPPORTED;
     if (B == 0) return CBFRRT_OK;
     CollideOutPtrs co{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     FilterOutPtrs fo{nullptr, nullptr, nullptr, nullptr};
@@ -340,6 +354,8 @@ int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* n
     if (rc) return rc;
     rc = check_net(n, net, fp, T, na);
     if (rc) return rc;
+    if (!net_is_fast(net)) return CBFRRT_ERR_UNSUPPORTED;   // the fused steer loop is built for 48 x 2; other shapes: the
+                                                            // host loop over cbfrrt_collide + cbfrrt_cbf_filter (steer())
     if (T == 0) return CBFRRT_OK;
     const RolloutArgs ra{rp->steps, rp->ctrl_every, rp->dt, rp->stuck_lag, rp->stuck_after, rp->stuck_eps, rp->keep_going, rp->stuck_mode};
     cudaStream_t st = (cudaStream_t)stream;

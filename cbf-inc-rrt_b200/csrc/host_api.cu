@@ -98,7 +98,7 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
     if (device < 0 || device >= 16 || B < 0 || !scene || !weights || !q || !goal || !K || !u_lo || !u_hi)
         return CBFRRT_ERR_BAD_SHAPE;
     if (goal_rows != 1 && goal_rows != B) return CBFRRT_ERR_BAD_SHAPE;
-    if (hidden < 4 || hidden > 64 || hidden % 4 || layers < 0 || layers > 8) return CBFRRT_ERR_UNSUPPORTED;
+    if (hidden < 1 || layers < 0) return CBFRRT_ERR_BAD_SHAPE;
     // packed weight count of include/cbfrrt.h: a short buffer would make the kernels read past the staged copy
     const int64_t in_pad = (n + 1 + 3) & ~3;
     if (n_weights != (int64_t)hidden * in_pad + hidden + (int64_t)layers * (hidden * hidden + hidden) + hidden + 4)
@@ -198,7 +198,7 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
             fp.goal_rows = rows;
         }
         rc = cbfrrt_safety_filter(robot, &dsc, &net, l.q, n, rows, &fp, thr_soft, thr_hard, safe ? l.safe : nullptr,
-                                  unsafe ? l.unsafe : nullptr, datax ? l.datax : nullptr, h ? l.h : nullptr,
+                                  unsafe ? l.unsafe : nullptr, (datax || hidden != 48 || layers != 2) ? l.datax : nullptr, h ? l.h : nullptr,
                                   J ? l.J : nullptr, u ? l.u : nullptr, r ? l.r : nullptr, l.st);
         if (rc) return fail(rc);
         if (safe) CKL(cudaMemcpyAsync(safe + off, l.safe, rows, cudaMemcpyDeviceToHost, l.st));

@@ -340,6 +340,94 @@ __global__ void __launch_bounds__(NT) filter_kernel(NetArgs net, const float* __
     }
 }
 
+// Barrier networks of ANY shape (cbf_hidden_layers / cbf_hidden_size are hyper-parameters of the reference:
+// neural_cbf/training/train_arm_mindis.py:176-177, neural_mindis_cbf_controller.py:41-53).  The specialised kernels are
+// built for the shape every shipped entry point uses (48 x 2); everything else runs here: one state per thread, CTAs of
+// 32 threads, weights read through the read-only path (every lane the same address: one broadcast per load), all layer
+// activations of the thread parked in a conflict-free shared-memory column (they double as the ReLU masks of the reverse
+// pass).  Same contract and packing as filter_kernel; O(L H^2) loads per state, so it is a compatibility path, not a fast
+// one.  Dynamic shared memory: 32 * (L + 2) * H floats (+ parameters).
+constexpr int GEN_NT = 32;
+template <int N>
+__global__ void __launch_bounds__(GEN_NT) filter_kernel_generic(NetArgs net, int H, int L, const float* __restrict__ datax,
+                                                                long long B, FilterOutPtrs out) {
+    extern __shared__ __align__(16) float smem_raw[];
+    constexpr int N_IN = N + 1, IN_PAD = (N_IN + 3) & ~3;
+    float* prm = smem_raw;                                     // ParamLayout<N>
+    float* act = smem_raw + ParamLayout<N>::TOTAL;             // [(L + 1) * H][32] activations, then [H][32] gradient
+    using PL = ParamLayout<N>;
+    for (int i = threadIdx.x; i < N * N; i += GEN_NT) prm[PL::K + i] = net.K ? net.K[i] : 0.f;
+    for (int i = threadIdx.x; i < N; i += GEN_NT) { prm[PL::LO + i] = net.u_lo[i]; prm[PL::HI + i] = net.u_hi[i]; }
+    __syncthreads();
+    const float* __restrict__ w = net.weights;
+    const float* W_in = w;
+    const float* b_in = w + H * IN_PAD;
+    const float* hid = b_in + H;
+    const long long hid_stride = (long long)H * H + H;
+    const float* w_out = hid + L * hid_stride;
+    const float* b_out = w_out + H;
+    const int lane = threadIdx.x;
+    float* grad = act + (L + 1) * H * GEN_NT;
+    for (long long b = (long long)blockIdx.x * GEN_NT + lane; b < B; b += (long long)gridDim.x * GEN_NT) {
+        const float* d = datax + b * (2 * N + 1);
+        float x[N_IN], q[N], dodq[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) { q[k] = __ldg(d + k); x[k] = q[k]; dodq[k] = __ldg(d + N + 1 + k); }
+        x[N] = __ldg(d + N);
+        for (int j = 0; j < H; ++j) {                          // input layer
+            float sacc = __ldg(b_in + j);
+#pragma unroll
+            for (int k = 0; k < N_IN; ++k) sacc = fmaf(__ldg(W_in + j * IN_PAD + k), x[k], sacc);
+            act[j * GEN_NT + lane] = fmaxf(sacc, 0.f);
+        }
+        for (int l = 0; l < L; ++l) {                          // hidden layers
+            const float* Wl = hid + l * hid_stride;
+            const float* bl = Wl + (long long)H * H;
+            const float* a_in = act + l * H * GEN_NT;
+            float* a_out = act + (l + 1) * H * GEN_NT;
+            for (int j = 0; j < H; ++j) {
+                float s0 = __ldg(bl + j), s1 = 0.f;
+                int k = 0;
+                for (; k + 1 < H; k += 2) {
+                    s0 = fmaf(__ldg(Wl + (long long)j * H + k), a_in[k * GEN_NT + lane], s0);
+                    s1 = fmaf(__ldg(Wl + (long long)j * H + k + 1), a_in[(k + 1) * GEN_NT + lane], s1);
+                }
+                if (k < H) s0 = fmaf(__ldg(Wl + (long long)j * H + k), a_in[k * GEN_NT + lane], s0);
+                a_out[j * GEN_NT + lane] = fmaxf(s0 + s1, 0.f);
+            }
+        }
+        const float* a_last = act + L * H * GEN_NT;
+        float h = __ldg(b_out);
+        for (int k = 0; k < H; ++k) {
+            const float a = a_last[k * GEN_NT + lane], wo = __ldg(w_out + k);
+            h = fmaf(wo, a, h);
+            grad[k * GEN_NT + lane] = a > 0.f ? wo : 0.f;      // seed of the reverse pass
+        }
+        for (int l = L - 1; l >= 0; --l) {                     // reverse mode through the hidden layers, in place
+            const float* Wl = hid + l * hid_stride;
+            float* a_prev = act + l * H * GEN_NT;              // relu outputs of layer l: mask, then overwritten by g_prev
+            for (int k = 0; k < H; ++k) {
+                float acc = 0.f;
+                for (int j = 0; j < H; ++j) acc = fmaf(__ldg(Wl + (long long)j * H + k), grad[j * GEN_NT + lane], acc);
+                a_prev[k * GEN_NT + lane] = a_prev[k * GEN_NT + lane] > 0.f ? acc : 0.f;
+            }
+            for (int k = 0; k < H; ++k) grad[k * GEN_NT + lane] = a_prev[k * GEN_NT + lane];
+        }
+        float jac[N_IN];
+#pragma unroll
+        for (int k = 0; k < N_IN; ++k) jac[k] = 0.f;
+        for (int j = 0; j < H; ++j) {
+            const float gj = grad[j * GEN_NT + lane];
+#pragma unroll
+            for (int k = 0; k < N_IN; ++k) jac[k] = fmaf(__ldg(W_in + j * IN_PAD + k), gj, jac[k]);
+        }
+        float g[N], J[N], u[N], r;
+        load_goal<N>(net, b, g);
+        cbf_filter_post<N>(prm, q, dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, jac, J, u, r);
+        write_filter<N>(out, b, h, J, u, r);
+    }
+}
+
 // stand-alone QP (CLFController.solve_CLF_QP with caller-computed Lie derivatives)
 template <int N>
 __global__ void __launch_bounds__(256) qp_kernel(const float* __restrict__ a, const float* __restrict__ c,
@@ -1093,11 +1181,17 @@ inline SceneArgs scene_for(const SceneArgs& sc, long long rows, bool is_rollout)
     return a;
 }
 
+constexpr long long GEN_MAX_UNITS = 1536;   // (layers + 2) * hidden: 32 threads x 1536 floats = 192 KB of shared memory
+inline bool net_is_fast(const cbfrrt_cbf_net* net) { return net->hidden == 48 && net->layers == 2; }
+
 inline int check_net(int n, const cbfrrt_cbf_net* net, const cbfrrt_filter_params* fp, long long B, NetArgs& a) {
     if (!net || !fp || !net->weights || !fp->u_lo || !fp->u_hi) return CBFRRT_ERR_BAD_SHAPE;
     if (!fp->u_ref && (!fp->goal || !fp->K)) return CBFRRT_ERR_BAD_SHAPE;
     if (net->n_in != n + 1) return CBFRRT_ERR_BAD_SHAPE;
-    if (net->hidden != 48 || net->layers != 2) return CBFRRT_ERR_UNSUPPORTED;
+    if (net->hidden < 1 || net->layers < 0) return CBFRRT_ERR_BAD_SHAPE;
+    // 48 x 2 has the specialised kernels; other shapes run filter_kernel_generic (cbf_filter, safety_filter) as long as
+    // a 32-thread CTA's activations fit in shared memory; the fused rollout exists for 48 x 2 only
+    if (!net_is_fast(net) && (long long)(net->layers + 2) * net->hidden > GEN_MAX_UNITS) return CBFRRT_ERR_UNSUPPORTED;
     if (!fp->u_ref && fp->goal_rows != 1 && fp->goal_rows != B) return CBFRRT_ERR_BAD_SHAPE;
     if (!aligned16(net->weights)) return CBFRRT_ERR_ALIGNMENT;
     a = NetArgs{net->weights, fp->K, fp->u_lo, fp->u_hi, fp->goal, (long long)fp->goal_rows, fp->cbf_lambda,
@@ -1144,6 +1238,26 @@ static int launch_collide(const SceneArgs& sc_in, const float* q, long long qs, 
 extern std::atomic<int> g_mlp_path;
 inline bool use_tc() { return g_mlp_path.load(std::memory_order_relaxed) != CBFRRT_MLP_FMA; }
 inline bool force_tc() { return g_mlp_path.load(std::memory_order_relaxed) == CBFRRT_MLP_TC; }
+
+template <int N>
+static int launch_filter_generic(const NetArgs& net, int H, int L, const float* datax, long long B, const FilterOutPtrs& out,
+                                 cudaStream_t st) {
+    const size_t smem = 4 * ((size_t)ParamLayout<N>::TOTAL + (size_t)GEN_NT * (L + 2) * H);
+    auto k = filter_kernel_generic<N>;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mu);
+        const CfgKey key{current_device(), reinterpret_cast<const void*>(k), smem};
+        if (g_cfg.find(key) == g_cfg.end()) {
+            if (smem > 48 * 1024 &&
+                cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return CBFRRT_ERR_CUDA;
+            g_cfg[key] = 1;
+        }
+    }
+    const long long tiles = (B + GEN_NT - 1) / GEN_NT;
+    const long long cap = (long long)num_sms() * 16;
+    k<<<(int)(tiles < cap ? tiles : cap), GEN_NT, smem, st>>>(net, H, L, datax, B, out);
+    return finish_launch();
+}
 
 template <int N>
 static int launch_filter(const NetArgs& net, const float* datax, long long B, const FilterOutPtrs& out, cudaStream_t st) {

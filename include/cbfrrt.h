@@ -71,8 +71,11 @@ typedef struct {
 
 typedef struct {
     int32_t n_in;          /* n + 1 */
-    int32_t hidden;        /* cbf_hidden_size  (48 in every shipped entry point) */
-    int32_t layers;        /* cbf_hidden_layers (2) */
+    int32_t hidden;        /* cbf_hidden_size  (48 in every shipped entry point; train_arm_mindis.py:176-177) */
+    int32_t layers;        /* cbf_hidden_layers (2).  48 x 2 runs the specialised (tcgen05 / FP32-FMA) kernels.  Any
+                              other shape with (layers + 2) * hidden <= 1536 runs a generic FP32 kernel in
+                              cbfrrt_cbf_filter and cbfrrt_safety_filter (there as two launches; datax must be given);
+                              cbfrrt_rollout and cbfrrt_safety_filter_scatter return CBFRRT_ERR_UNSUPPORTED for it */
     int32_t _pad;
     const float *weights;  /* device, packed as described above, 16-byte aligned */
 } cbfrrt_cbf_net;
@@ -286,6 +289,44 @@ int cbfrrt_rollout(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_net *n
 /* ---- counter-based uniform state sampler (ControlAffineSystem.sample_state_space,
  * control_affine_system.py:291-300, made shard-invariant): row g = start_row + b, q[b,j] = lo_j + U(g,j)(hi_j-lo_j) */
 int cbfrrt_sample_states(int robot, uint32_t seed, uint64_t start_row, int64_t B, float *q, void *stream);
+
+/* ---- LiDAR / point-cloud barrier (the one GEMM-sized workload of the reference) ------------------------------
+ * Replaces NeuralLidarCBFController.h / h_with_jacobian (neural_cbf/controllers/neural_lidar_cbf_controller.py:115-219)
+ * with everything they call: ArmLidar.datax_to_x (neural_cbf/systems/arm_lidar.py:219-248: the sampled cloud points of
+ * every sensor taken to the sensor frame, R_s^T (x - p_s), normals R_s^T n), PointNetfeat (neural_cbf/controllers/
+ * utils/pointnet.py:13-70: [point | normal | one-hot sensor] -> 64 -> 128 -> 512 with LeakyReLU(0.1), max over the rays of
+ * a sensor, 512 -> 256 -> per_feature_dim), PointNetVanillaEncoder (pointnet.py:73-97), the h_nn head on [q | encoded],
+ * batch_lookahead (arm_lidar.py:250-288) and the one-sided differences J_k = (h(q + d e_k) - h(q)) / (2 d) (:205-213).
+ * The three per-point layers run on the tcgen05 tensor cores (TF32 3-term split, fp32-grade), the rest in FP32.
+ *
+ * Weights: the per-point layers as TF32 hi / lo tiles prepared by the host (cbfrrt.ops.pack_lidar_net documents the
+ * layout: no-swizzle K-major core matrices W4[k/4][n], layer 3 in 8 chunks of 64 outputs); everything after the
+ * max-pool as the raw torch tensors (row-major [out][in]).  All pointers device, 16-byte aligned. */
+typedef struct {
+    int32_t n;                /* joints (q_dims) */
+    int32_t n_sensors;        /* S <= 7 */
+    int32_t point_dims;       /* 3, or 6 with normals (add_normal) */
+    int32_t per_feature_dim;  /* PointNetfeat output per sensor, <= 64 */
+    int32_t feature_dim;      /* encoder output, n + feature_dim <= 72 */
+    int32_t hidden, layers;   /* h_nn: (n + feature_dim) -> hidden x (layers + 1) -> 1, hidden <= 512 */
+    int32_t _pad;
+    const float *w1t, *w2t, *w3t, *bias;                /* backbone_nn tiles + [b1 | b2 | b3] */
+    const float *fc2_w, *fc2_b, *fc3_w, *fc3_b;         /* backbone_fc 512 -> 256 -> per_feature_dim */
+    const float *e1_w, *e1_b, *e2_w, *e2_b, *e4_w, *e4_b; /* encoder_nn S*PF -> 512 -> 256 -> feature_dim */
+    const float *h_in_w, *h_in_b, *h_hid_w, *h_hid_b, *h_out_w, *h_out_b; /* h_nn; h_hid_*: the `layers` blocks concatenated */
+} cbfrrt_lidar_net;
+
+/* bytes of device workspace for B states (with_jacobian: n + 1 evaluations per state) */
+int64_t cbfrrt_lidar_workspace_bytes(const cbfrrt_lidar_net *net, int64_t B, int32_t with_jacobian);
+
+/* q [B, n]; cloud [B, n_cloud, point_dims] (world frame); frames [B, S, 12] = per sensor origin (3) | rotation (9,
+ * row-major); sampled_index [S, rays] int32 = the cloud indices of every sensor's rays (ONE draw for the whole batch,
+ * as the reference's torch.randint inside datax_to_x, arm_lidar.py:236-238); rays % 32 == 0.
+ * h [B] (optional).  J [B, n] optional: then J_p [B, S, 3, n] and J_R [B, S, 9, n] (the frame Jacobians of
+ * data_jacobian) and delta = controller_dt / 2 are required. */
+int cbfrrt_lidar_cbf(const cbfrrt_lidar_net *net, const float *q, const float *cloud, int64_t n_cloud, const float *frames,
+                     const float *J_p, const float *J_R, const int32_t *sampled_index, int32_t rays, int64_t B,
+                     float delta, void *workspace, float *h, float *J, void *stream);
 
 /* ---- host-buffer front end (what a ctypes / numpy caller of the reference would use) ----------------------
  * Same semantics as cbfrrt_safety_filter but every pointer (including scene, weights and parameters) is a

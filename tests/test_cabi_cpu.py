@@ -50,9 +50,13 @@ def test_argument_validation_happens_before_cuda():
     assert lib.cbfrrt_collide(0, C.byref(big), p, 7, 1, 0.02, 0.0, *([None] * 6), None) == -3  # > MAX_OBSTACLES
     mis = _lib.Scene(1, 0, 1, 0, C.c_void_p(p.value + 4), None, None)
     assert lib.cbfrrt_collide(0, C.byref(mis), p, 7, 1, 0.02, 0.0, *([None] * 6), None) == -5  # alignment
-    net = _lib.CbfNet(8, 64, 2, 0, p)
+    net = _lib.CbfNet(8, 1024, 2, 0, p)
     fp = _lib.FilterParams(p, 1, p, p, p, 0.1, 5000.0, None)
-    assert lib.cbfrrt_cbf_filter(7, C.byref(net), p, 1, C.byref(fp), p, p, p, p, None) == -3   # hidden != 48
+    assert lib.cbfrrt_cbf_filter(7, C.byref(net), p, 1, C.byref(fp), p, p, p, p, None) == -3   # (layers + 2) * hidden > 1536
+    net = _lib.CbfNet(8, 64, 3, 0, p)                                                      # generic shape: fine for the
+    rp = _lib.RolloutParams(10, 4, 0.01, 0, 10, 0.1, 0, 0)                                 # filter, not for the fused rollout
+    assert lib.cbfrrt_rollout(0, C.byref(sc), C.byref(net), p, 1, C.byref(fp), C.byref(rp), 0.02, 0.0, p, p, p, None, None) == -3
+    assert lib.cbfrrt_safety_filter(0, C.byref(sc), C.byref(net), p, 7, 1, C.byref(fp), 0.02, 0.0, p, p, None, p, p, p, p, None) == -3  # needs datax
     net = _lib.CbfNet(8, 48, 2, 0, p)
     fp = _lib.FilterParams(p, 3, p, p, p, 0.1, 5000.0, None)
     assert lib.cbfrrt_cbf_filter(7, C.byref(net), p, 5, C.byref(fp), p, p, p, p, None) == -2   # goal_rows not in {1,B}

@@ -266,3 +266,50 @@ def test_batched_steer_reference_semantics_gpu(coracle):
             tr = traj.cpu().numpy()
             for b in np.nonzero(same)[0][:40]:
                 assert np.abs(tr[b, :do_[b]] - to[b, :do_[b]]).max() < 1e-4
+
+
+@pytest.mark.parametrize("robot,hidden,layers", [("panda", 64, 2), ("panda", 48, 3), ("magician", 32, 1), ("panda", 128, 4),
+                                                 ("magician", 17, 0), ("panda", 256, 2)])
+def test_generic_network_shapes(coracle, robot, hidden, layers):
+    """cbf_hidden_size / cbf_hidden_layers other than 48 x 2 (train_arm_mindis.py:176-177): the generic FP32 kernel behind
+    cbfrrt_cbf_filter and cbfrrt_safety_filter against the float64 truth / the oracle, and through the controller mirror"""
+    from cbfrrt import ops, workloads as W
+    w = _workload(robot)
+    n, rid, B = w["n"], ops.ROBOT_ID[robot], 3000
+    sd, _ = W.make_state_dict(n, seed=5, hidden=hidden, layers=layers)
+    wp = W.pack_weights_np(sd, n, hidden, layers)
+    net = ops.pack_weights(sd, n, hidden, layers, device=DEV)
+    boxes = W.random_boxes(8, 2, 0.05, 0.12)
+    b8, s4, gr = _scene(boxes, None)
+    q = W.sample_states(robot, B, 71)
+    goal = W.sample_states(robot, B, 72)
+    args = (_t(q), _t(goal), b8, s4, 1, gr, net, _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"], w["thr_soft"],
+            w["thr_hard"], rid, hidden, layers)
+    safe, unsafe, datax, h, J, u, r = ops.safety_filter(*args)
+    o = coracle.collide(robot, q, boxes, None, True, w["thr_soft"], w["thr_hard"])
+    assert np.array_equal(safe.cpu().numpy(), o["safe"]) and np.array_equal(datax.cpu().numpy()[:, :n + 1], o["datax"][:, :n + 1])
+    if hidden <= 128 and layers <= 4:          # the C oracle's own limits (MAXH, MAXL); the float64 truth shares them
+        of = coracle.cbf_filter(n, wp, hidden, layers, datax.cpu().numpy(), goal, w["K"], w["u_lo"], w["u_hi"], w["lam"], w["penalty"])
+        assert rel_err(h.cpu().numpy(), of["h"], floor=0.1) < TOL
+        tr = coracle.cbf_filter_f64(n, wp, hidden, layers, datax.cpu().numpy(), goal, w["K"], w["u_lo"], w["u_hi"], w["lam"], w["penalty"])
+        away = tr["margin"] > 1e-5
+        assert away.mean() > 0.9
+        assert rel_err(h.cpu().numpy(), tr["h"], floor=0.1) < TOL and rel_err(J.cpu().numpy()[away], tr["J"][away], floor=0.1) < TOL
+        eu = np.abs(u.cpu().numpy() - tr["u"]).max(1)
+        bound = TOL * np.maximum(1.0, np.abs(tr["u"]).max(1)) + 2.0 * (tr["kappa_c"] * np.abs(w["lam"] * (h.cpu().numpy() - tr["h"]))
+                                                                      + tr["kappa_a"] * np.abs(J.cpu().numpy() - tr["J"]).max(1))
+        assert (eu[away] <= bound[away]).all()
+    else:                                      # beyond the oracle's table sizes: torch float64 on the CPU
+        net64 = W.make_state_dict(n, seed=5, hidden=hidden, layers=layers)[1].double()
+        x = torch.as_tensor(datax.cpu().numpy()[:, :n + 1], dtype=torch.float64)
+        assert rel_err(h.cpu().numpy(), net64(x)[:, 0].detach().numpy(), floor=0.1) < TOL
+    v2, u2 = ops.valid_control(*args)
+    assert torch.equal(v2, safe) and torch.equal(u2, u)
+    h2, J2, u3, r2 = ops.cbf_filter(datax, _t(goal), net, _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"], hidden, layers,
+                                    torch.empty(0, device=DEV))
+    assert torch.equal(h2, h) and torch.equal(u3, u)
+    # the fused rollout is built for 48 x 2 only and says so
+    from cbfrrt._lib import CbfrrtError
+    with pytest.raises(CbfrrtError):
+        ops.rollout(_t(q[:10]), _t(goal[:10]), 5, 4, 1 / 120, 0, 10, 0.1, False, False, b8, s4, 1, gr, net, _t(w["K"]), _t(w["u_lo"]),
+                    _t(w["u_hi"]), w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, hidden, layers)
