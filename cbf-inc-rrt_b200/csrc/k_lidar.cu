@@ -1,5 +1,6 @@
 // k_lidar.cu -- C-ABI of the LiDAR / PointNet barrier (include/cbfrrt.h: cbfrrt_lidar_*), kernels in lidar.cuh
 #include <atomic>
+#include <cstdlib>
 
 #include "lidar.cuh"
 
@@ -63,16 +64,23 @@ extern "C" int cbfrrt_lidar_cbf(const cbfrrt_lidar_net* net, const float* q, con
     const long long nk = n_groups * lidar::N3;
     lidar::preset_keys<<<(unsigned)((nk + 255) / 256 < 4096 ? (nk + 255) / 256 : 4096), 256, 0, st>>>(keys, nk);
     if ((rc = finish())) return rc;
-    const size_t smem = lidar::S_TOTAL * sizeof(float);
+    static const bool use_v1 = [] { const char* e = getenv("CBFRRT_LIDAR_V1"); return e && e[0] == '1'; }();
+    const size_t smem = (use_v1 ? lidar::S_TOTAL : lidar::v2::S_TOTAL) * sizeof(float);
     static std::atomic<unsigned long long> configured{0};   // bit per device
     if (!((configured.load() >> (dev & 63)) & 1ull)) {
-        if (cudaFuncSetAttribute(lidar::backbone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(lidar::backbone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(lidar::S_TOTAL * sizeof(float))) != cudaSuccess ||
+            cudaFuncSetAttribute(lidar::v2::backbone_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(lidar::v2::S_TOTAL * sizeof(float))) != cudaSuccess)
             return CBFRRT_ERR_CUDA;
         configured.fetch_or(1ull << (dev & 63));
     }
     const long long tiles = (n_points + lidar::PT - 1) / lidar::PT;
-    lidar::backbone_kernel<<<(unsigned)(tiles < sms ? tiles : sms), lidar::PT, smem, st>>>(a, n_points, net->w1t, net->w2t, net->w3t,
-                                                                                          net->bias, keys);
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    if (use_v1)
+        lidar::backbone_kernel<<<grid, lidar::PT, smem, st>>>(a, n_points, net->w1t, net->w2t, net->w3t, net->bias, keys);
+    else
+        lidar::v2::backbone_kernel_v2<<<grid, lidar::PT, smem, st>>>(a, n_points, net->w1t, net->w2t, net->w3t, net->bias, keys);
     if ((rc = finish())) return rc;
     lidar::head_kernel<<<(unsigned)n_eval, 256, 0, st>>>(keys, a, *net, h_eval);
     if ((rc = finish())) return rc;

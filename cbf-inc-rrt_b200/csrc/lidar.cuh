@@ -241,6 +241,215 @@ __global__ void __launch_bounds__(PT, 1) backbone_kernel(CloudArgs a, long long 
     if (c.t < 32) tmem_dealloc(c.tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// backbone_kernel_v2: the same arithmetic, software-pipelined.  What changed against backbone_kernel (kept as the
+// reference implementation, CBFRRT_LIDAR_V1=1):
+//   * A_lo lives in TENSOR MEMORY next to A_hi (columns 256..383), so all three passes of the split are TS-form MMAs and
+//     the 64 KB shared-memory A_lo tile is gone -- which pays for a SECOND layer-3 weight buffer;
+//   * the layer-3 chunks (64 output columns = 64 KB of hi / lo tiles each) arrive by TMA bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx) into the two buffers, issued as soon as the MMAs that read a buffer have
+//     completed: the copy of chunk c + 1 overlaps the MMAs of chunk c and the epilogue of chunk c - 1;
+//   * two accumulators (TMEM columns 0..63 / 64..127): the MMAs of chunk c run while all four warps reduce chunk c - 1;
+//   * epilogue: max over the warp's rows FIRST (REDUX on the ordered-int image of the raw accumulator), then bias +
+//     LeakyReLU once per (warp, column) -- both are monotone, so max(leaky(x + b)) = leaky(max(x) + b).
+namespace v2 {
+constexpr int COL_ALO = 256;
+constexpr int CH_FLOATS = 2 * N2 * NCH;                     // one chunk: [hi | lo] 128 x 64
+constexpr uint32_t CH_BYTES = CH_FLOATS * 4;
+constexpr int S_W1 = 0;
+constexpr int S_W2 = S_W1 + 2 * K1 * N1;
+constexpr int S_W3A = S_W2 + 2 * N1 * N2;                   // chunk buffer 0
+constexpr int S_W3B = S_W3A + CH_FLOATS;                    // chunk buffer 1
+constexpr int S_B = S_W3B + CH_FLOATS;
+constexpr int S_MBAR = S_B + N1 + N2 + N3;                  // 5 mbarriers: layer gemm, weights[2], accumulators[2]
+constexpr int S_TMEM = S_MBAR + 12;
+constexpr int S_TOTAL = S_TMEM + 4;
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+template <int K>
+__device__ __forceinline__ void store_a2(const Tile& c, const float* v) {
+    const uint32_t row = c.tmem + c.lane;
+#pragma unroll
+    for (int j = 0; j < K / 16; ++j) {
+        float lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) lo[i] = v[16 * j + i] - __uint_as_float(__float_as_uint(v[16 * j + i]) & 0xffffe000u);
+        tmem_st16(row + COLA + 16 * j, v + 16 * j);
+        tmem_st16(row + COL_ALO + 16 * j, lo);
+    }
+    tmem_st_wait();
+}
+
+// issue the three passes of D[d_col .. d_col + N) = A . B^T (warp 0, elected lane inside the wrappers) and commit to bar
+template <int K, int N>
+__device__ __forceinline__ void issue_mmas(const Tile& c, uint32_t d_col, const float* w_hi, const float* w_lo, uint64_t* bar) {
+    constexpr uint32_t idesc = instr_desc(N);
+    constexpr uint32_t B_LBO = N * 16, B_SBO = 128, B_STEP = 2 * N * 16;
+    const uint32_t b_hi = smem_addr(w_hi), b_lo = smem_addr(w_lo);
+    const uint32_t a_hi = c.tmem + COLA, a_lo = c.tmem + COL_ALO, d = c.tmem + d_col;
+#pragma unroll
+    for (int ks = 0; ks < K / 8; ++ks)
+        mma_tf32_ts(d, a_hi + 8 * ks, smem_desc(b_hi + ks * B_STEP, B_LBO, B_SBO), idesc, ks ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < K / 8; ++ks)
+        mma_tf32_ts(d, a_hi + 8 * ks, smem_desc(b_lo + ks * B_STEP, B_LBO, B_SBO), idesc, 1u);
+#pragma unroll
+    for (int ks = 0; ks < K / 8; ++ks)
+        mma_tf32_ts(d, a_lo + 8 * ks, smem_desc(b_hi + ks * B_STEP, B_LBO, B_SBO), idesc, 1u);
+    mma_commit(bar);
+}
+
+// synchronous GEMM of layers 1 and 2 into columns [0, N)
+template <int K, int N>
+__device__ __forceinline__ void gemm_sync(Tile& c, const float* w_hi, const float* w_lo, uint64_t* bar) {
+    fence_before_sync();
+    __syncthreads();
+    if (c.t < 32) {
+        fence_after_sync();
+        issue_mmas<K, N>(c, COLD, w_hi, w_lo, bar);
+    }
+    mbar_wait_parity(bar, c.phase);
+    c.phase ^= 1u;
+    fence_after_sync();
+}
+
+template <int NCOL>
+__device__ __forceinline__ void load_cols(const Tile& c, uint32_t col, float* v) {
+    const uint32_t row = c.tmem + c.lane + col;
+#pragma unroll
+    for (int j = 0; j < NCOL / 16; ++j) tmem_ld16(row + 16 * j, v + 16 * j);
+    tmem_ld_wait();
+}
+
+// reduce one 64-column chunk of the accumulator over the warp's 32 rows and merge it into the group's keys
+__device__ __forceinline__ void chunk_epilogue(const Tile& c, uint32_t d_col, int ch, bool active, int* __restrict__ out) {
+    float d[NCH];
+    load_cols<NCH>(c, d_col, d);
+    if (!active) return;
+    int mine0 = 0, mine1 = 0;
+    const int lane = c.t & 31;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int i = __float_as_int(d[k]);
+        const int key = __reduce_max_sync(0xffffffffu, i ^ ((i >> 31) & 0x7fffffff));
+        if (k == lane) mine0 = key;
+        if (k == lane + 32) mine1 = key;
+    }
+    const float* b3 = c.sm + S_B + N1 + N2 + ch * NCH;
+    atomicMax(out + ch * NCH + lane, ordered(leaky(unordered(mine0) + b3[lane])));
+    atomicMax(out + ch * NCH + lane + 32, ordered(leaky(unordered(mine1) + b3[lane + 32])));
+}
+
+__global__ void __launch_bounds__(PT, 1) backbone_kernel_v2(CloudArgs a, long long n_points, const float* __restrict__ w1t,
+                                                            const float* __restrict__ w2t, const float* __restrict__ w3t,
+                                                            const float* __restrict__ bias, int* __restrict__ out_max) {
+    extern __shared__ __align__(128) float sm[];
+    Tile c;
+    c.sm = sm;
+    c.t = threadIdx.x;
+    c.phase = 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S_MBAR);      // 0: layer gemm, 1..2: weights, 3..4: accumulators
+    for (int i = c.t; i < 2 * K1 * N1; i += PT) sm[S_W1 + i] = __ldg(w1t + i);
+    for (int i = c.t; i < 2 * N1 * N2; i += PT) sm[S_W2 + i] = __ldg(w2t + i);
+    for (int i = c.t; i < N1 + N2 + N3; i += PT) sm[S_B + i] = __ldg(bias + i);
+    if (c.t == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init1(bars + i);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (c.t < 32) tmem_alloc(reinterpret_cast<uint32_t*>(sm + S_TMEM), 512);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    c.tmem = *reinterpret_cast<uint32_t*>(sm + S_TMEM);
+    c.lane = (uint32_t)(c.t & ~31) << 16;
+    uint32_t ph_w[2] = {0u, 0u}, ph_d[2] = {0u, 0u};
+    float* const buf[2] = {sm + S_W3A, sm + S_W3B};
+
+    const long long n_tiles = (n_points + PT - 1) / PT;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long p = tile * PT + c.t;
+        const bool active = p < n_points;                  // R % 32 == 0: uniform over a warp
+        // both chunk buffers are free here (their last readers, the MMAs of chunks 6 and 7 of the previous tile, were
+        // waited for): start the copies of chunks 0 and 1 under layers 1 and 2
+        if (c.t == 0) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                mbar_expect_tx(bars + 1 + b, CH_BYTES);
+                tma_g2s(buf[b], w3t + (long long)b * CH_FLOATS, CH_BYTES, bars + 1 + b);
+            }
+        }
+        float v[N2];
+        {   // layer 1: K = 16, N = 64
+            float x[K1];
+#pragma unroll
+            for (int i = 0; i < K1; ++i) x[i] = 0.f;
+            if (active) point_row(a, p, x);
+            store_a2<K1>(c, x);
+            gemm_sync<K1, N1>(c, sm + S_W1, sm + S_W1 + K1 * N1, bars);
+            load_cols<N1>(c, COLD, v);
+#pragma unroll
+            for (int k = 0; k < N1; ++k) v[k] = leaky(v[k] + sm[S_B + k]);
+        }
+        {   // layer 2: K = 64, N = 128
+            store_a2<N1>(c, v);
+            gemm_sync<N1, N2>(c, sm + S_W2, sm + S_W2 + N1 * N2, bars);
+            load_cols<N2>(c, COLD, v);
+#pragma unroll
+            for (int k = 0; k < N2; ++k) v[k] = leaky(v[k] + sm[S_B + N1 + k]);
+        }
+        store_a2<N2>(c, v);                                 // A of layer 3 (hi and lo) stays in TMEM for all 8 chunks
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        int* out = out_max + ((tile * PT + (c.t & ~31)) / a.R) * N3;
+        for (int ch = 0; ch < CHUNKS; ++ch) {               // layer 3, pipelined: MMAs of chunk ch | epilogue of chunk ch - 1
+            const int b = ch & 1;
+            if (c.t < 32) {
+                mbar_wait_parity(bars + 1 + b, ph_w[b]);    // weights of chunk ch have landed
+                issue_mmas<N2, NCH>(c, (uint32_t)(b * NCH), buf[b], buf[b] + N2 * NCH, bars + 3 + b);
+            }
+            ph_w[b] ^= 1u;
+            if (ch >= 1) {
+                const int pb = b ^ 1;
+                mbar_wait_parity(bars + 3 + pb, ph_d[pb]);  // MMAs of chunk ch - 1 complete: accumulator pb ready, buffer pb free
+                ph_d[pb] ^= 1u;
+                fence_after_sync();
+                if (c.t == 0 && ch + 1 < CHUNKS) {
+                    mbar_expect_tx(bars + 1 + pb, CH_BYTES);
+                    tma_g2s(buf[pb], w3t + (long long)(ch + 1) * CH_FLOATS, CH_BYTES, bars + 1 + pb);
+                }
+                chunk_epilogue(c, (uint32_t)(pb * NCH), ch - 1, active, out);
+                fence_before_sync();
+                __syncthreads();                            // accumulator pb may be overwritten by chunk ch + 1
+                fence_after_sync();
+            }
+        }
+        {
+            const int pb = (CHUNKS - 1) & 1;
+            mbar_wait_parity(bars + 3 + pb, ph_d[pb]);
+            ph_d[pb] ^= 1u;
+            fence_after_sync();
+            chunk_epilogue(c, (uint32_t)(pb * NCH), CHUNKS - 1, active, out);
+            fence_before_sync();
+            __syncthreads();
+            fence_after_sync();
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (c.t < 32) tmem_dealloc(c.tmem, 512);
+}
+}  // namespace v2
+
 static __global__ void preset_keys(int* __restrict__ keys, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         keys[i] = (int)0x80000000;
