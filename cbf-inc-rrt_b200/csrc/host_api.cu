@@ -146,7 +146,7 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
     // broad phase (built once per scene, kept resident): dense scenes from a few thousand rows on; small scenes for
     // planner-sized calls, where the kernels prefer the field path (kernels.cuh: scene_for) and the build is a few us
     const int n_obs = scene->n_boxes + scene->n_spheres;
-    const bool use_grid = n_obs >= 1 && (n_obs >= 40 ? B >= 4096 : B <= 16384);
+    const bool use_grid = n_obs >= 1 && (n_obs >= 12 ? (B >= 4096 || B <= 16384) : B <= 16384);
     std::vector<unsigned char> image(16 + b8.size() * 4 + (size_t)scene->n_spheres * 16 + (size_t)n_weights * 4 + sizeof small);
     {
         unsigned char* w = image.data();

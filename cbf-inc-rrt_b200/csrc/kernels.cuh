@@ -728,6 +728,28 @@ __device__ __forceinline__ void flush_block(const float* __restrict__ stg, int t
         else *reinterpret_cast<float4*>(dst + 4 * i) = v;
     }
 }
+// Per-WARP coalesced row I/O: the 32 rows of a warp are 32 x W consecutive floats in global memory, i.e. W full 128-byte
+// lines.  Rows go through a warp-private staging block (conflict-free for odd W) with only a __syncwarp: instruction k
+// then moves floats [32 k, 32 k + 32) of the block -- one full line per instruction -- instead of 32 scattered 4-byte
+// pieces at a 4 W-byte stride (ncu, round 2: 2.9x the algorithmic DRAM write traffic with the strided stores).
+template <int W>
+__device__ __forceinline__ void warp_store_rows(float* __restrict__ stg, int lane, const float (&v)[W], float* __restrict__ dst) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < W; ++k) stg[lane * W + k] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < W; ++k) dst[32 * k + lane] = stg[32 * k + lane];
+}
+template <int W>
+__device__ __forceinline__ void warp_load_rows(float* __restrict__ stg, int lane, const float* __restrict__ src, float (&v)[W]) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < W; ++k) stg[32 * k + lane] = __ldg(src + 32 * k + lane);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < W; ++k) v[k] = stg[lane * W + k];
+}
 constexpr int VEC_Q = 1, VEC_OUT = 2, VEC_PEER = 4;   // which pointer sets are 16-byte aligned (checked on the host)
 
 template <class RB, int L, bool GRID, int GG>
@@ -752,6 +774,9 @@ __global__ void __launch_bounds__(GG * tc::M_TILE, 1) safety_kernel_tc(SceneArgs
     for (long long tile = (long long)blockIdx.x * GG + c.g; tile < n_tiles; tile += (long long)gridDim.x * GG) {
         const long long b0 = tile * tc::M_TILE, b = b0 + c.t;
         const bool active = b < B, full = b0 + tc::M_TILE <= B;      // full: uniform over the group
+        const long long bw = b0 + (c.t & ~31);                        // first row of this warp
+        const bool warp_full = bw + 32 <= B;                          // uniform over the warp
+        float* const wstg = alo + 2048 + ((c.t >> 5) & 3) * 512;      // warp-private staging inside the output region
         float qq[N], g[N], J[N], u[N], h, r;
 #pragma unroll
         for (int k = 0; k < N; ++k) { qq[k] = 0.f; g[k] = 0.f; }
@@ -766,6 +791,8 @@ __global__ void __launch_bounds__(GG * tc::M_TILE, 1) safety_kernel_tc(SceneArgs
             tc::group_sync(c.g);
 #pragma unroll
             for (int k = 0; k < N; ++k) qq[k] = alo[1024 + c.t * N + k];
+        } else if (warp_full && q_stride == N) {                       // the warp's 32 rows: N full lines
+            warp_load_rows<N>(wstg, c.t & 31, q + bw * N, qq);
         } else if (active) {
 #pragma unroll
             for (int k = 0; k < N; ++k) qq[k] = __ldg(q + b * q_stride + k);
@@ -815,13 +842,28 @@ __global__ void __launch_bounds__(GG * tc::M_TILE, 1) safety_kernel_tc(SceneArgs
                 }
             }
         }
-        if (active) {   // tail tile / unaligned pointers: per-row stores
-            if (!out_fast) {
-                write_collide<RB>(cout, b, qq, cr, thr_soft, thr_hard);
-                write_filter<N>(fout, b, h, J, u, r);
+        if (!out_fast && warp_full) {   // whole warp: rows through the warp's staging block, full-line stores
+            const int lane = c.t & 31;
+            if (cout.safe) cout.safe[b] = safe;
+            if (cout.unsafe) cout.unsafe[b] = unsafe;
+            if (cout.datax) {
+                float row[DX];
+#pragma unroll
+                for (int k = 0; k < N; ++k) { row[k] = qq[k]; row[N + 1 + k] = cr.dodq[k]; }
+                row[N] = cr.o;
+                warp_store_rows<DX>(wstg, lane, row, cout.datax + bw * DX);
             }
-            if (po.n && !peer_fast) write_peers<N>(po, b, safe, u);
+            if (cout.arg_link) cout.arg_link[b] = cr.arg_sphere >= 0 ? RB::sph_link(cr.arg_sphere) : -2;
+            if (cout.arg_obs) cout.arg_obs[b] = cr.arg_obs;
+            if (fout.h) fout.h[b] = h;
+            if (fout.r) fout.r[b] = r;
+            if (fout.J) warp_store_rows<N>(wstg, lane, J, fout.J + bw * N);
+            if (fout.u) warp_store_rows<N>(wstg, lane, u, fout.u + bw * N);
+        } else if (active && !out_fast) {   // tail warp: per-row stores
+            write_collide<RB>(cout, b, qq, cr, thr_soft, thr_hard);
+            write_filter<N>(fout, b, h, J, u, r);
         }
+        if (active && po.n && !peer_fast) write_peers<N>(po, b, safe, u);
     }
     tc::teardown<L, GG>(c);
 }
@@ -1151,7 +1193,7 @@ inline int finish_launch() {
     return CBFRRT_OK;
 }
 
-constexpr int GRID_MIN_OBSTACLES = 40;
+constexpr int GRID_MIN_OBSTACLES = 12;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -1166,14 +1208,18 @@ inline int check_scene(const cbfrrt_scene* sc, SceneArgs& a) {
 }
 
 // When to use the broad phase a caller supplied (results are bit-identical either way).  Measured on B200
-// (profiles/r2c_configs_*.jsonl): with >= 40 obstacles the distance-bound field always wins (256 boxes: masks 2.5x,
-// valid+u 1.8x over the round-1 candidate grid); below that the shared-memory sweep with ball culling has no global
-// loads at all and wins where calls are long dependent chains (rollouts, 8 boxes: 17 vs 35 ms) and ties on the fused
-// kernel, while planner-sized launches (<= SMALL_BATCH rows: cold instruction cache, one wave) are faster on the field
-// path's much smaller instruction stream (4096 states, 1 box: 68 -> 42 us).  CBFRRT_GRID_MIN overrides the threshold.
+// (profiles/r2c_configs_*.jsonl, r2j_configs*.jsonl): from about a dozen obstacles on the distance-bound field wins for
+// single-shot kernels (16 boxes, Magician: masks 0.176 -> 0.119 ms, fused 0.416 -> 0.373 ms per 2^20 states; 256 boxes,
+// Panda: masks 2.5x, valid+u 1.8x over the round-1 candidate grid).  Rollouts are long dependent chains of small sweeps:
+// there the shared-memory sweep with ball culling (no global loads at all) wins until the scene is dense (8 boxes: 17 vs
+// 35 ms), so they switch at GRID_MIN_OBSTACLES_ROLLOUT.  Planner-sized launches (<= SMALL_BATCH rows: cold instruction
+// cache, one wave) are faster on the field path's much smaller instruction stream whatever the scene (4096 states,
+// 1 box: 68 -> 42 us).  CBFRRT_GRID_MIN overrides both thresholds.
 constexpr long long SMALL_BATCH = 16384;
+constexpr int GRID_MIN_OBSTACLES_ROLLOUT = 40;
 inline SceneArgs scene_for(const SceneArgs& sc, long long rows, bool is_rollout) {
-    static const int grid_min = [] { const char* e = getenv("CBFRRT_GRID_MIN"); return e ? atoi(e) : GRID_MIN_OBSTACLES; }();
+    static const int grid_min_env = [] { const char* e = getenv("CBFRRT_GRID_MIN"); return e ? atoi(e) : -1; }();
+    const int grid_min = grid_min_env >= 0 ? grid_min_env : (is_rollout ? GRID_MIN_OBSTACLES_ROLLOUT : GRID_MIN_OBSTACLES);
     SceneArgs a = sc;
     const int n_obs = sc.n_boxes + sc.n_spheres;
     const bool use = sc.grid && (n_obs >= grid_min || (!is_rollout && rows <= SMALL_BATCH && n_obs >= 1));

@@ -554,8 +554,9 @@ def test_host_buffer_api_matches_device_api():
     w2 = W.pack_weights_np(sd2, n)
     b8b, s4b, grb = _scene(boxes2, w["spheres"])
     net2 = ops.pack_weights(sd2, n, 48, 2, device="cuda")
-    for bx, b8_, wt, net_ in ((boxes2, b8b, w2, net2), (w["boxes"], b8, w["weights"], _net(w)), (boxes2, b8b, w["weights"], _net(w))):
-        dev = ops.valid_control(_t(w["q"]), _t(w["goal"]), b8_, s4, 1, gr, net_, _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]),
+    for bx, b8_, gr_, wt, net_ in ((boxes2, b8b, grb, w2, net2), (w["boxes"], b8, gr, w["weights"], _net(w)), (boxes2, b8b, grb, w["weights"], _net(w))):
+        # (the broad phase belongs to ITS scene: the device-pointer API gets the grid built for the boxes it is given)
+        dev = ops.valid_control(_t(w["q"]), _t(w["goal"]), b8_, s4, 1, gr_, net_, _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]),
                                 w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], 1, 48, 2)
         ops.safety_filter_host("magician", w["q"], bx, w["spheres"], True, wt, 48, 2, w["goal"], w["K"],
                                w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], out)

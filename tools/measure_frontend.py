@@ -85,6 +85,25 @@ def main():
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     out.append(dict(op="EpisodicDataModule.sample_trajectories", trajectories=16, stored_states_per_trajectory=400, rows=int(xs.shape[0]),
                     wall_ms=dt * 1e3, stored_states_per_s=xs.shape[0] / dt, note="host wall clock; one observe launch per stored step"))
+    # planner-sized calls: the reference's real regime is 1-50 states per call (eval_batchrrt_mindis_cbfsteer.py:66);
+    # device time (CUDA events) and host wall time per call of the fused op, with the scene's broad phase built
+    import time as _t
+    w8 = W.config(3, scale=1e-9)
+    b8p, s4p = ops.pack_scene(w8["boxes"][:, :3], w8["boxes"][:, 3:], w8["spheres"], device=dev)
+    grp = ops.build_grid(b8p, s4p)
+    netp = ops.pack_weights(w8["state_dict"], 7, 48, 2, device=dev)
+    Kp, lop, hip, goalp = t(w8["K"]), t(w8["u_lo"]), t(w8["u_hi"]), t(w8["goal"][:1])
+    for Bq in (1, 16, 64, 1024, 4096):
+        qq = t(W.sample_states("panda", Bq, 3))
+        for name, fn in (("safety_filter", lambda: ops.safety_filter(qq, goalp, b8p, s4p, 1, grp, netp, Kp, lop, hip, 0.1, 5000.0, 0.02, 0.0, 0, 48, 2)),
+                         ("masks", lambda: ops.masks(qq, b8p, s4p, 1, grp, 0.02, 0.0, 0)),
+                         ("safety_filter (no broad phase)", lambda: ops.safety_filter(qq, goalp, b8p, s4p, 1, ops.no_grid(dev), netp, Kp, lop, hip, 0.1, 5000.0, 0.02, 0.0, 0, 48, 2))):
+            dev_ms = timed(fn, iters=20)
+            torch.cuda.synchronize(); t0 = _t.perf_counter()
+            for _ in range(200):
+                fn()
+            torch.cuda.synchronize(); wall = (_t.perf_counter() - t0) / 200
+            out.append(dict(op=f"planner-sized {name}", robot="panda", boxes=8, states=Bq, device_us=dev_ms * 1e3, host_wall_us_per_call=wall * 1e6))
     for r in out:
         print(json.dumps(r))
 
