@@ -93,3 +93,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "c_oracle" not in txt, os.path.join(dp, f)
+
+
+def test_fused_exchange_stores_are_multimem_in_the_ptx(tmp_path):
+    """The multicast form of the fused exchange must access the NVSwitch multicast address with multimem.* (PTX ISA).
+    ptxas lowers multimem.st to STG.E.STRONG.SYS on sm_100a, so the SASS shows no distinct mnemonic: the evidence is the
+    PTX of the store helpers of csrc/kernels.cuh, compiled here."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = tmp_path / "mm.cu"
+    src.write_text('#include "%s"\n__global__ void probe(float* p, float4 v) {\n'
+                   '    cbfrrt::multimem_st_v4(p, v.x, v.y, v.z, v.w);\n    cbfrrt::multimem_st_f32(p + 4, v.x);\n'
+                   '    cbfrrt::flush_block<true>(p, threadIdx.x, p + 8, 32);\n}\n'
+                   % os.path.join(ROOT, "cbf-inc-rrt_b200", "csrc", "kernels.cuh"))
+    ptx = tmp_path / "mm.ptx"
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=compute_100a", "-std=c++17", "--expt-relaxed-constexpr",
+                           "-diag-suppress", "20091", "-ptx", "-o", str(ptx), str(src)])
+    text = ptx.read_text()
+    assert text.count("multimem.st.relaxed.sys.global.v4.f32") >= 2 and "multimem.st.relaxed.sys.global.f32" in text
