@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy, float32) of the reference's LiDAR / point-cloud barrier path,
-SURVEY.md 8f rank 2.  No CUDA kernel exists for this row yet: this file and tests/golden/ref_lidar_panda.npz
-are step (a) of widening into it -- the oracle, pinned against the reference's own Python (tests/golden/make_lidar_golden.py
-executes neural_cbf/systems/arm_lidar.py, neural_cbf/controllers/neural_lidar_cbf_controller.py and
-neural_cbf/controllers/utils/pointnet.py unmodified).  Nothing in the product imports it.
+SURVEY.md 8f rank 2: the checker of cbfrrt_lidar_cbf (csrc/lidar.cuh, tests/test_gpu_lidar.py).  Pinned against the
+reference's own Python: tests/golden/make_lidar_golden.py executes neural_cbf/systems/arm_lidar.py,
+neural_cbf/controllers/neural_lidar_cbf_controller.py and neural_cbf/controllers/utils/pointnet.py unmodified and records
+tests/golden/ref_lidar_panda.npz (tests/test_lidar_oracle_cpu.py).  Nothing in the product imports it.
 
     datax = [q (n) | global point cloud (P x point_dims, world frame) | per-sensor frames (S x (p 3 | R 9))]
     datax_to_x        arm_lidar.py:219-248     per sensor: R sampled points -> sensor frame  R_s^T (x - p_s)  (+ normals R_s^T n)

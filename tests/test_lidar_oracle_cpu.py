@@ -1,4 +1,4 @@
-"""LiDAR / point-cloud barrier path -- ORACLE ONLY, no CUDA kernel yet.
+"""LiDAR / point-cloud barrier path: the oracle (the kernels are checked in tests/test_gpu_lidar.py).
 oracle/lidar_oracle.py (numpy) against the golden vectors recorded from the reference's own ArmLidar / PointNetfeat /
 PointNetVanillaEncoder / NeuralLidarCBFController (tests/golden/make_lidar_golden.py -> ref_lidar_panda.npz)."""
 import json
