@@ -81,6 +81,8 @@ SIGNATURES = {
     "cbfrrt_edge_validity_var": (C.c_int, [_I, C.POINTER(Scene), _P, _P, _L, _P, _L, _F, _F, _P, _P, _P]),
     "cbfrrt_rollout": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, C.POINTER(FilterParams),
                                  C.POINTER(RolloutParams), _F, _F, _P, _P, _P, _P, _P]),
+    "cbfrrt_rollout_segments": (C.c_int, [_I, C.POINTER(Scene), C.POINTER(CbfNet), _P, _L, C.POINTER(FilterParams),
+                                          C.POINTER(RolloutParams), C.c_int32, _F, _F, _P, _P, _P, _P, _P]),
     "cbfrrt_fma_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "cbfrrt_lidar_workspace_bytes": (C.c_int64, [C.POINTER(LidarNet), _L, C.c_int32]),
     "cbfrrt_lidar_cbf": (C.c_int, [C.POINTER(LidarNet), _P, _P, _L, _P, _P, _P, _P, C.c_int32, _L, _F, _P, _P, _P, _P]),

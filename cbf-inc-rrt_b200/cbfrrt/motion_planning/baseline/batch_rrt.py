@@ -13,7 +13,8 @@ import time
 import numpy as np
 import torch
 
-from .batch_tsa import explore_nearest, explore_nearest_each, steer as batch_steer, steer_fused_reference
+from .batch_tsa import (explore_nearest, explore_nearest_each, steer as batch_steer, steer_fused_reference,
+                        steer_segments_fused, MAX_FUSED_BATCH)
 from .tsa import _rollout
 
 
@@ -150,8 +151,16 @@ def global_explore(search_tree, dynamics_model, sample_states=None, steer_type="
     first_parents = [search_tree.non_terminal_idxes[j] for j in nearest_idxs]
     parents = list(first_parents)
     new_states, no_collisions = current, [True] * len(parents)
-    for _ in range(RRT_PARAM // 20):
-        new_states, no_collisions, edges = _steer_batch(dm, controller, steer_type, sample_states, current, 20)
+    n_seg = RRT_PARAM // 20
+    fused = steer_type == "cbf" and n_seg >= 1 and len(parents) <= MAX_FUSED_BATCH
+    if fused:   # all segments of the expansion in one launch and one read-back (cbfrrt_rollout_segments)
+        assert hasattr(controller, "u")
+        segments = steer_segments_fused(controller, dm, sample_states, current, n_seg, RRT_step=20)
+    for k in range(n_seg):
+        if fused:
+            new_states, no_collisions, edges = segments[k]
+        else:
+            new_states, no_collisions, edges = _steer_batch(dm, controller, steer_type, sample_states, current, 20)
         done = _goal_test(dm, new_states)
         for i in range(len(parents)):
             parents[i] = insert_new_state(search_tree, new_states[i], sample_states[i], edges[i], parents[i],

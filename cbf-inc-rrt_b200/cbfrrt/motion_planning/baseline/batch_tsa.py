@@ -11,6 +11,8 @@ import torch
 from ... import ops
 from .tsa import _rollout
 
+MAX_FUSED_BATCH = 128     # cbfrrt_rollout_segments: the rows of a batch share one CTA
+
 
 def explore_nearest(non_terminal_states, sample_states, batch, device="cuda"):
     """The nearest-neighbour selection of global_explore (batch_tsa.py:129-145) on the GPU (cbfrrt::knn):
@@ -114,3 +116,28 @@ def steer_fused_reference(controller, dynamics_model, sample_states, nearests, R
     traj_np = traj.cpu().numpy()
     xs_list = [[row for row in traj_np[i, :done_np[i]]] for i in range(traj_np.shape[0])]
     return qf.cpu().numpy(), [bool(a) for a in alive_np], xs_list
+
+
+@torch.no_grad()
+def steer_segments_fused(controller, dynamics_model, sample_states, nearests, n_segments, RRT_step=20):
+    """The segment loop of global_explore (batch_tsa.py:154-170: ``RRT_PARAM // 20`` batched steer calls, each starting
+    where the previous one ended) in ONE launch and ONE read-back (cbfrrt_rollout_segments), with the reference's
+    semantics per segment (batch_tsa.py:191-231, incl. the batch-wide early exit once every row is dead).
+    -> list over segments of (x_last (B,n) numpy, no_collisions [bool]*B, xs_list), exactly what ``n_segments``
+    consecutive ``steer(controller.u, ...)`` calls return.  B <= MAX_FUSED_BATCH."""
+    dm = dynamics_model
+    dm.set_intermediate_goals(np.asarray(sample_states))
+    q0 = torch.as_tensor(np.asarray(nearests), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
+    b, s, fl, gr = dm.env.scene
+    lo, hi = controller._limits()
+    seg_q, seg_alive, seg_done, traj = ops.rollout_segments(
+        q0, dm.goal_tensor(dm.device), int(n_segments), int(RRT_step), int(dm.controller_dt // dm.dt), float(dm.dt), 9, 10, 3e-2,
+        b, s, fl, gr, controller._weights(), dm.K_on(dm.device), lo, hi, float(controller.clf_lambda),
+        float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard), dm.robot.robot_id,
+        controller.h_hidden_size, controller.h_hidden_layers)
+    seg_q, seg_alive, seg_done, traj = seg_q.cpu().numpy(), seg_alive.cpu().numpy().astype(bool), seg_done.cpu().numpy(), traj.cpu().numpy()
+    out = []
+    for k in range(int(n_segments)):
+        xs = [[row for row in traj[i, k * RRT_step:k * RRT_step + seg_done[i, k]]] for i in range(traj.shape[0])]
+        out.append((seg_q[:, k], [bool(a) for a in seg_alive[:, k]], xs))
+    return out

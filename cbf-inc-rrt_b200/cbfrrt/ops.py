@@ -509,6 +509,33 @@ def rollout(q0: Tensor, goal: Tensor, steps: int, ctrl_every: int, dt: float, st
     return qf, alive, done, traj
 
 
+def rollout_segments(q0: Tensor, goal: Tensor, n_segments: int, seg_len: int, ctrl_every: int, dt: float, stuck_lag: int,
+                     stuck_after: int, stuck_eps: float, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, weights: Tensor,
+                     K: Tensor, u_lo: Tensor, u_hi: Tensor, lam: float, penalty: float, thr_soft: float, thr_hard: float,
+                     robot_id: int, hidden: int, layers: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """n_segments consecutive batched steer segments of ONE batch (T <= 128 rows) in one launch
+    (include/cbfrrt.h cbfrrt_rollout_segments; batch_tsa.py:154-170 over :191-231)
+    -> seg_q f32[T,n_seg,n], seg_alive u8[T,n_seg], seg_done i32[T,n_seg], traj f32[T,n_seg*seg_len,n]"""
+    n = ROBOT_N[robot_id]
+    q0 = _f32c(q0)
+    if q0.dim() != 2 or q0.shape[1] != n or not q0.is_cuda:
+        raise ValueError(f"q0 must be a CUDA tensor (T, {n})")
+    T, dev = q0.shape[0], q0.device
+    net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, T, lam, penalty, hidden, layers)
+    sc = _scene(boxes, spheres, floor, grid)
+    rp = RolloutParams(seg_len, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, 1, 1)
+    seg_q = torch.empty((T, n_segments, n), dtype=torch.float32, device=dev)
+    seg_alive = torch.empty((T, n_segments), dtype=torch.uint8, device=dev)
+    seg_done = torch.empty((T, n_segments), dtype=torch.int32, device=dev)
+    traj = torch.zeros((T, n_segments * seg_len, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_rollout_segments(robot_id, C.byref(sc), C.byref(net), _ptr(q0), T, C.byref(fp), C.byref(rp), n_segments,
+                                          thr_soft, thr_hard, _ptr(seg_q), _ptr(seg_alive), _ptr(seg_done), _ptr(traj),
+                                          _stream()), "cbfrrt_rollout_segments")
+    del keep
+    return seg_q, seg_alive, seg_done, traj
+
+
 # ----------------------------------------------------------------------------- direct entry points
 registered = {}
 

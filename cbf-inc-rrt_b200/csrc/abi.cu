@@ -364,6 +364,32 @@ int cbfrrt_rollout(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* n
                : launch_rollout_magician(sc, na, q0, T, ra, thr_soft, thr_hard, q_final, alive, steps_done, traj, st);
 }
 
+int cbfrrt_rollout_segments(int robot, const cbfrrt_scene* scene, const cbfrrt_cbf_net* net, const float* q0, int64_t T,
+                            const cbfrrt_filter_params* fp, const cbfrrt_rollout_params* rp, int32_t n_segments,
+                            float thr_soft, float thr_hard, float* seg_q, uint8_t* seg_alive, int32_t* seg_done, float* traj,
+                            void* stream) {
+    if (robot != CBFRRT_ROBOT_PANDA && robot != CBFRRT_ROBOT_MAGICIAN) return CBFRRT_ERR_BAD_ROBOT;
+    if (T < 0 || !rp || rp->steps < 1 || rp->ctrl_every < 1 || n_segments < 1 || !q0 || !seg_q || !seg_alive || !seg_done || !traj)
+        return CBFRRT_ERR_BAD_SHAPE;
+    if (rp->stuck_lag < 0 || (rp->stuck_lag > 0 && rp->stuck_after < rp->stuck_lag)) return CBFRRT_ERR_BAD_SHAPE;
+    if (T > NT) return CBFRRT_ERR_UNSUPPORTED;            // the rows of a batch share one CTA (batch-wide early exit)
+    if (fp && fp->u_ref) return CBFRRT_ERR_UNSUPPORTED;
+    const int n = robot == CBFRRT_ROBOT_PANDA ? Panda::N : Magician::N;
+    SceneArgs sc;
+    NetArgs na;
+    int rc = check_scene(scene, sc);
+    if (rc) return rc;
+    rc = check_net(n, net, fp, T, na);
+    if (rc) return rc;
+    if (!net_is_fast(net)) return CBFRRT_ERR_UNSUPPORTED;
+    if (T == 0) return CBFRRT_OK;
+    const RolloutArgs ra{rp->steps, rp->ctrl_every, rp->dt, rp->stuck_lag, rp->stuck_after, rp->stuck_eps, 1, 1};
+    cudaStream_t st = (cudaStream_t)stream;
+    return robot == CBFRRT_ROBOT_PANDA
+               ? launch_rollout_segments_panda(sc, na, q0, (int)T, n_segments, rp->steps, ra, thr_soft, thr_hard, seg_q, seg_alive, seg_done, traj, st)
+               : launch_rollout_segments_magician(sc, na, q0, (int)T, n_segments, rp->steps, ra, thr_soft, thr_hard, seg_q, seg_alive, seg_done, traj, st);
+}
+
 int cbfrrt_fma_probe(int32_t grid, int32_t block, int32_t iters, float* sink, void* stream) {
     if (grid < 1 || block < 32 || block > 1024 || iters < 1 || !sink) return CBFRRT_ERR_BAD_SHAPE;
     fma_probe_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);

@@ -1064,6 +1064,73 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
     }
 }
 
+// A whole expansion of the batched planner in ONE launch: n_seg consecutive batched steer segments
+// (batch_tsa.py:154-170 over :191-231) for ONE batch of T <= NT rows in a single CTA.  Per segment: fresh observation of
+// every row, the mode-1 step logic of rollout_after_step (stuck rows count as collisions, dead rows keep integrating),
+// and the reference's batch-wide early exit -- the segment's loop ends once EVERY row is dead (:229-230) -- which is why
+// the rows of a batch must share a CTA (__syncthreads_or over the alive flags; the loops are uniform over the CTA).
+// The planner's nine 20-step segments per expansion become one launch and one read-back instead of nine.
+template <class RB, int H, int L, bool GRID>
+__global__ void __launch_bounds__(NT) rollout_segments_kernel(SceneArgs sc, NetArgs net, const float* __restrict__ q0, int T,
+                                                              int n_seg, int seg_len, RolloutArgs ra, float thr_soft,
+                                                              float thr_hard, float* __restrict__ seg_q,
+                                                              uint8_t* __restrict__ seg_alive, int* __restrict__ seg_done,
+                                                              float* __restrict__ traj) {
+    constexpr int N = RB::N;
+    extern __shared__ __align__(16) float smem_raw[];
+    using LY = NetLayout<N + 1, H, L>;
+    const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<N>::TOTAL);
+    stage<N>(s, sc, &net, LY::TOTAL);
+    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
+    const float base_min = base_min_cta<RB>(s, sv);
+    float* scr = s.scratch + threadIdx.x;
+    const int b = threadIdx.x;
+    const bool active = b < T;
+    float q[N], qn[N], g[N], u[N], dodq[N], o = 0.f;
+#pragma unroll
+    for (int k = 0; k < N; ++k) { q[k] = active ? __ldg(q0 + b * N + k) : 0.f; u[k] = 0.f; g[k] = 0.f; dodq[k] = 0.f; }
+    if (active) load_goal<N>(net, b, g);
+    CollideResult<RB> cr;
+    const long long steps = (long long)n_seg * seg_len;
+    for (int sg = 0; sg < n_seg; ++sg) {
+        if (active) {                                  // complete_sample_with_observations at the start of the segment
+            collide_state<RB, true, false, GRID>(q, sv, base_min, cr);
+            o = cr.o;
+#pragma unroll
+            for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
+        }
+        bool ok = true, dead = !active;
+        int done = 0;
+        float* tr = traj + ((long long)b * steps + (long long)sg * seg_len) * N;
+        for (int t = 0; t < seg_len; ++t) {
+            if (active) {
+                if (t % ra.ctrl_every == 0) {
+                    float J[N], h, r;
+                    cbf_filter_state<N, H, L, NT>(s.weights, s.params, scr, q, o, dodq, g, false, net.lam, net.penalty, h, J, u, r);
+                }
+#pragma unroll
+                for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);
+                if ((t + 1) % ra.ctrl_every == 0) {
+                    collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
+                    o = cr.o;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
+                } else {
+                    collide_state<RB, false, false, GRID, false>(qn, sv, base_min, cr);
+                }
+                rollout_after_step<N>(ra, t, cr.hard_min <= thr_hard, q, qn, tr, ok, dead, done);   // stuck_mode 1, keep_going 1
+            }
+            if (!__syncthreads_or(!dead)) break;       // batch_tsa.py:229-230: every row of the batch is dead
+        }
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) seg_q[((long long)b * n_seg + sg) * N + k] = q[k];
+            seg_alive[(long long)b * n_seg + sg] = ok;
+            seg_done[(long long)b * n_seg + sg] = done;
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
@@ -1414,6 +1481,19 @@ static int launch_rollout(const SceneArgs& sc_in, const NetArgs& net, const floa
     return finish_launch();
 }
 
+template <class RB>
+static int launch_rollout_segments(const SceneArgs& sc_in, const NetArgs& net, const float* q0, int T, int n_seg, int seg_len,
+                                   const RolloutArgs& ra, float ts, float th, float* seg_q, uint8_t* seg_alive, int* seg_done,
+                                   float* traj, cudaStream_t st) {
+    const SceneArgs sc = scene_for(sc_in, T, true);
+    using LY = NetLayout<RB::N + 1, 48, 2>;
+    const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<RB::N>::TOTAL, 48 * NT);
+    auto k = sc.grid ? rollout_segments_kernel<RB, 48, 2, true> : rollout_segments_kernel<RB, 48, 2, false>;
+    if (grid_for(k, smem, 1) < 0) return CBFRRT_ERR_CUDA;
+    k<<<1, NT, smem, st>>>(sc, net, q0, T, n_seg, seg_len, ra, ts, th, seg_q, seg_alive, seg_done, traj);
+    return finish_launch();
+}
+
 // ---- per-robot launch wrappers: each is defined in its own translation unit (k_<family>_<robot>.cu) so that the
 // big template instantiations compile in parallel
 #define CBF_DECLARE_ROBOT(R)                                                                                          \
@@ -1426,7 +1506,9 @@ static int launch_rollout(const SceneArgs& sc_in, const NetArgs& net, const floa
     int launch_edges_var_##R(const SceneArgs&, const float*, const float*, long long, const long long*, long long,     \
                              float, float, uint8_t*, int*, cudaStream_t);                                              \
     int launch_rollout_##R(const SceneArgs&, const NetArgs&, const float*, long long, const RolloutArgs&, float,       \
-                           float, float*, uint8_t*, int*, float*, cudaStream_t);
+                           float, float*, uint8_t*, int*, float*, cudaStream_t);                                       \
+    int launch_rollout_segments_##R(const SceneArgs&, const NetArgs&, const float*, int, int, int, const RolloutArgs&,  \
+                                    float, float, float*, uint8_t*, int*, float*, cudaStream_t);
 CBF_DECLARE_ROBOT(panda)
 CBF_DECLARE_ROBOT(magician)
 #undef CBF_DECLARE_ROBOT

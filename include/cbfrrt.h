@@ -286,6 +286,20 @@ int cbfrrt_rollout(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_net *n
                    const cbfrrt_filter_params *fp, const cbfrrt_rollout_params *rp, float thr_soft, float thr_hard,
                    float *q_final, uint8_t *alive, int32_t *steps_done, float *traj, void *stream);
 
+/* ---- a whole expansion of the batched planner in one launch -----------------------------------------------------
+ * Replaces the segment loop of global_explore (motion_planning/baseline/batch_tsa.py:154-170: RRT_PARAM // 20 calls of
+ * the batched steer, each starting where the previous one ended) for ONE batch of T <= 128 rows: n_segments consecutive
+ * segments of rp->steps steps each with the semantics of batch_tsa.py:191-231 (stuck_mode 1, dead rows keep
+ * integrating, and the reference's batch-wide early exit: a segment ends once every row of the batch is dead, :229-230;
+ * keep_going / stuck_mode of rp are ignored).  Every segment starts with a fresh observation of the rows' current states.
+ *   seg_q [T, n_segments, n] = x_current at the end of each segment (the node the planner inserts),
+ *   seg_alive [T, n_segments] = no_collisions, seg_done [T, n_segments] = stored states of the segment,
+ *   traj [T, n_segments * steps, n]: segment k's stored states start at row k * steps (required). */
+int cbfrrt_rollout_segments(int robot, const cbfrrt_scene *scene, const cbfrrt_cbf_net *net, const float *q0, int64_t T,
+                            const cbfrrt_filter_params *fp, const cbfrrt_rollout_params *rp, int32_t n_segments,
+                            float thr_soft, float thr_hard, float *seg_q, uint8_t *seg_alive, int32_t *seg_done,
+                            float *traj, void *stream);
+
 /* ---- counter-based uniform state sampler (ControlAffineSystem.sample_state_space,
  * control_affine_system.py:291-300, made shard-invariant): row g = start_row + b, q[b,j] = lo_j + U(g,j)(hi_j-lo_j) */
 int cbfrrt_sample_states(int robot, uint32_t seed, uint64_t start_row, int64_t B, float *q, void *stream);

@@ -271,6 +271,30 @@ def rollout(robot, q0, goal, steps, ctrl_every, dt, boxes, spheres, floor, weigh
     return qf, alive, done, traj
 
 
+def rollout_segments(robot, q0, goal, n_seg, seg_len, ctrl_every, dt, boxes, spheres, floor, weights, hidden, layers, K, u_lo,
+                     u_hi, thr_soft, thr_hard, lam, penalty, stuck_lag=9, stuck_after=10, stuck_eps=3e-2):
+    """n_seg consecutive batched steer segments of one batch (batch_tsa.py:154-170 over :191-231)
+    -> seg_q [T, n_seg, n], seg_alive [T, n_seg], seg_done [T, n_seg], traj [T, n_seg * seg_len, n]"""
+    q0 = _f(q0)
+    n, L, _ = robot_info(robot)
+    T = q0.shape[0]
+    goal = _f(goal).reshape(-1, n)
+    b8, sp = pack_scene(boxes, spheres)
+    w, K, u_lo, u_hi = _f(weights), _f(K), _f(u_lo), _f(u_hi)
+    seg_q = np.empty((T, n_seg, n), np.float32)
+    seg_alive = np.empty((T, n_seg), np.uint8)
+    seg_done = np.empty((T, n_seg), np.int32)
+    traj = np.zeros((T, n_seg * seg_len, n), np.float32)
+    rc = lib().oracle_rollout_segments(ROBOT_ID[robot], b8.shape[0], _p(b8), sp.shape[0], _p(sp), int(bool(floor)), hidden,
+                                       layers, _p(w), _p(q0), _p(goal), C.c_long(goal.shape[0]), C.c_long(T), int(n_seg),
+                                       int(seg_len), int(ctrl_every), C.c_float(dt), int(stuck_lag), int(stuck_after),
+                                       C.c_float(stuck_eps), _p(K), _p(u_lo), _p(u_hi), C.c_float(thr_soft),
+                                       C.c_float(thr_hard), C.c_float(lam), C.c_float(penalty), _p(seg_q), _p(seg_alive),
+                                       _p(seg_done), _p(traj))
+    assert rc == 0
+    return seg_q, seg_alive, seg_done, traj
+
+
 def sample_states(robot, seed, start_row, B):
     n, _, _ = robot_info(robot)
     q = np.empty((B, n), np.float32)

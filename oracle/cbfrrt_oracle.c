@@ -1149,6 +1149,88 @@ API int oracle_rollout(int robot, int n_boxes, const float *boxes, int n_sph, co
     return 0;
 }
 
+/* A whole expansion of the batched planner in one call: n_seg consecutive batched steer segments
+ * (motion_planning/baseline/batch_tsa.py:154-170: `for _ in range(RRT_PARAM // 20): new_states, no_collisions, ... =
+ * steer(..., current, RRT_step=20); current = new_states`), each with the semantics of batch_tsa.py:191-231:
+ *   - a segment starts with a fresh observation of every row's current state (complete_sample_with_observations);
+ *   - control every ctrl_every steps, Euler every step, observation refresh when (t+1) % ctrl_every == 0;
+ *   - per row: stuck (more than stuck_after states stored: last vs the one stuck_lag before, < stuck_eps) OR unsafe new
+ *     state -> no_collision = False for good, nothing appended any more, but the row keeps integrating;
+ *   - the segment's loop ends early once EVERY row of the batch is dead (:229-230); x_current of that step is what the
+ *     next segment starts from.
+ * Outputs per segment: seg_q [T, n_seg, n] = x_current at the end of the segment, seg_alive [T, n_seg], seg_done
+ * [T, n_seg] = stored states, traj [T, n_seg * seg_len, n] with segment k's stored states from row k * seg_len.
+ * Rows of one call form ONE batch (single-threaded here: the batch-wide break couples the rows). */
+API int oracle_rollout_segments(int robot, int n_boxes, const float *boxes, int n_sph, const float *spheres, int floor,
+                                int hidden, int layers, const float *weights, const float *q0, const float *goal,
+                                long goal_rows, long T, int n_seg, int seg_len, int ctrl_every, float dt, int stuck_lag,
+                                int stuck_after, float stuck_eps, const float *K, const float *u_lo, const float *u_hi,
+                                float thr_soft, float thr_hard, float lam, float penalty, float *seg_q, uint8_t *seg_alive,
+                                int *seg_done, float *traj) {
+    if (hidden > MAXH || layers > MAXL || T > 4096) return -1;
+    const Robot *rb = &ROBOTS[robot];
+    const int n = rb->n;
+    Scene sc = {n_boxes, n_sph, floor, boxes, spheres};
+    Net net = {n + 1, hidden, layers, weights};
+    float (*d)[2 * MAXN + 1] = malloc(sizeof(float[2 * MAXN + 1]) * T);
+    float (*u)[MAXN] = calloc(T, sizeof(float[MAXN]));
+    int *ok = malloc(sizeof(int) * T), *dead = malloc(sizeof(int) * T), *done = malloc(sizeof(int) * T);
+    CollideOut co;
+    for (long b = 0; b < T; ++b)
+        for (int k = 0; k < n; ++k) d[b][k] = q0[b * n + k];
+    const long steps = (long)n_seg * seg_len;
+    for (int sg = 0; sg < n_seg; ++sg) {
+        for (long b = 0; b < T; ++b) {       /* fresh observation at the start of the segment */
+            collide_state(rb, &sc, d[b], thr_soft, thr_hard, &co);
+            d[b][n] = co.o;
+            for (int k = 0; k < n; ++k) d[b][n + 1 + k] = co.dodq[k];
+            ok[b] = 1; dead[b] = 0; done[b] = 0;
+        }
+        for (int t = 0; t < seg_len; ++t) {
+            int any_alive = 0;
+            for (long b = 0; b < T; ++b) {
+                float qn[MAXN];
+                if (t % ctrl_every == 0) {
+                    float hh, JJ[MAXN], rr;
+                    const float *g = goal + (goal_rows == 1 ? 0 : b * n);
+                    filter_state(n, &net, d[b], g, 0, K, u_lo, u_hi, lam, penalty, &hh, JJ, u[b], &rr);
+                }
+                for (int k = 0; k < n; ++k) qn[k] = fmaf(u[b][k], dt, d[b][k]);
+                collide_state(rb, &sc, qn, thr_soft, thr_hard, &co);
+                if ((t + 1) % ctrl_every == 0) {
+                    d[b][n] = co.o;
+                    for (int k = 0; k < n; ++k) d[b][n + 1 + k] = co.dodq[k];
+                }
+                float *tr = traj + (b * steps + (long)sg * seg_len) * n;
+                if (!dead[b]) {
+                    int stuck = 0;
+                    if (stuck_lag > 0 && done[b] > stuck_after) {
+                        const float *a = tr + (done[b] - 1) * n, *o2 = tr + (done[b] - 1 - stuck_lag) * n;
+                        float dsq = 0.f;
+                        for (int k = 0; k < n; ++k) { float e = a[k] - o2[k]; dsq = fmaf(e, e, dsq); }
+                        stuck = sqrtf(dsq) < stuck_eps;
+                    }
+                    if (stuck || co.unsafe) { ok[b] = 0; dead[b] = 1; }
+                }
+                for (int k = 0; k < n; ++k) d[b][k] = qn[k];
+                if (!dead[b]) {
+                    for (int k = 0; k < n; ++k) tr[done[b] * n + k] = d[b][k];
+                    ++done[b];
+                    any_alive = 1;
+                }
+            }
+            if (!any_alive) break;           /* batch_tsa.py:229-230 */
+        }
+        for (long b = 0; b < T; ++b) {
+            for (int k = 0; k < n; ++k) seg_q[(b * n_seg + sg) * n + k] = d[b][k];
+            seg_alive[b * n_seg + sg] = (uint8_t)ok[b];
+            seg_done[b * n_seg + sg] = done[b];
+        }
+    }
+    free(d); free(u); free(ok); free(dead); free(done);
+    return 0;
+}
+
 /* counter-based state sampler (BASELINE config 5: results must not depend on the shard count):
  *   x = hash(seed, global_row * n + j)  ->  u = (x >> 8) * 2^-24 in [0,1)  ->  q = fmaf(u, hi-lo, lo)
  * hash = two rounds of the 32-bit "lowbias32" mix over (index ^ seed*0x9E3779B9). */

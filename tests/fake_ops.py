@@ -90,6 +90,15 @@ def install(monkeypatch):
         return (torch.from_numpy(qf), torch.from_numpy(alive), torch.from_numpy(done),
                 torch.from_numpy(traj) if traj is not None else torch.empty(0))
 
+    def rollout_segments(q0, goal, n_segments, seg_len, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, boxes, spheres, floor, grid,
+                         weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id, hidden, layers):
+        b, s = _scene(boxes, spheres)
+        sq, sa, sd, tr = c_oracle.rollout_segments(NAME[robot_id], _np(q0), _np(goal), n_segments, seg_len, ctrl_every, dt, b, s,
+                                                   bool(floor), _np(weights), hidden, layers, _np(K), _np(u_lo), _np(u_hi), thr_soft,
+                                                   thr_hard, lam, penalty, stuck_lag=stuck_lag, stuck_after=stuck_after,
+                                                   stuck_eps=stuck_eps)
+        return torch.from_numpy(sq), torch.from_numpy(sa), torch.from_numpy(sd), torch.from_numpy(tr)
+
     def valid_control(q, goal, boxes, spheres, floor, grid, weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id,
                       hidden, layers):
         b, s = _scene(boxes, spheres)
@@ -98,5 +107,5 @@ def install(monkeypatch):
         return torch.from_numpy(o["safe"]), torch.from_numpy(o["u"])
 
     for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp, qp_backward=qp_backward, qp_multi=qp_multi, qp_multi_backward=qp_multi_backward,
-                         edge_validity=edge_validity, edge_validity_var=edge_validity_var, knn=knn, radius_mask=radius_mask, rollout=rollout, valid_control=valid_control).items():
+                         edge_validity=edge_validity, edge_validity_var=edge_validity_var, knn=knn, radius_mask=radius_mask, rollout=rollout, rollout_segments=rollout_segments, valid_control=valid_control).items():
         monkeypatch.setattr(ops, name, fn)

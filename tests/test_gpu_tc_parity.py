@@ -313,3 +313,42 @@ def test_generic_network_shapes(coracle, robot, hidden, layers):
     with pytest.raises(CbfrrtError):
         ops.rollout(_t(q[:10]), _t(goal[:10]), 5, 4, 1 / 120, 0, 10, 0.1, False, False, b8, s4, 1, gr, net, _t(w["K"]), _t(w["u_lo"]),
                     _t(w["u_hi"]), w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, hidden, layers)
+
+
+@pytest.mark.parametrize("robot,T", [("panda", 1), ("panda", 50), ("magician", 128), ("panda", 7)])
+def test_rollout_segments_matches_oracle(coracle, robot, T):
+    """cbfrrt_rollout_segments: the nine 20-step segments of a planner expansion in one launch, incl. the batch-wide early
+    exit (every row dead) and rows that stall, against the oracle's restatement of batch_tsa.py:154-170 / :191-231"""
+    from cbfrrt import ops, workloads as W
+    w = _workload(robot)
+    n, rid = w["n"], ops.ROBOT_ID[robot]
+    boxes = W.scene(3)[0]
+    cand = W.sample_states(robot, 4000, 81 + T)
+    pool = cand[coracle.collide(robot, cand, boxes, None, True)["safe"].astype(bool)]
+    q0 = np.ascontiguousarray(pool[:T])
+    goal = W.sample_states(robot, T, 82)
+    goal[::3] = q0[::3] + 0.02                      # every third row stalls next to its start (stuck test)
+    b8, s4, gr = _scene(boxes, None)
+    n_seg, seg_len = 9, 20
+    for use_grid in (True, False):
+        g = gr if use_grid else ops.no_grid(DEV)
+        sq, sa, sd, tr = ops.rollout_segments(_t(q0), _t(goal), n_seg, seg_len, 4, 1 / 120, 9, 10, 3e-2, b8, s4, 1, g, _net(w), _t(w["K"]),
+                                              _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
+        oq, oa, od, ot = coracle.rollout_segments(robot, q0, goal, n_seg, seg_len, 4, 1 / 120, boxes, None, True, w["weights"], 48, 2,
+                                                  w["K"], w["u_lo"], w["u_hi"], w["thr_soft"], w["thr_hard"], w["lam"], w["penalty"])
+        same = (sa.cpu().numpy() == oa) & (sd.cpu().numpy() == od)
+        # a discrete event that differs in one segment moves everything after it in that row: compare rows up to there
+        first_diff = np.where(same.all(1), n_seg, np.argmin(same, axis=1))
+        assert (first_diff == n_seg).mean() >= 0.97, first_diff
+        for b in range(T):
+            k = first_diff[b]
+            if k:
+                assert np.abs(sq.cpu().numpy()[b, :k] - oq[b, :k]).max() < 2e-4
+                for s_ in range(k):
+                    m = od[b, s_]
+                    assert m == 0 or np.abs(tr.cpu().numpy()[b, s_ * seg_len:s_ * seg_len + m] - ot[b, s_ * seg_len:s_ * seg_len + m]).max() < 2e-4
+        assert (oa == 0).any() or T == 1
+    from cbfrrt._lib import CbfrrtError
+    with pytest.raises(CbfrrtError):               # more rows than one CTA holds
+        ops.rollout_segments(_t(np.repeat(q0[:1], 129, 0)), _t(goal[:1]), 2, 20, 4, 1 / 120, 9, 10, 3e-2, b8, s4, 1, gr, _net(w),
+                             _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)

@@ -220,6 +220,36 @@ def test_batched_steer_reference_semantics_fused(stack):
     assert seen["dead"] > 0 and seen["stuck"] > 0, seen
 
 
+def test_fused_segments_equal_consecutive_batched_steers(stack):
+    """cbfrrt_rollout_segments (one launch for all segments of an expansion) against what global_explore did before:
+    n_seg consecutive calls of the batched steer host loop, each starting where the previous one ended
+    (batch_tsa.py:154-170), incl. batches of ONE row (the batch-wide early exit fires at every death) and rows that die"""
+    env, robot, dyn, ctrl = stack("panda")
+    from cbfrrt.motion_planning.baseline import batch_steer, steer_segments_fused
+    x = dyn.sample_state_space(400)
+    xs = x[dyn.safe_mask(x)].numpy()[:, :7]
+    fold = np.array([[0., 1.7, 0., -0.1, 0., 3.7, 0.]], np.float32)            # a pose that folds onto the floor
+    n_dead = n_early = 0
+    for starts, targets in ((xs[:5], xs[5:10]), (xs[10:11], fold), (xs[11:14], np.repeat(fold, 3, 0)), (xs[20:21], xs[20:21] + 0.02),
+                            (xs[30:36], xs[36:42])):
+        n_seg = 4
+        segs = steer_segments_fused(ctrl, dyn, targets, starts, n_seg, RRT_step=20)
+        cur = starts
+        for k in range(n_seg):
+            xb, oks, _, lists = batch_steer(ctrl.u, dyn, targets, cur, RRT_step=20, device="cpu")
+            xf, okf, lf = segs[k]
+            assert list(oks) == list(okf), (k, oks, okf)
+            assert [len(a) for a in lists] == [len(b) for b in lf]
+            assert np.abs(xb - xf).max() < 2e-4
+            for a, b in zip(lists, lf):
+                if len(a):
+                    assert np.abs(np.asarray(a)[:, :7] - np.asarray(b)).max() < 2e-4
+            n_dead += sum(not o for o in oks)
+            n_early += int(not any(oks) and max(len(a) for a in lists) < 19)
+            cur = xb
+    assert n_dead > 0 and n_early > 0, (n_dead, n_early)
+
+
 def test_edge_checking_reference_loop_equals_batched(stack):
     env, robot, dyn, ctrl = stack("panda")
     from cbfrrt.motion_planning.baseline import (edge_checking, edge_checking_batch, edge_checking_eps,
