@@ -156,12 +156,15 @@ def global_explore(search_tree, dynamics_model, sample_states=None, steer_type="
     if fused:   # all segments of the expansion in one launch and one read-back (cbfrrt_rollout_segments)
         assert hasattr(controller, "u")
         segments = steer_segments_fused(controller, dm, sample_states, current, n_seg, RRT_step=20)
+    if fused:   # one goal test for the new states of all segments (same float32 torch expression, one call instead of n_seg)
+        done_all = _goal_test(dm, np.concatenate([seg[0] for seg in segments])).reshape(n_seg, -1)
     for k in range(n_seg):
         if fused:
             new_states, no_collisions, edges = segments[k]
+            done = done_all[k]
         else:
             new_states, no_collisions, edges = _steer_batch(dm, controller, steer_type, sample_states, current, 20)
-        done = _goal_test(dm, new_states)
+            done = _goal_test(dm, new_states)
         for i in range(len(parents)):
             parents[i] = insert_new_state(search_tree, new_states[i], sample_states[i], edges[i], parents[i],
                                           no_collisions[i], bool(done[i]), expanded_by_rrt=True)

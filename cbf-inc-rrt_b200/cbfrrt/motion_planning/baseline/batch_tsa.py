@@ -135,7 +135,12 @@ def steer_segments_fused(controller, dynamics_model, sample_states, nearests, n_
         b, s, fl, gr, controller._weights(), dm.K_on(dm.device), lo, hi, float(controller.clf_lambda),
         float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard), dm.robot.robot_id,
         controller.h_hidden_size, controller.h_hidden_layers)
-    seg_q, seg_alive, seg_done, traj = seg_q.cpu().numpy(), seg_alive.cpu().numpy().astype(bool), seg_done.cpu().numpy(), traj.cpu().numpy()
+    # two read-backs instead of four (each one is a stream synchronisation)
+    B_, n_ = seg_q.shape[0], seg_q.shape[2]
+    flt = torch.cat([seg_q.reshape(B_, -1), traj.reshape(B_, -1)], dim=1).cpu().numpy()
+    flags = torch.stack([seg_alive.to(torch.int32), seg_done], dim=0).cpu().numpy()
+    seg_q, traj = flt[:, :n_segments * n_].reshape(B_, n_segments, n_), flt[:, n_segments * n_:].reshape(B_, -1, n_)
+    seg_alive, seg_done = flags[0].astype(bool), flags[1]
     out = []
     for k in range(int(n_segments)):
         xs = [[row for row in traj[i, k * RRT_step:k * RRT_step + seg_done[i, k]]] for i in range(traj.shape[0])]

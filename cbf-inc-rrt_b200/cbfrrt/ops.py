@@ -527,7 +527,7 @@ def rollout_segments(q0: Tensor, goal: Tensor, n_segments: int, seg_len: int, ct
     seg_q = torch.empty((T, n_segments, n), dtype=torch.float32, device=dev)
     seg_alive = torch.empty((T, n_segments), dtype=torch.uint8, device=dev)
     seg_done = torch.empty((T, n_segments), dtype=torch.int32, device=dev)
-    traj = torch.zeros((T, n_segments * seg_len, n), dtype=torch.float32, device=dev)
+    traj = torch.empty((T, n_segments * seg_len, n), dtype=torch.float32, device=dev)   # rows beyond seg_done are never read
     with torch.cuda.device(dev):
         check(lib.cbfrrt_rollout_segments(robot_id, C.byref(sc), C.byref(net), _ptr(q0), T, C.byref(fp), C.byref(rp), n_segments,
                                           thr_soft, thr_hard, _ptr(seg_q), _ptr(seg_alive), _ptr(seg_done), _ptr(traj),

@@ -868,6 +868,8 @@ __global__ void __launch_bounds__(GG * tc::M_TILE, 1) safety_kernel_tc(SceneArgs
     tc::teardown<L, GG>(c);
 }
 
+// (The rollout kernels never read the self-collision predicate -- the steer loop tests unsafe_mask only, tsa.py:251 --
+// so every collide_state call in them is instantiated without it: WANT_SELF = false.)
 // steer loop on the tensor-core path: the time loop is uniform over a tile group (a finished trajectory idles,
 // it does not leave), because the MLP rounds are group-wide; the group exits early once all its rows are finished.
 template <class RB, int L, bool GRID>
@@ -896,7 +898,7 @@ __global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) rollout_kerne
 #pragma unroll
             for (int k = 0; k < N; ++k) q[k] = __ldg(q0 + b * N + k);
             load_goal<N>(net, b, g);
-            collide_state<RB, true, false, GRID>(q, sv, base_min, cr);
+            collide_state<RB, true, false, GRID, false>(q, sv, base_min, cr);
             o = cr.o;
 #pragma unroll
             for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
@@ -918,7 +920,7 @@ __global__ void __launch_bounds__(tc_groups(GRID) * tc::M_TILE, 1) rollout_kerne
 #pragma unroll
             for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);  // arm_dynamics.py:508 (step = 1)
             if ((t + 1) % ra.ctrl_every == 0) {       // observation refresh: minimum + gradient needed
-                collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
+                collide_state<RB, true, false, GRID, false>(qn, sv, base_min, cr);
             } else {                                  // only the hard collision test is read: mask-only, no self test
                 collide_state<RB, false, false, GRID, false>(qn, sv, base_min, cr);
             }
@@ -1027,7 +1029,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
         for (int k = 0; k < N; ++k) { q[k] = __ldg(q0 + b * N + k); u[k] = 0.f; }
         load_goal<N>(net, b, g);
         CollideResult<RB> cr;
-        collide_state<RB, true, false, GRID>(q, sv, base_min, cr);
+        collide_state<RB, true, false, GRID, false>(q, sv, base_min, cr);
         o = cr.o;
 #pragma unroll
         for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
@@ -1043,7 +1045,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
 #pragma unroll
             for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);  // arm_dynamics.py:508 (step = 1)
             if ((t + 1) % ra.ctrl_every == 0) {       // observation refresh: minimum + gradient needed
-                collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
+                collide_state<RB, true, false, GRID, false>(qn, sv, base_min, cr);
             } else {                                  // only the hard collision test is read: mask-only, no self test
                 collide_state<RB, false, false, GRID, false>(qn, sv, base_min, cr);
             }
@@ -1061,6 +1063,124 @@ __global__ void __launch_bounds__(NT) rollout_kernel(SceneArgs sc, NetArgs net, 
         for (int k = 0; k < N; ++k) q_final[b * N + k] = q[k];
         alive[b] = ok;
         steps_done[b] = done;
+    }
+}
+
+// CTA-cooperative barrier network for planner-sized batches: the (row, neuron) outputs of every layer are spread over
+// the 128 threads of the CTA instead of one thread walking all ~20 k multiply-adds of its row (with ONE row per call --
+// the reference's regime -- 127 threads used to idle).  Activations / back-propagated gradients of a chunk of COOP_ROWS
+// rows live in shared memory; forward layers read a transposed copy of the hidden weights (lanes over output neurons:
+// conflict-free), the reverse pass the packed row-major weights (lanes over input neurons: conflict-free).  FP32 FMAs,
+// tolerance-checked like the other FP32 path.  All NT threads must call it; `x` / outputs are per row (thread b < T).
+constexpr int COOP_ROWS = 32;
+template <int N_IN, int H>
+struct CoopLayout {   // floats
+    static constexpr int IN_PAD = (N_IN + 3) & ~3;
+    static constexpr int WT = 0;                                   // [2][H (k)][H (j)] transposed hidden weights
+    static constexpr int X = WT + 2 * H * H;                       // [COOP_ROWS][IN_PAD]
+    static constexpr int A = X + COOP_ROWS * IN_PAD;               // [3][COOP_ROWS][H]  relu outputs of the three layers
+    static constexpr int G = A + 3 * COOP_ROWS * H;                // [2][COOP_ROWS][H]  gradients (ping-pong)
+    static constexpr int HJ = G + 2 * COOP_ROWS * H;               // [COOP_ROWS][IN_PAD + 1]  h, jac
+    static constexpr int TOTAL = HJ + COOP_ROWS * (IN_PAD + 4);
+};
+template <int N_IN, int H, int NTH>
+__device__ __forceinline__ void coop_setup(const float* __restrict__ w, float* __restrict__ cb) {
+    using LY = NetLayout<N_IN, H, 2>;
+    using CL = CoopLayout<N_IN, H>;
+    for (int l = 0; l < 2; ++l)
+        for (int i = threadIdx.x; i < H * H; i += NTH) {
+            const int j = i / H, k = i % H;
+            cb[CL::WT + l * H * H + k * H + j] = w[LY::HID0 + l * LY::HID_STRIDE + i];
+        }
+    __syncthreads();
+}
+template <int N_IN, int H, int NTH>
+__device__ __forceinline__ void coop_mlp_h_jac(const float* __restrict__ w, float* __restrict__ cb, int T, bool active,
+                                               const float (&x)[N_IN], float& h_out, float (&jac)[N_IN]) {
+    using LY = NetLayout<N_IN, H, 2>;
+    using CL = CoopLayout<N_IN, H>;
+    const int tid = threadIdx.x;
+    for (int r0 = 0; r0 < T; r0 += COOP_ROWS) {
+        const int rows = min(COOP_ROWS, T - r0);
+        const bool mine = active && tid >= r0 && tid < r0 + rows;
+        __syncthreads();                                           // previous chunk's readers are done
+        if (mine) {
+#pragma unroll
+            for (int k = 0; k < N_IN; ++k) cb[CL::X + (tid - r0) * CL::IN_PAD + k] = x[k];
+        }
+        __syncthreads();
+        float* A0 = cb + CL::A;
+        float* A1 = A0 + COOP_ROWS * H;
+        float* A2 = A1 + COOP_ROWS * H;
+        float* G0 = cb + CL::G;
+        float* G1 = G0 + COOP_ROWS * H;
+        for (int idx = tid; idx < rows * H; idx += NTH) {          // input layer
+            const int r = idx / H, j = idx % H;
+            float sacc = w[LY::B_IN + j];
+#pragma unroll
+            for (int k = 0; k < N_IN; ++k) sacc = fmaf(w[LY::W_IN + j * LY::IN_PAD + k], cb[CL::X + r * CL::IN_PAD + k], sacc);
+            A0[r * H + j] = fmaxf(sacc, 0.f);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {                              // hidden layers (transposed weights: lanes over j)
+            const float* in = l ? A1 : A0;
+            float* out = l ? A2 : A1;
+            const float* wt = cb + CL::WT + l * H * H;
+            const float* bias = w + LY::HID0 + l * LY::HID_STRIDE + H * H;
+            for (int idx = tid; idx < rows * H; idx += NTH) {
+                const int r = idx / H, j = idx % H;
+                float s0 = bias[j], s1 = 0.f;
+#pragma unroll 8
+                for (int k = 0; k < H; k += 2) {
+                    s0 = fmaf(wt[k * H + j], in[r * H + k], s0);
+                    s1 = fmaf(wt[(k + 1) * H + j], in[r * H + k + 1], s1);
+                }
+                out[r * H + j] = fmaxf(s0 + s1, 0.f);
+            }
+            __syncthreads();
+        }
+        for (int idx = tid; idx < rows * H; idx += NTH) {          // seed of the reverse pass; h by the row's first lane
+            const int r = idx / H, k = idx % H;
+            G0[r * H + k] = A2[r * H + k] > 0.f ? w[LY::W_OUT + k] : 0.f;
+        }
+        for (int r = tid; r < rows; r += NTH) {
+            float hh = w[LY::B_OUT];
+            for (int k = 0; k < H; ++k) hh = fmaf(w[LY::W_OUT + k], A2[r * H + k], hh);
+            cb[CL::HJ + r * (CL::IN_PAD + 4)] = hh;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int l = 1; l >= 0; --l) {                             // reverse mode through the hidden layers (row-major: lanes over k)
+            const float* gin = l ? G0 : G1;
+            float* gout = l ? G1 : G0;
+            const float* mask = l ? A1 : A0;
+            const float* W = w + LY::HID0 + l * LY::HID_STRIDE;
+            for (int idx = tid; idx < rows * H; idx += NTH) {
+                const int r = idx / H, k = idx % H;
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                for (int j = 0; j < H; j += 2) {
+                    s0 = fmaf(W[j * H + k], gin[r * H + j], s0);
+                    s1 = fmaf(W[(j + 1) * H + k], gin[r * H + j + 1], s1);
+                }
+                gout[r * H + k] = mask[r * H + k] > 0.f ? s0 + s1 : 0.f;
+            }
+            __syncthreads();
+        }
+        for (int idx = tid; idx < rows * N_IN; idx += NTH) {       // input layer, reverse: jac = W_in^T g   (g = G0)
+            const int r = idx / N_IN, k = idx % N_IN;
+            float acc = 0.f;
+            for (int j = 0; j < H; ++j) acc = fmaf(w[LY::W_IN + j * LY::IN_PAD + k], G0[r * H + j], acc);
+            cb[CL::HJ + r * (CL::IN_PAD + 4) + 1 + k] = acc;
+        }
+        __syncthreads();
+        if (mine) {
+            const float* o = cb + CL::HJ + (tid - r0) * (CL::IN_PAD + 4);
+            h_out = o[0];
+#pragma unroll
+            for (int k = 0; k < N_IN; ++k) jac[k] = o[1 + k];
+        }
     }
 }
 
@@ -1083,7 +1203,8 @@ __global__ void __launch_bounds__(NT) rollout_segments_kernel(SceneArgs sc, NetA
     stage<N>(s, sc, &net, LY::TOTAL);
     const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
     const float base_min = base_min_cta<RB>(s, sv);
-    float* scr = s.scratch + threadIdx.x;
+    float* const coop = s.scratch;                     // CoopLayout (cooperative barrier network, above)
+    coop_setup<N + 1, H, NT>(s.weights, coop);
     const int b = threadIdx.x;
     const bool active = b < T;
     float q[N], qn[N], g[N], u[N], dodq[N], o = 0.f;
@@ -1094,7 +1215,7 @@ __global__ void __launch_bounds__(NT) rollout_segments_kernel(SceneArgs sc, NetA
     const long long steps = (long long)n_seg * seg_len;
     for (int sg = 0; sg < n_seg; ++sg) {
         if (active) {                                  // complete_sample_with_observations at the start of the segment
-            collide_state<RB, true, false, GRID>(q, sv, base_min, cr);
+            collide_state<RB, true, false, GRID, false>(q, sv, base_min, cr);
             o = cr.o;
 #pragma unroll
             for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
@@ -1103,15 +1224,22 @@ __global__ void __launch_bounds__(NT) rollout_segments_kernel(SceneArgs sc, NetA
         int done = 0;
         float* tr = traj + ((long long)b * steps + (long long)sg * seg_len) * N;
         for (int t = 0; t < seg_len; ++t) {
-            if (active) {
-                if (t % ra.ctrl_every == 0) {
-                    float J[N], h, r;
-                    cbf_filter_state<N, H, L, NT>(s.weights, s.params, scr, q, o, dodq, g, false, net.lam, net.penalty, h, J, u, r);
+            if (t % ra.ctrl_every == 0) {              // uniform over the CTA: all threads work on the rows' networks
+                float x[N + 1], jac[N + 1], h = 0.f;
+#pragma unroll
+                for (int k = 0; k < N; ++k) x[k] = q[k];
+                x[N] = o;
+                coop_mlp_h_jac<N + 1, H, NT>(s.weights, coop, T, active, x, h, jac);
+                if (active) {
+                    float J[N], r;
+                    cbf_filter_post<N>(s.params, q, dodq, g, false, net.lam, net.penalty, h, jac, J, u, r);
                 }
+            }
+            if (active) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) qn[k] = fmaf(u[k], ra.dt, q[k]);
                 if ((t + 1) % ra.ctrl_every == 0) {
-                    collide_state<RB, true, false, GRID>(qn, sv, base_min, cr);
+                    collide_state<RB, true, false, GRID, false>(qn, sv, base_min, cr);
                     o = cr.o;
 #pragma unroll
                     for (int k = 0; k < N; ++k) dodq[k] = cr.dodq[k];
@@ -1487,7 +1615,7 @@ static int launch_rollout_segments(const SceneArgs& sc_in, const NetArgs& net, c
                                    float* traj, cudaStream_t st) {
     const SceneArgs sc = scene_for(sc_in, T, true);
     using LY = NetLayout<RB::N + 1, 48, 2>;
-    const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<RB::N>::TOTAL, 48 * NT);
+    const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<RB::N>::TOTAL, CoopLayout<RB::N + 1, 48>::TOTAL);
     auto k = sc.grid ? rollout_segments_kernel<RB, 48, 2, true> : rollout_segments_kernel<RB, 48, 2, false>;
     if (grid_for(k, smem, 1) < 0) return CBFRRT_ERR_CUDA;
     k<<<1, NT, smem, st>>>(sc, net, q0, T, n_seg, seg_len, ra, ts, th, seg_q, seg_alive, seg_done, traj);
