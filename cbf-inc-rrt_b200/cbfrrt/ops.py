@@ -737,12 +737,12 @@ def lidar_cbf(net: PackedLidarNet, q: Tensor, cloud: Tensor, frames: Tensor, sam
     return (h, J) if want_j else h
 
 
-MLP_PATHS = {"auto": 0, "fma": 1, "tc": 2}
+MLP_PATHS = {"auto": 0, "fma": 1, "tc": 2, "warp": 3}
 
 
 def set_mlp_path(path: str) -> None:
-    """'auto' (tcgen05 kernels above 16 384 rows, FP32-FMA below), 'fma' or 'tc' for every size (include/cbfrrt.h
-    cbfrrt_set_mlp_path).  Process-wide."""
+    """'auto' (one state per warp up to 4096 rows, FP32-FMA kernels up to 16 384 rows, tcgen05 kernels above), or 'fma' /
+    'tc' / 'warp' for every size (include/cbfrrt.h cbfrrt_set_mlp_path).  Process-wide."""
     check(lib.cbfrrt_set_mlp_path(MLP_PATHS[path]), "cbfrrt_set_mlp_path")
 
 

@@ -10,6 +10,7 @@ std::mutex g_cfg_mu;
 std::map<CfgKey, int> g_cfg;
 static int mlp_path_from_env() {
     const char* e = getenv("CBFRRT_MLP");
+    if (e && e[0] == 'w') return CBFRRT_MLP_WARP;
     return (e && e[0] == 'f') ? CBFRRT_MLP_FMA : ((e && e[0] == 't') ? CBFRRT_MLP_TC : CBFRRT_MLP_AUTO);
 }
 std::atomic<int> g_mlp_path{mlp_path_from_env()};
@@ -36,7 +37,7 @@ const char* cbfrrt_status_string(int s) {
 int cbfrrt_last_cuda_error(void) { return g_last_cuda.load(); }
 
 int cbfrrt_set_mlp_path(int path) {
-    if (path != CBFRRT_MLP_AUTO && path != CBFRRT_MLP_FMA && path != CBFRRT_MLP_TC) return CBFRRT_ERR_BAD_SHAPE;
+    if (path != CBFRRT_MLP_AUTO && path != CBFRRT_MLP_FMA && path != CBFRRT_MLP_TC && path != CBFRRT_MLP_WARP) return CBFRRT_ERR_BAD_SHAPE;
     g_mlp_path.store(path);
     return CBFRRT_OK;
 }

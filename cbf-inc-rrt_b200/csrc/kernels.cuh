@@ -1259,6 +1259,10 @@ __global__ void __launch_bounds__(NT) rollout_segments_kernel(SceneArgs sc, NetA
     }
 }
 
+}  // namespace cbfrrt
+#include "warp.cuh"   // one state per warp: the planner-sized kernels
+namespace cbfrrt {
+
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
@@ -1337,7 +1341,7 @@ extern std::mutex g_cfg_mu;
 extern std::map<CfgKey, int> g_cfg;
 
 template <class Kern>
-static int grid_for(Kern kern, size_t smem, long long tiles) {
+static int grid_for(Kern kern, size_t smem, long long tiles, int threads = NT) {
     int per_sm = 0;
     {
         std::lock_guard<std::mutex> lock(g_cfg_mu);
@@ -1347,7 +1351,7 @@ static int grid_for(Kern kern, size_t smem, long long tiles) {
         else {
             if (smem > 48 * 1024 &&
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) return -1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) return -1;
             g_cfg[key] = per_sm;
         }
     }
@@ -1440,6 +1444,37 @@ inline int check_net(int n, const cbfrrt_cbf_net* net, const cbfrrt_filter_param
     return CBFRRT_OK;
 }
 
+// Batches of at most SMALL_BATCH rows (< 1 tile group per SM) are launch-latency bound: the tcgen05 kernels' per-CTA
+// set-up (two weight tilings, TMEM allocation) costs more than it saves there, so they take the FP32-FMA kernels
+// (measured on cfg0, 4096 rows: 59 us vs 75 us).  cbfrrt_set_mlp_path(CBFRRT_MLP_TC) forces the tensor-core kernels.
+// MLP path: CBFRRT_MLP_AUTO (tcgen05 kernels above SMALL_BATCH rows, FP32-FMA kernels below), _FMA or _TC for every
+// size.  Set through cbfrrt_set_mlp_path() (include/cbfrrt.h); the environment variable CBFRRT_MLP=fma|tc only gives
+// the initial value.  Read at every launch, so one process can exercise both paths (the parity tests do).
+extern std::atomic<int> g_mlp_path;
+inline bool use_tc() { return g_mlp_path.load(std::memory_order_relaxed) != CBFRRT_MLP_FMA; }
+inline bool force_tc() { return g_mlp_path.load(std::memory_order_relaxed) == CBFRRT_MLP_TC; }
+
+// One state per warp (warp.cuh) for planner-sized calls.  Measured on B200 (profiles/r2r_*): a one-thread-per-state launch
+// costs the same 70-90 us from 1 to 4096 Panda states (one dependent chain per state, < 1 warp per scheduler); the warp
+// form is bound by its total instruction count instead and wins up to a few thousand rows.  CBFRRT_MLP_WARP forces it at
+// every size, CBFRRT_MLP_FMA / _TC keep the one-thread-per-state kernels (the parity tests run every path).
+constexpr long long WARP_MAX_ROWS = 4096;       // masks / observations / fused filter: rows per call
+constexpr long long WARP_MAX_TRAJ = 2048;       // closed-loop rollouts: trajectories per call
+constexpr int WARP_GRID_MIN_OBSTACLES = 48;     // below it a lane sweeps the whole staged scene (no global look-ups)
+inline bool use_warp(long long rows, long long max_rows) {
+    const int p = g_mlp_path.load(std::memory_order_relaxed);
+    if (p == CBFRRT_MLP_WARP) return true;
+    if (p != CBFRRT_MLP_AUTO) return false;
+    static const long long env_max = [] { const char* e = getenv("CBFRRT_WARP_MAX"); return e ? atoll(e) : -1LL; }();
+    return rows <= (env_max >= 0 ? env_max : max_rows);
+}
+inline SceneArgs scene_for_warp(const SceneArgs& sc) {
+    SceneArgs a = sc;
+    if (sc.n_boxes + sc.n_spheres < WARP_GRID_MIN_OBSTACLES) a.grid = nullptr;
+    a.stats = nullptr;
+    return a;
+}
+
 template <class RB>
 static int launch_fk(const float* q, long long qs, long long B, float* pos, float* rot, cudaStream_t st) {
     const long long tiles = (B + NT - 1) / NT;
@@ -1451,11 +1486,27 @@ static int launch_fk(const float* q, long long qs, long long B, float* pos, floa
 template <class RB>
 static int launch_collide(const SceneArgs& sc_in, const float* q, long long qs, long long B, float ts, float th,
                           const CollideOutPtrs& out, cudaStream_t st) {
+    const bool grad = out.datax || out.arg_link || out.arg_obs;
+    int grid;
+    if (use_warp(B, WARP_MAX_ROWS) && !sc_in.stats) {
+        const SceneArgs sc = scene_for_warp(sc_in);
+        const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
+        const long long tiles = (B + wp::WARPS - 1) / wp::WARPS;
+#define CBF_LAUNCH_COLLIDE_W(G_, S_)                                                       \
+    {                                                                                      \
+        auto k = wp::collide_kernel_warp<RB, G_, S_>;                                      \
+        if ((grid = grid_for(k, smem, tiles, wp::WNT)) < 0) return CBFRRT_ERR_CUDA;        \
+        k<<<grid, wp::WNT, smem, st>>>(sc, q, qs, B, ts, th, out);                         \
+    }
+        if (out.mins) CBF_LAUNCH_COLLIDE_W(true, true)
+        else if (grad) CBF_LAUNCH_COLLIDE_W(true, false)
+        else CBF_LAUNCH_COLLIDE_W(false, false)
+#undef CBF_LAUNCH_COLLIDE_W
+        return finish_launch();
+    }
     const SceneArgs sc = scene_for(sc_in, B, false);
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
     const long long tiles = (B + NT - 1) / NT;
-    const bool grad = out.datax || out.arg_link || out.arg_obs;
-    int grid;
 #define CBF_LAUNCH_COLLIDE(G_, S_, U_)                                             \
     {                                                                              \
         auto k = collide_kernel<RB, G_, S_, U_>;                                   \
@@ -1469,16 +1520,6 @@ static int launch_collide(const SceneArgs& sc_in, const float* q, long long qs, 
 #undef CBF_LAUNCH_COLLIDE
     return finish_launch();
 }
-
-// Batches of at most SMALL_BATCH rows (< 1 tile group per SM) are launch-latency bound: the tcgen05 kernels' per-CTA
-// set-up (two weight tilings, TMEM allocation) costs more than it saves there, so they take the FP32-FMA kernels
-// (measured on cfg0, 4096 rows: 59 us vs 75 us).  cbfrrt_set_mlp_path(CBFRRT_MLP_TC) forces the tensor-core kernels.
-// MLP path: CBFRRT_MLP_AUTO (tcgen05 kernels above SMALL_BATCH rows, FP32-FMA kernels below), _FMA or _TC for every
-// size.  Set through cbfrrt_set_mlp_path() (include/cbfrrt.h); the environment variable CBFRRT_MLP=fma|tc only gives
-// the initial value.  Read at every launch, so one process can exercise both paths (the parity tests do).
-extern std::atomic<int> g_mlp_path;
-inline bool use_tc() { return g_mlp_path.load(std::memory_order_relaxed) != CBFRRT_MLP_FMA; }
-inline bool force_tc() { return g_mlp_path.load(std::memory_order_relaxed) == CBFRRT_MLP_TC; }
 
 template <int N>
 static int launch_filter_generic(const NetArgs& net, int H, int L, const float* datax, long long B, const FilterOutPtrs& out,
@@ -1502,6 +1543,15 @@ static int launch_filter_generic(const NetArgs& net, int H, int L, const float* 
 
 template <int N>
 static int launch_filter(const NetArgs& net, const float* datax, long long B, const FilterOutPtrs& out, cudaStream_t st) {
+    if (use_warp(B, WARP_MAX_ROWS)) {
+        using LYW = NetLayout<N + 1, 48, 2>;
+        const size_t smem = 4 * smem_floats(0, 0, LYW::TOTAL, ParamLayout<N>::TOTAL, wp::WarpNet<N + 1, 48>::TOTAL);
+        auto k = wp::filter_kernel_warp<N, 48>;
+        const int grid = grid_for(k, smem, (B + wp::WARPS - 1) / wp::WARPS, wp::WNT);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, wp::WNT, smem, st>>>(net, datax, B, out);
+        return finish_launch();
+    }
     if (use_tc() && (B > SMALL_BATCH || force_tc())) {
         const size_t smem = 4 * smem_floats(0, 0, tc::Layout<2, 4>::TOTAL, ParamLayout<N>::TOTAL, 0);
         auto k = filter_kernel_tc<N, 2>;
@@ -1522,6 +1572,17 @@ static int launch_filter(const NetArgs& net, const float* datax, long long B, co
 template <class RB>
 static int launch_safety(const SceneArgs& sc_in, const NetArgs& net, const float* q, long long qs, long long B, float ts,
                          float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, const PeerOut& po, cudaStream_t st) {
+    if (use_warp(B, WARP_MAX_ROWS) && po.n == 0 && !sc_in.stats) {
+        const SceneArgs sc = scene_for_warp(sc_in);
+        using LYW = NetLayout<RB::N + 1, 48, 2>;
+        const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LYW::TOTAL, ParamLayout<RB::N>::TOTAL,
+                                            wp::WarpNet<RB::N + 1, 48>::TOTAL);
+        auto k = wp::safety_kernel_warp<RB, 48>;
+        const int grid = grid_for(k, smem, (B + wp::WARPS - 1) / wp::WARPS, wp::WNT);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, wp::WNT, smem, st>>>(sc, net, q, qs, B, ts, th, co, fo);
+        return finish_launch();
+    }
     const SceneArgs sc = scene_for(sc_in, B, false);
     const int gg = 4;
     const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2, 4>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
@@ -1570,12 +1631,19 @@ static int launch_edges(const SceneArgs& sc, const float* qf, const float* qt, l
 template <class RB>
 static int launch_edges_var(const SceneArgs& sc_in, const float* qf, const float* qt, long long E, const long long* off,
                             int K_all, long long P, float ts, float th, uint8_t* valid, int* first_bad, cudaStream_t st) {
-    const SceneArgs sc = scene_for(sc_in, P, false);
+    const bool warp = use_warp(P, WARP_MAX_ROWS) && !sc_in.stats;
+    const SceneArgs sc = warp ? scene_for_warp(sc_in) : scene_for(sc_in, P, false);
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, 0, 0, 0);
     const int eg = (int)((E + 255) / 256 < 1184 ? (E + 255) / 256 : 1184);
     edge_var_init<0><<<eg, 256, 0, st>>>(first_bad, E);
     if (finish_launch()) return CBFRRT_ERR_CUDA;
-    if (P > 0) {
+    if (P > 0 && warp) {
+        auto k = wp::edge_var_kernel_warp<RB>;
+        const int grid = grid_for(k, smem, (P + wp::WARPS - 1) / wp::WARPS, wp::WNT);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, wp::WNT, smem, st>>>(sc, qf, qt, E, off, K_all, P, ts, th, first_bad);
+        if (finish_launch()) return CBFRRT_ERR_CUDA;
+    } else if (P > 0) {
         auto k = sc.grid ? edge_var_kernel<RB, true> : edge_var_kernel<RB, false>;
         const int grid = grid_for(k, smem, (P + NT - 1) / NT);
         if (grid < 0) return CBFRRT_ERR_CUDA;
@@ -1589,6 +1657,17 @@ static int launch_edges_var(const SceneArgs& sc_in, const float* qf, const float
 template <class RB>
 static int launch_rollout(const SceneArgs& sc_in, const NetArgs& net, const float* q0, long long T, const RolloutArgs& ra,
                           float ts, float th, float* qf, uint8_t* alive, int* done, float* traj, cudaStream_t st) {
+    if (use_warp(T, WARP_MAX_TRAJ)) {
+        const SceneArgs sc = scene_for_warp(sc_in);
+        using LYW = NetLayout<RB::N + 1, 48, 2>;
+        const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LYW::TOTAL, ParamLayout<RB::N>::TOTAL,
+                                            wp::WarpNet<RB::N + 1, 48>::TOTAL);
+        auto k = wp::rollout_kernel_warp<RB, 48>;
+        const int grid = grid_for(k, smem, (T + wp::WARPS - 1) / wp::WARPS, wp::WNT);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, wp::WNT, smem, st>>>(sc, net, q0, T, ra, ts, th, qf, alive, done, traj);
+        return finish_launch();
+    }
     const SceneArgs sc = scene_for(sc_in, T, true);
     const int gg = 4;
     const size_t smem_tc = 4 * smem_floats(sc.n_boxes, sc.n_spheres, tc::Layout<2, 4>::TOTAL, ParamLayout<RB::N>::TOTAL, 0);
@@ -1613,6 +1692,34 @@ template <class RB>
 static int launch_rollout_segments(const SceneArgs& sc_in, const NetArgs& net, const float* q0, int T, int n_seg, int seg_len,
                                    const RolloutArgs& ra, float ts, float th, float* seg_q, uint8_t* seg_alive, int* seg_done,
                                    float* traj, cudaStream_t st) {
+    if (use_warp(T, wp::SEG_SLOTS * wp::SEG_MAX_CLUSTER * wp::WARPS)) {
+        // one row per warp over a cluster of CTAs (two rows per warp beyond 64 rows)
+        const SceneArgs sc = scene_for_warp(sc_in);
+        using LYW = NetLayout<RB::N + 1, 48, 2>;
+        const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LYW::TOTAL, ParamLayout<RB::N>::TOTAL,
+                                            wp::WarpNet<RB::N + 1, 48>::TOTAL + wp::WARPS * wp::SEG_SLOTS * wp::RowState<RB::N>::TOTAL +
+                                                2 * wp::SEG_MAX_CLUSTER);
+        auto k = wp::rollout_segments_kernel_warp<RB, 48>;
+        if (grid_for(k, smem, 1, wp::WNT) < 0) return CBFRRT_ERR_CUDA;
+        int n_cta = (T + wp::WARPS - 1) / wp::WARPS;
+        if (n_cta > wp::SEG_MAX_CLUSTER) n_cta = wp::SEG_MAX_CLUSTER;
+        if (n_cta < 1) n_cta = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_cta);
+        cfg.blockDim = dim3(wp::WNT);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = n_cta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, k, sc, net, q0, T, n_seg, seg_len, ra, ts, th, seg_q, seg_alive, seg_done, traj) != cudaSuccess) {
+            g_last_cuda = (int)cudaGetLastError();
+            return CBFRRT_ERR_CUDA;
+        }
+        return finish_launch();
+    }
     const SceneArgs sc = scene_for(sc_in, T, true);
     using LY = NetLayout<RB::N + 1, 48, 2>;
     const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LY::TOTAL, ParamLayout<RB::N>::TOTAL, CoopLayout<RB::N + 1, 48>::TOTAL);

@@ -128,9 +128,13 @@ int cbfrrt_robot_info(int robot, int32_t *n, int32_t *n_links, int32_t *n_sphere
  * The MLP of cbf_filter / safety_filter / rollout has two implementations with the same contract (1e-5 against the
  * oracle): tcgen05 tensor-core kernels (TF32x3) and FP32-FMA kernels.  AUTO (default) takes the tensor-core kernels
  * above 16 384 rows and the FP32-FMA kernels below (launch-latency bound sizes).  FMA / TC force one path for every
- * size (A/B measurements, and the parity tests, which cover both).  Process-wide; initial value from the environment
- * variable CBFRRT_MLP=fma|tc.  Returns CBFRRT_ERR_BAD_SHAPE for an unknown value. */
-typedef enum { CBFRRT_MLP_AUTO = 0, CBFRRT_MLP_FMA = 1, CBFRRT_MLP_TC = 2 } cbfrrt_mlp_path;
+ * size (A/B measurements, and the parity tests, which cover both).  Planner-sized calls (the reference's own regime:
+ * batch = 1, eval_batchrrt_mindis_cbfsteer.py:66) have a third form of every kernel that spreads ONE state over the 32
+ * lanes of a warp (csrc/warp.cuh: bit-identical masks / minima / arg-mins, same tolerance for the network); AUTO takes it
+ * up to 4096 rows per call (2048 trajectories, every rollout_segments call), WARP forces it for every size, FMA / TC
+ * never use it.  Process-wide; initial value from the environment variable CBFRRT_MLP=fma|tc|warp.  Returns
+ * CBFRRT_ERR_BAD_SHAPE for an unknown value. */
+typedef enum { CBFRRT_MLP_AUTO = 0, CBFRRT_MLP_FMA = 1, CBFRRT_MLP_TC = 2, CBFRRT_MLP_WARP = 3 } cbfrrt_mlp_path;
 int cbfrrt_set_mlp_path(int path);
 int cbfrrt_get_mlp_path(void);
 
