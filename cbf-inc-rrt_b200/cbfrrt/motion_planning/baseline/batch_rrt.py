@@ -117,7 +117,14 @@ def _goal_test(dynamics_model, states):
     batch: the distance part is evaluated first, in the same float32 torch expression, and the safe_mask launch is made
     only for the rows inside the goal ball -- none, for most expansions."""
     dm = dynamics_model
-    x = torch.as_tensor(np.asarray(states), dtype=torch.float32).reshape(-1, dm.q_dims)
+    xs = np.asarray(states, dtype=np.float32).reshape(-1, dm.q_dims)
+    # screen in numpy (an expansion makes this test for a handful of rows): a row whose distance is not within 1e-4 of the
+    # 0.2 rad threshold gets the same answer from any float32 evaluation order; otherwise the reference's own torch
+    # expression decides
+    d = np.sqrt(((xs - np.asarray(dm.goal_state[:dm.q_dims], dtype=np.float32)) ** 2).sum(1))
+    if not (d <= 0.2 + 1e-4).any():
+        return np.zeros(xs.shape[0], dtype=bool)
+    x = torch.from_numpy(xs)
     goal = torch.as_tensor(dm.goal_state[:dm.q_dims]).type_as(x)
     near = (x[:, :dm.q_dims] - goal).norm(dim=1) <= 0.2
     done = torch.zeros(x.shape[0], dtype=torch.bool)

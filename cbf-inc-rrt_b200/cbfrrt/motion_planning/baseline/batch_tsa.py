@@ -14,28 +14,43 @@ from .tsa import _rollout
 MAX_FUSED_BATCH = 128     # cbfrrt_rollout_segments: the rows of a batch share one CTA
 
 
+def _gain_host(dm):
+    key = (id(dm.K), dm.K._version)
+    if getattr(dm, "_K_np_key", None) != key:
+        dm._K_np = dm.K.detach().cpu().numpy().astype(np.float32)
+        dm._K_np_key = key
+    return dm._K_np
+
+
+def _dev_index(device):
+    d = torch.device(device)
+    if d.type != "cuda":
+        return 0
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
 def explore_nearest(non_terminal_states, sample_states, batch, device="cuda"):
     """The nearest-neighbour selection of global_explore (batch_tsa.py:129-145) on the GPU (cbfrrt::knn):
       * tree smaller than ``batch`` (or freshly sampled states): one nearest node per sample (np.argmin per row);
       * otherwise: the ``batch`` nearest nodes of sample_states[0] (np.argsort(dists)[:batch]), the sample repeated.
     -> (nearest_idxs int64 (B,), min_dists float32 (B,), sample_states (B, n)) with the reference's shapes.
     Ties go to the lowest node index, as np.argmin / a stable sort do."""
-    tree = torch.as_tensor(np.asarray(non_terminal_states), dtype=torch.float32, device=device)
-    samples = torch.as_tensor(np.asarray(sample_states), dtype=torch.float32, device=device).reshape(-1, tree.shape[1])
+    tree = np.asarray(non_terminal_states, dtype=np.float32)
+    samples = np.asarray(sample_states, dtype=np.float32).reshape(-1, tree.shape[1])
     if tree.shape[0] < batch:
-        idx, dist = ops.knn(samples, tree, 1)
-        return idx[:, 0].cpu().numpy().astype(np.int64), dist[:, 0].cpu().numpy(), np.asarray(sample_states)
-    idx, dist = ops.knn(samples[:1], tree, int(batch))
+        idx, dist = ops.knn_host(samples, tree, 1, device=_dev_index(device))
+        return idx[:, 0].astype(np.int64), dist[:, 0], np.asarray(sample_states)
+    idx, dist = ops.knn_host(samples[:1], tree, int(batch), device=_dev_index(device))
     rep = np.array([np.asarray(sample_states)[0] for _ in range(batch)])
-    return idx[0].cpu().numpy().astype(np.int64), dist[0].cpu().numpy(), rep
+    return idx[0].astype(np.int64), dist[0], rep
 
 
 def explore_nearest_each(non_terminal_states, sample_states, device="cuda"):
     """first branch of global_explore (batch_tsa.py:129-137): one nearest node for every freshly sampled state"""
-    tree = torch.as_tensor(np.asarray(non_terminal_states), dtype=torch.float32, device=device)
-    samples = torch.as_tensor(np.asarray(sample_states), dtype=torch.float32, device=device).reshape(-1, tree.shape[1])
-    idx, dist = ops.knn(samples, tree, 1)
-    return idx[:, 0].cpu().numpy().astype(np.int64), dist[:, 0].cpu().numpy()
+    tree = np.asarray(non_terminal_states, dtype=np.float32)
+    samples = np.asarray(sample_states, dtype=np.float32).reshape(-1, tree.shape[1])
+    idx, dist = ops.knn_host(samples, tree, 1, device=_dev_index(device))
+    return idx[:, 0].astype(np.int64), dist[:, 0]
 
 
 @torch.no_grad()
@@ -126,21 +141,20 @@ def steer_segments_fused(controller, dynamics_model, sample_states, nearests, n_
     -> list over segments of (x_last (B,n) numpy, no_collisions [bool]*B, xs_list), exactly what ``n_segments``
     consecutive ``steer(controller.u, ...)`` calls return.  B <= MAX_FUSED_BATCH."""
     dm = dynamics_model
+    goals = np.asarray(sample_states, dtype=np.float32).reshape(-1, dm.q_dims)
     dm.set_intermediate_goals(np.asarray(sample_states))
-    q0 = torch.as_tensor(np.asarray(nearests), dtype=torch.float32).reshape(-1, dm.q_dims).to(dm.device)
-    b, s, fl, gr = dm.env.scene
-    lo, hi = controller._limits()
-    seg_q, seg_alive, seg_done, traj = ops.rollout_segments(
-        q0, dm.goal_tensor(dm.device), int(n_segments), int(RRT_step), int(dm.controller_dt // dm.dt), float(dm.dt), 9, 10, 3e-2,
-        b, s, fl, gr, controller._weights(), dm.K_on(dm.device), lo, hi, float(controller.clf_lambda),
-        float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard), dm.robot.robot_id,
-        controller.h_hidden_size, controller.h_hidden_layers)
-    # two read-backs instead of four (each one is a stream synchronisation)
-    B_, n_ = seg_q.shape[0], seg_q.shape[2]
-    flt = torch.cat([seg_q.reshape(B_, -1), traj.reshape(B_, -1)], dim=1).cpu().numpy()
-    flags = torch.stack([seg_alive.to(torch.int32), seg_done], dim=0).cpu().numpy()
-    seg_q, traj = flt[:, :n_segments * n_].reshape(B_, n_segments, n_), flt[:, n_segments * n_:].reshape(B_, -1, n_)
-    seg_alive, seg_done = flags[0].astype(bool), flags[1]
+    q0 = np.asarray(nearests, dtype=np.float32).reshape(-1, dm.q_dims)
+    if goals.shape[0] == 1 and q0.shape[0] > 1:
+        goals = np.repeat(goals, q0.shape[0], 0)
+    env = dm.env
+    lo, hi = controller._limits_host()
+    # numpy in / numpy out (cbfrrt_rollout_segments_host): one pinned H2D copy, the launch, one D2H copy
+    seg_q, seg_alive, seg_done, traj = ops.rollout_segments_host(
+        dm.robot.name, q0, goals, int(n_segments), int(RRT_step), int(dm.controller_dt // dm.dt), float(dm.dt), 9, 10, 3e-2,
+        np.concatenate([env.obs_positions, env.obs_sizes], 1), env.obs_spheres, bool(env.include_floor), controller._weights_host(),
+        controller.h_hidden_size, controller.h_hidden_layers, _gain_host(dm), lo, hi, float(controller.clf_lambda),
+        float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard),
+        device=_dev_index(dm.device))
     out = []
     for k in range(int(n_segments)):
         xs = [[row for row in traj[i, k * RRT_step:k * RRT_step + seg_done[i, k]]] for i in range(traj.shape[0])]

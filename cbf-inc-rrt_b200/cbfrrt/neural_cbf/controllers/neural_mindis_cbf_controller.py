@@ -41,13 +41,35 @@ class NeuralMindisCBFController(NeuralObsCBFController):
         self._consts = None
 
     # ------------------------------------------------------------------ device-side constants
+    def _weights_key(self):
+        ps = getattr(self, "_param_list", None)
+        if ps is None:
+            ps = self._param_list = list(self.h_nn.parameters())
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
     def _weights(self) -> torch.Tensor:
-        key = tuple((p.data_ptr(), p._version) for p in self.h_nn.parameters())
+        key = self._weights_key()
         if self._packed is None or key != self._packed_key:
             self._packed = ops.pack_weights(self.h_nn.state_dict(), self.dynamics_model.n_dims, self.h_hidden_size,
                                             self.h_hidden_layers, device=self.device)
             self._packed_key = key
         return self._packed
+
+    def _weights_host(self):
+        """the packed network as a numpy buffer, for the host-pointer entry points (cbfrrt_*_host)"""
+        key = self._weights_key()
+        if getattr(self, "_packed_np", None) is None or key != getattr(self, "_packed_np_key", None):
+            from ...workloads import pack_weights_np
+            self._packed_np = pack_weights_np(self.h_nn.state_dict(), self.dynamics_model.n_dims, self.h_hidden_size,
+                                              self.h_hidden_layers)
+            self._packed_np_key = key
+        return self._packed_np
+
+    def _limits_host(self):
+        if getattr(self, "_consts_np", None) is None:
+            upper, lower = self.dynamics_model.control_limits
+            self._consts_np = (lower.detach().cpu().numpy().astype("float32"), upper.detach().cpu().numpy().astype("float32"))
+        return self._consts_np
 
     def _limits(self):
         if self._consts is None:

@@ -641,6 +641,47 @@ def safety_filter_host(robot: str, q: np.ndarray, boxes6: np.ndarray, spheres: n
     return out
 
 
+def rollout_segments_host(robot: str, q0: np.ndarray, goal: np.ndarray, n_segments: int, seg_len: int, ctrl_every: int,
+                          dt: float, stuck_lag: int, stuck_after: int, stuck_eps: float, boxes6: np.ndarray, spheres,
+                          floor: bool, weights: np.ndarray, hidden: int, layers: int, K: np.ndarray, u_lo, u_hi, lam: float,
+                          penalty: float, thr_soft: float, thr_hard: float, device: int = 0):
+    """numpy in / numpy out form of rollout_segments (include/cbfrrt.h cbfrrt_rollout_segments_host): one pinned H2D copy,
+    the launch, one D2H copy.  -> seg_q f32[T,n_seg,n], seg_alive bool[T,n_seg], seg_done i32[T,n_seg],
+    traj f32[T,n_seg*seg_len,n].  ``weights``: the packed buffer (workloads.pack_weights_np)."""
+    n = ROBOT_N[ROBOT_ID[robot]]
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    q0, goal, K, u_lo, u_hi, weights = f(q0).reshape(-1, n), f(goal).reshape(-1, n), f(K), f(u_lo), f(u_hi), f(weights)
+    T = q0.shape[0]
+    if goal.shape[0] != T:
+        raise ValueError(f"goal must hold one row per trajectory ({T}), got {goal.shape[0]}")
+    boxes6 = f(boxes6).reshape(-1, 6)
+    spheres = f(spheres).reshape(-1, 4) if spheres is not None else np.zeros((0, 4), np.float32)
+    hs = _lib.HostScene(boxes6.shape[0], spheres.shape[0], int(bool(floor)), 0, boxes6.ctypes.data, spheres.ctypes.data)
+    rp = RolloutParams(seg_len, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, 1, 1)
+    seg_q = np.empty((T, n_segments, n), np.float32)
+    seg_alive = np.empty((T, n_segments), np.uint8)
+    seg_done = np.empty((T, n_segments), np.int32)
+    traj = np.empty((T, n_segments * seg_len, n), np.float32)
+    check(lib.cbfrrt_rollout_segments_host(device, ROBOT_ID[robot], C.byref(hs), hidden, layers, weights.ctypes.data, weights.size,
+                                           q0.ctypes.data, T, goal.ctypes.data, K.ctypes.data, u_lo.ctypes.data, u_hi.ctypes.data,
+                                           lam, penalty, C.byref(rp), n_segments, thr_soft, thr_hard, seg_q.ctypes.data,
+                                           seg_alive.ctypes.data, seg_done.ctypes.data, traj.ctypes.data),
+          "cbfrrt_rollout_segments_host")
+    return seg_q, seg_alive.astype(bool), seg_done, traj
+
+
+def knn_host(queries: np.ndarray, tree: np.ndarray, k: int, device: int = 0):
+    """numpy in / numpy out form of knn (include/cbfrrt.h cbfrrt_knn_host) -> idx i32[M,k], dist f32[M,k]"""
+    queries, tree = np.ascontiguousarray(queries, np.float32), np.ascontiguousarray(tree, np.float32)
+    if queries.ndim != 2 or tree.ndim != 2 or queries.shape[1] != tree.shape[1]:
+        raise ValueError("knn_host: queries [M,n] and tree [N,n] must share n")
+    M, n = queries.shape
+    idx, dist = np.empty((M, k), np.int32), np.empty((M, k), np.float32)
+    check(lib.cbfrrt_knn_host(device, n, queries.ctypes.data, tree.ctypes.data, M, tree.shape[0], k, idx.ctypes.data,
+                              dist.ctypes.data), "cbfrrt_knn_host")
+    return idx, dist
+
+
 # ----------------------------------------------------------------------------- LiDAR / PointNet barrier
 def _rna_tf32(w: np.ndarray) -> np.ndarray:
     """cvt.rna.tf32.f32: round to nearest (ties away from zero) onto 10 mantissa bits"""

