@@ -482,10 +482,15 @@ def main():
     bound = max(pipes, key=lambda k: pipes[k]["frac"])
     traffic = None   # per launch, from the committed ncu --set full capture of this command (profiles/); filled in below
     tr_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tr_file) and world == 1:
-        traffic = json.load(open(tr_file)).get(w["name"])
+    traffic_note = "no ncu --set full capture committed for this workload"
+    if os.path.exists(tr_file):
+        ent = json.load(open(tr_file)).get(w["name"])
+        if ent:   # bytes per state from the committed capture x the rows of one launch of THIS run
+            traffic = ent["dram_bytes_per_state"] * rows_per_launch
+            traffic_note = ent["source"]
     roofline = {"bound": bound, "achieved": pipes[bound]["achieved"], "peak": pipes[bound]["peak"], "unit": pipes[bound]["unit"],
-                "frac": pipes[bound]["frac"], "traffic": traffic, "pipes": pipes,
+                "frac": pipes[bound]["frac"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                "traffic_source": traffic_note, "pipes": pipes,
                 "kernel": ("safety_kernel_tc" if tc_path else "safety_kernel") + f"<{robot}, grid={bool(stats['grid'])}>",
                 "kernel_ms": kernel_s * 1e3, "rows_per_launch": rows_per_launch, "broad_phase": stats,
                 "fp32_work_per_state_brute_force_formula": cost["fp32_brute_force"],
