@@ -649,6 +649,64 @@ __device__ __forceinline__ bool rollout_after_step(const RolloutArgs& ra, int t,
     return false;
 }
 
+// The same step logic with the stored states mirrored in a RING of the last STUCK_RING rows (shared memory of the warp
+// kernels): the stuck test re-reads states written a few steps ago, and from the trajectory array that is an L2 round trip
+// (~0.35 us) on the critical path of every step of a one-warp trajectory.  tr (global, optional) is only written.
+// Requires ra.stuck_lag < STUCK_RING (the launcher checks).  Ring slot of stored state number d: d % STUCK_RING.
+constexpr int STUCK_RING = 16;
+template <int N>
+__device__ __forceinline__ bool rollout_after_step_ring(const RolloutArgs& ra, int t, bool unsafe, float (&q)[N],
+                                                        const float (&qn)[N], float* __restrict__ tr, float* __restrict__ ring,
+                                                        bool& ok, bool& dead, int& done) {
+    if (ra.stuck_mode == 1) {
+        if (!dead) {
+            bool stuck = false;
+            if (ra.stuck_lag > 0 && done > ra.stuck_after) {
+                const float* a = ring + ((done - 1) % STUCK_RING) * N;
+                const float* b = ring + ((done - 1 - ra.stuck_lag) % STUCK_RING) * N;
+                float dsq = 0.f;
+#pragma unroll
+                for (int k = 0; k < N; ++k) { const float d = __fsub_rn(a[k], b[k]); dsq = fmaf(d, d, dsq); }
+                stuck = __fsqrt_rn(dsq) < ra.stuck_eps;
+            }
+            if (stuck || unsafe) { ok = false; dead = true; }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) q[k] = qn[k];
+        if (!dead) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) ring[(done % STUCK_RING) * N + k] = q[k];
+            if (tr) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) tr[done * N + k] = q[k];
+            }
+            ++done;
+        }
+        return dead && !ra.keep_going;
+    }
+    if (unsafe) {
+        ok = false;
+        if (!ra.keep_going) return true;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) q[k] = qn[k];
+#pragma unroll
+    for (int k = 0; k < N; ++k) ring[(t % STUCK_RING) * N + k] = q[k];
+    if (tr) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) tr[t * N + k] = q[k];
+    }
+    done = t + 1;
+    if (ra.stuck_lag > 0 && t > ra.stuck_after) {
+        const float* old = ring + ((t - ra.stuck_lag) % STUCK_RING) * N;
+        float dsq = 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { const float d = __fsub_rn(q[k], old[k]); dsq = fmaf(d, d, dsq); }
+        if (__fsqrt_rn(dsq) < ra.stuck_eps) return true;
+    }
+    return false;
+}
+
 // ------------------------------------------------------------------ tensor-core (tcgen05) variants
 // Same contracts as filter_kernel / safety_kernel; the MLP of every 128-state tile runs as TF32x3 GEMMs on the
 // tensor cores (mlp_tc.cuh).  One CTA per SM of GG tile groups (see tc_groups) sharing the staged weights; all 128
@@ -1663,7 +1721,7 @@ static int launch_rollout(const SceneArgs& sc_in, const NetArgs& net, const floa
         const SceneArgs sc = scene_for_warp(sc_in);
         using LYW = NetLayout<RB::N + 1, 48, 2>;
         const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LYW::TOTAL, ParamLayout<RB::N>::TOTAL,
-                                            wp::WarpNet<RB::N + 1, 48>::TOTAL);
+                                            wp::WarpNet<RB::N + 1, 48>::TOTAL + wp::WARPS * STUCK_RING * RB::N);
         auto k = wp::rollout_kernel_warp<RB, 48>;
         const int grid = grid_for(k, smem, (T + wp::WARPS - 1) / wp::WARPS, wp::WNT);
         if (grid < 0) return CBFRRT_ERR_CUDA;
@@ -1694,13 +1752,13 @@ template <class RB>
 static int launch_rollout_segments(const SceneArgs& sc_in, const NetArgs& net, const float* q0, int T, int n_seg, int seg_len,
                                    const RolloutArgs& ra, float ts, float th, float* seg_q, uint8_t* seg_alive, int* seg_done,
                                    float* traj, cudaStream_t st) {
-    if (use_warp(T, wp::SEG_SLOTS * wp::SEG_MAX_CLUSTER * wp::WARPS)) {
+    using LYW = NetLayout<RB::N + 1, 48, 2>;
+    const size_t smem_w = 4 * smem_floats(sc_in.n_boxes, sc_in.n_spheres, LYW::TOTAL, ParamLayout<RB::N>::TOTAL,
+                                          wp::seg_scratch_floats<RB, 48>(seg_len));
+    if (use_warp(T, wp::SEG_MAX_ROWS) && smem_w <= TC_SMEM_MAX) {
         // one row per warp over a cluster of CTAs (two rows per warp beyond 64 rows)
         const SceneArgs sc = scene_for_warp(sc_in);
-        using LYW = NetLayout<RB::N + 1, 48, 2>;
-        const size_t smem = 4 * smem_floats(sc.n_boxes, sc.n_spheres, LYW::TOTAL, ParamLayout<RB::N>::TOTAL,
-                                            wp::WarpNet<RB::N + 1, 48>::TOTAL + wp::WARPS * wp::SEG_SLOTS * wp::RowState<RB::N>::TOTAL +
-                                                2 * wp::SEG_MAX_CLUSTER);
+        const size_t smem = smem_w;
         auto k = wp::rollout_segments_kernel_warp<RB, 48>;
         if (grid_for(k, smem, 1, wp::WNT) < 0) return CBFRRT_ERR_CUDA;
         int n_cta = (T + wp::WARPS - 1) / wp::WARPS;

@@ -462,6 +462,8 @@ __global__ void __launch_bounds__(WNT) rollout_kernel_warp(SceneArgs sc, NetArgs
     warp_net_setup<N + 1, H, WNT>(s.weights, s.scratch);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* ws = s.scratch + WN::WT + warp * WN::SCR;
+    float* ring = s.scratch + WN::TOTAL + warp * STUCK_RING * N;   // last stored states (stuck test)
+    const bool use_ring = ra.stuck_lag < STUCK_RING;
     for (long long b = (long long)blockIdx.x * WARPS + warp; b < T; b += (long long)gridDim.x * WARPS) {
         float q[N], qn[N], g[N], u[N], dodq[N], o;
         load_row<N>(q0 + b * N, q);
@@ -495,9 +497,12 @@ __global__ void __launch_bounds__(WNT) rollout_kernel_warp(SceneArgs sc, NetArgs
             } else {
                 collide_state_warp<RB, false, false>(qn, sv, base_min, cr);
             }
-            __syncwarp();                                  // trajectory rows of earlier steps are visible to every lane
-            if (rollout_after_step<N>(ra, t, cr.hard_min <= thr_hard, q, qn, tr, ok, dead, done)) break;
+            __syncwarp();                                  // stored states of earlier steps are visible to every lane
+            const bool fin = use_ring ? rollout_after_step_ring<N>(ra, t, cr.hard_min <= thr_hard, q, qn, tr, ring, ok, dead, done)
+                                      : rollout_after_step<N>(ra, t, cr.hard_min <= thr_hard, q, qn, tr, ok, dead, done);
+            if (fin) break;
         }
+        __syncwarp();
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < N; ++k) q_final[b * N + k] = q[k];
@@ -508,16 +513,31 @@ __global__ void __launch_bounds__(WNT) rollout_kernel_warp(SceneArgs sc, NetArgs
 }
 
 // A whole expansion of the batched planner (see rollout_segments_kernel): one row per warp, the rows of the batch spread
-// over a thread-block CLUSTER of up to 8 CTAs (64 warps; up to two rows per warp for T <= 128).  The reference's batch-
-// wide early exit (batch_tsa.py:229-230: the segment ends once EVERY row is dead) is a cluster-wide OR per step: each CTA
-// reduces its warps (__syncthreads_or), publishes the bit into every CTA's shared memory (distributed shared memory
-// stores), and one cluster barrier later every CTA reads the same vector.  Two alternating flag vectors: a vector is
-// rewritten two steps later, i.e. after the barrier that follows its last read.
-constexpr int SEG_SLOTS = 2, SEG_MAX_CLUSTER = 8;
+// over a thread-block CLUSTER of up to 8 CTAs (64 warps; up to two rows per warp for T <= 128).
+//
+// The reference's batch-wide early exit (batch_tsa.py:229-230: the segment's loop ends after the first step at which EVERY
+// row is dead, and x_last is the running state of every row after THAT step) couples the rows.  A barrier per step would
+// put a cluster round trip (~1.5 us) on a 2 us step, so the rows run DECOUPLED within a segment and the exit step is
+// reconstructed exactly:
+//   * a row that dies at step d publishes d into every CTA's shared memory (distributed shared memory stores) -- a row dies
+//     at most once per segment, so the entry is final once written;
+//   * after each of its steps a warp polls its CTA's copy: when every row has a death step, t* = max d is THE exit step; the
+//     warp keeps stepping while t < t* and stops at t >= t*.  Polling a stale copy only delays the exit;
+//   * a dead row saves its running state after every step (it can run past t* before it learns t*); after the ONE cluster
+//     barrier at the end of the segment every CTA computes the same exact t* and rows that ran past it restore the state
+//     after step t*.  Appended states, counts and flags stop changing at a row's death, so nothing else needs a roll-back.
+// Two death vectors alternate between segments; the next segment's vector is reset before the barrier of this one.
+constexpr int SEG_SLOTS = 2, SEG_MAX_CLUSTER = 8, SEG_MAX_ROWS = SEG_SLOTS * SEG_MAX_CLUSTER * WARPS, SEG_ALIVE = 0x7fffffff;
 template <int N>
 struct RowState {   // floats per (warp, slot)
     static constexpr int Q = 0, U = N, G = 2 * N, DODQ = 3 * N, O = 4 * N, TOTAL = 4 * N + 4;
 };
+// floats of shared memory behind the staged scene / weights / parameters
+template <class RB, int H>
+__host__ __device__ constexpr int seg_scratch_floats(int seg_len) {
+    return WarpNet<RB::N + 1, H>::TOTAL + WARPS * SEG_SLOTS * (RowState<RB::N>::TOTAL + STUCK_RING * RB::N + seg_len * RB::N) +
+           2 * SEG_MAX_ROWS;
+}
 template <class RB, int H>
 __global__ void __launch_bounds__(WNT) rollout_segments_kernel_warp(SceneArgs sc, NetArgs net, const float* __restrict__ q0,
                                                                     int T, int n_seg, int seg_len, RolloutArgs ra,
@@ -538,12 +558,19 @@ __global__ void __launch_bounds__(WNT) rollout_segments_kernel_warp(SceneArgs sc
     warp_net_setup<N + 1, H, WNT>(s.weights, s.scratch);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* ws = s.scratch + WN::WT + warp * WN::SCR;
-    float* rows = s.scratch + WN::TOTAL + warp * SEG_SLOTS * RS::TOTAL;
-    int* flags = reinterpret_cast<int*>(s.scratch + WN::TOTAL + WARPS * SEG_SLOTS * RS::TOTAL);   // [2][SEG_MAX_CLUSTER]
+    float* p_rows = s.scratch + WN::TOTAL;
+    float* p_rings = p_rows + WARPS * SEG_SLOTS * RS::TOTAL;
+    float* p_hist = p_rings + WARPS * SEG_SLOTS * STUCK_RING * N;
+    int* death = reinterpret_cast<int*>(p_hist + WARPS * SEG_SLOTS * seg_len * N);   // [2][SEG_MAX_ROWS]
+    float* rows = p_rows + warp * SEG_SLOTS * RS::TOTAL;
+    float* rings = p_rings + warp * SEG_SLOTS * STUCK_RING * N;
+    float* hist = p_hist + warp * SEG_SLOTS * seg_len * N;
+    const bool use_ring = ra.stuck_lag < STUCK_RING;
     const int total_warps = n_cta * WARPS, gw = rank * WARPS + warp;
     const long long steps = (long long)n_seg * seg_len;
     bool ok[SEG_SLOTS], dead[SEG_SLOTS];
     int done[SEG_SLOTS];
+    for (int i = threadIdx.x; i < 2 * SEG_MAX_ROWS; i += WNT) death[i] = SEG_ALIVE;
 #pragma unroll
     for (int sl = 0; sl < SEG_SLOTS; ++sl) {
         const int b = gw + sl * total_warps;
@@ -558,9 +585,9 @@ __global__ void __launch_bounds__(WNT) rollout_segments_kernel_warp(SceneArgs sc
         }
     }
     __syncwarp();
-    cluster.sync();                                        // every CTA of the cluster runs before remote stores reach it
-    int phase = 0;
+    cluster.sync();                                        // every CTA runs and has initialised its death vectors
     for (int sg = 0; sg < n_seg; ++sg) {
+        int* dv = death + (sg & 1) * SEG_MAX_ROWS;
 #pragma unroll
         for (int sl = 0; sl < SEG_SLOTS; ++sl) {           // complete_sample_with_observations at the start of the segment
             const int b = gw + sl * total_warps;
@@ -581,8 +608,8 @@ __global__ void __launch_bounds__(WNT) rollout_segments_kernel_warp(SceneArgs sc
                 __syncwarp();
             }
         }
+        int last = -1;                                     // last step this warp executed
         for (int t = 0; t < seg_len; ++t) {
-            bool any_alive = false;
 #pragma unroll
             for (int sl = 0; sl < SEG_SLOTS; ++sl) {
                 const int b = gw + sl * total_warps;
@@ -606,8 +633,12 @@ __global__ void __launch_bounds__(WNT) rollout_segments_kernel_warp(SceneArgs sc
                     if (refresh) collide_state_warp<RB, true, false>(qn, sv, base_min, cr);
                     else collide_state_warp<RB, false, false>(qn, sv, base_min, cr);
                     float* tr = traj + ((long long)b * steps + (long long)sg * seg_len) * N;
-                    __syncwarp();                          // earlier trajectory rows / row state: visible, reads done
-                    rollout_after_step<N>(ra, t, cr.hard_min <= thr_hard, q, qn, tr, ok[sl], dead[sl], done[sl]);   // mode 1, keep_going
+                    const bool was_dead = dead[sl];
+                    __syncwarp();                          // earlier stored states / row state: visible, reads done
+                    if (use_ring)                          // mode 1, keep_going
+                        rollout_after_step_ring<N>(ra, t, cr.hard_min <= thr_hard, q, qn, tr, rings + sl * STUCK_RING * N, ok[sl], dead[sl], done[sl]);
+                    else
+                        rollout_after_step<N>(ra, t, cr.hard_min <= thr_hard, q, qn, tr, ok[sl], dead[sl], done[sl]);
                     if (lane == 0) {
 #pragma unroll
                         for (int k = 0; k < N; ++k) { st[RS::Q + k] = q[k]; st[RS::U + k] = u[k]; }
@@ -616,35 +647,56 @@ __global__ void __launch_bounds__(WNT) rollout_segments_kernel_warp(SceneArgs sc
 #pragma unroll
                             for (int k = 0; k < N; ++k) st[RS::DODQ + k] = cr.dodq[k];
                         }
+                        if (dead[sl]) {                    // running state after step t of a dead row (roll-back target)
+#pragma unroll
+                            for (int k = 0; k < N; ++k) hist[(sl * seg_len + t) * N + k] = q[k];
+                        }
                     }
+                    if (dead[sl] && !was_dead && lane < n_cta) *cluster.map_shared_rank(dv + b, lane) = t;   // died at step t
                     __syncwarp();
-                    any_alive = any_alive || !dead[sl];
                 }
             }
-            // batch_tsa.py:229-230 over the whole cluster
-            const int cta_alive = __syncthreads_or(any_alive);
-            if (n_cta > 1) {
-                if (threadIdx.x < n_cta) *cluster.map_shared_rank(flags + phase * SEG_MAX_CLUSTER + rank, threadIdx.x) = cta_alive;
-                cluster.sync();
-                int any = 0;
-                for (int c = 0; c < n_cta; ++c) any |= flags[phase * SEG_MAX_CLUSTER + c];
-                phase ^= 1;
-                if (!any) break;
-            } else if (!cta_alive) break;
+            last = t;
+            // every row has a death step?  then t* = the largest is the reference's exit step (batch_tsa.py:229-230)
+            int mx = -1;
+            bool fin = true;
+            for (int r = lane; r < T; r += 32) {
+                const int d = *reinterpret_cast<volatile int*>(dv + r);
+                fin = fin && d != SEG_ALIVE;
+                mx = max(mx, d);
+            }
+            fin = __all_sync(FULL, fin);
+            mx = __reduce_max_sync(FULL, mx);
+            if (fin && t >= mx) break;
         }
+        for (int i = threadIdx.x; i < SEG_MAX_ROWS; i += WNT) death[((sg + 1) & 1) * SEG_MAX_ROWS + i] = SEG_ALIVE;
+        cluster.sync();                                    // every death step of this segment is published
+        int t_exit = -1;
+        bool all_dead = true;
+        for (int r = lane; r < T; r += 32) {
+            const int d = dv[r];
+            all_dead = all_dead && d != SEG_ALIVE;
+            t_exit = max(t_exit, d);
+        }
+        all_dead = __all_sync(FULL, all_dead);
+        t_exit = __reduce_max_sync(FULL, t_exit);
 #pragma unroll
         for (int sl = 0; sl < SEG_SLOTS; ++sl) {
             const int b = gw + sl * total_warps;
             if (b < T && lane == 0) {
-                const float* st = rows + sl * RS::TOTAL;
+                float* st = rows + sl * RS::TOTAL;
+                if (all_dead && t_exit < last) {           // ran past the exit step: the state after step t_exit
+#pragma unroll
+                    for (int k = 0; k < N; ++k) st[RS::Q + k] = hist[(sl * seg_len + t_exit) * N + k];
+                }
 #pragma unroll
                 for (int k = 0; k < N; ++k) seg_q[((long long)b * n_seg + sg) * N + k] = st[RS::Q + k];
                 seg_alive[(long long)b * n_seg + sg] = ok[sl];
                 seg_done[(long long)b * n_seg + sg] = done[sl];
             }
         }
+        __syncwarp();
     }
-    cluster.sync();                                        // no CTA leaves while its shared memory can still be a target
 }
 
 }  // namespace wp
