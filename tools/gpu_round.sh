@@ -14,6 +14,8 @@ python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1;
 python tools/measure_configs.py --iters 5 --cpu > $OUT/${TAG}_configs.jsonl 2>> $OUT/${TAG}_bench.err
 CBFRRT_GRID_MIN=12 python tools/measure_configs.py --iters 5 --only cfg1,cfg3 > $OUT/${TAG}_configs_gridmin12.jsonl 2>> $OUT/${TAG}_bench.err
 python tools/measure_frontend.py > $OUT/${TAG}_frontend.jsonl 2>> $OUT/${TAG}_bench.err
+python tools/measure_planner_sized.py > $OUT/${TAG}_planner_sized.jsonl 2>> $OUT/${TAG}_bench.err
+python tools/eval_planning.py > $OUT/${TAG}_planning.jsonl 2>> $OUT/${TAG}_bench.err
 python tools/measure_lidar.py --states 256 > $OUT/${TAG}_lidar.jsonl 2>> $OUT/${TAG}_bench.err
 python tools/measure_lidar.py --states 2048 --rays 64 --cloud 512 >> $OUT/${TAG}_lidar.jsonl 2>> $OUT/${TAG}_bench.err
 B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-other-configs --scale 0.125"
