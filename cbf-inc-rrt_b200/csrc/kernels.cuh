@@ -1398,6 +1398,23 @@ struct CfgKey {
 extern std::mutex g_cfg_mu;
 extern std::map<CfgKey, int> g_cfg;
 
+// Opt-in to more than 48 KB of dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is ONE value per
+// (device, kernel): it is only ever raised -- a launch with a small scene after a launch with a large one must not lower
+// it under the size a cached configuration still relies on.  Call with g_cfg_mu held.
+template <class Kern>
+static bool smem_optin(Kern kern, size_t smem) {
+    if (smem <= 48 * 1024) return true;
+    const CfgKey key{current_device(), reinterpret_cast<const void*>(kern), ~size_t(0)};
+    auto it = g_cfg.find(key);
+    if (it != g_cfg.end() && (size_t)it->second >= smem) return true;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    g_cfg[key] = (int)smem;
+    return true;
+}
+
 template <class Kern>
 static int grid_for(Kern kern, size_t smem, long long tiles, int threads = NT) {
     int per_sm = 0;
@@ -1407,9 +1424,11 @@ static int grid_for(Kern kern, size_t smem, long long tiles, int threads = NT) {
         auto it = g_cfg.find(key);
         if (it != g_cfg.end()) per_sm = it->second;
         else {
-            if (smem > 48 * 1024 &&
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) return -1;
+            if (!smem_optin(kern, smem)) return -1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                return -1;
+            }
             g_cfg[key] = per_sm;
         }
     }
@@ -1427,12 +1446,7 @@ template <class Kern>
 static int grid_for_tc(Kern kern, size_t smem, long long rows, int groups) {
     {
         std::lock_guard<std::mutex> lock(g_cfg_mu);
-        const CfgKey key{current_device(), reinterpret_cast<const void*>(kern), smem};
-        if (g_cfg.find(key) == g_cfg.end()) {
-            if (smem > 48 * 1024 &&
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            g_cfg[key] = 1;
-        }
+        if (!smem_optin(kern, smem)) return -1;
     }
     const long long tiles = (rows + tc::M_TILE - 1) / tc::M_TILE;
     long long g = (tiles + groups - 1) / groups;
@@ -1588,12 +1602,7 @@ static int launch_filter_generic(const NetArgs& net, int H, int L, const float* 
     auto k = filter_kernel_generic<N>;
     {
         std::lock_guard<std::mutex> lock(g_cfg_mu);
-        const CfgKey key{current_device(), reinterpret_cast<const void*>(k), smem};
-        if (g_cfg.find(key) == g_cfg.end()) {
-            if (smem > 48 * 1024 &&
-                cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return CBFRRT_ERR_CUDA;
-            g_cfg[key] = 1;
-        }
+        if (!smem_optin(k, smem)) return CBFRRT_ERR_CUDA;
     }
     const long long tiles = (B + GEN_NT - 1) / GEN_NT;
     const long long cap = (long long)num_sms() * 16;

@@ -344,3 +344,29 @@ def test_planner_host_front_ends_equal_device_api(coracle, robot, T):
         assert np.array_equal(hi, di.cpu().numpy()) and np.array_equal(hd_, dd.cpu().numpy())
         oi, od = coracle.knn(qs, tree, k)
         assert np.array_equal(hi, oi) and np.array_equal(hd_, od)
+
+
+@pytest.mark.parametrize("path", ["warp", "fma", "tc"])
+def test_scene_size_sequence_large_small_large(coracle, path):
+    """the per-kernel opt-in to > 48 KB of dynamic shared memory is only ever raised: a large scene, then a small one, then
+    the large one again through the same kernel (regression: the cached configuration of the large scene used to meet an
+    attribute lowered by the small one -> cudaErrorInvalidValue)"""
+    from cbfrrt import ops, workloads as W
+    w = _workload("panda")
+    big = (W.random_boxes(300, 3, 0.01, 0.04), W.random_spheres(200, 5, 0.01, 0.04))
+    small = (W.random_boxes(2, 2, 0.05, 0.12), None)
+    q = W.sample_states("panda", 300, 3)
+    goal = W.sample_states("panda", 300, 4)
+    ops.set_mlp_path(path)
+    for boxes, sph in (big, small, big, small):
+        b8, s4, gr = _scene(boxes, sph)
+        args = (_t(q), _t(goal), b8, s4, 1, gr, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"],
+                w["thr_soft"], w["thr_hard"], 0, 48, 2)
+        safe, unsafe, datax, h, J, u, r = ops.safety_filter(*args)
+        o = coracle.collide("panda", q, boxes, sph, True, w["thr_soft"], w["thr_hard"])
+        assert np.array_equal(safe.cpu().numpy(), o["safe"]) and np.array_equal(datax.cpu().numpy()[:, 7], o["datax"][:, 7])
+        qf, alive, done, traj = ops.rollout(_t(q[:40]), _t(goal[:40]), 12, 4, 1 / 120, 0, 10, 0.1, False, False, b8, s4, 1, gr, _net(w),
+                                            _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], 0, 48, 2)
+        s2, u2 = ops.masks(_t(q), b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], 0)
+        assert torch.equal(s2, safe)
+        torch.cuda.synchronize()
