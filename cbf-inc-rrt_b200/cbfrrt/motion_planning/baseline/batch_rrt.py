@@ -159,10 +159,12 @@ def global_explore(search_tree, dynamics_model, sample_states=None, steer_type="
     parents = list(first_parents)
     new_states, no_collisions = current, [True] * len(parents)
     n_seg = RRT_PARAM // 20
-    fused = steer_type == "cbf" and n_seg >= 1 and len(parents) <= MAX_FUSED_BATCH
+    if steer_type not in ("line", "cbf"):
+        raise ValueError("Unknown steer_type, must be one of {'line', 'cbf'}.")
+    fused = n_seg >= 1 and len(parents) <= MAX_FUSED_BATCH
     if fused:   # all segments of the expansion in one launch and one read-back (cbfrrt_rollout_segments)
-        assert hasattr(controller, "u")
-        segments = steer_segments_fused(controller, dm, sample_states, current, n_seg, RRT_step=20)
+        assert steer_type == "line" or hasattr(controller, "u")
+        segments = steer_segments_fused(controller, dm, sample_states, current, n_seg, RRT_step=20, nominal=steer_type == "line")
     if fused:   # one goal test for the new states of all segments (same float32 torch expression, one call instead of n_seg)
         done_all = _goal_test(dm, np.concatenate([seg[0] for seg in segments])).reshape(n_seg, -1)
     for k in range(n_seg):

@@ -22,6 +22,15 @@ def _gain_host(dm):
     return dm._K_np
 
 
+_ZERO_NETS = {}
+
+
+def _zero_net(n):
+    if n not in _ZERO_NETS:
+        _ZERO_NETS[n] = np.zeros(ops.packed_weight_count(n, 48, 2), np.float32)
+    return _ZERO_NETS[n]
+
+
 def _dev_index(device):
     d = torch.device(device)
     if d.type != "cuda":
@@ -134,12 +143,15 @@ def steer_fused_reference(controller, dynamics_model, sample_states, nearests, R
 
 
 @torch.no_grad()
-def steer_segments_fused(controller, dynamics_model, sample_states, nearests, n_segments, RRT_step=20):
+def steer_segments_fused(controller, dynamics_model, sample_states, nearests, n_segments, RRT_step=20, nominal=False):
     """The segment loop of global_explore (batch_tsa.py:154-170: ``RRT_PARAM // 20`` batched steer calls, each starting
     where the previous one ended) in ONE launch and ONE read-back (cbfrrt_rollout_segments), with the reference's
     semantics per segment (batch_tsa.py:191-231, incl. the batch-wide early exit once every row is dead).
     -> list over segments of (x_last (B,n) numpy, no_collisions [bool]*B, xs_list), exactly what ``n_segments``
-    consecutive ``steer(controller.u, ...)`` calls return.  B <= MAX_FUSED_BATCH."""
+    consecutive ``steer(controller.u, ...)`` calls return.  B <= MAX_FUSED_BATCH.
+    ``nominal``: the 'line' steer of the vanilla planners, ``steer(dynamics_model.u_nominal, ...)`` (batch_tsa.py:158): the
+    same kernel with relaxation penalty 0 -- the QP's multiplier is confined to [0, penalty], so u is exactly the clamped
+    LQR control u_nominal (arm_dynamics.py:124-161) and the network is never consulted (a zero network is passed)."""
     dm = dynamics_model
     goals = np.asarray(sample_states, dtype=np.float32).reshape(-1, dm.q_dims)
     dm.set_intermediate_goals(np.asarray(sample_states))
@@ -147,14 +159,19 @@ def steer_segments_fused(controller, dynamics_model, sample_states, nearests, n_
     if goals.shape[0] == 1 and q0.shape[0] > 1:
         goals = np.repeat(goals, q0.shape[0], 0)
     env = dm.env
-    lo, hi = controller._limits_host()
+    if nominal:
+        upper, lower = dm.control_limits
+        lo, hi = lower.detach().cpu().numpy().astype(np.float32), upper.detach().cpu().numpy().astype(np.float32)
+        weights, hidden, layers, lam, penalty = _zero_net(dm.q_dims), 48, 2, 0.0, 0.0
+    else:
+        lo, hi = controller._limits_host()
+        weights, hidden, layers = controller._weights_host(), controller.h_hidden_size, controller.h_hidden_layers
+        lam, penalty = float(controller.clf_lambda), float(controller.clf_relaxation_penalty)
     # numpy in / numpy out (cbfrrt_rollout_segments_host): one pinned H2D copy, the launch, one D2H copy
     seg_q, seg_alive, seg_done, traj = ops.rollout_segments_host(
         dm.robot.name, q0, goals, int(n_segments), int(RRT_step), int(dm.controller_dt // dm.dt), float(dm.dt), 9, 10, 3e-2,
-        np.concatenate([env.obs_positions, env.obs_sizes], 1), env.obs_spheres, bool(env.include_floor), controller._weights_host(),
-        controller.h_hidden_size, controller.h_hidden_layers, _gain_host(dm), lo, hi, float(controller.clf_lambda),
-        float(controller.clf_relaxation_penalty), float(dm.dis_threshold), float(dm.thr_hard),
-        device=_dev_index(dm.device))
+        np.concatenate([env.obs_positions, env.obs_sizes], 1), env.obs_spheres, bool(env.include_floor), weights, hidden, layers,
+        _gain_host(dm), lo, hi, lam, penalty, float(dm.dis_threshold), float(dm.thr_hard), device=_dev_index(dm.device))
     out = []
     for k in range(int(n_segments)):
         xs = [[row for row in traj[i, k * RRT_step:k * RRT_step + seg_done[i, k]]] for i in range(traj.shape[0])]

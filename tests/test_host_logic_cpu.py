@@ -250,6 +250,33 @@ def test_fused_segments_equal_consecutive_batched_steers(stack):
     assert n_dead > 0 and n_early > 0, (n_dead, n_early)
 
 
+def test_fused_line_steer_equals_nominal_host_loop(stack):
+    """the vanilla planners' 'line' steer (steer(dynamics_model.u_nominal, ...), batch_tsa.py:158) through the same fused
+    kernel with relaxation penalty 0: nodes, flags and stored states of the per-step host loop"""
+    env, robot, dyn, ctrl = stack("panda")
+    from cbfrrt.motion_planning.baseline import batch_steer, steer_segments_fused
+    x = dyn.sample_state_space(400)
+    xs = x[dyn.safe_mask(x)].numpy()[:, :7]
+    fold = np.array([[0., 1.7, 0., -0.1, 0., 3.7, 0.]], np.float32)
+    n_dead = 0
+    for starts, targets in ((xs[:5], xs[5:10]), (xs[10:11], fold), (xs[20:21], xs[20:21] + 0.02), (xs[30:36], xs[36:42])):
+        n_seg = 3
+        segs = steer_segments_fused(None, dyn, targets, starts, n_seg, RRT_step=20, nominal=True)
+        cur = starts
+        for k in range(n_seg):
+            xb, oks, _, lists = batch_steer(dyn.u_nominal, dyn, targets, cur, RRT_step=20, device="cpu")
+            xf, okf, lf = segs[k]
+            assert list(oks) == list(okf), (k, oks, okf)
+            assert [len(a) for a in lists] == [len(b) for b in lf]
+            assert np.abs(xb - xf).max() < 1e-5
+            for a, b in zip(lists, lf):
+                if len(a):
+                    assert np.abs(np.asarray(a)[:, :7] - np.asarray(b)).max() < 1e-5
+            n_dead += sum(not o for o in oks)
+            cur = xb
+    assert n_dead > 0
+
+
 def test_edge_checking_reference_loop_equals_batched(stack):
     env, robot, dyn, ctrl = stack("panda")
     from cbfrrt.motion_planning.baseline import (edge_checking, edge_checking_batch, edge_checking_eps,
