@@ -92,6 +92,7 @@ SIGNATURES = {
     "cbfrrt_rollout_segments_host": (C.c_int, [_I, _I, C.POINTER(HostScene), C.c_int32, C.c_int32, _P, _L, _P, _L, _P, _P, _P, _P,
                                                _F, _F, C.POINTER(RolloutParams), C.c_int32, _F, _F, _P, _P, _P, _P]),
     "cbfrrt_knn_host": (C.c_int, [_I, _I, _P, _P, _L, _L, C.c_int32, _P, _P]),
+    "cbfrrt_edge_validity_host": (C.c_int, [_I, _I, C.POINTER(HostScene), _P, _P, _L, _P, _F, _F, _P, _P]),
 }
 
 if not os.path.exists(LIB_PATH):

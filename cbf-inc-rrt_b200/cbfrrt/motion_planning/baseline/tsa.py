@@ -109,15 +109,16 @@ def edge_checking_eps(states, new_states, dynamics_model, eps):
     """E edges, each with its own K_e = int(|new - old| / eps) (tsa.py:277-279, computed in float64 on the host like
     the reference), in one launch (cbfrrt::edge_validity_var) -> (valid bool[E], first_bad i32[E])."""
     dm = dynamics_model
-    b, s, fl, gr = dm.env.scene
+    env = dm.env
     a64 = np.asarray(states, dtype=np.float64).reshape(-1, dm.q_dims)
     b64 = np.asarray(new_states, dtype=np.float64).reshape(-1, dm.q_dims)
     K = (np.linalg.norm(a64 - b64, axis=1) / eps).astype(np.int64)
-    qf = torch.as_tensor(a64, dtype=torch.float32).to(dm.device)
-    qt = torch.as_tensor(b64, dtype=torch.float32).to(dm.device)
-    valid, first_bad = ops.edge_validity_var(qf, qt, torch.from_numpy(K), b, s, fl, gr, float(dm.dis_threshold),
-                                             float(dm.thr_hard), dm.robot.robot_id)
-    return valid.bool(), first_bad
+    # planners check a handful of edges per call: numpy in / numpy out (cbfrrt_edge_validity_host), one copy each way
+    d = torch.device(dm.device)
+    valid, first_bad = ops.edge_validity_host(dm.robot.name, a64, b64, K, np.concatenate([env.obs_positions, env.obs_sizes], 1),
+                                              env.obs_spheres, bool(env.include_floor), float(dm.dis_threshold), float(dm.thr_hard),
+                                              device=(d.index if d.type == "cuda" and d.index is not None else 0))
+    return torch.from_numpy(valid), torch.from_numpy(first_bad)
 
 
 def edge_checking_batch(states, new_states, dynamics_model, n_interp):

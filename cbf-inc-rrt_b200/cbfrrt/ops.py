@@ -670,6 +670,26 @@ def rollout_segments_host(robot: str, q0: np.ndarray, goal: np.ndarray, n_segmen
     return seg_q, seg_alive.astype(bool), seg_done, traj
 
 
+def edge_validity_host(robot: str, q_from: np.ndarray, q_to: np.ndarray, n_interp: np.ndarray, boxes6: np.ndarray, spheres,
+                       floor: bool, thr_soft: float, thr_hard: float, device: int = 0):
+    """numpy in / numpy out form of edge_validity_var (include/cbfrrt.h cbfrrt_edge_validity_host)
+    -> valid bool[E], first_bad i32[E]"""
+    n = ROBOT_N[ROBOT_ID[robot]]
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    q_from, q_to = f(q_from).reshape(-1, n), f(q_to).reshape(-1, n)
+    K = np.ascontiguousarray(n_interp, dtype=np.int32).reshape(-1)
+    E = q_from.shape[0]
+    if q_to.shape[0] != E or K.shape[0] != E:
+        raise ValueError("q_from, q_to and n_interp must describe the same number of edges")
+    boxes6 = f(boxes6).reshape(-1, 6)
+    spheres = f(spheres).reshape(-1, 4) if spheres is not None else np.zeros((0, 4), np.float32)
+    hs = _lib.HostScene(boxes6.shape[0], spheres.shape[0], int(bool(floor)), 0, boxes6.ctypes.data, spheres.ctypes.data)
+    valid, first_bad = np.empty(E, np.uint8), np.empty(E, np.int32)
+    check(lib.cbfrrt_edge_validity_host(device, ROBOT_ID[robot], C.byref(hs), q_from.ctypes.data, q_to.ctypes.data, E, K.ctypes.data,
+                                        thr_soft, thr_hard, valid.ctypes.data, first_bad.ctypes.data), "cbfrrt_edge_validity_host")
+    return valid.astype(bool), first_bad
+
+
 def knn_host(queries: np.ndarray, tree: np.ndarray, k: int, device: int = 0):
     """numpy in / numpy out form of knn (include/cbfrrt.h cbfrrt_knn_host) -> idx i32[M,k], dist f32[M,k]"""
     queries, tree = np.ascontiguousarray(queries, np.float32), np.ascontiguousarray(tree, np.float32)

@@ -31,7 +31,8 @@ struct Ctx {
     float *boxes = nullptr, *spheres = nullptr, *weights = nullptr, *small = nullptr;  // small: goal(1 row) K lo hi
     void* grid = nullptr;
     int64_t cap_boxes = 0, cap_spheres = 0, cap_weights = 0;
-    std::vector<unsigned char> resident;   // host image of what boxes/spheres/weights/small/grid currently hold
+    std::vector<unsigned char> resident;       // host image of what boxes / spheres (and the grid built from them) hold
+    std::vector<unsigned char> resident_net;   // ... of what weights / small hold
     bool resident_grid = false;
     // planner-sized calls (cbfrrt_rollout_segments_host, cbfrrt_knn_host): one pinned block and its device twin, so that a
     // call is one H2D copy, the kernels and one D2H copy on lane 0
@@ -74,7 +75,8 @@ int ensure(Ctx& c, int device, int64_t rows, int n, int64_t n_boxes, int64_t n_s
         }
         c.cap_rows = rows;
     }
-    if (n_boxes > c.cap_boxes || n_spheres > c.cap_spheres || n_weights > c.cap_weights) c.resident.clear();
+    if (n_boxes > c.cap_boxes || n_spheres > c.cap_spheres) c.resident.clear();
+    if (n_weights > c.cap_weights) c.resident_net.clear();
     if (n_boxes > c.cap_boxes) { c.cap_boxes = 0; if (grow(c.boxes, n_boxes * 32)) return CBFRRT_ERR_CUDA; c.cap_boxes = n_boxes; }
     if (n_spheres > c.cap_spheres) { c.cap_spheres = 0; if (grow(c.spheres, n_spheres * 16)) return CBFRRT_ERR_CUDA; c.cap_spheres = n_spheres; }
     if (n_weights > c.cap_weights) { c.cap_weights = 0; if (grow(c.weights, n_weights * 4)) return CBFRRT_ERR_CUDA; c.cap_weights = n_weights; }
@@ -88,47 +90,67 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// Scene / weights / small parameters: tiny (<= 60 KB).  They are uploaded on lane 0 only when they differ from what the
-// device already holds (planners call with the same scene and network thousands of times), the broad phase is rebuilt
-// with them; returns after the upload is complete, so every lane may read them.  dsc: the device view of the scene.
-int make_resident(Ctx& c, int n, const cbfrrt_host_scene* scene, const float* weights, int64_t n_weights, const float* goal1,
-                  const float* K, const float* u_lo, const float* u_hi, bool use_grid, cbfrrt_scene& dsc) {
+// Scene and network constants are tiny (<= 60 KB).  Each of the two groups is uploaded on lane 0 only when its bytes
+// differ from what the device already holds (planners call with the same scene and network thousands of times, and
+// alternate between entry points that need only one of the groups); the broad phase is rebuilt with the scene.  Both
+// return after the upload is complete, so every lane may read the buffers.  dsc: the device view of the scene.
+int make_resident_scene(Ctx& c, const cbfrrt_host_scene* scene, bool use_grid, cbfrrt_scene& dsc) {
     cudaStream_t s0 = c.lane[0].st;
     std::vector<float> b8((size_t)scene->n_boxes * 8, 0.f);
     for (int i = 0; i < scene->n_boxes; ++i) memcpy(&b8[8 * i], scene->boxes + 6 * i, 24);
-    float small[8 + 64 + 8 + 8] = {0};
-    if (goal1) memcpy(small, goal1, 4 * n);
-    memcpy(small + 8, K, 4 * n * n);
-    memcpy(small + 72, u_lo, 4 * n);
-    memcpy(small + 80, u_hi, 4 * n);
-    std::vector<unsigned char> image(16 + b8.size() * 4 + (size_t)scene->n_spheres * 16 + (size_t)n_weights * 4 + sizeof small);
+    std::vector<unsigned char> image(16 + b8.size() * 4 + (size_t)scene->n_spheres * 16);
     {
         unsigned char* w = image.data();
-        const int32_t hdr[4] = {scene->n_boxes, scene->n_spheres, (int32_t)n_weights, scene->floor};
+        const int32_t hdr[4] = {scene->n_boxes, scene->n_spheres, scene->floor, 0};
         memcpy(w, hdr, 16); w += 16;
         memcpy(w, b8.data(), b8.size() * 4); w += b8.size() * 4;
         if (scene->n_spheres) memcpy(w, scene->spheres, (size_t)scene->n_spheres * 16);
-        w += (size_t)scene->n_spheres * 16;
-        memcpy(w, weights, (size_t)n_weights * 4); w += (size_t)n_weights * 4;
-        memcpy(w, small, sizeof small);
     }
     dsc = cbfrrt_scene{scene->n_boxes, scene->n_spheres, scene->floor, 0, c.boxes, c.spheres, nullptr, nullptr};
     if (image != c.resident || (use_grid && !c.resident_grid)) {
         c.resident.clear();
+        c.resident_grid = false;
         if (scene->n_boxes) CK(cudaMemcpyAsync(c.boxes, b8.data(), b8.size() * 4, cudaMemcpyHostToDevice, s0));
         if (scene->n_spheres) CK(cudaMemcpyAsync(c.spheres, scene->spheres, (size_t)scene->n_spheres * 16, cudaMemcpyHostToDevice, s0));
-        CK(cudaMemcpyAsync(c.weights, weights, n_weights * 4, cudaMemcpyHostToDevice, s0));
-        CK(cudaMemcpyAsync(c.small, small, sizeof small, cudaMemcpyHostToDevice, s0));
         if (use_grid) {
             const int rc = cbfrrt_grid_build(&dsc, c.grid, s0);
             if (rc) return rc;
         }
-        CK(cudaStreamSynchronize(s0));  // b8/small live on this stack frame; lanes 1.. may now read scene + grid
+        CK(cudaStreamSynchronize(s0));  // b8 lives on this stack frame; lanes 1.. may now read scene + grid
         c.resident.swap(image);
         c.resident_grid = use_grid;
     }
     if (use_grid) dsc.grid = c.grid;
     return CBFRRT_OK;
+}
+
+int make_resident_net(Ctx& c, int n, const float* weights, int64_t n_weights, const float* goal1, const float* K,
+                      const float* u_lo, const float* u_hi) {
+    if (n_weights < 0 || n_weights > (1 << 24) || n < 1 || n > 8) return CBFRRT_ERR_BAD_SHAPE;
+    cudaStream_t s0 = c.lane[0].st;
+    float small[8 + 64 + 8 + 8] = {0};
+    if (goal1) memcpy(small, goal1, 4 * n);
+    memcpy(small + 8, K, 4 * n * n);
+    memcpy(small + 72, u_lo, 4 * n);
+    memcpy(small + 80, u_hi, 4 * n);
+    const size_t wb = (size_t)n_weights * 4;
+    std::vector<unsigned char> image(wb + sizeof small);
+    memcpy(image.data(), weights, wb);
+    memcpy(&image[wb], small, sizeof small);
+    if (image != c.resident_net) {
+        c.resident_net.clear();
+        CK(cudaMemcpyAsync(c.weights, weights, n_weights * 4, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(c.small, small, sizeof small, cudaMemcpyHostToDevice, s0));
+        CK(cudaStreamSynchronize(s0));  // small lives on this stack frame
+        c.resident_net.swap(image);
+    }
+    return CBFRRT_OK;
+}
+
+int make_resident(Ctx& c, int n, const cbfrrt_host_scene* scene, const float* weights, int64_t n_weights, const float* goal1,
+                  const float* K, const float* u_lo, const float* u_hi, bool use_grid, cbfrrt_scene& dsc) {
+    const int rc = make_resident_scene(c, scene, use_grid, dsc);
+    return rc ? rc : make_resident_net(c, n, weights, n_weights, goal1, K, u_lo, u_hi);
 }
 
 // pinned block + device twin of at least `bytes`
@@ -329,5 +351,53 @@ extern "C" int cbfrrt_knn_host(int device, int n, const float* queries, const fl
     CK(cudaStreamSynchronize(st));
     memcpy(idx, c.pin + o_idx, out_b);
     memcpy(dist, c.pin + o_dist, out_b);
+    return CBFRRT_OK;
+}
+
+extern "C" int cbfrrt_edge_validity_host(int device, int robot, const cbfrrt_host_scene* scene, const float* q_from,
+                                         const float* q_to, int64_t E, const int32_t* n_interp, float thr_soft, float thr_hard,
+                                         uint8_t* valid, int32_t* first_bad) {
+    int32_t n = 0, nl = 0, ns = 0;
+    int rc = cbfrrt_robot_info(robot, &n, &nl, &ns);
+    if (rc) return rc;
+    if (device < 0 || device >= 16 || E < 1 || !scene || !q_from || !q_to || !n_interp || !valid || !first_bad)
+        return CBFRRT_ERR_BAD_SHAPE;
+    if (scene->n_boxes < 0 || scene->n_spheres < 0 || (scene->n_boxes && !scene->boxes) || (scene->n_spheres && !scene->spheres))
+        return CBFRRT_ERR_BAD_SHAPE;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device >= n_dev) return CBFRRT_ERR_BAD_SHAPE;
+    DeviceGuard guard(device);
+    Ctx& c = g_ctx[device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    rc = ensure(c, device, 0, n, scene->n_boxes, scene->n_spheres, 0);
+    if (rc) return rc;
+    // block: in [offsets int64 (E + 1) | q_from | q_to], out [first_bad int32 E | valid u8 E]
+    const size_t off_b = ((size_t)(E + 1) * 8 + 15) & ~size_t(15), rows_b = (size_t)E * n * 4;
+    const size_t o_fb = (off_b + 2 * rows_b + 15) & ~size_t(15), o_v = (o_fb + (size_t)E * 4 + 15) & ~size_t(15), total = o_v + (size_t)E;
+    rc = ensure_block(c, total);
+    if (rc) return rc;
+    int64_t* off = reinterpret_cast<int64_t*>(c.pin);
+    off[0] = 0;
+    for (int64_t e = 0; e < E; ++e) {
+        if (n_interp[e] < 0) return CBFRRT_ERR_BAD_SHAPE;
+        off[e + 1] = off[e] + n_interp[e] + 1;
+    }
+    const int64_t n_points = off[E];
+    const int n_obs = scene->n_boxes + scene->n_spheres;
+    cbfrrt_scene dsc;
+    rc = make_resident_scene(c, scene, (n_obs >= 40 && n_points > 4096) || (c.resident_grid && n_obs >= 1), dsc);
+    if (rc) return rc;
+    cudaStream_t st = c.lane[0].st;
+    memcpy(c.pin + off_b, q_from, rows_b);
+    memcpy(c.pin + off_b + rows_b, q_to, rows_b);
+    CK(cudaMemcpyAsync(c.dblk, c.pin, off_b + 2 * rows_b, cudaMemcpyHostToDevice, st));
+    rc = cbfrrt_edge_validity_var(robot, &dsc, reinterpret_cast<float*>(c.dblk + off_b), reinterpret_cast<float*>(c.dblk + off_b + rows_b),
+                                  E, reinterpret_cast<int64_t*>(c.dblk), n_points, thr_soft, thr_hard, c.dblk + o_v,
+                                  reinterpret_cast<int32_t*>(c.dblk + o_fb), st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CK(cudaMemcpyAsync(c.pin + o_fb, c.dblk + o_fb, total - o_fb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(first_bad, c.pin + o_fb, (size_t)E * 4);
+    memcpy(valid, c.pin + o_v, (size_t)E);
     return CBFRRT_OK;
 }

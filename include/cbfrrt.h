@@ -377,6 +377,11 @@ int cbfrrt_rollout_segments_host(int device, int robot, const cbfrrt_host_scene 
                                  float *traj);
 int cbfrrt_knn_host(int device, int n, const float *queries, const float *tree, int64_t M, int64_t N_tree, int32_t k,
                     int32_t *idx, float *dist);
+/* edge_checking (motion_planning/baseline/tsa.py:272-286; BIT* is_edge_free, bit_star.py:126-129) for numpy callers:
+ * n_interp [E] = the K_e of every edge (host, >= 0); same results as cbfrrt_edge_validity_var */
+int cbfrrt_edge_validity_host(int device, int robot, const cbfrrt_host_scene *scene, const float *q_from, const float *q_to,
+                              int64_t E, const int32_t *n_interp, float thr_soft, float thr_hard, uint8_t *valid,
+                              int32_t *first_bad);
 
 /* ---- measurement utility: FP32 FMA throughput probe (the roofline denominator of this path is the CUDA-core
  * FMA rate, which MEASURED_PEAKS.json does not contain).  Launches grid x block threads, each running

@@ -108,6 +108,12 @@ def install(monkeypatch):
                                                    stuck_lag=stuck_lag, stuck_after=stuck_after, stuck_eps=stuck_eps)
         return sq, sa.astype(bool), sd, tr
 
+    def edge_validity_host(robot, q_from, q_to, n_interp, boxes6, spheres, floor, thr_soft, thr_hard, device=0):
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        v, fb = c_oracle.edge_validity_var(robot, f(q_from), f(q_to), np.asarray(n_interp, np.int32), f(boxes6).reshape(-1, 6),
+                                           None if spheres is None or len(spheres) == 0 else f(spheres), bool(floor), thr_soft, thr_hard)
+        return v.astype(bool), fb
+
     def knn_host(queries, tree, k, device=0):
         return c_oracle.knn(np.ascontiguousarray(queries, np.float32), np.ascontiguousarray(tree, np.float32), k)
 
@@ -120,5 +126,5 @@ def install(monkeypatch):
 
     for name, fn in dict(fk=fk, collide=collide, observe=observe, masks=masks, cbf_filter=cbf_filter, qp=qp, qp_backward=qp_backward, qp_multi=qp_multi, qp_multi_backward=qp_multi_backward,
                          edge_validity=edge_validity, edge_validity_var=edge_validity_var, knn=knn, radius_mask=radius_mask, rollout=rollout, rollout_segments=rollout_segments, rollout_segments_host=rollout_segments_host,
-                         knn_host=knn_host, valid_control=valid_control).items():
+                         knn_host=knn_host, edge_validity_host=edge_validity_host, valid_control=valid_control).items():
         monkeypatch.setattr(ops, name, fn)

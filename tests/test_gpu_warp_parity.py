@@ -335,6 +335,22 @@ def test_planner_host_front_ends_equal_device_api(coracle, robot, T):
     with pytest.raises(CbfrrtError):
         ops.rollout_segments_host(robot, np.repeat(q0[:1], 129, 0), np.repeat(goal[:1], 129, 0), 2, 20, 4, 1 / 120, 9, 10, 3e-2, boxes, sph,
                                   True, w["weights"], 48, 2, w["K"], w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"])
+    # edge checks between the steer calls, as the planners interleave them (scene and network residency are independent)
+    E = max(T, 3)
+    qf, qt = W.sample_states(robot, E, 5), W.sample_states(robot, E, 6)
+    qt = qf + 0.3 * (qt - qf)
+    K = (np.linalg.norm(qf.astype(np.float64) - qt, axis=1) / 0.03).astype(np.int32)
+    K[0] = 0
+    for boxes_e, sph_e in ((boxes, sph), (W.scene(3)[0], None), (boxes, sph)):
+        hv, hf = ops.edge_validity_host(robot, qf, qt, K, boxes_e, sph_e, True, 0.02, 0.0)
+        b8e, s4e, gre = _scene(boxes_e, sph_e)
+        dv, df = ops.edge_validity_var(_t(qf), _t(qt), torch.from_numpy(K), b8e, s4e, 1, gre, 0.02, 0.0, rid)
+        assert np.array_equal(hv, dv.cpu().numpy().astype(bool)) and np.array_equal(hf, df.cpu().numpy())
+        vo, fo = coracle.edge_validity_var(robot, qf, qt, K, boxes_e, sph_e, True, 0.02, 0.0)
+        assert np.array_equal(hv, vo.astype(bool)) and np.array_equal(hf, fo)
+        hq2, ha2, hd2, _ = ops.rollout_segments_host(robot, q0, goal, 9, 20, 4, 1 / 120, 9, 10, 3e-2, boxes, sph, True, w["weights"], 48, 2,
+                                                     w["K"], w["u_lo"], w["u_hi"], w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"])
+        assert np.array_equal(hq2, hq) and np.array_equal(hd2, hd)
     rng = np.random.default_rng(T)
     for M, N, k in ((1, 1, 1), (T, 300, 1), (1, 5000, min(T, 50)), (3, 40, 64)):
         qs, tree = rng.normal(size=(M, n)).astype(np.float32), rng.normal(size=(N, n)).astype(np.float32)

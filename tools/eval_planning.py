@@ -63,7 +63,13 @@ def main():
         pos, siz, starts, goals = get_test_cases(refined, 0, len(records))
         kw = dict(simulation_dt=1 / 120, controller_period=1 / 30, RRT_STEP=a.rrt_step, goal_biasing=0.2,
                   max_node=a.max_node, start_idx=0, end_idx=len(records), cbf_alpha=0.1)
-        res = eval_batchrrt_vanilla(23, env2, env2.robot_list[0], pos, siz, starts, goals, **kw)
+        # every method runs twice (same seed, same plans); the faster run is reported: the totals are ~0.1 s, a single
+        # host hiccup (first use of a launch shape, page pinning) would otherwise double a figure
+        def best_of_two(fn):
+            runs = [fn() for _ in range(2)]
+            return min(runs, key=lambda r: summarize(r)["total_time"])
+
+        res = best_of_two(lambda: eval_batchrrt_vanilla(23, env2, env2.robot_list[0], pos, siz, starts, goals, **kw))
         s = summarize(res)
         s.update(method="batchrrt_vanilla (line steer, batch 10)", ms_per_explored_node=1e3 * s["total_time"] / max(1, sum(r["explored_nodes"] for r in res)))
         print(json.dumps(s))
@@ -72,8 +78,8 @@ def main():
         ctrl = NeuralMindisCBFController(dyn2, [{"name": 1}], None, None, cbf_alpha=0.1, cbf_relaxation_penalty=500,
                                          safe_level=0.01, unsafe_level=0.01, cbf_hidden_layers=2, cbf_hidden_size=48)
         for batch in (1, 10, 50):
-            res = eval_batchrrt_mindis(23, env2, env2.robot_list[0], None, pos, siz, starts, goals, controller=ctrl,
-                                       batch=batch, **kw)
+            res = best_of_two(lambda: eval_batchrrt_mindis(23, env2, env2.robot_list[0], None, pos, siz, starts, goals,
+                                                           controller=ctrl, batch=batch, **kw))
             s = summarize(res)
             s.update(method=f"batchrrt_mindis (fused CBF steer, batch {batch}, random-init network)",
                      ms_per_explored_node=1e3 * s["total_time"] / max(1, sum(r["explored_nodes"] for r in res)))
