@@ -50,6 +50,35 @@ def _f32c(t: Tensor) -> Tensor:
     return t.to(dtype=torch.float32).contiguous()
 
 
+# scratch of the two-pass sweeps (include/cbfrrt.h cbfrrt_set_workspace): one tensor per device, grown on demand.  The
+# library never allocates device memory itself; this layer owns the buffer and registers it.
+SPLIT_MIN_ROWS = 1 << 18
+_WORKSPACE = {}
+
+
+def _ensure_workspace(dev: torch.device, rows: int, n: int, hidden: int, layers: int) -> None:
+    """room for the observation rows (+ mask bytes) of a sweep of ``rows`` states between its two passes"""
+    if rows < SPLIT_MIN_ROWS or (hidden, layers) != (48, 2):
+        return
+    need = 16 + (4 * (2 * n + 1) + 1) * rows + 16
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _WORKSPACE.get(idx)
+    if ws is None or ws.numel() < need:
+        ws = None
+        _WORKSPACE.pop(idx, None)
+        with torch.cuda.device(dev):
+            check(lib.cbfrrt_set_workspace(None, 0), "cbfrrt_set_workspace")
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            check(lib.cbfrrt_set_workspace(C.c_void_p(ws.data_ptr()), ws.numel()), "cbfrrt_set_workspace")
+        _WORKSPACE[idx] = ws
+
+
+def set_two_pass(enabled: bool) -> None:
+    """False: large sweeps always run the single fused kernel (A/B measurements, tests); True (default): the two-pass form
+    from 262 144 rows on (include/cbfrrt.h cbfrrt_set_two_pass)"""
+    check(lib.cbfrrt_set_two_pass(int(bool(enabled))), "cbfrrt_set_two_pass")
+
+
 def build_grid(boxes8: Tensor, spheres: Tensor) -> Tensor:
     """Nearest-candidate grid of a packed scene (include/cbfrrt.h cbfrrt_grid_build).  Returns a uint8 device
     tensor to be passed as ``grid`` to the scene-consuming ops; an EMPTY tensor means brute force.  Results are
@@ -324,6 +353,7 @@ def valid_control(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, floor
     u = torch.empty((B, n), dtype=torch.float32, device=dev)
     # network shapes other than 48 x 2 run as two launches and need the observation rows in between
     datax = None if (hidden, layers) == (48, 2) else torch.empty((B, 2 * n + 1), dtype=torch.float32, device=dev)
+    _ensure_workspace(dev, B, n, hidden, layers)
     with torch.cuda.device(dev):
         check(lib.cbfrrt_safety_filter(robot_id, C.byref(sc), C.byref(net), _ptr(q), qs, B, C.byref(fp), thr_soft,
                                        thr_hard, _ptr(safe), None, _ptr(datax), None, None, _ptr(u), None, _stream()),
@@ -345,6 +375,7 @@ def valid_control_into(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tensor, 
         raise ValueError("valid_control_into: outputs must be contiguous (B,) uint8 and (B, n) float32 on q's device")
     net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers)
     sc = _scene(boxes, spheres, floor, grid)
+    _ensure_workspace(dev, B, n, hidden, layers)
     with torch.cuda.device(dev):
         check(lib.cbfrrt_safety_filter(robot_id, C.byref(sc), C.byref(net), _ptr(q), qs, B, C.byref(fp), thr_soft,
                                        thr_hard, _ptr(valid_out), None, None, None, None, _ptr(u_out), None, _stream()),
@@ -396,6 +427,7 @@ def valid_control_scatter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tenso
     po.n_peers, po.multicast, po.row_offset = len(valid_ptrs), int(bool(multicast)), int(row_offset)
     for i, (v, u) in enumerate(zip(valid_ptrs, u_ptrs)):
         po.valid[i], po.u[i] = int(v), int(u)
+    _ensure_workspace(dev, B, n, hidden, layers)
     with torch.cuda.device(dev):
         check(lib.cbfrrt_safety_filter_scatter(robot_id, C.byref(sc), C.byref(net), _ptr(q), qs, B, C.byref(fp), thr_soft,
                                                thr_hard, C.byref(po), _stream()), "cbfrrt_safety_filter_scatter")

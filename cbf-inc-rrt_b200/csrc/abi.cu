@@ -14,6 +14,8 @@ static int mlp_path_from_env() {
     return (e && e[0] == 'f') ? CBFRRT_MLP_FMA : ((e && e[0] == 't') ? CBFRRT_MLP_TC : CBFRRT_MLP_AUTO);
 }
 std::atomic<int> g_mlp_path{mlp_path_from_env()};
+Workspace g_workspace[64] = {};
+std::atomic<int> g_split{[] { const char* e = getenv("CBFRRT_SPLIT"); return (e && e[0] == '0') ? 0 : 1; }()};
 }  // namespace cbfrrt
 
 using namespace cbfrrt;
@@ -42,6 +44,16 @@ int cbfrrt_set_mlp_path(int path) {
     return CBFRRT_OK;
 }
 int cbfrrt_get_mlp_path(void) { return g_mlp_path.load(); }
+
+int cbfrrt_set_workspace(void* device_ptr, int64_t bytes) {
+    if (bytes < 0 || (bytes > 0 && !device_ptr) || !aligned16(device_ptr)) return CBFRRT_ERR_BAD_SHAPE;
+    g_workspace[current_device() & 63] = Workspace{bytes > 0 ? device_ptr : nullptr, bytes > 0 ? (long long)bytes : 0};
+    return CBFRRT_OK;
+}
+int cbfrrt_set_two_pass(int enabled) {
+    g_split.store(enabled ? 1 : 0);
+    return CBFRRT_OK;
+}
 int64_t cbfrrt_launch_count(void) { return g_launches.load(); }
 
 int cbfrrt_robot_info(int robot, int32_t* n, int32_t* n_links, int32_t* n_spheres) {

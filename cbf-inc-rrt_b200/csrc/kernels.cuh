@@ -729,36 +729,6 @@ __device__ __forceinline__ void filter_tile_tc(tc::Ctx<L, GG>& c, const float* p
     cbf_filter_post<N>(prm, q, dodq, goal, goal_is_uref, lam, penalty, h, jac, J, u, r);
 }
 
-template <int N, int L>
-__global__ void __launch_bounds__(4 * tc::M_TILE, 1) filter_kernel_tc(NetArgs net, const float* __restrict__ datax,
-                                                                      long long B, FilterOutPtrs out) {
-    constexpr int GG = 4, NTC = GG * tc::M_TILE;
-    extern __shared__ __align__(16) float smem_raw[];
-    const Smem s = carve(smem_raw, 0, 0, tc::Layout<L, GG>::TOTAL, ParamLayout<N>::TOTAL);
-    SceneArgs none{nullptr, nullptr, 0, 0, 0, nullptr, nullptr};
-    stage<N, NTC>(s, none, &net, 0);
-    tc::Ctx<L, GG> c;
-    tc::setup<N + 1, L, GG>(c, s.weights, net.weights);
-    const long long n_tiles = (B + tc::M_TILE - 1) / tc::M_TILE;
-    for (long long tile = (long long)blockIdx.x * GG + c.g; tile < n_tiles; tile += (long long)gridDim.x * GG) {
-        const long long b = tile * tc::M_TILE + c.t;
-        const bool active = b < B;
-        float q[N], dodq[N], g[N], J[N], u[N], h, r, o = 0.f;
-#pragma unroll
-        for (int k = 0; k < N; ++k) { q[k] = 0.f; dodq[k] = 0.f; g[k] = 0.f; }
-        if (active) {
-            const float* d = datax + b * (2 * N + 1);
-#pragma unroll
-            for (int k = 0; k < N; ++k) { q[k] = __ldg(d + k); dodq[k] = __ldg(d + N + 1 + k); }
-            o = __ldg(d + N);
-            load_goal<N>(net, b, g);
-        }
-        filter_tile_tc<N, L, GG>(c, s.params, q, o, dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
-        if (active) write_filter<N>(out, b, h, J, u, r);
-    }
-    tc::teardown<L, GG>(c);
-}
-
 // ---- coalesced tile I/O of the tensor-core safety kernel.  A tile is 128 CONSECUTIVE rows, so every per-row array of
 // the tile is one contiguous, 16-byte aligned block in global memory (128 x 28 B of q, 128 x 60 B of datax, ...).  Rows
 // are exchanged through the group's A_lo tile, which is idle between the last GEMM of a tile and the first hidden-layer
@@ -809,6 +779,65 @@ __device__ __forceinline__ void warp_load_rows(float* __restrict__ stg, int lane
     for (int k = 0; k < W; ++k) v[k] = stg[lane * W + k];
 }
 constexpr int VEC_Q = 1, VEC_OUT = 2, VEC_PEER = 4;   // which pointer sets are 16-byte aligned (checked on the host)
+
+// datax -> (h, J, u, r) on the tensor cores.  PEERS: the barrier-network pass of the two-pass sweep (launch_safety) in the
+// multi-GPU exchange: the row's control and the mask byte the geometry pass left in safe_in are stored into every rank's
+// replica (fused all-gather, see safety_kernel_tc) -- whole 128-row tiles staged through the group's A_lo tile and
+// streamed as 16-byte (multimem) stores, ragged tiles row by row.
+template <int N, int L, bool PEERS>
+__global__ void __launch_bounds__(4 * tc::M_TILE, 1) filter_kernel_tc(NetArgs net, const float* __restrict__ datax,
+                                                                      long long B, FilterOutPtrs out, PeerOut po,
+                                                                      const uint8_t* __restrict__ safe_in, int vec) {
+    constexpr int GG = 4, NTC = GG * tc::M_TILE, MT = tc::M_TILE;
+    constexpr int O_U = 2048, O_B = O_U + MT * N;          // staging offsets (floats) inside the group's A_lo tile
+    static_assert(O_B + MT / 4 <= tc::ALO_TILE, "staging does not fit the A_lo tile");
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, 0, 0, tc::Layout<L, GG>::TOTAL, ParamLayout<N>::TOTAL);
+    SceneArgs none{nullptr, nullptr, 0, 0, 0, nullptr, nullptr};
+    stage<N, NTC>(s, none, &net, 0);
+    tc::Ctx<L, GG> c;
+    tc::setup<N + 1, L, GG>(c, s.weights, net.weights);
+    float* const alo = reinterpret_cast<float*>(c.alo());
+    const long long n_tiles = (B + tc::M_TILE - 1) / tc::M_TILE;
+    for (long long tile = (long long)blockIdx.x * GG + c.g; tile < n_tiles; tile += (long long)gridDim.x * GG) {
+        const long long b0 = tile * tc::M_TILE, b = b0 + c.t;
+        const bool active = b < B;
+        float q[N], dodq[N], g[N], J[N], u[N], h, r, o = 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { q[k] = 0.f; dodq[k] = 0.f; g[k] = 0.f; }
+        if (active) {
+            const float* d = datax + b * (2 * N + 1);
+#pragma unroll
+            for (int k = 0; k < N; ++k) { q[k] = __ldg(d + k); dodq[k] = __ldg(d + N + 1 + k); }
+            o = __ldg(d + N);
+            load_goal<N>(net, b, g);
+        }
+        filter_tile_tc<N, L, GG>(c, s.params, q, o, dodq, g, net.u_ref != nullptr, net.lam, net.penalty, h, J, u, r);
+        if (active) write_filter<N>(out, b, h, J, u, r);
+        if constexpr (PEERS) {
+            const bool safe = active && safe_in[b] != 0;
+            if (b0 + MT <= B && (vec & VEC_PEER)) {        // uniform over the group
+                park_row<N>(alo + O_U, c.t, u);
+                reinterpret_cast<uint8_t*>(alo + O_B)[c.t] = safe;
+                tc::group_sync(c.g);
+                const long long g0 = po.row_offset + b0;
+                if (po.multicast) {
+                    flush_block<true>(alo + O_U, c.t, po.u[0] + g0 * N, MT * N / 4);
+                    flush_block<true>(alo + O_B, c.t, reinterpret_cast<float*>(po.valid[0] + g0), MT / 16);
+                } else {
+                    for (int p = 0; p < po.n; ++p) {
+                        flush_block<false>(alo + O_U, c.t, po.u[p] + g0 * N, MT * N / 4);
+                        flush_block<false>(alo + O_B, c.t, reinterpret_cast<float*>(po.valid[p] + g0), MT / 16);
+                    }
+                }
+                tc::group_sync(c.g);                       // the staging block is the next tile's A_lo
+            } else if (active) {
+                write_peers<N>(po, b, safe, u);
+            }
+        }
+    }
+    tc::teardown<L, GG>(c);
+}
 
 template <class RB, int L, bool GRID, int GG>
 __global__ void __launch_bounds__(GG * tc::M_TILE, 1) safety_kernel_tc(SceneArgs sc, NetArgs net, const float* __restrict__ q,
@@ -1623,10 +1652,10 @@ static int launch_filter(const NetArgs& net, const float* datax, long long B, co
     }
     if (use_tc() && (B > SMALL_BATCH || force_tc())) {
         const size_t smem = 4 * smem_floats(0, 0, tc::Layout<2, 4>::TOTAL, ParamLayout<N>::TOTAL, 0);
-        auto k = filter_kernel_tc<N, 2>;
+        auto k = filter_kernel_tc<N, 2, false>;
         const int grid = grid_for_tc(k, smem, B, 4);
         if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, 4 * tc::M_TILE, smem, st>>>(net, datax, B, out);
+        k<<<grid, 4 * tc::M_TILE, smem, st>>>(net, datax, B, out, PeerOut{}, nullptr, 0);
         return finish_launch();
     }
     using LY = NetLayout<N + 1, 48, 2>;
@@ -1638,9 +1667,89 @@ static int launch_filter(const NetArgs& net, const float* datax, long long B, co
     return finish_launch();
 }
 
+// ---- per-robot launch wrappers: each is defined in its own translation unit (k_<family>_<robot>.cu) so that the
+// big template instantiations compile in parallel
+#define CBF_DECLARE_ROBOT(R)                                                                                          \
+    int launch_collide_##R(const SceneArgs&, const float*, long long, long long, float, float, const CollideOutPtrs&,  \
+                           cudaStream_t);                                                                              \
+    int launch_safety_##R(const SceneArgs&, const NetArgs&, const float*, long long, long long, float, float,          \
+                          const CollideOutPtrs&, const FilterOutPtrs&, const PeerOut&, cudaStream_t);                  \
+    int launch_edges_##R(const SceneArgs&, const float*, const float*, long long, int, float, float, uint8_t*, int*,   \
+                         cudaStream_t);                                                                                \
+    int launch_edges_var_##R(const SceneArgs&, const float*, const float*, long long, const long long*, long long,     \
+                             float, float, uint8_t*, int*, cudaStream_t);                                              \
+    int launch_rollout_##R(const SceneArgs&, const NetArgs&, const float*, long long, const RolloutArgs&, float,       \
+                           float, float*, uint8_t*, int*, float*, cudaStream_t);                                       \
+    int launch_rollout_segments_##R(const SceneArgs&, const NetArgs&, const float*, int, int, int, const RolloutArgs&,  \
+                                    float, float, float*, uint8_t*, int*, float*, cudaStream_t);
+CBF_DECLARE_ROBOT(panda)
+CBF_DECLARE_ROBOT(magician)
+#undef CBF_DECLARE_ROBOT
+
+
+// Two-pass form of the large sweeps.  The fused kernel runs the geometry at the occupancy the barrier network dictates
+// (one 512-thread CTA per SM: TMEM, 180 KB of weights and A_lo tiles, 128 registers) and measures 5.65 ms per 2^23 Panda
+// states on the 256-box scene; the same work as a geometry pass at its own occupancy (collide_kernel -> masks + datax)
+// followed by a barrier-network pass through datax (filter_kernel_tc -> u) takes 3.2 + 1.5 = 4.7 ms although it moves
+// 120 B per state more (profiles/r2w_split_pipeline_probe.json; the outputs are bit-identical: same device functions).
+// It needs somewhere to put datax (60 B per row; + 1 B per row for the mask in the multi-GPU exchange): the caller's
+// datax output when requested, else the scratch registered with cbfrrt_set_workspace for this device.
+constexpr long long SPLIT_MIN_ROWS = 1 << 18;
+struct Workspace {
+    void* ptr;
+    long long bytes;
+};
+extern Workspace g_workspace[64];
+extern std::atomic<int> g_split;   // 1: two-pass form allowed (default), 0: always the fused kernel (CBFRRT_SPLIT=0, tests)
+
+template <class RB>
+static int launch_safety_two_pass(const SceneArgs& sc, const NetArgs& net, const float* q, long long qs, long long B, float ts,
+                                  float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, const PeerOut& po, float* dx,
+                                  uint8_t* safe_loc, cudaStream_t st) {
+    constexpr int N = RB::N;
+    CollideOutPtrs a = co;
+    a.datax = dx;
+    if (po.n) a.safe = safe_loc;
+    int rc = RB::ID == 0 ? launch_collide_panda(sc, q, qs, B, ts, th, a, st) : launch_collide_magician(sc, q, qs, B, ts, th, a, st);
+    if (rc) return rc;
+    if (!fo.h && !fo.J && !fo.u && !fo.r && !po.n) return CBFRRT_OK;
+    const size_t smem = 4 * smem_floats(0, 0, tc::Layout<2, 4>::TOTAL, ParamLayout<N>::TOTAL, 0);
+    if (po.n) {
+        int vec = 0;
+        if (po.row_offset % 16 == 0) {
+            bool ok = true;
+            for (int p = 0; p < po.n; ++p) ok = ok && aligned16(po.valid[p]) && aligned16(po.u[p]);
+            if (ok) vec |= VEC_PEER;
+        }
+        auto k = filter_kernel_tc<N, 2, true>;
+        const int grid = grid_for_tc(k, smem, B, 4);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, 4 * tc::M_TILE, smem, st>>>(net, dx, B, fo, po, safe_loc, vec);
+    } else {
+        auto k = filter_kernel_tc<N, 2, false>;
+        const int grid = grid_for_tc(k, smem, B, 4);
+        if (grid < 0) return CBFRRT_ERR_CUDA;
+        k<<<grid, 4 * tc::M_TILE, smem, st>>>(net, dx, B, fo, po, nullptr, 0);
+    }
+    return finish_launch();
+}
+
 template <class RB>
 static int launch_safety(const SceneArgs& sc_in, const NetArgs& net, const float* q, long long qs, long long B, float ts,
                          float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, const PeerOut& po, cudaStream_t st) {
+    if (B >= SPLIT_MIN_ROWS && use_tc() && !force_tc() && g_split.load(std::memory_order_relaxed) && !sc_in.stats) {
+        constexpr long long DXB = 4 * (2 * RB::N + 1);
+        float* dx = co.datax;
+        uint8_t* safe_loc = co.safe;
+        const Workspace ws = g_workspace[current_device() & 63];
+        const long long need = (dx ? 0 : ((B * DXB + 15) & ~15LL)) + ((po.n && !safe_loc) ? B : 0);
+        if (need > 0 && ws.ptr && ws.bytes >= need) {
+            char* w = static_cast<char*>(ws.ptr);
+            if (!dx) { dx = reinterpret_cast<float*>(w); w += (B * DXB + 15) & ~15LL; }
+            if (po.n && !safe_loc) safe_loc = reinterpret_cast<uint8_t*>(w);
+        }
+        if (dx && (!po.n || safe_loc)) return launch_safety_two_pass<RB>(sc_in, net, q, qs, B, ts, th, co, fo, po, dx, safe_loc, st);
+    }
     if (use_warp(B, WARP_MAX_ROWS) && po.n == 0 && !sc_in.stats) {
         const SceneArgs sc = scene_for_warp(sc_in);
         using LYW = NetLayout<RB::N + 1, 48, 2>;
@@ -1797,24 +1906,5 @@ static int launch_rollout_segments(const SceneArgs& sc_in, const NetArgs& net, c
     k<<<1, NT, smem, st>>>(sc, net, q0, T, n_seg, seg_len, ra, ts, th, seg_q, seg_alive, seg_done, traj);
     return finish_launch();
 }
-
-// ---- per-robot launch wrappers: each is defined in its own translation unit (k_<family>_<robot>.cu) so that the
-// big template instantiations compile in parallel
-#define CBF_DECLARE_ROBOT(R)                                                                                          \
-    int launch_collide_##R(const SceneArgs&, const float*, long long, long long, float, float, const CollideOutPtrs&,  \
-                           cudaStream_t);                                                                              \
-    int launch_safety_##R(const SceneArgs&, const NetArgs&, const float*, long long, long long, float, float,          \
-                          const CollideOutPtrs&, const FilterOutPtrs&, const PeerOut&, cudaStream_t);                  \
-    int launch_edges_##R(const SceneArgs&, const float*, const float*, long long, int, float, float, uint8_t*, int*,   \
-                         cudaStream_t);                                                                                \
-    int launch_edges_var_##R(const SceneArgs&, const float*, const float*, long long, const long long*, long long,     \
-                             float, float, uint8_t*, int*, cudaStream_t);                                              \
-    int launch_rollout_##R(const SceneArgs&, const NetArgs&, const float*, long long, const RolloutArgs&, float,       \
-                           float, float*, uint8_t*, int*, float*, cudaStream_t);                                       \
-    int launch_rollout_segments_##R(const SceneArgs&, const NetArgs&, const float*, int, int, int, const RolloutArgs&,  \
-                                    float, float, float*, uint8_t*, int*, float*, cudaStream_t);
-CBF_DECLARE_ROBOT(panda)
-CBF_DECLARE_ROBOT(magician)
-#undef CBF_DECLARE_ROBOT
 
 }  // namespace cbfrrt

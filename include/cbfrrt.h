@@ -138,6 +138,18 @@ typedef enum { CBFRRT_MLP_AUTO = 0, CBFRRT_MLP_FMA = 1, CBFRRT_MLP_TC = 2, CBFRR
 int cbfrrt_set_mlp_path(int path);
 int cbfrrt_get_mlp_path(void);
 
+/* ---- optional scratch for the large sweeps --------------------------------------------------------------------
+ * From 262 144 rows on, cbfrrt_safety_filter / cbfrrt_safety_filter_scatter run as TWO launches when they have room for
+ * the intermediate observation rows: a geometry pass at its own occupancy (masks + datax) and a tensor-core barrier-network
+ * pass through datax (h, J, u, r and the peer stores of the fused exchange) -- measured 1.2x faster on B200 than the single
+ * fused kernel, whose geometry runs at the occupancy the tensor-core stage dictates; results are bit-identical.  Room =
+ * the caller's datax output when it is requested, else a scratch of at least 16 + (4 (2 n + 1) + 1) B bytes registered
+ * here for the CURRENT device (the library never allocates device memory in the device-pointer entry points; the buffer
+ * must stay valid, and not be used by the caller, while such calls are in flight).  bytes = 0 unregisters.  Without room
+ * the fused kernel runs.  cbfrrt_set_two_pass(0) forces the fused kernel (A/B measurements, tests). */
+int cbfrrt_set_workspace(void *device_ptr, int64_t bytes);
+int cbfrrt_set_two_pass(int enabled);
+
 /* ---- scene acceleration structure (built once per ArmEnv.reset_env, environment/arm_env.py:63) --------------
  * Nearest-candidate grid over the arm's workspace: per 5 cm cell, the obstacles that can be the closest one for
  * some point of the cell.  Results with and without the grid are bit-identical (csrc/grid.cuh).  The caller owns

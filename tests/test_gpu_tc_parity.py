@@ -352,3 +352,54 @@ def test_rollout_segments_matches_oracle(coracle, robot, T):
     with pytest.raises(CbfrrtError):               # more rows than one CTA holds
         ops.rollout_segments(_t(np.repeat(q0[:1], 129, 0)), _t(goal[:1]), 2, 20, 4, 1 / 120, 9, 10, 3e-2, b8, s4, 1, gr, _net(w),
                              _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"], w["thr_soft"], w["thr_hard"], rid, 48, 2)
+
+
+@pytest.mark.parametrize("case", ["panda-256box-grid", "magician-16box", "panda-8box"])
+def test_two_pass_sweep_equals_fused_kernel_and_oracle(coracle, case):
+    """From 2^18 rows on the sweep runs as a geometry pass + a tensor-core barrier-network pass through datax (the caller's
+    datax output, or the registered scratch): every output bit-identical to the single fused kernel, the fused exchange
+    (peer stores from the second pass) included, and equal to the oracle on the first and last rows"""
+    from cbfrrt import ops, workloads as W
+    robot, boxes, sph = _cases()[case]
+    w = _workload(robot)
+    n, rid, B = w["n"], ops.ROBOT_ID[robot], (1 << 18) + 77
+    q = ops.sample_states(B, 5, 0, rid, device=DEV)
+    goal = _t(W.sample_states(robot, B, 24))
+    b8, s4, gr = _scene(boxes, sph)
+    res = {}
+    try:
+        for two_pass in (True, False):
+            ops.set_two_pass(two_pass)
+            for goal_t in (goal, goal[:1]):
+                args = (q, goal_t, b8, s4, 1, gr, _net(w), _t(w["K"]), _t(w["u_lo"]), _t(w["u_hi"]), w["lam"], w["penalty"],
+                        w["thr_soft"], w["thr_hard"], rid, 48, 2)
+                n0 = ops.launch_count()
+                full = ops.safety_filter(*args)
+                torch.cuda.synchronize()
+                assert ops.launch_count() - n0 == (2 if two_pass else 1)
+                n0 = ops.launch_count()
+                v, u = ops.valid_control(*args)                       # no datax output: the registered scratch
+                assert ops.launch_count() - n0 == (2 if two_pass else 1)
+                assert torch.equal(v, full[0]) and torch.equal(u, full[5])
+                # fused exchange into local "replicas" (one peer, plain pointers), at a row offset, ragged last tile
+                G = B + 256
+                vbuf, ubuf = torch.zeros(G, dtype=torch.uint8, device=DEV), torch.zeros((G, n), device=DEV)
+                ops.valid_control_scatter(*args, [vbuf.data_ptr()], [ubuf.data_ptr()], 128, False)
+                torch.cuda.synchronize()
+                assert torch.equal(vbuf[128:128 + B], v) and torch.equal(ubuf[128:128 + B], u)
+                assert not vbuf[:128].any() and not ubuf[128 + B:].any()
+                res[(two_pass, goal_t.shape[0])] = full
+    finally:
+        ops.set_two_pass(True)
+    for rows in (B, 1):
+        for a, b in zip(res[(True, rows)], res[(False, rows)]):
+            assert torch.equal(a, b)
+    safe, unsafe, datax, h, J, u, r = res[(True, B)]
+    for sl in (slice(0, 3000), slice(B - 3000, B)):
+        qh, gh = q[sl].cpu().numpy(), goal[sl].cpu().numpy()
+        o = coracle.safety_filter(robot, qh, boxes, sph, True, w["weights"], 48, 2, gh, w["K"], w["u_lo"], w["u_hi"],
+                                  w["thr_soft"], w["thr_hard"], w["lam"], w["penalty"])
+        assert np.array_equal(safe[sl].cpu().numpy(), o["safe"]) and np.array_equal(unsafe[sl].cpu().numpy(), o["unsafe"])
+        assert np.array_equal(datax[sl].cpu().numpy()[:, :n + 1], o["datax"][:, :n + 1])
+        assert_filter_matches_truth(coracle, n, w["weights"], datax[sl].cpu().numpy(), gh, w["K"], w["u_lo"], w["u_hi"], w["lam"],
+                                    w["penalty"], h[sl], J[sl], u[sl], r[sl], name=f"two-pass sweep {case}")
