@@ -25,6 +25,7 @@ Prints ONE JSON line (rank 0).
                load the CUDA library
 """
 import argparse
+import ctypes
 import importlib
 import json
 import os
@@ -458,7 +459,7 @@ def main():
     tf32_peak = 2 * 8192 ** 3 / (min(tt) * 1e-3) / 1e12
     del a_, b_
     torch.backends.cuda.matmul.allow_tf32 = False
-    kernel_s = ms * 1e-3 / args.steps
+    step_s = ms * 1e-3 / args.steps
     rows_per_launch = B
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -466,32 +467,81 @@ def main():
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     tc_path = B > 16384
-    pipes = {
-        "fp32": {"achieved": cost["fp32"] * rows_per_launch / kernel_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                 "peak_source": "cbfrrt_fma_probe in this run (FP32 FMA rate; not in MEASURED_PEAKS.json)",
-                 "work_per_state": cost["fp32"]},
-        "tensor": {"achieved": (3 * cost["mlp"] if tc_path else 0) * rows_per_launch / kernel_s / 1e12, "peak": tf32_peak,
-                   "unit": "TFLOP/s", "peak_source": "torch.matmul TF32 8192^3 in this run (cuBLAS)",
-                   "work_per_state": 3 * cost["mlp"],
-                   "note": "executed tcgen05 flops of the barrier network: 3-term TF32 split = 3 x the algorithmic 2*MACs"},
-        "hbm": {"achieved": cost["bytes"] * rows_per_launch / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "peak_source": hbm_src, "work_per_state": cost["bytes"]},
-    }
-    for p in pipes.values():
-        p["frac"] = p["achieved"] / p["peak"]
-    bound = max(pipes, key=lambda k: pipes[k]["frac"])
-    traffic = None   # per launch, from the committed ncu --set full capture of this command (profiles/); filled in below
+    per_step = launches / max(1, args.steps)
+    two_pass = world == 1 and round(per_step) == 2 or (world > 1 and B >= ops.SPLIT_MIN_ROWS and os.environ.get("CBFRRT_SPLIT", "1") != "0")
+    qp_flops = 2 * n * (3 * n + 4)
+
+    def pipes_of(seconds, fp32, tensor, byts):
+        d = {"fp32": {"achieved": fp32 * rows_per_launch / seconds / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                      "peak_source": "cbfrrt_fma_probe in this run (FP32 FMA rate; not in MEASURED_PEAKS.json)", "work_per_state": fp32},
+             "tensor": {"achieved": tensor * rows_per_launch / seconds / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "peak_source": "torch.matmul TF32 8192^3 in this run (cuBLAS)", "work_per_state": tensor,
+                        "note": "executed tcgen05 flops of the barrier network: 3-term TF32 split = 3 x the algorithmic 2*MACs"},
+             "hbm": {"achieved": byts * rows_per_launch / seconds / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+                     "work_per_state": byts}}
+        for p in d.values():
+            p["frac"] = p["achieved"] / p["peak"]
+        return d
+
     tr_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    traffic_note = "no ncu --set full capture committed for this workload"
-    if os.path.exists(tr_file):
-        ent = json.load(open(tr_file)).get(w["name"])
-        if ent:   # bytes per state from the committed capture x the rows of one launch of THIS run
-            traffic = ent["dram_bytes_per_state"] * rows_per_launch
-            traffic_note = ent["source"]
+    tr_db = json.load(open(tr_file)) if os.path.exists(tr_file) else {}
+
+    def traffic_of(key):
+        ent = tr_db.get(key)
+        if not ent:
+            return None, "no ncu --set full capture committed for this kernel"
+        return ent["dram_bytes_per_state"] * rows_per_launch, ent["source"]   # bytes per state of the capture x rows of THIS launch
+
+    passes = None
+    if two_pass:
+        # the step is two launches: each pass is timed alone, live, with the same kernels / inputs / outputs (CUDA events on
+        # the launching stream, L2 flushed in between); their sum against the step time is printed as a cross-check
+        dx_s = torch.empty((B, 2 * n + 1), dtype=torch.float32, device=dev)
+        safe_s, unsafe_s = torch.empty(B, dtype=torch.uint8, device=dev), torch.empty(B, dtype=torch.uint8, device=dev)
+        u_s = torch.empty((B, n), dtype=torch.float32, device=dev)
+        sc_c = ops._scene(b8, s4, 1, gr)
+
+        def pass_a():
+            ops.check(ops.lib.cbfrrt_collide(rid, ctypes.byref(sc_c), q.data_ptr(), n, B, w["thr_soft"], w["thr_hard"], safe_s.data_ptr(),
+                                             None, dx_s.data_ptr(), None, None, None, torch.cuda.current_stream().cuda_stream), "cbfrrt_collide")
+
+        def pass_b():
+            ops.cbf_filter_u_into(dx_s, goal, net, K, lo, hi, w["lam"], w["penalty"], 48, 2, u_s)
+
+        def timed_pass(fn):
+            fn()
+            tt_ = []
+            for _ in range(3):
+                flush.zero_()
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                tt_.append(e0.elapsed_time(e1) * 1e-3)
+            return sum(tt_) / len(tt_)
+
+        t_a, t_b = timed_pass(pass_a), timed_pass(pass_b)
+        del dx_s, safe_s, unsafe_s, u_s
+        in_b, dx_b = 4 * n, 4 * (2 * n + 1)
+        passes = [
+            {"kernel": f"collide_kernel<{robot}, grad, grid={bool(stats['grid'])}> (geometry pass: q -> valid, datax)", "ms": t_a * 1e3,
+             "pipes": pipes_of(t_a, cost["fp32"] - qp_flops, 0, in_b + 1 + dx_b), "key": w["name"] + ":geometry_pass"},
+            {"kernel": f"filter_kernel_tc<{n}> (barrier-network pass: datax -> u, tcgen05)", "ms": t_b * 1e3,
+             "pipes": pipes_of(t_b, qp_flops, 3 * cost["mlp"], dx_b + in_b), "key": w["name"] + ":network_pass"},
+        ]
+        for p_ in passes:
+            p_["bound"] = max(p_["pipes"], key=lambda k: p_["pipes"][k]["frac"])
+            p_["frac"] = p_["pipes"][p_["bound"]]["frac"]
+            p_["traffic"], p_["traffic_source"] = traffic_of(p_.pop("key"))
+        dom = max(passes, key=lambda p_: p_["ms"])
+        pipes, kernel_s, kernel_name = dom["pipes"], dom["ms"] * 1e-3, dom["kernel"]
+        traffic, traffic_note = dom["traffic"], dom["traffic_source"]
+    else:
+        kernel_s = step_s
+        pipes = pipes_of(kernel_s, cost["fp32"], 3 * cost["mlp"] if tc_path else 0, cost["bytes"])
+        kernel_name = ("safety_kernel_tc" if tc_path else "safety_kernel") + f"<{robot}, grid={bool(stats['grid'])}>"
+        traffic, traffic_note = traffic_of(w["name"])
+    bound = max(pipes, key=lambda k: pipes[k]["frac"])
     roofline = {"bound": bound, "achieved": pipes[bound]["achieved"], "peak": pipes[bound]["peak"], "unit": pipes[bound]["unit"],
                 "frac": pipes[bound]["frac"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
-                "traffic_source": traffic_note, "pipes": pipes,
-                "kernel": ("safety_kernel_tc" if tc_path else "safety_kernel") + f"<{robot}, grid={bool(stats['grid'])}>",
+                "traffic_source": traffic_note, "pipes": pipes, "kernel": kernel_name,
                 "kernel_ms": kernel_s * 1e3, "rows_per_launch": rows_per_launch, "broad_phase": stats,
                 "fp32_work_per_state_brute_force_formula": cost["fp32_brute_force"],
                 "note": "per pipe, never summed: fp32 = algorithmic CUDA-core flops of the path as built (FK, centres, broad-"
@@ -499,6 +549,13 @@ def main():
                         "scene --, self pairs, gradient, QP) / kernel time against the measured FMA rate; tensor = executed "
                         "tcgen05 flops against a measured dense TF32 matmul; hbm = compulsory bytes against the measured "
                         "copy bandwidth.  frac = the largest.  SURVEY 8d's brute-force pair formula is kept beside it."}
+    if passes is not None:
+        roofline["passes"] = passes
+        roofline["step_ms"] = step_s * 1e3
+        roofline["passes_ms_sum"] = sum(p_["ms"] for p_ in passes)
+        roofline["note"] += ("  The step is TWO launches (DESIGN.md 4.8): a geometry pass at its own occupancy and a tensor-core "
+                             "barrier-network pass through the observation rows; the top-level figures are those of the longer "
+                             "pass, `passes` holds both, each timed alone in this run.")
 
     # ---- end to end through the host-buffer C-ABI (pinned host buffers; H2D + D2H inside the timed region)
     e2e = None
@@ -560,7 +617,7 @@ def main():
                 "l2": "per-GPU inputs + outputs exceed the 126 MB L2; a 256 MiB write also flushes it between timed steps "
                       "(outside the event pairs)",
                 "collective": collective, "host_cpus_bound": affinity}),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(round(launches / max(1, args.steps))),
             "roofline": roofline, "cpu_baseline": cpu, "targets": targets, "other_configs": others,
         }))
     if world > 1:

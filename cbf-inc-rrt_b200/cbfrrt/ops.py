@@ -238,6 +238,22 @@ def cbf_filter(datax: Tensor, goal: Tensor, weights: Tensor, K: Tensor, u_lo: Te
     return h, J, u, r
 
 
+def cbf_filter_u_into(datax: Tensor, goal: Tensor, weights: Tensor, K: Tensor, u_lo: Tensor, u_hi: Tensor, lam: float,
+                      penalty: float, hidden: int, layers: int, u_out: Tensor) -> Tensor:
+    """the barrier-network pass alone with only the control written (what the second pass of a valid + u sweep does):
+    datax f32[B,2n+1] -> u_out f32[B,n] (caller-owned).  bench.py times it for the per-pass roofline."""
+    datax = _f32c(datax)
+    B, n, dev = datax.shape[0], (datax.shape[1] - 1) // 2, datax.device
+    if tuple(u_out.shape) != (B, n) or u_out.dtype != torch.float32 or not u_out.is_contiguous() or u_out.device != dev:
+        raise ValueError("cbf_filter_u_into: u_out must be a contiguous (B, n) float32 tensor on datax's device")
+    net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, B, lam, penalty, hidden, layers, None)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_cbf_filter(n, C.byref(net), _ptr(datax), B, C.byref(fp), None, None, _ptr(u_out), None, _stream()),
+              "cbfrrt_cbf_filter")
+    del keep
+    return u_out
+
+
 @torch.library.custom_op("cbfrrt::qp", mutates_args=(), device_types="cuda")
 def qp(a: Tensor, c: Tensor, u_ref: Tensor, u_lo: Tensor, u_hi: Tensor, penalty: float) -> Tuple[Tensor, Tensor]:
     """a = Lg_V f32[B,n], c = Lf_V + lam*V f32[B], u_ref f32[B,n] -> u f32[B,n], r f32[B]"""

@@ -60,6 +60,22 @@ def _worker(rank, world, port, ret):
     torch.cuda.synchronize()
     ok.append(bool(torch.equal(v, ref_v2) and torch.equal(u, ref_u2)))
     dist.barrier()
+    # >= 2^18 rows per rank: the two-pass sweep, the peer stores (multicast, then per-peer) issued by its second pass
+    B3 = (1 << 18) + 128
+    q3 = ops.sample_states(world * B3, 7, 0, rid, device=dev)
+    ops.set_two_pass(False)
+    ref_v3, ref_u3 = ops.valid_control(q3, *common)                   # single fused kernel
+    ops.set_two_pass(True)
+    for no_mc in ("0", "1"):
+        os.environ["CBFRRT_NO_MULTICAST"] = no_mc
+        sweep3 = FusedSweep(lambda qb, vp, up, off, mc: ops.valid_control_scatter(qb, *common, vp, up, off, mc), n, B3, dev)
+        n0 = ops.launch_count()
+        v, u = sweep3(q3[rank * B3:(rank + 1) * B3])
+        torch.cuda.synchronize()
+        ok.append(bool(torch.equal(v, ref_v3) and torch.equal(u, ref_u3)) and ops.launch_count() - n0 == 2)
+        dist.barrier()
+        del sweep3
+    os.environ["CBFRRT_NO_MULTICAST"] = "0"
     if rank == 0:
         print("fused exchange modes tested (multicast, per-peer):", modes, flush=True)
     # NCCL all-gather, block-cyclic

@@ -21,6 +21,8 @@ python tools/measure_lidar.py --states 2048 --rays 64 --cloud 512 >> $OUT/${TAG}
 B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-other-configs --scale 0.125"
 $B > $OUT/${TAG}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $B > $OUT/${TAG}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:safety_kernel_tc -s 6 -c 1 -o $OUT/${TAG}_ncu_full $B > $OUT/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:collide_kernel -s 6 -c 1 -o $OUT/${TAG}_ncu_full_geometry_pass $B > $OUT/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:filter_kernel_tc -s 6 -c 1 -o $OUT/${TAG}_ncu_full_network_pass $B >> $OUT/${TAG}_ncu_full.log 2>&1
+CBFRRT_SPLIT=0 ncu --set full --clock-control none --import-source on -k regex:safety_kernel_tc -s 6 -c 1 -o $OUT/${TAG}_ncu_full_fused $B >> $OUT/${TAG}_ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:backbone_kernel_v2 -s 2 -c 1 -o $OUT/${TAG}_ncu_full_lidar python tools/measure_lidar.py --states 64 --iters 2 > $OUT/${TAG}_ncu_full_lidar.log 2>&1
-ls -la $OUT/${TAG}_ncu_full.ncu-rep $OUT/${TAG}_ncu_full_lidar.ncu-rep
+ls -la $OUT/${TAG}_ncu_full*.ncu-rep
