@@ -22,7 +22,10 @@ namespace cbfrrt {
 
 constexpr int NT = 128;
 #ifndef CBF_COLLIDE_MIN_CTAS
-#define CBF_COLLIDE_MIN_CTAS 4   // <= 128 registers: 16 warps per SM for the distance sweeps
+#define CBF_COLLIDE_MIN_CTAS 6   // <= 80 registers: 24 warps per SM.  The field path is bound by the latency of its L2 gathers,
+                                 // not by registers: measured per 2^23 Panda states, 256 boxes (4 / 5 / 6 / 7 / 8 CTAs per SM):
+                                 // masks 2.15 / 2.09 / 1.97 / 2.16 / 2.30 ms, masks + datax 3.23 / 3.14 / 3.16 / 3.13 / 3.28 ms,
+                                 // 2^22 edges x 33 points 25.3 / 22.4 / 22.3 / 22.7 / 25.2 ms
 #endif
 
 // ------------------------------------------------------------------ TMA bulk copy + mbarrier (PTX)

@@ -74,7 +74,11 @@ def test_gpu_arm_default_workload_line():
     """the default (headline) workload: BASELINE configs[4], strong scaling, valid + u; shrunk 1/64 here"""
     r = _run("--steps", "3", "--warmup", "3", "--scale", str(1 / 64), "--no-other-configs")
     assert r["config"]["workload"].startswith("cfg4") and r["scaling"] == "strong" and r["config"]["outputs"] == "valid+u"
-    assert r["config"]["states"] == 1 << 20 and r["gpu_launches"] == 3 and r["value"] > 0
+    # 2^20 rows: the two-pass sweep (geometry pass + barrier-network pass) -> two launches per step, each with its roofline
+    assert r["config"]["states"] == 1 << 20 and r["gpu_launches"] == 6 and r["launches_per_step"] == 2 and r["value"] > 0
+    ps = r["roofline"]["passes"]
+    assert len(ps) == 2 and all(set(p["pipes"]) == {"fp32", "tensor", "hbm"} and p["ms"] > 0 for p in ps)
+    assert abs(r["roofline"]["passes_ms_sum"] - r["roofline"]["step_ms"]) < 0.35 * r["roofline"]["step_ms"]
     assert 0.05 < r["config"]["valid_fraction"] < 0.5
     assert r["e2e"]["h2d_bytes_per_step"] == (1 << 20) * 28 and r["e2e"]["d2h_bytes_per_step"] == (1 << 20) * 29
     bp = r["roofline"]["broad_phase"]
