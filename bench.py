@@ -369,13 +369,20 @@ def main():
     else:
         try:   # fused epilogue all-gather over NVLink peer mappings (one kernel + barriers per step)
             from cbfrrt.sharded import FusedSweep
-            sweep = FusedSweep(lambda qb, vp, up, off, mc: ops.valid_control_scatter(qb, *common, vp, up, off, mc), n, B, dev)
+            env_chunks = os.environ.get("CBFRRT_EXCHANGE_CHUNKS")
+            sweep = FusedSweep(lambda qb, vp, up, off, mc: ops.valid_control_scatter(qb, *common, vp, up, off, mc), n, B, dev,
+                               passes=(lambda qb, s_out, d_out: ops.observe_into(qb, b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid, s_out, d_out),
+                                       lambda dx, sv, rows, vp, up, off, mc: ops.cbf_filter_scatter(dx, sv, rows, goal, net, K, lo, hi, w["lam"],
+                                                                                                   w["penalty"], 48, 2, n, vp, up, off, mc)),
+                               chunks=int(env_chunks) if env_chunks else None)
             def step():
                 return sweep(q)
             launches_per_step = 1
             collective = ("fused: kernel epilogue stores (valid u8, u f32xn) into every rank's replica over NVLink ("
                           + ("multimem.st to the NVSwitch multicast address, replicated by the switch" if sweep.multicast else "per-peer stores")
-                          + ", symmetric memory) + barrier")
+                          + ", symmetric memory) + barrier"
+                          + (f"; pipelined in {sweep.chunks} chunks over two streams (stores of chunk k drain under the geometry pass of chunk k+1)"
+                             if sweep.chunks > 1 else ""))
         except Exception as e:   # no P2P / symmetric memory: NCCL all-gather, block-cyclic, overlapped on a 2nd stream
             sys.stderr.write(f"[bench] symmetric memory unavailable ({e!r}); using NCCL all_gather\n")
             n_blocks = 4

@@ -91,6 +91,7 @@ SIGNATURES = {
                                             _P, _P, _P, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "cbfrrt_rollout_segments_host": (C.c_int, [_I, _I, C.POINTER(HostScene), C.c_int32, C.c_int32, _P, _L, _P, _L, _P, _P, _P, _P,
                                                _F, _F, C.POINTER(RolloutParams), C.c_int32, _F, _F, _P, _P, _P, _P]),
+    "cbfrrt_cbf_filter_scatter": (C.c_int, [_I, C.POINTER(CbfNet), _P, _P, _L, C.POINTER(FilterParams), C.POINTER(PeerOut), _P]),
     "cbfrrt_set_workspace": (C.c_int, [_P, _L]),
     "cbfrrt_set_two_pass": (C.c_int, [_I]),
     "cbfrrt_knn_host": (C.c_int, [_I, _I, _P, _P, _L, _L, C.c_int32, _P, _P]),

@@ -450,6 +450,37 @@ def valid_control_scatter(q: Tensor, goal: Tensor, boxes: Tensor, spheres: Tenso
     del keep
 
 
+def observe_into(q: Tensor, boxes: Tensor, spheres: Tensor, floor: int, grid: Tensor, thr_soft: float, thr_hard: float,
+                 robot_id: int, safe_out: Tensor, datax_out: Tensor) -> None:
+    """the geometry pass into caller-owned buffers: q -> safe u8[B], datax f32[B,2n+1] (cbfrrt_collide)"""
+    n = ROBOT_N[robot_id]
+    q, qs = _rows(q, n)
+    B, dev = q.shape[0], q.device
+    if safe_out.numel() < B or datax_out.numel() < B * (2 * n + 1) or safe_out.dtype != torch.uint8 or datax_out.dtype != torch.float32:
+        raise ValueError("observe_into: safe_out u8[>=B], datax_out f32[>=B*(2n+1)]")
+    sc = _scene(boxes, spheres, floor, grid)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_collide(robot_id, C.byref(sc), _ptr(q), qs, B, thr_soft, thr_hard, _ptr(safe_out), None, _ptr(datax_out),
+                                 None, None, None, _stream()), "cbfrrt_collide")
+
+
+def cbf_filter_scatter(datax: Tensor, valid_in: Tensor, rows: int, goal: Tensor, weights: Tensor, K: Tensor, u_lo: Tensor,
+                       u_hi: Tensor, lam: float, penalty: float, hidden: int, layers: int, n: int, valid_ptrs, u_ptrs,
+                       row_offset: int, multicast: bool = False) -> None:
+    """the barrier-network pass with the fused exchange (include/cbfrrt.h cbfrrt_cbf_filter_scatter): the first ``rows`` rows of
+    datax / valid_in -> (valid, u) stored at global row ``row_offset + b`` of every peer buffer"""
+    dev = datax.device
+    net, fp, keep = _net_params(n, weights, K, u_lo, u_hi, goal, rows, lam, penalty, hidden, layers)
+    po = PeerOut()
+    po.n_peers, po.multicast, po.row_offset = len(valid_ptrs), int(bool(multicast)), int(row_offset)
+    for i, (v, u) in enumerate(zip(valid_ptrs, u_ptrs)):
+        po.valid[i], po.u[i] = int(v), int(u)
+    with torch.cuda.device(dev):
+        check(lib.cbfrrt_cbf_filter_scatter(n, C.byref(net), _ptr(datax), _ptr(valid_in), rows, C.byref(fp), C.byref(po), _stream()),
+              "cbfrrt_cbf_filter_scatter")
+    del keep
+
+
 @torch.library.custom_op("cbfrrt::edge_validity", mutates_args=(), device_types="cuda")
 def edge_validity(q_from: Tensor, q_to: Tensor, n_interp: int, boxes: Tensor, spheres: Tensor, floor: int,
                   grid: Tensor, thr_soft: float, thr_hard: float, robot_id: int) -> Tuple[Tensor, Tensor]:

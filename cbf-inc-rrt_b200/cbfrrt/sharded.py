@@ -106,7 +106,17 @@ class FusedSweep:
     every rank before any store of step i+1 is issued.  The multicast form needs rows_per_rank % 128 == 0 (the mask
     bytes of 32 rows travel as packed words); otherwise the per-peer form is used."""
 
-    def __init__(self, launch, n: int, rows_per_rank: int, device, group=None):
+    # the step is exchange-bound when the stores of a step (every rank receives G rows of 4 n + 1 bytes over NVLink,
+    # ~800 GB/s) take longer than the kernel pass that issues them (the barrier-network pass of the two-pass sweep,
+    # ~1.3 ns per local row on B200): 8 GPUs on 2^26 Panda states (2.2 ms of stores behind a 1.4 ms pass)
+    NVLINK_BYTES_PER_S, NETWORK_PASS_S_PER_ROW, MIN_CHUNK_ROWS = 800e9, 1.3e-9, 1 << 20
+
+    def __init__(self, launch, n: int, rows_per_rank: int, device, group=None, passes=None, chunks=None):
+        """passes = (geometry(q_rows, safe_out, datax_out), network(datax, safe, rows, valid_ptrs, u_ptrs, row_offset,
+        multicast)): the two passes of the sweep as separate calls (ops.observe_into / ops.cbf_filter_scatter).  Given
+        them, an exchange-bound step (or chunks > 1) is PIPELINED in chunks over two streams: the geometry pass of chunk
+        k + 1 runs while the NVLink stores issued by the barrier-network pass of chunk k drain (a kernel's CTAs retire
+        long before its posted remote stores are acknowledged; in one stream the next kernel would wait for them)."""
         import torch.distributed._symmetric_memory as symm_mem
         self.launch, self.n, self.B = launch, n, rows_per_rank
         self.group = group if group is not None else dist.group.WORLD
@@ -124,10 +134,37 @@ class FusedSweep:
                           and rows_per_rank % 128 == 0)
         if self.multicast:
             self.valid_ptrs, self.u_ptrs = [mc_v], [mc_u]
+        self.passes, self.chunks = passes, 1
+        if passes is not None:
+            if chunks is None:
+                bound = G * (4 * n + 1) / self.NVLINK_BYTES_PER_S > rows_per_rank * self.NETWORK_PASS_S_PER_ROW
+                chunks = 4 if bound and rows_per_rank >= 4 * self.MIN_CHUNK_ROWS else 1
+            if chunks > 1 and rows_per_rank % (128 * chunks) == 0:
+                self.chunks = int(chunks)
+                bc = rows_per_rank // self.chunks
+                self.side = torch.cuda.Stream(device=device, priority=-1)
+                self.scratch = [(torch.empty(bc, dtype=torch.uint8, device=device),
+                                 torch.empty((bc, 2 * n + 1), dtype=torch.float32, device=device)) for _ in range(3)]
 
     def __call__(self, q_local: torch.Tensor):
         assert q_local.shape[0] == self.B
         self.h_u.barrier(channel=1)     # every rank is done reading the previous step's rows
-        self.launch(q_local, self.valid_ptrs, self.u_ptrs, self.rank * self.B, self.multicast)
+        if self.chunks == 1:
+            self.launch(q_local, self.valid_ptrs, self.u_ptrs, self.rank * self.B, self.multicast)
+        else:
+            geometry, network = self.passes
+            cur, bc, done = torch.cuda.current_stream(), self.B // self.chunks, []
+            for c in range(self.chunks):
+                safe_c, datax_c = self.scratch[c % 3]
+                if c >= 3:
+                    cur.wait_event(done[c - 3])          # the network pass that read this scratch has finished
+                geometry(q_local[c * bc:(c + 1) * bc], safe_c, datax_c)
+                ready = cur.record_event()
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(ready)
+                    network(datax_c, safe_c, bc, self.valid_ptrs, self.u_ptrs, self.rank * self.B + c * bc, self.multicast)
+                    done.append(self.side.record_event())
+            for ev in done[-3:]:
+                cur.wait_event(ev)
         self.h_u.barrier(channel=0)     # all ranks' kernels (and their peer stores) are complete past this point
         return self.valid, self.u

@@ -120,6 +120,41 @@ int cbfrrt_cbf_filter(int n, const cbfrrt_cbf_net* net, const float* datax, int6
     return n == Panda::N ? launch_filter<Panda::N>(na, datax, B, out, st) : launch_filter<Magician::N>(na, datax, B, out, st);
 }
 
+static int peers_from(const cbfrrt_peer_out* peers, int64_t B, PeerOut& po) {
+    if (!peers || peers->n_peers < 1 || peers->n_peers > CBFRRT_MAX_PEERS || peers->row_offset < 0) return CBFRRT_ERR_BAD_SHAPE;
+    po = PeerOut{};
+    po.n = peers->n_peers;
+    po.multicast = peers->multicast ? 1 : 0;
+    po.row_offset = peers->row_offset;
+    // multicast mode packs the mask bytes of 32 consecutive rows into words: whole, aligned 128-row tiles only
+    if (po.multicast && (po.n != 1 || B % 128 != 0 || peers->row_offset % 128 != 0)) return CBFRRT_ERR_BAD_SHAPE;
+    for (int p = 0; p < po.n; ++p) {
+        if (!peers->valid[p] || !peers->u[p]) return CBFRRT_ERR_BAD_SHAPE;
+        if (!aligned16(peers->u[p])) return CBFRRT_ERR_ALIGNMENT;
+        po.valid[p] = peers->valid[p];
+        po.u[p] = peers->u[p];
+    }
+    return CBFRRT_OK;
+}
+
+int cbfrrt_cbf_filter_scatter(int n, const cbfrrt_cbf_net* net, const float* datax, const uint8_t* valid_in, int64_t B,
+                              const cbfrrt_filter_params* fp, const cbfrrt_peer_out* peers, void* stream) {
+    if (B < 0 || !datax || !valid_in) return CBFRRT_ERR_BAD_SHAPE;
+    if (n != Panda::N && n != Magician::N) return CBFRRT_ERR_UNSUPPORTED;
+    PeerOut po;
+    int rc = peers_from(peers, B, po);
+    if (rc) return rc;
+    NetArgs na;
+    rc = check_net(n, net, fp, B, na);
+    if (rc) return rc;
+    if (!net_is_fast(net)) return CBFRRT_ERR_UNSUPPORTED;
+    if (B == 0) return CBFRRT_OK;
+    FilterOutPtrs fo{nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st = (cudaStream_t)stream;
+    return n == Panda::N ? launch_filter_peers<Panda::N>(na, datax, valid_in, B, fo, po, st)
+                         : launch_filter_peers<Magician::N>(na, datax, valid_in, B, fo, po, st);
+}
+
 int cbfrrt_qp(int n, const float* a, const float* c, const float* u_ref, int64_t B, const float* u_lo, const float* u_hi,
               float relaxation_penalty, float* u, float* r, void* stream) {
     if (B < 0 || !a || !c || !u_ref || !u_lo || !u_hi || !u) return CBFRRT_ERR_BAD_SHAPE;

@@ -1705,6 +1705,24 @@ struct Workspace {
 extern Workspace g_workspace[64];
 extern std::atomic<int> g_split;   // 1: two-pass form allowed (default), 0: always the fused kernel (CBFRRT_SPLIT=0, tests)
 
+// the barrier-network pass with the fused exchange: datax -> u, and (u, safe_in) stored into every rank's replica
+template <int N>
+static int launch_filter_peers(const NetArgs& net, const float* dx, const uint8_t* safe_loc, long long B, const FilterOutPtrs& fo,
+                               const PeerOut& po, cudaStream_t st) {
+    const size_t smem = 4 * smem_floats(0, 0, tc::Layout<2, 4>::TOTAL, ParamLayout<N>::TOTAL, 0);
+    int vec = 0;
+    if (po.row_offset % 16 == 0) {
+        bool ok = true;
+        for (int p = 0; p < po.n; ++p) ok = ok && aligned16(po.valid[p]) && aligned16(po.u[p]);
+        if (ok) vec |= VEC_PEER;
+    }
+    auto k = filter_kernel_tc<N, 2, true>;
+    const int grid = grid_for_tc(k, smem, B, 4);
+    if (grid < 0) return CBFRRT_ERR_CUDA;
+    k<<<grid, 4 * tc::M_TILE, smem, st>>>(net, dx, B, fo, po, safe_loc, vec);
+    return finish_launch();
+}
+
 template <class RB>
 static int launch_safety_two_pass(const SceneArgs& sc, const NetArgs& net, const float* q, long long qs, long long B, float ts,
                                   float th, const CollideOutPtrs& co, const FilterOutPtrs& fo, const PeerOut& po, float* dx,
@@ -1716,24 +1734,12 @@ static int launch_safety_two_pass(const SceneArgs& sc, const NetArgs& net, const
     int rc = RB::ID == 0 ? launch_collide_panda(sc, q, qs, B, ts, th, a, st) : launch_collide_magician(sc, q, qs, B, ts, th, a, st);
     if (rc) return rc;
     if (!fo.h && !fo.J && !fo.u && !fo.r && !po.n) return CBFRRT_OK;
+    if (po.n) return launch_filter_peers<N>(net, dx, safe_loc, B, fo, po, st);
     const size_t smem = 4 * smem_floats(0, 0, tc::Layout<2, 4>::TOTAL, ParamLayout<N>::TOTAL, 0);
-    if (po.n) {
-        int vec = 0;
-        if (po.row_offset % 16 == 0) {
-            bool ok = true;
-            for (int p = 0; p < po.n; ++p) ok = ok && aligned16(po.valid[p]) && aligned16(po.u[p]);
-            if (ok) vec |= VEC_PEER;
-        }
-        auto k = filter_kernel_tc<N, 2, true>;
-        const int grid = grid_for_tc(k, smem, B, 4);
-        if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, 4 * tc::M_TILE, smem, st>>>(net, dx, B, fo, po, safe_loc, vec);
-    } else {
-        auto k = filter_kernel_tc<N, 2, false>;
-        const int grid = grid_for_tc(k, smem, B, 4);
-        if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, 4 * tc::M_TILE, smem, st>>>(net, dx, B, fo, po, nullptr, 0);
-    }
+    auto k = filter_kernel_tc<N, 2, false>;
+    const int grid = grid_for_tc(k, smem, B, 4);
+    if (grid < 0) return CBFRRT_ERR_CUDA;
+    k<<<grid, 4 * tc::M_TILE, smem, st>>>(net, dx, B, fo, po, nullptr, 0);
     return finish_launch();
 }
 

@@ -256,6 +256,14 @@ int cbfrrt_safety_filter_scatter(int robot, const cbfrrt_scene *scene, const cbf
                                  int64_t q_stride, int64_t B, const cbfrrt_filter_params *fp, float thr_soft,
                                  float thr_hard, const cbfrrt_peer_out *peers, void *stream);
 
+/* The barrier-network pass alone with the fused exchange: datax [B, 2n+1] (e.g. from cbfrrt_collide) -> u, and
+ * (valid_in[b], u[b]) stored at global row row_offset + b of every peer buffer.  With cbfrrt_collide on one stream and this
+ * call on a second (higher-priority) one, a caller can pipeline a sweep in chunks so that the NVLink stores of chunk k
+ * drain under the geometry pass of chunk k + 1 (cbfrrt.sharded.FusedSweep does, where the exchange would otherwise bound
+ * the step: 8 GPUs).  48 x 2 networks only. */
+int cbfrrt_cbf_filter_scatter(int n, const cbfrrt_cbf_net *net, const float *datax, const uint8_t *valid_in, int64_t B,
+                              const cbfrrt_filter_params *fp, const cbfrrt_peer_out *peers, void *stream);
+
 /* ---- K10 edge validity -----------------------------------------------------------------------------------
  * Replaces edge_checking (motion_planning/baseline/tsa.py:272-286) for E edges with a fixed number n_interp
  * of interpolation points: valid <=> safe(q_to) and safe(q_from + k/n_interp (q_to - q_from)), k=0..n_interp-1.

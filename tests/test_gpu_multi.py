@@ -76,6 +76,24 @@ def _worker(rank, world, port, ret):
         dist.barrier()
         del sweep3
     os.environ["CBFRRT_NO_MULTICAST"] = "0"
+    # the same sweep pipelined in chunks over two streams (geometry pass / barrier-network pass with the peer stores)
+    B4 = (1 << 18) + 512
+    q4 = ops.sample_states(world * B4, 8, 0, rid, device=dev)
+    ref_v4, ref_u4 = ops.valid_control(q4, *common)
+    goal_t, K_t, lo_t, hi_t = common[0], common[6], common[7], common[8]
+    passes = (lambda qb, s_out, d_out: ops.observe_into(qb, b8, s4, 1, gr, w["thr_soft"], w["thr_hard"], rid, s_out, d_out),
+              lambda dx, sv, rows, vp, up, off, mc: ops.cbf_filter_scatter(dx, sv, rows, goal_t, net, K_t, lo_t, hi_t, w["lam"], w["penalty"],
+                                                                          48, 2, n, vp, up, off, mc))
+    for chunks in (4, 2):
+        sweep4 = FusedSweep(lambda qb, vp, up, off, mc: ops.valid_control_scatter(qb, *common, vp, up, off, mc), n, B4, dev,
+                            passes=passes, chunks=chunks)
+        assert sweep4.chunks == chunks
+        for _ in range(2):
+            v, u = sweep4(q4[rank * B4:(rank + 1) * B4])
+            torch.cuda.synchronize()
+            ok.append(bool(torch.equal(v, ref_v4) and torch.equal(u, ref_u4)))
+        dist.barrier()
+        del sweep4
     if rank == 0:
         print("fused exchange modes tested (multicast, per-peer):", modes, flush=True)
     # NCCL all-gather, block-cyclic
