@@ -108,8 +108,10 @@ class FusedSweep:
 
     # the step is exchange-bound when the stores of a step (every rank receives G rows of 4 n + 1 bytes over NVLink,
     # ~800 GB/s) take longer than the kernel pass that issues them (the barrier-network pass of the two-pass sweep,
-    # ~1.3 ns per local row on B200): 8 GPUs on 2^26 Panda states (2.2 ms of stores behind a 1.4 ms pass)
-    NVLINK_BYTES_PER_S, NETWORK_PASS_S_PER_ROW, MIN_CHUNK_ROWS = 800e9, 1.3e-9, 1 << 20
+    # 0.17 ns per local row on B200): 8 GPUs on 2^26 Panda states (2.4 ms of stores behind a 1.4 ms pass).  Measured
+    # there (ms per step): one chunk 6.20, 2 / 4 / 8 / 16 chunks 6.01 / 5.81 / 5.58 / 5.16, the single fused kernel
+    # 5.86 (profiles/r2y_scale_n8_*).  Chunks of 2^19 rows keep the tail of each launch small.
+    NVLINK_BYTES_PER_S, NETWORK_PASS_S_PER_ROW, MIN_CHUNK_ROWS, MAX_CHUNKS = 800e9, 0.17e-9, 1 << 19, 16
 
     def __init__(self, launch, n: int, rows_per_rank: int, device, group=None, passes=None, chunks=None):
         """passes = (geometry(q_rows, safe_out, datax_out), network(datax, safe, rows, valid_ptrs, u_ptrs, row_offset,
@@ -138,7 +140,10 @@ class FusedSweep:
         if passes is not None:
             if chunks is None:
                 bound = G * (4 * n + 1) / self.NVLINK_BYTES_PER_S > rows_per_rank * self.NETWORK_PASS_S_PER_ROW
-                chunks = 4 if bound and rows_per_rank >= 4 * self.MIN_CHUNK_ROWS else 1
+                chunks = 1
+                while bound and chunks < self.MAX_CHUNKS and rows_per_rank // (2 * chunks) >= self.MIN_CHUNK_ROWS \
+                        and rows_per_rank % (256 * chunks) == 0:
+                    chunks *= 2
             if chunks > 1 and rows_per_rank % (128 * chunks) == 0:
                 self.chunks = int(chunks)
                 bc = rows_per_rank // self.chunks
