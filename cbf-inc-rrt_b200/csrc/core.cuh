@@ -180,6 +180,8 @@ struct SceneS {
     const uint16_t* grid;   // nearest-candidate grid in global memory (grid.cuh) or nullptr = brute force
     float cull_floor;       // max(thr_soft, thr_hard): pair distances above max(this, running min) cannot matter
     float thr_min;          // min(thr_soft, thr_hard): a pair distance at or below it decides both masks
+    float* scratch = nullptr;   // SCR instantiations of the field path: this thread's column of the CTA's shared-memory
+    int scratch_stride = 0;     // sphere-centre scratch -- component c of sphere i at scratch[(3 i + c) * scratch_stride]
 };
 
 // exact per-pair formulas (oracle: sd_box / sd_sphere / normal_box / normal_sphere)
@@ -369,7 +371,7 @@ struct CollideResult {
     unsigned n_refined, n_pairs;   // broad-phase statistics (field path): spheres swept exactly, pair evaluations
 };
 
-template <class RB, bool WANT_GRAD, bool WANT_SELF>
+template <class RB, bool WANT_GRAD, bool WANT_SELF, bool SCR>
 __device__ __forceinline__ void collide_state_field(const float (&q)[RB::N], const SceneS& sc, float base_min,
                                                     CollideResult<RB>& res);   // distance-bound field path, below
 
@@ -379,13 +381,15 @@ __device__ __forceinline__ void collide_state_field(const float (&q)[RB::N], con
 // scene kernels free of the look-up code and its registers.
 // WANT_SELF = false skips the self-collision predicate (res.self_ok stays true): the unsafe test of the steer loop
 // (tsa.py:251, hard check only) does not read it.
-template <class RB, bool WANT_GRAD, bool WANT_SELFMIN, bool GRID, bool WANT_SELF = true>
+// SCR: the field path keeps the sphere centres of pass A in the CTA's shared memory (sc.scratch) instead of a per-thread
+// local-memory array: kernels that have the room (no network weights) avoid the write-back of that scratch to DRAM.
+template <class RB, bool WANT_GRAD, bool WANT_SELFMIN, bool GRID, bool WANT_SELF = true, bool SCR = false>
 __device__ __forceinline__ void collide_state(const float (&q)[RB::N], const SceneS& sc, float base_min,
                                               CollideResult<RB>& res) {
     constexpr int N = RB::N;
     res.n_refined = 0u; res.n_pairs = 0u;
     if constexpr (GRID && !WANT_SELFMIN) {           // distance-bound field: exact sweeps only where they can matter
-        collide_state_field<RB, WANT_GRAD, WANT_SELF>(q, sc, base_min, res);
+        collide_state_field<RB, WANT_GRAD, WANT_SELF, SCR>(q, sc, base_min, res);
         return;
     }
     float o = CBF_INF, soft = base_min, hard = base_min;
@@ -602,13 +606,17 @@ __device__ __forceinline__ float scene_min_exact(const SceneS& sc, float cx, flo
 // m_i > max(o_floor, thresholds): it can neither win or tie the observation minimum (which is <= o_floor) nor move a
 // mask.  Mask-only callers stop even earlier: min_k hi_k <= min(thr_soft, thr_hard) already proves unsafe and not safe.
 // The merge reproduces the oracle's scan order (sphere-major, floor candidate before the obstacle term, strict '<').
-template <class RB, bool WANT_GRAD, bool WANT_SELF>
+template <class RB, bool WANT_GRAD, bool WANT_SELF, bool SCR>
 __device__ __forceinline__ void collide_state_field(const float (&q)[RB::N], const SceneS& sc, float base_min,
                                                     CollideResult<RB>& res) {
     constexpr int N = RB::N, NS = RB::NSPH;
     constexpr float WIDEN = grid::FIELD_HALF_DIAG + grid::SLACK;
     const float* __restrict__ field = grid::field_of(sc.grid);
-    float Cx[NS], Cy[NS], Cz[NS];            // indexed dynamically in pass B -> local memory (L1 / L2 resident)
+    float Cx[SCR ? 1 : NS], Cy[SCR ? 1 : NS], Cz[SCR ? 1 : NS];   // indexed dynamically in pass B -> local memory, or (SCR) shared
+    float* const scr = sc.scratch;
+    const int sst = sc.scratch_stride;
+    constexpr int SFIRST = RB::sph_begin(0);  // scratch rows start at the first non-base sphere
+
     float fc[NS];                            // field samples (static indices: registers)
     float o_fl = CBF_INF, soft_fl = CBF_INF, hard_fl = CBF_INF;
     int arg_fl = -1;
@@ -645,7 +653,11 @@ __device__ __forceinline__ void collide_state_field(const float (&q)[RB::N], con
                 for (int r = 0; r < 3; ++r)
                     C[r] = fmaf(fr[L].R[3 * r + 2], c2, fmaf(fr[L].R[3 * r + 1], c1, fmaf(fr[L].R[3 * r + 0], c0, fr[L].p[r])));
                 SC[i][0] = C[0]; SC[i][1] = C[1]; SC[i][2] = C[2];
-                Cx[i] = C[0]; Cy[i] = C[1]; Cz[i] = C[2];
+                if constexpr (SCR) {
+                    scr[(3 * (i - SFIRST) + 0) * sst] = C[0]; scr[(3 * (i - SFIRST) + 1) * sst] = C[1]; scr[(3 * (i - SFIRST) + 2) * sst] = C[2];
+                } else {
+                    Cx[i] = C[0]; Cy[i] = C[1]; Cz[i] = C[2];
+                }
                 const int cell = grid::field_index(C[0], C[1], C[2]);
                 fc[i] = __ldg(field + max(cell, 0));
                 if (cell < 0) outside |= 1u << i;
@@ -677,6 +689,10 @@ __device__ __forceinline__ void collide_state_field(const float (&q)[RB::N], con
         }
     });
 
+    auto centre = [&](int i, int c) -> float {       // pass B / arg-min recovery: the centres of pass A
+        if constexpr (SCR) return scr[(3 * (i - SFIRST) + c) * sst];
+        else return c == 0 ? Cx[i] : (c == 1 ? Cy[i] : Cz[i]);
+    };
     // brackets of the obstacle terms and the pruning bound
     constexpr int FIRST = RB::sph_begin(0);          // spheres of the static base link are not part of the sweep
     float best_hi = CBF_INF;
@@ -704,7 +720,7 @@ __device__ __forceinline__ void collide_state_field(const float (&q)[RB::N], con
     while (need) {                                   // ascending sphere order: strict '<' keeps the first minimum
         const int i = __ffs(need) - 1;
         need &= need - 1;
-        const float m = __fsub_rn(scene_min_exact(sc, Cx[i], Cy[i], Cz[i], n_pairs), RB::rad_dyn(i));
+        const float m = __fsub_rn(scene_min_exact(sc, centre(i, 0), centre(i, 1), centre(i, 2), n_pairs), RB::rad_dyn(i));
         if (m < M) { M = m; argM = i; }
     }
     res.n_refined = n_ref; res.n_pairs = n_pairs;
@@ -721,7 +737,7 @@ __device__ __forceinline__ void collide_state_field(const float (&q)[RB::N], con
     for (int k = 0; k < N; ++k) res.dodq[k] = 0.f;
     if constexpr (WANT_GRAD) {
         if (arg_s < 0) return;
-        const float argC[3] = {Cx[arg_s], Cy[arg_s], Cz[arg_s]};
+        const float argC[3] = {centre(arg_s, 0), centre(arg_s, 1), centre(arg_s, 2)};
         const int link = RB::sph_link(arg_s);
         const float r = RB::rad_dyn(arg_s);
         const int off = sc.floor ? 1 : 0;

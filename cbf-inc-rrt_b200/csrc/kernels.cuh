@@ -22,7 +22,7 @@ namespace cbfrrt {
 
 constexpr int NT = 128;
 #ifndef CBF_COLLIDE_MIN_CTAS
-#define CBF_COLLIDE_MIN_CTAS 6   // <= 80 registers: 24 warps per SM.  The field path is bound by the latency of its L2 gathers,
+#define CBF_COLLIDE_MIN_CTAS 5   // <= 96 registers: 20 warps per SM.  The field path is bound by the latency of its L2 gathers,
                                  // not by registers: measured per 2^23 Panda states, 256 boxes (4 / 5 / 6 / 7 / 8 CTAs per SM):
                                  // masks 2.15 / 2.09 / 1.97 / 2.16 / 2.30 ms, masks + datax 3.23 / 3.14 / 3.16 / 3.13 / 3.28 ms,
                                  // 2^22 edges x 33 points 25.3 / 22.4 / 22.3 / 22.7 / 25.2 ms
@@ -208,13 +208,18 @@ __device__ __forceinline__ void write_collide(const CollideOutPtrs& o, long long
     }
 }
 
-template <class RB, bool WANT_GRAD, bool WANT_SELFMIN, bool GRID>
-__global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) collide_kernel(SceneArgs sc, const float* __restrict__ q, long long q_stride,
+// floats of the shared-memory sphere-centre scratch of the SCR instantiations (field path): 3 per non-base sphere and thread
+template <class RB>
+constexpr int scr_floats() { return 3 * (RB::NSPH - RB::sph_begin(0)) * NT; }
+
+template <class RB, bool WANT_GRAD, bool WANT_SELFMIN, bool GRID, bool SCR = false>
+__global__ void __launch_bounds__(NT, SCR ? 4 : CBF_COLLIDE_MIN_CTAS) collide_kernel(SceneArgs sc, const float* __restrict__ q, long long q_stride,
                                                      long long B, float thr_soft, float thr_hard, CollideOutPtrs out) {
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
     stage<RB::N>(s, sc, nullptr, 0);
-    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
+    SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
+    if constexpr (SCR) { sv.scratch = s.scratch + threadIdx.x; sv.scratch_stride = NT; }
     const float base_min = base_min_cta<RB>(s, sv);
     unsigned long long n_states = 0, n_ref = 0, n_pairs = 0;
     for (long long b = (long long)blockIdx.x * NT + threadIdx.x; b < B; b += (long long)gridDim.x * NT) {
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) collide_kernel(Scene
 #pragma unroll
         for (int k = 0; k < RB::N; ++k) qq[k] = __ldg(q + b * q_stride + k);
         CollideResult<RB> r;
-        collide_state<RB, WANT_GRAD, WANT_SELFMIN, GRID>(qq, sv, base_min, r);
+        collide_state<RB, WANT_GRAD, WANT_SELFMIN, GRID, true, SCR>(qq, sv, base_min, r);
         write_collide<RB>(out, b, qq, r, thr_soft, thr_hard);
         n_states += 1; n_ref += r.n_refined; n_pairs += r.n_pairs;
     }
@@ -1051,8 +1056,8 @@ __global__ void edge_var_finish(int* __restrict__ first_bad, uint8_t* __restrict
         if (bad == EDGE_SENTINEL) first_bad[e] = -1;
     }
 }
-template <class RB, bool GRID>
-__global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_var_kernel(SceneArgs sc, const float* __restrict__ q_from,
+template <class RB, bool GRID, bool SCR = false>
+__global__ void __launch_bounds__(NT, SCR ? 4 : CBF_COLLIDE_MIN_CTAS) edge_var_kernel(SceneArgs sc, const float* __restrict__ q_from,
                                                       const float* __restrict__ q_to, long long E,
                                                       const long long* __restrict__ off, int K_all, long long P,
                                                       float thr_soft, float thr_hard, int* __restrict__ first_bad) {
@@ -1060,7 +1065,8 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_var_kernel(Scen
     extern __shared__ __align__(16) float smem_raw[];
     const Smem s = carve(smem_raw, sc.n_boxes, sc.n_spheres, 0, 0);
     stage<N>(s, sc, nullptr, 0);
-    const SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
+    SceneS sv = scene_view(s, sc, thr_soft, thr_hard);
+    if constexpr (SCR) { sv.scratch = s.scratch + threadIdx.x; sv.scratch_stride = NT; }
     const float base_min = base_min_cta<RB>(s, sv);
     for (long long p = (long long)blockIdx.x * NT + threadIdx.x; p < P; p += (long long)gridDim.x * NT) {
         long long e;
@@ -1093,7 +1099,7 @@ __global__ void __launch_bounds__(NT, CBF_COLLIDE_MIN_CTAS) edge_var_kernel(Scen
             }
         }
         CollideResult<RB> r;
-        collide_state<RB, false, false, GRID>(c, sv, base_min, r);
+        collide_state<RB, false, false, GRID, true, SCR>(c, sv, base_min, r);
         const bool unsafe = r.hard_min <= thr_hard;
         const bool safe = r.self_ok && (r.soft_min > thr_soft) && !unsafe;
         if (!safe) atomicMin(first_bad + e, k);
@@ -1620,9 +1626,25 @@ static int launch_collide(const SceneArgs& sc_in, const float* q, long long qs, 
         k<<<grid, NT, smem, st>>>(sc, q, qs, B, ts, th, out);                      \
     }
     const bool ug = sc.grid != nullptr;
+    // Field path with the sphere-centre scratch in shared memory instead of local memory (CBFRRT_SMEM_SCRATCH=1; four CTAs
+    // per SM must still fit).  Measured per 2^23 Panda states, 256 boxes (profiles/r3a_* vs r3b_*): DRAM traffic 108 instead
+    // of 478 B per state (89 compulsory: the rest of the default's traffic is write-back of that scratch and of register
+    // spills at 96 registers) but 3.44 instead of 3.19 ms -- five CTAs of latency hiding beat the cleaner memory picture
+    // while DRAM runs at a fifth of its bandwidth, so the local-memory form stays the default.
+    static const bool smem_scratch = [] { const char* e = getenv("CBFRRT_SMEM_SCRATCH"); return e && e[0] == '1'; }();
+    const size_t smem_scr = smem + 4 * (size_t)scr_floats<RB>();
+    const bool scr_ok = smem_scratch && ug && !out.mins && B > SMALL_BATCH && smem_scr + 1024 <= (227 * 1024) / 4;
+#define CBF_LAUNCH_COLLIDE_SCR(G_)                                                 \
+    {                                                                              \
+        auto k = collide_kernel<RB, G_, false, true, true>;                        \
+        if ((grid = grid_for(k, smem_scr, tiles)) < 0) return CBFRRT_ERR_CUDA;     \
+        k<<<grid, NT, smem_scr, st>>>(sc, q, qs, B, ts, th, out);                  \
+    }
     if (out.mins) { if (ug) CBF_LAUNCH_COLLIDE(true, true, true) else CBF_LAUNCH_COLLIDE(true, true, false) }
+    else if (scr_ok) { if (grad) CBF_LAUNCH_COLLIDE_SCR(true) else CBF_LAUNCH_COLLIDE_SCR(false) }
     else if (grad) { if (ug) CBF_LAUNCH_COLLIDE(true, false, true) else CBF_LAUNCH_COLLIDE(true, false, false) }
     else { if (ug) CBF_LAUNCH_COLLIDE(false, false, true) else CBF_LAUNCH_COLLIDE(false, false, false) }
+#undef CBF_LAUNCH_COLLIDE_SCR
 #undef CBF_LAUNCH_COLLIDE
     return finish_launch();
 }
@@ -1831,10 +1853,14 @@ static int launch_edges_var(const SceneArgs& sc_in, const float* qf, const float
         k<<<grid, wp::WNT, smem, st>>>(sc, qf, qt, E, off, K_all, P, ts, th, first_bad);
         if (finish_launch()) return CBFRRT_ERR_CUDA;
     } else if (P > 0) {
-        auto k = sc.grid ? edge_var_kernel<RB, true> : edge_var_kernel<RB, false>;
-        const int grid = grid_for(k, smem, (P + NT - 1) / NT);
+        const size_t smem_scr = smem + 4 * (size_t)scr_floats<RB>();
+        static const bool smem_scratch = [] { const char* e = getenv("CBFRRT_SMEM_SCRATCH"); return e && e[0] == '1'; }();
+        const bool scr_ok = smem_scratch && sc.grid && P > SMALL_BATCH && smem_scr + 1024 <= (227 * 1024) / 4;
+        auto k = scr_ok ? edge_var_kernel<RB, true, true> : (sc.grid ? edge_var_kernel<RB, true> : edge_var_kernel<RB, false>);
+        const size_t smem_k = scr_ok ? smem_scr : smem;
+        const int grid = grid_for(k, smem_k, (P + NT - 1) / NT);
         if (grid < 0) return CBFRRT_ERR_CUDA;
-        k<<<grid, NT, smem, st>>>(sc, qf, qt, E, off, K_all, P, ts, th, first_bad);
+        k<<<grid, NT, smem_k, st>>>(sc, qf, qt, E, off, K_all, P, ts, th, first_bad);
         if (finish_launch()) return CBFRRT_ERR_CUDA;
     }
     edge_var_finish<0><<<eg, 256, 0, st>>>(first_bad, valid, E);
