@@ -113,6 +113,17 @@ class FusedSweep:
     # 5.86 (profiles/r2y_scale_n8_*).  Chunks of 2^19 rows keep the tail of each launch small.
     NVLINK_BYTES_PER_S, NETWORK_PASS_S_PER_ROW, MIN_CHUNK_ROWS, MAX_CHUNKS = 800e9, 0.17e-9, 1 << 19, 16
 
+    @classmethod
+    def choose_chunks(cls, n: int, rows_per_rank: int, world: int) -> int:
+        """1 unless the step is exchange-bound; then the largest power of two <= MAX_CHUNKS whose chunks keep MIN_CHUNK_ROWS
+        rows and whole 128-row tiles"""
+        bound = world * rows_per_rank * (4 * n + 1) / cls.NVLINK_BYTES_PER_S > rows_per_rank * cls.NETWORK_PASS_S_PER_ROW
+        chunks = 1
+        while bound and chunks < cls.MAX_CHUNKS and rows_per_rank // (2 * chunks) >= cls.MIN_CHUNK_ROWS \
+                and rows_per_rank % (256 * chunks) == 0:
+            chunks *= 2
+        return chunks
+
     def __init__(self, launch, n: int, rows_per_rank: int, device, group=None, passes=None, chunks=None):
         """passes = (geometry(q_rows, safe_out, datax_out), network(datax, safe, rows, valid_ptrs, u_ptrs, row_offset,
         multicast)): the two passes of the sweep as separate calls (ops.observe_into / ops.cbf_filter_scatter).  Given
@@ -139,11 +150,7 @@ class FusedSweep:
         self.passes, self.chunks = passes, 1
         if passes is not None:
             if chunks is None:
-                bound = G * (4 * n + 1) / self.NVLINK_BYTES_PER_S > rows_per_rank * self.NETWORK_PASS_S_PER_ROW
-                chunks = 1
-                while bound and chunks < self.MAX_CHUNKS and rows_per_rank // (2 * chunks) >= self.MIN_CHUNK_ROWS \
-                        and rows_per_rank % (256 * chunks) == 0:
-                    chunks *= 2
+                chunks = self.choose_chunks(n, rows_per_rank, self.world)
             if chunks > 1 and rows_per_rank % (128 * chunks) == 0:
                 self.chunks = int(chunks)
                 bc = rows_per_rank // self.chunks

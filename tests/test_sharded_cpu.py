@@ -63,3 +63,18 @@ def test_layout_helpers():
     rows = torch.cat([local_global_rows(r, 4, 64, rounds) for r in range(4)])
     assert torch.equal(rows.sort().values, torch.arange(G))
     assert local_global_rows(1, 4, 64, rounds)[:2].tolist() == [64, 65] and local_global_rows(1, 4, 64, rounds)[64].item() == 320
+
+
+def test_fused_sweep_chunk_policy():
+    """FusedSweep pipelines a step only where the exchange bounds it (every rank receives all G rows of 4 n + 1 bytes per
+    step, whatever the number of GPUs): BASELINE config 5 (2^26 Panda states) at 8 GPUs, not at 2 or 4; chunks keep whole
+    128-row tiles and at least 2^19 rows"""
+    from cbfrrt.sharded import FusedSweep
+    G = 1 << 26
+    assert [FusedSweep.choose_chunks(7, G // w, w) for w in (2, 4, 8)] == [1, 1, 16]
+    assert FusedSweep.choose_chunks(4, (1 << 20) // 8, 8) == 1                  # too few rows per rank to cut
+    assert FusedSweep.choose_chunks(7, (1 << 23) + 128, 8) == 1                 # rows per rank not a multiple of 256
+    assert FusedSweep.choose_chunks(7, 3 << 21, 8) == 8                         # 6 291 456 rows: 8 chunks of 786 432
+    for rows, w in ((1 << 23, 8), (3 << 21, 8), (1 << 22, 16)):
+        c = FusedSweep.choose_chunks(7, rows, w)
+        assert rows % (128 * c) == 0 and (c == 1 or rows // c >= FusedSweep.MIN_CHUNK_ROWS)
