@@ -47,6 +47,7 @@ int cbfrrt_get_mlp_path(void) { return g_mlp_path.load(); }
 
 int cbfrrt_set_workspace(void* device_ptr, int64_t bytes) {
     if (bytes < 0 || (bytes > 0 && !device_ptr) || !aligned16(device_ptr)) return CBFRRT_ERR_BAD_SHAPE;
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
     g_workspace[current_device() & 63] = Workspace{bytes > 0 ? device_ptr : nullptr, bytes > 0 ? (long long)bytes : 0};
     return CBFRRT_OK;
 }

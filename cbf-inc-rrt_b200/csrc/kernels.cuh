@@ -1724,7 +1724,11 @@ struct Workspace {
     void* ptr;
     long long bytes;
 };
-extern Workspace g_workspace[64];
+extern Workspace g_workspace[64];   // guarded by g_cfg_mu (set by cbfrrt_set_workspace, read at every large launch)
+inline Workspace workspace_of_current_device() {
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
+    return g_workspace[current_device() & 63];
+}
 extern std::atomic<int> g_split;   // 1: two-pass form allowed (default), 0: always the fused kernel (CBFRRT_SPLIT=0, tests)
 
 // the barrier-network pass with the fused exchange: datax -> u, and (u, safe_in) stored into every rank's replica
@@ -1772,7 +1776,7 @@ static int launch_safety(const SceneArgs& sc_in, const NetArgs& net, const float
         constexpr long long DXB = 4 * (2 * RB::N + 1);
         float* dx = co.datax;
         uint8_t* safe_loc = co.safe;
-        const Workspace ws = g_workspace[current_device() & 63];
+        const Workspace ws = workspace_of_current_device();
         const long long need = (dx ? 0 : ((B * DXB + 15) & ~15LL)) + ((po.n && !safe_loc) ? B : 0);
         if (need > 0 && ws.ptr && ws.bytes >= need) {
             char* w = static_cast<char*>(ws.ptr);

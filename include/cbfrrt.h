@@ -145,7 +145,9 @@ int cbfrrt_get_mlp_path(void);
  * fused kernel, whose geometry runs at the occupancy the tensor-core stage dictates; results are bit-identical.  Room =
  * the caller's datax output when it is requested, else a scratch of at least 16 + (4 (2 n + 1) + 1) B bytes registered
  * here for the CURRENT device (the library never allocates device memory in the device-pointer entry points; the buffer
- * must stay valid, and not be used by the caller, while such calls are in flight).  bytes = 0 unregisters.  Without room
+ * must stay valid, and not be used by the caller, while such calls are in flight; calls that use it must be ordered on
+ * ONE stream -- concurrent streams need their own buffers, registered before each launch: the pointer is read at launch
+ * time).  bytes = 0 unregisters.  Without room
  * the fused kernel runs.  cbfrrt_set_two_pass(0) forces the fused kernel (A/B measurements, tests). */
 int cbfrrt_set_workspace(void *device_ptr, int64_t bytes);
 int cbfrrt_set_two_pass(int enabled);
