@@ -52,7 +52,7 @@ def _f32c(t: Tensor) -> Tensor:
 
 # scratch of the two-pass sweeps (include/cbfrrt.h cbfrrt_set_workspace): one tensor per device, grown on demand.  The
 # library never allocates device memory itself; this layer owns the buffer and registers it.
-SPLIT_MIN_ROWS = 1 << 18
+SPLIT_MIN_ROWS = 1 << 19
 _WORKSPACE = {}
 
 
@@ -75,7 +75,7 @@ def _ensure_workspace(dev: torch.device, rows: int, n: int, hidden: int, layers:
 
 def set_two_pass(enabled: bool) -> None:
     """False: large sweeps always run the single fused kernel (A/B measurements, tests); True (default): the two-pass form
-    from 262 144 rows on (include/cbfrrt.h cbfrrt_set_two_pass)"""
+    from 524 288 rows on (include/cbfrrt.h cbfrrt_set_two_pass)"""
     check(lib.cbfrrt_set_two_pass(int(bool(enabled))), "cbfrrt_set_two_pass")
 
 

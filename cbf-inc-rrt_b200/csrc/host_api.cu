@@ -249,7 +249,7 @@ extern "C" int cbfrrt_safety_filter_host(int device, int robot, const cbfrrt_hos
             fp.goal_rows = rows;
         }
         rc = cbfrrt_safety_filter(robot, &dsc, &net, l.q, n, rows, &fp, thr_soft, thr_hard, safe ? l.safe : nullptr,
-                                  unsafe ? l.unsafe : nullptr, (datax || hidden != 48 || layers != 2 || rows >= (1 << 18)) ? l.datax : nullptr, h ? l.h : nullptr,
+                                  unsafe ? l.unsafe : nullptr, (datax || hidden != 48 || layers != 2 || rows >= (1 << 19)) ? l.datax : nullptr, h ? l.h : nullptr,
                                   J ? l.J : nullptr, u ? l.u : nullptr, r ? l.r : nullptr, l.st);
         if (rc) return fail(rc);
         if (safe) CKL(cudaMemcpyAsync(safe + off, l.safe, rows, cudaMemcpyDeviceToHost, l.st));

@@ -1719,7 +1719,7 @@ CBF_DECLARE_ROBOT(magician)
 // 120 B per state more (profiles/r2w_split_pipeline_probe.json; the outputs are bit-identical: same device functions).
 // It needs somewhere to put datax (60 B per row; + 1 B per row for the mask in the multi-GPU exchange): the caller's
 // datax output when requested, else the scratch registered with cbfrrt_set_workspace for this device.
-constexpr long long SPLIT_MIN_ROWS = 1 << 18;
+constexpr long long SPLIT_MIN_ROWS = 1 << 19;   // per-call times, Panda 256 boxes: 2^18 rows 0.183 (two-pass) vs 0.177 ms (fused), 2^19 rows 0.323 vs 0.353 ms
 struct Workspace {
     void* ptr;
     long long bytes;

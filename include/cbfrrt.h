@@ -139,7 +139,7 @@ int cbfrrt_set_mlp_path(int path);
 int cbfrrt_get_mlp_path(void);
 
 /* ---- optional scratch for the large sweeps --------------------------------------------------------------------
- * From 262 144 rows on, cbfrrt_safety_filter / cbfrrt_safety_filter_scatter run as TWO launches when they have room for
+ * From 524 288 rows on, cbfrrt_safety_filter / cbfrrt_safety_filter_scatter run as TWO launches when they have room for
  * the intermediate observation rows: a geometry pass at its own occupancy (masks + datax) and a tensor-core barrier-network
  * pass through datax (h, J, u, r and the peer stores of the fused exchange) -- measured 1.2x faster on B200 than the single
  * fused kernel, whose geometry runs at the occupancy the tensor-core stage dictates; results are bit-identical.  Room =

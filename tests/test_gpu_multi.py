@@ -60,8 +60,8 @@ def _worker(rank, world, port, ret):
     torch.cuda.synchronize()
     ok.append(bool(torch.equal(v, ref_v2) and torch.equal(u, ref_u2)))
     dist.barrier()
-    # >= 2^18 rows per rank: the two-pass sweep, the peer stores (multicast, then per-peer) issued by its second pass
-    B3 = (1 << 18) + 128
+    # >= 2^19 rows per rank: the two-pass sweep, the peer stores (multicast, then per-peer) issued by its second pass
+    B3 = (1 << 19) + 128
     q3 = ops.sample_states(world * B3, 7, 0, rid, device=dev)
     ops.set_two_pass(False)
     ref_v3, ref_u3 = ops.valid_control(q3, *common)                   # single fused kernel

@@ -356,13 +356,13 @@ def test_rollout_segments_matches_oracle(coracle, robot, T):
 
 @pytest.mark.parametrize("case", ["panda-256box-grid", "magician-16box", "panda-8box"])
 def test_two_pass_sweep_equals_fused_kernel_and_oracle(coracle, case):
-    """From 2^18 rows on the sweep runs as a geometry pass + a tensor-core barrier-network pass through datax (the caller's
+    """From 2^19 rows on the sweep runs as a geometry pass + a tensor-core barrier-network pass through datax (the caller's
     datax output, or the registered scratch): every output bit-identical to the single fused kernel, the fused exchange
     (peer stores from the second pass) included, and equal to the oracle on the first and last rows"""
     from cbfrrt import ops, workloads as W
     robot, boxes, sph = _cases()[case]
     w = _workload(robot)
-    n, rid, B = w["n"], ops.ROBOT_ID[robot], (1 << 18) + 77
+    n, rid, B = w["n"], ops.ROBOT_ID[robot], (1 << 19) + 77
     q = ops.sample_states(B, 5, 0, rid, device=DEV)
     goal = _t(W.sample_states(robot, B, 24))
     b8, s4, gr = _scene(boxes, sph)
