@@ -556,6 +556,14 @@ def main():
                         "scene --, self pairs, gradient, QP) / kernel time against the measured FMA rate; tensor = executed "
                         "tcgen05 flops against a measured dense TF32 matmul; hbm = compulsory bytes against the measured "
                         "copy bandwidth.  frac = the largest.  SURVEY 8d's brute-force pair formula is kept beside it."}
+    brute = cost["fp32_brute_force"]
+    roofline["survey_8d_formula"] = {
+        "fp32_flops_per_state": brute, "achieved": brute * rows_per_launch / step_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": brute * rows_per_launch / step_s / 1e12 / fp32_peak,
+        "note": "SURVEY 8d's per-unit figure (every link sphere against every obstacle) x the units of one step / the step time: "
+                "above 1 because the exact broad phase evaluates "
+                f"{stats['pairs_per_state']:.1f} of the {W.ROBOT_MODELS[robot]['n_spheres'] if 'n_spheres' in W.ROBOT_MODELS[robot] else len(W.ROBOT_MODELS[robot]['spheres'])} x "
+                f"{int(w['boxes'].shape[0] + w['spheres'].shape[0])} pairs the formula counts; the fractions above use the work actually left"}
     if passes is not None:
         roofline["passes"] = passes
         roofline["step_ms"] = step_s * 1e3
